@@ -1,0 +1,1342 @@
+// neus_oracle.cpp -- CPU restatement of the zbqq/neus2 NeuS hot path.
+//
+// TEST INFRASTRUCTURE ONLY.  This file is the parity oracle for the CUDA
+// product in neus2_b200/csrc.  Only tests/, __graft_entry__.smoke() and
+// bench.py's cpu_baseline / --impl reference legs may load it.  The product
+// never links, imports or falls back to anything in oracle/.
+//
+// Every function cites the reference lines it restates (paths relative to
+// /root/reference; "tcnn" = dependencies/my_tcnn).  Nothing here is copied:
+// the reference is CUDA + Eigen, this is scalar C++ over flat arrays.
+//
+// Pinning status (see DESIGN.md "Oracle"):
+//   * hash grid / fused MLP / Adam+EMA arithmetic: pinned against the
+//     reference's own kernels (oracle/_ref/libtcnn_ref.so, built from the
+//     sources in place by oracle/Makefile.ref) by tests/test_ref_kernels.py
+//     on the GPU box.
+//   * ngp layer (sample generation, loss, occupancy grid): PARITY UNPINNED by
+//     any reference artefact -- the ngp sources do not compile here (Eigen/Core
+//     is missing from the snapshot) and the reference ships no golden vectors.
+//     The restatement below follows the cited lines operation by operation.
+//
+// Floating-point conventions (stated once, used by oracle AND product):
+//   * compiled with -ffp-contract=off; a fused multiply-add appears exactly
+//     where fmaf() is written.
+//   * "half" values are IEEE binary16, round-to-nearest-even from float.
+//   * MLP dot products accumulate in fp32 and round to half once per output
+//     element (the reference accumulates in fp16 inside HMMA, whose internal
+//     order is not architecturally defined; tests against the reference
+//     kernels use the 1e-3 relative tolerance BASELINE.json states).
+//   * Grid/weight gradients accumulate in fp32 (reference: fp16 atomics whose
+//     order is nondeterministic run to run).
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <cstdio>
+#include <vector>
+#include <algorithm>
+#include <random>
+
+typedef uint16_t h16;
+
+// ----------------------------------------------------------------------------
+// binary16 <-> float (round to nearest even), via the compiler's _Float16.
+// ----------------------------------------------------------------------------
+static inline float h2f(h16 h) { _Float16 v; std::memcpy(&v, &h, 2); return (float)v; }
+static inline h16 f2h(float f) { _Float16 v = (_Float16)f; h16 h; std::memcpy(&h, &v, 2); return h; }
+static inline float rh(float f) { return h2f(f2h(f)); }  // round float to half precision
+
+// ----------------------------------------------------------------------------
+// PCG32 (tcnn/dependencies/pcg32/pcg32.h:44-170).  The published PCG32 XSH-RR
+// generator with an O(log n) jump-ahead.
+// ----------------------------------------------------------------------------
+struct Pcg32 {
+	uint64_t state, inc;
+	static constexpr uint64_t MULT = 0x5851f42d4c957f2dULL;
+	Pcg32() : state(0x853c49e6748fea9bULL), inc(0xda3e39cb94b95bdbULL) {}
+	explicit Pcg32(uint64_t initstate, uint64_t initseq = 1u) {  // pcg32.h:55-62
+		state = 0u; inc = (initseq << 1u) | 1u;
+		next_uint(); state += initstate; next_uint();
+	}
+	uint32_t next_uint() {  // pcg32.h:65-71
+		uint64_t old = state;
+		state = old * MULT + inc;
+		uint32_t xorshifted = (uint32_t)(((old >> 18u) ^ old) >> 27u);
+		uint32_t rot = (uint32_t)(old >> 59u);
+		return (xorshifted >> rot) | (xorshifted << ((~rot + 1u) & 31));
+	}
+	float next_float() {  // pcg32.h:107-116
+		uint32_t u = (next_uint() >> 9) | 0x3f800000u;
+		float f; std::memcpy(&f, &u, 4);
+		return f - 1.0f;
+	}
+	void advance(int64_t delta_ = (1ll << 32)) {  // pcg32.h:149-170
+		uint64_t cur_mult = MULT, cur_plus = inc, acc_mult = 1u, acc_plus = 0u;
+		uint64_t delta = (uint64_t)delta_;
+		while (delta > 0) {
+			if (delta & 1) { acc_mult *= cur_mult; acc_plus = acc_plus * cur_mult + cur_plus; }
+			cur_plus = (cur_mult + 1) * cur_plus;
+			cur_mult *= cur_mult;
+			delta /= 2;
+		}
+		state = acc_mult * state + acc_plus;
+	}
+};
+
+extern "C" {
+
+// rng state is passed across the ABI as two uint64 {state, inc}.
+void orc_pcg32_seed(uint64_t seed, uint64_t* st) { Pcg32 r(seed); st[0] = r.state; st[1] = r.inc; }
+uint32_t orc_pcg32_next_uint(uint64_t* st) { Pcg32 r; r.state = st[0]; r.inc = st[1]; uint32_t v = r.next_uint(); st[0] = r.state; return v; }
+float orc_pcg32_next_float(uint64_t* st) { Pcg32 r; r.state = st[0]; r.inc = st[1]; float v = r.next_float(); st[0] = r.state; return v; }
+void orc_pcg32_advance(uint64_t* st, int64_t delta) { Pcg32 r; r.state = st[0]; r.inc = st[1]; r.advance(delta); st[0] = r.state; }
+
+// Trainer seed derivation (tcnn trainer.h:56-59): std::seed_seq{seed}, first of two words.
+uint32_t orc_trainer_seed_word(uint32_t seed) {
+	std::seed_seq seq{seed};
+	std::vector<uint32_t> seeds(2);
+	seq.generate(seeds.begin(), seeds.end());
+	return seeds.front();
+}
+
+// generate_random_uniform (tcnn random.h:67-99): thread i jumps i*4 draws and
+// writes out[i + n_threads*j]; the host rng then advances by n.
+void orc_generate_random_uniform(uint64_t* st, uint64_t n, float* out, float lower, float upper) {
+	Pcg32 base; base.state = st[0]; base.inc = st[1];
+	const uint64_t n_threads_needed = (n + 3) / 4;
+	const uint64_t n_blocks = (n_threads_needed + 127) / 128;
+	const uint64_t n_threads = n_blocks * 128;
+	for (uint64_t i = 0; i < n_threads; ++i) {
+		Pcg32 r = base; r.advance((int64_t)(i * 4));
+		for (uint64_t j = 0; j < 4; ++j) {
+			uint64_t idx = i + n_threads * j;
+			if (idx >= n) break;
+			float v = r.next_float();
+			out[idx] = v * (upper - lower) + lower;  // lambda in random.h:95 (no contraction possible to differ: see note)
+		}
+	}
+	base.advance((int64_t)n);
+	st[0] = base.state;
+}
+
+// Xavier-uniform init of one weight matrix (tcnn gpu_matrix.h:292-307).
+void orc_xavier_uniform(uint64_t* st, uint32_t fan_out, uint32_t fan_in, float* out) {
+	Pcg32 r; r.state = st[0]; r.inc = st[1];
+	float scale = 1.0f;
+	scale *= std::sqrt(6.0f / (float)(fan_in + fan_out));
+	for (uint32_t i = 0; i < fan_out * fan_in; ++i) out[i] = r.next_float() * 2.0f * scale - scale;
+	st[0] = r.state;
+}
+
+// ----------------------------------------------------------------------------
+// Hash grid (tcnn encodings/grid.h).
+// ----------------------------------------------------------------------------
+
+// per_level_scale (src/testbed.cu:2175-2185): exp(log(top*aabb/base)/(L-1)) in float.
+float orc_per_level_scale(float desired_resolution, int aabb_scale, uint32_t base_resolution, uint32_t n_levels) {
+	return std::exp(std::log(desired_resolution * (float)aabb_scale / (float)base_resolution) / (n_levels - 1));
+}
+
+// Level tables (grid.h:1472-1508): scale is the INTEGER resolution-1.
+void orc_grid_tables(uint32_t n_levels, uint32_t base_resolution, float per_level_scale, uint32_t log2_hashmap_size,
+                     uint32_t* offsets, uint32_t* resolutions, float* scales) {
+	uint32_t offset = 0;
+	for (uint32_t i = 0; i < n_levels; ++i) {
+		const float scale = exp2f(i * std::log2(per_level_scale)) * base_resolution - 1.0f;
+		const uint32_t resolution = (uint32_t)(ceilf(scale)) + 1;
+		scales[i] = (float)(resolution - 1);
+		resolutions[i] = resolution;
+		uint32_t max_params = std::numeric_limits<uint32_t>::max() / 2;
+		uint32_t params_in_level = std::pow((float)resolution, 3) > (float)max_params ? max_params : resolution * resolution * resolution;
+		params_in_level = (params_in_level + 7u) / 8u * 8u;
+		params_in_level = std::min(params_in_level, (1u << log2_hashmap_size));
+		offsets[i] = offset;
+		offset += params_in_level;
+	}
+	offsets[n_levels] = offset;
+}
+
+// grid.h:119-153 (fast_hash + grid_index, N_POS_DIMS=3).
+static inline uint32_t grid_index(uint32_t hashmap_size, uint32_t res, const uint32_t p[3]) {
+	uint32_t stride = 1, index = 0;
+	for (uint32_t dim = 0; dim < 3 && stride <= hashmap_size; ++dim) {
+		index += p[dim] * stride;
+		stride *= res;
+	}
+	if (hashmap_size < stride) {
+		index = (p[0] * 1u) ^ (p[1] * 2654435761u) ^ (p[2] * 805459861u);
+	}
+	return (index % hashmap_size) * 2;
+}
+
+// exposed for bit-exact index tests
+uint32_t orc_grid_index(uint32_t hashmap_size, uint32_t res, uint32_t x, uint32_t y, uint32_t z) {
+	uint32_t p[3] = {x, y, z};
+	return grid_index(hashmap_size, res, p);
+}
+
+// pos_fract (tcnn common_device.h:403-434), Linear interpolation: pos = x*scale+0.5 (fused, as nvcc
+// contracts it), floor, fract.  derivative = 1, 2nd derivative = 0.
+static inline void pos_fract(float x, float scale, float* frac, uint32_t* cell) {
+	float p = fmaf(x, scale, 0.5f);
+	int tmp = (int)floorf(p);
+	*cell = (uint32_t)tmp;
+	*frac = p - (float)tmp;
+}
+
+void orc_pos_fract(float x, float scale, float* frac, uint32_t* cell) { pos_fract(x, scale, frac, cell); }
+
+// kernel_grid (grid.h:174-369): encoded features (accumulated in HALF in corner order, grid.h:316-318)
+// and dy/dx (fp32, grid.h:329-367).  enc is SoA [2L][n]; dy_dx is [2L][n][3].
+// Levels > valid_level emit zeros (grid.h:198-214).
+void orc_grid_forward(uint32_t n, const float* pos, uint32_t pos_stride, const h16* grid,
+                      uint32_t n_levels, const uint32_t* offsets, const uint32_t* resolutions, const float* scales,
+                      uint32_t valid_level, h16* enc, float* dy_dx) {
+	#pragma omp parallel for schedule(static)
+	for (int64_t ii = 0; ii < (int64_t)n; ++ii) {
+		const uint32_t i = (uint32_t)ii;
+		for (uint32_t level = 0; level < n_levels; ++level) {
+			if (level > valid_level) {
+				for (uint32_t f = 0; f < 2; ++f) {
+					if (enc) enc[(size_t)(level * 2 + f) * n + i] = 0;
+					if (dy_dx) for (int d = 0; d < 3; ++d) dy_dx[((size_t)(level * 2 + f) * n + i) * 3 + d] = 0.f;
+				}
+				continue;
+			}
+			const h16* g = grid + (size_t)offsets[level] * 2;
+			const uint32_t hashmap_size = offsets[level + 1] - offsets[level];
+			const float scale = scales[level];
+			const uint32_t res = resolutions[level];
+			float p[3]; uint32_t pg[3];
+			for (int d = 0; d < 3; ++d) pos_fract(pos[(size_t)i * pos_stride + d], scale, &p[d], &pg[d]);
+
+			if (enc) {
+				float result[2] = {0.f, 0.f};  // held in half precision between adds
+				for (uint32_t idx = 0; idx < 8; ++idx) {
+					float weight = 1;
+					uint32_t pl[3];
+					for (int d = 0; d < 3; ++d) {
+						if ((idx & (1u << d)) == 0) { weight *= 1 - p[d]; pl[d] = pg[d]; }
+						else { weight *= p[d]; pl[d] = pg[d] + 1; }
+					}
+					uint32_t index = grid_index(hashmap_size, res, pl);
+					for (int f = 0; f < 2; ++f) {
+						float data = h2f(g[index + f]);
+						// ((T*)&result)[feature] += (T)(weight * data);   half += half
+						result[f] = rh(result[f] + rh(weight * data));
+					}
+				}
+				for (int f = 0; f < 2; ++f) enc[(size_t)(level * 2 + f) * n + i] = f2h(result[f]);
+			}
+			if (dy_dx) {
+				float grads[2][3] = {{0, 0, 0}, {0, 0, 0}};
+				for (uint32_t gd = 0; gd < 3; ++gd) {
+					for (uint32_t idx = 0; idx < 4; ++idx) {
+						float weight = scale;
+						uint32_t pl[3];
+						for (uint32_t ngd = 0; ngd < 2; ++ngd) {
+							const uint32_t d = ngd >= gd ? (ngd + 1) : ngd;
+							if ((idx & (1u << ngd)) == 0) { weight *= 1 - p[d]; pl[d] = pg[d]; }
+							else { weight *= p[d]; pl[d] = pg[d] + 1; }
+						}
+						pl[gd] = pg[gd];
+						uint32_t il = grid_index(hashmap_size, res, pl);
+						pl[gd] = pg[gd] + 1;
+						uint32_t ir = grid_index(hashmap_size, res, pl);
+						for (int f = 0; f < 2; ++f) {
+							// grads += weight * (right - left) * pos_derivative(=1)   (no contraction)
+							float t = weight * (h2f(g[ir + f]) - h2f(g[il + f]));
+							t = t * 1.0f;
+							grads[f][gd] = grads[f][gd] + t;
+						}
+					}
+				}
+				for (int f = 0; f < 2; ++f) for (int d = 0; d < 3; ++d)
+					dy_dx[((size_t)(level * 2 + f) * n + i) * 3 + d] = grads[f][d];
+			}
+		}
+	}
+}
+
+// kernel_grid_backward (grid.h:371-500): scatter dL/dy into the grid gradient with the trilinear weights.
+// Accumulation in fp32 (see header).  dL_dy is SoA half [2L][n].  Serial over samples (deterministic).
+void orc_grid_backward(uint32_t n, const float* pos, uint32_t pos_stride, const h16* dL_dy,
+                       uint32_t n_levels, const uint32_t* offsets, const uint32_t* resolutions, const float* scales,
+                       uint32_t valid_level, float* grid_grad) {
+	for (uint32_t level = 0; level < n_levels; ++level) {
+		if (level > valid_level) continue;
+		float* gg = grid_grad + (size_t)offsets[level] * 2;
+		const uint32_t hashmap_size = offsets[level + 1] - offsets[level];
+		const float scale = scales[level];
+		const uint32_t res = resolutions[level];
+		for (uint32_t i = 0; i < n; ++i) {
+			float p[3]; uint32_t pg[3];
+			for (int d = 0; d < 3; ++d) pos_fract(pos[(size_t)i * pos_stride + d], scale, &p[d], &pg[d]);
+			float grad[2] = {h2f(dL_dy[(size_t)(level * 2) * n + i]), h2f(dL_dy[(size_t)(level * 2 + 1) * n + i])};
+			for (uint32_t idx = 0; idx < 8; ++idx) {
+				float weight = 1;
+				uint32_t pl[3];
+				for (int d = 0; d < 3; ++d) {
+					if ((idx & (1u << d)) == 0) { weight *= 1 - p[d]; pl[d] = pg[d]; }
+					else { weight *= p[d]; pl[d] = pg[d] + 1; }
+				}
+				uint32_t index = grid_index(hashmap_size, res, pl);
+				gg[index] += grad[0] * weight;
+				gg[index + 1] += grad[1] * weight;
+			}
+		}
+	}
+}
+
+// kernel_grid_backward_input (grid.h:803-830): dL/dx = sum_k dL/dy_k * dy_k/dx, fp32, k ascending.
+// dL_dy SoA half [2L][n]; out [n][3].
+void orc_grid_backward_input(uint32_t n, uint32_t n_features, const h16* dL_dy, const float* dy_dx, float* dL_dx) {
+	#pragma omp parallel for schedule(static)
+	for (int64_t ii = 0; ii < (int64_t)n; ++ii) {
+		const uint32_t i = (uint32_t)ii;
+		float r[3] = {0, 0, 0};
+		for (uint32_t k = 0; k < n_features; ++k) {
+			float dl = h2f(dL_dy[(size_t)k * n + i]);
+			for (int d = 0; d < 3; ++d) r[d] = r[d] + dl * dy_dx[((size_t)k * n + i) * 3 + d];
+		}
+		for (int d = 0; d < 3; ++d) dL_dx[(size_t)i * 3 + d] = r[d];
+	}
+}
+
+// kernel_grid_backward_input_backward_grid (grid.h:880-1007): second-order term, dL/d(dL/dx) -> grid.
+// v = dL_ddLdx [n][3]; dL_dy SoA half [2L][n] (here: d sdf / d enc).
+void orc_grid_bwdbwd_grid(uint32_t n, const float* pos, uint32_t pos_stride, const float* v, const h16* dL_dy,
+                          uint32_t n_levels, const uint32_t* offsets, const uint32_t* resolutions, const float* scales,
+                          uint32_t valid_level, float* grid_grad) {
+	for (uint32_t level = 0; level < n_levels; ++level) {
+		if (level > valid_level) continue;
+		float* gg = grid_grad + (size_t)offsets[level] * 2;
+		const uint32_t hashmap_size = offsets[level + 1] - offsets[level];
+		const float scale = scales[level];
+		const uint32_t res = resolutions[level];
+		for (uint32_t i = 0; i < n; ++i) {
+			float p[3]; uint32_t pg[3];
+			for (int d = 0; d < 3; ++d) pos_fract(pos[(size_t)i * pos_stride + d], scale, &p[d], &pg[d]);
+			float grad[2] = {h2f(dL_dy[(size_t)(level * 2) * n + i]), h2f(dL_dy[(size_t)(level * 2 + 1) * n + i])};
+			for (uint32_t gd = 0; gd < 3; ++gd) {
+				float grad_in = scale * v[(size_t)i * 3 + gd] * 1.0f;
+				for (uint32_t idx = 0; idx < 4; ++idx) {
+					float weight = grad_in;
+					uint32_t pl[3];
+					for (uint32_t ngd = 0; ngd < 2; ++ngd) {
+						const uint32_t d = ngd >= gd ? (ngd + 1) : ngd;
+						if ((idx & (1u << ngd)) == 0) { weight *= 1 - p[d]; pl[d] = pg[d]; }
+						else { weight *= p[d]; pl[d] = pg[d] + 1; }
+					}
+					pl[gd] = pg[gd];
+					uint32_t il = grid_index(hashmap_size, res, pl);
+					gg[il] += grad[0] * -weight; gg[il + 1] += grad[1] * -weight;
+					pl[gd] = pg[gd] + 1;
+					uint32_t ir = grid_index(hashmap_size, res, pl);
+					gg[ir] += grad[0] * weight; gg[ir + 1] += grad[1] * weight;
+				}
+			}
+		}
+	}
+}
+
+// kernel_grid_backward_input_backward_dLdoutput (grid.h:1183-1207): dL/d(dL/dy)_k = dy_k/dx . v, rounded to half.
+// out is SoA half [2L][n].
+void orc_grid_bwdbwd_dLdoutput(uint32_t n, uint32_t n_features, const float* v, const float* dy_dx, h16* out) {
+	#pragma omp parallel for schedule(static)
+	for (int64_t ii = 0; ii < (int64_t)n; ++ii) {
+		const uint32_t i = (uint32_t)ii;
+		for (uint32_t k = 0; k < n_features; ++k) {
+			float result = 0;
+			for (int d = 0; d < 3; ++d) result = result + dy_dx[((size_t)k * n + i) * 3 + d] * v[(size_t)i * 3 + d];
+			out[(size_t)k * n + i] = f2h(result);
+		}
+	}
+}
+
+// ----------------------------------------------------------------------------
+// Fully fused MLP (tcnn src/fully_fused_mlp.cu): bias-free, ReLU hidden, no output activation,
+// weights row-major [out][in] per layer, layers contiguous (fully_fused_mlp.cu:1209-1219).
+// Activations here are AoS [n][width] half.
+// ----------------------------------------------------------------------------
+static void mlp_layer(uint32_t n, uint32_t in_w, uint32_t out_w, const h16* W, const h16* in, h16* out, bool relu) {
+	std::vector<float> Wf((size_t)out_w * in_w);
+	for (size_t i = 0; i < Wf.size(); ++i) Wf[i] = h2f(W[i]);
+	#pragma omp parallel for schedule(static)
+	for (int64_t i = 0; i < (int64_t)n; ++i) {
+		float x[64];
+		for (uint32_t k = 0; k < in_w; ++k) x[k] = h2f(in[(size_t)i * in_w + k]);
+		for (uint32_t o = 0; o < out_w; ++o) {
+			float acc = 0.f;
+			const float* w = &Wf[(size_t)o * in_w];
+			for (uint32_t k = 0; k < in_w; ++k) acc = fmaf(x[k], w[k], acc);
+			if (relu && !(acc > 0.f)) acc = 0.f;
+			out[(size_t)i * out_w + o] = f2h(acc);
+		}
+	}
+}
+
+// forward (fully_fused_mlp.cu:679-812, 939-965).  hidden: [n_hidden][n][64] post-activation.
+void orc_mlp_forward(uint32_t n, uint32_t in_w, uint32_t n_hidden, uint32_t out_w, const h16* weights,
+                     const h16* in, h16* hidden, h16* out) {
+	const uint32_t W = 64;
+	const h16* w = weights;
+	mlp_layer(n, in_w, W, w, in, hidden, true);
+	w += (size_t)W * in_w;
+	for (uint32_t l = 1; l < n_hidden; ++l) {
+		mlp_layer(n, W, W, w, hidden + (size_t)(l - 1) * n * W, hidden + (size_t)l * n * W, true);
+		w += (size_t)W * W;
+	}
+	mlp_layer(n, W, out_w, w, hidden + (size_t)(n_hidden - 1) * n * W, out, false);
+}
+
+// y[n][out_w] = mask(relu_ref) * (W^T x): W is [rows=in_w_of_x][out_w] row-major i.e. we compute
+// y[o] = sum_r W[r][o] * x[r].  Used for all backward sweeps.
+static void mlp_layer_T(uint32_t n, uint32_t rows, uint32_t cols, const h16* W, const h16* x, h16* y, const h16* relu_ref) {
+	std::vector<float> Wf((size_t)rows * cols);
+	for (size_t i = 0; i < Wf.size(); ++i) Wf[i] = h2f(W[i]);
+	#pragma omp parallel for schedule(static)
+	for (int64_t i = 0; i < (int64_t)n; ++i) {
+		float acc[64];
+		for (uint32_t c = 0; c < cols; ++c) acc[c] = 0.f;
+		for (uint32_t r = 0; r < rows; ++r) {
+			float xr = h2f(x[(size_t)i * rows + r]);
+			const float* w = &Wf[(size_t)r * cols];
+			for (uint32_t c = 0; c < cols; ++c) acc[c] = fmaf(xr, w[c], acc[c]);
+		}
+		for (uint32_t c = 0; c < cols; ++c) {
+			float a = acc[c];
+			if (relu_ref && !(h2f(relu_ref[(size_t)i * cols + c]) > 0.f)) a = 0.f;
+			y[(size_t)i * cols + c] = f2h(a);
+		}
+	}
+}
+
+// wgrad[o][k] += sum_i dy[i][o] * x[i][k]   (fp32, sample order ascending)
+static void mlp_wgrad(uint32_t n, uint32_t out_w, uint32_t in_w, const h16* dy, const h16* x, float* wgrad) {
+	std::vector<double> dummy;
+	#pragma omp parallel for schedule(static)
+	for (int64_t o = 0; o < (int64_t)out_w; ++o) {
+		for (uint32_t k = 0; k < in_w; ++k) {
+			float acc = 0.f;
+			for (uint32_t i = 0; i < n; ++i) acc = fmaf(h2f(dy[(size_t)i * out_w + o]), h2f(x[(size_t)i * in_w + k]), acc);
+			wgrad[(size_t)o * in_w + k] += acc;
+		}
+	}
+}
+
+// backward (fully_fused_mlp.cu:968-1085, kernel :151-260).  dL_din (half, [n][in_w]) and/or wgrad (fp32,
+// same layout as weights, ACCUMULATED) may be null.  bwd_tmp: [n_hidden][n][64] scratch, index 0 = last hidden.
+void orc_mlp_backward(uint32_t n, uint32_t in_w, uint32_t n_hidden, uint32_t out_w, const h16* weights,
+                      const h16* in, const h16* hidden, const h16* dL_dout, h16* dL_din, float* wgrad, h16* bwd_tmp) {
+	const uint32_t W = 64;
+	std::vector<const h16*> wl(n_hidden + 1);
+	std::vector<size_t> woff(n_hidden + 1);
+	{
+		size_t off = 0;
+		wl[0] = weights; woff[0] = 0; off = (size_t)W * in_w;
+		for (uint32_t l = 1; l < n_hidden; ++l) { wl[l] = weights + off; woff[l] = off; off += (size_t)W * W; }
+		wl[n_hidden] = weights + off; woff[n_hidden] = off;
+	}
+	std::vector<h16> local;
+	if (!bwd_tmp) { local.resize((size_t)n_hidden * n * W); bwd_tmp = local.data(); }
+	const h16* last_hidden = hidden + (size_t)(n_hidden - 1) * n * W;
+	// output layer: dW_out = dL_dout^T . hidden_last (:1020); tmp0 = relu'(hidden_last) * (W_out^T dL_dout) (:151 kernel)
+	if (wgrad) mlp_wgrad(n, out_w, W, dL_dout, last_hidden, wgrad + woff[n_hidden]);
+	mlp_layer_T(n, out_w, W, wl[n_hidden], dL_dout, bwd_tmp, last_hidden);
+	// hidden layers (:1049-1060)
+	for (uint32_t i = 0; i + 1 < n_hidden; ++i) {
+		uint32_t l = n_hidden - 1 - i;           // weight matrix index (hidden->hidden)
+		const h16* cur = bwd_tmp + (size_t)i * n * W;
+		const h16* act_below = hidden + (size_t)(l - 1) * n * W;
+		if (wgrad) mlp_wgrad(n, W, W, cur, act_below, wgrad + woff[l]);
+		mlp_layer_T(n, W, W, wl[l], cur, bwd_tmp + (size_t)(i + 1) * n * W, act_below);
+	}
+	const h16* first = bwd_tmp + (size_t)(n_hidden - 1) * n * W;
+	if (wgrad) mlp_wgrad(n, W, in_w, first, in, wgrad + woff[0]);          // :1062-1067
+	if (dL_din) mlp_layer_T(n, W, in_w, wl[0], first, dL_din, nullptr);    // :1070-1074
+}
+
+// backward_backward_input (fully_fused_mlp.cu:1089-1198), ReLU => only the mixed second-order term.
+// d_in = dL/d(dL/dinput) [n][in_w]; dL_dout = the first-order seed [n][out_w].  wgrad ACCUMULATED (fp32).
+void orc_mlp_bwdbwd(uint32_t n, uint32_t in_w, uint32_t n_hidden, uint32_t out_w, const h16* weights,
+                    const h16* hidden, const h16* d_in, const h16* dL_dout, float* wgrad) {
+	const uint32_t W = 64;
+	std::vector<const h16*> wl(n_hidden + 1);
+	std::vector<size_t> woff(n_hidden + 1);
+	std::vector<uint32_t> w_in(n_hidden + 1), w_out(n_hidden + 1);
+	{
+		size_t off = 0;
+		wl[0] = weights; woff[0] = 0; w_in[0] = in_w; w_out[0] = W; off = (size_t)W * in_w;
+		for (uint32_t l = 1; l < n_hidden; ++l) { wl[l] = weights + off; woff[l] = off; w_in[l] = W; w_out[l] = W; off += (size_t)W * W; }
+		wl[n_hidden] = weights + off; woff[n_hidden] = off; w_in[n_hidden] = W; w_out[n_hidden] = out_w;
+	}
+	// forward-mode sweep (:1151-1161): front[0] = d_in; front[l+1] = relu'(hidden[l]) * (W_l front[l])
+	std::vector<std::vector<h16>> front(n_hidden + 1);
+	const h16* cur = d_in;
+	for (uint32_t l = 0; l < n_hidden; ++l) {
+		front[l + 1].resize((size_t)n * W);
+		// y = W x with relu mask:  reuse mlp_layer (acc then mask on hidden, not on acc sign)
+		std::vector<float> Wf((size_t)w_out[l] * w_in[l]);
+		for (size_t i = 0; i < Wf.size(); ++i) Wf[i] = h2f(wl[l][i]);
+		const h16* hid = hidden + (size_t)l * n * W;
+		#pragma omp parallel for schedule(static)
+		for (int64_t i = 0; i < (int64_t)n; ++i) {
+			for (uint32_t o = 0; o < W; ++o) {
+				float acc = 0.f;
+				for (uint32_t k = 0; k < w_in[l]; ++k) acc = fmaf(h2f(cur[(size_t)i * w_in[l] + k]), Wf[(size_t)o * w_in[l] + k], acc);
+				if (!(h2f(hid[(size_t)i * W + o]) > 0.f)) acc = 0.f;
+				front[l + 1][(size_t)i * W + o] = f2h(acc);
+			}
+		}
+		cur = front[l + 1].data();
+	}
+	// reverse sweep (:1163-1174): back[n_hidden+1] = dL_dout; back[l] = relu'(hidden[l-1]) * (W_l^T back[l+1])
+	std::vector<std::vector<h16>> back(n_hidden + 2);
+	const h16* bcur = dL_dout;
+	std::vector<const h16*> backp(n_hidden + 2, nullptr);
+	backp[n_hidden + 1] = dL_dout;
+	for (uint32_t l = n_hidden; l >= 1; --l) {
+		back[l].resize((size_t)n * W);
+		mlp_layer_T(n, w_out[l], W, wl[l], bcur, back[l].data(), hidden + (size_t)(l - 1) * n * W);
+		bcur = back[l].data(); backp[l] = bcur;
+	}
+	// weight gradients (:1176-1187): dW_l += back[l+1] . front[l]^T
+	for (uint32_t l = 0; l <= n_hidden; ++l) {
+		const h16* f = (l == 0) ? d_in : front[l].data();
+		mlp_wgrad(n, w_out[l], w_in[l], backp[l + 1], f, wgrad + woff[l]);
+	}
+}
+
+// ----------------------------------------------------------------------------
+// Spherical harmonics degree 4 (tcnn encodings/spherical_harmonics.h:47-100) on the WARPED direction.
+// ----------------------------------------------------------------------------
+static void sh4(const float* dir_warped, h16* out) {
+	float x = fmaf(dir_warped[0], 2.f, -1.f);
+	float y = fmaf(dir_warped[1], 2.f, -1.f);
+	float z = fmaf(dir_warped[2], 2.f, -1.f);
+	float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+	float o[16];
+	o[0] = 0.28209479177387814f;
+	o[1] = -0.48860251190291987f * y;
+	o[2] = 0.48860251190291987f * z;
+	o[3] = -0.48860251190291987f * x;
+	o[4] = 1.0925484305920792f * xy;
+	o[5] = -1.0925484305920792f * yz;
+	o[6] = fmaf(0.94617469575755997f, z2, -0.31539156525251999f);
+	o[7] = -1.0925484305920792f * xz;
+	o[8] = fmaf(0.54627421529603959f, x2, -(0.54627421529603959f * y2));
+	o[9] = 0.59004358992664352f * y * fmaf(-3.0f, x2, y2);
+	o[10] = 2.8906114426405538f * xy * z;
+	o[11] = 0.45704579946446572f * y * fmaf(-5.0f, z2, 1.0f);
+	o[12] = 0.3731763325901154f * z * fmaf(5.0f, z2, -3.0f);
+	o[13] = 0.45704579946446572f * x * fmaf(-5.0f, z2, 1.0f);
+	o[14] = 1.4453057213202769f * z * (x2 - y2);
+	o[15] = 0.59004358992664352f * x * fmaf(3.0f, y2, -x2);
+	for (int i = 0; i < 16; ++i) out[i] = f2h(o[i]);
+}
+void orc_sh4(uint32_t n, const float* dirs_warped, uint32_t stride, h16* out) {
+	for (uint32_t i = 0; i < n; ++i) sh4(dirs_warped + (size_t)i * stride, out + (size_t)i * 16);
+}
+
+// ----------------------------------------------------------------------------
+// NerfNetwork (include/neural-graphics-primitives/nerf_network.h).
+// Parameter buffer order (nerf_network.h:741-785): [sdf-MLP | colour-MLP | grid | (dir-enc: 0) | variance(4)].
+// ----------------------------------------------------------------------------
+struct NetCfg {
+	uint32_t n_levels;
+	uint32_t offsets[33];
+	uint32_t resolutions[32];
+	float scales[32];
+	uint32_t valid_level;
+	uint32_t sdf_hidden_layers;   // 1
+	uint32_t rgb_hidden_layers;   // 2
+	float sdf_bias;               // -0.1 (nerf_network.h:87)
+};
+
+static inline uint32_t n_enc(const NetCfg& c) { return c.n_levels * 2; }
+static inline uint32_t sdf_in_w(const NetCfg& c) { return (3 + n_enc(c) + 15) / 16 * 16; }   // nerf_network.h:60
+static inline uint32_t rgb_in_w(const NetCfg&) { return 48; }                                // nerf_network.h:73: next_multiple(3+3+16+16,16)
+static inline size_t sdf_n_params(const NetCfg& c) { return (size_t)64 * sdf_in_w(c) + (size_t)(c.sdf_hidden_layers - 1) * 64 * 64 + 16 * 64; }
+static inline size_t rgb_n_params(const NetCfg& c) { return (size_t)64 * 48 + (size_t)(c.rgb_hidden_layers - 1) * 64 * 64 + 16 * 64; }
+static inline size_t grid_n_params(const NetCfg& c) { return (size_t)c.offsets[c.n_levels] * 2; }
+
+uint64_t orc_net_n_params(const NetCfg* c) { return sdf_n_params(*c) + rgb_n_params(*c) + grid_n_params(*c) + 4; }
+
+struct NetCtx {
+	uint32_t n;
+	std::vector<h16> enc;        // SoA [2L][n]
+	std::vector<float> dy_dx;    // [2L][n][3]
+	std::vector<h16> sdf_in;     // [n][32]
+	std::vector<h16> sdf_hidden; // [hl][n][64]
+	std::vector<h16> rgb_in;     // [n][48]
+	std::vector<h16> rgb_hidden; // [hl][n][64]
+	std::vector<h16> rgb_out;    // [n][16]
+	std::vector<float> normal;   // [n][3]  dSDF_dPos
+	std::vector<h16> dsdf_dinput;// [n][32] (in-forward backward through the SDF MLP, seed=1)
+};
+
+// forward_impl (nerf_network.h:145-328), m_use_delta=false.  coords: [n][7] = pos3, dt, dir3 (warped).
+// out: [n][16] half AoS.
+static void net_forward(const NetCfg& c, uint32_t n, const float* coords, const h16* params, h16* out, NetCtx& ctx) {
+	const uint32_t E = n_enc(c), SI = sdf_in_w(c), RI = 48;
+	const h16* p_sdf = params;
+	const h16* p_rgb = params + sdf_n_params(c);
+	const h16* p_grid = p_rgb + rgb_n_params(c);
+	const h16* p_var = p_grid + grid_n_params(c);
+	ctx.n = n;
+	ctx.enc.assign((size_t)E * n, 0);
+	ctx.dy_dx.assign((size_t)E * n * 3, 0.f);
+	ctx.sdf_in.assign((size_t)n * SI, 0);
+	ctx.sdf_hidden.assign((size_t)c.sdf_hidden_layers * n * 64, 0);
+	ctx.rgb_in.assign((size_t)n * RI, 0);
+	ctx.rgb_hidden.assign((size_t)c.rgb_hidden_layers * n * 64, 0);
+	ctx.rgb_out.assign((size_t)n * 16, 0);
+	ctx.normal.assign((size_t)n * 3, 0.f);
+	ctx.dsdf_dinput.assign((size_t)n * SI, 0);
+
+	// :197 pos encoding forward with dy_dx
+	orc_grid_forward(n, coords, 7, p_grid, c.n_levels, c.offsets, c.resolutions, c.scales, c.valid_level, ctx.enc.data(), ctx.dy_dx.data());
+	// :206-212 SDF-MLP input = [ half(x) - half(0.5) | enc | 0 ]
+	for (uint32_t i = 0; i < n; ++i) {
+		for (int d = 0; d < 3; ++d) ctx.sdf_in[(size_t)i * SI + d] = f2h(rh(coords[(size_t)i * 7 + d]) - 0.5f);
+		for (uint32_t k = 0; k < E; ++k) ctx.sdf_in[(size_t)i * SI + 3 + k] = ctx.enc[(size_t)k * n + i];
+	}
+	// :225 SDF MLP forward -> rows 0..15 of the colour-MLP input
+	std::vector<h16> sdf_out((size_t)n * 16);
+	orc_mlp_forward(n, SI, c.sdf_hidden_layers, 16, p_sdf, ctx.sdf_in.data(), ctx.sdf_hidden.data(), sdf_out.data());
+	// :228-253 analytic normal: backward with dSDF/dSDF = e0, then through the grid (dy_dx) + identity path
+	std::vector<h16> seed((size_t)n * 16, 0);
+	for (uint32_t i = 0; i < n; ++i) seed[(size_t)i * 16] = f2h(1.0f);
+	orc_mlp_backward(n, SI, c.sdf_hidden_layers, 16, p_sdf, ctx.sdf_in.data(), ctx.sdf_hidden.data(), seed.data(), ctx.dsdf_dinput.data(), nullptr, nullptr);
+	{
+		std::vector<h16> dl_denc((size_t)E * n);
+		for (uint32_t i = 0; i < n; ++i) for (uint32_t k = 0; k < E; ++k) dl_denc[(size_t)k * n + i] = ctx.dsdf_dinput[(size_t)i * SI + 3 + k];
+		orc_grid_backward_input(n, E, dl_denc.data(), ctx.dy_dx.data(), ctx.normal.data());
+		// :249 add_positions_view<float, T>: normal += (float)dSDF_dSDFInput[0..2]
+		for (uint32_t i = 0; i < n; ++i) for (int d = 0; d < 3; ++d)
+			ctx.normal[(size_t)i * 3 + d] += h2f(ctx.dsdf_dinput[(size_t)i * SI + d]);
+	}
+	// :264-280 colour-MLP input = [sdf out 16 | SH(dir) 16 | half(xyz) 3 | half(normal) 3 | 0]
+	for (uint32_t i = 0; i < n; ++i) {
+		h16* r = &ctx.rgb_in[(size_t)i * RI];
+		for (int k = 0; k < 16; ++k) r[k] = sdf_out[(size_t)i * 16 + k];
+		sh4(coords + (size_t)i * 7 + 4, r + 16);
+		for (int d = 0; d < 3; ++d) r[32 + d] = f2h(coords[(size_t)i * 7 + d]);
+		for (int d = 0; d < 3; ++d) r[35 + d] = f2h(ctx.normal[(size_t)i * 3 + d]);
+	}
+	// :284 colour MLP
+	orc_mlp_forward(n, RI, c.rgb_hidden_layers, 16, p_rgb, ctx.rgb_in.data(), ctx.rgb_hidden.data(), ctx.rgb_out.data());
+	// :287-325 output assembly
+	if (out) {
+		const float bias_h = rh(c.sdf_bias);
+		for (uint32_t i = 0; i < n; ++i) {
+			h16* o = out + (size_t)i * 16;
+			for (int k = 0; k < 16; ++k) o[k] = ctx.rgb_out[(size_t)i * 16 + k];
+			o[3] = f2h(h2f(sdf_out[(size_t)i * 16]) + bias_h);          // :290 sdf + bias (half add)
+			for (int d = 0; d < 3; ++d) o[4 + d] = f2h(ctx.normal[(size_t)i * 3 + d]);   // :306
+			o[7] = p_var[0];                                            // :312
+			for (int d = 0; d < 3; ++d) o[8 + d] = f2h(coords[(size_t)i * 7 + 4 + d]);   // :319
+		}
+	}
+}
+
+void orc_net_forward(const NetCfg* c, uint32_t n, const float* coords, const h16* params, h16* out) {
+	NetCtx ctx;
+	net_forward(*c, n, coords, params, out, ctx);
+}
+
+// Forward that also exports the intermediate tensors the parity tests look at.
+void orc_net_forward_debug(const NetCfg* c, uint32_t n, const float* coords, const h16* params, h16* out,
+                           h16* enc_soa, float* normal, h16* sdf_in, h16* rgb_in, h16* sdf_hidden, h16* rgb_hidden) {
+	NetCtx ctx;
+	net_forward(*c, n, coords, params, out, ctx);
+	if (sdf_hidden) std::memcpy(sdf_hidden, ctx.sdf_hidden.data(), ctx.sdf_hidden.size() * 2);
+	if (rgb_hidden) std::memcpy(rgb_hidden, ctx.rgb_hidden.data(), ctx.rgb_hidden.size() * 2);
+	if (enc_soa) std::memcpy(enc_soa, ctx.enc.data(), ctx.enc.size() * 2);
+	if (normal) std::memcpy(normal, ctx.normal.data(), ctx.normal.size() * 4);
+	if (sdf_in) std::memcpy(sdf_in, ctx.sdf_in.data(), ctx.sdf_in.size() * 2);
+	if (rgb_in) std::memcpy(rgb_in, ctx.rgb_in.data(), ctx.rgb_in.size() * 2);
+}
+
+// backward_impl (nerf_network.h:330-601), m_train_canonical=true, m_use_delta=false.
+// dL_dout [n][16] half.  grads: fp32 [n_params], OVERWRITTEN (EGradientMode::Overwrite at testbed_nerf.cu:3946).
+// indeed_batch_size: the eikonal normaliser (nerf_network.h:490-496; set at testbed_nerf.cu:3941).
+void orc_net_backward(const NetCfg* cp, uint32_t n, const float* coords, const h16* params, const h16* dL_dout,
+                      uint32_t indeed_batch_size, float* grads) {
+	const NetCfg& c = *cp;
+	const uint32_t E = n_enc(c), SI = sdf_in_w(c), RI = 48;
+	const size_t NP = orc_net_n_params(cp);
+	std::memset(grads, 0, NP * sizeof(float));
+	const h16* p_sdf = params;
+	const h16* p_rgb = params + sdf_n_params(c);
+	float* g_sdf = grads;
+	float* g_rgb = grads + sdf_n_params(c);
+	float* g_grid = g_rgb + rgb_n_params(c);
+	float* g_var = g_grid + grid_n_params(c);
+
+	NetCtx ctx;
+	std::vector<h16> out((size_t)n * 16);
+	net_forward(c, n, coords, params, out.data(), ctx);
+
+	// :345-353 colour MLP backward from rows 0..2
+	std::vector<h16> dL_drgb((size_t)n * 16, 0);
+	for (uint32_t i = 0; i < n; ++i) for (int k = 0; k < 3; ++k) dL_drgb[(size_t)i * 16 + k] = dL_dout[(size_t)i * 16 + k];
+	std::vector<h16> dL_drgb_in((size_t)n * RI);
+	orc_mlp_backward(n, RI, c.rgb_hidden_layers, 16, p_rgb, ctx.rgb_in.data(), ctx.rgb_hidden.data(), dL_drgb.data(), dL_drgb_in.data(), g_rgb, nullptr);
+
+	// :401-415 SDF MLP backward: rows 0..15 of the colour-input gradient, + dL/dsdf on row 0 (half add)
+	std::vector<h16> dL_dsdf_out((size_t)n * 16);
+	for (uint32_t i = 0; i < n; ++i) {
+		for (int k = 0; k < 16; ++k) dL_dsdf_out[(size_t)i * 16 + k] = dL_drgb_in[(size_t)i * RI + k];
+		dL_dsdf_out[(size_t)i * 16] = f2h(h2f(dL_dsdf_out[(size_t)i * 16]) + h2f(dL_dout[(size_t)i * 16 + 3]));
+	}
+	std::vector<h16> dL_dsdf_in((size_t)n * SI);
+	orc_mlp_backward(n, SI, c.sdf_hidden_layers, 16, p_sdf, ctx.sdf_in.data(), ctx.sdf_hidden.data(), dL_dsdf_out.data(), dL_dsdf_in.data(), g_sdf, nullptr);
+
+	// :423-442 grid backward (first order)
+	std::vector<h16> dl_denc((size_t)E * n);
+	for (uint32_t i = 0; i < n; ++i) for (uint32_t k = 0; k < E; ++k) dl_denc[(size_t)k * n + i] = dL_dsdf_in[(size_t)i * SI + 3 + k];
+	orc_grid_backward(n, coords, 7, dl_denc.data(), c.n_levels, c.offsets, c.resolutions, c.scales, c.valid_level, g_grid);
+
+	// :463-474 variance gradient: fp32 sum of row 7, rounded once to half (reduce_sum -> T)
+	{
+		float s = 0.f;
+		for (uint32_t i = 0; i < n; ++i) s += h2f(dL_dout[(size_t)i * 16 + 7]);
+		g_var[0] = rh(s);
+	}
+
+	// :476-504 v = dL/d(normal): colour-input grad at the normal slots + eikonal rows / B + cos rows
+	std::vector<float> v((size_t)n * 3);
+	for (uint32_t i = 0; i < n; ++i) for (int d = 0; d < 3; ++d) {
+		float a = h2f(dL_drgb_in[(size_t)i * RI + 35 + d]);
+		a += h2f(dL_dout[(size_t)i * 16 + 4 + d]) / (float)indeed_batch_size;
+		a += h2f(dL_dout[(size_t)i * 16 + 8 + d]);
+		v[(size_t)i * 3 + d] = a;
+	}
+	// :510-533 d sdf / d enc again (identical to the forward's)
+	for (uint32_t i = 0; i < n; ++i) for (uint32_t k = 0; k < E; ++k) dl_denc[(size_t)k * n + i] = ctx.dsdf_dinput[(size_t)i * SI + 3 + k];
+	// :547-557 grid second order: -> grid grads (Accumulate), -> pos_encoding_dy
+	orc_grid_bwdbwd_grid(n, coords, 7, v.data(), dl_denc.data(), c.n_levels, c.offsets, c.resolutions, c.scales, c.valid_level, g_grid);
+	std::vector<h16> pos_encoding_dy((size_t)E * n);
+	orc_grid_bwdbwd_dLdoutput(n, E, v.data(), ctx.dy_dx.data(), pos_encoding_dy.data());
+	// :560-584 SDF MLP second order with d_density_input = [half(v) | pos_encoding_dy | 0], seed e0
+	std::vector<h16> d_in((size_t)n * SI, 0);
+	for (uint32_t i = 0; i < n; ++i) {
+		for (int d = 0; d < 3; ++d) d_in[(size_t)i * SI + d] = f2h(v[(size_t)i * 3 + d]);
+		for (uint32_t k = 0; k < E; ++k) d_in[(size_t)i * SI + 3 + k] = pos_encoding_dy[(size_t)k * n + i];
+	}
+	std::vector<h16> seed((size_t)n * 16, 0);
+	for (uint32_t i = 0; i < n; ++i) seed[(size_t)i * 16] = f2h(1.0f);
+	orc_mlp_bwdbwd(n, SI, c.sdf_hidden_layers, 16, p_sdf, ctx.sdf_hidden.data(), d_in.data(), seed.data(), g_sdf);
+}
+
+// sdf() and density() (nerf_network.h:656-739; common_operation.cuh:293-324).  pos: [n][stride] floats.
+// out: half [n]: sdf(+bias) or density = s*sig(s*sdf)*(1-sig(s*sdf)), s = exp(10*var), all in half arithmetic.
+void orc_net_sdf(const NetCfg* cp, uint32_t n, const float* pos, uint32_t stride, const h16* params, int as_density, h16* out) {
+	const NetCfg& c = *cp;
+	const uint32_t E = n_enc(c), SI = sdf_in_w(c);
+	const h16* p_sdf = params;
+	const h16* p_grid = params + sdf_n_params(c) + rgb_n_params(c);
+	const h16* p_var = p_grid + grid_n_params(c);
+	std::vector<h16> enc((size_t)E * n);
+	orc_grid_forward(n, pos, stride, p_grid, c.n_levels, c.offsets, c.resolutions, c.scales, c.valid_level, enc.data(), nullptr);
+	std::vector<h16> in((size_t)n * SI, 0), hidden((size_t)c.sdf_hidden_layers * n * 64), o((size_t)n * 16);
+	for (uint32_t i = 0; i < n; ++i) {
+		for (int d = 0; d < 3; ++d) in[(size_t)i * SI + d] = f2h(rh(pos[(size_t)i * stride + d]) - 0.5f);
+		for (uint32_t k = 0; k < E; ++k) in[(size_t)i * SI + 3 + k] = enc[(size_t)k * n + i];
+	}
+	orc_mlp_forward(n, SI, c.sdf_hidden_layers, 16, p_sdf, in.data(), hidden.data(), o.data());
+	const float bias_h = rh(c.sdf_bias);
+	for (uint32_t i = 0; i < n; ++i) {
+		float sdf = rh(h2f(o[(size_t)i * 16]) + bias_h);
+		if (!as_density) { out[i] = f2h(sdf); continue; }
+		float variance = h2f(p_var[0]);
+		float s = rh(expf(rh(variance * 10.0f)));                  // (T)__expf(variance*(T)10)
+		float sig = rh(1.0f / (1.0f + expf(-rh(sdf * s))));        // tcnn::logistic(sdf*s) -> T
+		float one_minus = rh(1.0f - sig);
+		float density = rh(rh(s * sig) * one_minus);
+		out[i] = f2h(density);
+	}
+}
+
+// ----------------------------------------------------------------------------
+// Adam + EMA (tcnn optimizers/adam.h:52-160, ema.h:64-77,112-147).
+// ----------------------------------------------------------------------------
+void orc_adam_ema_step(uint64_t n, uint64_t n_matrix, float loss_scale, float lr, float beta1, float beta2, float eps, float l2_reg,
+                       float ema_decay, uint32_t ema_step /* nested step count after increment */,
+                       const float* grads /* as (float)half */, float* master, h16* params, float* m1, float* m2, uint32_t* steps, h16* ema) {
+	float ema_debias_old = 1 - (float)std::pow(ema_decay, ema_step - 1);
+	float ema_debias_new = 1.0f / (1 - (float)std::pow(ema_decay, ema_step));
+	#pragma omp parallel for schedule(static)
+	for (int64_t ii = 0; ii < (int64_t)n; ++ii) {
+		const uint64_t i = (uint64_t)ii;
+		bool skip = false;
+		float gradient = grads[i] / loss_scale;
+		const bool is_matrix = i < n_matrix;
+		if (!is_matrix && gradient == 0) skip = true;     // adam.h:109-112
+		if (!skip) {
+			const float w = master[i];
+			if (is_matrix) gradient += l2_reg * w;        // adam.h:132-135
+			const float gsq = gradient * gradient;
+			float fm = m1[i] = beta1 * m1[i] + (1 - beta1) * gradient;
+			const float sm = m2[i] = beta2 * m2[i] + (1 - beta2) * gsq;
+			float learning_rate = lr;
+			const uint32_t cs = ++steps[i];
+			learning_rate *= sqrtf(1 - powf(beta2, (float)cs)) / (1 - powf(beta1, (float)cs));
+			const float eff = fminf(fmaxf(learning_rate / (sqrtf(sm) + eps), 0.f), std::numeric_limits<float>::max());
+			const float decayed = (1 - 0.f * learning_rate) * w - copysignf(0.f * learning_rate, w);
+			const float nw = decayed - eff * fm;
+			master[i] = nw;
+			params[i] = f2h(nw);
+		}
+		// EMA over ALL params (ema.h:64-77)
+		float filtered = (h2f(ema[i]) * ema_decay * ema_debias_old + h2f(params[i]) * (1 - ema_decay)) * ema_debias_new;
+		ema[i] = f2h(filtered);
+	}
+}
+
+// ----------------------------------------------------------------------------
+// ngp layer: training-sample generation (src/testbed_nerf.cu:1263-1456) and helpers.
+// ----------------------------------------------------------------------------
+static const uint32_t GRIDSIZE = 128;
+static const uint32_t NERF_STEPS = 1024;
+static const uint32_t NERF_CASCADES = 8;
+static inline float MIN_CONE_STEPSIZE() { return 1.73205080757f / 1024; }          // testbed_nerf.cu:61-63
+static inline float MAX_CONE_STEPSIZE() { return MIN_CONE_STEPSIZE() * (1 << (NERF_CASCADES - 1)) * NERF_STEPS / GRIDSIZE; }  // :65
+
+static inline float clampf(float v, float lo, float hi) { return v < lo ? lo : (hi < v ? hi : v); }  // tcnn common.h:250
+static inline float calc_dt(float t, float cone_angle) { return clampf(t * cone_angle, MIN_CONE_STEPSIZE(), MAX_CONE_STEPSIZE()); }  // :162
+
+static inline uint32_t expand_bits(uint32_t v) {   // tcnn common_device.h:339-345
+	v = (v * 0x00010001u) & 0xFF0000FFu;
+	v = (v * 0x00000101u) & 0x0F00F00Fu;
+	v = (v * 0x00000011u) & 0xC30C30C3u;
+	v = (v * 0x00000005u) & 0x49249249u;
+	return v;
+}
+static inline uint32_t morton3D(uint32_t x, uint32_t y, uint32_t z) { return expand_bits(x) | (expand_bits(y) << 1) | (expand_bits(z) << 2); }
+static inline uint32_t morton3D_invert(uint32_t x) {   // :355-362
+	x = x & 0x49249249;
+	x = (x | (x >> 2)) & 0xc30c30c3;
+	x = (x | (x >> 4)) & 0x0f00f00f;
+	x = (x | (x >> 8)) & 0xff0000ff;
+	x = (x | (x >> 16)) & 0x0000ffff;
+	return x;
+}
+uint32_t orc_morton3D(uint32_t x, uint32_t y, uint32_t z) { return morton3D(x, y, z); }
+uint32_t orc_morton3D_invert(uint32_t x) { return morton3D_invert(x); }
+
+static inline int mip_from_pos(const float p[3], uint32_t max_cascade = NERF_CASCADES - 1) {   // :624-629
+	int exponent;
+	float maxval = std::max(std::max(fabsf(p[0] - 0.5f), fabsf(p[1] - 0.5f)), fabsf(p[2] - 0.5f));
+	frexpf(maxval, &exponent);
+	return std::min((int)max_cascade, std::max(0, exponent + 1));
+}
+static inline int mip_from_dt(float dt, const float p[3], uint32_t max_cascade = NERF_CASCADES - 1) {   // :631-638
+	int mip = mip_from_pos(p, max_cascade);
+	dt *= 2 * GRIDSIZE;
+	if (dt < 1.f) return mip;
+	int exponent;
+	frexpf(dt, &exponent);
+	return std::min((int)max_cascade, std::max(exponent, mip));
+}
+static inline uint32_t cascaded_grid_idx_at(const float pin[3], uint32_t mip) {   // :494-514
+	float mip_scale = scalbnf(1.0f, -(int)mip);
+	int i[3];
+	for (int d = 0; d < 3; ++d) {
+		float p = pin[d] - 0.5f;
+		p *= mip_scale;
+		p += 0.5f;
+		i[d] = (int)(p * GRIDSIZE);
+		i[d] = std::min(std::max(i[d], 0), (int)GRIDSIZE - 1);
+	}
+	return morton3D(i[0], i[1], i[2]);
+}
+static inline bool density_grid_occupied_at(const float p[3], const uint8_t* bitfield, uint32_t mip) {   // :516-520
+	uint32_t idx = cascaded_grid_idx_at(p, mip);
+	return bitfield[idx / 8 + (GRIDSIZE * GRIDSIZE * GRIDSIZE * mip) / 8] & (1 << (idx % 8));
+}
+static inline float signf(float x) { return copysignf(1.0f, x); }   // common.h:187
+static inline float distance_to_next_voxel(const float pos[3], const float dir[3], const float idir[3], uint32_t res) {   // :356-364
+	float p[3] = {(float)res * pos[0], (float)res * pos[1], (float)res * pos[2]};
+	float tx = (floorf(p[0] + 0.5f + 0.5f * signf(dir[0])) - p[0]) * idir[0];
+	float ty = (floorf(p[1] + 0.5f + 0.5f * signf(dir[1])) - p[1]) * idir[1];
+	float tz = (floorf(p[2] + 0.5f + 0.5f * signf(dir[2])) - p[2]) * idir[2];
+	float t = std::min(std::min(tx, ty), tz);
+	return fmaxf(t / (float)res, 0.0f);
+}
+static inline float advance_to_next_voxel(float t, float cone_angle, const float pos[3], const float dir[3], const float idir[3], uint32_t res) {   // :366-378
+	float t_target = t + distance_to_next_voxel(pos, dir, idir, res);
+	do { t += calc_dt(t, cone_angle); } while (t < t_target);
+	return t;
+}
+static inline float srgb_to_linear(float s) { return s <= 0.04045f ? s / 12.92f : powf((s + 0.055f) / 1.055f, 2.4f); }   // common_device.cuh:30-36
+static inline float linear_to_srgb(float l) { return l < 0.0031308f ? 12.92f * l : 1.055f * powf(l, 0.41666f) - 0.055f; }   // :55-61
+float orc_srgb_to_linear(float s) { return srgb_to_linear(s); }
+float orc_linear_to_srgb(float l) { return linear_to_srgb(l); }
+
+struct Dataset {
+	uint32_t n_images;
+	int32_t width, height;            // all images share one resolution
+	const uint8_t* pixels;            // [n_images][h][w][4] RGBA8
+	const float* focal;               // [n_images][2] pixels
+	const float* principal;           // [n_images][2] relative (cx/w, cy/h)
+	const float* xforms;              // [n_images][3][4] row-major camera-to-world (ngp convention)
+};
+
+// read_rgba, Byte images (common_device.cuh:635-656)
+static inline void read_rgba(const Dataset& ds, uint32_t img, int px, int py, float out[4]) {
+	const uint8_t* v = ds.pixels + (((size_t)img * ds.height + py) * ds.width + px) * 4;
+	uint32_t word; std::memcpy(&word, v, 4);
+	if (word == 0x00FF00FF) { out[0] = out[1] = out[2] = out[3] = -1.0f; return; }
+	float alpha = (float)v[3] * (1.0f / 255.0f);
+	out[0] = srgb_to_linear((float)v[0] * (1.0f / 255.0f)) * alpha;
+	out[1] = srgb_to_linear((float)v[1] * (1.0f / 255.0f)) * alpha;
+	out[2] = srgb_to_linear((float)v[2] * (1.0f / 255.0f)) * alpha;
+	out[3] = alpha;
+}
+static inline void image_pos(const float xy[2], int w, int h, int* px, int* py) {   // common_device.cuh:591-593
+	*px = std::max(std::min((int)(xy[0] * (float)w), w - 1), 0);
+	*py = std::max(std::min((int)(xy[1] * (float)h), h - 1), 0);
+}
+static inline uint32_t image_idx(uint32_t base_idx, uint32_t n_rays, uint32_t n_rays_total, uint32_t n_images) {   // :1241-1261
+	return (((base_idx + n_rays_total) * n_images) / n_rays) % n_images;
+}
+static inline void random_image_pos_training(Pcg32& rng, int w, int h, bool snap, float xy[2]) {   // :1226-1239
+	xy[0] = rng.next_float(); xy[1] = rng.next_float();
+	if (snap) {
+		int ix = std::min(std::max((int)(xy[0] * (float)w), 0), w - 1);
+		int iy = std::min(std::max((int)(xy[1] * (float)h), 0), h - 1);
+		xy[0] = ((float)ix + 0.5f) / (float)w;
+		xy[1] = ((float)iy + 0.5f) / (float)h;
+	}
+}
+
+struct Ray { float o[3], d[3]; };
+
+// ray for pixel xy of image img, unnormalised direction (:1319-1374, no distortion, rolling shutter = 0)
+static inline void make_ray(const Dataset& ds, uint32_t img, const float xy[2], Ray& r) {
+	const float* X = ds.xforms + (size_t)img * 12;
+	const float fx = ds.focal[img * 2], fy = ds.focal[img * 2 + 1];
+	const float cx = ds.principal[img * 2], cy = ds.principal[img * 2 + 1];
+	float d[3] = {(xy[0] - cx) * (float)ds.width / fx, (xy[1] - cy) * (float)ds.height / fy, 1.0f};
+	for (int k = 0; k < 3; ++k) {
+		r.o[k] = X[k * 4 + 3];
+		// xform.block<3,3>(0,0) * d : row k dot d, evaluated left to right with fused multiply-adds
+		r.d[k] = fmaf(X[k * 4 + 2], d[2], fmaf(X[k * 4 + 1], d[1], X[k * 4 + 0] * d[0]));
+	}
+}
+static inline void normalize3(const float v[3], float out[3]) {
+	float n2 = fmaf(v[2], v[2], fmaf(v[1], v[1], v[0] * v[0]));
+	float n = sqrtf(n2);
+	if (n2 > 0) { out[0] = v[0] / n; out[1] = v[1] / n; out[2] = v[2] / n; } else { out[0] = v[0]; out[1] = v[1]; out[2] = v[2]; }
+}
+// global_movement_with_rotation_6d (:194-213): o = R o + t, d = R d; R (9) and t (3) stored in half.
+static inline void global_move(const h16* rot, const h16* trans, float o[3], float d[3]) {
+	float R[9]; for (int k = 0; k < 9; ++k) R[k] = h2f(rot[k]);
+	float T[3] = {h2f(trans[0]), h2f(trans[1]), h2f(trans[2])};
+	float no[3], nd[3];
+	for (int k = 0; k < 3; ++k) {
+		no[k] = fmaf(R[k * 3 + 2], o[2], fmaf(R[k * 3 + 1], o[1], R[k * 3] * o[0])) + T[k];
+		nd[k] = fmaf(R[k * 3 + 2], d[2], fmaf(R[k * 3 + 1], d[1], R[k * 3] * d[0]));
+	}
+	for (int k = 0; k < 3; ++k) { o[k] = no[k]; d[k] = nd[k]; }
+}
+// BoundingBox::ray_intersect (bounding_box.cuh:163-211)
+static inline void ray_intersect(const float bmin[3], const float bmax[3], const float o[3], const float d[3], float* tmin_out, float* tmax_out) {
+	const float FMAX = std::numeric_limits<float>::max();
+	float tmin = (bmin[0] - o[0]) / d[0], tmax = (bmax[0] - o[0]) / d[0];
+	if (tmin > tmax) std::swap(tmin, tmax);
+	float tymin = (bmin[1] - o[1]) / d[1], tymax = (bmax[1] - o[1]) / d[1];
+	if (tymin > tymax) std::swap(tymin, tymax);
+	if (tmin > tymax || tymin > tmax) { *tmin_out = FMAX; *tmax_out = FMAX; return; }
+	if (tymin > tmin) tmin = tymin;
+	if (tymax < tmax) tmax = tymax;
+	float tzmin = (bmin[2] - o[2]) / d[2], tzmax = (bmax[2] - o[2]) / d[2];
+	if (tzmin > tzmax) std::swap(tzmin, tzmax);
+	if (tmin > tzmax || tzmin > tmax) { *tmin_out = FMAX; *tmax_out = FMAX; return; }
+	if (tzmin > tmin) tmin = tzmin;
+	if (tzmax < tmax) tmax = tzmax;
+	*tmin_out = tmin; *tmax_out = tmax;
+}
+static inline bool aabb_contains(const float bmin[3], const float bmax[3], const float p[3]) {
+	return p[0] >= bmin[0] && p[0] <= bmax[0] && p[1] >= bmin[1] && p[1] <= bmax[1] && p[2] >= bmin[2] && p[2] <= bmax[2];
+}
+static inline float warp_dt(float dt) {   // :484-487
+	float max_stepsize = MIN_CONE_STEPSIZE() * (1 << (NERF_CASCADES - 1));
+	return (dt - MIN_CONE_STEPSIZE()) / (max_stepsize - MIN_CONE_STEPSIZE());
+}
+static inline float unwarp_dt(float dt) {   // :489-492
+	float max_stepsize = MIN_CONE_STEPSIZE() * (1 << (NERF_CASCADES - 1));
+	return dt * (max_stepsize - MIN_CONE_STEPSIZE()) + MIN_CONE_STEPSIZE();
+}
+
+// One ray's march: returns numsteps; if coords != null, emits up to `limit` samples.
+// (:1391-1449; the reference walks twice -- count, then emit -- with identical arithmetic.)
+static uint32_t march_ray(const float bmin[3], const float bmax[3], const float ray_o[3], const float dir[3], float startt,
+                          float cone_angle, const uint8_t* bitfield, uint32_t limit, float* coords) {
+	float idir[3] = {1.0f / dir[0], 1.0f / dir[1], 1.0f / dir[2]};
+	float wdir[3] = {(dir[0] + 1.0f) * 0.5f, (dir[1] + 1.0f) * 0.5f, (dir[2] + 1.0f) * 0.5f};   // warp_direction :468
+	float diag[3] = {bmax[0] - bmin[0], bmax[1] - bmin[1], bmax[2] - bmin[2]};
+	uint32_t j = 0;
+	float t = startt;
+	float pos[3];
+	while (true) {
+		for (int k = 0; k < 3; ++k) pos[k] = fmaf(t, dir[k], ray_o[k]);
+		if (!(aabb_contains(bmin, bmax, pos) && j < limit)) break;
+		float dt = calc_dt(t, cone_angle);
+		uint32_t mip = (uint32_t)mip_from_dt(dt, pos);
+		if (density_grid_occupied_at(pos, bitfield, mip)) {
+			if (coords) {
+				float* c = coords + (size_t)j * 7;
+				for (int k = 0; k < 3; ++k) c[k] = (pos[k] - bmin[k]) / diag[k];   // warp_position :445 / bounding_box.cuh:86
+				c[3] = warp_dt(dt);
+				c[4] = wdir[0]; c[5] = wdir[1]; c[6] = wdir[2];
+			}
+			++j;
+			t += dt;
+		} else {
+			uint32_t res = GRIDSIZE >> mip;
+			t = advance_to_next_voxel(t, cone_angle, pos, dir, idir, res);
+		}
+	}
+	return j;
+}
+
+// generate_training_samples_nerf_with_global_movement (:1263-1456) made deterministic: rays keep their
+// index order (the reference orders by atomicAdd arrival; SURVEY §9.5 defines parity on the ray->numsteps map).
+// Outputs:
+//   numsteps_all[n_rays]  : per GLOBAL ray index: numsteps (0 if the ray was skipped or empty)  -- integer parity target
+//   ray_indices/rays/numsteps(2 per ray)/coords: the kept rays in ascending index order, base = exclusive scan
+//   counters[0] = n kept rays, counters[1] = total numsteps of all rays with j>0 (the reference's numsteps_counter,
+//                 which includes rays dropped by the max_samples check, :1421-1424)
+void orc_generate_training_samples(uint32_t n_rays, const float* aabb /*min3,max3*/, uint32_t max_samples, uint32_t n_rays_total,
+                                   const uint64_t* rng_state, const Dataset* dsp, const uint8_t* bitfield, int snap_to_pixel_centers,
+                                   float cone_angle_constant, const h16* rotation, const h16* transition, const float* first_frame_offset,
+                                   uint32_t* numsteps_all, uint32_t* ray_indices, float* rays /*[n][6]*/, uint32_t* numsteps /*[n][2]*/,
+                                   float* coords /*[max_samples][7]*/, uint32_t* counters) {
+	const Dataset& ds = *dsp;
+	const float* bmin = aabb; const float* bmax = aabb + 3;
+	uint32_t ray_counter = 0, numsteps_counter = 0;
+	for (uint32_t i = 0; i < n_rays; ++i) {
+		numsteps_all[i] = 0;
+		uint32_t img = image_idx(i, n_rays, n_rays_total, ds.n_images);
+		Pcg32 rng; rng.state = rng_state[0]; rng.inc = rng_state[1];
+		rng.advance((int64_t)(uint32_t)(i * 8u));   // :1304 (uint32 product)
+		float xy[2];
+		random_image_pos_training(rng, ds.width, ds.height, snap_to_pixel_centers != 0, xy);
+		int px, py; image_pos(xy, ds.width, ds.height, &px, &py);
+		float rgba[4]; read_rgba(ds, img, px, py, rgba);
+		if (rgba[0] <= 0.0f && rng.next_float() >= 0.9) continue;   // :1310 (short-circuit consumes a draw only here)
+		(void)rng.next_float();   // motionblur_time :1317
+		Ray ray; make_ray(ds, img, xy, ray);
+		float ray_o[3] = {ray.o[0], ray.o[1], ray.o[2]};
+		float dir[3]; normalize3(ray.d, dir);
+		for (int k = 0; k < 3; ++k) ray_o[k] -= first_frame_offset[k];
+		global_move(rotation, transition, ray_o, dir);
+		float tmin, tmax; ray_intersect(bmin, bmax, ray_o, dir, &tmin, &tmax);
+		float cone_angle = cone_angle_constant;
+		tmin = fmaxf(tmin, 0.0f);
+		float startt = tmin;
+		startt += calc_dt(startt, cone_angle) * rng.next_float();
+		uint32_t j = march_ray(bmin, bmax, ray_o, dir, startt, cone_angle, bitfield, NERF_STEPS, nullptr);
+		if (j == 0) continue;
+		numsteps_all[i] = j;
+		uint32_t base = numsteps_counter; numsteps_counter += j;
+		if (base + j > max_samples) continue;
+		uint32_t ridx = ray_counter++;
+		ray_indices[ridx] = i;
+		for (int k = 0; k < 3; ++k) { rays[(size_t)ridx * 6 + k] = ray.o[k]; rays[(size_t)ridx * 6 + 3 + k] = ray.d[k]; }
+		numsteps[ridx * 2] = j; numsteps[ridx * 2 + 1] = base;
+		march_ray(bmin, bmax, ray_o, dir, startt, cone_angle, bitfield, j, coords + (size_t)base * 7);
+	}
+	counters[0] = ray_counter; counters[1] = numsteps_counter;
+}
+
+// ----------------------------------------------------------------------------
+// Loss / compositing (src/testbed_nerf.cu:1475-1997).  Byte images, LDR: rgb_activation = Logistic,
+// Huber(0.1)/5, color_space Linear & train_in_linear_colors=false => loss in sRGB space.
+// Literal types (float vs double) follow the reference's expressions.
+// ----------------------------------------------------------------------------
+static inline float logistic(float x) { return 1.0f / (1.0f + expf(-x)); }   // tcnn common_device.h:52
+static inline float relu(float v) { return v > 0.0f ? v : 0.0f; }
+
+struct LossParams {
+	float loss_scale;            // LOSS_SCALE = 128
+	float background_color[3];
+	int random_bg_color;
+	int snap_to_pixel_centers;
+	float mask_loss_weight;
+	float ek_loss_weight;
+	float cos_anneal_ratio;
+};
+
+struct SampleEval { float alpha, p_div_c, true_cos, iter_cos, inv_s, sdf, next_sdf, dt; float rgb[3]; float g[3]; };
+
+static inline SampleEval eval_sample(const h16* o, const float* coord, const float dir[3], float cos_anneal_ratio) {
+	SampleEval e;
+	for (int k = 0; k < 3; ++k) e.rgb[k] = logistic(h2f(o[k]));                      // network_to_rgb :392
+	e.dt = unwarp_dt(coord[3]);
+	e.inv_s = expf(rh(10.0f * h2f(o[7])));                                            // :1590 (half multiply, then __expf)
+	e.sdf = h2f(o[3]);
+	for (int k = 0; k < 3; ++k) e.g[k] = h2f(o[4 + k]);
+	e.true_cos = (dir[0] * e.g[0] + dir[1] * e.g[1] + dir[2] * e.g[2]);               // :1600
+	e.iter_cos = (float)-(relu((float)(-e.true_cos * 0.5 + 0.5)) * (1.0 - cos_anneal_ratio) + relu(-e.true_cos) * cos_anneal_ratio);   // :1603
+	e.next_sdf = (float)(e.sdf + e.iter_cos * e.dt * 0.5);                            // :1606
+	float prev_sdf = (float)(e.sdf - e.iter_cos * e.dt * 0.5);
+	float next_cdf = logistic(e.next_sdf * e.inv_s);
+	float prev_cdf = logistic(prev_sdf * e.inv_s);
+	float p = prev_cdf - next_cdf;
+	float c = prev_cdf;
+	e.p_div_c = (p + 1e-5f) / (c + 1e-5f);
+	e.alpha = clampf(e.p_div_c, 0.0f, 1.0f);
+	return e;
+}
+
+// Deterministic version of the kernel: rays processed in index order, compacted_base = exclusive scan.
+// Inputs: per kept ray (ray_indices, rays, numsteps[2]), coords [.][7], network_output [.][16] half.
+// Outputs: numsteps rewritten (compacted count, compacted base); coords_compacted; dloss_doutput [.][16] half
+//          (entries 11..15 written as 0 -- uninitialised in the reference, never read: nerf_network.h:345-504);
+//          loss/ek_loss/mask_loss per ray; counters[0] = total compacted (un-clamped) count.
+void orc_compute_loss(uint32_t n_rays /* rays_per_batch */, uint32_t n_kept, const float* aabb, uint32_t n_rays_total,
+                      const uint64_t* rng_state, uint32_t max_samples_compacted, const LossParams* lp, const Dataset* dsp,
+                      const h16* network_output, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps,
+                      const float* coords, float* coords_compacted, h16* dloss_doutput,
+                      float* loss_output, float* ek_loss_output, float* mask_loss_output,
+                      const h16* rotation, const h16* transition, const float* first_frame_offset, uint32_t* counters) {
+	const Dataset& ds = *dsp;
+	const float* bmin = aabb; const float* bmax = aabb + 3;
+	float diag[3] = {bmax[0] - bmin[0], bmax[1] - bmin[1], bmax[2] - bmin[2]};
+	(void)diag;
+	uint32_t numsteps_counter = 0;
+	for (uint32_t i = 0; i < n_kept; ++i) {
+		uint32_t ns = numsteps[i * 2 + 0];
+		uint32_t base = numsteps[i * 2 + 1];
+		const float* cin = coords + (size_t)base * 7;
+		const h16* nout = network_output + (size_t)base * 16;
+		float T = 1.f;
+		const float EPSILON = 1e-4f;
+		float rgb_ray[3] = {0, 0, 0};
+		float weight_sum = 0.f;
+		uint32_t compacted = 0;
+		float ray_o[3] = {rays[(size_t)i * 6], rays[(size_t)i * 6 + 1], rays[(size_t)i * 6 + 2]};
+		float dir[3]; normalize3(&rays[(size_t)i * 6 + 3], dir);
+		for (int k = 0; k < 3; ++k) ray_o[k] -= first_frame_offset[k];
+		global_move(rotation, transition, ray_o, dir);
+
+		for (; compacted < ns; ++compacted) {
+			if (T < EPSILON) break;
+			const h16* o = nout + (size_t)compacted * 16;
+			if (compacted == 0) {   // BENT_DIR :1583-1588
+				float dv[3] = {h2f(o[8]) * 2.0f - 1.0f, h2f(o[9]) * 2.0f - 1.0f, h2f(o[10]) * 2.0f - 1.0f};
+				normalize3(dv, dir);
+			}
+			SampleEval e = eval_sample(o, cin + (size_t)compacted * 7, dir, lp->cos_anneal_ratio);
+			const float weight = e.alpha * T;
+			for (int k = 0; k < 3; ++k) rgb_ray[k] += weight * e.rgb[k];
+			weight_sum += weight;
+			T *= (1.f - e.alpha);
+		}
+
+		uint32_t ray_idx = ray_indices[i];
+		Pcg32 rng; rng.state = rng_state[0]; rng.inc = rng_state[1];
+		rng.advance((int64_t)(uint32_t)(ray_idx * 8u));   // :1632
+		uint32_t img = image_idx(ray_idx, n_rays, n_rays_total, ds.n_images);
+		float xy[2];
+		random_image_pos_training(rng, ds.width, ds.height, lp->snap_to_pixel_centers != 0, xy);
+		float bg[3] = {lp->background_color[0], lp->background_color[1], lp->background_color[2]};
+		if (lp->random_bg_color) { bg[0] = rng.next_float(); bg[1] = rng.next_float(); bg[2] = rng.next_float(); }   // :1642-1644
+		for (int k = 0; k < 3; ++k) bg[k] = srgb_to_linear(bg[k]);   // :1645
+		int px, py; image_pos(xy, ds.width, ds.height, &px, &py);
+		float tex[4]; read_rgba(ds, img, px, py, tex);
+		float rgbtarget[3];
+		for (int k = 0; k < 3; ++k) {   // :1658-1663 (exposure = 0 => scale exp(0)=1)
+			float exposure_scale = expf(0.6931471805599453f * 0.0f);
+			rgbtarget[k] = exposure_scale * tex[k] + (1.0f - tex[3]) * bg[k];
+			rgbtarget[k] = linear_to_srgb(rgbtarget[k]);
+			bg[k] = linear_to_srgb(bg[k]);
+		}
+		if (compacted == ns) for (int k = 0; k < 3; ++k) rgb_ray[k] += T * bg[k];   // :1673-1676
+
+		uint32_t compacted_base = numsteps_counter; numsteps_counter += compacted;   // :1682
+		compacted = std::min(max_samples_compacted - std::min(max_samples_compacted, compacted_base), compacted);
+		numsteps[i * 2 + 0] = compacted;
+		numsteps[i * 2 + 1] = compacted_base;
+		if (compacted == 0) continue;
+
+		float* cout = coords_compacted + (size_t)compacted_base * 7;
+		h16* dout = dloss_doutput + (size_t)compacted_base * 16;
+
+		// loss_and_gradient: Huber(alpha=0.1)/5 (:311-327, :1469)
+		float lg_loss[3], lg_grad[3];
+		for (int k = 0; k < 3; ++k) {
+			const float alpha_h = 0.1f;
+			float difference = rgb_ray[k] - rgbtarget[k];
+			float abs_diff = fabsf(difference);
+			float square = 0.5f / alpha_h * difference * difference;
+			lg_loss[k] = (abs_diff > alpha_h ? (abs_diff - 0.5f * alpha_h) : square) / 5.0f;
+			lg_grad[k] = (abs_diff > alpha_h ? (difference > 0 ? 1.0f : -1.0f) : (difference / alpha_h)) / 5.0f;
+		}
+		float mask_gt = (float)(tex[3] > 0.9999);   // :1700
+		float gradient_weight_sum;
+		if (weight_sum >= 1.0 - 1e-4) { weight_sum = (float)(1.0 - 1e-4); gradient_weight_sum = 0.0f; }   // :1705-1716
+		else if (weight_sum <= 1e-4) { weight_sum = (float)1e-4; gradient_weight_sum = 0.0f; }
+		else {
+			float sigmoid_weight_sum = 1.0f / (1.0f + expf(-weight_sum));
+			gradient_weight_sum = (mask_gt - sigmoid_weight_sum) * weight_sum * lp->mask_loss_weight;
+		}
+		float mean_loss = (lg_loss[0] + lg_loss[1] + lg_loss[2]) / 3.0f;
+		loss_output[i] = mean_loss / (float)n_rays;   // :1726
+		mask_loss_output[i] = -(mask_gt * logf(weight_sum) + (1 - mask_gt) * logf(1 - weight_sum));   // :1730
+		ek_loss_output[i] = 0.f;
+
+		float loss_scale = lp->loss_scale / n_rays;   // :1765
+		float rgb_ray2[3] = {0, 0, 0};
+		T = 1.f;
+		for (uint32_t j = 0; j < compacted; ++j) {
+			std::memcpy(cout + (size_t)j * 7, cin + (size_t)j * 7, 7 * sizeof(float));   // :1781-1783
+			const h16* o = nout + (size_t)j * 16;
+			SampleEval e = eval_sample(o, cin + (size_t)j * 7, dir, lp->cos_anneal_ratio);
+			const float weight = e.alpha * T;
+			for (int k = 0; k < 3; ++k) rgb_ray2[k] += weight * e.rgb[k];
+			T *= (1.f - e.alpha);
+			float suffix[3], dloss_by_drgb[3];
+			for (int k = 0; k < 3; ++k) { suffix[k] = rgb_ray[k] - rgb_ray2[k]; dloss_by_drgb[k] = weight * lg_grad[k]; }
+			float local[16];
+			for (int k = 0; k < 16; ++k) local[k] = 0.f;
+			for (int k = 0; k < 3; ++k) {   // :1830-1832 (output_l2_reg = 0 for Logistic)
+				float density = logistic(h2f(o[k]));
+				float deriv = density * (1 - density);
+				local[k] = loss_scale * (dloss_by_drgb[k] * deriv + fmaxf(0.0f, 0.0f * h2f(o[k])));
+			}
+			float dot = lg_grad[0] * (T * e.rgb[0] - suffix[0]) + lg_grad[1] * (T * e.rgb[1] - suffix[1]) + lg_grad[2] * (T * e.rgb[2] - suffix[2]);
+			float dloss_dalpha = (float)((dot + gradient_weight_sum * (1 - weight_sum)) / (1.0f - e.alpha + 1e-5));   // :1838-1841
+
+			float dalpha_d_e_minus_sigmoidx, d_e_minus_sigmoidx_dsdf, d_e_minus_sigmoidx_dinvs, d_alpha_d_plus_e, d_plus_e_dinvs, d_plus_e_iter_cos, d_e_minus_sigmoidx_diter_cos;
+			if (e.p_div_c <= 0.0f || e.p_div_c >= 1.0f) {   // :1852-1860
+				dalpha_d_e_minus_sigmoidx = d_e_minus_sigmoidx_dsdf = d_e_minus_sigmoidx_dinvs = d_alpha_d_plus_e = d_plus_e_dinvs = d_plus_e_iter_cos = d_e_minus_sigmoidx_diter_cos = 0.0f;
+			} else {   // :1861-1884
+				float plus_sigmoid_x = e.inv_s * e.iter_cos * e.dt;
+				float plus_e = expf(plus_sigmoid_x);
+				float e_minus_sigmoid = expf(-e.next_sdf * e.inv_s);
+				d_e_minus_sigmoidx_dsdf = -e.inv_s * e_minus_sigmoid;
+				d_e_minus_sigmoidx_dinvs = -e.next_sdf * e_minus_sigmoid;
+				float a = 1 + e_minus_sigmoid;
+				float b = 1 + plus_e * e_minus_sigmoid;
+				float c = (float)(1e-5 + 1 / (1 + plus_e * e_minus_sigmoid));
+				float delta = a * (b * b) * (c * c);
+				dalpha_d_e_minus_sigmoidx = -(plus_e / (delta) - 1 / (a * a * c));
+				d_alpha_d_plus_e = -e_minus_sigmoid / (delta);
+				d_plus_e_dinvs = plus_e * e.iter_cos * e.dt;
+				d_plus_e_iter_cos = plus_e * e.inv_s * e.dt;
+				d_e_minus_sigmoidx_diter_cos = (float)(-e.inv_s * e_minus_sigmoid * e.dt * 0.5);
+			}
+			float dloss_dinvs = dloss_dalpha * (dalpha_d_e_minus_sigmoidx * d_e_minus_sigmoidx_dinvs + d_alpha_d_plus_e * d_plus_e_dinvs);
+			float dloss_dvariance = dloss_dinvs * e.inv_s * 10;
+			float d_iter_cos_true_cos = (e.true_cos >= 0) ? 0.0f : 1.0f;   // :1890-1896
+			float gradient_norm = (float)std::sqrt(e.g[0] * e.g[0] + e.g[1] * e.g[1] + e.g[2] * e.g[2] + 1e-6);   // :1897 (double sqrt)
+			float pos_gradient_norm_inv = 1 - 1 / gradient_norm;
+			float dloss_dnormal_norm = dloss_dalpha * (dalpha_d_e_minus_sigmoidx * d_e_minus_sigmoidx_diter_cos + d_plus_e_iter_cos * d_alpha_d_plus_e) * d_iter_cos_true_cos;
+			float dloss_dsdf = dloss_dalpha * dalpha_d_e_minus_sigmoidx * d_e_minus_sigmoidx_dsdf;
+			local[3] = loss_scale * dloss_dsdf;   // :1903
+			ek_loss_output[i] += (gradient_norm - 1.0f) * (gradient_norm - 1.0f);   // :1907
+			for (int k = 0; k < 3; ++k) local[4 + k] = lp->ek_loss_weight * 2 * lp->loss_scale * pos_gradient_norm_inv * e.g[k];   // :1911-1913
+			local[7] = loss_scale * dloss_dvariance;   // :1915
+			for (int k = 0; k < 3; ++k) local[8 + k] = loss_scale * dloss_dnormal_norm * dir[k];   // :1944-1946
+			for (int k = 0; k < 16; ++k) dout[(size_t)j * 16 + k] = f2h(local[k]);
+		}
+		ek_loss_output[i] /= (float)compacted * (float)n_rays;   // :1956
+	}
+	counters[0] = numsteps_counter;
+}
+
+// fill_rollover_and_rescale / fill_rollover (tcnn common_device.h:511-534; calls testbed_nerf.cu:3922-3927).
+void orc_fill_rollover(uint32_t n_elements, uint32_t stride, uint32_t n_input, h16* dl /*nullable*/, uint32_t dl_stride, float* coords /*nullable*/) {
+	// Rows [0, n_input) are left untouched (NOT rescaled); rows [n_input, n_elements) are wrap-around copies,
+	// and only in the "_and_rescale" variant are those copies multiplied by n_input/n_elements:
+	//   result = (T)((float)result * n_input_elements / n_elements)     (float*float, then float/float)
+	if (n_input == 0 || n_input >= n_elements) return;
+	if (dl) {
+		for (size_t i = (size_t)n_input * dl_stride; i < (size_t)n_elements * dl_stride; ++i)
+			dl[i] = f2h(h2f(dl[i % ((size_t)n_input * dl_stride)]) * (float)n_input / (float)n_elements);
+	}
+	if (coords) {
+		for (size_t i = (size_t)n_input * stride; i < (size_t)n_elements * stride; ++i) coords[i] = coords[i % ((size_t)n_input * stride)];
+	}
+}
+
+// ----------------------------------------------------------------------------
+// Occupancy grid (src/testbed_nerf.cu:640-795, 3293-3397).
+// ----------------------------------------------------------------------------
+// generate_grid_samples_nerf_nonuniform (:640-669).  positions: [n][3]; indices: [n].
+void orc_generate_grid_samples(uint32_t n, const uint64_t* rng_state, uint32_t step, const float* aabb, const float* grid_in,
+                               uint32_t n_cascades, float thresh, float* positions, uint32_t* indices) {
+	const float* bmin = aabb; const float* bmax = aabb + 3;
+	const uint32_t G3 = GRIDSIZE * GRIDSIZE * GRIDSIZE;
+	for (uint32_t i = 0; i < n; ++i) {
+		Pcg32 rng; rng.state = rng_state[0]; rng.inc = rng_state[1];
+		rng.advance((int64_t)(uint32_t)(i * 4u));
+		uint32_t level = (uint32_t)(rng.next_float() * n_cascades) % n_cascades;
+		uint32_t idx = 0;
+		for (uint32_t j = 0; j < 10; ++j) {
+			idx = ((i + step * n) * 56924617u + j * 19349663u + 96925573u) % G3;
+			idx += level * G3;
+			if (grid_in[idx] > thresh) break;
+		}
+		uint32_t pos_idx = idx % G3;
+		uint32_t x = morton3D_invert(pos_idx >> 0), y = morton3D_invert(pos_idx >> 1), z = morton3D_invert(pos_idx >> 2);
+		float r[3] = {rng.next_float(), rng.next_float(), rng.next_float()};
+		float c[3] = {(float)x, (float)y, (float)z};
+		for (int k = 0; k < 3; ++k) {
+			float p = ((c[k] + r[k]) / (float)GRIDSIZE - 0.5f) * scalbnf(1.0f, (int)level) + 0.5f;
+			positions[(size_t)i * 3 + k] = (p - bmin[k]) / (bmax[k] - bmin[k]);
+		}
+		indices[i] = idx;
+	}
+}
+// splat (atomicMax on float bits, :671-690) + ema_grid_samples_nerf (:710-740)
+void orc_splat_and_decay(uint32_t n_samples, const uint32_t* indices, const h16* density, uint32_t n_elements, float decay, float* grid_tmp, float* grid) {
+	for (uint32_t i = 0; i < n_elements; ++i) grid_tmp[i] = 0.f;
+	for (uint32_t i = 0; i < n_samples; ++i) {
+		float v = h2f(density[i]);
+		uint32_t a, b; std::memcpy(&a, &grid_tmp[indices[i]], 4); std::memcpy(&b, &v, 4);
+		if (b > a) grid_tmp[indices[i]] = v;
+	}
+	for (uint32_t i = 0; i < n_elements; ++i) {
+		float prev = grid[i];
+		grid[i] = (prev < 0.f) ? prev : fmaxf(prev * decay, grid_tmp[i]);
+	}
+}
+// update_density_grid_mean_and_bitfield (:3377-3397): mean over cascade 0, grid_to_bitfield (:748-772), max-pool mips (:774-795).
+// bitfield: GRIDSIZE^3/8 * NERF_CASCADES bytes.  Returns the mean (fp32 sum order: ascending index, double-free).
+float orc_update_bitfield(const float* grid, uint32_t n_cascades_used, uint8_t* bitfield) {
+	const uint32_t G3 = GRIDSIZE * GRIDSIZE * GRIDSIZE;
+	double acc = 0;   // the reference reduces in fp32 with an unspecified tree order; tests compare with tolerance
+	for (uint32_t i = 0; i < G3; ++i) acc += (double)(fmaxf(grid[i], 0.f) / (float)G3);
+	float mean = (float)acc;
+	float thresh = std::min(0.1f, mean);   // NERF_MIN_OPTICAL_THICKNESS :75, :764
+	const uint32_t n_bytes = G3 / 8 * NERF_CASCADES, n_nonzero = G3 / 8 * n_cascades_used;
+	for (uint32_t i = 0; i < n_bytes; ++i) {
+		if (i >= n_nonzero) { bitfield[i] = 0; continue; }
+		uint8_t bits = 0;
+		for (uint8_t j = 0; j < 8; ++j) bits |= grid[i * 8 + j] > thresh ? ((uint8_t)1 << j) : 0;
+		bitfield[i] = bits;
+	}
+	for (uint32_t level = 1; level < NERF_CASCADES; ++level) {
+		const uint8_t* prev = bitfield + (size_t)G3 / 8 * (level - 1);
+		uint8_t* next = bitfield + (size_t)G3 / 8 * level;
+		for (uint32_t i = 0; i < G3 / 64; ++i) {
+			uint8_t bits = 0;
+			for (uint8_t j = 0; j < 8; ++j) bits |= prev[i * 8 + j] > 0 ? ((uint8_t)1 << j) : 0;
+			uint32_t x = morton3D_invert(i >> 0) + GRIDSIZE / 8;
+			uint32_t y = morton3D_invert(i >> 1) + GRIDSIZE / 8;
+			uint32_t z = morton3D_invert(i >> 2) + GRIDSIZE / 8;
+			// next_level[morton3D(x,y,z)] |= bits  -- indexes BYTES with a cell-level morton code (reference as written)
+			next[morton3D(x, y, z)] |= bits;
+		}
+	}
+	return mean;
+}
+
+}  // extern "C"
