@@ -1,0 +1,144 @@
+/* neus2_b200.h -- C ABI of the B200-native NeuS2 training / rendering hot path.
+ *
+ * Drop-in boundary for the path the reference drives through
+ *   tcnn::DifferentiableObject<float, half, half> as implemented by NerfNetwork<half>
+ *   (dependencies/my_tcnn/include/tiny-cuda-nn/object.h:96-303, include/neural-graphics-primitives/nerf_network.h:100-145,330)
+ * and its callers in Testbed (src/testbed_nerf.cu:3293-3397, 3440-4001; src/testbed.cu:2640-2740).
+ *
+ * Conventions: every function returns 0 on success, non-zero on failure (message via neus2_last_error());
+ * nothing throws across the ABI.  Pointers named *_dev are CUDA device pointers on the context's device,
+ * *_host are host pointers.  All work is enqueued on the caller's stream (a cudaStream_t passed as void*,
+ * NULL = default stream); functions that return host values synchronise that stream themselves.
+ * Matrices use the reference's layouts: network input = NerfCoordinate AoS, 7 floats (nerf.h:76-102);
+ * network output = 16 halves per sample AoS (nerf_network.h:935; [0..2] rgb logits, [3] sdf, [4..6] d sdf/dx,
+ * [7] variance, [8..10] warped view dir).  Parameters live in ONE contiguous buffer in the reference order
+ * [sdf-MLP | colour-MLP | hash grid | variance(4)] (nerf_network.h:741-785).
+ */
+#ifndef NEUS2_B200_H
+#define NEUS2_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct neus2_ctx neus2_ctx;
+
+/* Mirrors the keys of configs/nerf/base.json that the hot path consumes (src/testbed.cu:2084-2199). */
+typedef struct neus2_config {
+	/* "encoding" */
+	uint32_t n_levels;               /* 14 */
+	uint32_t log2_hashmap_size;      /* 19 */
+	uint32_t base_resolution;        /* 16 */
+	float top_resolution;            /* 2048 */
+	float per_level_scale;           /* 0 = derive: exp(log(top*aabb/base)/(L-1)), testbed.cu:2175-2185 */
+	float valid_level_scale;         /* 0.02  progressive levels, grid.h:2427-2440 */
+	float base_valid_level_scale;    /* 0.2 */
+	uint32_t base_training_step;     /* 100 */
+	/* "network" / "rgb_network": 64 wide, ReLU, n_hidden_layers 1 / 2 (fixed shape of this build) */
+	float sdf_bias;                  /* -0.1, nerf_network.h:87 */
+	/* "optimizer" (Ema{ExponentialDecay{Adam}}) */
+	float learning_rate;             /* 1e-3 */
+	float beta1, beta2, epsilon;     /* 0.9, 0.99, 1e-15 */
+	float l2_reg;                    /* 1e-6 */
+	float ema_decay;                 /* 0.95 */
+	/* "hyperparams" */
+	float mask_loss_weight;          /* 0.0 */
+	float ek_loss_weight;            /* 0.01 */
+	int32_t anneal_end;              /* 0 -> cos_anneal_ratio = 1 */
+	uint32_t batch_size;             /* 1<<18 (testbed.cu:2120) */
+	/* dataset / testbed */
+	int32_t aabb_scale;              /* 1 */
+	uint32_t seed;                   /* 1337 (testbed.h:524) */
+	int32_t random_bg_color;         /* 1 (nerf.training.random_bg_color) */
+	int32_t snap_to_pixel_centers;   /* 1 (testbed.h:623) */
+	float background_color[3];       /* used when random_bg_color == 0 */
+	float density_grid_decay;        /* 0.95 (testbed.h:644) */
+	float loss_scale;                /* 128 (LOSS_SCALE) */
+} neus2_config;
+
+typedef struct neus2_step_stats {
+	uint32_t training_step;              /* after the step */
+	uint32_t rays_per_batch;             /* rays traced this step (global) */
+	uint32_t rays_per_batch_next;        /* adapted value for the next step (testbed_nerf.cu:3434-3435) */
+	uint32_t n_rays_kept;                /* rays with >0 samples that fit */
+	uint32_t measured_batch_size_before_compaction;  /* N_u */
+	uint32_t measured_batch_size;        /* compacted sample count (un-clamped) */
+	float loss, ek_loss, mask_loss;      /* valid when loss_valid (refreshed every 16 steps, testbed.cu:2714) */
+	int32_t loss_valid;
+	int32_t density_grid_updated;
+} neus2_step_stats;
+
+const char* neus2_last_error(void);
+void neus2_default_config(neus2_config* cfg);                       /* base.json values */
+
+/* Testbed::reset_network (src/testbed.cu:2084) for TestbedMode::Nerf: builds tables, allocates every buffer. */
+int neus2_ctx_create(const neus2_config* cfg, int device, neus2_ctx** out);
+void neus2_ctx_destroy(neus2_ctx* ctx);
+
+/* ParametricObject::n_params / layer sizes (object.h:60-94).  layout[8] = {sdf_in_width, off_W0, off_W1, off_C0, off_C1, off_C2, off_grid, off_variance}. */
+uint64_t neus2_n_params(const neus2_ctx* ctx);
+int neus2_param_layout(const neus2_ctx* ctx, uint32_t layout[8]);
+/* Grid level tables (grid.h:1472-1508): offsets[n_levels+1], resolutions[n_levels], scales[n_levels]. */
+int neus2_grid_tables(const neus2_ctx* ctx, uint32_t* offsets, uint32_t* resolutions, float* scales);
+/* Trainer-owned buffers (trainer.h:72-109): fp32 master, fp16 params, fp16 EMA ("inference") params, gradients (fp32 here). */
+int neus2_buffers(neus2_ctx* ctx, float** master_dev, void** params_f16_dev, void** ema_f16_dev, float** grads_f32_dev);
+
+/* Trainer::initialize_params (trainer.h:70-108) + NerfNetwork::initialize_params (nerf_network.h:815-905): same RNG
+ * stream as the reference.  sdf_mlp_weights_host: contents of utils/mlp_weights_hidden_layer_num_1_hidden_size_32.txt
+ * (3072 floats, row-major [out][in], first layer then last; nerf_network.h:787-813) or NULL to generate the geometric
+ * init (dependencies/my_tcnn/scripts/geometry_init_save_weights.py:292-389). */
+int neus2_init_params(neus2_ctx* ctx, const float* sdf_mlp_weights_host);
+/* Trainer::set_params_full_precision: upload n fp32 params, cast to fp16; reset=1 also zeroes Adam/EMA state. */
+int neus2_set_params(neus2_ctx* ctx, const float* master_host, uint64_t n, int reset_optimizer);
+int neus2_get_params(neus2_ctx* ctx, float* master_host, uint64_t n);
+
+/* Encoding::set_training_step (grid.h:2427-2440). */
+int neus2_set_training_step(neus2_ctx* ctx, int32_t step);
+
+/* NerfNetwork::inference_mixed_precision_impl (nerf_network.h:100-103): coords [n][7] float -> out [n][16] half. */
+int neus2_forward(neus2_ctx* ctx, void* stream, const float* coords_dev, uint32_t n, void* out_f16_dev, int use_inference_params);
+/* NerfNetwork::sdf / ::density (nerf_network.h:656-739): pos [n][stride] float -> half [n]. */
+int neus2_sdf(neus2_ctx* ctx, void* stream, const float* pos_dev, uint32_t stride, uint32_t n, void* out_f16_dev, int as_density, int use_inference_params);
+/* NerfNetwork::forward + ::backward (nerf_network.h:145,330) with EGradientMode::Overwrite on the compacted batch:
+ * rows [0,n_rows) read source row i % n_in (fill_rollover, testbed_nerf.cu:3922-3930); gradients land in grads_f32. */
+int neus2_backward(neus2_ctx* ctx, void* stream, const float* coords_dev, const void* dL_dout_f16_dev, const uint32_t* n_in_dev,
+                   uint32_t n_rows, uint32_t indeed_batch_size);
+/* Trainer::optimizer_step (trainer.h:170): fused Adam + EMA (adam.h:52-160, ema.h:64-77). */
+int neus2_optimizer_step(neus2_ctx* ctx, void* stream, float loss_scale);
+
+/* Training data (NerfDataset, nerf_loader.h): n RGBA8 images of one resolution, per-image focal length (pixels),
+ * principal point (relative), camera-to-world 3x4 row-major in ngp convention (nerf_matrix_to_ngp already applied). */
+int neus2_set_dataset(neus2_ctx* ctx, uint32_t n_images, int32_t width, int32_t height, const uint8_t* pixels_host,
+                      const float* focal_host, const float* principal_host, const float* xforms_host);
+
+/* Testbed::update_density_grid_nerf via training_prep_nerf (testbed_nerf.cu:3293-3397, 4003-4016). */
+int neus2_update_density_grid(neus2_ctx* ctx, void* stream);
+
+/* Testbed::train(batch) for one step (src/testbed.cu:2640-2740 -> testbed_nerf.cu:3440-4001), split so that a
+ * data-parallel caller can all-reduce grads_f32 between the halves:
+ *   begin: progressive level, occupancy refresh, sample generation for global rays [ray_offset, ray_offset+n_local)
+ *          of this step's rays_per_batch, forward, loss, backward on n_rows_local compacted rows.
+ *   end:   optimizer step, counters read-back, rays_per_batch adaptation, rng advance.
+ * world_size = 1: ray_offset = 0, n_local = 0 (= all rays), n_rows_local = 0 (= batch_size). */
+int neus2_train_step_begin(neus2_ctx* ctx, void* stream, uint32_t rank, uint32_t world_size);
+/* counts_global: {kept rays, N_u, compacted} summed over ranks (NULL = use the local counts). */
+int neus2_train_step_end(neus2_ctx* ctx, void* stream, const uint32_t* counts_global_host, neus2_step_stats* stats);
+int neus2_local_counts(neus2_ctx* ctx, void* stream, uint32_t counts_host[3]);
+/* convenience: begin + end on one GPU */
+int neus2_train_step(neus2_ctx* ctx, void* stream, neus2_step_stats* stats);
+
+/* Test / integration access to the step's device buffers by name: "numsteps_all", "ray_indices", "rays", "numsteps",
+ * "coords", "mlp_out", "coords_compacted", "dloss", "loss", "ek_loss", "mask_loss", "counters", "density_grid",
+ * "bitfield", "density_grid_mean". */
+int neus2_debug_buffer(neus2_ctx* ctx, const char* name, void** ptr_dev, uint64_t* n_bytes);
+/* Testbed state the drivers read (python_api.cu:317-471): training_step, rays_per_batch, rng state. */
+int neus2_get_state(neus2_ctx* ctx, uint32_t* training_step, uint32_t* rays_per_batch, uint64_t rng_state[2]);
+int neus2_set_state(neus2_ctx* ctx, uint32_t training_step, uint32_t rays_per_batch, uint32_t n_rays_total, uint32_t measured_before_compaction);
+int neus2_set_bitfield(neus2_ctx* ctx, const uint8_t* bitfield_host, uint64_t n_bytes);
+/* number of kernels this library launched on the context since creation (bench.py's gpu_launches) */
+uint64_t neus2_launch_count(const neus2_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

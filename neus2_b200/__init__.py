@@ -1,0 +1,203 @@
+"""neus2_b200 -- B200-native (sm_100a) NeuS2 training / rendering hot path.
+
+Python is a thin host mirror of the C ABI (include/neus2_b200.h); the compute lives in
+neus2_b200/libneus2_b200.so (hand-written CUDA).  PyTorch is used for device memory, streams and
+torch.distributed only.  There is no CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import Config, Neus2Error, StepStats, check, load, LIB_PATH  # noqa: F401
+
+__all__ = ["Config", "Context", "Neus2Error", "StepStats", "default_config"]
+
+
+def default_config(**overrides):
+    cfg = Config()
+    load().neus2_default_config(C.byref(cfg))
+    for k, v in overrides.items():
+        if k == "background_color":
+            for i in range(3):
+                cfg.background_color[i] = float(v[i])
+        else:
+            setattr(cfg, k, v)
+    return cfg
+
+
+class _DevArray:
+    """Exposes a raw device pointer through __cuda_array_interface__ so torch can view it without a copy."""
+
+    def __init__(self, ptr, shape, typestr, owner):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3, "strides": None}
+        self._owner = owner
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(stream):
+    if stream is None:
+        return C.c_void_p(_torch().cuda.current_stream().cuda_stream)
+    return C.c_void_p(stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream))
+
+
+class Context:
+    """One NeuS2 model + trainer state on one GPU (the reference's Testbed in Nerf mode + Trainer + NerfNetwork)."""
+
+    def __init__(self, cfg=None, device=0):
+        self._lib = load()
+        self.cfg = cfg if cfg is not None else default_config()
+        self.device = device
+        h = C.c_void_p()
+        check(self._lib.neus2_ctx_create(C.byref(self.cfg), C.c_int(device), C.byref(h)))
+        self._h = h
+        self.n_params = int(self._lib.neus2_n_params(self._h))
+        lay = (C.c_uint32 * 8)()
+        check(self._lib.neus2_param_layout(self._h, lay))
+        self.layout = dict(zip(["sdf_in", "W0", "W1", "C0", "C1", "C2", "grid", "variance"], [int(x) for x in lay]))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.neus2_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- tables / buffers --------------------------------------------------------------------
+    def grid_tables(self):
+        L = self.cfg.n_levels
+        off = np.zeros(L + 1, dtype=np.uint32)
+        res = np.zeros(L, dtype=np.uint32)
+        sc = np.zeros(L, dtype=np.float32)
+        check(self._lib.neus2_grid_tables(self._h, off.ctypes.data_as(C.c_void_p), res.ctypes.data_as(C.c_void_p), sc.ctypes.data_as(C.c_void_p)))
+        return off, res, sc
+
+    def buffers(self):
+        """(master fp32, params fp16, ema fp16, grads fp32) as zero-copy torch views of the context's device buffers."""
+        torch = _torch()
+        m, p, e, g = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(self._lib.neus2_buffers(self._h, C.byref(m), C.byref(p), C.byref(e), C.byref(g)))
+        dev = f"cuda:{self.device}"
+        n = self.n_params
+        return (torch.as_tensor(_DevArray(m.value, (n,), "<f4", self), device=dev), torch.as_tensor(_DevArray(p.value, (n,), "<f2", self), device=dev),
+                torch.as_tensor(_DevArray(e.value, (n,), "<f2", self), device=dev), torch.as_tensor(_DevArray(g.value, (n,), "<f4", self), device=dev))
+
+    def debug_buffer(self, name, typestr, shape):
+        torch = _torch()
+        p, nb = C.c_void_p(), C.c_uint64()
+        check(self._lib.neus2_debug_buffer(self._h, name.encode(), C.byref(p), C.byref(nb)))
+        count = int(np.prod(shape))
+        assert count * int(typestr[-1]) <= nb.value, (name, shape, nb.value)
+        return torch.as_tensor(_DevArray(p.value, shape, typestr, self), device=f"cuda:{self.device}")
+
+    # ---- parameters --------------------------------------------------------------------------
+    def init_params(self, sdf_mlp_weights=None):
+        w = None
+        if sdf_mlp_weights is not None:
+            w = np.ascontiguousarray(sdf_mlp_weights, dtype=np.float32)
+            assert w.size == 64 * 32 + 16 * 64
+        check(self._lib.neus2_init_params(self._h, w.ctypes.data_as(C.c_void_p) if w is not None else None))
+
+    def set_params(self, master, reset_optimizer=True):
+        m = np.ascontiguousarray(master, dtype=np.float32)
+        check(self._lib.neus2_set_params(self._h, m.ctypes.data_as(C.c_void_p), C.c_uint64(m.size), C.c_int(1 if reset_optimizer else 0)))
+
+    def get_params(self):
+        m = np.empty(self.n_params, dtype=np.float32)
+        check(self._lib.neus2_get_params(self._h, m.ctypes.data_as(C.c_void_p), C.c_uint64(m.size)))
+        return m
+
+    def set_training_step(self, step):
+        check(self._lib.neus2_set_training_step(self._h, C.c_int32(step)))
+
+    # ---- operators ---------------------------------------------------------------------------
+    def forward(self, coords, out=None, use_inference_params=False, stream=None):
+        torch = _torch()
+        assert coords.dtype == torch.float32 and coords.is_contiguous() and coords.shape[1] == 7
+        n = coords.shape[0]
+        if out is None:
+            out = torch.empty((n, 16), dtype=torch.float16, device=coords.device)
+        check(self._lib.neus2_forward(self._h, _stream(stream), _ptr(coords), C.c_uint32(n), _ptr(out), C.c_int(int(use_inference_params))))
+        return out
+
+    def sdf(self, pos, as_density=False, use_inference_params=False, stream=None):
+        torch = _torch()
+        assert pos.dtype == torch.float32 and pos.is_contiguous()
+        n, stride = pos.shape
+        out = torch.empty((n,), dtype=torch.float16, device=pos.device)
+        check(self._lib.neus2_sdf(self._h, _stream(stream), _ptr(pos), C.c_uint32(stride), C.c_uint32(n), _ptr(out), C.c_int(int(as_density)),
+                                  C.c_int(int(use_inference_params))))
+        return out
+
+    def backward(self, coords, dL_dout, n_in, n_rows, indeed_batch_size, stream=None):
+        torch = _torch()
+        assert coords.dtype == torch.float32 and dL_dout.dtype == torch.float16
+        n_in_dev = torch.tensor([n_in], dtype=torch.int32, device=coords.device)
+        check(self._lib.neus2_backward(self._h, _stream(stream), _ptr(coords), _ptr(dL_dout), _ptr(n_in_dev), C.c_uint32(n_rows), C.c_uint32(indeed_batch_size)))
+        return self.buffers()[3]
+
+    def optimizer_step(self, loss_scale=128.0, stream=None):
+        check(self._lib.neus2_optimizer_step(self._h, _stream(stream), C.c_float(loss_scale)))
+
+    # ---- training ----------------------------------------------------------------------------
+    def set_dataset(self, pixels, focal, principal, xforms):
+        px = np.ascontiguousarray(pixels, dtype=np.uint8)
+        assert px.ndim == 4 and px.shape[3] == 4
+        f = np.ascontiguousarray(focal, dtype=np.float32)
+        pp = np.ascontiguousarray(principal, dtype=np.float32)
+        x = np.ascontiguousarray(xforms, dtype=np.float32)
+        n, h, w, _ = px.shape
+        assert f.shape == (n, 2) and pp.shape == (n, 2) and x.shape == (n, 3, 4)
+        check(self._lib.neus2_set_dataset(self._h, C.c_uint32(n), C.c_int32(w), C.c_int32(h), px.ctypes.data_as(C.c_void_p),
+                                          f.ctypes.data_as(C.c_void_p), pp.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p)))
+
+    def update_density_grid(self, stream=None):
+        check(self._lib.neus2_update_density_grid(self._h, _stream(stream)))
+
+    def train_step_begin(self, rank=0, world_size=1, stream=None):
+        check(self._lib.neus2_train_step_begin(self._h, _stream(stream), C.c_uint32(rank), C.c_uint32(world_size)))
+
+    def local_counts(self, stream=None):
+        c = (C.c_uint32 * 3)()
+        check(self._lib.neus2_local_counts(self._h, _stream(stream), c))
+        return [int(x) for x in c]
+
+    def train_step_end(self, counts_global=None, stream=None):
+        st = StepStats()
+        cg = None
+        if counts_global is not None:
+            cg = (C.c_uint32 * 3)(*[int(x) for x in counts_global])
+        check(self._lib.neus2_train_step_end(self._h, _stream(stream), cg, C.byref(st)))
+        return st
+
+    def train_step(self, stream=None):
+        st = StepStats()
+        check(self._lib.neus2_train_step(self._h, _stream(stream), C.byref(st)))
+        return st
+
+    def get_state(self):
+        ts, rpb = C.c_uint32(), C.c_uint32()
+        rng = (C.c_uint64 * 2)()
+        check(self._lib.neus2_get_state(self._h, C.byref(ts), C.byref(rpb), rng))
+        return dict(training_step=ts.value, rays_per_batch=rpb.value, rng_state=(int(rng[0]), int(rng[1])))
+
+    def set_state(self, training_step, rays_per_batch, n_rays_total=0, measured_before=0):
+        check(self._lib.neus2_set_state(self._h, C.c_uint32(training_step), C.c_uint32(rays_per_batch), C.c_uint32(n_rays_total), C.c_uint32(measured_before)))
+
+    def set_bitfield(self, bitfield):
+        b = np.ascontiguousarray(bitfield, dtype=np.uint8)
+        check(self._lib.neus2_set_bitfield(self._h, b.ctypes.data_as(C.c_void_p), C.c_uint64(b.size)))
+
+    def launch_count(self):
+        return int(self._lib.neus2_launch_count(self._h))

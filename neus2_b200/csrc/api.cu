@@ -1,0 +1,526 @@
+// api.cu -- context, buffers and the C ABI declared in include/neus2_b200.h.
+// Host-side restatement of the Testbed/Trainer plumbing around the hot path:
+//   reset_network (src/testbed.cu:2084-2349), Trainer::initialize_params (tcnn trainer.h:70-108),
+//   NerfNetwork::initialize_params (nerf_network.h:815-905), Testbed::train (testbed.cu:2640-2740),
+//   train_nerf / train_nerf_step (testbed_nerf.cu:3440-4001), update_density_grid_nerf (:3293-3397),
+//   Counters::update_after_training (:3412-3438).
+#include "../../include/neus2_b200.h"
+#include "kernels.h"
+#include "ngp_kernels.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+static thread_local std::string g_error;
+unsigned long long g_neus_launches = 0;
+void neus_set_error(const char* msg, const char* file, int line) {
+	char buf[512];
+	snprintf(buf, sizeof(buf), "%s (%s:%d)", msg, file, line);
+	g_error = buf;
+}
+#define FAIL(msg) do { neus_set_error(msg, __FILE__, __LINE__); return -1; } while (0)
+#define CHECK(x) do { if ((x) != 0) return -1; } while (0)
+
+struct neus2_ctx {
+	neus2_config cfg;
+	int device;
+	GridMeta gm;
+	ParamLayout pl;
+	uint64_t n_params;
+	uint32_t B;                 // target batch size
+	uint32_t max_rays;          // 1<<18
+	uint32_t max_samples;       // 16*B
+	uint32_t n_cascades;        // max_cascade + 1
+	Aabb aabb;
+	GlobalMove gmv;
+	float cone_angle_constant;
+
+	// Trainer buffers
+	float* master; __half* params; __half* ema; float* grads; float* m1; float* m2; uint32_t* steps;
+	uint32_t adam_step;
+
+	// dataset
+	DatasetDev ds; uint8_t* d_pixels; float* d_focal; float* d_principal; float* d_xforms;
+
+	// training scratch
+	uint32_t *numsteps_all, *base, *slot, *ray_indices, *numsteps, *scan_tmp, *counters;
+	float *rays, *coords, *ray_tmp, *coords_compacted, *loss, *ek_loss, *mask_loss;
+	__half *mlp_out, *dloss;
+	StagedOperands so;
+	float *partials, *var_acc, *w1row0_acc, *scalar_tmp;
+
+	// occupancy grid
+	float *density_grid, *density_grid_tmp, *grid_positions, *density_grid_mean;
+	uint32_t* grid_indices; __half* grid_density; uint8_t* bitfield;
+	uint32_t density_grid_ema_step;
+
+	// Testbed state
+	Pcg32 rng, density_grid_rng;
+	uint32_t training_step, rays_per_batch, n_rays_total, measured_before;
+	uint32_t step_rays, step_rays_local, step_n_rays_total;   // of the step in flight
+	bool step_density_updated;
+	uint32_t* h_counters;       // pinned
+	float* h_scalars;           // pinned
+};
+
+static int dmalloc(void** p, size_t bytes) {
+	CUDA_CHECK(cudaMalloc(p, bytes));
+	CUDA_CHECK(cudaMemset(*p, 0, bytes));
+	return 0;
+}
+#define DMALLOC(ptr, count) CHECK(dmalloc((void**)&(ptr), sizeof(*(ptr)) * (size_t)(count)))
+
+extern "C" {
+
+const char* neus2_last_error(void) { return g_error.c_str(); }
+
+void neus2_default_config(neus2_config* c) {
+	memset(c, 0, sizeof(*c));
+	c->n_levels = 14; c->log2_hashmap_size = 19; c->base_resolution = 16; c->top_resolution = 2048.f; c->per_level_scale = 0.f;
+	c->valid_level_scale = 0.02f; c->base_valid_level_scale = 0.2f; c->base_training_step = 100;
+	c->sdf_bias = -0.1f;
+	c->learning_rate = 1e-3f; c->beta1 = 0.9f; c->beta2 = 0.99f; c->epsilon = 1e-15f; c->l2_reg = 1e-6f; c->ema_decay = 0.95f;
+	c->mask_loss_weight = 0.f; c->ek_loss_weight = 0.01f; c->anneal_end = 0; c->batch_size = 1u << 18;
+	c->aabb_scale = 1; c->seed = 1337; c->random_bg_color = 1; c->snap_to_pixel_centers = 1;
+	c->background_color[0] = c->background_color[1] = c->background_color[2] = 0.f;
+	c->density_grid_decay = 0.95f; c->loss_scale = 128.f;
+}
+
+static int build_tables(neus2_ctx* ctx) {
+	const neus2_config& c = ctx->cfg;
+	if (c.n_levels < 1 || c.n_levels > NEUS_MAX_LEVELS) FAIL("n_levels out of range (1..16)");
+	if (3 + 2 * c.n_levels > 32) FAIL("this build fixes the sdf-MLP input width at 32: need 3 + 2*n_levels <= 32");
+	float pls = c.per_level_scale;
+	if (pls <= 0.f && c.n_levels > 1) pls = std::exp(std::log(c.top_resolution * (float)c.aabb_scale / (float)c.base_resolution) / (c.n_levels - 1));   // testbed.cu:2181
+	if (pls <= 0.f) pls = 1.f;
+	GridMeta& gm = ctx->gm;
+	memset(&gm, 0, sizeof(gm));
+	gm.n_levels = c.n_levels;
+	gm.valid_level = c.n_levels;
+	uint32_t offset = 0;
+	for (uint32_t i = 0; i < c.n_levels; ++i) {   // grid.h:1472-1505
+		const float scale = exp2f(i * std::log2(pls)) * c.base_resolution - 1.0f;
+		const uint32_t resolution = (uint32_t)(ceilf(scale)) + 1;
+		gm.scale[i] = (float)(resolution - 1);
+		gm.res[i] = resolution;
+		const uint32_t max_params = std::numeric_limits<uint32_t>::max() / 2;
+		uint32_t params_in_level = std::pow((float)resolution, 3) > (float)max_params ? max_params : resolution * resolution * resolution;
+		params_in_level = (params_in_level + 7u) / 8u * 8u;
+		params_in_level = std::min(params_in_level, (1u << c.log2_hashmap_size));
+		gm.offset[i] = offset;
+		offset += params_in_level;
+	}
+	gm.offset[c.n_levels] = offset;
+	ParamLayout& pl = ctx->pl;
+	pl.sdf_in_w = 32;
+	pl.off_w0 = 0; pl.off_w1 = 64 * 32;
+	pl.off_c0 = pl.off_w1 + 16 * 64; pl.off_c1 = pl.off_c0 + 64 * 48; pl.off_c2 = pl.off_c1 + 64 * 64;
+	pl.off_grid = pl.off_c2 + 16 * 64;
+	pl.off_var = pl.off_grid + offset * 2;
+	pl.n_params = pl.off_var + 4;
+	ctx->n_params = pl.n_params;
+	return 0;
+}
+
+int neus2_ctx_create(const neus2_config* cfg, int device, neus2_ctx** out) {
+	if (!cfg || !out) FAIL("null argument");
+	CUDA_CHECK(cudaSetDevice(device));
+	neus2_ctx* ctx = new neus2_ctx();
+	memset(ctx, 0, sizeof(*ctx));
+	ctx->cfg = *cfg;
+	ctx->device = device;
+	if (build_tables(ctx)) { delete ctx; return -1; }
+	ctx->B = cfg->batch_size;
+	if (ctx->B == 0 || ctx->B % 128 != 0) { delete ctx; FAIL("batch_size must be a positive multiple of 128 (tcnn batch_size_granularity)"); }
+	ctx->max_rays = 1u << 18;
+	ctx->max_samples = ctx->B * 16;
+	uint32_t max_cascade = 0;
+	while ((1 << max_cascade) < cfg->aabb_scale) ++max_cascade;
+	ctx->n_cascades = max_cascade + 1;
+	const float half_ext = 0.5f * std::min(1 << (NERF_CASCADES - 1), cfg->aabb_scale);   // testbed_nerf.cu:3075-3076
+	for (int k = 0; k < 3; ++k) { ctx->aabb.mn[k] = 0.5f - half_ext; ctx->aabb.mx[k] = 0.5f + half_ext; }
+	ctx->cone_angle_constant = cfg->aabb_scale <= 1 ? 0.0f : (1.0f / 256.0f);            // :3090
+	const float I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+	memcpy(ctx->gmv.R, I, sizeof(I));
+
+	const uint64_t N = ctx->n_params;
+	const uint32_t B = ctx->B, R = ctx->max_rays, S = ctx->max_samples;
+	#define CTXCHECK(x) do { if ((x) != 0) { neus2_ctx_destroy(ctx); return -1; } } while (0)
+	#define CDM(ptr, count) CTXCHECK(dmalloc((void**)&(ptr), sizeof(*(ptr)) * (size_t)(count)))
+	CDM(ctx->master, N); CDM(ctx->params, N); CDM(ctx->ema, N); CDM(ctx->grads, N); CDM(ctx->m1, N); CDM(ctx->m2, N); CDM(ctx->steps, N);
+	CDM(ctx->numsteps_all, R); CDM(ctx->base, R); CDM(ctx->slot, R); CDM(ctx->ray_indices, R); CDM(ctx->numsteps, 2 * (size_t)R); CDM(ctx->scan_tmp, 2 * (size_t)R);
+	CDM(ctx->counters, 8); CDM(ctx->rays, 6 * (size_t)R); CDM(ctx->coords, 7 * (size_t)S); CDM(ctx->ray_tmp, 12 * (size_t)R);
+	CDM(ctx->coords_compacted, 7 * (size_t)B); CDM(ctx->loss, R); CDM(ctx->ek_loss, R); CDM(ctx->mask_loss, R);
+	CDM(ctx->mlp_out, 16 * (size_t)S); CDM(ctx->dloss, 16 * (size_t)B);
+	CDM(ctx->so.dOUT, 16 * (size_t)B); CDM(ctx->so.H2, 64 * (size_t)B); CDM(ctx->so.dH2, 64 * (size_t)B); CDM(ctx->so.H1, 64 * (size_t)B); CDM(ctx->so.dH1, 64 * (size_t)B);
+	CDM(ctx->so.CIN, 48 * (size_t)B); CDM(ctx->so.dSO, 16 * (size_t)B); CDM(ctx->so.H0, 64 * (size_t)B); CDM(ctx->so.dH0, 64 * (size_t)B);
+	CDM(ctx->so.X0, 32 * (size_t)B); CDM(ctx->so.gH, 64 * (size_t)B); CDM(ctx->so.dI, 32 * (size_t)B);
+	CDM(ctx->partials, (size_t)weight_gradient_partials() * ctx->pl.off_grid); CDM(ctx->var_acc, 1); CDM(ctx->w1row0_acc, 64); CDM(ctx->scalar_tmp, 4);
+	const size_t G3n = (size_t)NERF_GRIDSIZE * NERF_GRIDSIZE * NERF_GRIDSIZE;
+	CDM(ctx->density_grid, G3n * ctx->n_cascades); CDM(ctx->density_grid_tmp, G3n * ctx->n_cascades);
+	CDM(ctx->grid_positions, 3 * G3n * ctx->n_cascades); CDM(ctx->grid_indices, G3n * ctx->n_cascades); CDM(ctx->grid_density, G3n * ctx->n_cascades);
+	CDM(ctx->bitfield, G3n / 8 * NERF_CASCADES); CDM(ctx->density_grid_mean, 1);
+	if (cudaMallocHost((void**)&ctx->h_counters, 8 * sizeof(uint32_t)) != cudaSuccess || cudaMallocHost((void**)&ctx->h_scalars, 4 * sizeof(float)) != cudaSuccess) {
+		neus2_ctx_destroy(ctx); FAIL("cudaMallocHost failed");
+	}
+	// reset_network state (testbed.cu:2087-2101)
+	ctx->rng = Pcg32(cfg->seed);
+	ctx->density_grid_rng = Pcg32(ctx->rng.next_uint());
+	(void)ctx->rng.next_uint();   // tv_loss_rng
+	ctx->rays_per_batch = 1u << 12;
+	ctx->measured_before = 0;
+	ctx->training_step = 0;
+	ctx->n_rays_total = 0;
+	*out = ctx;
+	return 0;
+}
+
+void neus2_ctx_destroy(neus2_ctx* ctx) {
+	if (!ctx) return;
+	void* ptrs[] = {ctx->master, ctx->params, ctx->ema, ctx->grads, ctx->m1, ctx->m2, ctx->steps, ctx->d_pixels, ctx->d_focal, ctx->d_principal, ctx->d_xforms,
+		ctx->numsteps_all, ctx->base, ctx->slot, ctx->ray_indices, ctx->numsteps, ctx->scan_tmp, ctx->counters, ctx->rays, ctx->coords, ctx->ray_tmp,
+		ctx->coords_compacted, ctx->loss, ctx->ek_loss, ctx->mask_loss, ctx->mlp_out, ctx->dloss, ctx->so.dOUT, ctx->so.H2, ctx->so.dH2, ctx->so.H1, ctx->so.dH1,
+		ctx->so.CIN, ctx->so.dSO, ctx->so.H0, ctx->so.dH0, ctx->so.X0, ctx->so.gH, ctx->so.dI, ctx->partials, ctx->var_acc, ctx->w1row0_acc, ctx->scalar_tmp,
+		ctx->density_grid, ctx->density_grid_tmp, ctx->grid_positions, ctx->grid_indices, ctx->grid_density, ctx->bitfield, ctx->density_grid_mean};
+	for (void* p : ptrs) if (p) cudaFree(p);
+	if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+	if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
+	delete ctx;
+}
+
+uint64_t neus2_n_params(const neus2_ctx* ctx) { return ctx->n_params; }
+
+int neus2_param_layout(const neus2_ctx* ctx, uint32_t layout[8]) {
+	const ParamLayout& p = ctx->pl;
+	layout[0] = p.sdf_in_w; layout[1] = p.off_w0; layout[2] = p.off_w1; layout[3] = p.off_c0; layout[4] = p.off_c1; layout[5] = p.off_c2;
+	layout[6] = p.off_grid; layout[7] = p.off_var;
+	return 0;
+}
+
+int neus2_grid_tables(const neus2_ctx* ctx, uint32_t* offsets, uint32_t* resolutions, float* scales) {
+	for (uint32_t i = 0; i <= ctx->gm.n_levels; ++i) offsets[i] = ctx->gm.offset[i];
+	for (uint32_t i = 0; i < ctx->gm.n_levels; ++i) { resolutions[i] = ctx->gm.res[i]; scales[i] = ctx->gm.scale[i]; }
+	return 0;
+}
+
+int neus2_buffers(neus2_ctx* ctx, float** master, void** params, void** ema, float** grads) {
+	if (master) *master = ctx->master;
+	if (params) *params = ctx->params;
+	if (ema) *ema = ctx->ema;
+	if (grads) *grads = ctx->grads;
+	return 0;
+}
+
+__global__ void k_cast_params(uint64_t n, const float* __restrict__ master, __half* __restrict__ params) {
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) params[i] = __float2half_rn(master[i]);
+}
+
+int neus2_set_params(neus2_ctx* ctx, const float* master_host, uint64_t n, int reset_optimizer) {
+	if (n != ctx->n_params) FAIL("parameter count mismatch");
+	CUDA_CHECK(cudaSetDevice(ctx->device));
+	CUDA_CHECK(cudaMemcpy(ctx->master, master_host, n * sizeof(float), cudaMemcpyHostToDevice));
+	k_cast_params<<<(uint32_t)((n + 255) / 256), 256>>>(n, ctx->master, ctx->params);
+	COUNT_LAUNCH(1);
+	CUDA_CHECK(cudaGetLastError());
+	if (reset_optimizer) {
+		CUDA_CHECK(cudaMemset(ctx->m1, 0, n * sizeof(float)));
+		CUDA_CHECK(cudaMemset(ctx->m2, 0, n * sizeof(float)));
+		CUDA_CHECK(cudaMemset(ctx->steps, 0, n * sizeof(uint32_t)));
+		CUDA_CHECK(cudaMemset(ctx->ema, 0, n * sizeof(__half)));
+		CUDA_CHECK(cudaMemset(ctx->grads, 0, n * sizeof(float)));
+		ctx->adam_step = 0;
+	}
+	CUDA_CHECK(cudaDeviceSynchronize());
+	return 0;
+}
+
+int neus2_get_params(neus2_ctx* ctx, float* master_host, uint64_t n) {
+	if (n != ctx->n_params) FAIL("parameter count mismatch");
+	CUDA_CHECK(cudaSetDevice(ctx->device));
+	CUDA_CHECK(cudaMemcpy(master_host, ctx->master, n * sizeof(float), cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+int neus2_init_params(neus2_ctx* ctx, const float* sdf_mlp_weights_host) {
+	const ParamLayout& pl = ctx->pl;
+	std::vector<float> p(ctx->n_params, 0.f);
+	// Trainer rng (trainer.h:56-59)
+	std::seed_seq seq{ctx->cfg.seed};
+	std::vector<uint32_t> seeds(2);
+	seq.generate(seeds.begin(), seeds.end());
+	Pcg32 rng{seeds.front()};
+	auto xavier = [&](float* dst, uint32_t fan_out, uint32_t fan_in) {   // gpu_matrix.h:292-307
+		float scale = 1.0f;
+		scale *= std::sqrt(6.0f / (float)(fan_in + fan_out));
+		for (uint32_t i = 0; i < fan_out * fan_in; ++i) dst[i] = rng.next_float() * 2.0f * scale - scale;
+	};
+	xavier(&p[pl.off_w0], 64, 32); xavier(&p[pl.off_w1], 16, 64);      // consumed, then overwritten (nerf_network.h:819-833)
+	if (sdf_mlp_weights_host) {
+		memcpy(&p[pl.off_w0], sdf_mlp_weights_host, sizeof(float) * (64 * 32 + 16 * 64));
+	} else {
+		// geometric init (geometry_init_save_weights.py:318-331) with our own generator (the reference file is not in the snapshot)
+		Pcg32 g{0x9e0u};
+		auto normal = [&]() {
+			float u1 = g.next_float(), u2 = g.next_float();
+			if (u1 < 1e-7f) u1 = 1e-7f;
+			return std::sqrt(-2.0f * std::log(u1)) * std::cos(6.283185307179586f * u2);
+		};
+		for (uint32_t o = 0; o < 64; ++o) for (uint32_t i = 0; i < 32; ++i) p[pl.off_w0 + o * 32 + i] = i < 3 ? normal() * (std::sqrt(2.0f) / std::sqrt(64.0f)) : 0.f;
+		for (uint32_t i = 0; i < 16 * 64; ++i) p[pl.off_w1 + i] = std::sqrt(3.14159265358979f) / std::sqrt(64.0f) + 1e-5f * normal();
+	}
+	xavier(&p[pl.off_c0], 64, 48); xavier(&p[pl.off_c1], 64, 64); xavier(&p[pl.off_c2], 16, 64);
+	{   // grid: generate_random_uniform(-1e-4, 1e-4) (grid.h:2375-2380; random.h:67-99)
+		const uint64_t n = (uint64_t)ctx->gm.offset[ctx->gm.n_levels] * 2;
+		const uint64_t n_threads = ((n + 3) / 4 + 127) / 128 * 128;
+		float* out = &p[pl.off_grid];
+		#pragma omp parallel for schedule(static)
+		for (int64_t i = 0; i < (int64_t)n_threads; ++i) {
+			Pcg32 r = rng; r.advance(i * 4);
+			for (uint64_t j = 0; j < 4; ++j) {
+				const uint64_t idx = (uint64_t)i + n_threads * j;
+				if (idx >= n) break;
+				out[idx] = fmaf(r.next_float(), 1e-4f - (-1e-4f), -1e-4f);
+			}
+		}
+		rng.advance((int64_t)n);
+	}
+	for (int k = 0; k < 4; ++k) p[pl.off_var + k] = 0.3f;   // nerf_network.h:897-899
+	return neus2_set_params(ctx, p.data(), ctx->n_params, 1);
+}
+
+int neus2_set_training_step(neus2_ctx* ctx, int32_t step) {   // grid.h:2427-2440
+	const neus2_config& c = ctx->cfg;
+	if (step <= 0) { ctx->gm.valid_level = c.n_levels; return 0; }
+	const uint32_t v = (uint32_t)ceil(c.base_valid_level_scale * c.n_levels + c.valid_level_scale * std::max(0, (int)(step - (int)c.base_training_step)));
+	ctx->gm.valid_level = std::min(c.n_levels, v);
+	return 0;
+}
+
+int neus2_forward(neus2_ctx* ctx, void* stream, const float* coords, uint32_t n, void* out, int use_inference_params) {
+	CUDA_CHECK(cudaSetDevice(ctx->device));
+	return launch_network_forward((cudaStream_t)stream, ctx->gm, ctx->pl, use_inference_params ? ctx->ema : ctx->params, coords, nullptr, n, ctx->cfg.sdf_bias, (__half*)out);
+}
+
+int neus2_sdf(neus2_ctx* ctx, void* stream, const float* pos, uint32_t stride, uint32_t n, void* out, int as_density, int use_inference_params) {
+	CUDA_CHECK(cudaSetDevice(ctx->device));
+	return launch_network_sdf((cudaStream_t)stream, ctx->gm, ctx->pl, use_inference_params ? ctx->ema : ctx->params, pos, stride, n, ctx->cfg.sdf_bias, as_density, (__half*)out, nullptr);
+}
+
+int neus2_backward(neus2_ctx* ctx, void* stream_, const float* coords, const void* dL_dout, const uint32_t* n_in_dev, uint32_t n_rows, uint32_t indeed_batch_size) {
+	cudaStream_t stream = (cudaStream_t)stream_;
+	CUDA_CHECK(cudaSetDevice(ctx->device));
+	if (n_rows > ctx->B) FAIL("n_rows exceeds the context's batch size");
+	CUDA_CHECK(cudaMemsetAsync(ctx->grads, 0, ctx->n_params * sizeof(float), stream));   // EGradientMode::Overwrite
+	CUDA_CHECK(cudaMemsetAsync(ctx->var_acc, 0, sizeof(float), stream));
+	CUDA_CHECK(cudaMemsetAsync(ctx->w1row0_acc, 0, 64 * sizeof(float), stream));
+	CHECK(launch_network_fwdbwd(stream, ctx->gm, ctx->pl, ctx->params, coords, (const __half*)dL_dout, n_in_dev, n_rows, ctx->cfg.sdf_bias, indeed_batch_size,
+	                            ctx->grads, ctx->var_acc, ctx->w1row0_acc, ctx->so));
+	CHECK(launch_weight_gradients(stream, ctx->pl, ctx->so, n_in_dev, n_rows, ctx->partials, weight_gradient_partials(), ctx->var_acc, ctx->w1row0_acc, ctx->grads));
+	return 0;
+}
+
+int neus2_optimizer_step(neus2_ctx* ctx, void* stream, float loss_scale) {
+	CUDA_CHECK(cudaSetDevice(ctx->device));
+	const neus2_config& c = ctx->cfg;
+	++ctx->adam_step;
+	return launch_adam_ema((cudaStream_t)stream, ctx->n_params, ctx->pl.off_grid, loss_scale, c.learning_rate, c.beta1, c.beta2, c.epsilon, c.l2_reg,
+	                       c.ema_decay, ctx->adam_step, ctx->grads, ctx->master, ctx->params, ctx->m1, ctx->m2, ctx->steps, ctx->ema);
+}
+
+int neus2_set_dataset(neus2_ctx* ctx, uint32_t n_images, int32_t width, int32_t height, const uint8_t* pixels, const float* focal, const float* principal, const float* xforms) {
+	CUDA_CHECK(cudaSetDevice(ctx->device));
+	if (!n_images || width <= 0 || height <= 0) FAIL("empty dataset");
+	if (ctx->d_pixels) { cudaFree(ctx->d_pixels); cudaFree(ctx->d_focal); cudaFree(ctx->d_principal); cudaFree(ctx->d_xforms); }
+	const size_t npx = (size_t)n_images * width * height * 4;
+	CUDA_CHECK(cudaMalloc((void**)&ctx->d_pixels, npx));
+	CUDA_CHECK(cudaMalloc((void**)&ctx->d_focal, n_images * 2 * sizeof(float)));
+	CUDA_CHECK(cudaMalloc((void**)&ctx->d_principal, n_images * 2 * sizeof(float)));
+	CUDA_CHECK(cudaMalloc((void**)&ctx->d_xforms, n_images * 12 * sizeof(float)));
+	CUDA_CHECK(cudaMemcpy(ctx->d_pixels, pixels, npx, cudaMemcpyHostToDevice));
+	CUDA_CHECK(cudaMemcpy(ctx->d_focal, focal, n_images * 2 * sizeof(float), cudaMemcpyHostToDevice));
+	CUDA_CHECK(cudaMemcpy(ctx->d_principal, principal, n_images * 2 * sizeof(float), cudaMemcpyHostToDevice));
+	CUDA_CHECK(cudaMemcpy(ctx->d_xforms, xforms, n_images * 12 * sizeof(float), cudaMemcpyHostToDevice));
+	ctx->ds.n_images = n_images; ctx->ds.width = width; ctx->ds.height = height;
+	ctx->ds.pixels = ctx->d_pixels; ctx->ds.focal = ctx->d_focal; ctx->ds.principal = ctx->d_principal; ctx->ds.xforms = ctx->d_xforms;
+	return 0;
+}
+
+int neus2_update_density_grid(neus2_ctx* ctx, void* stream_) {   // training_prep_nerf (:4003-4016) -> update_density_grid_nerf (:3293-3375)
+	cudaStream_t stream = (cudaStream_t)stream_;
+	CUDA_CHECK(cudaSetDevice(ctx->device));
+	const uint32_t G3n = NERF_GRIDSIZE * NERF_GRIDSIZE * NERF_GRIDSIZE;
+	const uint32_t n_elements = G3n * ctx->n_cascades;
+	uint32_t n_uniform, n_nonuniform;
+	if (ctx->training_step < 256) { n_uniform = G3n * ctx->n_cascades; n_nonuniform = 0; }
+	else { n_uniform = G3n / 4 * ctx->n_cascades; n_nonuniform = G3n / 4 * ctx->n_cascades; }
+	if (ctx->training_step == 0) {
+		ctx->density_grid_ema_step = 0;
+		CUDA_CHECK(cudaMemsetAsync(ctx->density_grid, 0, sizeof(float) * n_elements, stream));
+	}
+	uint64_t st[2] = {ctx->density_grid_rng.state, ctx->density_grid_rng.inc};
+	CHECK(launch_density_grid_samples(stream, n_uniform, st, ctx->density_grid_ema_step, ctx->aabb, ctx->density_grid, ctx->n_cascades, -0.01f,
+	                                  ctx->grid_positions, ctx->grid_indices));
+	ctx->density_grid_rng.advance();
+	st[0] = ctx->density_grid_rng.state;
+	CHECK(launch_density_grid_samples(stream, n_nonuniform, st, ctx->density_grid_ema_step, ctx->aabb, ctx->density_grid, ctx->n_cascades, 0.1f,
+	                                  ctx->grid_positions + (size_t)n_uniform * 3, ctx->grid_indices + n_uniform));
+	ctx->density_grid_rng.advance();
+	const uint32_t n = n_uniform + n_nonuniform;
+	// density with the TRAINING params (use_inference_params=false, :3366)
+	CHECK(launch_network_sdf(stream, ctx->gm, ctx->pl, ctx->params, ctx->grid_positions, 3, n, ctx->cfg.sdf_bias, 1, ctx->grid_density, nullptr));
+	CHECK(launch_density_grid_splat_decay(stream, n, ctx->grid_indices, ctx->grid_density, n_elements, ctx->cfg.density_grid_decay, ctx->density_grid_tmp, ctx->density_grid));
+	++ctx->density_grid_ema_step;
+	CHECK(launch_density_grid_bitfield(stream, ctx->density_grid, ctx->n_cascades, ctx->density_grid_mean, ctx->bitfield));
+	return 0;
+}
+
+int neus2_train_step_begin(neus2_ctx* ctx, void* stream_, uint32_t rank, uint32_t world_size) {
+	cudaStream_t stream = (cudaStream_t)stream_;
+	CUDA_CHECK(cudaSetDevice(ctx->device));
+	if (!ctx->d_pixels) FAIL("no training data: call neus2_set_dataset first");
+	if (world_size == 0 || rank >= world_size) FAIL("bad rank / world_size");
+	const neus2_config& c = ctx->cfg;
+	neus2_set_training_step(ctx, (int32_t)ctx->training_step);                          // testbed.cu:2651-2657
+	const uint32_t n_prep_to_skip = std::min(std::max(ctx->training_step / 16u, 1u), 16u);   // :2669
+	ctx->step_density_updated = false;
+	if (ctx->training_step % n_prep_to_skip == 0) { CHECK(neus2_update_density_grid(ctx, stream_)); ctx->step_density_updated = true; }
+
+	// Counters::prepare_for_training_steps (:3399-3410)
+	const uint32_t R = ctx->rays_per_batch;
+	CUDA_CHECK(cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(uint32_t), stream));
+	CUDA_CHECK(cudaMemsetAsync(ctx->loss, 0, sizeof(float) * R, stream));
+	CUDA_CHECK(cudaMemsetAsync(ctx->ek_loss, 0, sizeof(float) * R, stream));
+	CUDA_CHECK(cudaMemsetAsync(ctx->mask_loss, 0, sizeof(float) * R, stream));
+
+	// train_nerf_step (:3723-4001)
+	const uint32_t n_local = R / world_size, ray_offset = rank * n_local;
+	const uint32_t rows_local = ctx->B / world_size;
+	const uint32_t max_samples = ctx->max_samples;
+	uint32_t max_inference;
+	if (ctx->measured_before == 0) { ctx->measured_before = max_inference = max_samples; }
+	else { max_inference = (std::min(ctx->measured_before, max_samples) + 127u) / 128u * 128u; }   // :3770-3775
+	if (ctx->training_step == 0) ctx->n_rays_total = 0;                                  // :3785-3787
+	const uint32_t n_rays_total = ctx->n_rays_total;
+	ctx->n_rays_total += R;
+	ctx->step_rays = R; ctx->step_rays_local = n_local; ctx->step_n_rays_total = n_rays_total;
+	const uint64_t st[2] = {ctx->rng.state, ctx->rng.inc};
+	CHECK(launch_generate_training_samples(stream, n_local, ray_offset, R, n_rays_total, st, ctx->ds, ctx->aabb, ctx->gmv, ctx->bitfield, c.snap_to_pixel_centers,
+	                                       ctx->cone_angle_constant, max_inference, ctx->numsteps_all, ctx->base, ctx->slot, ctx->ray_indices, ctx->rays,
+	                                       ctx->numsteps, ctx->coords, ctx->counters));
+	CHECK(launch_network_forward(stream, ctx->gm, ctx->pl, ctx->params, ctx->coords, ctx->counters + 1, max_inference, c.sdf_bias, ctx->mlp_out));   // :3854
+	LossParamsDev lp;
+	lp.loss_scale = c.loss_scale; memcpy(lp.background_color, c.background_color, sizeof(lp.background_color));
+	lp.random_bg_color = c.random_bg_color; lp.snap_to_pixel_centers = c.snap_to_pixel_centers;
+	lp.mask_loss_weight = c.mask_loss_weight; lp.ek_loss_weight = c.ek_loss_weight;
+	lp.cos_anneal_ratio = c.anneal_end == 0 ? 1.0f : (float)std::min(1.0, (double)((float)ctx->training_step / c.anneal_end));   // nerf_network.h:1119-1128
+	CHECK(launch_compute_loss(stream, n_local, R, n_rays_total, st, ctx->ds, ctx->aabb, ctx->gmv, lp, rows_local, ctx->counters + 0, ctx->mlp_out, ctx->ray_indices,
+	                          ctx->rays, ctx->numsteps, ctx->coords, ctx->ray_tmp, ctx->scan_tmp, ctx->coords_compacted, ctx->dloss, ctx->loss, ctx->ek_loss,
+	                          ctx->mask_loss, ctx->counters + 2));
+	CHECK(neus2_backward(ctx, stream_, ctx->coords_compacted, ctx->dloss, ctx->counters + 2, rows_local, ctx->B));   // :3941-3946
+	return 0;
+}
+
+int neus2_local_counts(neus2_ctx* ctx, void* stream_, uint32_t counts[3]) {
+	cudaStream_t stream = (cudaStream_t)stream_;
+	CUDA_CHECK(cudaMemcpyAsync(ctx->h_counters, ctx->counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+	CUDA_CHECK(cudaStreamSynchronize(stream));
+	counts[0] = ctx->h_counters[0]; counts[1] = ctx->h_counters[1]; counts[2] = ctx->h_counters[2];
+	return 0;
+}
+
+int neus2_train_step_end(neus2_ctx* ctx, void* stream_, const uint32_t* counts_global, neus2_step_stats* stats) {
+	cudaStream_t stream = (cudaStream_t)stream_;
+	CUDA_CHECK(cudaSetDevice(ctx->device));
+	const neus2_config& c = ctx->cfg;
+	const bool get_loss_scalar = ctx->training_step % 16 == 0;                           // testbed.cu:2714
+	CHECK(neus2_optimizer_step(ctx, stream_, c.loss_scale));                             // testbed_nerf.cu:3503-3505
+	if (get_loss_scalar) {
+		CHECK(launch_reduce_sum(stream, ctx->loss, ctx->step_rays, ctx->scalar_tmp + 0));
+		CHECK(launch_reduce_sum(stream, ctx->ek_loss, ctx->step_rays, ctx->scalar_tmp + 1));
+		CHECK(launch_reduce_sum(stream, ctx->mask_loss, ctx->step_rays, ctx->scalar_tmp + 2));
+		CUDA_CHECK(cudaMemcpyAsync(ctx->h_scalars, ctx->scalar_tmp, 3 * sizeof(float), cudaMemcpyDeviceToHost, stream));
+	}
+	uint32_t counts[3];
+	CHECK(neus2_local_counts(ctx, stream_, counts));   // the one structurally required host sync per step (:3412-3416)
+	const uint32_t n_kept_local = counts[0];
+	if (counts_global) { counts[0] = counts_global[0]; counts[1] = counts_global[1]; counts[2] = counts_global[2]; }
+	++ctx->training_step;
+	ctx->rng.advance();                                                                  // :3996
+	neus2_step_stats s;
+	memset(&s, 0, sizeof(s));
+	s.training_step = ctx->training_step;
+	s.rays_per_batch = ctx->step_rays;
+	s.n_rays_kept = counts_global ? counts[0] : n_kept_local;
+	s.density_grid_updated = ctx->step_density_updated;
+	// Counters::update_after_training (:3412-3438)
+	if (counts[1] == 0 || counts[2] == 0) {
+		s.measured_batch_size = 0; s.measured_batch_size_before_compaction = 0;
+		ctx->measured_before = 0;
+	} else {
+		s.measured_batch_size_before_compaction = counts[1];
+		s.measured_batch_size = counts[2];
+		ctx->measured_before = counts[1];
+		if (get_loss_scalar) {
+			const float f = (float)counts[2] / (float)ctx->B;
+			s.loss = ctx->h_scalars[0] * f; s.ek_loss = ctx->h_scalars[1] * f; s.mask_loss = ctx->h_scalars[2] * f;
+			s.loss_valid = 1;
+		}
+		uint32_t rpb = (uint32_t)((float)ctx->rays_per_batch * (float)ctx->B / (float)counts[2]);
+		rpb = std::min((rpb + 127u) / 128u * 128u, 1u << 18);
+		ctx->rays_per_batch = rpb;
+	}
+	s.rays_per_batch_next = ctx->rays_per_batch;
+	if (stats) *stats = s;
+	return 0;
+}
+
+int neus2_train_step(neus2_ctx* ctx, void* stream, neus2_step_stats* stats) {
+	CHECK(neus2_train_step_begin(ctx, stream, 0, 1));
+	return neus2_train_step_end(ctx, stream, nullptr, stats);
+}
+
+int neus2_debug_buffer(neus2_ctx* ctx, const char* name, void** ptr, uint64_t* n_bytes) {
+	struct E { const char* n; void* p; uint64_t b; };
+	const uint64_t R = ctx->max_rays, S = ctx->max_samples, B = ctx->B;
+	const uint64_t G3n = (uint64_t)NERF_GRIDSIZE * NERF_GRIDSIZE * NERF_GRIDSIZE;
+	const E table[] = {
+		{"numsteps_all", ctx->numsteps_all, R * 4}, {"ray_indices", ctx->ray_indices, R * 4}, {"rays", ctx->rays, R * 24}, {"numsteps", ctx->numsteps, R * 8},
+		{"coords", ctx->coords, S * 28}, {"mlp_out", ctx->mlp_out, S * 32}, {"coords_compacted", ctx->coords_compacted, B * 28}, {"dloss", ctx->dloss, B * 32},
+		{"loss", ctx->loss, R * 4}, {"ek_loss", ctx->ek_loss, R * 4}, {"mask_loss", ctx->mask_loss, R * 4}, {"counters", ctx->counters, 32},
+		{"density_grid", ctx->density_grid, G3n * ctx->n_cascades * 4}, {"bitfield", ctx->bitfield, G3n / 8 * NERF_CASCADES}, {"density_grid_mean", ctx->density_grid_mean, 4},
+		{"grid_positions", ctx->grid_positions, G3n * ctx->n_cascades * 12}, {"grid_indices", ctx->grid_indices, G3n * ctx->n_cascades * 4},
+		{"grid_density", ctx->grid_density, G3n * ctx->n_cascades * 2},
+	};
+	for (const E& e : table) if (!strcmp(e.n, name)) { *ptr = e.p; if (n_bytes) *n_bytes = e.b; return 0; }
+	FAIL("unknown buffer name");
+}
+
+int neus2_get_state(neus2_ctx* ctx, uint32_t* training_step, uint32_t* rays_per_batch, uint64_t rng_state[2]) {
+	if (training_step) *training_step = ctx->training_step;
+	if (rays_per_batch) *rays_per_batch = ctx->rays_per_batch;
+	if (rng_state) { rng_state[0] = ctx->rng.state; rng_state[1] = ctx->rng.inc; }
+	return 0;
+}
+
+int neus2_set_state(neus2_ctx* ctx, uint32_t training_step, uint32_t rays_per_batch, uint32_t n_rays_total, uint32_t measured_before) {
+	ctx->training_step = training_step; ctx->rays_per_batch = rays_per_batch; ctx->n_rays_total = n_rays_total; ctx->measured_before = measured_before;
+	return 0;
+}
+
+int neus2_set_bitfield(neus2_ctx* ctx, const uint8_t* bitfield_host, uint64_t n_bytes) {
+	const uint64_t want = (uint64_t)NERF_GRIDSIZE * NERF_GRIDSIZE * NERF_GRIDSIZE / 8 * NERF_CASCADES;
+	if (n_bytes != want) FAIL("bitfield size mismatch");
+	CUDA_CHECK(cudaSetDevice(ctx->device));
+	CUDA_CHECK(cudaMemcpy(ctx->bitfield, bitfield_host, n_bytes, cudaMemcpyHostToDevice));
+	return 0;
+}
+
+uint64_t neus2_launch_count(const neus2_ctx* ctx) { (void)ctx; return g_neus_launches; }
+
+}  // extern "C"

@@ -1,0 +1,279 @@
+// loss.cu -- NeuS compositing, loss and dL/d(network output) (compiled with -fmad=false).
+// Restates compute_loss_kernel_train_nerf_with_global_movement (src/testbed_nerf.cu:1475-1997) for Byte (LDR)
+// images: rgb activation Logistic, Huber(0.1)/5 in sRGB space, NeuS logistic-CDF alpha with the learned inv_s,
+// mask term, eikonal rows, cos rows.  Float/double literal types follow the reference expression by expression.
+// The reference's atomicAdd compaction (:1682) becomes an exclusive scan in ray-slot order (deterministic).
+#include "ngp_common.cuh"
+#include "ngp_kernels.h"
+
+__device__ __forceinline__ float logistic_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float relu_f(float v) { return v > 0.0f ? v : 0.0f; }
+
+struct SampleEval { float alpha, p_div_c, true_cos, iter_cos, inv_s, sdf, next_sdf, dt; float rgb[3]; float g[3]; };
+
+__device__ __forceinline__ SampleEval eval_sample(const __half* __restrict__ o_ptr, const float* __restrict__ coord, const float dir[3], float cos_anneal_ratio) {
+	// one 32-byte row of network output
+	uint4 lo = reinterpret_cast<const uint4*>(o_ptr)[0], hi = reinterpret_cast<const uint4*>(o_ptr)[1];
+	const __half* o = reinterpret_cast<const __half*>(&lo);
+	const __half* o2 = reinterpret_cast<const __half*>(&hi);
+	(void)o2;
+	SampleEval e;
+	#pragma unroll
+	for (int k = 0; k < 3; ++k) e.rgb[k] = logistic_f(__half2float(o[k]));
+	e.dt = unwarp_dt(coord[3]);
+	e.inv_s = expf(__half2float(__hmul(__float2half_rn(10.0f), o[7])));     // :1590
+	e.sdf = __half2float(o[3]);
+	#pragma unroll
+	for (int k = 0; k < 3; ++k) e.g[k] = __half2float(o[4 + k]);
+	e.true_cos = (dir[0] * e.g[0] + dir[1] * e.g[1] + dir[2] * e.g[2]);
+	e.iter_cos = (float)-(relu_f((float)(-e.true_cos * 0.5 + 0.5)) * (1.0 - cos_anneal_ratio) + relu_f(-e.true_cos) * cos_anneal_ratio);
+	e.next_sdf = (float)(e.sdf + e.iter_cos * e.dt * 0.5);
+	const float prev_sdf = (float)(e.sdf - e.iter_cos * e.dt * 0.5);
+	const float next_cdf = logistic_f(e.next_sdf * e.inv_s);
+	const float prev_cdf = logistic_f(prev_sdf * e.inv_s);
+	const float p = prev_cdf - next_cdf;
+	const float c = prev_cdf;
+	e.p_div_c = (p + 1e-5f) / (c + 1e-5f);
+	e.alpha = clampf(e.p_div_c, 0.0f, 1.0f);
+	return e;
+}
+
+__device__ __forceinline__ void ray_dir_for_loss(const float* __restrict__ ray, const GlobalMove& gmv, float ray_o[3], float dir[3]) {
+	ray_o[0] = ray[0]; ray_o[1] = ray[1]; ray_o[2] = ray[2];
+	normalize3(ray + 3, dir);
+	#pragma unroll
+	for (int k = 0; k < 3; ++k) ray_o[k] -= gmv.first_frame_offset[k];
+	global_move(gmv, ray_o, dir);
+}
+
+// pass 1: composite; ray_tmp[i] = {compacted (bits), rgb_ray[3], weight_sum, dir[3]}
+__global__ void k_loss_composite(const uint32_t* __restrict__ n_kept_ptr, GlobalMove gmv, float cos_anneal_ratio,
+                                 const __half* __restrict__ network_output, const float* __restrict__ rays, const uint32_t* __restrict__ numsteps,
+                                 const float* __restrict__ coords, float* __restrict__ ray_tmp, uint32_t* __restrict__ compacted_counts) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= *n_kept_ptr) return;
+	const uint32_t ns = numsteps[i * 2 + 0], base = numsteps[i * 2 + 1];
+	const float* cin = coords + (size_t)base * 7;
+	const __half* nout = network_output + (size_t)base * 16;
+	float T = 1.f;
+	const float EPSILON = 1e-4f;
+	float rgb_ray[3] = {0.f, 0.f, 0.f};
+	float weight_sum = 0.f;
+	uint32_t compacted = 0;
+	float ray_o[3], dir[3];
+	ray_dir_for_loss(rays + (size_t)i * 6, gmv, ray_o, dir);
+	for (; compacted < ns; ++compacted) {
+		if (T < EPSILON) break;
+		const __half* o = nout + (size_t)compacted * 16;
+		if (compacted == 0) {   // BENT_DIR :1583-1588
+			float dv[3] = {__half2float(o[8]) * 2.0f - 1.0f, __half2float(o[9]) * 2.0f - 1.0f, __half2float(o[10]) * 2.0f - 1.0f};
+			normalize3(dv, dir);
+		}
+		SampleEval e = eval_sample(o, cin + (size_t)compacted * 7, dir, cos_anneal_ratio);
+		const float weight = e.alpha * T;
+		#pragma unroll
+		for (int k = 0; k < 3; ++k) rgb_ray[k] += weight * e.rgb[k];
+		weight_sum += weight;
+		T *= (1.f - e.alpha);
+	}
+	float* rt = ray_tmp + (size_t)i * 12;
+	rt[0] = __uint_as_float(compacted);
+	rt[1] = rgb_ray[0]; rt[2] = rgb_ray[1]; rt[3] = rgb_ray[2];
+	rt[4] = weight_sum; rt[5] = T;
+	rt[6] = dir[0]; rt[7] = dir[1]; rt[8] = dir[2];
+	compacted_counts[i] = compacted;
+}
+
+#define SCAN_THREADS 1024
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_compacted(const uint32_t* __restrict__ n_ptr, const uint32_t* __restrict__ counts, uint32_t* __restrict__ base, uint32_t* __restrict__ total_out) {
+	__shared__ uint32_t warp_sums[32];
+	const uint32_t n = *n_ptr;
+	const uint32_t per = (n + SCAN_THREADS - 1) / SCAN_THREADS;
+	const uint32_t b = min(n, threadIdx.x * per), e = min(n, b + per);
+	uint32_t s = 0;
+	for (uint32_t i = b; i < e; ++i) s += counts[i];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t inc = s;
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+	if (lane == 31) warp_sums[warp] = inc;
+	__syncthreads();
+	if (warp == 0) {
+		uint32_t w = warp_sums[lane], winc = w;
+		#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += y; }
+		warp_sums[lane] = winc - w;
+		if (lane == 31) *total_out = winc;
+	}
+	__syncthreads();
+	uint32_t off = warp_sums[warp] + inc - s;
+	for (uint32_t i = b; i < e; ++i) { base[i] = off; off += counts[i]; }
+}
+
+// pass 2: loss + dL/doutput + compaction (:1629-1957)
+__global__ void k_loss_gradient(uint32_t n_rays, uint32_t n_rays_total, Pcg32 rng_in, DatasetDev ds, LossParamsDev lp, uint32_t max_samples_compacted,
+                                const uint32_t* __restrict__ n_kept_ptr, const __half* __restrict__ network_output, const uint32_t* __restrict__ ray_indices,
+                                uint32_t* __restrict__ numsteps, const float* __restrict__ coords, const float* __restrict__ ray_tmp,
+                                const uint32_t* __restrict__ compacted_base_arr, float* __restrict__ coords_compacted, __half* __restrict__ dloss_doutput,
+                                float* __restrict__ loss_output, float* __restrict__ ek_loss_output, float* __restrict__ mask_loss_output) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= *n_kept_ptr) return;
+	const uint32_t ns = numsteps[i * 2 + 0], base = numsteps[i * 2 + 1];
+	const float* cin = coords + (size_t)base * 7;
+	const __half* nout = network_output + (size_t)base * 16;
+	const float* rt = ray_tmp + (size_t)i * 12;
+	uint32_t compacted = __float_as_uint(rt[0]);
+	float rgb_ray[3] = {rt[1], rt[2], rt[3]};
+	float weight_sum = rt[4];
+	float T = rt[5];
+	const float dir[3] = {rt[6], rt[7], rt[8]};
+
+	const uint32_t ray_idx = ray_indices[i];
+	Pcg32 rng = rng_in;
+	rng.advance((int64_t)(uint32_t)(ray_idx * N_MAX_RANDOM_SAMPLES_PER_RAY));
+	const uint32_t img = image_idx(ray_idx, n_rays, n_rays_total, ds.n_images);
+	float xy[2];
+	random_image_pos_training(rng, ds.width, ds.height, lp.snap_to_pixel_centers != 0, xy);
+	float bg[3] = {lp.background_color[0], lp.background_color[1], lp.background_color[2]};
+	if (lp.random_bg_color) { bg[0] = rng.next_float(); bg[1] = rng.next_float(); bg[2] = rng.next_float(); }
+	#pragma unroll
+	for (int k = 0; k < 3; ++k) bg[k] = srgb_to_linear(bg[k]);
+	int px, py; image_pos(xy, ds.width, ds.height, &px, &py);
+	float tex[4]; read_rgba(ds, img, px, py, tex);
+	float rgbtarget[3];
+	#pragma unroll
+	for (int k = 0; k < 3; ++k) {
+		const float exposure_scale = expf(0.6931471805599453f * 0.0f);
+		rgbtarget[k] = exposure_scale * tex[k] + (1.0f - tex[3]) * bg[k];
+		rgbtarget[k] = linear_to_srgb(rgbtarget[k]);
+		bg[k] = linear_to_srgb(bg[k]);
+	}
+	if (compacted == ns) {
+		#pragma unroll
+		for (int k = 0; k < 3; ++k) rgb_ray[k] += T * bg[k];
+	}
+	const uint32_t compacted_base = compacted_base_arr[i];
+	compacted = min(max_samples_compacted - min(max_samples_compacted, compacted_base), compacted);
+	numsteps[i * 2 + 0] = compacted;
+	numsteps[i * 2 + 1] = compacted_base;
+	if (compacted == 0) return;
+
+	float* cout = coords_compacted + (size_t)compacted_base * 7;
+	__half* dout = dloss_doutput + (size_t)compacted_base * 16;
+
+	float lg_loss[3], lg_grad[3];
+	#pragma unroll
+	for (int k = 0; k < 3; ++k) {
+		const float alpha_h = 0.1f;
+		const float difference = rgb_ray[k] - rgbtarget[k];
+		const float abs_diff = fabsf(difference);
+		const float square = 0.5f / alpha_h * difference * difference;
+		lg_loss[k] = (abs_diff > alpha_h ? (abs_diff - 0.5f * alpha_h) : square) / 5.0f;
+		lg_grad[k] = (abs_diff > alpha_h ? (difference > 0 ? 1.0f : -1.0f) : (difference / alpha_h)) / 5.0f;
+	}
+	const float mask_gt = (float)(tex[3] > 0.9999);
+	float gradient_weight_sum;
+	if (weight_sum >= 1.0 - 1e-4) { weight_sum = (float)(1.0 - 1e-4); gradient_weight_sum = 0.0f; }
+	else if (weight_sum <= 1e-4) { weight_sum = (float)1e-4; gradient_weight_sum = 0.0f; }
+	else {
+		const float sigmoid_weight_sum = 1.0f / (1.0f + expf(-weight_sum));
+		gradient_weight_sum = (mask_gt - sigmoid_weight_sum) * weight_sum * lp.mask_loss_weight;
+	}
+	const float mean_loss = (lg_loss[0] + lg_loss[1] + lg_loss[2]) / 3.0f;
+	loss_output[i] = mean_loss / (float)n_rays;
+	mask_loss_output[i] = -(mask_gt * logf(weight_sum) + (1 - mask_gt) * logf(1 - weight_sum));
+	float ek_acc = 0.f;
+
+	const float loss_scale = lp.loss_scale / n_rays;
+	float rgb_ray2[3] = {0.f, 0.f, 0.f};
+	T = 1.f;
+	for (uint32_t j = 0; j < compacted; ++j) {
+		#pragma unroll
+		for (int k = 0; k < 7; ++k) cout[(size_t)j * 7 + k] = cin[(size_t)j * 7 + k];
+		const __half* o = nout + (size_t)j * 16;
+		SampleEval e = eval_sample(o, cin + (size_t)j * 7, dir, lp.cos_anneal_ratio);
+		const float weight = e.alpha * T;
+		#pragma unroll
+		for (int k = 0; k < 3; ++k) rgb_ray2[k] += weight * e.rgb[k];
+		T *= (1.f - e.alpha);
+		float suffix[3], dloss_by_drgb[3];
+		#pragma unroll
+		for (int k = 0; k < 3; ++k) { suffix[k] = rgb_ray[k] - rgb_ray2[k]; dloss_by_drgb[k] = weight * lg_grad[k]; }
+		float local[16];
+		#pragma unroll
+		for (int k = 0; k < 16; ++k) local[k] = 0.f;
+		#pragma unroll
+		for (int k = 0; k < 3; ++k) {
+			const float ov = __half2float(o[k]);
+			const float density = logistic_f(ov);
+			const float deriv = density * (1 - density);
+			local[k] = loss_scale * (dloss_by_drgb[k] * deriv + fmaxf(0.0f, 0.0f * ov));
+		}
+		const float dot = lg_grad[0] * (T * e.rgb[0] - suffix[0]) + lg_grad[1] * (T * e.rgb[1] - suffix[1]) + lg_grad[2] * (T * e.rgb[2] - suffix[2]);
+		const float dloss_dalpha = (float)((dot + gradient_weight_sum * (1 - weight_sum)) / (1.0f - e.alpha + 1e-5));
+		float dalpha_d_e_minus_sigmoidx, d_e_minus_sigmoidx_dsdf, d_e_minus_sigmoidx_dinvs, d_alpha_d_plus_e, d_plus_e_dinvs, d_plus_e_iter_cos, d_e_minus_sigmoidx_diter_cos;
+		if (e.p_div_c <= 0.0f || e.p_div_c >= 1.0f) {
+			dalpha_d_e_minus_sigmoidx = d_e_minus_sigmoidx_dsdf = d_e_minus_sigmoidx_dinvs = d_alpha_d_plus_e = d_plus_e_dinvs = d_plus_e_iter_cos = d_e_minus_sigmoidx_diter_cos = 0.0f;
+		} else {
+			const float plus_sigmoid_x = e.inv_s * e.iter_cos * e.dt;
+			const float plus_e = expf(plus_sigmoid_x);
+			const float e_minus_sigmoid = expf(-e.next_sdf * e.inv_s);
+			d_e_minus_sigmoidx_dsdf = -e.inv_s * e_minus_sigmoid;
+			d_e_minus_sigmoidx_dinvs = -e.next_sdf * e_minus_sigmoid;
+			const float a = 1 + e_minus_sigmoid;
+			const float b = 1 + plus_e * e_minus_sigmoid;
+			const float c = (float)(1e-5 + 1 / (1 + plus_e * e_minus_sigmoid));
+			const float delta = a * (b * b) * (c * c);
+			dalpha_d_e_minus_sigmoidx = -(plus_e / (delta) - 1 / (a * a * c));
+			d_alpha_d_plus_e = -e_minus_sigmoid / (delta);
+			d_plus_e_dinvs = plus_e * e.iter_cos * e.dt;
+			d_plus_e_iter_cos = plus_e * e.inv_s * e.dt;
+			d_e_minus_sigmoidx_diter_cos = (float)(-e.inv_s * e_minus_sigmoid * e.dt * 0.5);
+		}
+		const float dloss_dinvs = dloss_dalpha * (dalpha_d_e_minus_sigmoidx * d_e_minus_sigmoidx_dinvs + d_alpha_d_plus_e * d_plus_e_dinvs);
+		const float dloss_dvariance = dloss_dinvs * e.inv_s * 10;
+		const float d_iter_cos_true_cos = (e.true_cos >= 0) ? 0.0f : 1.0f;
+		const float gradient_norm = (float)sqrt((double)(e.g[0] * e.g[0] + e.g[1] * e.g[1] + e.g[2] * e.g[2]) + 1e-6);
+		const float pos_gradient_norm_inv = 1 - 1 / gradient_norm;
+		const float dloss_dnormal_norm = dloss_dalpha * (dalpha_d_e_minus_sigmoidx * d_e_minus_sigmoidx_diter_cos + d_plus_e_iter_cos * d_alpha_d_plus_e) * d_iter_cos_true_cos;
+		const float dloss_dsdf = dloss_dalpha * dalpha_d_e_minus_sigmoidx * d_e_minus_sigmoidx_dsdf;
+		local[3] = loss_scale * dloss_dsdf;
+		ek_acc += (gradient_norm - 1.0f) * (gradient_norm - 1.0f);
+		#pragma unroll
+		for (int k = 0; k < 3; ++k) local[4 + k] = lp.ek_loss_weight * 2 * lp.loss_scale * pos_gradient_norm_inv * e.g[k];
+		local[7] = loss_scale * dloss_dvariance;
+		#pragma unroll
+		for (int k = 0; k < 3; ++k) local[8 + k] = loss_scale * dloss_dnormal_norm * dir[k];
+		uint32_t packed[8];
+		#pragma unroll
+		for (int k = 0; k < 8; ++k) packed[k] = pack_h2(local[2 * k], local[2 * k + 1]);
+		reinterpret_cast<uint4*>(dout + (size_t)j * 16)[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+		reinterpret_cast<uint4*>(dout + (size_t)j * 16)[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+	}
+	ek_loss_output[i] = ek_acc / ((float)compacted * (float)n_rays);
+}
+
+int launch_compute_loss(cudaStream_t stream, uint32_t n_rays_local, uint32_t n_rays, uint32_t n_rays_total, const uint64_t rng_state[2], const DatasetDev& ds, const Aabb& bb,
+                        const GlobalMove& gmv, const LossParamsDev& lp, uint32_t max_samples_compacted, const uint32_t* n_kept_ptr,
+                        const __half* network_output, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps, const float* coords,
+                        float* ray_tmp, uint32_t* scan_tmp, float* coords_compacted, __half* dloss_doutput,
+                        float* loss_output, float* ek_loss_output, float* mask_loss_output, uint32_t* out_counter) {
+	(void)bb;
+	if (n_rays_local == 0) return 0;
+	Pcg32 rng; rng.state = rng_state[0]; rng.inc = rng_state[1];
+	const uint32_t blocks = (n_rays_local + 127) / 128;
+	uint32_t* counts = scan_tmp;
+	uint32_t* cbase = scan_tmp + n_rays_local;
+	k_loss_composite<<<blocks, 128, 0, stream>>>(n_kept_ptr, gmv, lp.cos_anneal_ratio, network_output, rays, numsteps, coords, ray_tmp, counts);
+	COUNT_LAUNCH(1);
+	CUDA_CHECK(cudaGetLastError());
+	k_scan_compacted<<<1, SCAN_THREADS, 0, stream>>>(n_kept_ptr, counts, cbase, out_counter);
+	COUNT_LAUNCH(1);
+	CUDA_CHECK(cudaGetLastError());
+	k_loss_gradient<<<blocks, 128, 0, stream>>>(n_rays, n_rays_total, rng, ds, lp, max_samples_compacted, n_kept_ptr, network_output, ray_indices,
+	                                           numsteps, coords, ray_tmp, cbase, coords_compacted, dloss_doutput, loss_output, ek_loss_output, mask_loss_output);
+	COUNT_LAUNCH(1);
+	CUDA_CHECK(cudaGetLastError());
+	return 0;
+}

@@ -1,0 +1,434 @@
+// network.cuh -- warp-level building blocks of the fused NeuS network kernels.
+//
+// One warp owns a tile of 16 samples end to end: hash-grid gather -> SDF MLP -> analytic normal ->
+// SH -> colour MLP (-> full backward incl. the second-order terms in the training kernel).  Activations
+// travel between layers in mma.sync fragments (registers); only the per-sample scalar stages go through
+// the warp's private shared-memory slab.  Warps never synchronise with each other after the weights are
+// staged, so gather latency of one warp overlaps tensor work of the others.
+//
+// Restates (does not copy) NerfNetwork::forward_impl / backward_impl (include/neural-graphics-primitives/
+// nerf_network.h:145-654), kernel_grid* (tcnn encodings/grid.h:174-1207) and the FullyFusedMLP arithmetic
+// (tcnn src/fully_fused_mlp.cu).  Rounding points are those of oracle/neus_oracle.cpp.
+#pragma once
+#include "common.cuh"
+
+#define TILE 16                // samples per warp tile (one mma m16 row block)
+#define LD_X0 40               // 32 + 8 pad (halves)   -> conflict-free fragment loads
+#define LD_H 72                // 64 + 8 pad
+#define LD_C0 56               // 48 + 8 pad
+#define LD_T16 24              // 16 + 8 pad
+#define LD_DY 85               // 84 floats + 1 pad per sample
+#define SDF_IN 32
+#define RGB_IN 48
+
+// ---- shared-memory weight block (halves) -------------------------------------------------------
+struct WeightSmem {
+	// forward orientation: row = output unit, contiguous = input unit  (B(k,n) = W[n][k])
+	static constexpr int W0 = 0;                       // [64][LD_X0]
+	static constexpr int W1 = W0 + 64 * LD_X0;         // [16][LD_H]
+	static constexpr int C0 = W1 + 16 * LD_H;          // [64][LD_C0]
+	static constexpr int C1 = C0 + 64 * LD_C0;         // [64][LD_H]
+	static constexpr int C2 = C1 + 64 * LD_H;          // [16][LD_H]
+	static constexpr int W0T = C2 + 16 * LD_H;         // [32][LD_H]   W0T[i][j] = W0[j][i]
+	static constexpr int FWD_END = W0T + 32 * LD_H;
+	// backward-only transposes
+	static constexpr int W1T = FWD_END;                // [64][LD_T16] W1T[j][o] = W1[o][j]
+	static constexpr int C0T = W1T + 64 * LD_T16;      // [48][LD_H]
+	static constexpr int C1T = C0T + 48 * LD_H;        // [64][LD_H]
+	static constexpr int C2T = C1T + 64 * LD_H;        // [64][LD_T16]
+	static constexpr int BWD_END = C2T + 64 * LD_T16;
+};
+
+// per-warp slab (bytes)
+struct WarpSlab {
+	static constexpr int COORD = 0;                          // float [16][7]
+	static constexpr int X0 = COORD + 16 * 7 * 4;            // half  [16][LD_X0]   sdf-MLP input
+	static constexpr int DIN = X0 + 16 * LD_X0 * 2;          // half  [16][LD_X0]   d sdf / d sdf-input  (gE in cols 3..30)
+	static constexpr int CIN = DIN + 16 * LD_X0 * 2;         // half  [16][LD_X0]   colour input cols 16..47
+	static constexpr int OUT = CIN + 16 * LD_X0 * 2;         // half  [16][16]      output staging
+	static constexpr int SDF = OUT + 16 * 16 * 2;            // half  [16]          raw sdf-MLP output 0
+	static constexpr int NRM = SDF + 16 * 2;                 // float [16][3]       normal
+	static constexpr int DY = NRM + 16 * 3 * 4;              // float [16][LD_DY]
+	static constexpr int FWD_END = DY + 16 * LD_DY * 4;
+	// training extras
+	static constexpr int DL = FWD_END;                       // half  [16][16]      dL/dout (after rollover scaling)
+	static constexpr int DX = DL + 16 * 16 * 2;              // half  [16][LD_X0]   dL/d sdf-input
+	static constexpr int DI = DX + 16 * LD_X0 * 2;           // half  [16][LD_X0]   d_density_input (2nd order)
+	static constexpr int V = DI + 16 * LD_X0 * 2;            // float [16][3]       v = dL/d normal
+	static constexpr int VN = V + 16 * 3 * 4;                // half  [16][8]       colour-input grad cols 32..39
+	static constexpr int BWD_END = VN + 16 * 8 * 2;
+};
+
+__device__ __forceinline__ void stage_matrix(__half* dst, int ld_dst, const __half* __restrict__ src, int rows, int cols, int tid, int nthreads) {
+	for (int i = tid; i < rows * cols; i += nthreads) {
+		int r = i / cols, c = i - r * cols;
+		dst[r * ld_dst + c] = src[i];
+	}
+}
+__device__ __forceinline__ void stage_matrix_T(__half* dst, int ld_dst, const __half* __restrict__ src, int rows, int cols, int tid, int nthreads) {
+	// dst[c][r] = src[r][c]
+	for (int i = tid; i < rows * cols; i += nthreads) {
+		int r = i / cols, c = i - r * cols;
+		dst[c * ld_dst + r] = src[i];
+	}
+}
+
+__device__ __forceinline__ void stage_weights(__half* sw, const __half* __restrict__ params, const ParamLayout& pl, bool train, int tid, int nthreads) {
+	stage_matrix(sw + WeightSmem::W0, LD_X0, params + pl.off_w0, 64, SDF_IN, tid, nthreads);
+	stage_matrix(sw + WeightSmem::W1, LD_H, params + pl.off_w1, 16, 64, tid, nthreads);
+	stage_matrix(sw + WeightSmem::C0, LD_C0, params + pl.off_c0, 64, RGB_IN, tid, nthreads);
+	stage_matrix(sw + WeightSmem::C1, LD_H, params + pl.off_c1, 64, 64, tid, nthreads);
+	stage_matrix(sw + WeightSmem::C2, LD_H, params + pl.off_c2, 16, 64, tid, nthreads);
+	stage_matrix_T(sw + WeightSmem::W0T, LD_H, params + pl.off_w0, 64, SDF_IN, tid, nthreads);
+	if (train) {
+		stage_matrix_T(sw + WeightSmem::W1T, LD_T16, params + pl.off_w1, 16, 64, tid, nthreads);
+		stage_matrix_T(sw + WeightSmem::C0T, LD_H, params + pl.off_c0, 64, RGB_IN, tid, nthreads);
+		stage_matrix_T(sw + WeightSmem::C1T, LD_H, params + pl.off_c1, 64, 64, tid, nthreads);
+		stage_matrix_T(sw + WeightSmem::C2T, LD_T16, params + pl.off_c2, 16, 64, tid, nthreads);
+	}
+}
+
+// ---- fragment helpers ------------------------------------------------------------------------------
+// c[NT][4] = A(regs a[KT][4]) x B, B(k,n) = W[n][k], W row stride ld (halves).
+template <int KT, int NT>
+__device__ __forceinline__ void mma_layer(const uint32_t (&a)[KT][4], const __half* W, int ld, float (&c)[NT][4], int g, int t) {
+	#pragma unroll
+	for (int nt = 0; nt < NT; ++nt) {
+		c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;
+		const __half* wrow = W + (8 * nt + g) * ld + 2 * t;
+		#pragma unroll
+		for (int kt = 0; kt < KT; ++kt) {
+			uint32_t b0 = *reinterpret_cast<const uint32_t*>(wrow + 16 * kt);
+			uint32_t b1 = *reinterpret_cast<const uint32_t*>(wrow + 16 * kt + 8);
+			mma16816(c[nt], a[kt], b0, b1);
+		}
+	}
+}
+
+// load an A fragment (16 rows x 16 cols starting at col0) from a row-major half tile in shared memory
+__device__ __forceinline__ void load_a_frag(uint32_t (&a)[4], const __half* S, int ld, int col0, int g, int t) {
+	a[0] = *reinterpret_cast<const uint32_t*>(S + g * ld + col0 + 2 * t);
+	a[1] = *reinterpret_cast<const uint32_t*>(S + (g + 8) * ld + col0 + 2 * t);
+	a[2] = *reinterpret_cast<const uint32_t*>(S + g * ld + col0 + 8 + 2 * t);
+	a[3] = *reinterpret_cast<const uint32_t*>(S + (g + 8) * ld + col0 + 8 + 2 * t);
+}
+
+template <int NT, bool RELU>
+__device__ __forceinline__ void pack_frags(const float (&c)[NT][4], uint32_t (&a)[NT / 2][4]) {
+	#pragma unroll
+	for (int kt = 0; kt < NT / 2; ++kt) {
+		#pragma unroll
+		for (int r = 0; r < 4; ++r) {
+			const int nt = 2 * kt + (r >> 1);
+			float v0 = c[nt][(r & 1) * 2], v1 = c[nt][(r & 1) * 2 + 1];
+			if (RELU) { v0 = v0 > 0.f ? v0 : 0.f; v1 = v1 > 0.f ? v1 : 0.f; }
+			a[kt][r] = pack_h2(v0, v1);
+		}
+	}
+}
+
+// per-half mask: 0xffff where the half in `ref` is > 0 (hidden activation passed the ReLU)
+__device__ __forceinline__ uint32_t relu_mask2(uint32_t ref) {
+	uint32_t lo = ((ref & 0x7fffu) != 0u && (ref & 0x8000u) == 0u) ? 0x0000ffffu : 0u;
+	uint32_t hi = ((ref & 0x7fff0000u) != 0u && (ref & 0x80000000u) == 0u) ? 0xffff0000u : 0u;
+	return lo | hi;
+}
+
+template <int NT>
+__device__ __forceinline__ void pack_frags_masked(const float (&c)[NT][4], const uint32_t (&ref)[NT / 2][4], uint32_t (&a)[NT / 2][4]) {
+	#pragma unroll
+	for (int kt = 0; kt < NT / 2; ++kt) {
+		#pragma unroll
+		for (int r = 0; r < 4; ++r) {
+			const int nt = 2 * kt + (r >> 1);
+			a[kt][r] = pack_h2(c[nt][(r & 1) * 2], c[nt][(r & 1) * 2 + 1]) & relu_mask2(ref[kt][r]);
+		}
+	}
+}
+
+// write C tiles (fp32 -> half) to a row-major shared tile: cols 8*nt + 2t
+template <int NT>
+__device__ __forceinline__ void store_c_smem(const float (&c)[NT][4], __half* S, int ld, int g, int t) {
+	#pragma unroll
+	for (int nt = 0; nt < NT; ++nt) {
+		*reinterpret_cast<uint32_t*>(S + g * ld + 8 * nt + 2 * t) = pack_h2(c[nt][0], c[nt][1]);
+		*reinterpret_cast<uint32_t*>(S + (g + 8) * ld + 8 * nt + 2 * t) = pack_h2(c[nt][2], c[nt][3]);
+	}
+}
+
+// store A-layout fragments (KT k-tiles = 16*KT columns) to a row-major global matrix [rows][ld] of halves
+template <int KT>
+__device__ __forceinline__ void store_a_global(const uint32_t (&a)[KT][4], __half* G, int ld, int row0, int n_valid, int g, int t) {
+	#pragma unroll
+	for (int kt = 0; kt < KT; ++kt) {
+		if (g < n_valid) {
+			*reinterpret_cast<uint32_t*>(G + (size_t)(row0 + g) * ld + 16 * kt + 2 * t) = a[kt][0];
+			*reinterpret_cast<uint32_t*>(G + (size_t)(row0 + g) * ld + 16 * kt + 8 + 2 * t) = a[kt][2];
+		}
+		if (g + 8 < n_valid) {
+			*reinterpret_cast<uint32_t*>(G + (size_t)(row0 + g + 8) * ld + 16 * kt + 2 * t) = a[kt][1];
+			*reinterpret_cast<uint32_t*>(G + (size_t)(row0 + g + 8) * ld + 16 * kt + 8 + 2 * t) = a[kt][3];
+		}
+	}
+}
+
+// ---- hash grid ----------------------------------------------------------------------------------
+// grid.h:119-153 with the per-level "hashed" decision hoisted to the host (GridMeta.hashed semantics:
+// hashed <=> res^3 > hashmap_size).
+__device__ __forceinline__ uint32_t grid_index(bool hashed, uint32_t hashmap_size, uint32_t res, uint32_t x, uint32_t y, uint32_t z) {
+	uint32_t index;
+	if (hashed) {
+		index = x ^ (y * 2654435761u) ^ (z * 805459861u);
+		return (index & (hashmap_size - 1u)) * 2u;   // hashed levels have power-of-two size (2^log2_hashmap_size)
+	}
+	index = x + y * res + z * res * res;
+	return (index % hashmap_size) * 2u;
+}
+
+struct LevelGeom {
+	float w[3];          // fractional position
+	uint32_t idx[8];     // feature-pair index (in halves) of the 8 corners, corner bit d set => +1 in dim d
+};
+
+__device__ __forceinline__ void level_geom(const GridMeta& gm, int l, float x, float y, float z, LevelGeom& lg) {
+	const float scale = gm.scale[l];
+	const uint32_t res = gm.res[l];
+	const uint32_t hs = gm.offset[l + 1] - gm.offset[l];
+	const bool hashed = (uint64_t)res * res * res > (uint64_t)hs;
+	uint32_t p[3];
+	const float in[3] = {x, y, z};
+	#pragma unroll
+	for (int d = 0; d < 3; ++d) {
+		float pf = fmaf(in[d], scale, 0.5f);      // pos_fract, tcnn common_device.h:403-434
+		float fl = floorf(pf);
+		p[d] = (uint32_t)(int)fl;
+		lg.w[d] = pf - fl;
+	}
+	#pragma unroll
+	for (int c = 0; c < 8; ++c) {
+		lg.idx[c] = grid_index(hashed, hs, res, p[0] + (c & 1), p[1] + ((c >> 1) & 1), p[2] + ((c >> 2) & 1));
+	}
+}
+
+// Gather for one 16-sample tile.  lane -> (sample lane&15, level parity lane>>4).
+// Writes: X0[s][3+2l..] = encoding (half, accumulated in half in corner order, grid.h:316-318),
+//         DY[s][ (2l+f)*3 + d ] = d enc / d x (fp32, grid.h:329-367)  when WANT_DY.
+template <bool WANT_DY>
+__device__ __forceinline__ void gather_tile(const GridMeta& gm, const __half* __restrict__ grid, const float* sCoord, __half* sX0, float* sDY, int lane) {
+	const int s = lane & 15;
+	const float x = sCoord[s * 7 + 0], y = sCoord[s * 7 + 1], z = sCoord[s * 7 + 2];
+	for (int l = lane >> 4; l < (int)gm.n_levels; l += 2) {
+		__half* xo = sX0 + s * LD_X0 + 3 + 2 * l;
+		float* dyo = sDY + s * LD_DY + 6 * l;
+		if ((uint32_t)l > gm.valid_level) {
+			xo[0] = __float2half(0.f); xo[1] = __float2half(0.f);
+			if (WANT_DY) { for (int k = 0; k < 6; ++k) dyo[k] = 0.f; }
+			continue;
+		}
+		LevelGeom lg;
+		level_geom(gm, l, x, y, z, lg);
+		const __half* g = grid + (size_t)gm.offset[l] * 2;
+		uint32_t v[8];
+		#pragma unroll
+		for (int c = 0; c < 8; ++c) v[c] = ld_nc_u32(g + lg.idx[c]);
+		const float wx[2] = {1.f - lg.w[0], lg.w[0]}, wy[2] = {1.f - lg.w[1], lg.w[1]}, wz[2] = {1.f - lg.w[2], lg.w[2]};
+		__half r0 = __float2half(0.f), r1 = __float2half(0.f);
+		#pragma unroll
+		for (int c = 0; c < 8; ++c) {
+			const float weight = (wx[c & 1] * wy[(c >> 1) & 1]) * wz[(c >> 2) & 1];
+			r0 = __hadd(r0, __float2half_rn(weight * h_lo(v[c])));
+			r1 = __hadd(r1, __float2half_rn(weight * h_hi(v[c])));
+		}
+		xo[0] = r0; xo[1] = r1;
+		if (WANT_DY) {
+			const float scale = gm.scale[l];
+			float g0[3] = {0.f, 0.f, 0.f}, g1[3] = {0.f, 0.f, 0.f};
+			#pragma unroll
+			for (int i = 0; i < 4; ++i) {
+				const int b0 = i & 1, b1 = (i >> 1) & 1;
+				{   // d/dx : other dims (y, z)
+					const float weight = (scale * wy[b0]) * wz[b1];
+					const int cl = (b0 << 1) | (b1 << 2), cr = cl | 1;
+					g0[0] = fmaf(weight, h_lo(v[cr]) - h_lo(v[cl]), g0[0]);
+					g1[0] = fmaf(weight, h_hi(v[cr]) - h_hi(v[cl]), g1[0]);
+				}
+				{   // d/dy : other dims (x, z)
+					const float weight = (scale * wx[b0]) * wz[b1];
+					const int cl = b0 | (b1 << 2), cr = cl | 2;
+					g0[1] = fmaf(weight, h_lo(v[cr]) - h_lo(v[cl]), g0[1]);
+					g1[1] = fmaf(weight, h_hi(v[cr]) - h_hi(v[cl]), g1[1]);
+				}
+				{   // d/dz : other dims (x, y)
+					const float weight = (scale * wx[b0]) * wy[b1];
+					const int cl = b0 | (b1 << 1), cr = cl | 4;
+					g0[2] = fmaf(weight, h_lo(v[cr]) - h_lo(v[cl]), g0[2]);
+					g1[2] = fmaf(weight, h_hi(v[cr]) - h_hi(v[cl]), g1[2]);
+				}
+			}
+			dyo[0] = g0[0]; dyo[1] = g0[1]; dyo[2] = g0[2];
+			dyo[3] = g1[0]; dyo[4] = g1[1]; dyo[5] = g1[2];
+		}
+	}
+}
+
+// SH degree 4 on the warped direction (tcnn encodings/spherical_harmonics.h:47-100); 16 halves.
+__device__ __forceinline__ void sh4(float dx, float dy, float dz, __half* out) {
+	const float x = fmaf(dx, 2.f, -1.f), y = fmaf(dy, 2.f, -1.f), z = fmaf(dz, 2.f, -1.f);
+	const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+	out[0] = __float2half_rn(0.28209479177387814f);
+	out[1] = __float2half_rn(-0.48860251190291987f * y);
+	out[2] = __float2half_rn(0.48860251190291987f * z);
+	out[3] = __float2half_rn(-0.48860251190291987f * x);
+	out[4] = __float2half_rn(1.0925484305920792f * xy);
+	out[5] = __float2half_rn(-1.0925484305920792f * yz);
+	out[6] = __float2half_rn(fmaf(0.94617469575755997f, z2, -0.31539156525251999f));
+	out[7] = __float2half_rn(-1.0925484305920792f * xz);
+	out[8] = __float2half_rn(fmaf(0.54627421529603959f, x2, -(0.54627421529603959f * y2)));
+	out[9] = __float2half_rn(__fmul_rn(__fmul_rn(0.59004358992664352f, y), fmaf(-3.0f, x2, y2)));
+	out[10] = __float2half_rn(__fmul_rn(__fmul_rn(2.8906114426405538f, xy), z));
+	out[11] = __float2half_rn(__fmul_rn(__fmul_rn(0.45704579946446572f, y), fmaf(-5.0f, z2, 1.0f)));
+	out[12] = __float2half_rn(__fmul_rn(__fmul_rn(0.3731763325901154f, z), fmaf(5.0f, z2, -3.0f)));
+	out[13] = __float2half_rn(__fmul_rn(__fmul_rn(0.45704579946446572f, x), fmaf(-5.0f, z2, 1.0f)));
+	out[14] = __float2half_rn(__fmul_rn(__fmul_rn(1.4453057213202769f, z), __fsub_rn(x2, y2)));
+	out[15] = __float2half_rn(__fmul_rn(__fmul_rn(0.59004358992664352f, x), fmaf(3.0f, y2, -x2)));
+}
+
+// Everything the forward leaves in registers for the backward.
+struct FwdState {
+	uint32_t h0a[4][4];    // SDF hidden (post-ReLU, half) as A fragments
+	uint32_t soa[4];       // SDF-MLP output (16 wide, half) as one A fragment
+	uint32_t h1a[4][4];    // colour hidden 1
+	uint32_t h2a[4][4];    // colour hidden 2
+};
+
+// Forward for one tile.  On return: sOUT holds the assembled 16x16 half output (nerf_network.h:287-325),
+// sDIN the d sdf/d sdf-input rows, sNRM the normals, sCIN colour-input cols 16..47.
+template <bool KEEP>
+__device__ __forceinline__ void forward_tile(const GridMeta& gm, const __half* __restrict__ params, const ParamLayout& pl,
+                                             const __half* sw, unsigned char* slab, float sdf_bias, int lane, FwdState& st) {
+	const int g = lane >> 2, t = lane & 3;
+	float* sCoord = reinterpret_cast<float*>(slab + WarpSlab::COORD);
+	__half* sX0 = reinterpret_cast<__half*>(slab + WarpSlab::X0);
+	__half* sDIN = reinterpret_cast<__half*>(slab + WarpSlab::DIN);
+	__half* sCIN = reinterpret_cast<__half*>(slab + WarpSlab::CIN);
+	__half* sOUT = reinterpret_cast<__half*>(slab + WarpSlab::OUT);
+	__half* sSDF = reinterpret_cast<__half*>(slab + WarpSlab::SDF);
+	float* sNRM = reinterpret_cast<float*>(slab + WarpSlab::NRM);
+	float* sDY = reinterpret_cast<float*>(slab + WarpSlab::DY);
+
+	// --- SDF-MLP input: [half(x)-half(0.5) | enc | 0]  (nerf_network.h:206-212)
+	if (lane < 16) {
+		#pragma unroll
+		for (int d = 0; d < 3; ++d) sX0[lane * LD_X0 + d] = __hsub(__float2half_rn(sCoord[lane * 7 + d]), __float2half_rn(0.5f));
+		for (int k = 3 + 2 * (int)gm.n_levels; k < SDF_IN; ++k) sX0[lane * LD_X0 + k] = __float2half(0.f);
+	}
+	gather_tile<true>(gm, params + pl.off_grid, sCoord, sX0, sDY, lane);
+	__syncwarp();
+
+	// --- SDF MLP (32 -> 64 -> 16), fp32 accumulate, half activations
+	uint32_t h0a[4][4];
+	{
+		uint32_t xa[2][4];
+		load_a_frag(xa[0], sX0, LD_X0, 0, g, t);
+		load_a_frag(xa[1], sX0, LD_X0, 16, g, t);
+		float c[8][4];
+		mma_layer<2, 8>(xa, sw + WeightSmem::W0, LD_X0, c, g, t);
+		pack_frags<8, true>(c, h0a);
+	}
+	uint32_t soa[4];
+	{
+		float c[2][4];
+		mma_layer<4, 2>(h0a, sw + WeightSmem::W1, LD_H, c, g, t);
+		uint32_t tmp[1][4];
+		pack_frags<2, false>(c, tmp);
+		soa[0] = tmp[0][0]; soa[1] = tmp[0][1]; soa[2] = tmp[0][2]; soa[3] = tmp[0][3];
+		if (t == 0) {
+			sSDF[g] = __ushort_as_half((unsigned short)(soa[0] & 0xffffu));
+			sSDF[g + 8] = __ushort_as_half((unsigned short)(soa[1] & 0xffffu));
+		}
+	}
+	// --- d sdf / d input = W0^T (relu'(h0) * W1[0,:])   (nerf_network.h:228-245; seed = 1 on output 0)
+	{
+		uint32_t gh[4][4];
+		#pragma unroll
+		for (int kt = 0; kt < 4; ++kt) {
+			const uint32_t wlo = *reinterpret_cast<const uint32_t*>(sw + WeightSmem::W1 + 16 * kt + 2 * t);
+			const uint32_t whi = *reinterpret_cast<const uint32_t*>(sw + WeightSmem::W1 + 16 * kt + 8 + 2 * t);
+			gh[kt][0] = wlo & relu_mask2(h0a[kt][0]);
+			gh[kt][1] = wlo & relu_mask2(h0a[kt][1]);
+			gh[kt][2] = whi & relu_mask2(h0a[kt][2]);
+			gh[kt][3] = whi & relu_mask2(h0a[kt][3]);
+		}
+		float c[4][4];
+		mma_layer<4, 4>(gh, sw + WeightSmem::W0T, LD_H, c, g, t);
+		store_c_smem<4>(c, sDIN, LD_X0, g, t);
+	}
+	__syncwarp();
+
+	// --- per-sample stage: normal (lanes 0..15), SH of the view direction (lanes 16..31)
+	if (lane < 16) {
+		const int s = lane;
+		float n0 = 0.f, n1 = 0.f, n2 = 0.f;
+		const int E = 2 * (int)gm.n_levels;
+		for (int k = 0; k < E; ++k) {   // kernel_grid_backward_input, grid.h:803-830
+			const float dl = __half2float(sDIN[s * LD_X0 + 3 + k]);
+			n0 = fmaf(dl, sDY[s * LD_DY + 3 * k + 0], n0);
+			n1 = fmaf(dl, sDY[s * LD_DY + 3 * k + 1], n1);
+			n2 = fmaf(dl, sDY[s * LD_DY + 3 * k + 2], n2);
+		}
+		n0 = __fadd_rn(n0, __half2float(sDIN[s * LD_X0 + 0]));   // identity path, nerf_network.h:249
+		n1 = __fadd_rn(n1, __half2float(sDIN[s * LD_X0 + 1]));
+		n2 = __fadd_rn(n2, __half2float(sDIN[s * LD_X0 + 2]));
+		sNRM[s * 3 + 0] = n0; sNRM[s * 3 + 1] = n1; sNRM[s * 3 + 2] = n2;
+		__half* ci = sCIN + s * LD_X0;   // colour-input cols 16..47 live at [0..31]
+		ci[16] = __float2half_rn(sCoord[s * 7 + 0]); ci[17] = __float2half_rn(sCoord[s * 7 + 1]); ci[18] = __float2half_rn(sCoord[s * 7 + 2]);
+		ci[19] = __float2half_rn(n0); ci[20] = __float2half_rn(n1); ci[21] = __float2half_rn(n2);
+		#pragma unroll
+		for (int k = 22; k < 32; ++k) ci[k] = __float2half(0.f);
+	} else {
+		const int s = lane - 16;
+		sh4(sCoord[s * 7 + 4], sCoord[s * 7 + 5], sCoord[s * 7 + 6], sCIN + s * LD_X0);
+	}
+	__syncwarp();
+
+	// --- colour MLP (48 -> 64 -> 64 -> 16)
+	uint32_t h1a[4][4], h2a[4][4];
+	{
+		uint32_t ca[3][4];
+		ca[0][0] = soa[0]; ca[0][1] = soa[1]; ca[0][2] = soa[2]; ca[0][3] = soa[3];
+		load_a_frag(ca[1], sCIN, LD_X0, 0, g, t);
+		load_a_frag(ca[2], sCIN, LD_X0, 16, g, t);
+		float c[8][4];
+		mma_layer<3, 8>(ca, sw + WeightSmem::C0, LD_C0, c, g, t);
+		pack_frags<8, true>(c, h1a);
+	}
+	{
+		float c[8][4];
+		mma_layer<4, 8>(h1a, sw + WeightSmem::C1, LD_H, c, g, t);
+		pack_frags<8, true>(c, h2a);
+	}
+	{
+		float c[2][4];
+		mma_layer<4, 2>(h2a, sw + WeightSmem::C2, LD_H, c, g, t);
+		store_c_smem<2>(c, sOUT, 16, g, t);
+	}
+	__syncwarp();
+	// --- output assembly (nerf_network.h:287-325)
+	if (lane < 16) {
+		const int s = lane;
+		__half* o = sOUT + s * 16;
+		o[3] = __hadd(sSDF[s], __float2half_rn(sdf_bias));
+		o[4] = __float2half_rn(sNRM[s * 3 + 0]); o[5] = __float2half_rn(sNRM[s * 3 + 1]); o[6] = __float2half_rn(sNRM[s * 3 + 2]);
+		o[7] = params[pl.off_var];
+		o[8] = __float2half_rn(sCoord[s * 7 + 4]); o[9] = __float2half_rn(sCoord[s * 7 + 5]); o[10] = __float2half_rn(sCoord[s * 7 + 6]);
+	}
+	__syncwarp();
+	if (KEEP) {
+		#pragma unroll
+		for (int kt = 0; kt < 4; ++kt) {
+			#pragma unroll
+			for (int r = 0; r < 4; ++r) { st.h0a[kt][r] = h0a[kt][r]; st.h1a[kt][r] = h1a[kt][r]; st.h2a[kt][r] = h2a[kt][r]; }
+		}
+		st.soa[0] = soa[0]; st.soa[1] = soa[1]; st.soa[2] = soa[2]; st.soa[3] = soa[3];
+	}
+}

@@ -1,0 +1,432 @@
+// network_kernels.cu -- fused NeuS network kernels: inference forward, SDF/density only, and the fused
+// forward+backward training kernel.  See network.cuh for the per-warp pipeline.
+#include "network.cuh"
+#include "kernels.h"
+
+#define WARPS_PER_CTA 8
+#define THREADS_PER_CTA (WARPS_PER_CTA * 32)
+
+static constexpr int FWD_SMEM = WeightSmem::FWD_END * 2 + WARPS_PER_CTA * WarpSlab::FWD_END;
+static constexpr int BWD_SMEM = WeightSmem::BWD_END * 2 + WARPS_PER_CTA * WarpSlab::BWD_END;
+
+// coalesced load of a tile's coords (16 x 7 floats) into the warp slab; rows >= n_valid are zero-filled.
+// src_row(i) maps tile row -> source row (identity, or the fill_rollover wrap).
+__device__ __forceinline__ void load_coords(float* sCoord, const float* __restrict__ coords, uint32_t row0, uint32_t n, uint32_t wrap, int lane) {
+	for (int i = lane; i < 16 * 7; i += 32) {
+		const uint32_t r = row0 + i / 7;
+		float v = 0.f;
+		if (r < n) {
+			const uint32_t src = wrap ? (r % wrap) : r;
+			v = coords[(size_t)src * 7 + (i % 7)];
+		}
+		sCoord[i] = v;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// Inference forward: coords [n][7] -> out [n][16] half   (NerfNetwork::inference_mixed_precision_impl ==
+// forward_impl, nerf_network.h:100-103,145-328)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS_PER_CTA, 2)
+k_network_forward(GridMeta gm, ParamLayout pl, const __half* __restrict__ params, const float* __restrict__ coords,
+                  const uint32_t* __restrict__ n_ptr, uint32_t n_max, float sdf_bias, __half* __restrict__ out) {
+	extern __shared__ __align__(16) unsigned char smem[];
+	__half* sw = reinterpret_cast<__half*>(smem);
+	stage_weights(sw, params, pl, false, threadIdx.x, blockDim.x);
+	__syncthreads();
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	unsigned char* slab = smem + WeightSmem::FWD_END * 2 + warp * WarpSlab::FWD_END;
+	uint32_t n = n_ptr ? *n_ptr : n_max;
+	if (n > n_max) n = n_max;
+	const uint32_t n_tiles = (n + TILE - 1) / TILE;
+	FwdState st;
+	for (uint32_t tile = blockIdx.x * WARPS_PER_CTA + warp; tile < n_tiles; tile += gridDim.x * WARPS_PER_CTA) {
+		const uint32_t row0 = tile * TILE;
+		load_coords(reinterpret_cast<float*>(slab + WarpSlab::COORD), coords, row0, n, 0, lane);
+		__syncwarp();
+		forward_tile<false>(gm, params, pl, sw, slab, sdf_bias, lane, st);
+		// 16 rows x 32 B, coalesced 16-byte stores
+		const uint32_t r = row0 + (lane >> 1);
+		if (r < n) {
+			const uint4 v = reinterpret_cast<const uint4*>(slab + WarpSlab::OUT)[lane];
+			reinterpret_cast<uint4*>(out)[(size_t)r * 2 + (lane & 1)] = v;
+		}
+		__syncwarp();
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// SDF / density only: positions [n][stride] -> half [n]   (NerfNetwork::sdf / density, nerf_network.h:656-739;
+// sdf_to_density_variance_buffer, common_operation.cuh:306-324)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS_PER_CTA, 2)
+k_network_sdf(GridMeta gm, ParamLayout pl, const __half* __restrict__ params, const float* __restrict__ pos, uint32_t stride,
+              uint32_t n, float sdf_bias, int as_density, __half* __restrict__ out_h, float* __restrict__ out_f) {
+	extern __shared__ __align__(16) unsigned char smem[];
+	__half* sw = reinterpret_cast<__half*>(smem);
+	stage_matrix(sw + WeightSmem::W0, LD_X0, params + pl.off_w0, 64, SDF_IN, threadIdx.x, blockDim.x);
+	stage_matrix(sw + WeightSmem::W1, LD_H, params + pl.off_w1, 16, 64, threadIdx.x, blockDim.x);
+	__syncthreads();
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int g = lane >> 2, t = lane & 3;
+	unsigned char* slab = smem + WeightSmem::FWD_END * 2 + warp * WarpSlab::FWD_END;
+	float* sCoord = reinterpret_cast<float*>(slab + WarpSlab::COORD);
+	__half* sX0 = reinterpret_cast<__half*>(slab + WarpSlab::X0);
+	__half* sSDF = reinterpret_cast<__half*>(slab + WarpSlab::SDF);
+	const uint32_t n_tiles = (n + TILE - 1) / TILE;
+	const __half variance = params[pl.off_var];
+	for (uint32_t tile = blockIdx.x * WARPS_PER_CTA + warp; tile < n_tiles; tile += gridDim.x * WARPS_PER_CTA) {
+		const uint32_t row0 = tile * TILE;
+		for (int i = lane; i < 16 * 3; i += 32) {
+			const uint32_t r = row0 + i / 3;
+			sCoord[(i / 3) * 7 + (i % 3)] = r < n ? pos[(size_t)r * stride + (i % 3)] : 0.f;
+		}
+		__syncwarp();
+		if (lane < 16) {
+			#pragma unroll
+			for (int d = 0; d < 3; ++d) sX0[lane * LD_X0 + d] = __hsub(__float2half_rn(sCoord[lane * 7 + d]), __float2half_rn(0.5f));
+			for (int k = 3 + 2 * (int)gm.n_levels; k < SDF_IN; ++k) sX0[lane * LD_X0 + k] = __float2half(0.f);
+		}
+		gather_tile<false>(gm, params + pl.off_grid, sCoord, sX0, nullptr, lane);
+		__syncwarp();
+		uint32_t xa[2][4], h0a[4][4];
+		load_a_frag(xa[0], sX0, LD_X0, 0, g, t);
+		load_a_frag(xa[1], sX0, LD_X0, 16, g, t);
+		{
+			float c[8][4];
+			mma_layer<2, 8>(xa, sw + WeightSmem::W0, LD_X0, c, g, t);
+			pack_frags<8, true>(c, h0a);
+		}
+		{
+			float c[1][4];   // only output n-tile 0 is needed (sdf = output 0)
+			mma_layer<4, 1>(h0a, sw + WeightSmem::W1, LD_H, c, g, t);
+			if (t == 0) { sSDF[g] = __float2half_rn(c[0][0]); sSDF[g + 8] = __float2half_rn(c[0][2]); }
+		}
+		__syncwarp();
+		if (lane < 16 && row0 + lane < n) {
+			__half sdf = __hadd(sSDF[lane], __float2half_rn(sdf_bias));
+			__half r = sdf;
+			if (as_density) {
+				// all in half arithmetic as the reference's T = __half instantiation
+				const __half s = __float2half_rn(__expf(__half2float(__hmul(variance, __float2half_rn(10.0f)))));
+				const float xs = __half2float(__hmul(sdf, s));
+				const __half sig = __float2half_rn(1.0f / (1.0f + expf(-xs)));
+				const __half density = __hmul(__hmul(s, sig), __hsub(__float2half_rn(1.0f), sig));
+				r = density;
+			}
+			if (out_h) out_h[row0 + lane] = r;
+			if (out_f) out_f[row0 + lane] = __half2float(r);
+		}
+		__syncwarp();
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// Training: fused second forward + full backward (nerf_network.h:330-601) for the compacted batch.
+//   rows i in [0, n_rows):  source row = i % n_in (fill_rollover, tcnn common_device.h:515-534); dL rows of
+//   wrapped copies are scaled by n_in / n_rows and re-rounded to half.
+// Outputs:
+//   grads_f32[grid part]  += first + second order grid gradients (fp32 vector atomics)
+//   var_acc               += sum of dL/dout row 7
+//   w1row0_acc[64]        += column sums of the forward-mode sweep (second-order term of W1 row 0)
+//   staged operand matrices (half, row-major [n_rows][w]) for the weight-gradient GEMMs.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS_PER_CTA, 1)
+k_network_fwdbwd(GridMeta gm, ParamLayout pl, const __half* __restrict__ params, const float* __restrict__ coords,
+                 const __half* __restrict__ dL_dout, const uint32_t* __restrict__ n_in_ptr, uint32_t n_rows, float sdf_bias,
+                 float batch_f, float* __restrict__ grads, float* __restrict__ var_acc, float* __restrict__ w1row0_acc, StagedOperands so) {
+	extern __shared__ __align__(16) unsigned char smem[];
+	__half* sw = reinterpret_cast<__half*>(smem);
+	stage_weights(sw, params, pl, true, threadIdx.x, blockDim.x);
+	__syncthreads();
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int g = lane >> 2, t = lane & 3;
+	unsigned char* slab = smem + WeightSmem::BWD_END * 2 + warp * WarpSlab::BWD_END;
+	float* sCoord = reinterpret_cast<float*>(slab + WarpSlab::COORD);
+	__half* sX0 = reinterpret_cast<__half*>(slab + WarpSlab::X0);
+	__half* sDIN = reinterpret_cast<__half*>(slab + WarpSlab::DIN);
+	__half* sCIN = reinterpret_cast<__half*>(slab + WarpSlab::CIN);
+	float* sDY = reinterpret_cast<float*>(slab + WarpSlab::DY);
+	__half* sDL = reinterpret_cast<__half*>(slab + WarpSlab::DL);
+	__half* sDX = reinterpret_cast<__half*>(slab + WarpSlab::DX);
+	__half* sDI = reinterpret_cast<__half*>(slab + WarpSlab::DI);
+	float* sV = reinterpret_cast<float*>(slab + WarpSlab::V);
+	__half* sVN = reinterpret_cast<__half*>(slab + WarpSlab::VN);
+
+	uint32_t n_in = *n_in_ptr;
+	if (n_in > n_rows) n_in = n_rows;
+	const uint32_t n_tiles = n_in == 0 ? 0 : (n_rows + TILE - 1) / TILE;
+	const float wrap_scale_num = (float)n_in, wrap_scale_den = (float)n_rows;
+	float var_local = 0.f;
+	float w1acc[4][4];
+	#pragma unroll
+	for (int a = 0; a < 4; ++a) { w1acc[a][0] = w1acc[a][1] = w1acc[a][2] = w1acc[a][3] = 0.f; }
+	float* ggrid = grads + pl.off_grid;
+	const int E = 2 * (int)gm.n_levels;
+
+	FwdState st;
+	for (uint32_t tile = blockIdx.x * WARPS_PER_CTA + warp; tile < n_tiles; tile += gridDim.x * WARPS_PER_CTA) {
+		const uint32_t row0 = tile * TILE;
+		const int n_valid = (int)min((uint32_t)TILE, n_rows - row0);
+		load_coords(sCoord, coords, row0, n_rows, n_in, lane);
+		// dL/dout rows with the rollover wrap + rescale (fill_rollover_and_rescale)
+		for (int i = lane; i < 16 * 16; i += 32) {
+			const uint32_t r = row0 + (i >> 4);
+			__half v = __float2half(0.f);
+			if (r < n_rows) {
+				if (r < n_in) v = dL_dout[(size_t)r * 16 + (i & 15)];
+				else v = __float2half_rn(__fdiv_rn(__fmul_rn(__half2float(dL_dout[(size_t)(r % n_in) * 16 + (i & 15)]), wrap_scale_num), wrap_scale_den));
+			}
+			sDL[i] = v;
+		}
+		__syncwarp();
+		forward_tile<true>(gm, params, pl, sw, slab, sdf_bias, lane, st);
+
+		// ---- colour MLP backward (fully_fused_mlp.cu:968-1085) -----------------------------------
+		uint32_t dout[1][4];   // dL/drgb: only output columns 0..2 (extract_rgb, nerf_network.h:345-349)
+		{
+			uint32_t r0 = *reinterpret_cast<const uint32_t*>(sDL + g * 16 + 2 * t);
+			uint32_t r1 = *reinterpret_cast<const uint32_t*>(sDL + (g + 8) * 16 + 2 * t);
+			if (t == 1) { r0 &= 0xffffu; r1 &= 0xffffu; }
+			if (t >= 2) { r0 = 0u; r1 = 0u; }
+			dout[0][0] = r0; dout[0][1] = r1; dout[0][2] = 0u; dout[0][3] = 0u;
+		}
+		{   // stage dL/drgb rows [16][16]: one 16-byte store per lane
+			const int r = lane >> 1;
+			uint4 v = make_uint4(0u, 0u, 0u, 0u);
+			if ((lane & 1) == 0) {
+				v.x = *reinterpret_cast<const uint32_t*>(sDL + r * 16);
+				v.y = *reinterpret_cast<const uint32_t*>(sDL + r * 16 + 2) & 0xffffu;
+			}
+			if (r < n_valid) reinterpret_cast<uint4*>(so.dOUT + (size_t)(row0 + r) * 16)[lane & 1] = v;
+		}
+		uint32_t dh2a[4][4], dh1a[4][4];
+		{
+			float c[8][4];
+			mma_layer<1, 8>(dout, sw + WeightSmem::C2T, LD_T16, c, g, t);
+			pack_frags_masked<8>(c, st.h2a, dh2a);
+		}
+		store_a_global<4>(st.h2a, so.H2, 64, row0, n_valid, g, t);
+		store_a_global<4>(dh2a, so.dH2, 64, row0, n_valid, g, t);
+		{
+			float c[8][4];
+			mma_layer<4, 8>(dh2a, sw + WeightSmem::C1T, LD_H, c, g, t);
+			pack_frags_masked<8>(c, st.h1a, dh1a);
+		}
+		store_a_global<4>(st.h1a, so.H1, 64, row0, n_valid, g, t);
+		store_a_global<4>(dh1a, so.dH1, 64, row0, n_valid, g, t);
+		uint32_t dso[1][4];
+		{
+			float c[6][4];
+			mma_layer<4, 6>(dh1a, sw + WeightSmem::C0T, LD_H, c, g, t);
+			// cols 0..15 -> gradient of the sdf-MLP output; + dL/dsdf on column 0 (add_density_gradient, nerf_network.h:401-408)
+			float c00 = round_h(c[0][0]), c02 = round_h(c[0][2]);
+			if (t == 0) {
+				c00 = __half2float(__hadd(__float2half_rn(c[0][0]), sDL[g * 16 + 3]));
+				c02 = __half2float(__hadd(__float2half_rn(c[0][2]), sDL[(g + 8) * 16 + 3]));
+			}
+			dso[0][0] = pack_h2(c00, c[0][1]);
+			dso[0][1] = pack_h2(c02, c[0][3]);
+			dso[0][2] = pack_h2(c[1][0], c[1][1]);
+			dso[0][3] = pack_h2(c[1][2], c[1][3]);
+			// cols 32..39 (n-tile 4) -> shared, the normal slots are 35..37
+			*reinterpret_cast<uint32_t*>(sVN + g * 8 + 2 * t) = pack_h2(c[4][0], c[4][1]);
+			*reinterpret_cast<uint32_t*>(sVN + (g + 8) * 8 + 2 * t) = pack_h2(c[4][2], c[4][3]);
+		}
+		// colour-MLP input [n][48]: cols 0..15 from registers, 16..47 from the slab
+		{
+			uint32_t tmp[1][4] = {{st.soa[0], st.soa[1], st.soa[2], st.soa[3]}};
+			store_a_global<1>(tmp, so.CIN, 48, row0, n_valid, g, t);
+			for (int i = lane; i < 16 * 16; i += 32) {   // 16 rows x 16 words (32 halves)
+				const int r = i >> 4, w = i & 15;
+				if (r < n_valid) reinterpret_cast<uint32_t*>(so.CIN + (size_t)(row0 + r) * 48 + 16)[w] = reinterpret_cast<const uint32_t*>(sCIN + r * LD_X0)[w];
+			}
+		}
+		// ---- sdf MLP backward --------------------------------------------------------------------
+		uint32_t dh0a[4][4];
+		{
+			float c[8][4];
+			mma_layer<1, 8>(dso, sw + WeightSmem::W1T, LD_T16, c, g, t);
+			pack_frags_masked<8>(c, st.h0a, dh0a);
+		}
+		store_a_global<1>(dso, so.dSO, 16, row0, n_valid, g, t);
+		store_a_global<4>(st.h0a, so.H0, 64, row0, n_valid, g, t);
+		store_a_global<4>(dh0a, so.dH0, 64, row0, n_valid, g, t);
+		{
+			float c[4][4];
+			mma_layer<4, 4>(dh0a, sw + WeightSmem::W0T, LD_H, c, g, t);
+			store_c_smem<4>(c, sDX, LD_X0, g, t);
+		}
+		// sdf-MLP input [n][32]
+		for (int i = lane; i < 16 * 16; i += 32) {
+			const int r = i >> 4, w = i & 15;
+			if (r < n_valid) reinterpret_cast<uint32_t*>(so.X0 + (size_t)(row0 + r) * 32)[w] = reinterpret_cast<const uint32_t*>(sX0 + r * LD_X0)[w];
+		}
+		__syncwarp();
+		// ---- per-sample: v = dL/d normal, pos_encoding_dy, second-order sdf-MLP input (nerf_network.h:476-570)
+		if (lane < 16) {
+			const int s = lane;
+			float v[3];
+			#pragma unroll
+			for (int d = 0; d < 3; ++d) {
+				float a = __half2float(sVN[s * 8 + 3 + d]);
+				a = __fadd_rn(a, __fdiv_rn(__half2float(sDL[s * 16 + 4 + d]), batch_f));
+				a = __fadd_rn(a, __half2float(sDL[s * 16 + 8 + d]));
+				v[d] = a;
+				sV[s * 3 + d] = a;
+				sDI[s * LD_X0 + d] = __float2half_rn(a);
+			}
+			for (int k = 0; k < E; ++k) {   // kernel_grid_backward_input_backward_dLdoutput, grid.h:1183-1207
+				float r = 0.f;
+				r = fmaf(sDY[s * LD_DY + 3 * k + 0], v[0], r);
+				r = fmaf(sDY[s * LD_DY + 3 * k + 1], v[1], r);
+				r = fmaf(sDY[s * LD_DY + 3 * k + 2], v[2], r);
+				sDI[s * LD_X0 + 3 + k] = __float2half_rn(r);
+			}
+			for (int k = 3 + E; k < SDF_IN; ++k) sDI[s * LD_X0 + k] = __float2half(0.f);
+			if (s < n_valid) var_local += __half2float(sDL[s * 16 + 7]);
+		}
+		__syncwarp();
+		// ---- second-order sdf-MLP sweeps (fully_fused_mlp.cu:1089-1198)
+		{
+			// back sweep operand: relu'(h0) * W1[0,:]  (seed e0)   -> staged as gH
+			uint32_t gh[4][4];
+			#pragma unroll
+			for (int kt = 0; kt < 4; ++kt) {
+				const uint32_t wlo = *reinterpret_cast<const uint32_t*>(sw + WeightSmem::W1 + 16 * kt + 2 * t);
+				const uint32_t whi = *reinterpret_cast<const uint32_t*>(sw + WeightSmem::W1 + 16 * kt + 8 + 2 * t);
+				gh[kt][0] = wlo & relu_mask2(st.h0a[kt][0]);
+				gh[kt][1] = wlo & relu_mask2(st.h0a[kt][1]);
+				gh[kt][2] = whi & relu_mask2(st.h0a[kt][2]);
+				gh[kt][3] = whi & relu_mask2(st.h0a[kt][3]);
+			}
+			store_a_global<4>(gh, so.gH, 64, row0, n_valid, g, t);
+			// forward-mode sweep: relu'(h0) * (W0 d_in)  -> contributes to dW1 row 0 (column sums over samples)
+			uint32_t da[2][4];
+			load_a_frag(da[0], sDI, LD_X0, 0, g, t);
+			load_a_frag(da[1], sDI, LD_X0, 16, g, t);
+			float c[8][4];
+			mma_layer<2, 8>(da, sw + WeightSmem::W0, LD_X0, c, g, t);
+			uint32_t tf[4][4];
+			pack_frags_masked<8>(c, st.h0a, tf);
+			#pragma unroll
+			for (int kt = 0; kt < 4; ++kt) {
+				// rows g (regs 0,2) and g+8 (regs 1,3); invalid rows were zero-input so they add 0 -- but mask anyway
+				const float m0 = g < n_valid ? 1.f : 0.f, m1 = g + 8 < n_valid ? 1.f : 0.f;
+				w1acc[kt][0] += m0 * h_lo(tf[kt][0]) + m1 * h_lo(tf[kt][1]);
+				w1acc[kt][1] += m0 * h_hi(tf[kt][0]) + m1 * h_hi(tf[kt][1]);
+				w1acc[kt][2] += m0 * h_lo(tf[kt][2]) + m1 * h_lo(tf[kt][3]);
+				w1acc[kt][3] += m0 * h_hi(tf[kt][2]) + m1 * h_hi(tf[kt][3]);
+			}
+			for (int i = lane; i < 16 * 16; i += 32) {
+				const int r = i >> 4, w = i & 15;
+				if (r < n_valid) reinterpret_cast<uint32_t*>(so.dI + (size_t)(row0 + r) * 32)[w] = reinterpret_cast<const uint32_t*>(sDI + r * LD_X0)[w];
+			}
+		}
+		// ---- hash-grid gradient: first order (grid.h:371-500) + second order (grid.h:880-1007), one vector
+		//      atomic per corner instead of 8 + 24 half2 atomics.
+		{
+			const int s = lane & 15;
+			if (s < n_valid) {
+				const float x = sCoord[s * 7 + 0], y = sCoord[s * 7 + 1], z = sCoord[s * 7 + 2];
+				const float v0 = sV[s * 3 + 0], v1 = sV[s * 3 + 1], v2 = sV[s * 3 + 2];
+				for (int l = lane >> 4; l < (int)gm.n_levels; l += 2) {
+					if ((uint32_t)l > gm.valid_level) continue;
+					LevelGeom lg;
+					level_geom(gm, l, x, y, z, lg);
+					const float scale = gm.scale[l];
+					const float d0 = __half2float(sDX[s * LD_X0 + 3 + 2 * l]), d1 = __half2float(sDX[s * LD_X0 + 4 + 2 * l]);   // dL/d enc
+					const float e0 = __half2float(sDIN[s * LD_X0 + 3 + 2 * l]), e1 = __half2float(sDIN[s * LD_X0 + 4 + 2 * l]); // d sdf/d enc
+					const float wx[2] = {1.f - lg.w[0], lg.w[0]}, wy[2] = {1.f - lg.w[1], lg.w[1]}, wz[2] = {1.f - lg.w[2], lg.w[2]};
+					const float gi0 = scale * v0, gi1 = scale * v1, gi2 = scale * v2;   // grad_in (pos_derivative = 1)
+					float* gl = ggrid + (size_t)gm.offset[l] * 2;
+					#pragma unroll
+					for (int c = 0; c < 8; ++c) {
+						const int bx = c & 1, by = (c >> 1) & 1, bz = (c >> 2) & 1;
+						const float w1 = (wx[bx] * wy[by]) * wz[bz];
+						// second order: sum over grad_dim of +-(grad_in * w_other0 * w_other1)
+						const float sx = (gi0 * wy[by]) * wz[bz], sy = (gi1 * wx[bx]) * wz[bz], sz = (gi2 * wx[bx]) * wy[by];
+						const float w2 = (bx ? sx : -sx) + (by ? sy : -sy) + (bz ? sz : -sz);
+						const float a0 = d0 * w1 + e0 * w2, a1 = d1 * w1 + e1 * w2;
+						atomicAdd(reinterpret_cast<float2*>(gl + lg.idx[c]), make_float2(a0, a1));
+					}
+				}
+			}
+		}
+		__syncwarp();
+	}
+	// ---- flush per-warp accumulators
+	#pragma unroll
+	for (int kt = 0; kt < 4; ++kt) {
+		#pragma unroll
+		for (int r = 0; r < 4; ++r) {
+			float v = w1acc[kt][r];
+			v += __shfl_xor_sync(0xffffffffu, v, 4);
+			v += __shfl_xor_sync(0xffffffffu, v, 8);
+			v += __shfl_xor_sync(0xffffffffu, v, 16);
+			if (g == 0 && v != 0.f) atomicAdd(w1row0_acc + 16 * kt + 8 * (r >> 1) + 2 * t + (r & 1), v);
+		}
+	}
+	var_local += __shfl_xor_sync(0xffffffffu, var_local, 1);
+	var_local += __shfl_xor_sync(0xffffffffu, var_local, 2);
+	var_local += __shfl_xor_sync(0xffffffffu, var_local, 4);
+	var_local += __shfl_xor_sync(0xffffffffu, var_local, 8);
+	var_local += __shfl_xor_sync(0xffffffffu, var_local, 16);
+	if (lane == 0 && var_local != 0.f) atomicAdd(var_acc, var_local);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------
+static int g_num_sms = 0;
+static int num_sms() {
+	if (!g_num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev); }
+	return g_num_sms;
+}
+
+int launch_network_forward(cudaStream_t stream, const GridMeta& gm, const ParamLayout& pl, const __half* params, const float* coords,
+                           const uint32_t* n_ptr, uint32_t n_max, float sdf_bias, __half* out) {
+	static bool attr = false;
+	if (!attr) { CUDA_CHECK(cudaFuncSetAttribute(k_network_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM)); attr = true; }
+	if (n_max == 0) return 0;
+	const uint32_t n_tiles = (n_max + TILE - 1) / TILE;
+	uint32_t grid = (uint32_t)num_sms() * 2;
+	const uint32_t need = (n_tiles + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+	if (need < grid) grid = need;
+	k_network_forward<<<grid, THREADS_PER_CTA, FWD_SMEM, stream>>>(gm, pl, params, coords, n_ptr, n_max, sdf_bias, out);
+	COUNT_LAUNCH(1);
+	CUDA_CHECK(cudaGetLastError());
+	return 0;
+}
+
+int launch_network_sdf(cudaStream_t stream, const GridMeta& gm, const ParamLayout& pl, const __half* params, const float* pos, uint32_t stride,
+                       uint32_t n, float sdf_bias, int as_density, __half* out_h, float* out_f) {
+	static bool attr = false;
+	if (!attr) { CUDA_CHECK(cudaFuncSetAttribute(k_network_sdf, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM)); attr = true; }
+	if (n == 0) return 0;
+	const uint32_t n_tiles = (n + TILE - 1) / TILE;
+	uint32_t grid = (uint32_t)num_sms() * 2;
+	const uint32_t need = (n_tiles + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+	if (need < grid) grid = need;
+	k_network_sdf<<<grid, THREADS_PER_CTA, FWD_SMEM, stream>>>(gm, pl, params, pos, stride, n, sdf_bias, as_density, out_h, out_f);
+	COUNT_LAUNCH(1);
+	CUDA_CHECK(cudaGetLastError());
+	return 0;
+}
+
+int launch_network_fwdbwd(cudaStream_t stream, const GridMeta& gm, const ParamLayout& pl, const __half* params, const float* coords,
+                          const __half* dL_dout, const uint32_t* n_in_ptr, uint32_t n_rows, float sdf_bias, uint32_t indeed_batch_size,
+                          float* grads, float* var_acc, float* w1row0_acc, const StagedOperands& so) {
+	static bool attr = false;
+	if (!attr) { CUDA_CHECK(cudaFuncSetAttribute(k_network_fwdbwd, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM)); attr = true; }
+	if (n_rows == 0) return 0;
+	const uint32_t n_tiles = (n_rows + TILE - 1) / TILE;
+	uint32_t grid = (uint32_t)num_sms();
+	const uint32_t need = (n_tiles + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+	if (need < grid) grid = need;
+	k_network_fwdbwd<<<grid, THREADS_PER_CTA, BWD_SMEM, stream>>>(gm, pl, params, coords, dL_dout, n_in_ptr, n_rows, sdf_bias,
+		(float)indeed_batch_size, grads, var_acc, w1row0_acc, so);
+	COUNT_LAUNCH(1);
+	CUDA_CHECK(cudaGetLastError());
+	return 0;
+}

@@ -1,0 +1,137 @@
+// sampling.cu -- training-ray generation and occupancy-grid marching (compiled with -fmad=false).
+// Restates generate_training_samples_nerf_with_global_movement (src/testbed_nerf.cu:1263-1456), made
+// deterministic: instead of ordering rays by atomicAdd arrival (:1421,:1428) the sample base offsets and ray
+// slots come from exclusive scans in ray-index order.  Per-ray numsteps are unchanged.
+// Data-parallel sharding: a rank traces global rays [ray_offset, ray_offset + n_rays) of a batch of n_rays_global;
+// image / pixel / jitter are pure functions of the GLOBAL ray index (:1241-1261,:1304).
+#include "ngp_common.cuh"
+#include "ngp_kernels.h"
+
+struct RaySetup { float o[3], d[3], ray_o[3], dir[3], startt; bool skip; };
+
+__device__ __forceinline__ RaySetup setup_ray(uint32_t i, uint32_t n_rays, uint32_t n_rays_total, Pcg32 rng, const DatasetDev& ds,
+                                               const Aabb& bb, const GlobalMove& gmv, bool snap, float cone_angle) {
+	RaySetup r;
+	r.skip = false;
+	const uint32_t img = image_idx(i, n_rays, n_rays_total, ds.n_images);
+	rng.advance((int64_t)(uint32_t)(i * N_MAX_RANDOM_SAMPLES_PER_RAY));
+	float xy[2];
+	random_image_pos_training(rng, ds.width, ds.height, snap, xy);
+	int px, py; image_pos(xy, ds.width, ds.height, &px, &py);
+	float rgba[4]; read_rgba(ds, img, px, py, rgba);
+	if (rgba[0] <= 0.0f && rng.next_float() >= 0.9) { r.skip = true; return r; }   // :1310
+	(void)rng.next_float();                                                         // motionblur_time :1317
+	make_ray(ds, img, xy, r.o, r.d);
+	#pragma unroll
+	for (int k = 0; k < 3; ++k) r.ray_o[k] = r.o[k];
+	normalize3(r.d, r.dir);
+	#pragma unroll
+	for (int k = 0; k < 3; ++k) r.ray_o[k] -= gmv.first_frame_offset[k];
+	global_move(gmv, r.ray_o, r.dir);
+	float tmin, tmax; ray_intersect(bb, r.ray_o, r.dir, &tmin, &tmax);
+	tmin = fmaxf(tmin, 0.0f);                                                       // :1395
+	r.startt = tmin + calc_dt(tmin, cone_angle) * rng.next_float();                 // :1397-1398
+	return r;
+}
+
+__global__ void k_rays_count(uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, uint32_t n_rays_total, Pcg32 rng, DatasetDev ds, Aabb bb, GlobalMove gmv,
+                             const uint8_t* __restrict__ bitfield, int snap, float cone_angle, uint32_t* __restrict__ numsteps_all) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_rays) return;
+	RaySetup r = setup_ray(i + ray_offset, n_rays_global, n_rays_total, rng, ds, bb, gmv, snap != 0, cone_angle);
+	uint32_t j = 0;
+	if (!r.skip) j = march_ray(bb, r.ray_o, r.dir, r.startt, cone_angle, bitfield, NERF_STEPS, nullptr);
+	numsteps_all[i] = j;
+}
+
+// Single-CTA two-stage exclusive scan over <= 2^20 elements (n_rays <= 2^18 in practice):
+//   base[i]  = exclusive sum of counts;      counters[1] = total (the reference's numsteps_counter incl. dropped rays)
+//   keep[i]  = count>0 && base+count <= max_samples;  slot[i] = exclusive sum of keep;  counters[0] = number kept
+#define SCAN_THREADS 1024
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* warp_sums, uint32_t* total) {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t inc = v;
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+	if (lane == 31) warp_sums[warp] = inc;
+	__syncthreads();
+	if (warp == 0) {
+		uint32_t w = warp_sums[lane];
+		uint32_t winc = w;
+		#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += y; }
+		warp_sums[lane] = winc - w;
+		if (lane == 31) *total = winc;
+	}
+	__syncthreads();
+	const uint32_t r = warp_sums[warp] + inc - v;
+	__syncthreads();
+	return r;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_rays(uint32_t n, const uint32_t* __restrict__ counts, uint32_t max_samples, uint32_t* __restrict__ base, uint32_t* __restrict__ slot,
+            uint32_t* __restrict__ counters) {
+	__shared__ uint32_t warp_sums[32];
+	__shared__ uint32_t total;
+	const uint32_t per = (n + SCAN_THREADS - 1) / SCAN_THREADS;
+	const uint32_t b = min(n, threadIdx.x * per), e = min(n, b + per);
+	uint32_t s = 0;
+	for (uint32_t i = b; i < e; ++i) s += counts[i];
+	uint32_t off = block_exclusive_scan(s, warp_sums, &total);
+	if (threadIdx.x == 0) counters[1] = total;
+	uint32_t kept = 0;
+	for (uint32_t i = b; i < e; ++i) {
+		const uint32_t c = counts[i];
+		base[i] = off;
+		const bool k = c > 0 && off + c <= max_samples;
+		kept += k ? 1u : 0u;
+		off += c;
+	}
+	uint32_t soff = block_exclusive_scan(kept, warp_sums, &total);
+	if (threadIdx.x == 0) counters[0] = total;
+	for (uint32_t i = b; i < e; ++i) {
+		const uint32_t c = counts[i];
+		const bool k = c > 0 && base[i] + c <= max_samples;
+		slot[i] = k ? soff : 0xffffffffu;
+		soff += k ? 1u : 0u;
+	}
+}
+
+__global__ void k_rays_emit(uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, uint32_t n_rays_total, Pcg32 rng, DatasetDev ds, Aabb bb, GlobalMove gmv,
+                            const uint8_t* __restrict__ bitfield, int snap, float cone_angle, const uint32_t* __restrict__ numsteps_all,
+                            const uint32_t* __restrict__ base, const uint32_t* __restrict__ slot,
+                            uint32_t* __restrict__ ray_indices, float* __restrict__ rays, uint32_t* __restrict__ numsteps, float* __restrict__ coords) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_rays) return;
+	const uint32_t sl = slot[i];
+	if (sl == 0xffffffffu) return;
+	RaySetup r = setup_ray(i + ray_offset, n_rays_global, n_rays_total, rng, ds, bb, gmv, snap != 0, cone_angle);
+	const uint32_t j = numsteps_all[i], b = base[i];
+	ray_indices[sl] = i + ray_offset;
+	#pragma unroll
+	for (int k = 0; k < 3; ++k) { rays[(size_t)sl * 6 + k] = r.o[k]; rays[(size_t)sl * 6 + 3 + k] = r.d[k]; }
+	numsteps[sl * 2 + 0] = j;
+	numsteps[sl * 2 + 1] = b;
+	march_ray(bb, r.ray_o, r.dir, r.startt, cone_angle, bitfield, j, coords + (size_t)b * 7);
+}
+
+int launch_generate_training_samples(cudaStream_t stream, uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, uint32_t n_rays_total, const uint64_t rng_state[2], const DatasetDev& ds,
+                                     const Aabb& bb, const GlobalMove& gmv, const uint8_t* bitfield, int snap, float cone_angle, uint32_t max_samples,
+                                     uint32_t* numsteps_all, uint32_t* base, uint32_t* slot, uint32_t* ray_indices, float* rays, uint32_t* numsteps,
+                                     float* coords, uint32_t* counters) {
+	if (n_rays == 0) return 0;
+	Pcg32 rng; rng.state = rng_state[0]; rng.inc = rng_state[1];
+	const uint32_t blocks = (n_rays + 127) / 128;
+	k_rays_count<<<blocks, 128, 0, stream>>>(n_rays, ray_offset, n_rays_global, n_rays_total, rng, ds, bb, gmv, bitfield, snap, cone_angle, numsteps_all);
+	COUNT_LAUNCH(1);
+	CUDA_CHECK(cudaGetLastError());
+	k_scan_rays<<<1, SCAN_THREADS, 0, stream>>>(n_rays, numsteps_all, max_samples, base, slot, counters);
+	COUNT_LAUNCH(1);
+	CUDA_CHECK(cudaGetLastError());
+	k_rays_emit<<<blocks, 128, 0, stream>>>(n_rays, ray_offset, n_rays_global, n_rays_total, rng, ds, bb, gmv, bitfield, snap, cone_angle, numsteps_all, base, slot,
+	                                       ray_indices, rays, numsteps, coords);
+	COUNT_LAUNCH(1);
+	CUDA_CHECK(cudaGetLastError());
+	return 0;
+}

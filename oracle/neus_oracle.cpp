@@ -244,10 +244,8 @@ void orc_grid_forward(uint32_t n, const float* pos, uint32_t pos_stride, const h
 						pl[gd] = pg[gd] + 1;
 						uint32_t ir = grid_index(hashmap_size, res, pl);
 						for (int f = 0; f < 2; ++f) {
-							// grads += weight * (right - left) * pos_derivative(=1)   (no contraction)
-							float t = weight * (h2f(g[ir + f]) - h2f(g[il + f]));
-							t = t * 1.0f;
-							grads[f][gd] = grads[f][gd] + t;
+							// grads += weight * (right - left) * pos_derivative(=1): one fused multiply-add
+							grads[f][gd] = fmaf(weight, h2f(g[ir + f]) - h2f(g[il + f]), grads[f][gd]);
 						}
 					}
 				}
@@ -297,7 +295,7 @@ void orc_grid_backward_input(uint32_t n, uint32_t n_features, const h16* dL_dy, 
 		float r[3] = {0, 0, 0};
 		for (uint32_t k = 0; k < n_features; ++k) {
 			float dl = h2f(dL_dy[(size_t)k * n + i]);
-			for (int d = 0; d < 3; ++d) r[d] = r[d] + dl * dy_dx[((size_t)k * n + i) * 3 + d];
+			for (int d = 0; d < 3; ++d) r[d] = fmaf(dl, dy_dx[((size_t)k * n + i) * 3 + d], r[d]);
 		}
 		for (int d = 0; d < 3; ++d) dL_dx[(size_t)i * 3 + d] = r[d];
 	}
@@ -348,7 +346,7 @@ void orc_grid_bwdbwd_dLdoutput(uint32_t n, uint32_t n_features, const float* v, 
 		const uint32_t i = (uint32_t)ii;
 		for (uint32_t k = 0; k < n_features; ++k) {
 			float result = 0;
-			for (int d = 0; d < 3; ++d) result = result + dy_dx[((size_t)k * n + i) * 3 + d] * v[(size_t)i * 3 + d];
+			for (int d = 0; d < 3; ++d) result = fmaf(dy_dx[((size_t)k * n + i) * 3 + d], v[(size_t)i * 3 + d], result);
 			out[(size_t)k * n + i] = f2h(result);
 		}
 	}

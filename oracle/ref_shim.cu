@@ -1,0 +1,153 @@
+// ref_shim.cu -- thin C ABI over the REFERENCE's own tiny-cuda-nn fork (dependencies/my_tcnn),
+// compiled against the reference sources in place by oracle/Makefile.ref into oracle/_ref/libtcnn_ref.so.
+//
+// TEST INFRASTRUCTURE ONLY.  This is the "real reference" half of the oracle: it runs the reference's
+// hash-grid and fused-MLP kernels (forward, backward, second-order backward) on the GPU box so that
+// tests/test_ref_kernels.py can pin both the CPU restatement (oracle/neus_oracle.cpp) and the product
+// kernels against them, and bench.py can time them as the reference-CUDA baseline.  Nothing in the
+// product links or loads this library.  No reference source is copied: only its public C++ API is called
+// (encoding.h: create_encoding, network.h: create_network, object.h:96-303 DifferentiableObject).
+#include <tiny-cuda-nn/common.h>
+#include <tiny-cuda-nn/encoding.h>
+#include <tiny-cuda-nn/network.h>
+#include <tiny-cuda-nn/gpu_matrix.h>
+#include <tiny-cuda-nn/gpu_memory.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <memory>
+#include <string>
+
+using namespace tcnn;
+using T = __half;
+
+static thread_local std::string g_err;
+
+struct RefGrid { std::shared_ptr<Encoding<T>> enc; };
+struct RefMlp { std::shared_ptr<Network<T>> net; };
+
+#define REF_TRY try {
+#define REF_CATCH } catch (const std::exception& e) { g_err = e.what(); fprintf(stderr, "ref_shim: %s\n", e.what()); return -1; }
+
+extern "C" {
+
+const char* ref_last_error() { return g_err.c_str(); }
+
+void* ref_grid_create(const char* cfg_json) {
+	try {
+		json cfg = json::parse(cfg_json);
+		auto* g = new RefGrid;
+		// alignment 2 as in NerfNetwork (nerf_network.h:59)
+		g->enc.reset(create_encoding<T>(3, cfg, 2));
+		return g;
+	} catch (const std::exception& e) { g_err = e.what(); fprintf(stderr, "ref_shim: %s\n", e.what()); return nullptr; }
+}
+uint64_t ref_grid_n_params(void* h) { return ((RefGrid*)h)->enc->n_params(); }
+uint32_t ref_grid_out_width(void* h) { return ((RefGrid*)h)->enc->padded_output_width(); }
+void ref_grid_set_training_step(void* h, int step) { ((RefGrid*)h)->enc->set_training_step(step); }
+void ref_grid_destroy(void* h) { delete (RefGrid*)h; }
+
+// Runs, on `iters` repetitions (timed as a whole with CUDA events when ms_out != null):
+//   forward (with dy_dx)                          -> enc_soa [E][n] half (row-major)
+//   backward(dL_dy_soa)  if dL_dy_soa             -> grid_grad (Overwrite, half [n_params]), dL_dx [n][3] float
+//   backward_backward_input(v, dL_dy2_soa) if v   -> grid_grad (Accumulate when dL_dy_soa also given, else Overwrite),
+//                                                    dL_ddLdy_soa [E][n] half
+// coords: device float [n][stride], stride >= 3.  `which` bit0 fwd only timing, bit1 bwd, bit2 bwdbwd (for timing splits).
+int ref_grid_eval(void* h, uint32_t n, const float* coords, uint32_t stride, T* params, T* enc_soa,
+                  const T* dL_dy_soa, float* dL_dx, T* grid_grad,
+                  const float* v, const T* dL_dy2_soa, T* dL_ddLdy_soa, int iters, int which, float* ms_out) {
+	REF_TRY
+	auto& enc = ((RefGrid*)h)->enc;
+	const uint32_t E = enc->padded_output_width();
+	enc->set_params(params, params, nullptr, grid_grad);
+	cudaStream_t stream = nullptr;
+	GPUMatrixDynamic<float> full((float*)coords, stride, n, CM);
+	GPUMatrixDynamic<float> pos = full.slice_rows(0, 3);
+	GPUMatrixDynamic<T> out(enc_soa, E, n, RM);
+	cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+	if (iters < 1) iters = 1;
+	std::unique_ptr<Context> ctx;
+	if (!(which & 1)) ctx = enc->forward(stream, pos, &out, false, true);
+	cudaEventRecord(e0, stream);
+	for (int it = 0; it < iters; ++it) {
+		if (which & 1) ctx = enc->forward(stream, pos, &out, false, true);
+		if ((which & 2) && dL_dy_soa) {
+			GPUMatrixDynamic<T> dy((T*)dL_dy_soa, E, n, RM);
+			GPUMatrixDynamic<float> dx(dL_dx, 3, n, CM);
+			enc->backward(stream, *ctx, pos, out, dy, dL_dx ? &dx : nullptr, false, grid_grad ? EGradientMode::Overwrite : EGradientMode::Ignore);
+		}
+		if ((which & 4) && v) {
+			GPUMatrixDynamic<float> vm((float*)v, 3, n, CM);
+			GPUMatrixDynamic<T> dy2((T*)dL_dy2_soa, E, n, RM);
+			GPUMatrixDynamic<T> ddy(dL_ddLdy_soa, E, n, RM);
+			enc->backward_backward_input(stream, *ctx, pos, vm, dy2, dL_ddLdy_soa ? &ddy : nullptr, nullptr, false,
+				grid_grad ? (((which & 2) && dL_dy_soa) ? EGradientMode::Accumulate : EGradientMode::Overwrite) : EGradientMode::Ignore);
+		}
+	}
+	cudaEventRecord(e1, stream);
+	CUDA_CHECK_THROW(cudaStreamSynchronize(stream));
+	float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+	if (ms_out) *ms_out = ms / iters;
+	cudaEventDestroy(e0); cudaEventDestroy(e1);
+	ctx.reset();
+	return 0;
+	REF_CATCH
+}
+
+void* ref_mlp_create(const char* cfg_json) {
+	try {
+		json cfg = json::parse(cfg_json);
+		auto* m = new RefMlp;
+		m->net.reset(create_network<T>(cfg));
+		return m;
+	} catch (const std::exception& e) { g_err = e.what(); fprintf(stderr, "ref_shim: %s\n", e.what()); return nullptr; }
+}
+uint64_t ref_mlp_n_params(void* h) { return ((RefMlp*)h)->net->n_params(); }
+void ref_mlp_destroy(void* h) { delete (RefMlp*)h; }
+
+// in: half, [in_w][n] row-major when in_soa!=0 (how NerfNetwork feeds the SDF MLP) else [n][in_w].
+// out / dL_dout / seed: [n][16] (column-major 16 x n).  dL_din / d_in2: same layout as `in`.
+//   forward                                   -> out
+//   backward(dL_dout) if dL_dout              -> dL_din (optional), wgrad (Overwrite, half [n_params]) (optional)
+//   backward_backward_input(d_in2, seed)      -> wgrad (Accumulate if the first backward ran with wgrad, else Overwrite)
+int ref_mlp_eval(void* h, uint32_t n, uint32_t in_w, int in_soa, const T* in, T* params, T* out,
+                 const T* dL_dout, T* dL_din, T* wgrad, const T* d_in2, const T* seed, int iters, int which, float* ms_out) {
+	REF_TRY
+	auto& net = ((RefMlp*)h)->net;
+	net->set_params(params, params, params, wgrad);
+	cudaStream_t stream = nullptr;
+	const MatrixLayout lay = in_soa ? RM : CM;
+	GPUMatrixDynamic<T> inm((T*)in, in_w, n, lay);
+	GPUMatrixDynamic<T> outm(out, net->padded_output_width(), n, CM);
+	cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+	if (iters < 1) iters = 1;
+	std::unique_ptr<Context> ctx;
+	if (!(which & 1)) ctx = net->forward(stream, inm, &outm, false, true);
+	cudaEventRecord(e0, stream);
+	for (int it = 0; it < iters; ++it) {
+		if (which & 1) ctx = net->forward(stream, inm, &outm, false, true);
+		if ((which & 2) && dL_dout) {
+			GPUMatrixDynamic<T> dy((T*)dL_dout, net->padded_output_width(), n, CM);
+			GPUMatrixDynamic<T> dx(dL_din, in_w, n, lay);
+			net->backward(stream, *ctx, inm, outm, dy, dL_din ? &dx : nullptr, false, wgrad ? EGradientMode::Overwrite : EGradientMode::Ignore);
+		}
+		if ((which & 4) && d_in2) {
+			GPUMatrixDynamic<T> d2((T*)d_in2, in_w, n, lay);
+			GPUMatrixDynamic<T> sd((T*)seed, net->padded_output_width(), n, CM);
+			net->backward_backward_input(stream, *ctx, inm, d2, sd, nullptr, nullptr, false,
+				wgrad ? (((which & 2) && dL_dout) ? EGradientMode::Accumulate : EGradientMode::Overwrite) : EGradientMode::Ignore);
+		}
+	}
+	cudaEventRecord(e1, stream);
+	CUDA_CHECK_THROW(cudaStreamSynchronize(stream));
+	float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+	if (ms_out) *ms_out = ms / iters;
+	cudaEventDestroy(e0); cudaEventDestroy(e1);
+	ctx.reset();
+	return 0;
+	REF_CATCH
+}
+
+void ref_free_temporary_memory() { free_all_gpu_memory_arenas(); }
+
+}  // extern "C"

@@ -1,0 +1,177 @@
+"""GPU parity of one full training step, stage by stage, against the CPU oracle.
+
+Each stage of neus2_train_step_begin is checked in isolation by feeding the ORACLE the GPU's output of the previous
+stage (so a half-ulp difference upstream cannot masquerade as, or hide, a difference downstream):
+occupancy-grid samples -> density -> grid/bitfield -> ray marching -> network -> loss/compaction -> backward.
+Integer work (cell indices, bitfield, per-ray sample counts, offsets) must match bit-exactly.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests import util as U
+
+pytestmark = pytest.mark.gpu
+
+B = 1 << 14
+G3 = 128 ** 3
+
+
+@pytest.fixture(scope="module")
+def stepped():
+    import torch
+    import neus2_b200 as N
+    from neus2_b200 import synthetic
+    cfg = U.base_cfg()
+    ctx = N.Context(N.default_config(batch_size=B, mask_loss_weight=0.1))
+    p = U.random_params(cfg, seed=2)
+    # make the random network look like an SDF of a blob so that rays find occupied cells: bias the sdf output
+    ctx.set_params(p)
+    data = synthetic.render_sphere_views(n_views=5, width=96, height=80, seed=1)
+    ctx.set_dataset(data["pixels"], data["focal"], data["principal"], data["xforms"])
+    state0 = ctx.get_state()
+    ctx.train_step_begin()
+    torch.cuda.synchronize()
+    yield dict(ctx=ctx, cfg=cfg, p=p, data=data, state0=state0)
+    ctx.close()
+
+
+def _np(t):
+    return t.cpu().numpy()
+
+
+def test_density_grid_stage(stepped):
+    ctx, cfg, p = stepped["ctx"], stepped["cfg"], stepped["p"]
+    # density_grid_rng = pcg32(m_rng.next_uint()), m_rng = pcg32(seed)   (testbed.cu:2087-2100)
+    m_rng = O.Pcg32(seed=1337)
+    dg_rng = O.Pcg32(seed=m_rng.next_uint())
+    grid0 = np.zeros(G3, dtype=np.float32)
+    pos, idx = O.generate_grid_samples(G3, dg_rng, 0, grid0, 1, -0.01)
+    g_pos = _np(ctx.debug_buffer("grid_positions", "<f4", (G3, 3)))
+    g_idx = _np(ctx.debug_buffer("grid_indices", "<u4", (G3,)))
+    assert np.array_equal(g_idx, idx)                                    # integer: bit exact
+    assert np.array_equal(g_pos.view(np.uint32), pos.view(np.uint32))    # fp32 positions: bit exact (same op order)
+    # density: network in half
+    sub = np.arange(0, G3, 97)
+    dens_ref = O.net_sdf(cfg, np.ascontiguousarray(g_pos[sub]), U.to_half_bits(p), as_density=True)
+    g_dens = _np(ctx.debug_buffer("grid_density", "<f2", (G3,))).view(np.uint16)
+    d = U.half_ulp_diff(g_dens[sub], dens_ref)
+    assert np.percentile(d, 99) <= 8, np.percentile(d, [50, 99, 100])
+    # splat + decay + bitfield from the GPU's own densities
+    grid = np.zeros(G3, dtype=np.float32)
+    O.splat_and_decay(g_idx, g_dens, 0.95, grid)
+    g_grid = _np(ctx.debug_buffer("density_grid", "<f4", (G3,)))
+    assert np.array_equal(g_grid.view(np.uint32), grid.view(np.uint32))
+    bitfield, mean = O.update_bitfield(g_grid, 1)
+    g_mean = float(_np(ctx.debug_buffer("density_grid_mean", "<f4", (1,)))[0])
+    assert abs(g_mean - mean) <= 1e-5 * abs(mean)
+    g_bits = _np(ctx.debug_buffer("bitfield", "<u1", (G3 // 8 * 8,)))
+    if min(0.1, g_mean) == min(0.1, mean):
+        assert np.array_equal(g_bits, bitfield)
+    else:   # threshold differs in the last bit of an fp32 mean: at most a handful of cells may flip
+        assert np.count_nonzero(np.unpackbits(g_bits ^ bitfield)) <= 8
+
+
+def test_sample_generation_stage(stepped):
+    ctx, cfg, data, st0 = stepped["ctx"], stepped["cfg"], stepped["data"], stepped["state0"]
+    R = st0["rays_per_batch"]
+    assert R == 4096
+    bitfield = _np(ctx.debug_buffer("bitfield", "<u1", (G3 // 8 * 8,)))
+    ds = O.make_dataset(data["pixels"], data["focal"], data["principal"], data["xforms"])
+    rng = O.Pcg32(state=st0["rng_state"])
+    ref = O.generate_training_samples(R, B * 16, 0, rng, ds, bitfield)
+    cnt = _np(ctx.debug_buffer("counters", "<u4", (4,)))
+    assert int(cnt[0]) == ref["n_kept"] and int(cnt[1]) == ref["n_samples"]
+    assert ref["n_kept"] > 100 and ref["n_samples"] > 1000, "degenerate test scene"
+    assert np.array_equal(_np(ctx.debug_buffer("numsteps_all", "<u4", (R,))), ref["numsteps_all"])       # per-ray sample counts: bit exact
+    k = ref["n_kept"]
+    assert np.array_equal(_np(ctx.debug_buffer("ray_indices", "<u4", (R,)))[:k], ref["ray_indices"][:k])
+    assert np.array_equal(_np(ctx.debug_buffer("numsteps", "<u4", (R, 2)))[:k], ref["numsteps"][:k])      # (count, base offset)
+    assert np.array_equal(_np(ctx.debug_buffer("rays", "<f4", (R, 6)))[:k].view(np.uint32), ref["rays"][:k].view(np.uint32))
+    n = ref["n_samples"]
+    g_coords = _np(ctx.debug_buffer("coords", "<f4", (B * 16, 7)))[:n]
+    assert np.array_equal(g_coords.view(np.uint32), ref["coords"][:n].view(np.uint32))                    # sample positions: bit exact
+    stepped["gen"] = ref
+
+
+def test_forward_stage(stepped):
+    ctx, cfg, p = stepped["ctx"], stepped["cfg"], stepped["p"]
+    cnt = _np(ctx.debug_buffer("counters", "<u4", (4,)))
+    n = int(cnt[1])
+    coords = _np(ctx.debug_buffer("coords", "<f4", (B * 16, 7)))[:n]
+    sub = np.arange(0, n, max(1, n // 4000))
+    cfg0 = U.base_cfg(valid_level=3)       # training step 0: valid_level = ceil(0.2*14) = 3  (grid.h:2433)
+    ref = O.net_forward(cfg0, np.ascontiguousarray(coords[sub]), U.to_half_bits(p))
+    out = _np(ctx.debug_buffer("mlp_out", "<f2", (B * 16, 16)))[:n].view(np.uint16)[sub]
+    d = U.half_ulp_diff(out[:, :11], ref[:, :11])
+    assert np.percentile(d, 99) <= 2, np.percentile(d, [50, 99, 100])
+
+
+def test_loss_stage(stepped):
+    ctx, cfg, data, st0 = stepped["ctx"], stepped["cfg"], stepped["data"], stepped["state0"]
+    R = st0["rays_per_batch"]
+    cnt = _np(ctx.debug_buffer("counters", "<u4", (4,)))
+    k, n = int(cnt[0]), int(cnt[1])
+    bitfield = _np(ctx.debug_buffer("bitfield", "<u1", (G3 // 8 * 8,)))
+    ds = O.make_dataset(data["pixels"], data["focal"], data["principal"], data["xforms"])
+    gen = O.generate_training_samples(R, B * 16, 0, O.Pcg32(state=st0["rng_state"]), ds, bitfield)
+    mlp_out = _np(ctx.debug_buffer("mlp_out", "<f2", (B * 16, 16)))[:n].view(np.uint16).copy()
+    lp = O.LossParams()
+    lp.loss_scale = 128.0
+    lp.random_bg_color = 1
+    lp.snap_to_pixel_centers = 1
+    lp.mask_loss_weight = 0.1
+    lp.ek_loss_weight = 0.01
+    lp.cos_anneal_ratio = 1.0
+    ref = O.compute_loss(R, k, 0, O.Pcg32(state=st0["rng_state"]), B, lp, ds, mlp_out, gen["ray_indices"], gen["rays"], gen["numsteps"], gen["coords"])
+    assert int(cnt[2]) == ref["n_compacted"]                                                       # compacted sample count
+    g_ns = _np(ctx.debug_buffer("numsteps", "<u4", (R, 2)))[:k]
+    assert np.array_equal(g_ns, ref["numsteps"][:k])                                                # per-ray compacted counts + offsets: bit exact
+    m = min(ref["n_compacted"], B)
+    g_cc = _np(ctx.debug_buffer("coords_compacted", "<f4", (B, 7)))[:m]
+    assert np.array_equal(g_cc.view(np.uint32), ref["coords_compacted"][:m].view(np.uint32))
+    g_dl = _np(ctx.debug_buffer("dloss", "<f2", (B, 16)))[:m].astype(np.float32)
+    r_dl = ref["dloss"][:m].view(np.float16).astype(np.float32)
+    # fp32 math with expf/powf/logf from different libms (CUDA vs glibc): 1e-5 relative, then one rounding to half
+    err = np.abs(g_dl[:, :11] - r_dl[:, :11])
+    tol = 2e-3 * np.abs(r_dl[:, :11]) + 1e-6 * np.max(np.abs(r_dl[:, :11]), axis=0, keepdims=True)
+    assert np.mean(err > tol) < 1e-3, np.mean(err > tol)
+    for name in ["loss", "ek_loss", "mask_loss"]:
+        g = _np(ctx.debug_buffer(name, "<f4", (R,)))[:k]
+        assert np.allclose(g, ref[name][:k], rtol=2e-5, atol=1e-9), name
+
+
+def test_backward_stage(stepped):
+    ctx, cfg, p = stepped["ctx"], stepped["cfg"], stepped["p"]
+    cnt = _np(ctx.debug_buffer("counters", "<u4", (4,)))
+    n_in = min(int(cnt[2]), B)
+    coords = _np(ctx.debug_buffer("coords_compacted", "<f4", (B, 7))).copy()
+    dl = _np(ctx.debug_buffer("dloss", "<f2", (B, 16))).view(np.uint16).copy()
+    O.fill_rollover(B, n_in, dl_h=dl, coords=coords)
+    cfg0 = U.base_cfg(valid_level=3)
+    ref = O.net_backward(cfg0, coords, U.to_half_bits(p), dl, B)
+    g = _np(ctx.buffers()[3])
+    lay = O.param_layout(cfg)
+    for name, a, b in [("sdf", 0, lay["rgb"]), ("rgb", lay["rgb"], lay["grid"]), ("grid", lay["grid"], lay["variance"])]:
+        x, y = g[a:b].astype(np.float64), ref[a:b].astype(np.float64)
+        rel = np.linalg.norm(x - y) / (np.linalg.norm(y) + 1e-30)
+        assert rel < 3e-3, (name, rel)
+    # levels above valid_level receive no gradient (grid.h:394, 906)
+    off, _, _ = O.cfg_tables(cfg)
+    assert not g[lay["grid"] + 2 * int(off[4]):lay["variance"]].any()
+
+
+def test_step_end_and_training_progress(stepped):
+    ctx = stepped["ctx"]
+    st = ctx.train_step_end()
+    assert st.training_step == 1 and st.loss_valid == 1 and np.isfinite(st.loss)
+    assert st.measured_batch_size > 0 and st.rays_per_batch_next % 128 == 0
+    # rays_per_batch <- rays * target / measured, rounded up to 128, capped at 2^18   (testbed_nerf.cu:3434-3435)
+    want = min((int(np.float32(np.float32(4096) * np.float32(B) / np.float32(st.measured_batch_size))) + 127) // 128 * 128, 1 << 18)
+    assert st.rays_per_batch_next == want
+    losses = []
+    for _ in range(48):
+        s = ctx.train_step()
+        if s.loss_valid:
+            losses.append(s.loss)
+    assert all(np.isfinite(losses))
