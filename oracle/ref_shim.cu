@@ -106,7 +106,9 @@ uint64_t ref_mlp_n_params(void* h) { return ((RefMlp*)h)->net->n_params(); }
 void ref_mlp_destroy(void* h) { delete (RefMlp*)h; }
 
 // in: half, [in_w][n] row-major when in_soa!=0 (how NerfNetwork feeds the SDF MLP) else [n][in_w].
-// out / dL_dout / seed: [n][16] (column-major 16 x n).  dL_din / d_in2: same layout as `in`.
+// out / dL_dout / seed: [n][16] (column-major 16 x n).  dL_din: same layout as `in`.  d_in2: ALWAYS [n][in_w]
+// (fully_fused_mlp.cu:1119 wraps dL_ddLdinput in a column-major GPUMatrix whatever its declared layout; NerfNetwork
+// allocates d_density_input column-major, nerf_network.h:560).
 //   forward                                   -> out
 //   backward(dL_dout) if dL_dout              -> dL_din (optional), wgrad (Overwrite, half [n_params]) (optional)
 //   backward_backward_input(d_in2, seed)      -> wgrad (Accumulate if the first backward ran with wgrad, else Overwrite)
@@ -132,7 +134,7 @@ int ref_mlp_eval(void* h, uint32_t n, uint32_t in_w, int in_soa, const T* in, T*
 			net->backward(stream, *ctx, inm, outm, dy, dL_din ? &dx : nullptr, false, wgrad ? EGradientMode::Overwrite : EGradientMode::Ignore);
 		}
 		if ((which & 4) && d_in2) {
-			GPUMatrixDynamic<T> d2((T*)d_in2, in_w, n, lay);
+			GPUMatrixDynamic<T> d2((T*)d_in2, in_w, n, CM);
 			GPUMatrixDynamic<T> sd((T*)seed, net->padded_output_width(), n, CM);
 			net->backward_backward_input(stream, *ctx, inm, d2, sd, nullptr, nullptr, false,
 				wgrad ? (((which & 2) && dL_dout) ? EGradientMode::Accumulate : EGradientMode::Overwrite) : EGradientMode::Ignore);
