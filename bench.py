@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- NeuS training throughput (rays/s, ms/step) at base.json settings on N B200s.
+
+  python bench.py --gpus 1 --steps K --warmup W                     # this framework (CUDA, sm_100a)
+  python bench.py --impl reference --gpus 1 --steps K --warmup W    # reference arm: CPU port of the reference path
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   # data-parallel rays + NCCL all-reduce
+
+One "step" = one Testbed::train() call (src/testbed.cu:2640): occupancy refresh when due, ray generation + marching,
+first forward, compositing/loss, fused second forward + backward (incl. eikonal second order), Adam+EMA.
+Workload (config.workload): BASELINE.json configs[1], the DTU-Scan24-shaped synthetic scene (49 views, 1600x1200
+RGBA, analytic-SDF images), base.json network, batch 2^18 samples per GPU.  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SCHEDULE_STEPS = 2000   # configs/nerf/base.json:123 first_frame_max_training_step
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--preroll", type=int, default=300, help="untimed training steps before warm-up so that rays_per_batch and the occupancy grid are in steady state")
+    ap.add_argument("--views", type=int, default=49)
+    ap.add_argument("--width", type=int, default=1600)
+    ap.add_argument("--height", type=int, default=1200)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return p.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    def __init__(self, device_index):
+        self.idx = device_index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def make_data(args):
+    from neus2_b200 import synthetic
+    return synthetic.dtu_like_views(n_views=args.views, width=args.width, height=args.height, seed=0)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU port of the reference path (oracle), timed on a bounded sample of the same workload
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_port_rays_per_s(data, params_f32, bitfield, rays_per_batch, n_u, n_compacted, batch, n_sample_rays=1024):
+    """Times oracle sample generation + forward + loss + backward + Adam on `n_sample_rays` rays of the workload and
+    scales to rays/s.  Returns (rays_per_s, description)."""
+    from oracle import oracle as O
+    cfg = O.make_cfg()
+    ds = O.make_dataset(data["pixels"], data["focal"], data["principal"], data["xforms"])
+    ph = params_f32.astype(np.float16).view(np.uint16)
+    R = n_sample_rays
+    t0 = time.perf_counter()
+    gen = O.generate_training_samples(R, 16 * batch, 0, O.Pcg32(seed=1337), ds, bitfield)
+    n = gen["n_samples"]
+    k = gen["n_kept"]
+    if n == 0:
+        return None, "no samples"
+    coords = np.ascontiguousarray(gen["coords"][:n])
+    out = O.net_forward(cfg, coords, ph)
+    lp = O.LossParams()
+    lp.loss_scale, lp.random_bg_color, lp.snap_to_pixel_centers, lp.mask_loss_weight, lp.ek_loss_weight, lp.cos_anneal_ratio = 128.0, 1, 1, 0.0, 0.01, 1.0
+    loss = O.compute_loss(R, k, 0, O.Pcg32(seed=1337), max(n, 128), lp, ds, out, gen["ray_indices"], gen["rays"], gen["numsteps"], gen["coords"])
+    m = max(1, min(loss["n_compacted"], n))
+    O.net_backward(cfg, np.ascontiguousarray(loss["coords_compacted"][:m]), ph, np.ascontiguousarray(loss["dloss"][:m]), batch)
+    t_net = time.perf_counter() - t0
+    # Adam + EMA over all parameters is per step, not per ray
+    lay = O.param_layout(cfg)
+    N = lay["total"]
+    g = np.zeros(N, np.float32)
+    g[:: 7] = 1e-3
+    mm, m1, m2, st, ema = params_f32.copy(), np.zeros(N, np.float32), np.zeros(N, np.float32), np.zeros(N, np.uint32), np.zeros(N, np.uint16)
+    php = ph.copy()
+    t1 = time.perf_counter()
+    O.adam_ema_step(lay["grid"], 128.0, 1e-3, 0.9, 0.99, 1e-15, 1e-6, 0.95, 1, g, mm, php, m1, m2, st, ema)
+    t_adam = time.perf_counter() - t1
+    # one full step = rays_per_batch rays  (sample work scales with rays) + one optimizer pass
+    t_step = t_net * (rays_per_batch / R) + t_adam
+    desc = (f"oracle (CPU port) on {R} rays of the workload: {n} samples fwd, {m} samples bwd in {t_net:.2f}s + Adam/EMA over {N} params "
+            f"{t_adam:.2f}s; scaled to {rays_per_batch} rays/step")
+    return rays_per_batch / t_step, desc
+
+
+def run_reference_arm(args):
+    """Reference arm: the reference has no CPU path (CUDA-only, and its ngp layer does not compile here: SURVEY §0.3), so
+    this times the CPU restatement of its path (oracle/) on the host cores for the same config/metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    data = make_data(args)
+    cfg = O.make_cfg()
+    lay = O.param_layout(cfg)
+    # geometric-init-like parameters + an occupancy grid of the true surface shell (what training converges to)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from tests import util as U
+    p = U.random_params(cfg, seed=0, grid_scale=1e-4)
+    bitfield = shell_bitfield(data)
+    cores = os.cpu_count()
+    vals = []
+    desc = ""
+    for it in range(args.warmup + args.steps):
+        v, desc = cpu_port_rays_per_s(data, p, bitfield, 4096 * 4, 0, 0, 1 << 18, n_sample_rays=256)
+        if it >= args.warmup:
+            vals.append(v)
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": "NeuS training rays/s (base.json)", "value": value, "unit": "rays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * 4096 * 4 / value, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference is CUDA-only and its ngp layer does not compile offline (Eigen/Core missing); this is the CPU port of its path",
+    }
+    print(json.dumps(line))
+
+
+def shell_bitfield(data):
+    """Occupancy bitfield of the analytic surface shell (|sdf| < 2 cells), all mips, via the oracle's bitfield builder."""
+    from oracle import oracle as O
+    from neus2_b200 import synthetic
+    G = 128
+    idx = np.arange(G ** 3, dtype=np.uint32)
+    # vectorised morton decode
+    def dec(x):
+        x = x & 0x49249249
+        x = (x | (x >> 2)) & 0xc30c30c3
+        x = (x | (x >> 4)) & 0x0f00f00f
+        x = (x | (x >> 8)) & 0xff0000ff
+        x = (x | (x >> 16)) & 0x0000ffff
+        return x
+    pts = np.stack([dec(idx), dec(idx >> 1), dec(idx >> 2)], axis=1).astype(np.float64)
+    pts = (pts + 0.5) / G
+    sdf = synthetic.sphere_sdf(pts, data["spheres"])
+    grid = np.where(np.abs(sdf) < 2.5 / G, 1.0, 0.0).astype(np.float32)
+    bitfield, _ = O.update_bitfield(grid, 1)
+    return bitfield
+
+
+def workload_config(args, n_gpus):
+    return {
+        "workload": f"DTU-Scan24-shaped synthetic scene ({args.views} views {args.width}x{args.height} RGBA from an analytic SDF), base.json "
+                    f"(hashgrid L=14 F=2 T=2^19, 64-wide fp16 SDF+colour MLPs, eikonal 0.01), batch 2^18 samples per GPU",
+        "batch_samples_per_gpu": 1 << 18, "global_batch_samples": (1 << 18) * n_gpus, "parallelism": f"dp{n_gpus} (rays sharded, NCCL all-reduce of fp32 grads)" if n_gpus > 1 else "single GPU",
+        "l2_policy": "per-step working set (>=470 MB of sample/activation buffers) exceeds the 126 MB L2; no explicit flush",
+        "preroll_steps": args.preroll,
+    }
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    import torch
+    import torch.distributed as dist
+    import neus2_b200 as N
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    else:
+        torch.cuda.set_device(0)
+    dev = torch.device(f"cuda:{local_rank}")
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    data = make_data(args)
+    B = (1 << 18) * world                      # weak scaling: every GPU back-propagates 2^18 samples per step
+    cfg = N.default_config(batch_size=B, world_size=world, max_rays_per_batch=(1 << 18) * world)
+    ctx = N.Context(cfg, device=local_rank)
+    ctx.init_params()
+    # pinned host copy of the dataset: the upload is part of the end-to-end number
+    px_pinned = torch.from_numpy(data["pixels"]).pin_memory()
+    torch.cuda.synchronize()
+    t_up0 = time.perf_counter()
+    ctx.set_dataset(px_pinned.numpy(), data["focal"], data["principal"], data["xforms"])
+    torch.cuda.synchronize()
+    t_upload = time.perf_counter() - t_up0
+    dataset_bytes = int(data["pixels"].nbytes + data["focal"].nbytes + data["principal"].nbytes + data["xforms"].nbytes)
+
+    grads = ctx.buffers()[3]
+    stream = torch.cuda.current_stream()
+
+    def step():
+        if world == 1:
+            return ctx.train_step()
+        ctx.train_step_begin(rank, world)
+        counts = torch.tensor(ctx.local_counts(), dtype=torch.int64, device=dev)
+        dist.all_reduce(grads)                 # NCCL over NVLink: 10.56 M fp32 gradients
+        dist.all_reduce(counts)
+        return ctx.train_step_end([int(x) for x in counts.tolist()])
+
+    for _ in range(args.preroll + args.warmup):
+        st = step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+    ctx.set_profiling(True)
+    launches0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    rays = 0
+    n_u = n_c = 0
+    t_wall0 = time.perf_counter()
+    with ClockSampler(local_rank) as clocks:
+        e0.record(stream)
+        for _ in range(args.steps):
+            st = step()
+            rays += st.rays_per_batch
+            n_u += st.measured_batch_size_before_compaction
+            n_c += st.measured_batch_size
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t_wall = time.perf_counter() - t_wall0
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    launches = ctx.launch_count() - launches0
+    stages = ctx.stage_times()
+    ctx.set_profiling(False)
+
+    if rank == 0:
+        K = args.steps
+        value = rays / (ms * 1e-3)
+        # end to end through the public API (Context.train_step): wall clock of the K steps incl. the per-step device->host
+        # read of the counters/loss, plus the host->device upload of the training images from pinned memory, amortised over
+        # the 2000-step schedule the metric is defined on.
+        t_e2e = t_wall + t_upload * (K / SCHEDULE_STEPS)
+        e2e = rays / t_e2e
+        peak, peak_src = peaks()
+        # dominant kernel = fused forward+backward over the compacted batch
+        dom = "fwdbwd"
+        dom_ms = stages[dom][0]
+        rows = (1 << 18)
+        alg_bytes = rows * (508 + 1376)        # 508 B/sample forward + ~1.4 KB/sample backward (algorithmic minimum)
+        achieved = alg_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        line = {
+            "metric": "NeuS training rays/s (base.json)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": workload_config(args, world),
+            "clocks": clocks.summary(),
+            "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": dataset_bytes / SCHEDULE_STEPS, "d2h_bytes_per_step": 28,
+                    "note": "wall clock through Context.train_step(); dataset upload from pinned host memory amortised over the 2000-step schedule"},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "k_network_fwdbwd", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes, "avg_launch_ms": dom_ms},
+            "stage_ms": {k: round(v[0], 4) for k, v in stages.items()},
+            "per_step": {"rays": rays / K, "samples_before_compaction": n_u / K, "samples_compacted": n_c / K, "training_step": int(st.training_step)},
+        }
+        if not args.no_cpu_baseline:
+            try:
+                bitfield = ctx.debug_buffer("bitfield", "<u1", (128 ** 3,)).cpu().numpy()
+                v, desc = cpu_port_rays_per_s(data, ctx.get_params(), bitfield, int(rays / K), n_u / K, n_c / K, 1 << 18, n_sample_rays=512)
+                line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port", "sample": desc}
+            except Exception as ex:   # the baseline is a report, it must not take the bench line down
+                line["cpu_baseline"] = {"value": None, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

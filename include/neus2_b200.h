@@ -54,6 +54,9 @@ typedef struct neus2_config {
 	float background_color[3];       /* used when random_bg_color == 0 */
 	float density_grid_decay;        /* 0.95 (testbed.h:644) */
 	float loss_scale;                /* 128 (LOSS_SCALE) */
+	/* data-parallel build-out (not in the reference, which is single-GPU): buffers are sized for this rank's share */
+	uint32_t world_size;             /* 1 */
+	uint32_t max_rays_per_batch;     /* 1<<18 (testbed_nerf.cu:3435); raise to world_size<<18 for weak scaling */
 } neus2_config;
 
 typedef struct neus2_step_stats {
@@ -135,6 +138,10 @@ int neus2_debug_buffer(neus2_ctx* ctx, const char* name, void** ptr_dev, uint64_
 int neus2_get_state(neus2_ctx* ctx, uint32_t* training_step, uint32_t* rays_per_batch, uint64_t rng_state[2]);
 int neus2_set_state(neus2_ctx* ctx, uint32_t training_step, uint32_t rays_per_batch, uint32_t n_rays_total, uint32_t measured_before_compaction);
 int neus2_set_bitfield(neus2_ctx* ctx, const uint8_t* bitfield_host, uint64_t n_bytes);
+/* Per-stage device timing (CUDA events on the caller's stream): stages = {occupancy grid, sample generation, forward,
+ * loss, fused forward+backward, weight-gradient GEMMs, optimizer, whole step}; sums in ms and number of samples. */
+int neus2_set_profiling(neus2_ctx* ctx, int enable);
+int neus2_get_stage_times(neus2_ctx* ctx, float ms_sum[8], uint32_t count[8]);
 /* number of kernels this library launched on the context since creation (bench.py's gpu_launches) */
 uint64_t neus2_launch_count(const neus2_ctx* ctx);
 

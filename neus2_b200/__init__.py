@@ -199,5 +199,17 @@ class Context:
         b = np.ascontiguousarray(bitfield, dtype=np.uint8)
         check(self._lib.neus2_set_bitfield(self._h, b.ctypes.data_as(C.c_void_p), C.c_uint64(b.size)))
 
+    STAGES = ["density_grid", "gen_samples", "forward", "loss", "fwdbwd", "wgrad", "optimizer", "step"]
+
+    def set_profiling(self, enable=True):
+        check(self._lib.neus2_set_profiling(self._h, C.c_int(int(enable))))
+
+    def stage_times(self):
+        """{stage: (mean ms, samples)} measured with CUDA events on the step's stream."""
+        ms = (C.c_float * 8)()
+        cnt = (C.c_uint32 * 8)()
+        check(self._lib.neus2_get_stage_times(self._h, ms, cnt))
+        return {s: ((ms[i] / cnt[i]) if cnt[i] else 0.0, int(cnt[i])) for i, s in enumerate(self.STAGES)}
+
     def launch_count(self):
         return int(self._lib.neus2_launch_count(self._h))

@@ -25,6 +25,7 @@ class Config(C.Structure):
         ("batch_size", C.c_uint32),
         ("aabb_scale", C.c_int32), ("seed", C.c_uint32), ("random_bg_color", C.c_int32), ("snap_to_pixel_centers", C.c_int32),
         ("background_color", C.c_float * 3), ("density_grid_decay", C.c_float), ("loss_scale", C.c_float),
+        ("world_size", C.c_uint32), ("max_rays_per_batch", C.c_uint32),
     ]
 
 
@@ -42,7 +43,7 @@ EXPORTS = [
     "neus2_grid_tables", "neus2_buffers", "neus2_init_params", "neus2_set_params", "neus2_get_params", "neus2_set_training_step",
     "neus2_forward", "neus2_sdf", "neus2_backward", "neus2_optimizer_step", "neus2_set_dataset", "neus2_update_density_grid",
     "neus2_train_step_begin", "neus2_train_step_end", "neus2_local_counts", "neus2_train_step", "neus2_debug_buffer",
-    "neus2_get_state", "neus2_set_state", "neus2_set_bitfield", "neus2_launch_count",
+    "neus2_get_state", "neus2_set_state", "neus2_set_bitfield", "neus2_launch_count", "neus2_set_profiling", "neus2_get_stage_times",
 ]
 
 _lib = None

@@ -23,6 +23,8 @@ void neus_set_error(const char* msg, const char* file, int line) {
 	snprintf(buf, sizeof(buf), "%s (%s:%d)", msg, file, line);
 	g_error = buf;
 }
+#define NEUS2_N_STAGES 8
+enum { ST_GRID = 0, ST_GEN = 1, ST_FWD = 2, ST_LOSS = 3, ST_FWDBWD = 4, ST_WGRAD = 5, ST_OPT = 6, ST_STEP = 7 };
 #define FAIL(msg) do { neus_set_error(msg, __FILE__, __LINE__); return -1; } while (0)
 #define CHECK(x) do { if ((x) != 0) return -1; } while (0)
 
@@ -32,7 +34,8 @@ struct neus2_ctx {
 	GridMeta gm;
 	ParamLayout pl;
 	uint64_t n_params;
-	uint32_t B;                 // target batch size
+	uint32_t B;                 // target batch size (global)
+	uint32_t B_local;           // rows this rank back-propagates (B / world_size)
 	uint32_t max_rays;          // 1<<18
 	uint32_t max_samples;       // 16*B
 	uint32_t n_cascades;        // max_cascade + 1
@@ -65,15 +68,34 @@ struct neus2_ctx {
 	uint32_t step_rays, step_rays_local, step_n_rays_total;   // of the step in flight
 	bool step_density_updated;
 	uint32_t* h_counters;       // pinned
+	int profiling;              // record CUDA events around the stages of a step
+	cudaEvent_t ev[2 * NEUS2_N_STAGES];
+	float stage_ms_sum[NEUS2_N_STAGES];
+	uint32_t stage_count[NEUS2_N_STAGES];
+	bool stage_pending[NEUS2_N_STAGES];
 	float* h_scalars;           // pinned
 };
 
+static void stage_begin(neus2_ctx* ctx, int st, cudaStream_t s);
+static void stage_end(neus2_ctx* ctx, int st, cudaStream_t s);
 static int dmalloc(void** p, size_t bytes) {
 	CUDA_CHECK(cudaMalloc(p, bytes));
 	CUDA_CHECK(cudaMemset(*p, 0, bytes));
 	return 0;
 }
 #define DMALLOC(ptr, count) CHECK(dmalloc((void**)&(ptr), sizeof(*(ptr)) * (size_t)(count)))
+
+static void stage_begin(neus2_ctx* ctx, int st, cudaStream_t s) { if (ctx->profiling) cudaEventRecord(ctx->ev[2 * st], s); }
+static void stage_end(neus2_ctx* ctx, int st, cudaStream_t s) { if (ctx->profiling) { cudaEventRecord(ctx->ev[2 * st + 1], s); ctx->stage_pending[st] = true; } }
+static void stage_collect(neus2_ctx* ctx) {   // call after the stream has been synchronised
+	if (!ctx->profiling) return;
+	for (int st = 0; st < NEUS2_N_STAGES; ++st) {
+		if (!ctx->stage_pending[st]) continue;
+		float ms = 0.f;
+		if (cudaEventElapsedTime(&ms, ctx->ev[2 * st], ctx->ev[2 * st + 1]) == cudaSuccess) { ctx->stage_ms_sum[st] += ms; ctx->stage_count[st]++; }
+		ctx->stage_pending[st] = false;
+	}
+}
 
 extern "C" {
 
@@ -89,6 +111,7 @@ void neus2_default_config(neus2_config* c) {
 	c->aabb_scale = 1; c->seed = 1337; c->random_bg_color = 1; c->snap_to_pixel_centers = 1;
 	c->background_color[0] = c->background_color[1] = c->background_color[2] = 0.f;
 	c->density_grid_decay = 0.95f; c->loss_scale = 128.f;
+	c->world_size = 1; c->max_rays_per_batch = 1u << 18;
 }
 
 static int build_tables(neus2_ctx* ctx) {
@@ -137,8 +160,13 @@ int neus2_ctx_create(const neus2_config* cfg, int device, neus2_ctx** out) {
 	if (build_tables(ctx)) { delete ctx; return -1; }
 	ctx->B = cfg->batch_size;
 	if (ctx->B == 0 || ctx->B % 128 != 0) { delete ctx; FAIL("batch_size must be a positive multiple of 128 (tcnn batch_size_granularity)"); }
-	ctx->max_rays = 1u << 18;
-	ctx->max_samples = ctx->B * 16;
+	if (ctx->cfg.world_size == 0) ctx->cfg.world_size = 1;
+	if (ctx->cfg.max_rays_per_batch == 0) ctx->cfg.max_rays_per_batch = 1u << 18;
+	const uint32_t W = ctx->cfg.world_size;
+	if (ctx->B % (128 * W) != 0 || ctx->cfg.max_rays_per_batch % (128 * W) != 0) { delete ctx; FAIL("batch_size and max_rays_per_batch must be multiples of 128*world_size"); }
+	ctx->max_rays = ctx->cfg.max_rays_per_batch / W;     // this rank's share
+	ctx->B_local = ctx->B / W;
+	ctx->max_samples = ctx->B_local * 16;
 	uint32_t max_cascade = 0;
 	while ((1 << max_cascade) < cfg->aabb_scale) ++max_cascade;
 	ctx->n_cascades = max_cascade + 1;
@@ -149,7 +177,7 @@ int neus2_ctx_create(const neus2_config* cfg, int device, neus2_ctx** out) {
 	memcpy(ctx->gmv.R, I, sizeof(I));
 
 	const uint64_t N = ctx->n_params;
-	const uint32_t B = ctx->B, R = ctx->max_rays, S = ctx->max_samples;
+	const uint32_t B = ctx->B_local, R = ctx->max_rays, S = ctx->max_samples;
 	#define CTXCHECK(x) do { if ((x) != 0) { neus2_ctx_destroy(ctx); return -1; } } while (0)
 	#define CDM(ptr, count) CTXCHECK(dmalloc((void**)&(ptr), sizeof(*(ptr)) * (size_t)(count)))
 	CDM(ctx->master, N); CDM(ctx->params, N); CDM(ctx->ema, N); CDM(ctx->grads, N); CDM(ctx->m1, N); CDM(ctx->m2, N); CDM(ctx->steps, N);
@@ -315,13 +343,17 @@ int neus2_sdf(neus2_ctx* ctx, void* stream, const float* pos, uint32_t stride, u
 int neus2_backward(neus2_ctx* ctx, void* stream_, const float* coords, const void* dL_dout, const uint32_t* n_in_dev, uint32_t n_rows, uint32_t indeed_batch_size) {
 	cudaStream_t stream = (cudaStream_t)stream_;
 	CUDA_CHECK(cudaSetDevice(ctx->device));
-	if (n_rows > ctx->B) FAIL("n_rows exceeds the context's batch size");
+	if (n_rows > ctx->B_local) FAIL("n_rows exceeds the context's (local) batch size");
 	CUDA_CHECK(cudaMemsetAsync(ctx->grads, 0, ctx->n_params * sizeof(float), stream));   // EGradientMode::Overwrite
 	CUDA_CHECK(cudaMemsetAsync(ctx->var_acc, 0, sizeof(float), stream));
 	CUDA_CHECK(cudaMemsetAsync(ctx->w1row0_acc, 0, 64 * sizeof(float), stream));
+	stage_begin(ctx, ST_FWDBWD, stream);
 	CHECK(launch_network_fwdbwd(stream, ctx->gm, ctx->pl, ctx->params, coords, (const __half*)dL_dout, n_in_dev, n_rows, ctx->cfg.sdf_bias, indeed_batch_size,
 	                            ctx->grads, ctx->var_acc, ctx->w1row0_acc, ctx->so));
+	stage_end(ctx, ST_FWDBWD, stream);
+	stage_begin(ctx, ST_WGRAD, stream);
 	CHECK(launch_weight_gradients(stream, ctx->pl, ctx->so, n_in_dev, n_rows, ctx->partials, weight_gradient_partials(), ctx->var_acc, ctx->w1row0_acc, ctx->grads));
+	stage_end(ctx, ST_WGRAD, stream);
 	return 0;
 }
 
@@ -329,8 +361,11 @@ int neus2_optimizer_step(neus2_ctx* ctx, void* stream, float loss_scale) {
 	CUDA_CHECK(cudaSetDevice(ctx->device));
 	const neus2_config& c = ctx->cfg;
 	++ctx->adam_step;
-	return launch_adam_ema((cudaStream_t)stream, ctx->n_params, ctx->pl.off_grid, loss_scale, c.learning_rate, c.beta1, c.beta2, c.epsilon, c.l2_reg,
+	stage_begin(ctx, ST_OPT, (cudaStream_t)stream);
+	const int rc_ = launch_adam_ema((cudaStream_t)stream, ctx->n_params, ctx->pl.off_grid, loss_scale, c.learning_rate, c.beta1, c.beta2, c.epsilon, c.l2_reg,
 	                       c.ema_decay, ctx->adam_step, ctx->grads, ctx->master, ctx->params, ctx->m1, ctx->m2, ctx->steps, ctx->ema);
+	stage_end(ctx, ST_OPT, (cudaStream_t)stream);
+	return rc_;
 }
 
 int neus2_set_dataset(neus2_ctx* ctx, uint32_t n_images, int32_t width, int32_t height, const uint8_t* pixels, const float* focal, const float* principal, const float* xforms) {
@@ -384,12 +419,18 @@ int neus2_train_step_begin(neus2_ctx* ctx, void* stream_, uint32_t rank, uint32_
 	cudaStream_t stream = (cudaStream_t)stream_;
 	CUDA_CHECK(cudaSetDevice(ctx->device));
 	if (!ctx->d_pixels) FAIL("no training data: call neus2_set_dataset first");
-	if (world_size == 0 || rank >= world_size) FAIL("bad rank / world_size");
+	if (world_size != ctx->cfg.world_size || rank >= world_size) FAIL("rank / world_size do not match the context's config.world_size");
 	const neus2_config& c = ctx->cfg;
 	neus2_set_training_step(ctx, (int32_t)ctx->training_step);                          // testbed.cu:2651-2657
 	const uint32_t n_prep_to_skip = std::min(std::max(ctx->training_step / 16u, 1u), 16u);   // :2669
 	ctx->step_density_updated = false;
-	if (ctx->training_step % n_prep_to_skip == 0) { CHECK(neus2_update_density_grid(ctx, stream_)); ctx->step_density_updated = true; }
+	stage_begin(ctx, ST_STEP, stream);
+	if (ctx->training_step % n_prep_to_skip == 0) {
+		stage_begin(ctx, ST_GRID, stream);
+		CHECK(neus2_update_density_grid(ctx, stream_));
+		stage_end(ctx, ST_GRID, stream);
+		ctx->step_density_updated = true;
+	}
 
 	// Counters::prepare_for_training_steps (:3399-3410)
 	const uint32_t R = ctx->rays_per_batch;
@@ -400,7 +441,7 @@ int neus2_train_step_begin(neus2_ctx* ctx, void* stream_, uint32_t rank, uint32_
 
 	// train_nerf_step (:3723-4001)
 	const uint32_t n_local = R / world_size, ray_offset = rank * n_local;
-	const uint32_t rows_local = ctx->B / world_size;
+	const uint32_t rows_local = ctx->B_local;
 	const uint32_t max_samples = ctx->max_samples;
 	uint32_t max_inference;
 	if (ctx->measured_before == 0) { ctx->measured_before = max_inference = max_samples; }
@@ -410,18 +451,24 @@ int neus2_train_step_begin(neus2_ctx* ctx, void* stream_, uint32_t rank, uint32_
 	ctx->n_rays_total += R;
 	ctx->step_rays = R; ctx->step_rays_local = n_local; ctx->step_n_rays_total = n_rays_total;
 	const uint64_t st[2] = {ctx->rng.state, ctx->rng.inc};
+	stage_begin(ctx, ST_GEN, stream);
 	CHECK(launch_generate_training_samples(stream, n_local, ray_offset, R, n_rays_total, st, ctx->ds, ctx->aabb, ctx->gmv, ctx->bitfield, c.snap_to_pixel_centers,
 	                                       ctx->cone_angle_constant, max_inference, ctx->numsteps_all, ctx->base, ctx->slot, ctx->ray_indices, ctx->rays,
 	                                       ctx->numsteps, ctx->coords, ctx->counters));
+	stage_end(ctx, ST_GEN, stream);
+	stage_begin(ctx, ST_FWD, stream);
 	CHECK(launch_network_forward(stream, ctx->gm, ctx->pl, ctx->params, ctx->coords, ctx->counters + 1, max_inference, c.sdf_bias, ctx->mlp_out));   // :3854
+	stage_end(ctx, ST_FWD, stream);
 	LossParamsDev lp;
 	lp.loss_scale = c.loss_scale; memcpy(lp.background_color, c.background_color, sizeof(lp.background_color));
 	lp.random_bg_color = c.random_bg_color; lp.snap_to_pixel_centers = c.snap_to_pixel_centers;
 	lp.mask_loss_weight = c.mask_loss_weight; lp.ek_loss_weight = c.ek_loss_weight;
 	lp.cos_anneal_ratio = c.anneal_end == 0 ? 1.0f : (float)std::min(1.0, (double)((float)ctx->training_step / c.anneal_end));   // nerf_network.h:1119-1128
+	stage_begin(ctx, ST_LOSS, stream);
 	CHECK(launch_compute_loss(stream, n_local, R, n_rays_total, st, ctx->ds, ctx->aabb, ctx->gmv, lp, rows_local, ctx->counters + 0, ctx->mlp_out, ctx->ray_indices,
 	                          ctx->rays, ctx->numsteps, ctx->coords, ctx->ray_tmp, ctx->scan_tmp, ctx->coords_compacted, ctx->dloss, ctx->loss, ctx->ek_loss,
 	                          ctx->mask_loss, ctx->counters + 2));
+	stage_end(ctx, ST_LOSS, stream);
 	CHECK(neus2_backward(ctx, stream_, ctx->coords_compacted, ctx->dloss, ctx->counters + 2, rows_local, ctx->B));   // :3941-3946
 	return 0;
 }
@@ -446,8 +493,10 @@ int neus2_train_step_end(neus2_ctx* ctx, void* stream_, const uint32_t* counts_g
 		CHECK(launch_reduce_sum(stream, ctx->mask_loss, ctx->step_rays, ctx->scalar_tmp + 2));
 		CUDA_CHECK(cudaMemcpyAsync(ctx->h_scalars, ctx->scalar_tmp, 3 * sizeof(float), cudaMemcpyDeviceToHost, stream));
 	}
+	stage_end(ctx, ST_STEP, stream);
 	uint32_t counts[3];
 	CHECK(neus2_local_counts(ctx, stream_, counts));   // the one structurally required host sync per step (:3412-3416)
+	stage_collect(ctx);
 	const uint32_t n_kept_local = counts[0];
 	if (counts_global) { counts[0] = counts_global[0]; counts[1] = counts_global[1]; counts[2] = counts_global[2]; }
 	++ctx->training_step;
@@ -472,7 +521,8 @@ int neus2_train_step_end(neus2_ctx* ctx, void* stream_, const uint32_t* counts_g
 			s.loss_valid = 1;
 		}
 		uint32_t rpb = (uint32_t)((float)ctx->rays_per_batch * (float)ctx->B / (float)counts[2]);
-		rpb = std::min((rpb + 127u) / 128u * 128u, 1u << 18);
+		const uint32_t gran = 128u * ctx->cfg.world_size;
+		rpb = std::min((rpb + gran - 1) / gran * gran, ctx->cfg.max_rays_per_batch);
 		ctx->rays_per_batch = rpb;
 	}
 	s.rays_per_batch_next = ctx->rays_per_batch;
@@ -487,7 +537,7 @@ int neus2_train_step(neus2_ctx* ctx, void* stream, neus2_step_stats* stats) {
 
 int neus2_debug_buffer(neus2_ctx* ctx, const char* name, void** ptr, uint64_t* n_bytes) {
 	struct E { const char* n; void* p; uint64_t b; };
-	const uint64_t R = ctx->max_rays, S = ctx->max_samples, B = ctx->B;
+	const uint64_t R = ctx->max_rays, S = ctx->max_samples, B = ctx->B_local;
 	const uint64_t G3n = (uint64_t)NERF_GRIDSIZE * NERF_GRIDSIZE * NERF_GRIDSIZE;
 	const E table[] = {
 		{"numsteps_all", ctx->numsteps_all, R * 4}, {"ray_indices", ctx->ray_indices, R * 4}, {"rays", ctx->rays, R * 24}, {"numsteps", ctx->numsteps, R * 8},
@@ -518,6 +568,18 @@ int neus2_set_bitfield(neus2_ctx* ctx, const uint8_t* bitfield_host, uint64_t n_
 	if (n_bytes != want) FAIL("bitfield size mismatch");
 	CUDA_CHECK(cudaSetDevice(ctx->device));
 	CUDA_CHECK(cudaMemcpy(ctx->bitfield, bitfield_host, n_bytes, cudaMemcpyHostToDevice));
+	return 0;
+}
+
+int neus2_set_profiling(neus2_ctx* ctx, int enable) {
+	if (enable && !ctx->ev[0]) { for (int i = 0; i < 2 * NEUS2_N_STAGES; ++i) CUDA_CHECK(cudaEventCreate(&ctx->ev[i])); }
+	ctx->profiling = enable;
+	for (int i = 0; i < NEUS2_N_STAGES; ++i) { ctx->stage_ms_sum[i] = 0.f; ctx->stage_count[i] = 0; ctx->stage_pending[i] = false; }
+	return 0;
+}
+
+int neus2_get_stage_times(neus2_ctx* ctx, float ms_sum[8], uint32_t count[8]) {
+	for (int i = 0; i < NEUS2_N_STAGES; ++i) { ms_sum[i] = ctx->stage_ms_sum[i]; count[i] = ctx->stage_count[i]; }
 	return 0;
 }
 
