@@ -32,7 +32,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--preroll", type=int, default=300, help="untimed training steps before warm-up so that rays_per_batch and the occupancy grid are in steady state")
+    ap.add_argument("--preroll", type=int, default=700, help="untimed training steps before warm-up so that rays_per_batch and the occupancy grid are in steady state")
     ap.add_argument("--views", type=int, default=49)
     ap.add_argument("--width", type=int, default=1600)
     ap.add_argument("--height", type=int, default=1200)

@@ -46,11 +46,17 @@ __device__ __forceinline__ void ray_dir_for_loss(const float* __restrict__ ray, 
 	global_move(gmv, ray_o, dir);
 }
 
-// pass 1: composite; ray_tmp[i] = {compacted (bits), rgb_ray[3], weight_sum, dir[3]}
-__global__ void k_loss_composite(const uint32_t* __restrict__ n_kept_ptr, GlobalMove gmv, float cos_anneal_ratio,
-                                 const __half* __restrict__ network_output, const float* __restrict__ rays, const uint32_t* __restrict__ numsteps,
-                                 const float* __restrict__ coords, float* __restrict__ ray_tmp, uint32_t* __restrict__ compacted_counts) {
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+// pass 1: composite, one WARP per ray.  Lanes evaluate 32 consecutive samples in parallel (the expensive part: three
+// logistic colours, exp(10*var), two logistic CDFs, a division); the order-dependent recurrences (T *= 1-alpha,
+// rgb_ray += w*rgb, weight_sum += w, and the T < 1e-4 early-out that fixes the compacted sample count) are then
+// replayed in sample order from warp shuffles, so every per-ray value is bit-identical to the serial loop.
+// ray_tmp[i] = {compacted (bits), rgb_ray[3], weight_sum, T, dir[3]}
+__global__ void __launch_bounds__(128)
+k_loss_composite(const uint32_t* __restrict__ n_kept_ptr, GlobalMove gmv, float cos_anneal_ratio,
+                 const __half* __restrict__ network_output, const float* __restrict__ rays, const uint32_t* __restrict__ numsteps,
+                 const float* __restrict__ coords, float* __restrict__ ray_tmp, uint32_t* __restrict__ compacted_counts) {
+	const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
 	if (i >= *n_kept_ptr) return;
 	const uint32_t ns = numsteps[i * 2 + 0], base = numsteps[i * 2 + 1];
 	const float* cin = coords + (size_t)base * 7;
@@ -62,26 +68,36 @@ __global__ void k_loss_composite(const uint32_t* __restrict__ n_kept_ptr, Global
 	uint32_t compacted = 0;
 	float ray_o[3], dir[3];
 	ray_dir_for_loss(rays + (size_t)i * 6, gmv, ray_o, dir);
-	for (; compacted < ns; ++compacted) {
-		if (T < EPSILON) break;
-		const __half* o = nout + (size_t)compacted * 16;
-		if (compacted == 0) {   // BENT_DIR :1583-1588
-			float dv[3] = {__half2float(o[8]) * 2.0f - 1.0f, __half2float(o[9]) * 2.0f - 1.0f, __half2float(o[10]) * 2.0f - 1.0f};
-			normalize3(dv, dir);
-		}
-		SampleEval e = eval_sample(o, cin + (size_t)compacted * 7, dir, cos_anneal_ratio);
-		const float weight = e.alpha * T;
-		#pragma unroll
-		for (int k = 0; k < 3; ++k) rgb_ray[k] += weight * e.rgb[k];
-		weight_sum += weight;
-		T *= (1.f - e.alpha);
+	{   // BENT_DIR :1583-1588 (from sample 0)
+		float dv[3] = {__half2float(nout[8]) * 2.0f - 1.0f, __half2float(nout[9]) * 2.0f - 1.0f, __half2float(nout[10]) * 2.0f - 1.0f};
+		if (ns > 0) normalize3(dv, dir);
 	}
-	float* rt = ray_tmp + (size_t)i * 12;
-	rt[0] = __uint_as_float(compacted);
-	rt[1] = rgb_ray[0]; rt[2] = rgb_ray[1]; rt[3] = rgb_ray[2];
-	rt[4] = weight_sum; rt[5] = T;
-	rt[6] = dir[0]; rt[7] = dir[1]; rt[8] = dir[2];
-	compacted_counts[i] = compacted;
+	bool stop = false;
+	for (uint32_t c0 = 0; c0 < ns && !stop; c0 += 32) {
+		const uint32_t idx = c0 + lane;
+		SampleEval e;
+		e.alpha = 0.f; e.rgb[0] = e.rgb[1] = e.rgb[2] = 0.f;
+		if (idx < ns) e = eval_sample(nout + (size_t)idx * 16, cin + (size_t)idx * 7, dir, cos_anneal_ratio);
+		const uint32_t cnt = min(32u, ns - c0);
+		for (uint32_t L = 0; L < cnt; ++L) {
+			if (T < EPSILON) { stop = true; break; }
+			const float a = __shfl_sync(0xffffffffu, e.alpha, L);
+			const float r0 = __shfl_sync(0xffffffffu, e.rgb[0], L), r1 = __shfl_sync(0xffffffffu, e.rgb[1], L), r2 = __shfl_sync(0xffffffffu, e.rgb[2], L);
+			const float weight = a * T;
+			rgb_ray[0] += weight * r0; rgb_ray[1] += weight * r1; rgb_ray[2] += weight * r2;
+			weight_sum += weight;
+			T *= (1.f - a);
+			++compacted;
+		}
+	}
+	if (lane == 0) {
+		float* rt = ray_tmp + (size_t)i * 12;
+		rt[0] = __uint_as_float(compacted);
+		rt[1] = rgb_ray[0]; rt[2] = rgb_ray[1]; rt[3] = rgb_ray[2];
+		rt[4] = weight_sum; rt[5] = T;
+		rt[6] = dir[0]; rt[7] = dir[1]; rt[8] = dir[2];
+		compacted_counts[i] = compacted;
+	}
 }
 
 #define SCAN_THREADS 1024
@@ -111,13 +127,15 @@ k_scan_compacted(const uint32_t* __restrict__ n_ptr, const uint32_t* __restrict_
 	for (uint32_t i = b; i < e; ++i) { base[i] = off; off += counts[i]; }
 }
 
-// pass 2: loss + dL/doutput + compaction (:1629-1957)
-__global__ void k_loss_gradient(uint32_t n_rays, uint32_t n_rays_total, Pcg32 rng_in, DatasetDev ds, LossParamsDev lp, uint32_t max_samples_compacted,
-                                const uint32_t* __restrict__ n_kept_ptr, const __half* __restrict__ network_output, const uint32_t* __restrict__ ray_indices,
-                                uint32_t* __restrict__ numsteps, const float* __restrict__ coords, const float* __restrict__ ray_tmp,
-                                const uint32_t* __restrict__ compacted_base_arr, float* __restrict__ coords_compacted, __half* __restrict__ dloss_doutput,
-                                float* __restrict__ loss_output, float* __restrict__ ek_loss_output, float* __restrict__ mask_loss_output) {
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+// pass 2: loss + dL/doutput + compaction (:1629-1957), one WARP per ray (see k_loss_composite).
+__global__ void __launch_bounds__(128)
+k_loss_gradient(uint32_t n_rays, uint32_t n_rays_total, Pcg32 rng_in, DatasetDev ds, LossParamsDev lp, uint32_t max_samples_compacted,
+                const uint32_t* __restrict__ n_kept_ptr, const __half* __restrict__ network_output, const uint32_t* __restrict__ ray_indices,
+                uint32_t* __restrict__ numsteps, const float* __restrict__ coords, const float* __restrict__ ray_tmp,
+                const uint32_t* __restrict__ compacted_base_arr, float* __restrict__ coords_compacted, __half* __restrict__ dloss_doutput,
+                float* __restrict__ loss_output, float* __restrict__ ek_loss_output, float* __restrict__ mask_loss_output) {
+	const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
 	if (i >= *n_kept_ptr) return;
 	const uint32_t ns = numsteps[i * 2 + 0], base = numsteps[i * 2 + 1];
 	const float* cin = coords + (size_t)base * 7;
@@ -153,10 +171,13 @@ __global__ void k_loss_gradient(uint32_t n_rays, uint32_t n_rays_total, Pcg32 rn
 		#pragma unroll
 		for (int k = 0; k < 3; ++k) rgb_ray[k] += T * bg[k];
 	}
+	__syncwarp();   // every lane has read numsteps before lane 0 rewrites it
 	const uint32_t compacted_base = compacted_base_arr[i];
 	compacted = min(max_samples_compacted - min(max_samples_compacted, compacted_base), compacted);
-	numsteps[i * 2 + 0] = compacted;
-	numsteps[i * 2 + 1] = compacted_base;
+	if (lane == 0) {
+		numsteps[i * 2 + 0] = compacted;
+		numsteps[i * 2 + 1] = compacted_base;
+	}
 	if (compacted == 0) return;
 
 	float* cout = coords_compacted + (size_t)compacted_base * 7;
@@ -181,25 +202,42 @@ __global__ void k_loss_gradient(uint32_t n_rays, uint32_t n_rays_total, Pcg32 rn
 		gradient_weight_sum = (mask_gt - sigmoid_weight_sum) * weight_sum * lp.mask_loss_weight;
 	}
 	const float mean_loss = (lg_loss[0] + lg_loss[1] + lg_loss[2]) / 3.0f;
-	loss_output[i] = mean_loss / (float)n_rays;
-	mask_loss_output[i] = -(mask_gt * logf(weight_sum) + (1 - mask_gt) * logf(1 - weight_sum));
+	if (lane == 0) {
+		loss_output[i] = mean_loss / (float)n_rays;
+		mask_loss_output[i] = -(mask_gt * logf(weight_sum) + (1 - mask_gt) * logf(1 - weight_sum));
+	}
 	float ek_acc = 0.f;
 
 	const float loss_scale = lp.loss_scale / n_rays;
 	float rgb_ray2[3] = {0.f, 0.f, 0.f};
 	T = 1.f;
-	for (uint32_t j = 0; j < compacted; ++j) {
-		#pragma unroll
-		for (int k = 0; k < 7; ++k) cout[(size_t)j * 7 + k] = cin[(size_t)j * 7 + k];
+	for (uint32_t c0 = 0; c0 < compacted; c0 += 32) {
+		const uint32_t cnt = min(32u, compacted - c0);
+		// compact the network inputs: cnt*7 contiguous floats, coalesced
+		for (uint32_t k = lane; k < cnt * 7; k += 32) cout[(size_t)c0 * 7 + k] = cin[(size_t)c0 * 7 + k];
+		const uint32_t j = c0 + lane;
+		const bool valid = lane < (int)cnt;
+		SampleEval e;
+		e.alpha = 0.f; e.rgb[0] = e.rgb[1] = e.rgb[2] = 0.f; e.p_div_c = 0.f; e.inv_s = 0.f; e.iter_cos = 0.f; e.dt = 0.f; e.next_sdf = 0.f; e.true_cos = 0.f; e.sdf = 0.f;
+		e.g[0] = e.g[1] = e.g[2] = 0.f;
 		const __half* o = nout + (size_t)j * 16;
-		SampleEval e = eval_sample(o, cin + (size_t)j * 7, dir, lp.cos_anneal_ratio);
-		const float weight = e.alpha * T;
-		#pragma unroll
-		for (int k = 0; k < 3; ++k) rgb_ray2[k] += weight * e.rgb[k];
-		T *= (1.f - e.alpha);
+		if (valid) e = eval_sample(o, cin + (size_t)j * 7, dir, lp.cos_anneal_ratio);
+		// replay the recurrences in sample order; lane L keeps the state right after its own sample
+		float my_weight = 0.f, my_T = 0.f, my_r2[3] = {0.f, 0.f, 0.f};
+		for (uint32_t L = 0; L < cnt; ++L) {
+			const float a = __shfl_sync(0xffffffffu, e.alpha, L);
+			const float r0 = __shfl_sync(0xffffffffu, e.rgb[0], L), r1 = __shfl_sync(0xffffffffu, e.rgb[1], L), r2 = __shfl_sync(0xffffffffu, e.rgb[2], L);
+			const float weight = a * T;
+			rgb_ray2[0] += weight * r0; rgb_ray2[1] += weight * r1; rgb_ray2[2] += weight * r2;
+			T *= (1.f - a);
+			if (lane == (int)L) { my_weight = weight; my_T = T; my_r2[0] = rgb_ray2[0]; my_r2[1] = rgb_ray2[1]; my_r2[2] = rgb_ray2[2]; }
+		}
+		if (!valid) continue;
+		const float weight = my_weight;
+		const float Tj = my_T;
 		float suffix[3], dloss_by_drgb[3];
 		#pragma unroll
-		for (int k = 0; k < 3; ++k) { suffix[k] = rgb_ray[k] - rgb_ray2[k]; dloss_by_drgb[k] = weight * lg_grad[k]; }
+		for (int k = 0; k < 3; ++k) { suffix[k] = rgb_ray[k] - my_r2[k]; dloss_by_drgb[k] = weight * lg_grad[k]; }
 		float local[16];
 		#pragma unroll
 		for (int k = 0; k < 16; ++k) local[k] = 0.f;
@@ -210,7 +248,7 @@ __global__ void k_loss_gradient(uint32_t n_rays, uint32_t n_rays_total, Pcg32 rn
 			const float deriv = density * (1 - density);
 			local[k] = loss_scale * (dloss_by_drgb[k] * deriv + fmaxf(0.0f, 0.0f * ov));
 		}
-		const float dot = lg_grad[0] * (T * e.rgb[0] - suffix[0]) + lg_grad[1] * (T * e.rgb[1] - suffix[1]) + lg_grad[2] * (T * e.rgb[2] - suffix[2]);
+		const float dot = lg_grad[0] * (Tj * e.rgb[0] - suffix[0]) + lg_grad[1] * (Tj * e.rgb[1] - suffix[1]) + lg_grad[2] * (Tj * e.rgb[2] - suffix[2]);
 		const float dloss_dalpha = (float)((dot + gradient_weight_sum * (1 - weight_sum)) / (1.0f - e.alpha + 1e-5));
 		float dalpha_d_e_minus_sigmoidx, d_e_minus_sigmoidx_dsdf, d_e_minus_sigmoidx_dinvs, d_alpha_d_plus_e, d_plus_e_dinvs, d_plus_e_iter_cos, d_e_minus_sigmoidx_diter_cos;
 		if (e.p_div_c <= 0.0f || e.p_div_c >= 1.0f) {
@@ -251,7 +289,10 @@ __global__ void k_loss_gradient(uint32_t n_rays, uint32_t n_rays_total, Pcg32 rn
 		reinterpret_cast<uint4*>(dout + (size_t)j * 16)[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
 		reinterpret_cast<uint4*>(dout + (size_t)j * 16)[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
 	}
-	ek_loss_output[i] = ek_acc / ((float)compacted * (float)n_rays);
+	// eikonal log value: warp reduction (the reference sums serially; fp32 order differs, it is a reported scalar only)
+	#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) ek_acc += __shfl_xor_sync(0xffffffffu, ek_acc, o);
+	if (lane == 0) ek_loss_output[i] = ek_acc / ((float)compacted * (float)n_rays);
 }
 
 int launch_compute_loss(cudaStream_t stream, uint32_t n_rays_local, uint32_t n_rays, uint32_t n_rays_total, const uint64_t rng_state[2], const DatasetDev& ds, const Aabb& bb,
@@ -262,7 +303,7 @@ int launch_compute_loss(cudaStream_t stream, uint32_t n_rays_local, uint32_t n_r
 	(void)bb;
 	if (n_rays_local == 0) return 0;
 	Pcg32 rng; rng.state = rng_state[0]; rng.inc = rng_state[1];
-	const uint32_t blocks = (n_rays_local + 127) / 128;
+	const uint32_t blocks = (n_rays_local + 3) / 4;   // one warp per ray
 	uint32_t* counts = scan_tmp;
 	uint32_t* cbase = scan_tmp + n_rays_local;
 	k_loss_composite<<<blocks, 128, 0, stream>>>(n_kept_ptr, gmv, lp.cos_anneal_ratio, network_output, rays, numsteps, coords, ray_tmp, counts);

@@ -34,14 +34,86 @@ __device__ __forceinline__ RaySetup setup_ray(uint32_t i, uint32_t n_rays, uint3
 	return r;
 }
 
-__global__ void k_rays_count(uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, uint32_t n_rays_total, Pcg32 rng, DatasetDev ds, Aabb bb, GlobalMove gmv,
-                             const uint8_t* __restrict__ bitfield, int snap, float cone_angle, uint32_t* __restrict__ numsteps_all) {
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+// Warp-per-ray marching.  Every position the reference's loop can visit lies on ONE arithmetic chain
+// t_0 = startt, t_{k+1} = fl(t_k + calc_dt(t_k)) -- both the occupied branch (t += dt, :1411) and the empty-space
+// skip (do t += dt while t < t_target, :374-376) only ever add dt.  A warp therefore evaluates a window of 32
+// consecutive chain positions in parallel (position, mip, occupancy bit, exit distance of the voxel) and then
+// replays the reference's control flow over the window with ballots.  The visited set, hence every per-ray sample
+// count and every emitted coordinate, is bit-identical to the serial loop; the dependent global load per step
+// (the reason the serial version is latency-bound) is gone.
+template <bool EMIT>
+__device__ __forceinline__ uint32_t march_ray_warp(const Aabb& bb, const float ray_o[3], const float dir[3], float startt, float cone_angle,
+                                                   const uint8_t* __restrict__ bitfield, uint32_t limit, float* __restrict__ coords, int lane) {
+	const float idir[3] = {1.0f / dir[0], 1.0f / dir[1], 1.0f / dir[2]};
+	const float wdir[3] = {(dir[0] + 1.0f) * 0.5f, (dir[1] + 1.0f) * 0.5f, (dir[2] + 1.0f) * 0.5f};
+	const float diag[3] = {bb.mx[0] - bb.mn[0], bb.mx[1] - bb.mn[1], bb.mx[2] - bb.mn[2]};
+	uint32_t j = 0;
+	float t_start = startt;
+	bool done = false;
+	while (!done) {
+		// chain positions of this window (sequential fp32 adds, identical in every lane)
+		float tl = t_start, t_mine = t_start;
+		#pragma unroll
+		for (int L = 0; L < 32; ++L) {
+			if (lane == L) t_mine = tl;
+			tl += calc_dt(tl, cone_angle);
+		}
+		float pos[3];
+		#pragma unroll
+		for (int k = 0; k < 3; ++k) pos[k] = fmaf(t_mine, dir[k], ray_o[k]);
+		const bool inside = aabb_contains(bb, pos);
+		const float dt = calc_dt(t_mine, cone_angle);
+		bool occ = false;
+		float t_target = 0.f;
+		if (inside) {
+			const uint32_t mip = (uint32_t)mip_from_dt(dt, pos);
+			occ = density_grid_occupied_at(pos, bitfield, mip);
+			if (!occ) t_target = t_mine + distance_to_next_voxel(pos, dir, idir, NERF_GRIDSIZE >> mip);
+		}
+		const uint32_t inside_mask = __ballot_sync(0xffffffffu, inside);
+		const uint32_t occ_mask = __ballot_sync(0xffffffffu, occ);
+		int my_j = -1;
+		int cur = 0;
+		float t_next = tl;   // start of the next window unless a skip overshoots it
+		while (cur < 32) {
+			if (!((inside_mask >> cur) & 1u) || j >= limit) { done = true; break; }
+			if ((occ_mask >> cur) & 1u) {
+				if (lane == cur) my_j = (int)j;
+				++j;
+				++cur;
+			} else {
+				const float tt = __shfl_sync(0xffffffffu, t_target, cur);
+				const uint32_t reach = __ballot_sync(0xffffffffu, lane > cur && t_mine >= tt);
+				if (reach) {
+					cur = __ffs(reach) - 1;
+				} else {   // lands beyond the window: keep walking the chain
+					while (t_next < tt) t_next += calc_dt(t_next, cone_angle);
+					cur = 32;
+				}
+			}
+		}
+		if (EMIT && my_j >= 0) {
+			float* c = coords + (size_t)my_j * 7;
+			#pragma unroll
+			for (int k = 0; k < 3; ++k) c[k] = (pos[k] - bb.mn[k]) / diag[k];
+			c[3] = warp_dt(dt);
+			c[4] = wdir[0]; c[5] = wdir[1]; c[6] = wdir[2];
+		}
+		t_start = t_next;
+	}
+	return j;
+}
+
+__global__ void __launch_bounds__(128)
+k_rays_count(uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, uint32_t n_rays_total, Pcg32 rng, DatasetDev ds, Aabb bb, GlobalMove gmv,
+             const uint8_t* __restrict__ bitfield, int snap, float cone_angle, uint32_t* __restrict__ numsteps_all) {
+	const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
 	if (i >= n_rays) return;
 	RaySetup r = setup_ray(i + ray_offset, n_rays_global, n_rays_total, rng, ds, bb, gmv, snap != 0, cone_angle);
 	uint32_t j = 0;
-	if (!r.skip) j = march_ray(bb, r.ray_o, r.dir, r.startt, cone_angle, bitfield, NERF_STEPS, nullptr);
-	numsteps_all[i] = j;
+	if (!r.skip) j = march_ray_warp<false>(bb, r.ray_o, r.dir, r.startt, cone_angle, bitfield, NERF_STEPS, nullptr, lane);
+	if (lane == 0) numsteps_all[i] = j;
 }
 
 // Single-CTA two-stage exclusive scan over <= 2^20 elements (n_rays <= 2^18 in practice):
@@ -98,22 +170,26 @@ k_scan_rays(uint32_t n, const uint32_t* __restrict__ counts, uint32_t max_sample
 	}
 }
 
-__global__ void k_rays_emit(uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, uint32_t n_rays_total, Pcg32 rng, DatasetDev ds, Aabb bb, GlobalMove gmv,
-                            const uint8_t* __restrict__ bitfield, int snap, float cone_angle, const uint32_t* __restrict__ numsteps_all,
-                            const uint32_t* __restrict__ base, const uint32_t* __restrict__ slot,
-                            uint32_t* __restrict__ ray_indices, float* __restrict__ rays, uint32_t* __restrict__ numsteps, float* __restrict__ coords) {
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128)
+k_rays_emit(uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, uint32_t n_rays_total, Pcg32 rng, DatasetDev ds, Aabb bb, GlobalMove gmv,
+            const uint8_t* __restrict__ bitfield, int snap, float cone_angle, const uint32_t* __restrict__ numsteps_all,
+            const uint32_t* __restrict__ base, const uint32_t* __restrict__ slot,
+            uint32_t* __restrict__ ray_indices, float* __restrict__ rays, uint32_t* __restrict__ numsteps, float* __restrict__ coords) {
+	const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
 	if (i >= n_rays) return;
 	const uint32_t sl = slot[i];
 	if (sl == 0xffffffffu) return;
 	RaySetup r = setup_ray(i + ray_offset, n_rays_global, n_rays_total, rng, ds, bb, gmv, snap != 0, cone_angle);
 	const uint32_t j = numsteps_all[i], b = base[i];
-	ray_indices[sl] = i + ray_offset;
-	#pragma unroll
-	for (int k = 0; k < 3; ++k) { rays[(size_t)sl * 6 + k] = r.o[k]; rays[(size_t)sl * 6 + 3 + k] = r.d[k]; }
-	numsteps[sl * 2 + 0] = j;
-	numsteps[sl * 2 + 1] = b;
-	march_ray(bb, r.ray_o, r.dir, r.startt, cone_angle, bitfield, j, coords + (size_t)b * 7);
+	if (lane == 0) {
+		ray_indices[sl] = i + ray_offset;
+		#pragma unroll
+		for (int k = 0; k < 3; ++k) { rays[(size_t)sl * 6 + k] = r.o[k]; rays[(size_t)sl * 6 + 3 + k] = r.d[k]; }
+		numsteps[sl * 2 + 0] = j;
+		numsteps[sl * 2 + 1] = b;
+	}
+	march_ray_warp<true>(bb, r.ray_o, r.dir, r.startt, cone_angle, bitfield, j, coords + (size_t)b * 7, lane);
 }
 
 int launch_generate_training_samples(cudaStream_t stream, uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, uint32_t n_rays_total, const uint64_t rng_state[2], const DatasetDev& ds,
@@ -122,7 +198,7 @@ int launch_generate_training_samples(cudaStream_t stream, uint32_t n_rays, uint3
                                      float* coords, uint32_t* counters) {
 	if (n_rays == 0) return 0;
 	Pcg32 rng; rng.state = rng_state[0]; rng.inc = rng_state[1];
-	const uint32_t blocks = (n_rays + 127) / 128;
+	const uint32_t blocks = (n_rays + 3) / 4;   // one warp per ray
 	k_rays_count<<<blocks, 128, 0, stream>>>(n_rays, ray_offset, n_rays_global, n_rays_total, rng, ds, bb, gmv, bitfield, snap, cone_angle, numsteps_all);
 	COUNT_LAUNCH(1);
 	CUDA_CHECK(cudaGetLastError());
