@@ -136,6 +136,7 @@ static int build_tables(neus2_ctx* ctx) {
 		params_in_level = (params_in_level + 7u) / 8u * 8u;
 		params_in_level = std::min(params_in_level, (1u << c.log2_hashmap_size));
 		gm.offset[i] = offset;
+		if ((uint64_t)resolution * resolution * resolution > (uint64_t)params_in_level) gm.hashed_mask |= 1u << i;
 		offset += params_in_level;
 	}
 	gm.offset[c.n_levels] = offset;
@@ -187,7 +188,7 @@ int neus2_ctx_create(const neus2_config* cfg, int device, neus2_ctx** out) {
 	CDM(ctx->mlp_out, 16 * (size_t)S); CDM(ctx->dloss, 16 * (size_t)B);
 	CDM(ctx->so.dOUT, 16 * (size_t)B); CDM(ctx->so.H2, 64 * (size_t)B); CDM(ctx->so.dH2, 64 * (size_t)B); CDM(ctx->so.H1, 64 * (size_t)B); CDM(ctx->so.dH1, 64 * (size_t)B);
 	CDM(ctx->so.CIN, 48 * (size_t)B); CDM(ctx->so.dSO, 16 * (size_t)B); CDM(ctx->so.H0, 64 * (size_t)B); CDM(ctx->so.dH0, 64 * (size_t)B);
-	CDM(ctx->so.X0, 32 * (size_t)B); CDM(ctx->so.gH, 64 * (size_t)B); CDM(ctx->so.dI, 32 * (size_t)B);
+	CDM(ctx->so.X0, 32 * (size_t)B); CDM(ctx->so.dI, 32 * (size_t)B);
 	CDM(ctx->partials, (size_t)weight_gradient_partials() * ctx->pl.off_grid); CDM(ctx->var_acc, 1); CDM(ctx->w1row0_acc, 64); CDM(ctx->scalar_tmp, 4);
 	const size_t G3n = (size_t)NERF_GRIDSIZE * NERF_GRIDSIZE * NERF_GRIDSIZE;
 	CDM(ctx->density_grid, G3n * ctx->n_cascades); CDM(ctx->density_grid_tmp, G3n * ctx->n_cascades);
@@ -213,7 +214,7 @@ void neus2_ctx_destroy(neus2_ctx* ctx) {
 	void* ptrs[] = {ctx->master, ctx->params, ctx->ema, ctx->grads, ctx->m1, ctx->m2, ctx->steps, ctx->d_pixels, ctx->d_focal, ctx->d_principal, ctx->d_xforms,
 		ctx->numsteps_all, ctx->base, ctx->slot, ctx->ray_indices, ctx->numsteps, ctx->scan_tmp, ctx->counters, ctx->rays, ctx->coords, ctx->ray_tmp,
 		ctx->coords_compacted, ctx->loss, ctx->ek_loss, ctx->mask_loss, ctx->mlp_out, ctx->dloss, ctx->so.dOUT, ctx->so.H2, ctx->so.dH2, ctx->so.H1, ctx->so.dH1,
-		ctx->so.CIN, ctx->so.dSO, ctx->so.H0, ctx->so.dH0, ctx->so.X0, ctx->so.gH, ctx->so.dI, ctx->partials, ctx->var_acc, ctx->w1row0_acc, ctx->scalar_tmp,
+		ctx->so.CIN, ctx->so.dSO, ctx->so.H0, ctx->so.dH0, ctx->so.X0, ctx->so.dI, ctx->partials, ctx->var_acc, ctx->w1row0_acc, ctx->scalar_tmp,
 		ctx->density_grid, ctx->density_grid_tmp, ctx->grid_positions, ctx->grid_indices, ctx->grid_density, ctx->bitfield, ctx->density_grid_mean};
 	for (void* p : ptrs) if (p) cudaFree(p);
 	if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
@@ -352,7 +353,7 @@ int neus2_backward(neus2_ctx* ctx, void* stream_, const float* coords, const voi
 	                            ctx->grads, ctx->var_acc, ctx->w1row0_acc, ctx->so));
 	stage_end(ctx, ST_FWDBWD, stream);
 	stage_begin(ctx, ST_WGRAD, stream);
-	CHECK(launch_weight_gradients(stream, ctx->pl, ctx->so, n_in_dev, n_rows, ctx->partials, weight_gradient_partials(), ctx->var_acc, ctx->w1row0_acc, ctx->grads));
+	CHECK(launch_weight_gradients(stream, ctx->pl, ctx->so, ctx->params, n_in_dev, n_rows, ctx->partials, weight_gradient_partials(), ctx->var_acc, ctx->w1row0_acc, ctx->grads));
 	stage_end(ctx, ST_WGRAD, stream);
 	return 0;
 }

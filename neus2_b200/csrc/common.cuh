@@ -10,6 +10,7 @@
 struct GridMeta {
 	uint32_t n_levels;
 	uint32_t valid_level;                 // levels > valid_level are masked (grid.h:198, 2427-2440)
+	uint32_t hashed_mask;                 // bit l set <=> level l is hashed (res^3 > hashmap size; grid.h:143-150)
 	uint32_t offset[NEUS_MAX_LEVELS + 1]; // in entries (x2 features)
 	uint32_t res[NEUS_MAX_LEVELS];
 	float scale[NEUS_MAX_LEVELS];         // == res-1 (integer valued, grid.h:1477)

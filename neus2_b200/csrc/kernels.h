@@ -14,7 +14,6 @@ struct StagedOperands {
 	__half* H0;   // [n][64] sdf hidden
 	__half* dH0;  // [n][64]
 	__half* X0;   // [n][32] sdf-MLP input
-	__half* gH;   // [n][64] relu'(h0) * W1[0,:]      (second-order reverse sweep)
 	__half* dI;   // [n][32] d_density_input           (second-order forward seed)
 };
 
@@ -27,7 +26,7 @@ int launch_network_fwdbwd(cudaStream_t stream, const GridMeta& gm, const ParamLa
                           float* grads, float* var_acc, float* w1row0_acc, const StagedOperands& so);
 
 // weight-gradient GEMMs: grads[mlp part] += sum over rows (see wgrad.cu)
-int launch_weight_gradients(cudaStream_t stream, const ParamLayout& pl, const StagedOperands& so,
+int launch_weight_gradients(cudaStream_t stream, const ParamLayout& pl, const StagedOperands& so, const __half* params,
                             const uint32_t* n_in_ptr, uint32_t n_rows, float* partials, uint32_t n_partials,
                             const float* var_acc, const float* w1row0_acc, float* grads);
 uint32_t weight_gradient_partials();   // number of per-CTA partial slots `partials` must hold (x n_mlp_params floats)

@@ -129,9 +129,7 @@ __device__ __forceinline__ void pack_frags(const float (&c)[NT][4], uint32_t (&a
 
 // per-half mask: 0xffff where the half in `ref` is > 0 (hidden activation passed the ReLU)
 __device__ __forceinline__ uint32_t relu_mask2(uint32_t ref) {
-	uint32_t lo = ((ref & 0x7fffu) != 0u && (ref & 0x8000u) == 0u) ? 0x0000ffffu : 0u;
-	uint32_t hi = ((ref & 0x7fff0000u) != 0u && (ref & 0x80000000u) == 0u) ? 0xffff0000u : 0u;
-	return lo | hi;
+	return __hgt2_mask(*reinterpret_cast<const __half2*>(&ref), __half2half2(__ushort_as_half((unsigned short)0)));   // one HSET2
 }
 
 template <int NT>
@@ -182,7 +180,13 @@ __device__ __forceinline__ uint32_t grid_index(bool hashed, uint32_t hashmap_siz
 		return (index & (hashmap_size - 1u)) * 2u;   // hashed levels have power-of-two size (2^log2_hashmap_size)
 	}
 	index = x + y * res + z * res * res;
-	return (index % hashmap_size) * 2u;
+	// index % hashmap_size: for positions in [0,1] the dense index is < 2*hashmap_size, so one conditional subtract
+	// replaces the integer division; anything else (out-of-range inputs) takes the general path.
+	if (index >= hashmap_size) {
+		index -= hashmap_size;
+		if (index >= hashmap_size) index %= hashmap_size;
+	}
+	return index * 2u;
 }
 
 struct LevelGeom {
@@ -194,7 +198,7 @@ __device__ __forceinline__ void level_geom(const GridMeta& gm, int l, float x, f
 	const float scale = gm.scale[l];
 	const uint32_t res = gm.res[l];
 	const uint32_t hs = gm.offset[l + 1] - gm.offset[l];
-	const bool hashed = (uint64_t)res * res * res > (uint64_t)hs;
+	const bool hashed = (gm.hashed_mask >> l) & 1u;
 	uint32_t p[3];
 	const float in[3] = {x, y, z};
 	#pragma unroll

@@ -7,7 +7,8 @@
 #define THREADS_PER_CTA (WARPS_PER_CTA * 32)
 
 static constexpr int FWD_SMEM = WeightSmem::FWD_END * 2 + WARPS_PER_CTA * WarpSlab::FWD_END;
-static constexpr int BWD_SMEM = WeightSmem::BWD_END * 2 + WARPS_PER_CTA * WarpSlab::BWD_END;
+#define WARPS_BWD 12
+static constexpr int BWD_SMEM = WeightSmem::BWD_END * 2 + WARPS_BWD * WarpSlab::BWD_END;
 
 // coalesced load of a tile's coords (16 x 7 floats) into the warp slab; rows >= n_valid are zero-filled.
 // src_row(i) maps tile row -> source row (identity, or the fill_rollover wrap).
@@ -131,7 +132,7 @@ k_network_sdf(GridMeta gm, ParamLayout pl, const __half* __restrict__ params, co
 //   w1row0_acc[64]        += column sums of the forward-mode sweep (second-order term of W1 row 0)
 //   staged operand matrices (half, row-major [n_rows][w]) for the weight-gradient GEMMs.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(THREADS_PER_CTA, 1)
+__global__ void __launch_bounds__(WARPS_BWD * 32, 1)
 k_network_fwdbwd(GridMeta gm, ParamLayout pl, const __half* __restrict__ params, const float* __restrict__ coords,
                  const __half* __restrict__ dL_dout, const uint32_t* __restrict__ n_in_ptr, uint32_t n_rows, float sdf_bias,
                  float batch_f, float* __restrict__ grads, float* __restrict__ var_acc, float* __restrict__ w1row0_acc, StagedOperands so) {
@@ -165,7 +166,7 @@ k_network_fwdbwd(GridMeta gm, ParamLayout pl, const __half* __restrict__ params,
 	const int E = 2 * (int)gm.n_levels;
 
 	FwdState st;
-	for (uint32_t tile = blockIdx.x * WARPS_PER_CTA + warp; tile < n_tiles; tile += gridDim.x * WARPS_PER_CTA) {
+	for (uint32_t tile = blockIdx.x * WARPS_BWD + warp; tile < n_tiles; tile += gridDim.x * WARPS_BWD) {
 		const uint32_t row0 = tile * TILE;
 		const int n_valid = (int)min((uint32_t)TILE, n_rows - row0);
 		load_coords(sCoord, coords, row0, n_rows, n_in, lane);
@@ -289,18 +290,7 @@ k_network_fwdbwd(GridMeta gm, ParamLayout pl, const __half* __restrict__ params,
 		__syncwarp();
 		// ---- second-order sdf-MLP sweeps (fully_fused_mlp.cu:1089-1198)
 		{
-			// back sweep operand: relu'(h0) * W1[0,:]  (seed e0)   -> staged as gH
-			uint32_t gh[4][4];
-			#pragma unroll
-			for (int kt = 0; kt < 4; ++kt) {
-				const uint32_t wlo = *reinterpret_cast<const uint32_t*>(sw + WeightSmem::W1 + 16 * kt + 2 * t);
-				const uint32_t whi = *reinterpret_cast<const uint32_t*>(sw + WeightSmem::W1 + 16 * kt + 8 + 2 * t);
-				gh[kt][0] = wlo & relu_mask2(st.h0a[kt][0]);
-				gh[kt][1] = wlo & relu_mask2(st.h0a[kt][1]);
-				gh[kt][2] = whi & relu_mask2(st.h0a[kt][2]);
-				gh[kt][3] = whi & relu_mask2(st.h0a[kt][3]);
-			}
-			store_a_global<4>(gh, so.gH, 64, row0, n_valid, g, t);
+			// (the reverse-sweep operand relu'(h0) * W1[0,:] is rebuilt from the staged H0 inside the weight-gradient kernel)
 			// forward-mode sweep: relu'(h0) * (W0 d_in)  -> contributes to dW1 row 0 (column sums over samples)
 			uint32_t da[2][4];
 			load_a_frag(da[0], sDI, LD_X0, 0, g, t);
@@ -422,9 +412,9 @@ int launch_network_fwdbwd(cudaStream_t stream, const GridMeta& gm, const ParamLa
 	if (n_rows == 0) return 0;
 	const uint32_t n_tiles = (n_rows + TILE - 1) / TILE;
 	uint32_t grid = (uint32_t)num_sms();
-	const uint32_t need = (n_tiles + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+	const uint32_t need = (n_tiles + WARPS_BWD - 1) / WARPS_BWD;
 	if (need < grid) grid = need;
-	k_network_fwdbwd<<<grid, THREADS_PER_CTA, BWD_SMEM, stream>>>(gm, pl, params, coords, dL_dout, n_in_ptr, n_rows, sdf_bias,
+	k_network_fwdbwd<<<grid, WARPS_BWD * 32, BWD_SMEM, stream>>>(gm, pl, params, coords, dL_dout, n_in_ptr, n_rows, sdf_bias,
 		(float)indeed_batch_size, grads, var_acc, w1row0_acc, so);
 	COUNT_LAUNCH(1);
 	CUDA_CHECK(cudaGetLastError());

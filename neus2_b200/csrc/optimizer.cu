@@ -5,43 +5,84 @@
 #include "ngp_common.cuh"
 #include "ngp_kernels.h"
 
-__global__ void k_adam_ema(uint64_t n, uint64_t n_matrix, float loss_scale, float lr, float beta1, float beta2, float eps, float l2_reg,
-                           float ema_decay, float ema_debias_old, float ema_debias_new, const float* __restrict__ grads,
-                           float* __restrict__ master, __half* __restrict__ params, float* __restrict__ m1, float* __restrict__ m2,
-                           uint32_t* __restrict__ steps, __half* __restrict__ ema) {
-	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	float gradient = grads[i] / loss_scale;
-	const bool is_matrix = i < n_matrix;
-	__half p = params[i];
+struct AdamHyper { float loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, ema_debias_old, ema_debias_new; };
+
+__device__ __forceinline__ __half adam_one(bool is_matrix, float g_raw, const AdamHyper& h, float& w, float& m1, float& m2, uint32_t& step, __half p, bool& touched) {
+	float gradient = g_raw / h.loss_scale;
+	touched = false;
 	if (is_matrix || gradient != 0) {            // adam.h:109-112: non-matrix params with zero gradient are skipped entirely
-		const float w = master[i];
-		if (is_matrix) gradient += l2_reg * w;   // adam.h:132-135
+		touched = true;
+		if (is_matrix) gradient += h.l2_reg * w;   // adam.h:132-135
 		const float gsq = gradient * gradient;
-		const float fm = beta1 * m1[i] + (1 - beta1) * gradient;
-		const float sm = beta2 * m2[i] + (1 - beta2) * gsq;
-		m1[i] = fm; m2[i] = sm;
-		float learning_rate = lr;
-		const uint32_t cs = ++steps[i];
-		learning_rate *= sqrtf(1 - powf(beta2, (float)cs)) / (1 - powf(beta1, (float)cs));
-		const float eff = fminf(fmaxf(learning_rate / (sqrtf(sm) + eps), 0.f), 3.402823466e+38f);
+		const float fm = h.beta1 * m1 + (1 - h.beta1) * gradient;
+		const float sm = h.beta2 * m2 + (1 - h.beta2) * gsq;
+		m1 = fm; m2 = sm;
+		float learning_rate = h.lr;
+		const uint32_t cs = ++step;
+		learning_rate *= sqrtf(1 - powf(h.beta2, (float)cs)) / (1 - powf(h.beta1, (float)cs));
+		const float eff = fminf(fmaxf(learning_rate / (sqrtf(sm) + h.eps), 0.f), 3.402823466e+38f);
 		const float decayed = (1 - 0.f * learning_rate) * w - copysignf(0.f * learning_rate, w);
 		const float nw = decayed - eff * fm;
-		master[i] = nw;
+		w = nw;
 		p = __float2half_rn(nw);
-		params[i] = p;
 	}
-	const float filtered = (__half2float(ema[i]) * ema_decay * ema_debias_old + __half2float(p) * (1 - ema_decay)) * ema_debias_new;
-	ema[i] = __float2half_rn(filtered);
+	return p;
+}
+
+// 4 consecutive parameters per thread (n and n_matrix are multiples of 4): 16-byte gradient loads; the optimizer state of an
+// untouched quad (the common case for the sparse hash-grid levels) is never read.
+__global__ void __launch_bounds__(256)
+k_adam_ema(uint64_t n4, uint64_t n_matrix4, AdamHyper h, const float* __restrict__ grads,
+           float* __restrict__ master, __half* __restrict__ params, float* __restrict__ m1, float* __restrict__ m2,
+           uint32_t* __restrict__ steps, __half* __restrict__ ema) {
+	const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= n4) return;
+	const bool is_matrix = q < n_matrix4;
+	const float4 g4 = reinterpret_cast<const float4*>(grads)[q];
+	uint2 pw = reinterpret_cast<const uint2*>(params)[q];
+	__half* ph = reinterpret_cast<__half*>(&pw);
+	const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+	if (is_matrix || g4.x != 0.f || g4.y != 0.f || g4.z != 0.f || g4.w != 0.f) {
+		float4 w4 = reinterpret_cast<const float4*>(master)[q];
+		float4 a4 = reinterpret_cast<const float4*>(m1)[q];
+		float4 b4 = reinterpret_cast<const float4*>(m2)[q];
+		uint4 s4 = reinterpret_cast<const uint4*>(steps)[q];
+		float* w = reinterpret_cast<float*>(&w4); float* a = reinterpret_cast<float*>(&a4); float* b = reinterpret_cast<float*>(&b4);
+		uint32_t* st = reinterpret_cast<uint32_t*>(&s4);
+		bool any = false;
+		#pragma unroll
+		for (int k = 0; k < 4; ++k) {
+			bool touched;
+			ph[k] = adam_one(is_matrix, g[k], h, w[k], a[k], b[k], st[k], ph[k], touched);
+			any |= touched;
+		}
+		if (any) {
+			reinterpret_cast<float4*>(master)[q] = w4;
+			reinterpret_cast<float4*>(m1)[q] = a4;
+			reinterpret_cast<float4*>(m2)[q] = b4;
+			reinterpret_cast<uint4*>(steps)[q] = s4;
+			reinterpret_cast<uint2*>(params)[q] = pw;
+		}
+	}
+	uint2 ew = reinterpret_cast<const uint2*>(ema)[q];
+	__half* eh = reinterpret_cast<__half*>(&ew);
+	#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		const float filtered = (__half2float(eh[k]) * h.ema_decay * h.ema_debias_old + __half2float(ph[k]) * (1 - h.ema_decay)) * h.ema_debias_new;
+		eh[k] = __float2half_rn(filtered);
+	}
+	reinterpret_cast<uint2*>(ema)[q] = ew;
 }
 
 int launch_adam_ema(cudaStream_t stream, uint64_t n, uint64_t n_matrix, float loss_scale, float lr, float beta1, float beta2, float eps, float l2_reg,
                     float ema_decay, uint32_t ema_step, const float* grads, float* master, __half* params, float* m1, float* m2, uint32_t* steps, __half* ema) {
 	const float ema_debias_old = 1 - (float)pow((double)ema_decay, (double)(ema_step - 1));
 	const float ema_debias_new = 1.0f / (1 - (float)pow((double)ema_decay, (double)ema_step));
-	const uint32_t blocks = (uint32_t)((n + 255) / 256);
-	k_adam_ema<<<blocks, 256, 0, stream>>>(n, n_matrix, loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, ema_debias_old, ema_debias_new,
-	                                      grads, master, params, m1, m2, steps, ema);
+	if (n % 4 != 0 || n_matrix % 4 != 0) { neus_set_error("parameter counts must be multiples of 4", __FILE__, __LINE__); return -1; }
+	AdamHyper h = {loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, ema_debias_old, ema_debias_new};
+	const uint64_t n4 = n / 4;
+	const uint32_t blocks = (uint32_t)((n4 + 255) / 256);
+	k_adam_ema<<<blocks, 256, 0, stream>>>(n4, n_matrix / 4, h, grads, master, params, m1, m2, steps, ema);
 	COUNT_LAUNCH(1);
 	CUDA_CHECK(cudaGetLastError());
 	return 0;
