@@ -51,7 +51,8 @@ struct neus2_ctx {
 	DatasetDev ds; uint8_t* d_pixels; float* d_focal; float* d_principal; float* d_xforms;
 
 	// training scratch
-	uint32_t *numsteps_all, *base, *slot, *ray_indices, *numsteps, *scan_tmp, *counters;
+	uint32_t *numsteps_all, *base, *slot, *ray_indices, *numsteps, *scan_tmp, *counters, *n_windows;
+	unsigned char* windows; float* ray_setup;
 	float *rays, *coords, *ray_tmp, *coords_compacted, *loss, *ek_loss, *mask_loss;
 	__half *mlp_out, *dloss;
 	StagedOperands so;
@@ -183,6 +184,7 @@ int neus2_ctx_create(const neus2_config* cfg, int device, neus2_ctx** out) {
 	#define CDM(ptr, count) CTXCHECK(dmalloc((void**)&(ptr), sizeof(*(ptr)) * (size_t)(count)))
 	CDM(ctx->master, N); CDM(ctx->params, N); CDM(ctx->ema, N); CDM(ctx->grads, N); CDM(ctx->m1, N); CDM(ctx->m2, N); CDM(ctx->steps, N);
 	CDM(ctx->numsteps_all, R); CDM(ctx->base, R); CDM(ctx->slot, R); CDM(ctx->ray_indices, R); CDM(ctx->numsteps, 2 * (size_t)R); CDM(ctx->scan_tmp, 2 * (size_t)R);
+	CDM(ctx->n_windows, R); CDM(ctx->windows, sampling_window_bytes_per_ray() * (size_t)R); CDM(ctx->ray_setup, 12 * (size_t)R);
 	CDM(ctx->counters, 8); CDM(ctx->rays, 6 * (size_t)R); CDM(ctx->coords, 7 * (size_t)S); CDM(ctx->ray_tmp, 12 * (size_t)R);
 	CDM(ctx->coords_compacted, 7 * (size_t)B); CDM(ctx->loss, R); CDM(ctx->ek_loss, R); CDM(ctx->mask_loss, R);
 	CDM(ctx->mlp_out, 16 * (size_t)S); CDM(ctx->dloss, 16 * (size_t)B);
@@ -212,7 +214,7 @@ int neus2_ctx_create(const neus2_config* cfg, int device, neus2_ctx** out) {
 void neus2_ctx_destroy(neus2_ctx* ctx) {
 	if (!ctx) return;
 	void* ptrs[] = {ctx->master, ctx->params, ctx->ema, ctx->grads, ctx->m1, ctx->m2, ctx->steps, ctx->d_pixels, ctx->d_focal, ctx->d_principal, ctx->d_xforms,
-		ctx->numsteps_all, ctx->base, ctx->slot, ctx->ray_indices, ctx->numsteps, ctx->scan_tmp, ctx->counters, ctx->rays, ctx->coords, ctx->ray_tmp,
+		ctx->numsteps_all, ctx->base, ctx->slot, ctx->ray_indices, ctx->numsteps, ctx->scan_tmp, ctx->counters, ctx->n_windows, ctx->windows, ctx->ray_setup, ctx->rays, ctx->coords, ctx->ray_tmp,
 		ctx->coords_compacted, ctx->loss, ctx->ek_loss, ctx->mask_loss, ctx->mlp_out, ctx->dloss, ctx->so.dOUT, ctx->so.H2, ctx->so.dH2, ctx->so.H1, ctx->so.dH1,
 		ctx->so.CIN, ctx->so.dSO, ctx->so.H0, ctx->so.dH0, ctx->so.X0, ctx->so.dI, ctx->partials, ctx->var_acc, ctx->w1row0_acc, ctx->scalar_tmp,
 		ctx->density_grid, ctx->density_grid_tmp, ctx->grid_positions, ctx->grid_indices, ctx->grid_density, ctx->bitfield, ctx->density_grid_mean};
@@ -455,7 +457,7 @@ int neus2_train_step_begin(neus2_ctx* ctx, void* stream_, uint32_t rank, uint32_
 	stage_begin(ctx, ST_GEN, stream);
 	CHECK(launch_generate_training_samples(stream, n_local, ray_offset, R, n_rays_total, st, ctx->ds, ctx->aabb, ctx->gmv, ctx->bitfield, c.snap_to_pixel_centers,
 	                                       ctx->cone_angle_constant, max_inference, ctx->numsteps_all, ctx->base, ctx->slot, ctx->ray_indices, ctx->rays,
-	                                       ctx->numsteps, ctx->coords, ctx->counters));
+	                                       ctx->numsteps, ctx->coords, ctx->counters, ctx->windows, ctx->n_windows, ctx->ray_setup));
 	stage_end(ctx, ST_GEN, stream);
 	stage_begin(ctx, ST_FWD, stream);
 	CHECK(launch_network_forward(stream, ctx->gm, ctx->pl, ctx->params, ctx->coords, ctx->counters + 1, max_inference, c.sdf_bias, ctx->mlp_out));   // :3854

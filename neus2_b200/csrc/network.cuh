@@ -192,6 +192,7 @@ __device__ __forceinline__ uint32_t grid_index(bool hashed, uint32_t hashmap_siz
 struct LevelGeom {
 	float w[3];          // fractional position
 	uint32_t idx[8];     // feature-pair index (in halves) of the 8 corners, corner bit d set => +1 in dim d
+	uint32_t cell[3];    // integer cell coordinates (pos_grid)
 };
 
 __device__ __forceinline__ void level_geom(const GridMeta& gm, int l, float x, float y, float z, LevelGeom& lg) {
@@ -207,6 +208,7 @@ __device__ __forceinline__ void level_geom(const GridMeta& gm, int l, float x, f
 		float fl = floorf(pf);
 		p[d] = (uint32_t)(int)fl;
 		lg.w[d] = pf - fl;
+		lg.cell[d] = p[d];
 	}
 	#pragma unroll
 	for (int c = 0; c < 8; ++c) {

@@ -2,6 +2,7 @@
 // forward+backward training kernel.  See network.cuh for the per-warp pipeline.
 #include "network.cuh"
 #include "kernels.h"
+#include <cstdlib>
 
 #define WARPS_PER_CTA 8
 #define THREADS_PER_CTA (WARPS_PER_CTA * 32)
@@ -135,7 +136,7 @@ k_network_sdf(GridMeta gm, ParamLayout pl, const __half* __restrict__ params, co
 __global__ void __launch_bounds__(WARPS_BWD * 32, 1)
 k_network_fwdbwd(GridMeta gm, ParamLayout pl, const __half* __restrict__ params, const float* __restrict__ coords,
                  const __half* __restrict__ dL_dout, const uint32_t* __restrict__ n_in_ptr, uint32_t n_rows, float sdf_bias,
-                 float batch_f, float* __restrict__ grads, float* __restrict__ var_acc, float* __restrict__ w1row0_acc, StagedOperands so) {
+                 float batch_f, float* __restrict__ grads, float* __restrict__ var_acc, float* __restrict__ w1row0_acc, StagedOperands so, int dbg) {
 	extern __shared__ __align__(16) unsigned char smem[];
 	__half* sw = reinterpret_cast<__half*>(smem);
 	stage_weights(sw, params, pl, true, threadIdx.x, blockDim.x);
@@ -207,15 +208,15 @@ k_network_fwdbwd(GridMeta gm, ParamLayout pl, const __half* __restrict__ params,
 			mma_layer<1, 8>(dout, sw + WeightSmem::C2T, LD_T16, c, g, t);
 			pack_frags_masked<8>(c, st.h2a, dh2a);
 		}
-		store_a_global<4>(st.h2a, so.H2, 64, row0, n_valid, g, t);
-		store_a_global<4>(dh2a, so.dH2, 64, row0, n_valid, g, t);
+		if (!(dbg & 2)) store_a_global<4>(st.h2a, so.H2, 64, row0, n_valid, g, t);
+		if (!(dbg & 2)) store_a_global<4>(dh2a, so.dH2, 64, row0, n_valid, g, t);
 		{
 			float c[8][4];
 			mma_layer<4, 8>(dh2a, sw + WeightSmem::C1T, LD_H, c, g, t);
 			pack_frags_masked<8>(c, st.h1a, dh1a);
 		}
-		store_a_global<4>(st.h1a, so.H1, 64, row0, n_valid, g, t);
-		store_a_global<4>(dh1a, so.dH1, 64, row0, n_valid, g, t);
+		if (!(dbg & 2)) store_a_global<4>(st.h1a, so.H1, 64, row0, n_valid, g, t);
+		if (!(dbg & 2)) store_a_global<4>(dh1a, so.dH1, 64, row0, n_valid, g, t);
 		uint32_t dso[1][4];
 		{
 			float c[6][4];
@@ -251,8 +252,8 @@ k_network_fwdbwd(GridMeta gm, ParamLayout pl, const __half* __restrict__ params,
 			pack_frags_masked<8>(c, st.h0a, dh0a);
 		}
 		store_a_global<1>(dso, so.dSO, 16, row0, n_valid, g, t);
-		store_a_global<4>(st.h0a, so.H0, 64, row0, n_valid, g, t);
-		store_a_global<4>(dh0a, so.dH0, 64, row0, n_valid, g, t);
+		if (!(dbg & 2)) store_a_global<4>(st.h0a, so.H0, 64, row0, n_valid, g, t);
+		if (!(dbg & 2)) store_a_global<4>(dh0a, so.dH0, 64, row0, n_valid, g, t);
 		{
 			float c[4][4];
 			mma_layer<4, 4>(dh0a, sw + WeightSmem::W0T, LD_H, c, g, t);
@@ -314,31 +315,62 @@ k_network_fwdbwd(GridMeta gm, ParamLayout pl, const __half* __restrict__ params,
 			}
 		}
 		// ---- hash-grid gradient: first order (grid.h:371-500) + second order (grid.h:880-1007), one vector
-		//      atomic per corner instead of 8 + 24 half2 atomics.
+		//      atomic per corner instead of 8 + 24 half2 atomics.  Samples of a tile are consecutive along a ray, so at the
+		//      coarse levels neighbouring lanes fall into the SAME cell: contributions of such a run of lanes are summed
+		//      with a segmented shuffle reduction and only the run head issues the atomics (warp-level pre-reduction).
 		{
 			const int s = lane & 15;
-			if (s < n_valid) {
-				const float x = sCoord[s * 7 + 0], y = sCoord[s * 7 + 1], z = sCoord[s * 7 + 2];
-				const float v0 = sV[s * 3 + 0], v1 = sV[s * 3 + 1], v2 = sV[s * 3 + 2];
-				for (int l = lane >> 4; l < (int)gm.n_levels; l += 2) {
-					if ((uint32_t)l > gm.valid_level) continue;
-					LevelGeom lg;
-					level_geom(gm, l, x, y, z, lg);
-					const float scale = gm.scale[l];
-					const float d0 = __half2float(sDX[s * LD_X0 + 3 + 2 * l]), d1 = __half2float(sDX[s * LD_X0 + 4 + 2 * l]);   // dL/d enc
-					const float e0 = __half2float(sDIN[s * LD_X0 + 3 + 2 * l]), e1 = __half2float(sDIN[s * LD_X0 + 4 + 2 * l]); // d sdf/d enc
-					const float wx[2] = {1.f - lg.w[0], lg.w[0]}, wy[2] = {1.f - lg.w[1], lg.w[1]}, wz[2] = {1.f - lg.w[2], lg.w[2]};
-					const float gi0 = scale * v0, gi1 = scale * v1, gi2 = scale * v2;   // grad_in (pos_derivative = 1)
+			const bool active = s < n_valid;
+			const float x = sCoord[s * 7 + 0], y = sCoord[s * 7 + 1], z = sCoord[s * 7 + 2];
+			const float v0 = sV[s * 3 + 0], v1 = sV[s * 3 + 1], v2 = sV[s * 3 + 2];
+			const uint32_t half_mask = (lane < 16) ? 0x0000ffffu : 0xffff0000u;
+			for (int l = lane >> 4; l < (int)gm.n_levels; l += 2) {   // both half-warps run the same number of iterations +-1
+				if ((uint32_t)l > gm.valid_level) continue;
+				LevelGeom lg;
+				level_geom(gm, l, x, y, z, lg);
+				const float scale = gm.scale[l];
+				const float d0 = __half2float(sDX[s * LD_X0 + 3 + 2 * l]), d1 = __half2float(sDX[s * LD_X0 + 4 + 2 * l]);   // dL/d enc
+				const float e0 = __half2float(sDIN[s * LD_X0 + 3 + 2 * l]), e1 = __half2float(sDIN[s * LD_X0 + 4 + 2 * l]); // d sdf/d enc
+				const float wx[2] = {1.f - lg.w[0], lg.w[0]}, wy[2] = {1.f - lg.w[1], lg.w[1]}, wz[2] = {1.f - lg.w[2], lg.w[2]};
+				const float gi0 = scale * v0, gi1 = scale * v1, gi2 = scale * v2;   // grad_in (pos_derivative = 1)
+				float a0[8], a1[8];
+				#pragma unroll
+				for (int c = 0; c < 8; ++c) {
+					const int bx = c & 1, by = (c >> 1) & 1, bz = (c >> 2) & 1;
+					const float w1 = (wx[bx] * wy[by]) * wz[bz];
+					// second order: sum over grad_dim of +-(grad_in * w_other0 * w_other1)
+					const float sx = (gi0 * wy[by]) * wz[bz], sy = (gi1 * wx[bx]) * wz[bz], sz = (gi2 * wx[bx]) * wy[by];
+					const float w2 = (bx ? sx : -sx) + (by ? sy : -sy) + (bz ? sz : -sz);
+					a0[c] = active ? d0 * w1 + e0 * w2 : 0.f;
+					a1[c] = active ? d1 * w1 + e1 * w2 : 0.f;
+				}
+				// runs of consecutive lanes (within this half-warp) that sit in the same grid cell; all 16 lanes of the
+				// half-warp reach every shuffle below (no divergent exits), the two half-warps sync independently
+				const uint32_t ka = lg.cell[0] | (lg.cell[1] << 16), kb = lg.cell[2];
+				const uint32_t pa = __shfl_up_sync(half_mask, ka, 1), pb = __shfl_up_sync(half_mask, kb, 1);
+				const bool head = (s == 0) || ka != pa || kb != pb;
+				const uint32_t heads = __ballot_sync(half_mask, head);
+				bool issue = active;
+				if (__popc(heads) <= 10) {   // enough merging to pay for the reduction (coarse levels); uniform per half-warp
+					const uint32_t hs16 = (heads >> (lane & 16)) & 0xffffu;
+					const int run = __popc(hs16 & ((2u << s) - 1u));
+					#pragma unroll
+					for (int d = 1; d < 16; d <<= 1) {
+						const int other = __shfl_down_sync(half_mask, run, d);
+						const bool take = (s + d < 16) && other == run;
+						#pragma unroll
+						for (int c = 0; c < 8; ++c) {
+							const float t0 = __shfl_down_sync(half_mask, a0[c], d), t1 = __shfl_down_sync(half_mask, a1[c], d);
+							if (take) { a0[c] += t0; a1[c] += t1; }
+						}
+					}
+					issue = head;   // inactive lanes contributed zeros; a head that is itself inactive still carries its run's sum
+				}
+				if (issue) {
 					float* gl = ggrid + (size_t)gm.offset[l] * 2;
 					#pragma unroll
 					for (int c = 0; c < 8; ++c) {
-						const int bx = c & 1, by = (c >> 1) & 1, bz = (c >> 2) & 1;
-						const float w1 = (wx[bx] * wy[by]) * wz[bz];
-						// second order: sum over grad_dim of +-(grad_in * w_other0 * w_other1)
-						const float sx = (gi0 * wy[by]) * wz[bz], sy = (gi1 * wx[bx]) * wz[bz], sz = (gi2 * wx[bx]) * wy[by];
-						const float w2 = (bx ? sx : -sx) + (by ? sy : -sy) + (bz ? sz : -sz);
-						const float a0 = d0 * w1 + e0 * w2, a1 = d1 * w1 + e1 * w2;
-						atomicAdd(reinterpret_cast<float2*>(gl + lg.idx[c]), make_float2(a0, a1));
+						if (!(dbg & 1)) atomicAdd(reinterpret_cast<float2*>(gl + lg.idx[c]), make_float2(a0[c], a1[c]));
 					}
 				}
 			}
@@ -414,8 +446,10 @@ int launch_network_fwdbwd(cudaStream_t stream, const GridMeta& gm, const ParamLa
 	uint32_t grid = (uint32_t)num_sms();
 	const uint32_t need = (n_tiles + WARPS_BWD - 1) / WARPS_BWD;
 	if (need < grid) grid = need;
+	static int dbg = -1;
+	if (dbg < 0) { const char* e = getenv("NEUS2_DBG"); dbg = e ? atoi(e) : 0; }
 	k_network_fwdbwd<<<grid, WARPS_BWD * 32, BWD_SMEM, stream>>>(gm, pl, params, coords, dL_dout, n_in_ptr, n_rows, sdf_bias,
-		(float)indeed_batch_size, grads, var_acc, w1row0_acc, so);
+		(float)indeed_batch_size, grads, var_acc, w1row0_acc, so, dbg);
 	COUNT_LAUNCH(1);
 	CUDA_CHECK(cudaGetLastError());
 	return 0;

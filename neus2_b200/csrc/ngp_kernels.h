@@ -15,7 +15,8 @@ struct LossParamsDev {
 int launch_generate_training_samples(cudaStream_t stream, uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, uint32_t n_rays_total, const uint64_t rng_state[2], const DatasetDev& ds,
                                      const Aabb& bb, const GlobalMove& gmv, const uint8_t* bitfield, int snap, float cone_angle, uint32_t max_samples,
                                      uint32_t* numsteps_all, uint32_t* base, uint32_t* slot, uint32_t* ray_indices, float* rays, uint32_t* numsteps,
-                                     float* coords, uint32_t* counters);
+                                     float* coords, uint32_t* counters, void* windows, uint32_t* n_windows, float* ray_setup);
+size_t sampling_window_bytes_per_ray();
 
 // counters: [0] = kept rays (device, from sample generation), out_counter = total compacted samples (un-clamped)
 int launch_compute_loss(cudaStream_t stream, uint32_t n_rays_local, uint32_t n_rays /* global: image mapping + normalisers */, uint32_t n_rays_total, const uint64_t rng_state[2], const DatasetDev& ds, const Aabb& bb,

@@ -41,13 +41,15 @@ __device__ __forceinline__ RaySetup setup_ray(uint32_t i, uint32_t n_rays, uint3
 // replays the reference's control flow over the window with ballots.  The visited set, hence every per-ray sample
 // count and every emitted coordinate, is bit-identical to the serial loop; the dependent global load per step
 // (the reason the serial version is latency-bound) is gone.
-template <bool EMIT>
+#define MAX_WINDOWS 72   // a ray crosses the unit cube in <= 1024 chain positions; every window but the last consumes >= 32
+struct WindowRec { float t_start; uint32_t mask; };
+
 __device__ __forceinline__ uint32_t march_ray_warp(const Aabb& bb, const float ray_o[3], const float dir[3], float startt, float cone_angle,
-                                                   const uint8_t* __restrict__ bitfield, uint32_t limit, float* __restrict__ coords, int lane) {
+                                                   const uint8_t* __restrict__ bitfield, uint32_t limit, WindowRec* __restrict__ windows,
+                                                   uint32_t* __restrict__ n_windows_out, int lane) {
 	const float idir[3] = {1.0f / dir[0], 1.0f / dir[1], 1.0f / dir[2]};
-	const float wdir[3] = {(dir[0] + 1.0f) * 0.5f, (dir[1] + 1.0f) * 0.5f, (dir[2] + 1.0f) * 0.5f};
-	const float diag[3] = {bb.mx[0] - bb.mn[0], bb.mx[1] - bb.mn[1], bb.mx[2] - bb.mn[2]};
 	uint32_t j = 0;
+	uint32_t n_win = 0;
 	float t_start = startt;
 	bool done = false;
 	while (!done) {
@@ -92,28 +94,36 @@ __device__ __forceinline__ uint32_t march_ray_warp(const Aabb& bb, const float r
 				}
 			}
 		}
-		if (EMIT && my_j >= 0) {
-			float* c = coords + (size_t)my_j * 7;
-			#pragma unroll
-			for (int k = 0; k < 3; ++k) c[k] = (pos[k] - bb.mn[k]) / diag[k];
-			c[3] = warp_dt(dt);
-			c[4] = wdir[0]; c[5] = wdir[1]; c[6] = wdir[2];
+		// remember which chain positions of this window became samples: the emit pass replays (t_start, mask) only
+		const uint32_t emit_mask = __ballot_sync(0xffffffffu, my_j >= 0);
+		if (emit_mask) {
+			if (lane == 0 && n_win < MAX_WINDOWS) { windows[n_win].t_start = t_start; windows[n_win].mask = emit_mask; }
+			++n_win;
 		}
 		t_start = t_next;
 	}
-	return j;
+	if (lane == 0) *n_windows_out = min(n_win, (uint32_t)MAX_WINDOWS);
+	return n_win > MAX_WINDOWS ? 0u : j;   // (cannot happen for rays through the unit cube; such a ray would be dropped)
 }
 
 __global__ void __launch_bounds__(128)
 k_rays_count(uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, uint32_t n_rays_total, Pcg32 rng, DatasetDev ds, Aabb bb, GlobalMove gmv,
-             const uint8_t* __restrict__ bitfield, int snap, float cone_angle, uint32_t* __restrict__ numsteps_all) {
+             const uint8_t* __restrict__ bitfield, int snap, float cone_angle, uint32_t* __restrict__ numsteps_all,
+             WindowRec* __restrict__ windows, uint32_t* __restrict__ n_windows, float* __restrict__ ray_setup) {
 	const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	const int lane = threadIdx.x & 31;
 	if (i >= n_rays) return;
 	RaySetup r = setup_ray(i + ray_offset, n_rays_global, n_rays_total, rng, ds, bb, gmv, snap != 0, cone_angle);
 	uint32_t j = 0;
-	if (!r.skip) j = march_ray_warp<false>(bb, r.ray_o, r.dir, r.startt, cone_angle, bitfield, NERF_STEPS, nullptr, lane);
-	if (lane == 0) numsteps_all[i] = j;
+	if (!r.skip) j = march_ray_warp(bb, r.ray_o, r.dir, r.startt, cone_angle, bitfield, NERF_STEPS, windows + (size_t)i * MAX_WINDOWS, n_windows + i, lane);
+	if (lane == 0) {
+		numsteps_all[i] = j;
+		if (j) {   // what the emit pass needs: unnormalised ray (o, d) + moved origin / direction
+			float* rs = ray_setup + (size_t)i * 12;
+			#pragma unroll
+			for (int k = 0; k < 3; ++k) { rs[k] = r.o[k]; rs[3 + k] = r.d[k]; rs[6 + k] = r.ray_o[k]; rs[9 + k] = r.dir[k]; }
+		}
+	}
 }
 
 // Single-CTA two-stage exclusive scan over <= 2^20 elements (n_rays <= 2^18 in practice):
@@ -170,42 +180,70 @@ k_scan_rays(uint32_t n, const uint32_t* __restrict__ counts, uint32_t max_sample
 	}
 }
 
+// Emit pass: replays the recorded windows (start of the window on the t-chain + bitmask of the positions that became
+// samples); no occupancy lookups, no control flow.  Positions are recomputed with the same arithmetic as the count pass.
 __global__ void __launch_bounds__(128)
-k_rays_emit(uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, uint32_t n_rays_total, Pcg32 rng, DatasetDev ds, Aabb bb, GlobalMove gmv,
-            const uint8_t* __restrict__ bitfield, int snap, float cone_angle, const uint32_t* __restrict__ numsteps_all,
-            const uint32_t* __restrict__ base, const uint32_t* __restrict__ slot,
+k_rays_emit(uint32_t n_rays, uint32_t ray_offset, Aabb bb, float cone_angle, const uint32_t* __restrict__ numsteps_all,
+            const uint32_t* __restrict__ base, const uint32_t* __restrict__ slot, const WindowRec* __restrict__ windows,
+            const uint32_t* __restrict__ n_windows, const float* __restrict__ ray_setup,
             uint32_t* __restrict__ ray_indices, float* __restrict__ rays, uint32_t* __restrict__ numsteps, float* __restrict__ coords) {
 	const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	const int lane = threadIdx.x & 31;
 	if (i >= n_rays) return;
 	const uint32_t sl = slot[i];
 	if (sl == 0xffffffffu) return;
-	RaySetup r = setup_ray(i + ray_offset, n_rays_global, n_rays_total, rng, ds, bb, gmv, snap != 0, cone_angle);
-	const uint32_t j = numsteps_all[i], b = base[i];
+	const float* rs = ray_setup + (size_t)i * 12;
+	const uint32_t j_total = numsteps_all[i], b = base[i];
+	if (lane < 6) rays[(size_t)sl * 6 + lane] = rs[lane];
 	if (lane == 0) {
 		ray_indices[sl] = i + ray_offset;
-		#pragma unroll
-		for (int k = 0; k < 3; ++k) { rays[(size_t)sl * 6 + k] = r.o[k]; rays[(size_t)sl * 6 + 3 + k] = r.d[k]; }
-		numsteps[sl * 2 + 0] = j;
+		numsteps[sl * 2 + 0] = j_total;
 		numsteps[sl * 2 + 1] = b;
 	}
-	march_ray_warp<true>(bb, r.ray_o, r.dir, r.startt, cone_angle, bitfield, j, coords + (size_t)b * 7, lane);
+	const float ray_o[3] = {rs[6], rs[7], rs[8]}, dir[3] = {rs[9], rs[10], rs[11]};
+	const float wdir[3] = {(dir[0] + 1.0f) * 0.5f, (dir[1] + 1.0f) * 0.5f, (dir[2] + 1.0f) * 0.5f};
+	const float diag[3] = {bb.mx[0] - bb.mn[0], bb.mx[1] - bb.mn[1], bb.mx[2] - bb.mn[2]};
+	const WindowRec* w = windows + (size_t)i * MAX_WINDOWS;
+	const uint32_t nw = n_windows[i];
+	float* out = coords + (size_t)b * 7;
+	uint32_t j = 0;
+	for (uint32_t wi = 0; wi < nw; ++wi) {
+		const WindowRec rec = w[wi];
+		float tl = rec.t_start, t_mine = rec.t_start;
+		#pragma unroll
+		for (int L = 0; L < 32; ++L) {
+			if (lane == L) t_mine = tl;
+			tl += calc_dt(tl, cone_angle);
+		}
+		if ((rec.mask >> lane) & 1u) {
+			const uint32_t my_j = j + __popc(rec.mask & ((1u << lane) - 1u));
+			float* c = out + (size_t)my_j * 7;
+			#pragma unroll
+			for (int k = 0; k < 3; ++k) c[k] = (fmaf(t_mine, dir[k], ray_o[k]) - bb.mn[k]) / diag[k];
+			c[3] = warp_dt(calc_dt(t_mine, cone_angle));
+			c[4] = wdir[0]; c[5] = wdir[1]; c[6] = wdir[2];
+		}
+		j += __popc(rec.mask);
+	}
 }
+
+size_t sampling_window_bytes_per_ray() { return sizeof(WindowRec) * MAX_WINDOWS; }
 
 int launch_generate_training_samples(cudaStream_t stream, uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, uint32_t n_rays_total, const uint64_t rng_state[2], const DatasetDev& ds,
                                      const Aabb& bb, const GlobalMove& gmv, const uint8_t* bitfield, int snap, float cone_angle, uint32_t max_samples,
                                      uint32_t* numsteps_all, uint32_t* base, uint32_t* slot, uint32_t* ray_indices, float* rays, uint32_t* numsteps,
-                                     float* coords, uint32_t* counters) {
+                                     float* coords, uint32_t* counters, void* windows, uint32_t* n_windows, float* ray_setup) {
 	if (n_rays == 0) return 0;
 	Pcg32 rng; rng.state = rng_state[0]; rng.inc = rng_state[1];
 	const uint32_t blocks = (n_rays + 3) / 4;   // one warp per ray
-	k_rays_count<<<blocks, 128, 0, stream>>>(n_rays, ray_offset, n_rays_global, n_rays_total, rng, ds, bb, gmv, bitfield, snap, cone_angle, numsteps_all);
+	k_rays_count<<<blocks, 128, 0, stream>>>(n_rays, ray_offset, n_rays_global, n_rays_total, rng, ds, bb, gmv, bitfield, snap, cone_angle, numsteps_all,
+	                                        (WindowRec*)windows, n_windows, ray_setup);
 	COUNT_LAUNCH(1);
 	CUDA_CHECK(cudaGetLastError());
 	k_scan_rays<<<1, SCAN_THREADS, 0, stream>>>(n_rays, numsteps_all, max_samples, base, slot, counters);
 	COUNT_LAUNCH(1);
 	CUDA_CHECK(cudaGetLastError());
-	k_rays_emit<<<blocks, 128, 0, stream>>>(n_rays, ray_offset, n_rays_global, n_rays_total, rng, ds, bb, gmv, bitfield, snap, cone_angle, numsteps_all, base, slot,
+	k_rays_emit<<<blocks, 128, 0, stream>>>(n_rays, ray_offset, bb, cone_angle, numsteps_all, base, slot, (const WindowRec*)windows, n_windows, ray_setup,
 	                                       ray_indices, rays, numsteps, coords);
 	COUNT_LAUNCH(1);
 	CUDA_CHECK(cudaGetLastError());
