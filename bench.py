@@ -238,14 +238,10 @@ def main():
     grads = ctx.buffers()[3]
     stream = torch.cuda.current_stream()
 
+    from neus2_b200 import parallel
+
     def step():
-        if world == 1:
-            return ctx.train_step()
-        ctx.train_step_begin(rank, world)
-        counts = torch.tensor(ctx.local_counts(), dtype=torch.int64, device=dev)
-        dist.all_reduce(grads)                 # NCCL over NVLink: 10.56 M fp32 gradients
-        dist.all_reduce(counts)
-        return ctx.train_step_end([int(x) for x in counts.tolist()])
+        return parallel.train_step(ctx, rank, world)   # world > 1: NCCL all-reduce of the 10.56 M fp32 gradients over NVLink
 
     for _ in range(args.preroll + args.warmup):
         st = step()

@@ -1,0 +1,104 @@
+"""world_size-2 gloo test of the data-parallel scheme (CPU): ray sharding by global index + all-reduce(sum) of gradients
+reproduces the single-rank result.  Compute is the CPU oracle (this is host-logic coverage; the GPU path is in bench.py)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import oracle as O
+from tests import util as U
+from neus2_b200 import parallel, synthetic
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _scene():
+    data = synthetic.render_sphere_views(n_views=3, width=48, height=40, seed=3)
+    grid = np.zeros(128 ** 3, dtype=np.float32)
+    idx = np.arange(128 ** 3, dtype=np.uint32)
+
+    def dec(x):
+        x = x & 0x49249249
+        x = (x | (x >> 2)) & 0xc30c30c3
+        x = (x | (x >> 4)) & 0x0f00f00f
+        x = (x | (x >> 8)) & 0xff0000ff
+        x = (x | (x >> 16)) & 0x0000ffff
+        return x
+    pts = (np.stack([dec(idx), dec(idx >> 1), dec(idx >> 2)], 1) + 0.5) / 128
+    grid[np.abs(synthetic.sphere_sdf(pts, data["spheres"])) < 0.02] = 1.0
+    bitfield, _ = O.update_bitfield(grid, 1)
+    return data, bitfield
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cfg = O.make_cfg(n_levels=4, base_resolution=8, log2_hashmap_size=12, per_level_scale=1.6)
+    lay = O.param_layout(cfg)
+    p = U.random_params(cfg, seed=5)
+    ph = U.to_half_bits(p)
+    data, bitfield = _scene()
+    ds = O.make_dataset(data["pixels"], data["focal"], data["principal"], data["xforms"])
+    R, B = 256, 1 << 14
+    rng = O.Pcg32(seed=1337)
+    # every rank can generate the whole batch (deterministic); it keeps only its shard of the GLOBAL ray indices
+    gen = O.generate_training_samples(R, 1 << 16, 0, rng, ds, bitfield)
+    lo, hi = parallel.shard_range(R, rank, world)
+    keep = [i for i in range(gen["n_kept"]) if lo <= gen["ray_indices"][i] < hi]
+    rows = np.concatenate([np.arange(gen["numsteps"][i][1], gen["numsteps"][i][1] + gen["numsteps"][i][0]) for i in keep]) if keep else np.zeros(0, int)
+    coords = np.ascontiguousarray(gen["coords"][rows])
+    rs = np.random.RandomState(0)
+    dL_all = np.zeros((gen["n_samples"], 16), dtype=np.float16)
+    dL_all[:, :11] = rs.normal(0, 1e-2, (gen["n_samples"], 11)).astype(np.float16)
+    dL = np.ascontiguousarray(dL_all[rows]).view(np.uint16)
+    g = O.net_backward(cfg, coords, ph, dL, B) if len(rows) else np.zeros(lay["total"], np.float32)
+    var_local = g[lay["variance"]]
+    t = torch.from_numpy(g.copy())
+    parallel.allreduce_sum_(t)
+    counts = torch.tensor([len(keep), len(rows)], dtype=torch.int64)
+    parallel.allreduce_sum_(counts)
+    if rank == 0:
+        np.savez(os.path.join(out_dir, "dp.npz"), grads=t.numpy(), counts=counts.numpy(), var_local=var_local)
+    dist.destroy_process_group()
+
+
+def test_dp2_gradients_equal_single_rank(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    got = np.load(tmp_path / "dp.npz")
+    # single rank reference
+    cfg = O.make_cfg(n_levels=4, base_resolution=8, log2_hashmap_size=12, per_level_scale=1.6)
+    lay = O.param_layout(cfg)
+    p = U.random_params(cfg, seed=5)
+    data, bitfield = _scene()
+    ds = O.make_dataset(data["pixels"], data["focal"], data["principal"], data["xforms"])
+    gen = O.generate_training_samples(256, 1 << 16, 0, O.Pcg32(seed=1337), ds, bitfield)
+    assert gen["n_kept"] > 10
+    rs = np.random.RandomState(0)
+    n = gen["n_samples"]
+    dL = np.zeros((n, 16), dtype=np.float16)
+    dL[:, :11] = rs.normal(0, 1e-2, (n, 11)).astype(np.float16)
+    ref = O.net_backward(cfg, np.ascontiguousarray(gen["coords"][:n]), U.to_half_bits(p), dL.view(np.uint16), 1 << 14)
+    assert list(got["counts"]) == [gen["n_kept"], n]                          # shards partition the rays exactly
+    v = lay["variance"]
+    a, b = got["grads"][:v], ref[:v]
+    assert np.linalg.norm(a - b) / np.linalg.norm(b) < 1e-5                   # linear in the batch: only fp32 summation order differs
+    assert abs(got["grads"][v] - ref[v]) <= 2e-3 * abs(ref[v]) + 1e-6         # per-rank half rounding of the variance gradient
+
+
+def test_shard_range_partitions():
+    for world in (1, 2, 4, 8):
+        R = 128 * world * 3
+        spans = [parallel.shard_range(R, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == R
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))

@@ -1,0 +1,131 @@
+"""CPU-only tests: published known-answer vectors, host-side logic, and the C-ABI surface (no compute calls)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_pcg32_published_known_answers():
+    # pcg32-demo of the PCG reference implementation (pcg-c-basic): seed(42, 54) -> first six outputs.
+    lib = O.lib()
+    st = np.zeros(2, dtype=np.uint64)
+    # Pcg32(initstate=42, initseq=54): orc_pcg32_seed uses initseq=1, so build the state by hand as pcg32.h:55-62 does
+    inc = np.uint64((54 << 1) | 1)
+    st[0], st[1] = 0, inc
+    lib.orc_pcg32_next_uint(st.ctypes.data_as(O.u64p))
+    st[0] = np.uint64((int(st[0]) + 42) & 0xFFFFFFFFFFFFFFFF)
+    lib.orc_pcg32_next_uint(st.ctypes.data_as(O.u64p))
+    got = [int(lib.orc_pcg32_next_uint(st.ctypes.data_as(O.u64p))) for _ in range(6)]
+    assert got == [0xa15c02b7, 0x7b47f409, 0xba1d3330, 0x83d2f293, 0xbfa4784b, 0xcbed606e]
+
+
+def test_pcg32_advance_equals_stepping():
+    a, b = O.Pcg32(seed=1337), O.Pcg32(seed=1337)
+    for _ in range(1000):
+        a.next_uint()
+    b.advance(1000)
+    assert a.next_uint() == b.next_uint()
+    f = O.Pcg32(seed=7).next_float()
+    assert 0.0 <= f < 1.0
+
+
+def test_morton_roundtrip_and_known_values():
+    lib = O.lib()
+    assert lib.orc_morton3D(1, 0, 0) == 1 and lib.orc_morton3D(0, 1, 0) == 2 and lib.orc_morton3D(0, 0, 1) == 4
+    assert lib.orc_morton3D(127, 127, 127) == 128 ** 3 - 1
+    for x, y, z in [(5, 77, 120), (127, 0, 64)]:
+        m = lib.orc_morton3D(x, y, z)
+        assert (lib.orc_morton3D_invert(m), lib.orc_morton3D_invert(m >> 1), lib.orc_morton3D_invert(m >> 2)) == (x, y, z)
+
+
+def test_grid_tables_base_json():
+    # SURVEY §8 table (float32 arithmetic of testbed.cu:2181 and grid.h:1472-1508)
+    cfg = O.make_cfg()
+    off, res, sc = O.cfg_tables(cfg)
+    assert list(res) == [16, 24, 34, 50, 72, 104, 151, 219, 317, 461, 669, 971, 1411, 2049]
+    assert list(sc) == [r - 1 for r in res]
+    assert list(np.diff(off)) == [4096, 13824, 39304, 125000, 373248] + [524288] * 9
+    lay = O.param_layout(cfg)
+    assert lay["total"] == 10559396 and lay["grid"] == 11264 and lay["sdf_in"] == 32
+
+
+def test_grid_index_dense_and_hash():
+    # dense: x + y*res + z*res^2 (mod size); hashed: x ^ y*2654435761 ^ z*805459861 (mod 2^19)   (grid.h:119-153)
+    assert O.grid_index(4096, 16, 3, 2, 1) == 2 * (3 + 2 * 16 + 1 * 256)
+    assert O.grid_index(4096, 16, 16, 15, 15) == 2 * ((16 + 15 * 16 + 15 * 256) % 4096)      # +1 corner wraps
+    x, y, z = 1000, 2000, 1234
+    h = (x ^ (y * 2654435761 & 0xFFFFFFFF) ^ (z * 805459861 & 0xFFFFFFFF)) % (1 << 19)
+    assert O.grid_index(1 << 19, 2049, x, y, z) == 2 * h
+
+
+def test_srgb_transfer_functions():
+    assert abs(O.lib().orc_srgb_to_linear(0.04045) - 0.04045 / 12.92) < 1e-9
+    assert abs(O.lib().orc_linear_to_srgb(1.0) - 1.0) < 1e-6
+    assert abs(O.lib().orc_srgb_to_linear(O.lib().orc_linear_to_srgb(0.5)) - 0.5) < 2e-4   # the reference's 0.41666 exponent is not exactly 1/2.4
+
+
+def test_fill_rollover_semantics():
+    # rows < n_in untouched; wrapped copies of dL are rescaled by n_in/n (tcnn common_device.h:515-534)
+    n, n_in = 16, 5
+    dl = np.arange(n * 16, dtype=np.float32).reshape(n, 16).astype(np.float16)
+    co = np.arange(n * 7, dtype=np.float32).reshape(n, 7)
+    d2, c2 = dl.view(np.uint16).copy(), co.copy()
+    O.fill_rollover(n, n_in, dl_h=d2, coords=c2)
+    d2 = d2.view(np.float16)
+    assert np.array_equal(d2[:n_in], dl[:n_in]) and np.array_equal(c2[:n_in], co[:n_in])
+    for i in range(n_in, n):
+        assert np.array_equal(c2[i], co[i % n_in])
+        assert np.array_equal(d2[i], (dl[i % n_in].astype(np.float32) * np.float32(n_in) / np.float32(n)).astype(np.float16))
+
+
+def test_bitfield_mips_are_max_pooled():
+    grid = np.zeros(128 ** 3, dtype=np.float32)
+    grid[O.lib().orc_morton3D(64, 64, 64)] = 1.0
+    bits, mean = O.update_bitfield(grid, 1)
+    assert abs(mean - 1.0 / 128 ** 3) < 1e-12
+    m = O.lib().orc_morton3D(64, 64, 64)
+    assert bits[m // 8] & (1 << (m % 8))
+    # mip 1 covers twice the extent: cell (64,64,64)/2 + 32 = (64,64,64)
+    m1 = O.lib().orc_morton3D(64, 64, 64)
+    assert bits[128 ** 3 // 8 + m1 // 8] & (1 << (m1 % 8))
+    assert np.unpackbits(bits[: 128 ** 3 // 8]).sum() == 1
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """The library must load without a GPU and export exactly what include/neus2_b200.h declares."""
+    hdr = open(os.path.join(ROOT, "include", "neus2_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(neus2_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 25
+    from neus2_b200 import _lib
+    lib = _lib.load()
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, missing
+    assert sorted(_lib.EXPORTS) == declared
+    # host-only entry points work without a device
+    cfg = _lib.Config()
+    lib.neus2_default_config(C.byref(cfg))
+    assert (cfg.n_levels, cfg.log2_hashmap_size, cfg.base_resolution, cfg.batch_size) == (14, 19, 16, 1 << 18)
+    assert abs(cfg.learning_rate - 1e-3) < 1e-9 and abs(cfg.epsilon - 1e-15) < 1e-20 and abs(cfg.ek_loss_weight - 0.01) < 1e-9
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under neus2_b200/ may reference it."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "neus2_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt.replace("oracle/neus_oracle.cpp", ""), f
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from neus2_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    import pytest
+    with pytest.raises(_lib.Neus2Error):
+        _lib.load()
