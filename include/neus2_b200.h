@@ -132,7 +132,7 @@ int neus2_train_step(neus2_ctx* ctx, void* stream, neus2_step_stats* stats);
 
 /* Test / integration access to the step's device buffers by name: "numsteps_all", "ray_indices", "rays", "numsteps",
  * "coords", "mlp_out", "coords_compacted", "dloss", "loss", "ek_loss", "mask_loss", "counters", "density_grid",
- * "bitfield", "density_grid_mean". */
+ * "bitfield", "density_grid_mean", "render_queue", "render_counters", "render_ray_rgba", "render_ray_depth", "render_ray_samples". */
 int neus2_debug_buffer(neus2_ctx* ctx, const char* name, void** ptr_dev, uint64_t* n_bytes);
 /* Testbed state the drivers read (python_api.cu:317-471): training_step, rays_per_batch, rng state. */
 int neus2_get_state(neus2_ctx* ctx, uint32_t* training_step, uint32_t* rays_per_batch, uint64_t rng_state[2]);
@@ -144,6 +144,43 @@ int neus2_set_profiling(neus2_ctx* ctx, int enable);
 int neus2_get_stage_times(neus2_ctx* ctx, float ms_sum[8], uint32_t count[8]);
 /* number of kernels this library launched on the context since creation (bench.py's gpu_launches) */
 uint64_t neus2_launch_count(const neus2_ctx* ctx);
+
+/* ---- inference rendering ------------------------------------------------------------------------------
+ * One call = one Testbed::render_frame (src/testbed.cu:2820-2990) in Nerf mode, ERenderMode::Shade, for one sample index of
+ * one image tile: NerfTracer::init_rays_from_camera + ::trace (src/testbed_nerf.cu:2397-2600), shade_kernel_nerf (:2148-2181),
+ * CudaRenderBuffer::accumulate / ::tonemap (src/render_buffer.cu:540-598).  Testbed::render_to_cpu (src/python_api.cu:123-170)
+ * is the loop `for s in range(spp): neus2_render(sample_index = s)`; sample 0 resets the accumulation. */
+typedef struct neus2_render_params {
+	int32_t width, height;           /* full image resolution */
+	float focal_length[2];           /* pixels: relative_focal_length * resolution[fov_axis] * zoom (testbed.cu:2738) */
+	float screen_center[2];          /* Testbed::render_screen_center (testbed.cu:2742); 0.5, 0.5 = centred */
+	float camera_matrix[12];         /* 3x4 row-major camera-to-world, ngp convention (m_smoothed_camera) */
+	uint32_t sample_index;           /* render_buffer.spp() */
+	int32_t snap_to_pixel_centers;   /* testbed.snap_to_pixel_centers */
+	float min_transmittance;         /* nerf.rendering_min_transmittance (0.01; the eval scripts set 1e-4) */
+	float background_color[4];       /* sRGB + alpha (testbed.h:842) */
+	float exposure;                  /* 0 */
+	int32_t to_srgb;                 /* render(linear=False) */
+	int32_t use_inference_params;    /* 1 = EMA weights, as the reference renders */
+	int32_t tile_x0, tile_y0, tile_w, tile_h;   /* 0, 0, width, height = whole image; tiles of one image are independent */
+} neus2_render_params;
+void neus2_default_render_params(neus2_render_params* p, int32_t width, int32_t height);
+/* rgba_out_dev: [tile_h][tile_w][4] float (the surface render_to_cpu copies out); depth_out_dev: [tile_h][tile_w] float or NULL. */
+int neus2_render(neus2_ctx* ctx, void* stream, const neus2_render_params* p, float* rgba_out_dev, float* depth_out_dev);
+/* after a render on `stream`: {rays that entered the occupancy grid, samples pushed through the network} (synchronises) */
+int neus2_render_stats(neus2_ctx* ctx, void* stream, uint32_t stats_host[2]);
+
+/* ---- SDF lattice + marching cubes ------------------------------------------------------------------------
+ * Testbed::get_density_on_grid (src/testbed_nerf.cu:4096-4143): SDF (inference params) at lattice points x in [0,res[0]),
+ * y in [0,res[1]), z in [z0,z1) of `aabb` (6 floats min,max; Testbed::marching_cubes rounds res up to multiples of 16 itself,
+ * :4176-4178).  out_dev[x + y*res0 + (z-z0)*res0*res1].  z-slabs are independent (one per GPU). */
+int neus2_sdf_lattice(neus2_ctx* ctx, void* stream, const uint32_t res[3], const float aabb[6], uint32_t z0, uint32_t z1, float* out_dev, int use_inference_params);
+/* marching_cubes_gpu (src/marching_cubes.cu:797-822) on a float lattice (inside = density > thresh).  Vertices are numbered in
+ * ascending (cell, axis) order and triangles in ascending cell order (the reference: atomicAdd arrival order).  Results stay
+ * in context-owned device buffers until the next call; synchronises `stream` once to size them, like the reference. */
+int neus2_marching_cubes(neus2_ctx* ctx, void* stream, const uint32_t res[3], const float aabb[6], float thresh, const float* density_dev,
+                         uint32_t* n_verts, uint32_t* n_indices);
+int neus2_mesh_buffers(neus2_ctx* ctx, float** verts_dev, uint32_t** indices_dev, uint32_t* n_verts, uint32_t* n_indices);
 
 #ifdef __cplusplus
 }

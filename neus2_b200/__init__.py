@@ -8,9 +8,9 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import Config, Neus2Error, StepStats, check, load, LIB_PATH  # noqa: F401
+from ._lib import Config, Neus2Error, RenderParams, StepStats, check, load, LIB_PATH  # noqa: F401
 
-__all__ = ["Config", "Context", "Neus2Error", "StepStats", "default_config"]
+__all__ = ["Config", "Context", "Neus2Error", "RenderParams", "StepStats", "default_config"]
 
 
 def default_config(**overrides):
@@ -213,3 +213,80 @@ class Context:
 
     def launch_count(self):
         return int(self._lib.neus2_launch_count(self._h))
+
+    # ---- inference rendering (Testbed::render_to_cpu, python_api.cu:123-170) -------------------------------------------
+    def render_params(self, width, height, camera_matrix=None, focal_length=None, screen_center=None, **kw):
+        """neus2_render_params with the reference's defaults (reset_camera, testbed.cu:272-287); keyword arguments set fields."""
+        p = RenderParams()
+        self._lib.neus2_default_render_params(C.byref(p), C.c_int32(width), C.c_int32(height))
+        if camera_matrix is not None:
+            p.camera_matrix[:] = [float(v) for v in np.asarray(camera_matrix, dtype=np.float32).reshape(-1)[:12]]
+        if focal_length is not None:
+            f = np.broadcast_to(np.asarray(focal_length, dtype=np.float32), (2,))
+            p.focal_length[:] = [float(f[0]), float(f[1])]
+        if screen_center is not None:
+            p.screen_center[:] = [float(screen_center[0]), float(screen_center[1])]
+        for k, v in kw.items():
+            if k == "background_color":
+                p.background_color[:] = [float(x) for x in v]
+            else:
+                setattr(p, k, v)
+        return p
+
+    def training_view_params(self, xform, focal, principal, train_res, width=None, height=None, zoom=1.0, **kw):
+        """Testbed::set_camera_to_training_view (testbed.cu:264-270) followed by calc_focal_length / render_screen_center
+        (testbed.cu:2738-2746): the view of training image (xform, focal [px], principal [relative], train_res) rendered at
+        width x height (default: the training resolution)."""
+        fov_axis = 1                                                             # m_fov_axis, testbed.h:500
+        width = int(train_res[0]) if width is None else int(width)
+        height = int(train_res[1]) if height is None else int(height)
+        rel_focal = np.asarray(focal, dtype=np.float32) / np.float32(train_res[fov_axis])
+        f = rel_focal * np.float32((width, height)[fov_axis]) * np.float32(zoom)
+        m_sc = np.float32(1.0) - np.asarray(principal, dtype=np.float32)          # m_screen_center
+        sc = (np.float32((np.float32(0.5) - m_sc[0]) * np.float32(zoom) + np.float32(0.5)),   # x in float, y in double (:2745)
+              np.float32((0.5 - float(m_sc[1])) * float(np.float32(zoom)) + 0.5))
+        return self.render_params(width, height, camera_matrix=xform, focal_length=f, screen_center=sc, **kw)
+
+    def render(self, params, spp=1, out=None, depth=None, stream=None):
+        """Renders params' tile for samples 0..spp-1 and returns the [tile_h, tile_w, 4] float32 device tensor."""
+        torch = _torch()
+        dev = f"cuda:{self.device}"
+        if out is None:
+            out = torch.empty((params.tile_h, params.tile_w, 4), dtype=torch.float32, device=dev)
+        for s in range(spp):
+            params.sample_index = s
+            check(self._lib.neus2_render(self._h, _stream(stream), C.byref(params), _ptr(out), _ptr(depth)))
+        return out
+
+    def render_stats(self, stream=None):
+        st = (C.c_uint32 * 2)()
+        check(self._lib.neus2_render_stats(self._h, _stream(stream), st))
+        return dict(rays_alive=int(st[0]), samples=int(st[1]))
+
+    # ---- SDF lattice + marching cubes (Testbed::marching_cubes, testbed_nerf.cu:4175-4226) ------------------------------
+    def sdf_lattice(self, res, aabb=(0, 0, 0, 1, 1, 1), z0=0, z1=None, use_inference_params=True, out=None, stream=None):
+        torch = _torch()
+        r = (C.c_uint32 * 3)(*[int(v) for v in res])
+        bb = (C.c_float * 6)(*[float(v) for v in aabb])
+        z1 = int(res[2]) if z1 is None else int(z1)
+        if out is None:
+            out = torch.empty((z1 - z0, int(res[1]), int(res[0])), dtype=torch.float32, device=f"cuda:{self.device}")
+        check(self._lib.neus2_sdf_lattice(self._h, _stream(stream), r, bb, C.c_uint32(z0), C.c_uint32(z1), _ptr(out), C.c_int(int(use_inference_params))))
+        return out
+
+    def marching_cubes(self, density, aabb=(0, 0, 0, 1, 1, 1), thresh=0.0, stream=None):
+        """density: float32 device tensor [rz, ry, rx].  Returns (verts [nv, 3] float32, faces [nt, 3] int64) device tensors."""
+        torch = _torch()
+        assert density.dtype == torch.float32 and density.is_contiguous() and density.dim() == 3
+        r = (C.c_uint32 * 3)(density.shape[2], density.shape[1], density.shape[0])
+        bb = (C.c_float * 6)(*[float(v) for v in aabb])
+        nv, ni = C.c_uint32(), C.c_uint32()
+        check(self._lib.neus2_marching_cubes(self._h, _stream(stream), r, bb, C.c_float(thresh), _ptr(density), C.byref(nv), C.byref(ni)))
+        pv, pi = C.c_void_p(), C.c_void_p()
+        check(self._lib.neus2_mesh_buffers(self._h, C.byref(pv), C.byref(pi), None, None))
+        dev = f"cuda:{self.device}"
+        if nv.value == 0 or ni.value == 0:
+            return torch.zeros((0, 3), dtype=torch.float32, device=dev), torch.zeros((0, 3), dtype=torch.int64, device=dev)
+        verts = torch.as_tensor(_DevArray(pv.value, (nv.value, 3), "<f4", self), device=dev).clone()
+        faces = torch.as_tensor(_DevArray(pi.value, (ni.value // 3, 3), "<i4", self), device=dev).to(torch.int64)
+        return verts, faces

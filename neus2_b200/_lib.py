@@ -38,12 +38,22 @@ class StepStats(C.Structure):
     ]
 
 
+class RenderParams(C.Structure):
+    _fields_ = [
+        ("width", C.c_int32), ("height", C.c_int32), ("focal_length", C.c_float * 2), ("screen_center", C.c_float * 2),
+        ("camera_matrix", C.c_float * 12), ("sample_index", C.c_uint32), ("snap_to_pixel_centers", C.c_int32),
+        ("min_transmittance", C.c_float), ("background_color", C.c_float * 4), ("exposure", C.c_float), ("to_srgb", C.c_int32),
+        ("use_inference_params", C.c_int32), ("tile_x0", C.c_int32), ("tile_y0", C.c_int32), ("tile_w", C.c_int32), ("tile_h", C.c_int32),
+    ]
+
+
 EXPORTS = [
     "neus2_last_error", "neus2_default_config", "neus2_ctx_create", "neus2_ctx_destroy", "neus2_n_params", "neus2_param_layout",
     "neus2_grid_tables", "neus2_buffers", "neus2_init_params", "neus2_set_params", "neus2_get_params", "neus2_set_training_step",
     "neus2_forward", "neus2_sdf", "neus2_backward", "neus2_optimizer_step", "neus2_set_dataset", "neus2_update_density_grid",
     "neus2_train_step_begin", "neus2_train_step_end", "neus2_local_counts", "neus2_train_step", "neus2_debug_buffer",
     "neus2_get_state", "neus2_set_state", "neus2_set_bitfield", "neus2_launch_count", "neus2_set_profiling", "neus2_get_stage_times",
+    "neus2_default_render_params", "neus2_render", "neus2_render_stats", "neus2_sdf_lattice", "neus2_marching_cubes", "neus2_mesh_buffers",
 ]
 
 _lib = None

@@ -75,6 +75,13 @@ struct neus2_ctx {
 	uint32_t stage_count[NEUS2_N_STAGES];
 	bool stage_pending[NEUS2_N_STAGES];
 	float* h_scalars;           // pinned
+	// inference render scratch (sized on first use / growth, then reused)
+	size_t render_cap;          // tile pixels
+	void* r_queue; uint32_t* r_counters; float *r_ray_rgba, *r_ray_depth, *r_accumulate; uint32_t* r_ray_samples;
+	// marching cubes
+	size_t mc_cells_cap, mc_blocks_cap, mc_verts_cap, mc_indices_cap;
+	uint32_t *mc_block_counts, *mc_counts, *mc_vert_prefix, *mc_indices; float* mc_verts;
+	uint32_t mc_n_verts, mc_n_indices;
 };
 
 static void stage_begin(neus2_ctx* ctx, int st, cudaStream_t s);
@@ -96,6 +103,16 @@ static void stage_collect(neus2_ctx* ctx) {   // call after the stream has been 
 		if (cudaEventElapsedTime(&ms, ctx->ev[2 * st], ctx->ev[2 * st + 1]) == cudaSuccess) { ctx->stage_ms_sum[st] += ms; ctx->stage_count[st]++; }
 		ctx->stage_pending[st] = false;
 	}
+}
+
+template <typename T> static int regrow(T** p, size_t* cap, size_t need) {
+	if (need <= *cap && *p) return 0;
+	if (*p) cudaFree(*p);
+	*p = nullptr; *cap = 0;
+	if (need == 0) need = 1;
+	CUDA_CHECK(cudaMalloc((void**)p, need * sizeof(T)));
+	*cap = need;
+	return 0;
 }
 
 extern "C" {
@@ -219,6 +236,9 @@ void neus2_ctx_destroy(neus2_ctx* ctx) {
 		ctx->so.CIN, ctx->so.dSO, ctx->so.H0, ctx->so.dH0, ctx->so.X0, ctx->so.dI, ctx->partials, ctx->var_acc, ctx->w1row0_acc, ctx->scalar_tmp,
 		ctx->density_grid, ctx->density_grid_tmp, ctx->grid_positions, ctx->grid_indices, ctx->grid_density, ctx->bitfield, ctx->density_grid_mean};
 	for (void* p : ptrs) if (p) cudaFree(p);
+	void* more[] = {ctx->r_queue, ctx->r_counters, ctx->r_ray_rgba, ctx->r_ray_depth, ctx->r_accumulate, ctx->r_ray_samples,
+		ctx->mc_block_counts, ctx->mc_counts, ctx->mc_vert_prefix, ctx->mc_indices, ctx->mc_verts};
+	for (void* p : more) if (p) cudaFree(p);
 	if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
 	if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
 	delete ctx;
@@ -549,8 +569,10 @@ int neus2_debug_buffer(neus2_ctx* ctx, const char* name, void** ptr, uint64_t* n
 		{"density_grid", ctx->density_grid, G3n * ctx->n_cascades * 4}, {"bitfield", ctx->bitfield, G3n / 8 * NERF_CASCADES}, {"density_grid_mean", ctx->density_grid_mean, 4},
 		{"grid_positions", ctx->grid_positions, G3n * ctx->n_cascades * 12}, {"grid_indices", ctx->grid_indices, G3n * ctx->n_cascades * 4},
 		{"grid_density", ctx->grid_density, G3n * ctx->n_cascades * 2},
+		{"render_queue", ctx->r_queue, ctx->render_cap * 32}, {"render_counters", ctx->r_counters, 16}, {"render_ray_rgba", ctx->r_ray_rgba, ctx->render_cap * 16},
+		{"render_ray_depth", ctx->r_ray_depth, ctx->render_cap * 4}, {"render_ray_samples", ctx->r_ray_samples, ctx->render_cap * 4},
 	};
-	for (const E& e : table) if (!strcmp(e.n, name)) { *ptr = e.p; if (n_bytes) *n_bytes = e.b; return 0; }
+	for (const E& e : table) if (!strcmp(e.n, name)) { if (!e.p) FAIL("buffer not allocated yet"); *ptr = e.p; if (n_bytes) *n_bytes = e.b; return 0; }
 	FAIL("unknown buffer name");
 }
 
@@ -587,5 +609,109 @@ int neus2_get_stage_times(neus2_ctx* ctx, float ms_sum[8], uint32_t count[8]) {
 }
 
 uint64_t neus2_launch_count(const neus2_ctx* ctx) { (void)ctx; return g_neus_launches; }
+
+// ---- inference render ---------------------------------------------------------------------------------------------------
+void neus2_default_render_params(neus2_render_params* p, int32_t width, int32_t height) {
+	memset(p, 0, sizeof(*p));
+	p->width = width; p->height = height;
+	// reset_camera (src/testbed.cu:272-287): fov_axis 1, fov 50.625 deg, camera at 0.5 - 1.5 * view_dir
+	const float rel_focal = 1.0f / (2.0f * std::tan(50.625f * 0.5f * 3.14159265358979323846f / 180.0f));   // set_fov / fov_to_focal_length
+	p->focal_length[0] = p->focal_length[1] = rel_focal * (float)height;
+	p->screen_center[0] = p->screen_center[1] = 0.5f;
+	const float cam[12] = {1.f, 0.f, 0.f, 0.5f, 0.f, -1.f, 0.f, 0.5f, 0.f, 0.f, -1.f, 0.5f + 1.5f};
+	memcpy(p->camera_matrix, cam, sizeof(cam));
+	p->sample_index = 0; p->snap_to_pixel_centers = 1; p->min_transmittance = 0.01f;
+	p->background_color[3] = 1.f; p->exposure = 0.f; p->to_srgb = 1; p->use_inference_params = 1;
+	p->tile_x0 = 0; p->tile_y0 = 0; p->tile_w = width; p->tile_h = height;
+}
+
+static int render_reserve(neus2_ctx* ctx, size_t n) {
+	if (n <= ctx->render_cap) return 0;
+	void* old[] = {ctx->r_queue, ctx->r_counters, ctx->r_ray_rgba, ctx->r_ray_depth, ctx->r_accumulate, ctx->r_ray_samples};
+	for (void* p : old) if (p) cudaFree(p);
+	ctx->r_queue = nullptr; ctx->r_counters = nullptr; ctx->r_ray_rgba = ctx->r_ray_depth = ctx->r_accumulate = nullptr; ctx->r_ray_samples = nullptr;
+	ctx->render_cap = 0;
+	CHECK(dmalloc(&ctx->r_queue, 32 * n));
+	DMALLOC(ctx->r_counters, 4); DMALLOC(ctx->r_ray_rgba, 4 * n); DMALLOC(ctx->r_ray_depth, n); DMALLOC(ctx->r_accumulate, 4 * n); DMALLOC(ctx->r_ray_samples, n);
+	ctx->render_cap = n;
+	return 0;
+}
+
+int neus2_render(neus2_ctx* ctx, void* stream_, const neus2_render_params* p, float* rgba_out, float* depth_out) {
+	cudaStream_t stream = (cudaStream_t)stream_;
+	CUDA_CHECK(cudaSetDevice(ctx->device));
+	if (!p || !rgba_out) FAIL("null argument");
+	if (p->width <= 0 || p->height <= 0 || p->tile_w < 0 || p->tile_h < 0 || p->tile_x0 < 0 || p->tile_y0 < 0 ||
+	    p->tile_x0 + p->tile_w > p->width || p->tile_y0 + p->tile_h > p->height) FAIL("render tile outside the image");
+	if (!(p->focal_length[0] > 0.f) || !(p->focal_length[1] > 0.f)) FAIL("focal length must be positive");
+	const size_t n = (size_t)p->tile_w * p->tile_h;
+	if (n == 0) return 0;
+	if (n > 0xffffffffull) FAIL("tile too large");
+	CHECK(render_reserve(ctx, n));
+	RenderLaunch r;
+	r.width = p->width; r.height = p->height;
+	r.focal[0] = p->focal_length[0]; r.focal[1] = p->focal_length[1];
+	r.screen_center[0] = p->screen_center[0]; r.screen_center[1] = p->screen_center[1];
+	memcpy(r.camera, p->camera_matrix, sizeof(r.camera));
+	r.sample_index = p->sample_index; r.snap_to_pixel_centers = p->snap_to_pixel_centers; r.min_transmittance = p->min_transmittance;
+	memcpy(r.background_color, p->background_color, sizeof(r.background_color));
+	r.exposure = p->exposure; r.to_srgb = p->to_srgb;
+	r.tile_x0 = p->tile_x0; r.tile_y0 = p->tile_y0; r.tile_w = p->tile_w; r.tile_h = p->tile_h;
+	const neus2_config& c = ctx->cfg;
+	const float cos_anneal_ratio = c.anneal_end == 0 ? 1.0f : (float)std::min(1.0, (double)((float)ctx->training_step / c.anneal_end));
+	// m_render_aabb == m_aabb unless the user crops (testbed_nerf.cu:3077)
+	return launch_render(stream, ctx->gm, ctx->pl, p->use_inference_params ? ctx->ema : ctx->params, c.sdf_bias, r, ctx->aabb, ctx->aabb, ctx->gmv, ctx->bitfield,
+	                     ctx->cone_angle_constant, cos_anneal_ratio, ctx->r_queue, ctx->r_counters, ctx->r_ray_rgba, ctx->r_ray_depth, ctx->r_ray_samples,
+	                     ctx->r_accumulate, rgba_out, depth_out);
+}
+
+int neus2_render_stats(neus2_ctx* ctx, void* stream_, uint32_t stats[2]) {
+	cudaStream_t stream = (cudaStream_t)stream_;
+	if (!ctx->r_counters) FAIL("no render has run on this context");
+	CUDA_CHECK(cudaMemcpyAsync(ctx->h_counters + 4, ctx->r_counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+	CUDA_CHECK(cudaStreamSynchronize(stream));
+	stats[0] = ctx->h_counters[4]; stats[1] = ctx->h_counters[6];
+	return 0;
+}
+
+// ---- SDF lattice + marching cubes -----------------------------------------------------------------------------------------
+int neus2_sdf_lattice(neus2_ctx* ctx, void* stream, const uint32_t res[3], const float aabb[6], uint32_t z0, uint32_t z1, float* out, int use_inference_params) {
+	CUDA_CHECK(cudaSetDevice(ctx->device));
+	if (!res || !aabb || !out) FAIL("null argument");
+	if (!res[0] || !res[1] || !res[2] || z0 > z1 || z1 > res[2]) FAIL("bad lattice extent");
+	Aabb bb; for (int k = 0; k < 3; ++k) { bb.mn[k] = aabb[k]; bb.mx[k] = aabb[3 + k]; }
+	return launch_sdf_lattice((cudaStream_t)stream, ctx->gm, ctx->pl, use_inference_params ? ctx->ema : ctx->params, ctx->cfg.sdf_bias, res, bb, ctx->aabb, z0, z1, out);
+}
+
+int neus2_marching_cubes(neus2_ctx* ctx, void* stream_, const uint32_t res[3], const float aabb[6], float thresh, const float* density, uint32_t* n_verts, uint32_t* n_indices) {
+	cudaStream_t stream = (cudaStream_t)stream_;
+	CUDA_CHECK(cudaSetDevice(ctx->device));
+	if (!res || !aabb || !density) FAIL("null argument");
+	const uint64_t cells = (uint64_t)res[0] * res[1] * res[2];
+	if (cells == 0 || cells > (1ull << 32)) FAIL("lattice must have between 1 and 2^32 points");
+	const uint32_t nb = marching_cubes_blocks(res);
+	CHECK(regrow(&ctx->mc_block_counts, &ctx->mc_blocks_cap, (size_t)nb * 2));
+	if (!ctx->mc_counts) DMALLOC(ctx->mc_counts, 4);
+	CHECK(launch_marching_cubes_count(stream, res, thresh, density, ctx->mc_block_counts, ctx->mc_counts));
+	CUDA_CHECK(cudaMemcpyAsync(ctx->h_counters + 4, ctx->mc_counts, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+	CUDA_CHECK(cudaStreamSynchronize(stream));   // marching_cubes_gpu sizes its outputs the same way (marching_cubes.cu:812-818)
+	ctx->mc_n_verts = ctx->h_counters[4]; ctx->mc_n_indices = ctx->h_counters[5];
+	CHECK(regrow(&ctx->mc_vert_prefix, &ctx->mc_cells_cap, (size_t)cells));
+	CHECK(regrow(&ctx->mc_verts, &ctx->mc_verts_cap, (size_t)ctx->mc_n_verts * 3));
+	CHECK(regrow(&ctx->mc_indices, &ctx->mc_indices_cap, (size_t)ctx->mc_n_indices));
+	Aabb bb; for (int k = 0; k < 3; ++k) { bb.mn[k] = aabb[k]; bb.mx[k] = aabb[3 + k]; }
+	CHECK(launch_marching_cubes_emit(stream, res, bb, thresh, density, ctx->mc_block_counts, ctx->mc_n_verts, ctx->mc_n_indices, ctx->mc_vert_prefix, ctx->mc_verts, ctx->mc_indices));
+	if (n_verts) *n_verts = ctx->mc_n_verts;
+	if (n_indices) *n_indices = ctx->mc_n_indices;
+	return 0;
+}
+
+int neus2_mesh_buffers(neus2_ctx* ctx, float** verts, uint32_t** indices, uint32_t* n_verts, uint32_t* n_indices) {
+	if (verts) *verts = ctx->mc_verts;
+	if (indices) *indices = ctx->mc_indices;
+	if (n_verts) *n_verts = ctx->mc_n_verts;
+	if (n_indices) *n_indices = ctx->mc_n_indices;
+	return 0;
+}
 
 }  // extern "C"

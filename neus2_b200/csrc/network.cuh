@@ -438,3 +438,33 @@ __device__ __forceinline__ void forward_tile(const GridMeta& gm, const __half* _
 		st.soa[0] = soa[0]; st.soa[1] = soa[1]; st.soa[2] = soa[2]; st.soa[3] = soa[3];
 	}
 }
+
+// SDF-MLP only (NerfNetwork::sdf / ::density, nerf_network.h:656-739): positions in the slab's COORD rows -> raw sdf-MLP
+// output 0 of the 16 samples in the slab's SDF row (half).  Needs W0 and W1 staged in `sw`.
+__device__ __forceinline__ void sdf_tile(const GridMeta& gm, const __half* __restrict__ grid, const __half* sw, unsigned char* slab, int lane) {
+	const int g = lane >> 2, t = lane & 3;
+	float* sCoord = reinterpret_cast<float*>(slab + WarpSlab::COORD);
+	__half* sX0 = reinterpret_cast<__half*>(slab + WarpSlab::X0);
+	__half* sSDF = reinterpret_cast<__half*>(slab + WarpSlab::SDF);
+	if (lane < 16) {
+		#pragma unroll
+		for (int d = 0; d < 3; ++d) sX0[lane * LD_X0 + d] = __hsub(__float2half_rn(sCoord[lane * 7 + d]), __float2half_rn(0.5f));
+		for (int k = 3 + 2 * (int)gm.n_levels; k < SDF_IN; ++k) sX0[lane * LD_X0 + k] = __float2half(0.f);
+	}
+	gather_tile<false>(gm, grid, sCoord, sX0, nullptr, lane);
+	__syncwarp();
+	uint32_t xa[2][4], h0a[4][4];
+	load_a_frag(xa[0], sX0, LD_X0, 0, g, t);
+	load_a_frag(xa[1], sX0, LD_X0, 16, g, t);
+	{
+		float c[8][4];
+		mma_layer<2, 8>(xa, sw + WeightSmem::W0, LD_X0, c, g, t);
+		pack_frags<8, true>(c, h0a);
+	}
+	{
+		float c[1][4];   // only output n-tile 0 is needed (sdf = output 0)
+		mma_layer<4, 1>(h0a, sw + WeightSmem::W1, LD_H, c, g, t);
+		if (t == 0) { sSDF[g] = __float2half_rn(c[0][0]); sSDF[g + 8] = __float2half_rn(c[0][2]); }
+	}
+	__syncwarp();
+}

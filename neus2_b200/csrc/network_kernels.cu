@@ -70,10 +70,8 @@ k_network_sdf(GridMeta gm, ParamLayout pl, const __half* __restrict__ params, co
 	stage_matrix(sw + WeightSmem::W1, LD_H, params + pl.off_w1, 16, 64, threadIdx.x, blockDim.x);
 	__syncthreads();
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int g = lane >> 2, t = lane & 3;
 	unsigned char* slab = smem + WeightSmem::FWD_END * 2 + warp * WarpSlab::FWD_END;
 	float* sCoord = reinterpret_cast<float*>(slab + WarpSlab::COORD);
-	__half* sX0 = reinterpret_cast<__half*>(slab + WarpSlab::X0);
 	__half* sSDF = reinterpret_cast<__half*>(slab + WarpSlab::SDF);
 	const uint32_t n_tiles = (n + TILE - 1) / TILE;
 	const __half variance = params[pl.off_var];
@@ -84,27 +82,7 @@ k_network_sdf(GridMeta gm, ParamLayout pl, const __half* __restrict__ params, co
 			sCoord[(i / 3) * 7 + (i % 3)] = r < n ? pos[(size_t)r * stride + (i % 3)] : 0.f;
 		}
 		__syncwarp();
-		if (lane < 16) {
-			#pragma unroll
-			for (int d = 0; d < 3; ++d) sX0[lane * LD_X0 + d] = __hsub(__float2half_rn(sCoord[lane * 7 + d]), __float2half_rn(0.5f));
-			for (int k = 3 + 2 * (int)gm.n_levels; k < SDF_IN; ++k) sX0[lane * LD_X0 + k] = __float2half(0.f);
-		}
-		gather_tile<false>(gm, params + pl.off_grid, sCoord, sX0, nullptr, lane);
-		__syncwarp();
-		uint32_t xa[2][4], h0a[4][4];
-		load_a_frag(xa[0], sX0, LD_X0, 0, g, t);
-		load_a_frag(xa[1], sX0, LD_X0, 16, g, t);
-		{
-			float c[8][4];
-			mma_layer<2, 8>(xa, sw + WeightSmem::W0, LD_X0, c, g, t);
-			pack_frags<8, true>(c, h0a);
-		}
-		{
-			float c[1][4];   // only output n-tile 0 is needed (sdf = output 0)
-			mma_layer<4, 1>(h0a, sw + WeightSmem::W1, LD_H, c, g, t);
-			if (t == 0) { sSDF[g] = __float2half_rn(c[0][0]); sSDF[g + 8] = __float2half_rn(c[0][2]); }
-		}
-		__syncwarp();
+		sdf_tile(gm, params + pl.off_grid, sw, slab, lane);
 		if (lane < 16 && row0 + lane < n) {
 			__half sdf = __hadd(sSDF[lane], __float2half_rn(sdf_bias));
 			__half r = sdf;

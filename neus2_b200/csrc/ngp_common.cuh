@@ -211,4 +211,40 @@ __device__ __forceinline__ uint32_t march_ray(const Aabb& bb, const float ray_o[
 	}
 	return j;
 }
+
+// ---- NeuS per-sample evaluation shared by the training loss (loss.cu) and the inference render (render.cu) ----
+// testbed_nerf.cu:1575-1625 (training) == :1003-1037 (composite_kernel_nerf): rgb = logistic, inv_s = exp(10*var) with the
+// product taken in half, alpha from the logistic CDF of the sdf half a step before / after the sample.
+__device__ __forceinline__ float logistic_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float relu_f(float v) { return v > 0.0f ? v : 0.0f; }
+
+struct SampleEval { float alpha, p_div_c, true_cos, iter_cos, inv_s, sdf, next_sdf, dt; float rgb[3]; float g[3]; };
+
+__device__ __forceinline__ SampleEval eval_sample(const __half* __restrict__ o_ptr, const float* __restrict__ coord, const float dir[3], float cos_anneal_ratio) {
+	// one 32-byte row of network output
+	uint4 lo = reinterpret_cast<const uint4*>(o_ptr)[0], hi = reinterpret_cast<const uint4*>(o_ptr)[1];
+	const __half* o = reinterpret_cast<const __half*>(&lo);
+	const __half* o2 = reinterpret_cast<const __half*>(&hi);
+	(void)o2;
+	SampleEval e;
+	#pragma unroll
+	for (int k = 0; k < 3; ++k) e.rgb[k] = logistic_f(__half2float(o[k]));
+	e.dt = unwarp_dt(coord[3]);
+	e.inv_s = expf(__half2float(__hmul(__float2half_rn(10.0f), o[7])));     // :1590
+	e.sdf = __half2float(o[3]);
+	#pragma unroll
+	for (int k = 0; k < 3; ++k) e.g[k] = __half2float(o[4 + k]);
+	e.true_cos = (dir[0] * e.g[0] + dir[1] * e.g[1] + dir[2] * e.g[2]);
+	e.iter_cos = (float)-(relu_f((float)(-e.true_cos * 0.5 + 0.5)) * (1.0 - cos_anneal_ratio) + relu_f(-e.true_cos) * cos_anneal_ratio);
+	e.next_sdf = (float)(e.sdf + e.iter_cos * e.dt * 0.5);
+	const float prev_sdf = (float)(e.sdf - e.iter_cos * e.dt * 0.5);
+	const float next_cdf = logistic_f(e.next_sdf * e.inv_s);
+	const float prev_cdf = logistic_f(prev_sdf * e.inv_s);
+	const float p = prev_cdf - next_cdf;
+	const float c = prev_cdf;
+	e.p_div_c = (p + 1e-5f) / (c + 1e-5f);
+	e.alpha = clampf(e.p_div_c, 0.0f, 1.0f);
+	return e;
+}
+
 #endif

@@ -34,3 +34,33 @@ int launch_density_grid_splat_decay(cudaStream_t stream, uint32_t n_samples, con
                                     float decay, float* grid_tmp, float* grid);
 int launch_density_grid_bitfield(cudaStream_t stream, const float* grid, uint32_t n_cascades_used, float* mean_tmp, uint8_t* bitfield);
 int launch_reduce_sum(cudaStream_t stream, const float* in, uint32_t n, float* out /* zeroed by the launcher */);
+
+// ---- inference render (render.cu) ----
+struct RenderLaunch {
+	int32_t width, height;
+	float focal[2], screen_center[2];
+	float camera[12];
+	uint32_t sample_index;
+	int32_t snap_to_pixel_centers;
+	float min_transmittance;
+	float background_color[4];
+	float exposure;
+	int32_t to_srgb;
+	int32_t tile_x0, tile_y0, tile_w, tile_h;
+};
+// queue: 32 B per tile pixel; counters: 4 x u32; ray_rgba / accumulate / out: float4 per tile pixel; ray_depth, depth_out (nullable): float;
+// ray_samples (nullable): u32 per tile pixel = samples composited along the ray.
+int launch_render(cudaStream_t stream, const GridMeta& gm, const ParamLayout& pl, const __half* params, float sdf_bias, const RenderLaunch& r,
+                  const Aabb& render_aabb, const Aabb& train_aabb, const GlobalMove& gmv, const uint8_t* bitfield, float cone_angle, float cos_anneal_ratio,
+                  void* queue, uint32_t* counters, float* ray_rgba, float* ray_depth, uint32_t* ray_samples, float* accumulate, float* out, float* depth_out);
+
+// ---- SDF lattice + marching cubes (mesh.cu) ----
+// SDF (with bias, half -> float) at lattice points x in [0,res0), y in [0,res1), z in [z0,z1): out[x + y*res0 + (z-z0)*res0*res1].
+int launch_sdf_lattice(cudaStream_t stream, const GridMeta& gm, const ParamLayout& pl, const __half* params, float sdf_bias, const uint32_t res[3],
+                       const Aabb& render_aabb, const Aabb& train_aabb, uint32_t z0, uint32_t z1, float* out);
+// Deterministic marching cubes.  Pass 1 (count): fills block_counts (2 x n_blocks u32) and counts_dev[0..1] = {vertices, indices}.
+// Pass 2 (emit): needs vert_prefix (u32 per cell), verts (3 floats per vertex) and indices.
+uint32_t marching_cubes_blocks(const uint32_t res[3]);
+int launch_marching_cubes_count(cudaStream_t stream, const uint32_t res[3], float thresh, const float* density, uint32_t* block_counts, uint32_t* counts_dev);
+int launch_marching_cubes_emit(cudaStream_t stream, const uint32_t res[3], const Aabb& aabb, float thresh, const float* density, const uint32_t* block_offsets,
+                               uint32_t n_verts, uint32_t n_indices, uint32_t* vert_prefix, float* verts, uint32_t* indices);

@@ -30,7 +30,7 @@ __device__ __forceinline__ RaySetup setup_ray(uint32_t i, uint32_t n_rays, uint3
 	global_move(gmv, r.ray_o, r.dir);
 	float tmin, tmax; ray_intersect(bb, r.ray_o, r.dir, &tmin, &tmax);
 	tmin = fmaxf(tmin, 0.0f);                                                       // :1395
-	r.startt = tmin + calc_dt(tmin, cone_angle) * rng.next_float();                 // :1397-1398
+	r.startt = fmaf(calc_dt(tmin, cone_angle), rng.next_float(), tmin);               // :1397-1398 (nvcc contracts `t += dt * u` into one FFMA)
 	return r;
 }
 

@@ -1037,7 +1037,7 @@ void orc_generate_training_samples(uint32_t n_rays, const float* aabb /*min3,max
 		float cone_angle = cone_angle_constant;
 		tmin = fmaxf(tmin, 0.0f);
 		float startt = tmin;
-		startt += calc_dt(startt, cone_angle) * rng.next_float();
+		startt = fmaf(calc_dt(startt, cone_angle), rng.next_float(), startt);   // `t += dt * u`: one FFMA under nvcc's default -fmad=true
 		uint32_t j = march_ray(bmin, bmax, ray_o, dir, startt, cone_angle, bitfield, NERF_STEPS, nullptr);
 		if (j == 0) continue;
 		numsteps_all[i] = j;
@@ -1336,5 +1336,7 @@ float orc_update_bitfield(const float* grid, uint32_t n_cascades_used, uint8_t* 
 	}
 	return mean;
 }
+
+#include "render_mc_oracle.inc"
 
 }  // extern "C"

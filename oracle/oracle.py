@@ -383,3 +383,113 @@ def update_bitfield(grid, n_cascades_used=1):
     bitfield = np.zeros(128 * 128 * 128 // 8 * 8, dtype=np.uint8)
     mean = lib().orc_update_bitfield(_p(grid, f32p), C.c_uint32(n_cascades_used), _p(bitfield, u8p))
     return bitfield, float(mean)
+
+
+# ---------------------------------------------------------------------------
+# inference render (a11) and marching cubes (a12)
+# ---------------------------------------------------------------------------
+class RenderCam(C.Structure):
+    _fields_ = [
+        ("width", C.c_int32),
+        ("height", C.c_int32),
+        ("focal", C.c_float * 2),
+        ("screen_center", C.c_float * 2),
+        ("camera", C.c_float * 12),
+        ("sample_index", C.c_uint32),
+        ("snap_to_pixel_centers", C.c_int32),
+        ("min_transmittance", C.c_float),
+        ("cone_angle_constant", C.c_float),
+        ("cos_anneal_ratio", C.c_float),
+    ]
+
+
+def make_render_cam(width, height, focal, screen_center, camera, sample_index=0, snap=True, min_transmittance=0.01,
+                    cone_angle=0.0, cos_anneal_ratio=1.0):
+    c = RenderCam()
+    c.width, c.height = width, height
+    c.focal[:] = [float(focal[0]), float(focal[1])]
+    c.screen_center[:] = [float(screen_center[0]), float(screen_center[1])]
+    c.camera[:] = [float(v) for v in np.asarray(camera, dtype=np.float32).reshape(-1)]
+    c.sample_index = sample_index
+    c.snap_to_pixel_centers = 1 if snap else 0
+    c.min_transmittance = min_transmittance
+    c.cone_angle_constant = cone_angle
+    c.cos_anneal_ratio = cos_anneal_ratio
+    return c
+
+
+def ld_random_val(index, seed):
+    lib().orc_ld_random_val.restype = C.c_float
+    return float(lib().orc_ld_random_val(C.c_uint32(index), C.c_uint32(seed)))
+
+
+def sobol(index, dim):
+    lib().orc_sobol.restype = C.c_uint32
+    return int(lib().orc_sobol(C.c_uint32(index), C.c_uint32(dim)))
+
+
+def ld_random_pixel_offset(spp):
+    out = np.zeros(2, dtype=np.float32)
+    lib().orc_ld_random_pixel_offset(C.c_uint32(spp), _p(out, f32p))
+    return out
+
+
+def render_init_rays(cam, bitfield, render_aabb=UNIT_AABB, rotation=IDENTITY_ROT_H, transition=ZERO_TRANS_H, first_frame_offset=None):
+    ffo = np.zeros(3, dtype=np.float32) if first_frame_offset is None else first_frame_offset
+    payload = np.zeros((cam.width * cam.height, 8), dtype=np.float32)
+    lib().orc_render_init_rays(C.byref(cam), _p(render_aabb, f32p), _p(rotation, h16p), _p(transition, h16p), _p(ffo, f32p),
+                               _p(bitfield, u8p), _p(payload, f32p))
+    return payload
+
+
+def render_trace(cfg, params_h, cam, bitfield, payload, render_aabb=UNIT_AABB, train_aabb=UNIT_AABB):
+    n = cam.width * cam.height
+    rgba = np.zeros((n, 4), dtype=np.float32)
+    depth = np.zeros(n, dtype=np.float32)
+    n_samples = np.zeros(n, dtype=np.uint32)
+    lib().orc_render_trace(C.byref(cfg), _p(params_h, h16p), C.byref(cam), _p(render_aabb, f32p), _p(train_aabb, f32p),
+                           _p(bitfield, u8p), _p(payload, f32p), _p(rgba, f32p), _p(depth, f32p), _p(n_samples, u32p))
+    return rgba, depth, n_samples
+
+
+def render_shade_accumulate_tonemap(rgba, depth, accumulate, sample_count, background_color, exposure=0.0, to_srgb=True):
+    n = rgba.shape[0]
+    out = np.zeros((n, 4), dtype=np.float32)
+    depth_out = np.zeros(n, dtype=np.float32)
+    bg = np.asarray(background_color, dtype=np.float32)
+    lib().orc_render_shade_accumulate_tonemap(C.c_uint32(n), _p(rgba, f32p), _p(depth, f32p), C.c_float(sample_count), _p(accumulate, f32p),
+                                              _p(bg, f32p), C.c_float(exposure), C.c_int(1 if to_srgb else 0), _p(out, f32p), _p(depth_out, f32p))
+    return out, depth_out
+
+
+def render(cfg, params_h, cam, bitfield, background_color=(0, 0, 0, 1), to_srgb=True, spp=1, **kw):
+    """Testbed::render_to_cpu (python_api.cu:123-170) for spp samples; returns [h, w, 4] float32."""
+    acc = np.zeros((cam.width * cam.height, 4), dtype=np.float32)
+    out = None
+    for s in range(spp):
+        cam.sample_index = s
+        payload = render_init_rays(cam, bitfield, **kw)
+        rgba, depth, _ = render_trace(cfg, params_h, cam, bitfield, payload)
+        out, _ = render_shade_accumulate_tonemap(rgba, depth, acc, float(s), background_color, 0.0, to_srgb)
+    return out.reshape(cam.height, cam.width, 4)
+
+
+def sdf_on_lattice(cfg, params_h, res, render_aabb=UNIT_AABB, train_aabb=UNIT_AABB, z0=0, z1=None):
+    res = np.asarray(res, dtype=np.uint32)
+    z1 = int(res[2]) if z1 is None else z1
+    out = np.zeros((z1 - z0, int(res[1]), int(res[0])), dtype=np.float32)
+    lib().orc_sdf_on_lattice(C.byref(cfg), _p(params_h, h16p), _p(res, u32p), _p(render_aabb, f32p), _p(train_aabb, f32p),
+                             C.c_uint32(z0), C.c_uint32(z1), _p(out, f32p))
+    return out
+
+
+def marching_cubes(density, aabb=UNIT_AABB, thresh=0.0):
+    """density: float32 [rz, ry, rx].  Returns (verts [nv,3] float32, indices [nt,3] uint32), deterministic numbering."""
+    res = np.array([density.shape[2], density.shape[1], density.shape[0]], dtype=np.uint32)
+    counts = np.zeros(2, dtype=np.uint32)
+    density = np.ascontiguousarray(density, dtype=np.float32)
+    lib().orc_marching_cubes(_p(res, u32p), _p(aabb, f32p), C.c_float(thresh), _p(density, f32p), _p(counts, u32p), None, None)
+    verts = np.zeros((int(counts[0]), 3), dtype=np.float32)
+    idx = np.zeros(int(counts[1]), dtype=np.uint32)
+    lib().orc_marching_cubes(_p(res, u32p), _p(aabb, f32p), C.c_float(thresh), _p(density, f32p), _p(counts, u32p), _p(verts, f32p), _p(idx, u32p))
+    return verts, idx.reshape(-1, 3)
