@@ -34,12 +34,12 @@ def camera_ring(n_views, radius=1.3, center=(0.5, 0.5, 0.5), elevation_deg=(15.0
 
 
 def render_sphere_views(n_views=16, width=256, height=256, focal=None, sphere_radius=0.25, center=(0.5, 0.5, 0.5),
-                        cam_radius=1.3, seed=0, second_sphere=True, principal=(0.5, 0.5)):
+                        cam_radius=1.3, seed=0, second_sphere=True, principal=(0.5, 0.5), elevation_deg=(15.0, 50.0)):
     """Returns dict(pixels uint8 [n,h,w,4], focal [n,2], principal [n,2], xforms [n,3,4])."""
     if focal is None:
         focal = 1.1 * width * cam_radius / (4 * sphere_radius) / 1.3
     fx, fy = (focal, focal) if np.isscalar(focal) else focal
-    xforms = camera_ring(n_views, radius=cam_radius, center=center, seed=seed)
+    xforms = camera_ring(n_views, radius=cam_radius, center=center, elevation_deg=elevation_deg, seed=seed)
     cx, cy = principal
     ys, xs = np.meshgrid((np.arange(height) + 0.5) / height, (np.arange(width) + 0.5) / width, indexing="ij")
     d_cam = np.stack([(xs - cx) * width / fx, (ys - cy) * height / fy, np.ones_like(xs)], axis=-1)

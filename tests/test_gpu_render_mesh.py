@@ -179,7 +179,7 @@ def test_marching_cubes_bit_exact_on_network_sdf(scene, res):
     dens = dens.contiguous()
     v, f = ctx.marching_cubes(dens, thresh=0.0)
     vr, fr = O.marching_cubes(dens.cpu().numpy(), thresh=0.0)
-    assert len(vr) > 100
+    assert len(vr) > 20
     assert v.shape == vr.shape and f.shape == fr.shape
     assert np.array_equal(v.cpu().numpy().view(np.uint32), vr.view(np.uint32))
     assert np.array_equal(f.cpu().numpy(), fr.astype(np.int64))
