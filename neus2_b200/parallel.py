@@ -34,3 +34,78 @@ def train_step(ctx, rank=0, world_size=1, group=None):
     allreduce_sum_(grads, group)      # 10,559,396 fp32 gradients over NVLink
     allreduce_sum_(counts, group)     # {rays kept, samples, compacted samples}: drives the shared rays_per_batch update
     return ctx.train_step_end([int(x) for x in counts.tolist()])
+
+
+# ---- inference: independent units, no data-path collective ---------------------------------------------------
+def split_rows(n_rows, rank, world_size):
+    """Rows [begin, end) of rank `rank` when n_rows image rows (or lattice z-layers) are dealt out in contiguous bands
+    whose sizes differ by at most one (the first n_rows % world_size ranks take the extra row)."""
+    base, extra = divmod(int(n_rows), int(world_size))
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def _gather_bands(local, n_rows, rank, world_size, group=None):
+    """All ranks contribute their band ([rows_r, ...], rows as in split_rows); every rank gets the stacked whole.
+    Bands are padded to the largest band so that one all_gather moves everything (results only: no collective sits on the
+    per-sample data path)."""
+    import torch
+    import torch.distributed as dist
+    if world_size == 1:
+        return local
+    max_rows = split_rows(n_rows, 0, world_size)[1]
+    pad = torch.zeros((max_rows,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    parts = [torch.empty_like(pad) for _ in range(world_size)]
+    dist.all_gather(parts, pad, group=group)
+    out = []
+    for r in range(world_size):
+        b, e = split_rows(n_rows, r, world_size)
+        out.append(parts[r][: e - b])
+    return torch.cat(out, dim=0)
+
+
+def interleaved_rows(n_rows, rank, world_size, chunk=16):
+    """Row chunks [(y0, y1), ...] of rank `rank`: the image is cut into chunks of `chunk` rows that are dealt round-robin, so
+    that every GPU gets a similar share of the rows that actually hit the object (contiguous bands would give the GPUs
+    holding the image centre most of the work)."""
+    return [(y, min(y + chunk, n_rows)) for i, y in enumerate(range(0, int(n_rows), chunk)) if i % world_size == rank]
+
+
+def render(ctx, params, spp=1, rank=0, world_size=1, group=None, chunk=16):
+    """Testbed::render_to_cpu with the image rows dealt across GPUs (tiles of a frame are independent: every pixel's ray,
+    Sobol jitter and colour depend only on its own index).  Returns the whole [H, W, 4] image on every rank."""
+    import torch
+    import torch.distributed as dist
+    if world_size == 1:
+        params.tile_x0, params.tile_y0, params.tile_w, params.tile_h = 0, 0, params.width, params.height
+        return ctx.render(params, spp=spp)
+    mine = []
+    for (y0, y1) in interleaved_rows(params.height, rank, world_size, chunk):
+        params.tile_x0, params.tile_w, params.tile_y0, params.tile_h = 0, params.width, y0, y1 - y0
+        mine.append(ctx.render(params, spp=spp).clone())
+    rows_max = max(sum(y1 - y0 for y0, y1 in interleaved_rows(params.height, r, world_size, chunk)) for r in range(world_size))
+    ref = mine[0] if mine else None
+    if ref is None:
+        raise ValueError("more ranks than row chunks: lower `chunk`")
+    pad = torch.zeros((rows_max, params.width, 4), dtype=ref.dtype, device=ref.device)
+    if mine:
+        local = torch.cat(mine, dim=0)
+        pad[: local.shape[0]] = local
+    parts = [torch.empty_like(pad) for _ in range(world_size)]
+    dist.all_gather(parts, pad, group=group)
+    out = torch.empty((params.height, params.width, 4), dtype=ref.dtype, device=ref.device)
+    for r in range(world_size):
+        off = 0
+        for (y0, y1) in interleaved_rows(params.height, r, world_size, chunk):
+            out[y0:y1] = parts[r][off:off + (y1 - y0)]
+            off += y1 - y0
+    return out
+
+
+def sdf_lattice(ctx, res, aabb=(0, 0, 0, 1, 1, 1), rank=0, world_size=1, group=None, use_inference_params=True):
+    """Testbed::get_density_on_grid with the lattice split into z-slabs, one per GPU; every rank gets the whole lattice
+    ([rz, ry, rx] float32), so marching cubes (milliseconds) can run anywhere without a seam."""
+    z0, z1 = split_rows(res[2], rank, world_size)
+    slab = ctx.sdf_lattice(res, aabb, z0=z0, z1=z1, use_inference_params=use_inference_params)
+    return _gather_bands(slab, res[2], rank, world_size, group)

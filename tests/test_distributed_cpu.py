@@ -102,3 +102,64 @@ def test_shard_range_partitions():
         spans = [parallel.shard_range(R, r, world) for r in range(world)]
         assert spans[0][0] == 0 and spans[-1][1] == R
         assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+
+
+def test_interleaved_rows_cover_everything_once():
+    for n in (5, 16, 1080):
+        for world in (1, 2, 4, 8):
+            rows = sorted(sum((list(range(a, b)) for r in range(world) for a, b in parallel.interleaved_rows(n, r, world, 4)), []))
+            assert rows == list(range(n))
+
+
+def test_split_rows_covers_everything_once():
+    for n in (1, 7, 16, 1080, 513):
+        for world in (1, 2, 3, 4, 8):
+            spans = [parallel.split_rows(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [e - b for b, e in spans]
+            assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+
+
+class _FakeCtx:
+    """Stands in for neus2_b200.Context on CPU: 'renders' a tile / 'evaluates' a slab as a pure function of the global
+    pixel / lattice index, which is the property the real kernels have (tests/test_gpu_render_mesh.py proves it on the GPU)."""
+
+    def render(self, p, spp=1):
+        ys = torch.arange(p.tile_y0, p.tile_y0 + p.tile_h, dtype=torch.float32)[:, None, None]
+        xs = torch.arange(p.tile_x0, p.tile_x0 + p.tile_w, dtype=torch.float32)[None, :, None]
+        return (ys * 1000 + xs + torch.arange(4, dtype=torch.float32)[None, None, :] * 0.25) * spp
+
+    def sdf_lattice(self, res, aabb, z0=0, z1=None, use_inference_params=True):
+        z = torch.arange(z0, z1, dtype=torch.float32)[:, None, None]
+        y = torch.arange(res[1], dtype=torch.float32)[None, :, None]
+        x = torch.arange(res[0], dtype=torch.float32)[None, None, :]
+        return z * 10000 + y * 100 + x
+
+
+class _P:
+    width, height = 13, 11
+    tile_x0 = tile_y0 = tile_w = tile_h = 0
+
+
+def _infer_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ctx = _FakeCtx()
+    img = parallel.render(ctx, _P(), spp=2, rank=rank, world_size=world, chunk=2)
+    lat = parallel.sdf_lattice(ctx, (5, 4, 7), rank=rank, world_size=world)
+    torch.save(dict(img=img, lat=lat), os.path.join(out_dir, f"r{rank}.pt"))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_render_bands_and_lattice_slabs_reassemble(tmp_path, world):
+    port = _free_port()
+    mp.spawn(_infer_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    p = _P()
+    p.tile_w, p.tile_h = p.width, p.height
+    whole_img = _FakeCtx().render(p, spp=2)
+    whole_lat = _FakeCtx().sdf_lattice((5, 4, 7), None, 0, 7)
+    for r in range(world):
+        got = torch.load(tmp_path / f"r{r}.pt")
+        assert torch.equal(got["img"], whole_img) and torch.equal(got["lat"], whole_lat)
