@@ -124,9 +124,12 @@ int neus2_update_density_grid(neus2_ctx* ctx, void* stream);
  *   end:   optimizer step, counters read-back, rays_per_batch adaptation, rng advance.
  * world_size = 1: ray_offset = 0, n_local = 0 (= all rays), n_rows_local = 0 (= batch_size). */
 int neus2_train_step_begin(neus2_ctx* ctx, void* stream, uint32_t rank, uint32_t world_size);
-/* counts_global: {kept rays, N_u, compacted} summed over ranks (NULL = use the local counts). */
+/* counts_global: {kept rays, N_u, compacted} summed over ranks, or NULL = take them from the device buffer returned by
+ * neus2_counts_device (begin() leaves this rank's counts there; a data-parallel caller all-reduces the 4 x uint32 in place,
+ * stream-ordered, between begin and end -- no host round trip; with world_size 1 they are simply the local counts). */
 int neus2_train_step_end(neus2_ctx* ctx, void* stream, const uint32_t* counts_global_host, neus2_step_stats* stats);
 int neus2_local_counts(neus2_ctx* ctx, void* stream, uint32_t counts_host[3]);
+int neus2_counts_device(neus2_ctx* ctx, uint32_t** counts_dev);
 /* convenience: begin + end on one GPU */
 int neus2_train_step(neus2_ctx* ctx, void* stream, neus2_step_stats* stats);
 

@@ -65,6 +65,7 @@ class Context:
 
     def close(self):
         if getattr(self, "_h", None):
+            self._buffers = self._counts = None
             self._lib.neus2_ctx_destroy(self._h)
             self._h = None
 
@@ -85,13 +86,16 @@ class Context:
 
     def buffers(self):
         """(master fp32, params fp16, ema fp16, grads fp32) as zero-copy torch views of the context's device buffers."""
+        if getattr(self, "_buffers", None) is not None:
+            return self._buffers
         torch = _torch()
         m, p, e, g = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
         check(self._lib.neus2_buffers(self._h, C.byref(m), C.byref(p), C.byref(e), C.byref(g)))
         dev = f"cuda:{self.device}"
         n = self.n_params
-        return (torch.as_tensor(_DevArray(m.value, (n,), "<f4", self), device=dev), torch.as_tensor(_DevArray(p.value, (n,), "<f2", self), device=dev),
-                torch.as_tensor(_DevArray(e.value, (n,), "<f2", self), device=dev), torch.as_tensor(_DevArray(g.value, (n,), "<f4", self), device=dev))
+        self._buffers = (torch.as_tensor(_DevArray(m.value, (n,), "<f4", None), device=dev), torch.as_tensor(_DevArray(p.value, (n,), "<f2", None), device=dev),
+                         torch.as_tensor(_DevArray(e.value, (n,), "<f2", None), device=dev), torch.as_tensor(_DevArray(g.value, (n,), "<f4", None), device=dev))
+        return self._buffers
 
     def debug_buffer(self, name, typestr, shape):
         torch = _torch()
@@ -172,6 +176,14 @@ class Context:
         c = (C.c_uint32 * 3)()
         check(self._lib.neus2_local_counts(self._h, _stream(stream), c))
         return [int(x) for x in c]
+
+    def counts_device(self):
+        """int32[4] device view of {kept rays, samples, compacted samples, 0} of the step in flight (all-reduce it in place)."""
+        if getattr(self, "_counts", None) is None:
+            p = C.c_void_p()
+            check(self._lib.neus2_counts_device(self._h, C.byref(p)))
+            self._counts = _torch().as_tensor(_DevArray(p.value, (4,), "<i4", None), device=f"cuda:{self.device}")
+        return self._counts
 
     def train_step_end(self, counts_global=None, stream=None):
         st = StepStats()

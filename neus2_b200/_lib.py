@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libneus2_b200.so")
+LIB_PATH = os.environ.get("NEUS2_B200_LIB") or os.path.join(_HERE, "libneus2_b200.so")   # the override selects an experimental build of the SAME library
 
 
 class Neus2Error(RuntimeError):
@@ -53,7 +53,7 @@ EXPORTS = [
     "neus2_forward", "neus2_sdf", "neus2_backward", "neus2_optimizer_step", "neus2_set_dataset", "neus2_update_density_grid",
     "neus2_train_step_begin", "neus2_train_step_end", "neus2_local_counts", "neus2_train_step", "neus2_debug_buffer",
     "neus2_get_state", "neus2_set_state", "neus2_set_bitfield", "neus2_launch_count", "neus2_set_profiling", "neus2_get_stage_times",
-    "neus2_default_render_params", "neus2_render", "neus2_render_stats", "neus2_sdf_lattice", "neus2_marching_cubes", "neus2_mesh_buffers",
+    "neus2_default_render_params", "neus2_render", "neus2_render_stats", "neus2_sdf_lattice", "neus2_marching_cubes", "neus2_mesh_buffers", "neus2_counts_device",
 ]
 
 _lib = None

@@ -52,6 +52,7 @@ struct neus2_ctx {
 
 	// training scratch
 	uint32_t *numsteps_all, *base, *slot, *ray_indices, *numsteps, *scan_tmp, *counters, *n_windows;
+	uint32_t* counts_global;    // {kept rays, N_u, compacted, 0}: copy of counters[0..2] after the backward pass; a data-parallel caller all-reduces it in place
 	unsigned char* windows; float* ray_setup;
 	float *rays, *coords, *ray_tmp, *coords_compacted, *loss, *ek_loss, *mask_loss;
 	__half *mlp_out, *dloss;
@@ -202,7 +203,7 @@ int neus2_ctx_create(const neus2_config* cfg, int device, neus2_ctx** out) {
 	CDM(ctx->master, N); CDM(ctx->params, N); CDM(ctx->ema, N); CDM(ctx->grads, N); CDM(ctx->m1, N); CDM(ctx->m2, N); CDM(ctx->steps, N);
 	CDM(ctx->numsteps_all, R); CDM(ctx->base, R); CDM(ctx->slot, R); CDM(ctx->ray_indices, R); CDM(ctx->numsteps, 2 * (size_t)R); CDM(ctx->scan_tmp, 2 * (size_t)R);
 	CDM(ctx->n_windows, R); CDM(ctx->windows, sampling_window_bytes_per_ray() * (size_t)R); CDM(ctx->ray_setup, 12 * (size_t)R);
-	CDM(ctx->counters, 8); CDM(ctx->rays, 6 * (size_t)R); CDM(ctx->coords, 7 * (size_t)S); CDM(ctx->ray_tmp, 12 * (size_t)R);
+	CDM(ctx->counters, 8); CDM(ctx->counts_global, 4); CDM(ctx->rays, 6 * (size_t)R); CDM(ctx->coords, 7 * (size_t)S); CDM(ctx->ray_tmp, 12 * (size_t)R);
 	CDM(ctx->coords_compacted, 7 * (size_t)B); CDM(ctx->loss, R); CDM(ctx->ek_loss, R); CDM(ctx->mask_loss, R);
 	CDM(ctx->mlp_out, 16 * (size_t)S); CDM(ctx->dloss, 16 * (size_t)B);
 	CDM(ctx->so.dOUT, 16 * (size_t)B); CDM(ctx->so.H2, 64 * (size_t)B); CDM(ctx->so.dH2, 64 * (size_t)B); CDM(ctx->so.H1, 64 * (size_t)B); CDM(ctx->so.dH1, 64 * (size_t)B);
@@ -232,7 +233,7 @@ void neus2_ctx_destroy(neus2_ctx* ctx) {
 	if (!ctx) return;
 	void* ptrs[] = {ctx->master, ctx->params, ctx->ema, ctx->grads, ctx->m1, ctx->m2, ctx->steps, ctx->d_pixels, ctx->d_focal, ctx->d_principal, ctx->d_xforms,
 		ctx->numsteps_all, ctx->base, ctx->slot, ctx->ray_indices, ctx->numsteps, ctx->scan_tmp, ctx->counters, ctx->n_windows, ctx->windows, ctx->ray_setup, ctx->rays, ctx->coords, ctx->ray_tmp,
-		ctx->coords_compacted, ctx->loss, ctx->ek_loss, ctx->mask_loss, ctx->mlp_out, ctx->dloss, ctx->so.dOUT, ctx->so.H2, ctx->so.dH2, ctx->so.H1, ctx->so.dH1,
+		ctx->coords_compacted, ctx->loss, ctx->ek_loss, ctx->mask_loss, ctx->mlp_out, ctx->dloss, ctx->counts_global, ctx->so.dOUT, ctx->so.H2, ctx->so.dH2, ctx->so.H1, ctx->so.dH1,
 		ctx->so.CIN, ctx->so.dSO, ctx->so.H0, ctx->so.dH0, ctx->so.X0, ctx->so.dI, ctx->partials, ctx->var_acc, ctx->w1row0_acc, ctx->scalar_tmp,
 		ctx->density_grid, ctx->density_grid_tmp, ctx->grid_positions, ctx->grid_indices, ctx->grid_density, ctx->bitfield, ctx->density_grid_mean};
 	for (void* p : ptrs) if (p) cudaFree(p);
@@ -493,6 +494,13 @@ int neus2_train_step_begin(neus2_ctx* ctx, void* stream_, uint32_t rank, uint32_
 	                          ctx->mask_loss, ctx->counters + 2));
 	stage_end(ctx, ST_LOSS, stream);
 	CHECK(neus2_backward(ctx, stream_, ctx->coords_compacted, ctx->dloss, ctx->counters + 2, rows_local, ctx->B));   // :3941-3946
+	CUDA_CHECK(cudaMemcpyAsync(ctx->counts_global, ctx->counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
+	return 0;
+}
+
+int neus2_counts_device(neus2_ctx* ctx, uint32_t** counts_dev) {
+	if (!counts_dev) FAIL("null argument");
+	*counts_dev = ctx->counts_global;
 	return 0;
 }
 
@@ -517,18 +525,22 @@ int neus2_train_step_end(neus2_ctx* ctx, void* stream_, const uint32_t* counts_g
 		CUDA_CHECK(cudaMemcpyAsync(ctx->h_scalars, ctx->scalar_tmp, 3 * sizeof(float), cudaMemcpyDeviceToHost, stream));
 	}
 	stage_end(ctx, ST_STEP, stream);
-	uint32_t counts[3];
-	CHECK(neus2_local_counts(ctx, stream_, counts));   // the one structurally required host sync per step (:3412-3416)
+	// the one structurally required host sync per step (:3412-3416): local counters + the (possibly all-reduced) global ones
+	CUDA_CHECK(cudaMemcpyAsync(ctx->h_counters, ctx->counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+	CUDA_CHECK(cudaMemcpyAsync(ctx->h_counters + 4, ctx->counts_global, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+	CUDA_CHECK(cudaStreamSynchronize(stream));
 	stage_collect(ctx);
-	const uint32_t n_kept_local = counts[0];
+	const uint32_t n_kept_local = ctx->h_counters[0];
+	uint32_t counts[3] = {ctx->h_counters[4], ctx->h_counters[5], ctx->h_counters[6]};
 	if (counts_global) { counts[0] = counts_global[0]; counts[1] = counts_global[1]; counts[2] = counts_global[2]; }
+	const bool have_global = counts_global != nullptr || ctx->cfg.world_size > 1;
 	++ctx->training_step;
 	ctx->rng.advance();                                                                  // :3996
 	neus2_step_stats s;
 	memset(&s, 0, sizeof(s));
 	s.training_step = ctx->training_step;
 	s.rays_per_batch = ctx->step_rays;
-	s.n_rays_kept = counts_global ? counts[0] : n_kept_local;
+	s.n_rays_kept = have_global ? counts[0] : n_kept_local;
 	s.density_grid_updated = ctx->step_density_updated;
 	// Counters::update_after_training (:3412-3438)
 	if (counts[1] == 0 || counts[2] == 0) {

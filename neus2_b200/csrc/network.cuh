@@ -219,60 +219,82 @@ __device__ __forceinline__ void level_geom(const GridMeta& gm, int l, float x, f
 // Gather for one 16-sample tile.  lane -> (sample lane&15, level parity lane>>4).
 // Writes: X0[s][3+2l..] = encoding (half, accumulated in half in corner order, grid.h:316-318),
 //         DY[s][ (2l+f)*3 + d ] = d enc / d x (fp32, grid.h:329-367)  when WANT_DY.
-template <bool WANT_DY>
+// The lane's levels are processed GATHER_BATCH at a time: all 8*GATHER_BATCH corner loads are issued before the first one
+// is consumed, so a warp keeps 4x more L2 requests in flight than a level-by-level loop (the gather is latency bound).
+#ifndef GATHER_BATCH_FWD
+#define GATHER_BATCH_FWD 2      // inference kernels: registers are free during the gather
+#endif
+#ifndef GATHER_BATCH_TRAIN
+#define GATHER_BATCH_TRAIN 2    // training kernel: per-warp accumulators are live across the gather
+#endif
+template <bool WANT_DY, int GATHER_BATCH>
 __device__ __forceinline__ void gather_tile(const GridMeta& gm, const __half* __restrict__ grid, const float* sCoord, __half* sX0, float* sDY, int lane) {
 	const int s = lane & 15;
 	const float x = sCoord[s * 7 + 0], y = sCoord[s * 7 + 1], z = sCoord[s * 7 + 2];
-	for (int l = lane >> 4; l < (int)gm.n_levels; l += 2) {
-		__half* xo = sX0 + s * LD_X0 + 3 + 2 * l;
-		float* dyo = sDY + s * LD_DY + 6 * l;
-		if ((uint32_t)l > gm.valid_level) {
-			xo[0] = __float2half(0.f); xo[1] = __float2half(0.f);
-			if (WANT_DY) { for (int k = 0; k < 6; ++k) dyo[k] = 0.f; }
-			continue;
-		}
-		LevelGeom lg;
-		level_geom(gm, l, x, y, z, lg);
-		const __half* g = grid + (size_t)gm.offset[l] * 2;
-		uint32_t v[8];
+	const int n_levels = (int)gm.n_levels;
+	for (int l0 = lane >> 4; l0 < n_levels; l0 += 2 * GATHER_BATCH) {
+		uint32_t v[GATHER_BATCH][8];
+		float w[GATHER_BATCH][3];
 		#pragma unroll
-		for (int c = 0; c < 8; ++c) v[c] = ld_nc_u32(g + lg.idx[c]);
-		const float wx[2] = {1.f - lg.w[0], lg.w[0]}, wy[2] = {1.f - lg.w[1], lg.w[1]}, wz[2] = {1.f - lg.w[2], lg.w[2]};
-		__half r0 = __float2half(0.f), r1 = __float2half(0.f);
-		#pragma unroll
-		for (int c = 0; c < 8; ++c) {
-			const float weight = (wx[c & 1] * wy[(c >> 1) & 1]) * wz[(c >> 2) & 1];
-			r0 = __hadd(r0, __float2half_rn(weight * h_lo(v[c])));
-			r1 = __hadd(r1, __float2half_rn(weight * h_hi(v[c])));
-		}
-		xo[0] = r0; xo[1] = r1;
-		if (WANT_DY) {
-			const float scale = gm.scale[l];
-			float g0[3] = {0.f, 0.f, 0.f}, g1[3] = {0.f, 0.f, 0.f};
-			#pragma unroll
-			for (int i = 0; i < 4; ++i) {
-				const int b0 = i & 1, b1 = (i >> 1) & 1;
-				{   // d/dx : other dims (y, z)
-					const float weight = (scale * wy[b0]) * wz[b1];
-					const int cl = (b0 << 1) | (b1 << 2), cr = cl | 1;
-					g0[0] = fmaf(weight, h_lo(v[cr]) - h_lo(v[cl]), g0[0]);
-					g1[0] = fmaf(weight, h_hi(v[cr]) - h_hi(v[cl]), g1[0]);
-				}
-				{   // d/dy : other dims (x, z)
-					const float weight = (scale * wx[b0]) * wz[b1];
-					const int cl = b0 | (b1 << 2), cr = cl | 2;
-					g0[1] = fmaf(weight, h_lo(v[cr]) - h_lo(v[cl]), g0[1]);
-					g1[1] = fmaf(weight, h_hi(v[cr]) - h_hi(v[cl]), g1[1]);
-				}
-				{   // d/dz : other dims (x, y)
-					const float weight = (scale * wx[b0]) * wy[b1];
-					const int cl = b0 | (b1 << 1), cr = cl | 4;
-					g0[2] = fmaf(weight, h_lo(v[cr]) - h_lo(v[cl]), g0[2]);
-					g1[2] = fmaf(weight, h_hi(v[cr]) - h_hi(v[cl]), g1[2]);
-				}
+		for (int u = 0; u < GATHER_BATCH; ++u) {
+			const int l = l0 + 2 * u;
+			if (l < n_levels && (uint32_t)l <= gm.valid_level) {
+				LevelGeom lg;
+				level_geom(gm, l, x, y, z, lg);
+				w[u][0] = lg.w[0]; w[u][1] = lg.w[1]; w[u][2] = lg.w[2];
+				const __half* g = grid + (size_t)gm.offset[l] * 2;
+				#pragma unroll
+				for (int c = 0; c < 8; ++c) v[u][c] = ld_nc_u32(g + lg.idx[c]);
 			}
-			dyo[0] = g0[0]; dyo[1] = g0[1]; dyo[2] = g0[2];
-			dyo[3] = g1[0]; dyo[4] = g1[1]; dyo[5] = g1[2];
+		}
+		#pragma unroll
+		for (int u = 0; u < GATHER_BATCH; ++u) {
+			const int l = l0 + 2 * u;
+			if (l >= n_levels) break;
+			__half* xo = sX0 + s * LD_X0 + 3 + 2 * l;
+			float* dyo = sDY + s * LD_DY + 6 * l;
+			if ((uint32_t)l > gm.valid_level) {
+				xo[0] = __float2half(0.f); xo[1] = __float2half(0.f);
+				if (WANT_DY) { for (int k = 0; k < 6; ++k) dyo[k] = 0.f; }
+				continue;
+			}
+			const float wx[2] = {1.f - w[u][0], w[u][0]}, wy[2] = {1.f - w[u][1], w[u][1]}, wz[2] = {1.f - w[u][2], w[u][2]};
+			__half r0 = __float2half(0.f), r1 = __float2half(0.f);
+			#pragma unroll
+			for (int c = 0; c < 8; ++c) {
+				const float weight = (wx[c & 1] * wy[(c >> 1) & 1]) * wz[(c >> 2) & 1];
+				r0 = __hadd(r0, __float2half_rn(weight * h_lo(v[u][c])));
+				r1 = __hadd(r1, __float2half_rn(weight * h_hi(v[u][c])));
+			}
+			xo[0] = r0; xo[1] = r1;
+			if (WANT_DY) {
+				const float scale = gm.scale[l];
+				float g0[3] = {0.f, 0.f, 0.f}, g1[3] = {0.f, 0.f, 0.f};
+				#pragma unroll
+				for (int i = 0; i < 4; ++i) {
+					const int b0 = i & 1, b1 = (i >> 1) & 1;
+					{   // d/dx : other dims (y, z)
+						const float weight = (scale * wy[b0]) * wz[b1];
+						const int cl = (b0 << 1) | (b1 << 2), cr = cl | 1;
+						g0[0] = fmaf(weight, h_lo(v[u][cr]) - h_lo(v[u][cl]), g0[0]);
+						g1[0] = fmaf(weight, h_hi(v[u][cr]) - h_hi(v[u][cl]), g1[0]);
+					}
+					{   // d/dy : other dims (x, z)
+						const float weight = (scale * wx[b0]) * wz[b1];
+						const int cl = b0 | (b1 << 2), cr = cl | 2;
+						g0[1] = fmaf(weight, h_lo(v[u][cr]) - h_lo(v[u][cl]), g0[1]);
+						g1[1] = fmaf(weight, h_hi(v[u][cr]) - h_hi(v[u][cl]), g1[1]);
+					}
+					{   // d/dz : other dims (x, y)
+						const float weight = (scale * wx[b0]) * wy[b1];
+						const int cl = b0 | (b1 << 1), cr = cl | 4;
+						g0[2] = fmaf(weight, h_lo(v[u][cr]) - h_lo(v[u][cl]), g0[2]);
+						g1[2] = fmaf(weight, h_hi(v[u][cr]) - h_hi(v[u][cl]), g1[2]);
+					}
+				}
+				dyo[0] = g0[0]; dyo[1] = g0[1]; dyo[2] = g0[2];
+				dyo[3] = g1[0]; dyo[4] = g1[1]; dyo[5] = g1[2];
+			}
 		}
 	}
 }
@@ -328,7 +350,7 @@ __device__ __forceinline__ void forward_tile(const GridMeta& gm, const __half* _
 		for (int d = 0; d < 3; ++d) sX0[lane * LD_X0 + d] = __hsub(__float2half_rn(sCoord[lane * 7 + d]), __float2half_rn(0.5f));
 		for (int k = 3 + 2 * (int)gm.n_levels; k < SDF_IN; ++k) sX0[lane * LD_X0 + k] = __float2half(0.f);
 	}
-	gather_tile<true>(gm, params + pl.off_grid, sCoord, sX0, sDY, lane);
+	gather_tile<true, KEEP ? GATHER_BATCH_TRAIN : GATHER_BATCH_FWD>(gm, params + pl.off_grid, sCoord, sX0, sDY, lane);
 	__syncwarp();
 
 	// --- SDF MLP (32 -> 64 -> 16), fp32 accumulate, half activations
@@ -451,7 +473,7 @@ __device__ __forceinline__ void sdf_tile(const GridMeta& gm, const __half* __res
 		for (int d = 0; d < 3; ++d) sX0[lane * LD_X0 + d] = __hsub(__float2half_rn(sCoord[lane * 7 + d]), __float2half_rn(0.5f));
 		for (int k = 3 + 2 * (int)gm.n_levels; k < SDF_IN; ++k) sX0[lane * LD_X0 + k] = __float2half(0.f);
 	}
-	gather_tile<false>(gm, grid, sCoord, sX0, nullptr, lane);
+	gather_tile<false, GATHER_BATCH_FWD>(gm, grid, sCoord, sX0, nullptr, lane);
 	__syncwarp();
 	uint32_t xa[2][4], h0a[4][4];
 	load_a_frag(xa[0], sX0, LD_X0, 0, g, t);

@@ -25,15 +25,13 @@ def allreduce_sum_(tensor, group=None):
 
 def train_step(ctx, rank=0, world_size=1, group=None):
     """One data-parallel Testbed::train() step on this rank's Context.  Returns the step stats (global counts)."""
-    import torch
     if world_size == 1:
         return ctx.train_step()
     ctx.train_step_begin(rank, world_size)
-    grads = ctx.buffers()[3]
-    counts = torch.tensor(ctx.local_counts(), dtype=torch.int64, device=grads.device)
-    allreduce_sum_(grads, group)      # 10,559,396 fp32 gradients over NVLink
-    allreduce_sum_(counts, group)     # {rays kept, samples, compacted samples}: drives the shared rays_per_batch update
-    return ctx.train_step_end([int(x) for x in counts.tolist()])
+    # both all-reduces are enqueued behind the backward pass on the step's stream: no host round trip between begin and end
+    allreduce_sum_(ctx.counts_device(), group)   # {rays kept, samples, compacted samples}: drives the shared rays_per_batch update
+    allreduce_sum_(ctx.buffers()[3], group)      # 10,559,396 fp32 gradients over NVLink
+    return ctx.train_step_end()
 
 
 # ---- inference: independent units, no data-path collective (SURVEY §8e) ---------------------------------------------------
