@@ -37,6 +37,7 @@ def parse():
     ap.add_argument("--width", type=int, default=1600)
     ap.add_argument("--height", type=int, default=1200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dp", default="p2p", choices=["p2p", "nccl"], help="N>1: optimizer fused with the gradient reduction over NVLink peer memory (p2p) or NCCL all-reduce + replicated Adam")
     return ap.parse_args()
 
 
@@ -195,7 +196,7 @@ def workload_config(args, n_gpus):
     return {
         "workload": f"DTU-Scan24-shaped synthetic scene ({args.views} views {args.width}x{args.height} RGBA from an analytic SDF), base.json "
                     f"(hashgrid L=14 F=2 T=2^19, 64-wide fp16 SDF+colour MLPs, eikonal 0.01), batch 2^18 samples per GPU",
-        "batch_samples_per_gpu": 1 << 18, "global_batch_samples": (1 << 18) * n_gpus, "parallelism": f"dp{n_gpus} (rays sharded, NCCL all-reduce of fp32 grads)" if n_gpus > 1 else "single GPU",
+        "batch_samples_per_gpu": 1 << 18, "global_batch_samples": (1 << 18) * n_gpus, "parallelism": (f"dp{n_gpus} (rays sharded; " + ("Adam fused with the gradient reduction over NVLink peer memory, 1/N of the optimizer state per GPU)" if args.dp == "p2p" else "NCCL all-reduce of fp32 grads + replicated Adam)")) if n_gpus > 1 else "single GPU",
         "l2_policy": "per-step working set (>=470 MB of sample/activation buffers) exceeds the 126 MB L2; no explicit flush",
         "preroll_steps": args.preroll,
     }
@@ -239,6 +240,8 @@ def main():
     stream = torch.cuda.current_stream()
 
     from neus2_b200 import parallel
+    if world > 1 and args.dp == "p2p":
+        parallel.attach_peers(ctx, rank, world)
 
     def step():
         return parallel.train_step(ctx, rank, world)   # world > 1: NCCL all-reduce of the 10.56 M fp32 gradients over NVLink

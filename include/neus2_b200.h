@@ -185,6 +185,21 @@ int neus2_marching_cubes(neus2_ctx* ctx, void* stream, const uint32_t res[3], co
                          uint32_t* n_verts, uint32_t* n_indices);
 int neus2_mesh_buffers(neus2_ctx* ctx, float** verts_dev, uint32_t** indices_dev, uint32_t* n_verts, uint32_t* n_indices);
 
+/* ---- data-parallel training over one NVSwitch domain (not in the reference, which is single-GPU) -----------------
+ * The optimizer step fused with its collective: rank r owns a contiguous 1/W slice of the parameters, sums that slice of every
+ * rank's gradient buffer through NVLink peer loads, applies Adam + EMA to it and stores the new fp16 parameters / EMA values
+ * into every rank's buffers.  Set-up: each rank exports CUDA IPC handles of its {gradient, fp16 parameter, EMA} buffers, the
+ * host side exchanges them (torch.distributed all_gather), every rank attaches all of them.  Per step:
+ *   neus2_train_step_begin -> [stream-ordered barrier, e.g. the all-reduce of neus2_counts_device] -> neus2_optimizer_step_sharded
+ *   -> [stream-ordered barrier] -> neus2_train_step_end (which then skips its own optimizer call).
+ * The fp32 master copy / Adam moments of a rank are current only for its own slice (neus2_optimizer_shard). */
+#define NEUS2_IPC_BUFFERS 3
+#define NEUS2_IPC_HANDLE_BYTES 64
+int neus2_ipc_export(neus2_ctx* ctx, unsigned char* handles /* NEUS2_IPC_BUFFERS x NEUS2_IPC_HANDLE_BYTES */);
+int neus2_ipc_attach(neus2_ctx* ctx, uint32_t rank, uint32_t world_size, const unsigned char* all_handles /* [world_size][NEUS2_IPC_BUFFERS][64] */);
+int neus2_optimizer_shard(const neus2_ctx* ctx, uint32_t rank, uint32_t world_size, uint64_t* begin, uint64_t* end);   /* parameter index range */
+int neus2_optimizer_step_sharded(neus2_ctx* ctx, void* stream, float loss_scale);
+
 #ifdef __cplusplus
 }
 #endif

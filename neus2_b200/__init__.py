@@ -58,6 +58,7 @@ class Context:
         h = C.c_void_p()
         check(self._lib.neus2_ctx_create(C.byref(self.cfg), C.c_int(device), C.byref(h)))
         self._h = h
+        self.peers_attached = False
         self.n_params = int(self._lib.neus2_n_params(self._h))
         lay = (C.c_uint32 * 8)()
         check(self._lib.neus2_param_layout(self._h, lay))
@@ -184,6 +185,28 @@ class Context:
             check(self._lib.neus2_counts_device(self._h, C.byref(p)))
             self._counts = _torch().as_tensor(_DevArray(p.value, (4,), "<i4", None), device=f"cuda:{self.device}")
         return self._counts
+
+    # ---- data-parallel peers (fused gradient reduction + Adam over NVLink peer memory) ------------------------------------
+    def ipc_export(self):
+        h = (C.c_ubyte * (3 * 64))()
+        check(self._lib.neus2_ipc_export(self._h, h))
+        return bytes(h)
+
+    def ipc_attach(self, rank, world_size, all_handles):
+        """all_handles: list of world_size `bytes` objects as returned by ipc_export on each rank, in rank order."""
+        blob = b"".join(all_handles)
+        assert len(blob) == world_size * 3 * 64
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        check(self._lib.neus2_ipc_attach(self._h, C.c_uint32(rank), C.c_uint32(world_size), buf))
+        self.peers_attached = True
+
+    def optimizer_shard(self, rank, world_size):
+        b, e = C.c_uint64(), C.c_uint64()
+        check(self._lib.neus2_optimizer_shard(self._h, C.c_uint32(rank), C.c_uint32(world_size), C.byref(b), C.byref(e)))
+        return int(b.value), int(e.value)
+
+    def optimizer_step_sharded(self, loss_scale=128.0, stream=None):
+        check(self._lib.neus2_optimizer_step_sharded(self._h, _stream(stream), C.c_float(loss_scale)))
 
     def train_step_end(self, counts_global=None, stream=None):
         st = StepStats()

@@ -76,6 +76,10 @@ struct neus2_ctx {
 	uint32_t stage_count[NEUS2_N_STAGES];
 	bool stage_pending[NEUS2_N_STAGES];
 	float* h_scalars;           // pinned
+	// data-parallel peers (CUDA IPC mappings of every rank's gradient / fp16 parameter / EMA buffers; slot [rank] = own)
+	uint32_t peer_world, peer_rank;
+	float* peer_grads[NEUS2_MAX_PEERS]; __half* peer_params[NEUS2_MAX_PEERS]; __half* peer_ema[NEUS2_MAX_PEERS];
+	bool optimizer_done;        // the sharded optimizer already ran for the step in flight
 	// inference render scratch (sized on first use / growth, then reused)
 	size_t render_cap;          // tile pixels
 	void* r_queue; uint32_t* r_counters; float *r_ray_rgba, *r_ray_depth, *r_accumulate; uint32_t* r_ray_samples;
@@ -237,6 +241,11 @@ void neus2_ctx_destroy(neus2_ctx* ctx) {
 		ctx->so.CIN, ctx->so.dSO, ctx->so.H0, ctx->so.dH0, ctx->so.X0, ctx->so.dI, ctx->partials, ctx->var_acc, ctx->w1row0_acc, ctx->scalar_tmp,
 		ctx->density_grid, ctx->density_grid_tmp, ctx->grid_positions, ctx->grid_indices, ctx->grid_density, ctx->bitfield, ctx->density_grid_mean};
 	for (void* p : ptrs) if (p) cudaFree(p);
+	for (uint32_t r = 0; r < ctx->peer_world; ++r) if (r != ctx->peer_rank) {
+		if (ctx->peer_grads[r]) cudaIpcCloseMemHandle(ctx->peer_grads[r]);
+		if (ctx->peer_params[r]) cudaIpcCloseMemHandle(ctx->peer_params[r]);
+		if (ctx->peer_ema[r]) cudaIpcCloseMemHandle(ctx->peer_ema[r]);
+	}
 	void* more[] = {ctx->r_queue, ctx->r_counters, ctx->r_ray_rgba, ctx->r_ray_depth, ctx->r_accumulate, ctx->r_ray_samples,
 		ctx->mc_block_counts, ctx->mc_counts, ctx->mc_vert_prefix, ctx->mc_indices, ctx->mc_verts};
 	for (void* p : more) if (p) cudaFree(p);
@@ -517,7 +526,8 @@ int neus2_train_step_end(neus2_ctx* ctx, void* stream_, const uint32_t* counts_g
 	CUDA_CHECK(cudaSetDevice(ctx->device));
 	const neus2_config& c = ctx->cfg;
 	const bool get_loss_scalar = ctx->training_step % 16 == 0;                           // testbed.cu:2714
-	CHECK(neus2_optimizer_step(ctx, stream_, c.loss_scale));                             // testbed_nerf.cu:3503-3505
+	if (!ctx->optimizer_done) CHECK(neus2_optimizer_step(ctx, stream_, c.loss_scale));   // testbed_nerf.cu:3503-3505
+	ctx->optimizer_done = false;
 	if (get_loss_scalar) {
 		CHECK(launch_reduce_sum(stream, ctx->loss, ctx->step_rays, ctx->scalar_tmp + 0));
 		CHECK(launch_reduce_sum(stream, ctx->ek_loss, ctx->step_rays, ctx->scalar_tmp + 1));
@@ -724,6 +734,61 @@ int neus2_mesh_buffers(neus2_ctx* ctx, float** verts, uint32_t** indices, uint32
 	if (n_verts) *n_verts = ctx->mc_n_verts;
 	if (n_indices) *n_indices = ctx->mc_n_indices;
 	return 0;
+}
+
+// ---- data-parallel peers: fused gradient reduction + Adam over NVLink peer memory ------------------------------------------
+int neus2_ipc_export(neus2_ctx* ctx, unsigned char* handles) {
+	CUDA_CHECK(cudaSetDevice(ctx->device));
+	if (!handles) FAIL("null argument");
+	static_assert(sizeof(cudaIpcMemHandle_t) == NEUS2_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+	void* bufs[NEUS2_IPC_BUFFERS] = {ctx->grads, ctx->params, ctx->ema};
+	for (int k = 0; k < NEUS2_IPC_BUFFERS; ++k) {
+		cudaIpcMemHandle_t h;
+		CUDA_CHECK(cudaIpcGetMemHandle(&h, bufs[k]));
+		memcpy(handles + (size_t)k * NEUS2_IPC_HANDLE_BYTES, &h, NEUS2_IPC_HANDLE_BYTES);
+	}
+	return 0;
+}
+
+int neus2_ipc_attach(neus2_ctx* ctx, uint32_t rank, uint32_t world, const unsigned char* all_handles) {
+	CUDA_CHECK(cudaSetDevice(ctx->device));
+	if (!all_handles) FAIL("null argument");
+	if (world != ctx->cfg.world_size || rank >= world) FAIL("rank / world_size do not match the context's config.world_size");
+	if (world > NEUS2_MAX_PEERS) FAIL("at most 8 peers (one NVSwitch domain)");
+	if (ctx->peer_world) FAIL("peers are already attached");
+	for (uint32_t r = 0; r < world; ++r) {
+		if (r == rank) { ctx->peer_grads[r] = ctx->grads; ctx->peer_params[r] = ctx->params; ctx->peer_ema[r] = ctx->ema; continue; }
+		void* ptrs[NEUS2_IPC_BUFFERS];
+		for (int k = 0; k < NEUS2_IPC_BUFFERS; ++k) {
+			cudaIpcMemHandle_t h;
+			memcpy(&h, all_handles + ((size_t)r * NEUS2_IPC_BUFFERS + k) * NEUS2_IPC_HANDLE_BYTES, NEUS2_IPC_HANDLE_BYTES);
+			CUDA_CHECK(cudaIpcOpenMemHandle(&ptrs[k], h, cudaIpcMemLazyEnablePeerAccess));
+		}
+		ctx->peer_grads[r] = (float*)ptrs[0]; ctx->peer_params[r] = (__half*)ptrs[1]; ctx->peer_ema[r] = (__half*)ptrs[2];
+	}
+	ctx->peer_world = world; ctx->peer_rank = rank;
+	return 0;
+}
+
+int neus2_optimizer_shard(const neus2_ctx* ctx, uint32_t rank, uint32_t world, uint64_t* begin, uint64_t* end) {
+	if (!world || rank >= world || !begin || !end) FAIL("bad argument");
+	uint64_t q0, q1;
+	optimizer_shard(ctx->n_params / 4, rank, world, &q0, &q1);
+	*begin = q0 * 4; *end = q1 * 4;
+	return 0;
+}
+
+int neus2_optimizer_step_sharded(neus2_ctx* ctx, void* stream, float loss_scale) {
+	CUDA_CHECK(cudaSetDevice(ctx->device));
+	if (!ctx->peer_world) FAIL("no peers attached: call neus2_ipc_attach first");
+	const neus2_config& c = ctx->cfg;
+	++ctx->adam_step;
+	stage_begin(ctx, ST_OPT, (cudaStream_t)stream);
+	const int rc_ = launch_adam_ema_p2p((cudaStream_t)stream, ctx->n_params, ctx->pl.off_grid, ctx->peer_rank, ctx->peer_world, loss_scale, c.learning_rate, c.beta1, c.beta2,
+	                                    c.epsilon, c.l2_reg, c.ema_decay, ctx->adam_step, ctx->peer_grads, ctx->peer_params, ctx->peer_ema, ctx->master, ctx->m1, ctx->m2, ctx->steps);
+	stage_end(ctx, ST_OPT, (cudaStream_t)stream);
+	ctx->optimizer_done = true;
+	return rc_;
 }
 
 }  // extern "C"

@@ -87,3 +87,95 @@ int launch_adam_ema(cudaStream_t stream, uint64_t n, uint64_t n_matrix, float lo
 	CUDA_CHECK(cudaGetLastError());
 	return 0;
 }
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Data-parallel optimizer step fused with its collective: instead of all-reduce(grads) followed by a replicated
+// Adam, rank r owns the contiguous quad range [q0, q1) of the parameters, SUMS the gradients of all ranks for that range
+// straight out of the peers' gradient buffers (NVLink/NVSwitch P2P loads, fixed rank order), runs Adam + EMA on it, and
+// stores the refreshed fp16 parameters and EMA values into every rank's buffers (P2P stores).  Optimizer state (fp32 master,
+// moments, step counters) is touched for 1/W of the parameters per GPU; no gradient ever round-trips through a reduced copy.
+// Ordering between ranks (backward finished before peers read; stores landed before peers' next forward) is the caller's:
+// a stream-ordered tiny collective on either side (neus2_b200/parallel.py).
+// ------------------------------------------------------------------------------------------------------------------------
+struct PeerPtrs { const float* grads[NEUS2_MAX_PEERS]; __half* params[NEUS2_MAX_PEERS]; __half* ema[NEUS2_MAX_PEERS]; };
+
+__global__ void __launch_bounds__(256)
+k_adam_ema_p2p(uint64_t q0, uint64_t q1, uint64_t n_matrix4, AdamHyper h, int world, PeerPtrs peers,
+               float* __restrict__ master, float* __restrict__ m1, float* __restrict__ m2, uint32_t* __restrict__ steps) {
+	const uint64_t q = q0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= q1) return;
+	const bool is_matrix = q < n_matrix4;
+	float4 gr[NEUS2_MAX_PEERS];
+	#pragma unroll
+	for (int r = 0; r < NEUS2_MAX_PEERS; ++r) if (r < world) gr[r] = reinterpret_cast<const float4*>(peers.grads[r])[q];   // all loads in flight together
+	float4 g4 = gr[0];
+	#pragma unroll
+	for (int r = 1; r < NEUS2_MAX_PEERS; ++r) if (r < world) { g4.x += gr[r].x; g4.y += gr[r].y; g4.z += gr[r].z; g4.w += gr[r].w; }
+	uint2 pw = reinterpret_cast<const uint2*>(peers.params[0])[q];     // slot 0 is always this rank's own buffer
+	__half* ph = reinterpret_cast<__half*>(&pw);
+	const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+	if (is_matrix || g4.x != 0.f || g4.y != 0.f || g4.z != 0.f || g4.w != 0.f) {
+		float4 w4 = reinterpret_cast<const float4*>(master)[q];
+		float4 a4 = reinterpret_cast<const float4*>(m1)[q];
+		float4 b4 = reinterpret_cast<const float4*>(m2)[q];
+		uint4 s4 = reinterpret_cast<const uint4*>(steps)[q];
+		float* w = reinterpret_cast<float*>(&w4); float* a = reinterpret_cast<float*>(&a4); float* b = reinterpret_cast<float*>(&b4);
+		uint32_t* st = reinterpret_cast<uint32_t*>(&s4);
+		bool any = false;
+		#pragma unroll
+		for (int k = 0; k < 4; ++k) {
+			bool touched;
+			ph[k] = adam_one(is_matrix, g[k], h, w[k], a[k], b[k], st[k], ph[k], touched);
+			any |= touched;
+		}
+		if (any) {
+			reinterpret_cast<float4*>(master)[q] = w4;
+			reinterpret_cast<float4*>(m1)[q] = a4;
+			reinterpret_cast<float4*>(m2)[q] = b4;
+			reinterpret_cast<uint4*>(steps)[q] = s4;
+			#pragma unroll
+			for (int r = 0; r < NEUS2_MAX_PEERS; ++r) if (r < world) reinterpret_cast<uint2*>(peers.params[r])[q] = pw;
+		}
+	}
+	uint2 ew = reinterpret_cast<const uint2*>(peers.ema[0])[q];
+	__half* eh = reinterpret_cast<__half*>(&ew);
+	#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		const float filtered = (__half2float(eh[k]) * h.ema_decay * h.ema_debias_old + __half2float(ph[k]) * (1 - h.ema_decay)) * h.ema_debias_new;
+		eh[k] = __float2half_rn(filtered);
+	}
+	#pragma unroll
+	for (int r = 0; r < NEUS2_MAX_PEERS; ++r) if (r < world) reinterpret_cast<uint2*>(peers.ema[r])[q] = ew;
+}
+
+int launch_adam_ema_p2p(cudaStream_t stream, uint64_t n, uint64_t n_matrix, uint32_t rank, uint32_t world, float loss_scale, float lr, float beta1, float beta2,
+                        float eps, float l2_reg, float ema_decay, uint32_t ema_step, const float* const* grads_peers, __half* const* params_peers,
+                        __half* const* ema_peers, float* master, float* m1, float* m2, uint32_t* steps) {
+	const float ema_debias_old = 1 - (float)pow((double)ema_decay, (double)(ema_step - 1));
+	const float ema_debias_new = 1.0f / (1 - (float)pow((double)ema_decay, (double)ema_step));
+	if (n % 4 != 0 || n_matrix % 4 != 0) { neus_set_error("parameter counts must be multiples of 4", __FILE__, __LINE__); return -1; }
+	if (world < 1 || world > NEUS2_MAX_PEERS || rank >= world) { neus_set_error("bad rank / world size for the sharded optimizer", __FILE__, __LINE__); return -1; }
+	AdamHyper h = {loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, ema_debias_old, ema_debias_new};
+	uint64_t q0, q1;
+	optimizer_shard(n / 4, rank, world, &q0, &q1);
+	PeerPtrs pp;
+	for (uint32_t r = 0; r < NEUS2_MAX_PEERS; ++r) { pp.grads[r] = nullptr; pp.params[r] = nullptr; pp.ema[r] = nullptr; }
+	// slot 0 = own buffers, then the peers in ascending rank order: the sum order is the same on every step
+	uint32_t slot = 0;
+	pp.grads[slot] = grads_peers[rank]; pp.params[slot] = params_peers[rank]; pp.ema[slot] = ema_peers[rank]; ++slot;
+	for (uint32_t r = 0; r < world; ++r) if (r != rank) { pp.grads[slot] = grads_peers[r]; pp.params[slot] = params_peers[r]; pp.ema[slot] = ema_peers[r]; ++slot; }
+	if (q1 > q0) {
+		const uint32_t blocks = (uint32_t)((q1 - q0 + 255) / 256);
+		k_adam_ema_p2p<<<blocks, 256, 0, stream>>>(q0, q1, n_matrix / 4, h, (int)world, pp, master, m1, m2, steps);
+		COUNT_LAUNCH(1);
+	}
+	CUDA_CHECK(cudaGetLastError());
+	return 0;
+}
+
+// quads [q0, q1) of rank `rank`: contiguous, sizes differ by at most one quad
+void optimizer_shard(uint64_t n_quads, uint32_t rank, uint32_t world, uint64_t* q0, uint64_t* q1) {
+	const uint64_t base = n_quads / world, extra = n_quads % world;
+	*q0 = rank * base + (rank < extra ? rank : extra);
+	*q1 = *q0 + base + (rank < extra ? 1 : 0);
+}
