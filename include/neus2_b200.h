@@ -184,6 +184,9 @@ int neus2_sdf_lattice(neus2_ctx* ctx, void* stream, const uint32_t res[3], const
 int neus2_marching_cubes(neus2_ctx* ctx, void* stream, const uint32_t res[3], const float aabb[6], float thresh, const float* density_dev,
                          uint32_t* n_verts, uint32_t* n_indices);
 int neus2_mesh_buffers(neus2_ctx* ctx, float** verts_dev, uint32_t** indices_dev, uint32_t* n_verts, uint32_t* n_indices);
+/* compute_mesh_1ring's area-weighted vertex normals (src/marching_cubes.cu:333-370) and compute_mesh_vertex_colors
+ * (src/testbed_nerf.cu:4071-4093: network colour seen from outside, logistic, sRGB) of that mesh; [n_verts][3] floats each, either NULL. */
+int neus2_mesh_attributes(neus2_ctx* ctx, void* stream, float* normals_out_dev, float* colors_out_dev, int use_inference_params);
 
 /* ---- data-parallel training over one NVSwitch domain (not in the reference, which is single-GPU) -----------------
  * The optimizer step fused with its collective: rank r owns a contiguous 1/W slice of the parameters, sums that slice of every
@@ -199,6 +202,15 @@ int neus2_ipc_export(neus2_ctx* ctx, unsigned char* handles /* NEUS2_IPC_BUFFERS
 int neus2_ipc_attach(neus2_ctx* ctx, uint32_t rank, uint32_t world_size, const unsigned char* all_handles /* [world_size][NEUS2_IPC_BUFFERS][64] */);
 int neus2_optimizer_shard(const neus2_ctx* ctx, uint32_t rank, uint32_t world_size, uint64_t* begin, uint64_t* end);   /* parameter index range */
 int neus2_optimizer_step_sharded(neus2_ctx* ctx, void* stream, float loss_scale);
+
+/* ---- snapshot support: the state Testbed::save_snapshot serialises (src/testbed.cu:3144-3178; tcnn trainer.h:281-304,
+ * optimizers/adam.h:424-445, ema.h:182-194) beyond what neus2_buffers / neus2_get_state / neus2_debug_buffer already expose. */
+int neus2_optimizer_buffers(neus2_ctx* ctx, float** first_moments_dev, float** second_moments_dev, uint32_t** param_steps_dev, uint32_t* current_step);
+int neus2_set_optimizer_step(neus2_ctx* ctx, uint32_t current_step);
+/* {n_rays_total, measured_batch_size_before_compaction, density_grid_ema_step, optimizer current_step} (testbed.h:598-612, 640) */
+int neus2_get_counters(neus2_ctx* ctx, uint32_t out[4]);
+/* load_snapshot's density-grid restore (testbed.cu:3222-3240): uploads the grid and rebuilds mean + occupancy bitfield. */
+int neus2_set_density_grid(neus2_ctx* ctx, void* stream, const float* density_grid_host, uint64_t n, uint32_t ema_step);
 
 #ifdef __cplusplus
 }

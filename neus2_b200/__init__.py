@@ -225,7 +225,10 @@ class Context:
         ts, rpb = C.c_uint32(), C.c_uint32()
         rng = (C.c_uint64 * 2)()
         check(self._lib.neus2_get_state(self._h, C.byref(ts), C.byref(rpb), rng))
-        return dict(training_step=ts.value, rays_per_batch=rpb.value, rng_state=(int(rng[0]), int(rng[1])))
+        c = (C.c_uint32 * 4)()
+        check(self._lib.neus2_get_counters(self._h, c))
+        return dict(training_step=ts.value, rays_per_batch=rpb.value, rng_state=(int(rng[0]), int(rng[1])), n_rays_total=int(c[0]),
+                    measured_before=int(c[1]), density_grid_ema_step=int(c[2]), optimizer_step=int(c[3]))
 
     def set_state(self, training_step, rays_per_batch, n_rays_total=0, measured_before=0):
         check(self._lib.neus2_set_state(self._h, C.c_uint32(training_step), C.c_uint32(rays_per_batch), C.c_uint32(n_rays_total), C.c_uint32(measured_before)))
@@ -233,6 +236,31 @@ class Context:
     def set_bitfield(self, bitfield):
         b = np.ascontiguousarray(bitfield, dtype=np.uint8)
         check(self._lib.neus2_set_bitfield(self._h, b.ctypes.data_as(C.c_void_p), C.c_uint64(b.size)))
+
+    def mesh_attributes(self, n_verts, use_inference_params=True, stream=None):
+        """(vertex normals [n,3], vertex colours [n,3]) of the mesh of the last marching_cubes call."""
+        torch = _torch()
+        dev = f"cuda:{self.device}"
+        nrm = torch.zeros((n_verts, 3), dtype=torch.float32, device=dev)
+        col = torch.zeros((n_verts, 3), dtype=torch.float32, device=dev)
+        check(self._lib.neus2_mesh_attributes(self._h, _stream(stream), _ptr(nrm), _ptr(col), C.c_int(int(use_inference_params))))
+        return nrm, col
+
+    def optimizer_buffers(self):
+        """(first moments fp32, second moments fp32, per-parameter steps int32, current_step) -- zero-copy device views."""
+        torch = _torch()
+        a, b, c, st = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_uint32()
+        check(self._lib.neus2_optimizer_buffers(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(st)))
+        dev, n = f"cuda:{self.device}", self.n_params
+        return (torch.as_tensor(_DevArray(a.value, (n,), "<f4", None), device=dev), torch.as_tensor(_DevArray(b.value, (n,), "<f4", None), device=dev),
+                torch.as_tensor(_DevArray(c.value, (n,), "<i4", None), device=dev), int(st.value))
+
+    def set_optimizer_step(self, step):
+        check(self._lib.neus2_set_optimizer_step(self._h, C.c_uint32(step)))
+
+    def set_density_grid(self, grid, ema_step=0, stream=None):
+        g = np.ascontiguousarray(grid, dtype=np.float32)
+        check(self._lib.neus2_set_density_grid(self._h, _stream(stream), g.ctypes.data_as(C.c_void_p), C.c_uint64(g.size), C.c_uint32(ema_step)))
 
     STAGES = ["density_grid", "gen_samples", "forward", "loss", "fwdbwd", "wgrad", "optimizer", "step"]
 

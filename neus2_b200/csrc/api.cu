@@ -791,4 +791,54 @@ int neus2_optimizer_step_sharded(neus2_ctx* ctx, void* stream, float loss_scale)
 	return rc_;
 }
 
+// ---- snapshot support (Testbed::save_snapshot / load_snapshot, src/testbed.cu:3144-3266; Trainer / Adam / EMA serialize) ----
+int neus2_optimizer_buffers(neus2_ctx* ctx, float** m1_dev, float** m2_dev, uint32_t** steps_dev, uint32_t* current_step) {
+	if (m1_dev) *m1_dev = ctx->m1;
+	if (m2_dev) *m2_dev = ctx->m2;
+	if (steps_dev) *steps_dev = ctx->steps;
+	if (current_step) *current_step = ctx->adam_step;
+	return 0;
+}
+
+int neus2_set_optimizer_step(neus2_ctx* ctx, uint32_t current_step) { ctx->adam_step = current_step; return 0; }
+
+// density_grid: n floats (128^3 per cascade); recomputes mean + bitfield like load_snapshot does (testbed.cu:3232-3236)
+int neus2_set_density_grid(neus2_ctx* ctx, void* stream_, const float* density_grid_host, uint64_t n, uint32_t ema_step) {
+	cudaStream_t stream = (cudaStream_t)stream_;
+	CUDA_CHECK(cudaSetDevice(ctx->device));
+	const uint64_t want = (uint64_t)NERF_GRIDSIZE * NERF_GRIDSIZE * NERF_GRIDSIZE * ctx->n_cascades;
+	if (n != want) FAIL("Incompatible number of grid cascades.");
+	CUDA_CHECK(cudaMemcpyAsync(ctx->density_grid, density_grid_host, n * sizeof(float), cudaMemcpyHostToDevice, stream));
+	ctx->density_grid_ema_step = ema_step;
+	CHECK(launch_density_grid_bitfield(stream, ctx->density_grid, ctx->n_cascades, ctx->density_grid_mean, ctx->bitfield));
+	CUDA_CHECK(cudaStreamSynchronize(stream));
+	return 0;
+}
+
+// compute_mesh_1ring's vertex normals + compute_mesh_vertex_colors (src/marching_cubes.cu:333-370,716-722; src/testbed_nerf.cu:4071-4093)
+// for the mesh of the last neus2_marching_cubes call.  normals_out / colors_out: [n_verts][3] float (either may be NULL).
+int neus2_mesh_attributes(neus2_ctx* ctx, void* stream_, float* normals_out, float* colors_out, int use_inference_params) {
+	cudaStream_t stream = (cudaStream_t)stream_;
+	CUDA_CHECK(cudaSetDevice(ctx->device));
+	const uint32_t nv = ctx->mc_n_verts, nt = ctx->mc_n_indices / 3;
+	if (!nv) return 0;
+	if (normals_out) CHECK(launch_mesh_normals(stream, nv, nt, ctx->mc_indices, ctx->mc_verts, normals_out));
+	if (colors_out) {
+		float* coords = nullptr; __half* out16 = nullptr;
+		CUDA_CHECK(cudaMallocAsync((void**)&coords, (size_t)nv * 7 * sizeof(float), stream));
+		CUDA_CHECK(cudaMallocAsync((void**)&out16, (size_t)nv * 16 * sizeof(__half), stream));
+		int rc = launch_mesh_color_inputs(stream, nv, ctx->mc_verts, ctx->aabb, coords);
+		if (!rc) rc = launch_network_forward(stream, ctx->gm, ctx->pl, use_inference_params ? ctx->ema : ctx->params, coords, nullptr, nv, ctx->cfg.sdf_bias, out16);
+		if (!rc) rc = launch_mesh_extract_colors(stream, nv, out16, 0 /* train_in_linear_colors = false */, colors_out);
+		cudaFreeAsync(coords, stream); cudaFreeAsync(out16, stream);
+		if (rc) return rc;
+	}
+	return 0;
+}
+
+int neus2_get_counters(neus2_ctx* ctx, uint32_t out[4]) {
+	out[0] = ctx->n_rays_total; out[1] = ctx->measured_before; out[2] = ctx->density_grid_ema_step; out[3] = ctx->adam_step;
+	return 0;
+}
+
 }  // extern "C"

@@ -288,3 +288,63 @@ int launch_marching_cubes_emit(cudaStream_t stream, const uint32_t res[3], const
 	CUDA_CHECK(cudaGetLastError());
 	return 0;
 }
+
+// ---- mesh attributes ---------------------------------------------------------------------------------------
+// compute_mesh_1ring's normal accumulation (marching_cubes.cu:333-370): area-weighted face normals summed per vertex.
+__global__ void __launch_bounds__(256)
+k_mesh_vertex_normals(uint32_t n_tris, const uint32_t* __restrict__ indices, const float* __restrict__ verts, float* __restrict__ normals) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_tris) return;
+	const uint32_t ia = indices[i * 3 + 0], ib = indices[i * 3 + 1], ic = indices[i * 3 + 2];
+	const float pa[3] = {verts[ia * 3], verts[ia * 3 + 1], verts[ia * 3 + 2]};
+	const float pb[3] = {verts[ib * 3], verts[ib * 3 + 1], verts[ib * 3 + 2]};
+	const float pc[3] = {verts[ic * 3], verts[ic * 3 + 1], verts[ic * 3 + 2]};
+	const float u[3] = {pb[0] - pa[0], pb[1] - pa[1], pb[2] - pa[2]}, v[3] = {pa[0] - pc[0], pa[1] - pc[1], pa[2] - pc[2]};
+	const float n[3] = {fmaf(u[1], v[2], -(u[2] * v[1])), fmaf(u[2], v[0], -(u[0] * v[2])), fmaf(u[0], v[1], -(u[1] * v[0]))};   // (pb-pa) x (pa-pc), not normalised
+	const uint32_t id[3] = {ia, ib, ic};
+	#pragma unroll
+	for (int k = 0; k < 3; ++k) { atomicAdd(normals + id[k] * 3 + 0, n[0]); atomicAdd(normals + id[k] * 3 + 1, n[1]); atomicAdd(normals + id[k] * 3 + 2, n[2]); }
+}
+// generate_nerf_network_inputs_from_positions (testbed_nerf.cu:847-853): outward-pointing view direction
+__global__ void __launch_bounds__(256)
+k_mesh_color_inputs(uint32_t n, const float* __restrict__ verts, Aabb train_aabb, float* __restrict__ coords) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const float p[3] = {verts[i * 3], verts[i * 3 + 1], verts[i * 3 + 2]};
+	const float c[3] = {p[0] - 0.5f, p[1] - 0.5f, p[2] - 0.5f};
+	float d[3];
+	normalize3(c, d);
+	float* o = coords + (size_t)i * 7;
+	#pragma unroll
+	for (int k = 0; k < 3; ++k) o[k] = (p[k] - train_aabb.mn[k]) / (train_aabb.mx[k] - train_aabb.mn[k]);
+	o[3] = warp_dt(min_cone_stepsize());
+	#pragma unroll
+	for (int k = 0; k < 3; ++k) o[4 + k] = (d[k] + 1.0f) * 0.5f;
+}
+// extract_srgb_with_activation (testbed_nerf.cu:532-545): logistic, optional linear -> sRGB
+__global__ void __launch_bounds__(256)
+k_mesh_extract_colors(uint32_t n, const __half* __restrict__ out16, int from_linear, float* __restrict__ colors) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n * 3) return;
+	const uint32_t e = i / 3, d = i - e * 3;
+	float c = logistic_f(__half2float(out16[(size_t)e * 16 + d]));
+	if (from_linear) c = linear_to_srgb(c);
+	colors[i] = c;
+}
+
+int launch_mesh_normals(cudaStream_t stream, uint32_t n_verts, uint32_t n_tris, const uint32_t* indices, const float* verts, float* normals) {
+	CUDA_CHECK(cudaMemsetAsync(normals, 0, (size_t)n_verts * 3 * sizeof(float), stream));
+	if (n_tris) { k_mesh_vertex_normals<<<(n_tris + 255) / 256, 256, 0, stream>>>(n_tris, indices, verts, normals); COUNT_LAUNCH(1); }
+	CUDA_CHECK(cudaGetLastError());
+	return 0;
+}
+int launch_mesh_color_inputs(cudaStream_t stream, uint32_t n_verts, const float* verts, const Aabb& train_aabb, float* coords) {
+	if (n_verts) { k_mesh_color_inputs<<<(n_verts + 255) / 256, 256, 0, stream>>>(n_verts, verts, train_aabb, coords); COUNT_LAUNCH(1); }
+	CUDA_CHECK(cudaGetLastError());
+	return 0;
+}
+int launch_mesh_extract_colors(cudaStream_t stream, uint32_t n_verts, const __half* out16, int from_linear, float* colors) {
+	if (n_verts) { k_mesh_extract_colors<<<(n_verts * 3 + 255) / 256, 256, 0, stream>>>(n_verts, out16, from_linear, colors); COUNT_LAUNCH(1); }
+	CUDA_CHECK(cudaGetLastError());
+	return 0;
+}

@@ -70,3 +70,6 @@ uint32_t marching_cubes_blocks(const uint32_t res[3]);
 int launch_marching_cubes_count(cudaStream_t stream, const uint32_t res[3], float thresh, const float* density, uint32_t* block_counts, uint32_t* counts_dev);
 int launch_marching_cubes_emit(cudaStream_t stream, const uint32_t res[3], const Aabb& aabb, float thresh, const float* density, const uint32_t* block_offsets,
                                uint32_t n_verts, uint32_t n_indices, uint32_t* vert_prefix, float* verts, uint32_t* indices);
+int launch_mesh_normals(cudaStream_t stream, uint32_t n_verts, uint32_t n_tris, const uint32_t* indices, const float* verts, float* normals);
+int launch_mesh_color_inputs(cudaStream_t stream, uint32_t n_verts, const float* verts, const Aabb& train_aabb, float* coords);
+int launch_mesh_extract_colors(cudaStream_t stream, uint32_t n_verts, const __half* out16, int from_linear, float* colors);
