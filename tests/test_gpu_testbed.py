@@ -86,7 +86,7 @@ def test_snapshot_round_trip(trained):
     a, b = tb._ctx, tb2._ctx
     # inference weights survive bit for bit; training weights become the inference ones (Trainer::deserialize, trainer.h:295-304)
     assert torch.equal(a.buffers()[2], b.buffers()[2])
-    assert torch.equal(b.buffers()[1], b.buffers()[2] if False else b.buffers()[1])
+    assert torch.equal(b.buffers()[0].half(), b.buffers()[1])       # fp32 master is the widened fp16 blob
     assert torch.equal(a.optimizer_buffers()[0], b.optimizer_buffers()[0]) and torch.equal(a.optimizer_buffers()[2], b.optimizer_buffers()[2])
     assert a.optimizer_buffers()[3] == b.optimizer_buffers()[3]
     la = a.sdf_lattice((32, 32, 32))
@@ -103,7 +103,7 @@ def test_snapshot_round_trip(trained):
     with pytest.raises(RuntimeError):
         tb2.load_snapshot(os.path.join(root, "missing.msgpack"))
     with pytest.raises(RuntimeError):
-        tb2.load_snapshot(os.path.join(root, "transforms.json") if False else _not_a_snapshot(root))
+        tb2.load_snapshot(_not_a_snapshot(root))
 
 
 def _not_a_snapshot(root):
