@@ -24,6 +24,7 @@ void neus_set_error(const char* msg, const char* file, int line) {
 	g_error = buf;
 }
 #define NEUS2_N_STAGES 8
+#define ADAM_BIAS_TABLE (1u << 20)
 enum { ST_GRID = 0, ST_GEN = 1, ST_FWD = 2, ST_LOSS = 3, ST_FWDBWD = 4, ST_WGRAD = 5, ST_OPT = 6, ST_STEP = 7 };
 #define FAIL(msg) do { neus_set_error(msg, __FILE__, __LINE__); return -1; } while (0)
 #define CHECK(x) do { if ((x) != 0) return -1; } while (0)
@@ -46,6 +47,7 @@ struct neus2_ctx {
 	// Trainer buffers
 	float* master; __half* params; __half* ema; float* grads; float* m1; float* m2; uint32_t* steps;
 	uint32_t adam_step;
+	float* adam_bias_table;     // sqrt(1-b2^k)/(1-b1^k) for per-parameter step counters k < ADAM_BIAS_TABLE (optimizer.cu)
 
 	// dataset
 	DatasetDev ds; uint8_t* d_pixels; float* d_focal; float* d_principal; float* d_xforms;
@@ -204,7 +206,7 @@ int neus2_ctx_create(const neus2_config* cfg, int device, neus2_ctx** out) {
 	const uint32_t B = ctx->B_local, R = ctx->max_rays, S = ctx->max_samples;
 	#define CTXCHECK(x) do { if ((x) != 0) { neus2_ctx_destroy(ctx); return -1; } } while (0)
 	#define CDM(ptr, count) CTXCHECK(dmalloc((void**)&(ptr), sizeof(*(ptr)) * (size_t)(count)))
-	CDM(ctx->master, N); CDM(ctx->params, N); CDM(ctx->ema, N); CDM(ctx->grads, N); CDM(ctx->m1, N); CDM(ctx->m2, N); CDM(ctx->steps, N);
+	CDM(ctx->master, N); CDM(ctx->params, N); CDM(ctx->ema, N); CDM(ctx->grads, N); CDM(ctx->m1, N); CDM(ctx->m2, N); CDM(ctx->steps, N); CDM(ctx->adam_bias_table, ADAM_BIAS_TABLE);
 	CDM(ctx->numsteps_all, R); CDM(ctx->base, R); CDM(ctx->slot, R); CDM(ctx->ray_indices, R); CDM(ctx->numsteps, 2 * (size_t)R); CDM(ctx->scan_tmp, 2 * (size_t)R);
 	CDM(ctx->n_windows, R); CDM(ctx->windows, sampling_window_bytes_per_ray() * (size_t)R); CDM(ctx->ray_setup, 12 * (size_t)R);
 	CDM(ctx->counters, 8); CDM(ctx->counts_global, 4); CDM(ctx->rays, 6 * (size_t)R); CDM(ctx->coords, 7 * (size_t)S); CDM(ctx->ray_tmp, 12 * (size_t)R);
@@ -235,7 +237,7 @@ int neus2_ctx_create(const neus2_config* cfg, int device, neus2_ctx** out) {
 
 void neus2_ctx_destroy(neus2_ctx* ctx) {
 	if (!ctx) return;
-	void* ptrs[] = {ctx->master, ctx->params, ctx->ema, ctx->grads, ctx->m1, ctx->m2, ctx->steps, ctx->d_pixels, ctx->d_focal, ctx->d_principal, ctx->d_xforms,
+	void* ptrs[] = {ctx->master, ctx->params, ctx->ema, ctx->grads, ctx->m1, ctx->m2, ctx->steps, ctx->adam_bias_table, ctx->d_pixels, ctx->d_focal, ctx->d_principal, ctx->d_xforms,
 		ctx->numsteps_all, ctx->base, ctx->slot, ctx->ray_indices, ctx->numsteps, ctx->scan_tmp, ctx->counters, ctx->n_windows, ctx->windows, ctx->ray_setup, ctx->rays, ctx->coords, ctx->ray_tmp,
 		ctx->coords_compacted, ctx->loss, ctx->ek_loss, ctx->mask_loss, ctx->mlp_out, ctx->dloss, ctx->counts_global, ctx->so.dOUT, ctx->so.H2, ctx->so.dH2, ctx->so.H1, ctx->so.dH1,
 		ctx->so.CIN, ctx->so.dSO, ctx->so.H0, ctx->so.dH0, ctx->so.X0, ctx->so.dI, ctx->partials, ctx->var_acc, ctx->w1row0_acc, ctx->scalar_tmp,
@@ -396,7 +398,7 @@ int neus2_optimizer_step(neus2_ctx* ctx, void* stream, float loss_scale) {
 	++ctx->adam_step;
 	stage_begin(ctx, ST_OPT, (cudaStream_t)stream);
 	const int rc_ = launch_adam_ema((cudaStream_t)stream, ctx->n_params, ctx->pl.off_grid, loss_scale, c.learning_rate, c.beta1, c.beta2, c.epsilon, c.l2_reg,
-	                       c.ema_decay, ctx->adam_step, ctx->grads, ctx->master, ctx->params, ctx->m1, ctx->m2, ctx->steps, ctx->ema);
+	                       c.ema_decay, ctx->adam_step, ctx->grads, ctx->master, ctx->params, ctx->m1, ctx->m2, ctx->steps, ctx->ema, ctx->adam_bias_table, ADAM_BIAS_TABLE);
 	stage_end(ctx, ST_OPT, (cudaStream_t)stream);
 	return rc_;
 }
@@ -785,7 +787,7 @@ int neus2_optimizer_step_sharded(neus2_ctx* ctx, void* stream, float loss_scale)
 	++ctx->adam_step;
 	stage_begin(ctx, ST_OPT, (cudaStream_t)stream);
 	const int rc_ = launch_adam_ema_p2p((cudaStream_t)stream, ctx->n_params, ctx->pl.off_grid, ctx->peer_rank, ctx->peer_world, loss_scale, c.learning_rate, c.beta1, c.beta2,
-	                                    c.epsilon, c.l2_reg, c.ema_decay, ctx->adam_step, ctx->peer_grads, ctx->peer_params, ctx->peer_ema, ctx->master, ctx->m1, ctx->m2, ctx->steps);
+	                                    c.epsilon, c.l2_reg, c.ema_decay, ctx->adam_step, ctx->peer_grads, ctx->peer_params, ctx->peer_ema, ctx->master, ctx->m1, ctx->m2, ctx->steps, ctx->adam_bias_table, ADAM_BIAS_TABLE);
 	stage_end(ctx, ST_OPT, (cudaStream_t)stream);
 	ctx->optimizer_done = true;
 	return rc_;
@@ -800,7 +802,13 @@ int neus2_optimizer_buffers(neus2_ctx* ctx, float** m1_dev, float** m2_dev, uint
 	return 0;
 }
 
-int neus2_set_optimizer_step(neus2_ctx* ctx, uint32_t current_step) { ctx->adam_step = current_step; return 0; }
+int neus2_set_optimizer_step(neus2_ctx* ctx, uint32_t current_step) {
+	CUDA_CHECK(cudaSetDevice(ctx->device));
+	ctx->adam_step = current_step;
+	CHECK(launch_adam_bias_table(nullptr, ctx->cfg.beta1, ctx->cfg.beta2, current_step, ctx->adam_bias_table, ADAM_BIAS_TABLE));
+	CUDA_CHECK(cudaDeviceSynchronize());
+	return 0;
+}
 
 // density_grid: n floats (128^3 per cascade); recomputes mean + bitfield like load_snapshot does (testbed.cu:3232-3236)
 int neus2_set_density_grid(neus2_ctx* ctx, void* stream_, const float* density_grid_host, uint64_t n, uint32_t ema_step) {

@@ -5,9 +5,23 @@
 #include "ngp_common.cuh"
 #include "ngp_kernels.h"
 
-struct AdamHyper { float loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, ema_debias_old, ema_debias_new; };
+struct AdamHyper { float loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, ema_debias_old, ema_debias_new;
+                   uint32_t cur_step; const float* bias_table; uint32_t bias_table_size; };
 
-__device__ __forceinline__ __half adam_one(bool is_matrix, float g_raw, const AdamHyper& h, float& w, float& m1, float& m2, uint32_t& step, __half p, bool& touched) {
+// Bias correction of adam_step (adam.h:149-150) for a parameter whose private step counter reads `cs`:
+// sqrt(1 - beta2^cs) / (1 - beta1^cs).  Two powf per parameter made the kernel issue-bound (83 % issue-active, 40 % of HBM peak
+// in the first ncu capture), so the factor is looked up instead: almost every touched parameter is on the CURRENT step
+// (computed once per thread), older counters index a table that k_adam_bias_table extends by one entry per step with the very
+// same expression -- identical bits, 8x fewer transcendental calls.
+__device__ __forceinline__ float adam_bias_factor(const AdamHyper& h, uint32_t cs) {
+	return sqrtf(1 - powf(h.beta2, (float)cs)) / (1 - powf(h.beta1, (float)cs));
+}
+__global__ void k_adam_bias_table(AdamHyper h, uint32_t first, uint32_t last, float* __restrict__ table) {
+	const uint32_t cs = first + blockIdx.x * blockDim.x + threadIdx.x;
+	if (cs <= last) table[cs] = adam_bias_factor(h, cs);
+}
+
+__device__ __forceinline__ __half adam_one(bool is_matrix, float g_raw, const AdamHyper& h, float cur_factor, float& w, float& m1, float& m2, uint32_t& step, __half p, bool& touched) {
 	float gradient = g_raw / h.loss_scale;
 	touched = false;
 	if (is_matrix || gradient != 0) {            // adam.h:109-112: non-matrix params with zero gradient are skipped entirely
@@ -19,7 +33,7 @@ __device__ __forceinline__ __half adam_one(bool is_matrix, float g_raw, const Ad
 		m1 = fm; m2 = sm;
 		float learning_rate = h.lr;
 		const uint32_t cs = ++step;
-		learning_rate *= sqrtf(1 - powf(h.beta2, (float)cs)) / (1 - powf(h.beta1, (float)cs));
+		learning_rate *= cs == h.cur_step ? cur_factor : (cs < h.bias_table_size ? h.bias_table[cs] : adam_bias_factor(h, cs));
 		const float eff = fminf(fmaxf(learning_rate / (sqrtf(sm) + h.eps), 0.f), 3.402823466e+38f);
 		const float decayed = (1 - 0.f * learning_rate) * w - copysignf(0.f * learning_rate, w);
 		const float nw = decayed - eff * fm;
@@ -43,6 +57,7 @@ k_adam_ema(uint64_t n4, uint64_t n_matrix4, AdamHyper h, const float* __restrict
 	__half* ph = reinterpret_cast<__half*>(&pw);
 	const float g[4] = {g4.x, g4.y, g4.z, g4.w};
 	if (is_matrix || g4.x != 0.f || g4.y != 0.f || g4.z != 0.f || g4.w != 0.f) {
+		const float cur_factor = adam_bias_factor(h, h.cur_step);
 		float4 w4 = reinterpret_cast<const float4*>(master)[q];
 		float4 a4 = reinterpret_cast<const float4*>(m1)[q];
 		float4 b4 = reinterpret_cast<const float4*>(m2)[q];
@@ -53,7 +68,7 @@ k_adam_ema(uint64_t n4, uint64_t n_matrix4, AdamHyper h, const float* __restrict
 		#pragma unroll
 		for (int k = 0; k < 4; ++k) {
 			bool touched;
-			ph[k] = adam_one(is_matrix, g[k], h, w[k], a[k], b[k], st[k], ph[k], touched);
+			ph[k] = adam_one(is_matrix, g[k], h, cur_factor, w[k], a[k], b[k], st[k], ph[k], touched);
 			any |= touched;
 		}
 		if (any) {
@@ -75,11 +90,13 @@ k_adam_ema(uint64_t n4, uint64_t n_matrix4, AdamHyper h, const float* __restrict
 }
 
 int launch_adam_ema(cudaStream_t stream, uint64_t n, uint64_t n_matrix, float loss_scale, float lr, float beta1, float beta2, float eps, float l2_reg,
-                    float ema_decay, uint32_t ema_step, const float* grads, float* master, __half* params, float* m1, float* m2, uint32_t* steps, __half* ema) {
+                    float ema_decay, uint32_t ema_step, const float* grads, float* master, __half* params, float* m1, float* m2, uint32_t* steps, __half* ema,
+                    float* bias_table, uint32_t bias_table_size) {
 	const float ema_debias_old = 1 - (float)pow((double)ema_decay, (double)(ema_step - 1));
 	const float ema_debias_new = 1.0f / (1 - (float)pow((double)ema_decay, (double)ema_step));
 	if (n % 4 != 0 || n_matrix % 4 != 0) { neus_set_error("parameter counts must be multiples of 4", __FILE__, __LINE__); return -1; }
-	AdamHyper h = {loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, ema_debias_old, ema_debias_new};
+	AdamHyper h = {loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, ema_debias_old, ema_debias_new, ema_step, bias_table, bias_table_size};
+	if (bias_table && ema_step < bias_table_size) { k_adam_bias_table<<<1, 32, 0, stream>>>(h, ema_step, ema_step, bias_table); COUNT_LAUNCH(1); }
 	const uint64_t n4 = n / 4;
 	const uint32_t blocks = (uint32_t)((n4 + 255) / 256);
 	k_adam_ema<<<blocks, 256, 0, stream>>>(n4, n_matrix / 4, h, grads, master, params, m1, m2, steps, ema);
@@ -115,6 +132,7 @@ k_adam_ema_p2p(uint64_t q0, uint64_t q1, uint64_t n_matrix4, AdamHyper h, int wo
 	__half* ph = reinterpret_cast<__half*>(&pw);
 	const float g[4] = {g4.x, g4.y, g4.z, g4.w};
 	if (is_matrix || g4.x != 0.f || g4.y != 0.f || g4.z != 0.f || g4.w != 0.f) {
+		const float cur_factor = adam_bias_factor(h, h.cur_step);
 		float4 w4 = reinterpret_cast<const float4*>(master)[q];
 		float4 a4 = reinterpret_cast<const float4*>(m1)[q];
 		float4 b4 = reinterpret_cast<const float4*>(m2)[q];
@@ -125,7 +143,7 @@ k_adam_ema_p2p(uint64_t q0, uint64_t q1, uint64_t n_matrix4, AdamHyper h, int wo
 		#pragma unroll
 		for (int k = 0; k < 4; ++k) {
 			bool touched;
-			ph[k] = adam_one(is_matrix, g[k], h, w[k], a[k], b[k], st[k], ph[k], touched);
+			ph[k] = adam_one(is_matrix, g[k], h, cur_factor, w[k], a[k], b[k], st[k], ph[k], touched);
 			any |= touched;
 		}
 		if (any) {
@@ -150,12 +168,13 @@ k_adam_ema_p2p(uint64_t q0, uint64_t q1, uint64_t n_matrix4, AdamHyper h, int wo
 
 int launch_adam_ema_p2p(cudaStream_t stream, uint64_t n, uint64_t n_matrix, uint32_t rank, uint32_t world, float loss_scale, float lr, float beta1, float beta2,
                         float eps, float l2_reg, float ema_decay, uint32_t ema_step, const float* const* grads_peers, __half* const* params_peers,
-                        __half* const* ema_peers, float* master, float* m1, float* m2, uint32_t* steps) {
+                        __half* const* ema_peers, float* master, float* m1, float* m2, uint32_t* steps, float* bias_table, uint32_t bias_table_size) {
 	const float ema_debias_old = 1 - (float)pow((double)ema_decay, (double)(ema_step - 1));
 	const float ema_debias_new = 1.0f / (1 - (float)pow((double)ema_decay, (double)ema_step));
 	if (n % 4 != 0 || n_matrix % 4 != 0) { neus_set_error("parameter counts must be multiples of 4", __FILE__, __LINE__); return -1; }
 	if (world < 1 || world > NEUS2_MAX_PEERS || rank >= world) { neus_set_error("bad rank / world size for the sharded optimizer", __FILE__, __LINE__); return -1; }
-	AdamHyper h = {loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, ema_debias_old, ema_debias_new};
+	AdamHyper h = {loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, ema_debias_old, ema_debias_new, ema_step, bias_table, bias_table_size};
+	if (bias_table && ema_step < bias_table_size) { k_adam_bias_table<<<1, 32, 0, stream>>>(h, ema_step, ema_step, bias_table); COUNT_LAUNCH(1); }
 	uint64_t q0, q1;
 	optimizer_shard(n / 4, rank, world, &q0, &q1);
 	PeerPtrs pp;
@@ -178,4 +197,15 @@ void optimizer_shard(uint64_t n_quads, uint32_t rank, uint32_t world, uint64_t* 
 	const uint64_t base = n_quads / world, extra = n_quads % world;
 	*q0 = rank * base + (rank < extra ? rank : extra);
 	*q1 = *q0 + base + (rank < extra ? 1 : 0);
+}
+
+// (re)build the bias-correction table for counters 1..last (after a snapshot restore)
+int launch_adam_bias_table(cudaStream_t stream, float beta1, float beta2, uint32_t last, float* bias_table, uint32_t bias_table_size) {
+	if (!bias_table || !bias_table_size || !last) return 0;
+	if (last >= bias_table_size) last = bias_table_size - 1;
+	AdamHyper h = {}; h.beta1 = beta1; h.beta2 = beta2;
+	k_adam_bias_table<<<(last + 255) / 256, 256, 0, stream>>>(h, 1, last, bias_table);
+	COUNT_LAUNCH(1);
+	CUDA_CHECK(cudaGetLastError());
+	return 0;
 }
