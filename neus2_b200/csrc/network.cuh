@@ -173,6 +173,10 @@ __device__ __forceinline__ void store_a_global(const uint32_t (&a)[KT][4], __hal
 // ---- hash grid ----------------------------------------------------------------------------------
 // grid.h:119-153 with the per-level "hashed" decision hoisted to the host (GridMeta.hashed semantics:
 // hashed <=> res^3 > hashmap_size).
+// general wrap of a dense index (grid.h:146: index % hashmap_size) -- out of line: for positions inside [0,1] the dense index is
+// below 2 * hashmap_size and the caller's single conditional subtract is the whole story
+static __device__ __noinline__ uint32_t grid_index_wrap(uint32_t index, uint32_t hashmap_size) { return index % hashmap_size; }
+
 __device__ __forceinline__ uint32_t grid_index(bool hashed, uint32_t hashmap_size, uint32_t res, uint32_t x, uint32_t y, uint32_t z) {
 	uint32_t index;
 	if (hashed) {
@@ -180,11 +184,9 @@ __device__ __forceinline__ uint32_t grid_index(bool hashed, uint32_t hashmap_siz
 		return (index & (hashmap_size - 1u)) * 2u;   // hashed levels have power-of-two size (2^log2_hashmap_size)
 	}
 	index = x + y * res + z * res * res;
-	// index % hashmap_size: for positions in [0,1] the dense index is < 2*hashmap_size, so one conditional subtract
-	// replaces the integer division; anything else (out-of-range inputs) takes the general path.
 	if (index >= hashmap_size) {
 		index -= hashmap_size;
-		if (index >= hashmap_size) index %= hashmap_size;
+		if (index >= hashmap_size) index = grid_index_wrap(index, hashmap_size);
 	}
 	return index * 2u;
 }

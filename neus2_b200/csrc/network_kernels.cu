@@ -11,18 +11,25 @@ static constexpr int FWD_SMEM = WeightSmem::FWD_END * 2 + WARPS_PER_CTA * WarpSl
 #define WARPS_BWD 12
 static constexpr int BWD_SMEM = WeightSmem::BWD_END * 2 + WARPS_BWD * WarpSlab::BWD_END;
 
-// coalesced load of a tile's coords (16 x 7 floats) into the warp slab; rows >= n_valid are zero-filled.
-// src_row(i) maps tile row -> source row (identity, or the fill_rollover wrap).
-__device__ __forceinline__ void load_coords(float* sCoord, const float* __restrict__ coords, uint32_t row0, uint32_t n, uint32_t wrap, int lane) {
-	for (int i = lane; i < 16 * 7; i += 32) {
+// A tile's coords (16 x 7 floats) travel global -> registers -> warp slab: the loads for the NEXT tile are issued before the
+// current tile is processed, so their HBM latency hides behind a whole tile of work.  Rows >= n are zero-filled; `wrap` maps
+// tile row -> source row (0 = identity, else r % wrap: the fill_rollover wrap).
+__device__ __forceinline__ void prefetch_coords(float (&cr)[4], const float* __restrict__ coords, uint32_t row0, uint32_t n, uint32_t wrap, int lane) {
+	#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		const int i = lane + 32 * k;
 		const uint32_t r = row0 + i / 7;
 		float v = 0.f;
-		if (r < n) {
+		if (i < 16 * 7 && r < n) {
 			const uint32_t src = wrap ? (r % wrap) : r;
 			v = coords[(size_t)src * 7 + (i % 7)];
 		}
-		sCoord[i] = v;
+		cr[k] = v;
 	}
+}
+__device__ __forceinline__ void store_coords(float* sCoord, const float (&cr)[4], int lane) {
+	#pragma unroll
+	for (int k = 0; k < 4; ++k) { const int i = lane + 32 * k; if (i < 16 * 7) sCoord[i] = cr[k]; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -42,10 +49,14 @@ k_network_forward(GridMeta gm, ParamLayout pl, const __half* __restrict__ params
 	if (n > n_max) n = n_max;
 	const uint32_t n_tiles = (n + TILE - 1) / TILE;
 	FwdState st;
-	for (uint32_t tile = blockIdx.x * WARPS_PER_CTA + warp; tile < n_tiles; tile += gridDim.x * WARPS_PER_CTA) {
+	float cr[4];
+	const uint32_t tile0 = blockIdx.x * WARPS_PER_CTA + warp, tile_stride = gridDim.x * WARPS_PER_CTA;
+	if (tile0 < n_tiles) prefetch_coords(cr, coords, tile0 * TILE, n, 0, lane);
+	for (uint32_t tile = tile0; tile < n_tiles; tile += tile_stride) {
 		const uint32_t row0 = tile * TILE;
-		load_coords(reinterpret_cast<float*>(slab + WarpSlab::COORD), coords, row0, n, 0, lane);
+		store_coords(reinterpret_cast<float*>(slab + WarpSlab::COORD), cr, lane);
 		__syncwarp();
+		if (tile + tile_stride < n_tiles) prefetch_coords(cr, coords, (tile + tile_stride) * TILE, n, 0, lane);
 		forward_tile<false>(gm, params, pl, sw, slab, sdf_bias, lane, st);
 		// 16 rows x 32 B, coalesced 16-byte stores
 		const uint32_t r = row0 + (lane >> 1);
@@ -145,21 +156,36 @@ k_network_fwdbwd(GridMeta gm, ParamLayout pl, const __half* __restrict__ params,
 	const int E = 2 * (int)gm.n_levels;
 
 	FwdState st;
-	for (uint32_t tile = blockIdx.x * WARPS_BWD + warp; tile < n_tiles; tile += gridDim.x * WARPS_BWD) {
+	float cr[4];
+	uint32_t dlr[4];   // the tile's dL/dout rows (16 x 16 halves = 128 words), 4 words per lane, prefetched like the coords
+	auto prefetch_dl = [&](uint32_t row0) {
+		#pragma unroll
+		for (int k = 0; k < 4; ++k) {
+			const int w = lane + 32 * k;                       // word w: row w >> 3, halves 2 * (w & 7), +1
+			const uint32_t r = row0 + (w >> 3);
+			dlr[k] = r < n_rows ? reinterpret_cast<const uint32_t*>(dL_dout)[(size_t)(r < n_in ? r : r % n_in) * 8 + (w & 7)] : 0u;
+		}
+	};
+	const uint32_t tile0 = blockIdx.x * WARPS_BWD + warp, tile_stride = gridDim.x * WARPS_BWD;
+	if (tile0 < n_tiles) { prefetch_coords(cr, coords, tile0 * TILE, n_rows, n_in, lane); prefetch_dl(tile0 * TILE); }
+	for (uint32_t tile = tile0; tile < n_tiles; tile += tile_stride) {
 		const uint32_t row0 = tile * TILE;
 		const int n_valid = (int)min((uint32_t)TILE, n_rows - row0);
-		load_coords(sCoord, coords, row0, n_rows, n_in, lane);
+		store_coords(sCoord, cr, lane);
 		// dL/dout rows with the rollover wrap + rescale (fill_rollover_and_rescale)
-		for (int i = lane; i < 16 * 16; i += 32) {
-			const uint32_t r = row0 + (i >> 4);
-			__half v = __float2half(0.f);
-			if (r < n_rows) {
-				if (r < n_in) v = dL_dout[(size_t)r * 16 + (i & 15)];
-				else v = __float2half_rn(__fdiv_rn(__fmul_rn(__half2float(dL_dout[(size_t)(r % n_in) * 16 + (i & 15)]), wrap_scale_num), wrap_scale_den));
+		#pragma unroll
+		for (int k = 0; k < 4; ++k) {
+			const int w = lane + 32 * k;
+			const uint32_t r = row0 + (w >> 3);
+			uint32_t v = dlr[k];
+			if (r < n_rows && r >= n_in) {
+				const float lo = __fdiv_rn(__fmul_rn(h_lo(v), wrap_scale_num), wrap_scale_den), hi = __fdiv_rn(__fmul_rn(h_hi(v), wrap_scale_num), wrap_scale_den);
+				v = pack_h2(lo, hi);
 			}
-			sDL[i] = v;
+			reinterpret_cast<uint32_t*>(sDL)[w] = v;
 		}
 		__syncwarp();
+		if (tile + tile_stride < n_tiles) { prefetch_coords(cr, coords, (tile + tile_stride) * TILE, n_rows, n_in, lane); prefetch_dl((tile + tile_stride) * TILE); }
 		forward_tile<true>(gm, params, pl, sw, slab, sdf_bias, lane, st);
 
 		// ---- colour MLP backward (fully_fused_mlp.cu:968-1085) -----------------------------------

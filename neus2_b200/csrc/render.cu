@@ -25,8 +25,19 @@
 static constexpr int RENDER_SMEM = WeightSmem::FWD_END * 2 + RENDER_WARPS * WarpSlab::FWD_END;
 
 // ---- low-discrepancy sequence (random_val.cuh:169-322): Sobol dims 0/1 from their generating recurrences -------------
-__device__ __forceinline__ uint32_t sobol_dim(uint32_t index, uint32_t dim) {
-	if (dim == 0) return __brev(index);
+__host__ __device__ __forceinline__ uint32_t brev32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+	return __brev(x);
+#else
+	x = ((x & 0xaaaaaaaau) >> 1) | ((x & 0x55555555u) << 1);
+	x = ((x & 0xccccccccu) >> 2) | ((x & 0x33333333u) << 2);
+	x = ((x & 0xf0f0f0f0u) >> 4) | ((x & 0x0f0f0f0fu) << 4);
+	x = ((x & 0xff00ff00u) >> 8) | ((x & 0x00ff00ffu) << 8);
+	return (x >> 16) | (x << 16);
+#endif
+}
+__host__ __device__ __forceinline__ uint32_t sobol_dim(uint32_t index, uint32_t dim) {
+	if (dim == 0) return brev32(index);
 	uint32_t X = 0, v = 0x80000000u;
 	#pragma unroll
 	for (uint32_t bit = 0; bit < 32; ++bit) {
@@ -35,8 +46,8 @@ __device__ __forceinline__ uint32_t sobol_dim(uint32_t index, uint32_t dim) {
 	}
 	return X;
 }
-__device__ __forceinline__ uint32_t hash_combine(uint32_t seed, uint32_t v) { return seed ^ (v + (seed << 6) + (seed >> 2)); }
-__device__ __forceinline__ uint32_t laine_karras_permutation(uint32_t x, uint32_t seed) {
+__host__ __device__ __forceinline__ uint32_t hash_combine(uint32_t seed, uint32_t v) { return seed ^ (v + (seed << 6) + (seed >> 2)); }
+__host__ __device__ __forceinline__ uint32_t laine_karras_permutation(uint32_t x, uint32_t seed) {
 	x += seed;
 	x ^= x * 0x6c50b47cu;
 	x ^= x * 0xb82f1e52u;
@@ -44,12 +55,12 @@ __device__ __forceinline__ uint32_t laine_karras_permutation(uint32_t x, uint32_
 	x ^= x * 0x8d22f6e6u;
 	return x;
 }
-__device__ __forceinline__ uint32_t nested_uniform_scramble_base2(uint32_t x, uint32_t seed) { return __brev(laine_karras_permutation(__brev(x), seed)); }
+__host__ __device__ __forceinline__ uint32_t nested_uniform_scramble_base2(uint32_t x, uint32_t seed) { return brev32(laine_karras_permutation(brev32(x), seed)); }
 __device__ __forceinline__ float ld_random_val(uint32_t index, uint32_t seed) {
 	index = nested_uniform_scramble_base2(index, seed);
 	return (float)nested_uniform_scramble_base2(sobol_dim(index, 0), hash_combine(seed, 0)) * 2.3283064365386963e-10f;   // 2^-32
 }
-__device__ __forceinline__ void ld_random_val_2d(uint32_t index, uint32_t seed, float out[2]) {
+__host__ __device__ __forceinline__ void ld_random_val_2d(uint32_t index, uint32_t seed, float out[2]) {
 	index = nested_uniform_scramble_base2(index, seed);
 	out[0] = (float)nested_uniform_scramble_base2(sobol_dim(index, 0), hash_combine(seed, 0)) * 2.3283064365386963e-10f;
 	out[1] = (float)nested_uniform_scramble_base2(sobol_dim(index, 1), hash_combine(seed, 1)) * 2.3283064365386963e-10f;
@@ -59,8 +70,8 @@ struct RenderView {
 	int32_t width, height;
 	float focal[2], screen_center[2];
 	float camera[12];
+	float pixel_offset[2];      // ld_random_pixel_offset(snap ? 0 : spp): the same for every pixel of a frame, evaluated once on the host (integer + exact float ops)
 	uint32_t sample_index;
-	int32_t snap_to_pixel_centers;
 	int32_t x0, y0, w, h;       // tile
 };
 
@@ -80,14 +91,7 @@ k_render_init(RenderView v, Aabb render_aabb, GlobalMove gmv, const uint8_t* __r
 		const int px = v.x0 + (int)(tp % (uint32_t)v.w), py = v.y0 + (int)(tp / (uint32_t)v.w);
 		const uint32_t idx = (uint32_t)px + (uint32_t)v.width * (uint32_t)py;
 		// pixel_to_ray (common_device.cuh:246-299)
-		float off[2];
-		{
-			float a[2], b[2];
-			ld_random_val_2d(0, 0xdeadbeefu, a);
-			ld_random_val_2d(v.snap_to_pixel_centers ? 0u : v.sample_index, 0xdeadbeefu, b);
-			#pragma unroll
-			for (int k = 0; k < 2; ++k) { const float o = (0.5f - a[k]) + b[k]; off[k] = o - floorf(o); }
-		}
+		const float off[2] = {v.pixel_offset[0], v.pixel_offset[1]};
 		const float uv[2] = {((float)px + off[0]) / (float)v.width, ((float)py + off[1]) / (float)v.height};
 		const float dl[3] = {(uv[0] - v.screen_center[0]) * (float)v.width / v.focal[0], (uv[1] - v.screen_center[1]) * (float)v.height / v.focal[1], 1.0f};
 		float o[3], du[3], d[3];
@@ -291,7 +295,13 @@ int launch_render(cudaStream_t stream, const GridMeta& gm, const ParamLayout& pl
 	v.width = r.width; v.height = r.height;
 	v.focal[0] = r.focal[0]; v.focal[1] = r.focal[1]; v.screen_center[0] = r.screen_center[0]; v.screen_center[1] = r.screen_center[1];
 	for (int k = 0; k < 12; ++k) v.camera[k] = r.camera[k];
-	v.sample_index = r.sample_index; v.snap_to_pixel_centers = r.snap_to_pixel_centers;
+	v.sample_index = r.sample_index;
+	{   // ld_random_pixel_offset (random_val.cuh:316-321)
+		float a[2], b[2];
+		ld_random_val_2d(0, 0xdeadbeefu, a);
+		ld_random_val_2d(r.snap_to_pixel_centers ? 0u : r.sample_index, 0xdeadbeefu, b);
+		for (int k = 0; k < 2; ++k) { const float o = (0.5f - a[k]) + b[k]; v.pixel_offset[k] = o - floorf(o); }
+	}
 	v.x0 = r.tile_x0; v.y0 = r.tile_y0; v.w = r.tile_w; v.h = r.tile_h;
 	CUDA_CHECK(cudaMemsetAsync(counters, 0, 4 * sizeof(uint32_t), stream));
 	k_render_init<<<(n + 127) / 128, 128, 0, stream>>>(v, render_aabb, gmv, bitfield, cone_angle, (RayPayload*)queue, counters, (float4*)ray_rgba, ray_depth);
