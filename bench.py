@@ -296,6 +296,21 @@ def main():
         rows = (1 << 18)
         alg_bytes = rows * (508 + 1376)        # 508 B/sample forward + ~1.4 KB/sample backward (algorithmic minimum)
         achieved = alg_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        # the hash-grid tables (21 MB fp16) and their gradients (42 MB fp32) live in L2, so the honest ceiling for the gather /
+        # scatter part is what L2 sustains for those access patterns (tools/l2_microbench.cu, measured on this pool's B200)
+        l2 = {}
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_l2_microbench.json")) as f:
+                mb = json.load(f)
+            gathers_fwd = (n_u / K) * 14 * 8
+            gathers_bwd, reds_bwd = rows * 14 * 8, rows * 14 * 8
+            floor_bwd_ms = (gathers_bwd / mb["gather4B_hash_corners_Gops"] + reds_bwd / mb["red_v2f32_random_Gops"]) * 1e-6
+            l2 = {"forward_gather_Gops": gathers_fwd / (stages["forward"][0] * 1e6), "gather_ceiling_Gops": mb["gather4B_hash_corners_Gops"],
+                  "gather_ceiling_random_Gops": mb["gather4B_random_Gops"], "forward_frac_of_ceiling": gathers_fwd / (stages["forward"][0] * 1e6) / mb["gather4B_hash_corners_Gops"],
+                  "fwdbwd_l2_floor_ms": floor_bwd_ms, "fwdbwd_frac_of_l2_floor": floor_bwd_ms / dom_ms if dom_ms > 0 else None,
+                  "source": "profiles/r01_l2_microbench.json (random 4-byte gathers over 16 MiB / 8-byte vector reductions over 32 MiB, both L2-resident)"}
+        except Exception:
+            pass
         line = {
             "metric": "NeuS training rays/s (base.json)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
@@ -305,7 +320,8 @@ def main():
                     "note": "wall clock through Context.train_step(); dataset upload from pinned host memory amortised over the 2000-step schedule"},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "k_network_fwdbwd", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes, "avg_launch_ms": dom_ms},
+                         "traffic": 422.4e6, "traffic_source": "profiles/r01_captureB.md: dram__bytes_read 111.6 MB + dram__bytes_write 310.8 MB per launch (ncu --set full)",
+                         "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes, "avg_launch_ms": dom_ms, "l2": l2},
             "stage_ms": {k: round(v[0], 4) for k, v in stages.items()},
             "per_step": {"rays": rays / K, "samples_before_compaction": n_u / K, "samples_compacted": n_c / K, "training_step": int(st.training_step)},
         }
