@@ -33,6 +33,23 @@ extern unsigned long long g_neus_launches;   // kernels launched by this library
 
 #ifdef __CUDACC__
 
+// cudaFuncSetAttribute is per DEVICE: a process that drives several GPUs (one context each) must opt every device in.
+#define NEUS_MAX_DEVICES 64
+template <typename K>
+static inline int ensure_dynamic_smem(K kernel, int bytes, bool (&done)[NEUS_MAX_DEVICES]) {
+	int dev = 0;
+	CUDA_CHECK(cudaGetDevice(&dev));
+	if (dev < 0 || dev >= NEUS_MAX_DEVICES) { neus_set_error("device index out of range", __FILE__, __LINE__); return -1; }
+	if (!done[dev]) { CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); done[dev] = true; }
+	return 0;
+}
+static inline int device_sm_count() {
+	int dev = 0, sms = 0;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	return sms;
+}
+
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 	__half2 h = __floats2half2_rn(a, b);
 	return *reinterpret_cast<uint32_t*>(&h);

@@ -61,12 +61,11 @@ k_sdf_lattice(GridMeta gm, ParamLayout pl, const __half* __restrict__ params, fl
 
 int launch_sdf_lattice(cudaStream_t stream, const GridMeta& gm, const ParamLayout& pl, const __half* params, float sdf_bias, const uint32_t res[3],
                        const Aabb& render_aabb, const Aabb& train_aabb, uint32_t z0, uint32_t z1, float* out) {
-	static bool attr = false;
-	if (!attr) { CUDA_CHECK(cudaFuncSetAttribute(k_sdf_lattice, cudaFuncAttributeMaxDynamicSharedMemorySize, LATTICE_SMEM)); attr = true; }
+	static bool attr[NEUS_MAX_DEVICES] = {};
+	if (ensure_dynamic_smem(k_sdf_lattice, LATTICE_SMEM, attr)) return -1;
 	if (z1 <= z0) return 0;
 	const uint64_t n = (uint64_t)res[0] * res[1] * (z1 - z0);
-	int dev = 0, sms = 0;
-	cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	const int sms = device_sm_count();
 	uint64_t grid = (uint64_t)sms * 2;
 	const uint64_t need = ((n + TILE - 1) / TILE + LATTICE_WARPS - 1) / LATTICE_WARPS;
 	if (need < grid) grid = need;

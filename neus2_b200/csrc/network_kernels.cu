@@ -404,16 +404,12 @@ k_network_fwdbwd(GridMeta gm, ParamLayout pl, const __half* __restrict__ params,
 // ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
-static int g_num_sms = 0;
-static int num_sms() {
-	if (!g_num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev); }
-	return g_num_sms;
-}
+static int num_sms() { return device_sm_count(); }
 
 int launch_network_forward(cudaStream_t stream, const GridMeta& gm, const ParamLayout& pl, const __half* params, const float* coords,
                            const uint32_t* n_ptr, uint32_t n_max, float sdf_bias, __half* out) {
-	static bool attr = false;
-	if (!attr) { CUDA_CHECK(cudaFuncSetAttribute(k_network_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM)); attr = true; }
+	static bool attr[NEUS_MAX_DEVICES] = {};
+	if (ensure_dynamic_smem(k_network_forward, FWD_SMEM, attr)) return -1;
 	if (n_max == 0) return 0;
 	const uint32_t n_tiles = (n_max + TILE - 1) / TILE;
 	uint32_t grid = (uint32_t)num_sms() * 2;
@@ -427,8 +423,8 @@ int launch_network_forward(cudaStream_t stream, const GridMeta& gm, const ParamL
 
 int launch_network_sdf(cudaStream_t stream, const GridMeta& gm, const ParamLayout& pl, const __half* params, const float* pos, uint32_t stride,
                        uint32_t n, float sdf_bias, int as_density, __half* out_h, float* out_f) {
-	static bool attr = false;
-	if (!attr) { CUDA_CHECK(cudaFuncSetAttribute(k_network_sdf, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM)); attr = true; }
+	static bool attr[NEUS_MAX_DEVICES] = {};
+	if (ensure_dynamic_smem(k_network_sdf, FWD_SMEM, attr)) return -1;
 	if (n == 0) return 0;
 	const uint32_t n_tiles = (n + TILE - 1) / TILE;
 	uint32_t grid = (uint32_t)num_sms() * 2;
@@ -443,8 +439,8 @@ int launch_network_sdf(cudaStream_t stream, const GridMeta& gm, const ParamLayou
 int launch_network_fwdbwd(cudaStream_t stream, const GridMeta& gm, const ParamLayout& pl, const __half* params, const float* coords,
                           const __half* dL_dout, const uint32_t* n_in_ptr, uint32_t n_rows, float sdf_bias, uint32_t indeed_batch_size,
                           float* grads, float* var_acc, float* w1row0_acc, const StagedOperands& so) {
-	static bool attr = false;
-	if (!attr) { CUDA_CHECK(cudaFuncSetAttribute(k_network_fwdbwd, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM)); attr = true; }
+	static bool attr[NEUS_MAX_DEVICES] = {};
+	if (ensure_dynamic_smem(k_network_fwdbwd, BWD_SMEM, attr)) return -1;
 	if (n_rows == 0) return 0;
 	const uint32_t n_tiles = (n_rows + TILE - 1) / TILE;
 	uint32_t grid = (uint32_t)num_sms();

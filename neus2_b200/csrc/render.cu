@@ -287,8 +287,8 @@ k_render_finish(uint32_t n, const float4* __restrict__ ray_rgba, const float* __
 int launch_render(cudaStream_t stream, const GridMeta& gm, const ParamLayout& pl, const __half* params, float sdf_bias, const RenderLaunch& r,
                   const Aabb& render_aabb, const Aabb& train_aabb, const GlobalMove& gmv, const uint8_t* bitfield, float cone_angle, float cos_anneal_ratio,
                   void* queue, uint32_t* counters, float* ray_rgba, float* ray_depth, uint32_t* ray_samples, float* accumulate, float* out, float* depth_out) {
-	static bool attr = false;
-	if (!attr) { CUDA_CHECK(cudaFuncSetAttribute(k_render_march, cudaFuncAttributeMaxDynamicSharedMemorySize, RENDER_SMEM)); attr = true; }
+	static bool attr[NEUS_MAX_DEVICES] = {};
+	if (ensure_dynamic_smem(k_render_march, RENDER_SMEM, attr)) return -1;
 	const uint32_t n = (uint32_t)r.tile_w * (uint32_t)r.tile_h;
 	if (n == 0) return 0;
 	RenderView v;
@@ -305,8 +305,7 @@ int launch_render(cudaStream_t stream, const GridMeta& gm, const ParamLayout& pl
 	v.x0 = r.tile_x0; v.y0 = r.tile_y0; v.w = r.tile_w; v.h = r.tile_h;
 	CUDA_CHECK(cudaMemsetAsync(counters, 0, 4 * sizeof(uint32_t), stream));
 	k_render_init<<<(n + 127) / 128, 128, 0, stream>>>(v, render_aabb, gmv, bitfield, cone_angle, (RayPayload*)queue, counters, (float4*)ray_rgba, ray_depth);
-	int dev = 0, sms = 0;
-	cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	const int sms = device_sm_count();
 	k_render_march<<<sms * 2, RENDER_WARPS * 32, RENDER_SMEM, stream>>>(gm, pl, params, sdf_bias, render_aabb, train_aabb, bitfield, cone_angle, cos_anneal_ratio,
 		r.min_transmittance, r.camera[2], r.camera[6], r.camera[10], r.camera[3], r.camera[7], r.camera[11],
 		(const RayPayload*)queue, counters, (float4*)ray_rgba, ray_depth, ray_samples);
