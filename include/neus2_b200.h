@@ -57,6 +57,9 @@ typedef struct neus2_config {
 	/* data-parallel build-out (not in the reference, which is single-GPU): buffers are sized for this rank's share */
 	uint32_t world_size;             /* 1 */
 	uint32_t max_rays_per_batch;     /* 1<<18 (testbed_nerf.cu:3435); raise to world_size<<18 for weak scaling */
+	/* 1 (default): the step's first network pass stops along each ray where the loss stops reading (T < 1e-4, testbed_nerf.cu:1567);
+	 * 0: evaluate every marched sample like the reference.  Same loss, gradients and counters either way (tests/test_gpu_step.py). */
+	int32_t forward_early_termination;
 } neus2_config;
 
 typedef struct neus2_step_stats {

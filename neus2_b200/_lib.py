@@ -25,7 +25,7 @@ class Config(C.Structure):
         ("batch_size", C.c_uint32),
         ("aabb_scale", C.c_int32), ("seed", C.c_uint32), ("random_bg_color", C.c_int32), ("snap_to_pixel_centers", C.c_int32),
         ("background_color", C.c_float * 3), ("density_grid_decay", C.c_float), ("loss_scale", C.c_float),
-        ("world_size", C.c_uint32), ("max_rays_per_batch", C.c_uint32),
+        ("world_size", C.c_uint32), ("max_rays_per_batch", C.c_uint32), ("forward_early_termination", C.c_int32),
     ]
 
 

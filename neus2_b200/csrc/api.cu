@@ -136,7 +136,7 @@ void neus2_default_config(neus2_config* c) {
 	c->aabb_scale = 1; c->seed = 1337; c->random_bg_color = 1; c->snap_to_pixel_centers = 1;
 	c->background_color[0] = c->background_color[1] = c->background_color[2] = 0.f;
 	c->density_grid_decay = 0.95f; c->loss_scale = 128.f;
-	c->world_size = 1; c->max_rays_per_batch = 1u << 18;
+	c->world_size = 1; c->max_rays_per_batch = 1u << 18; c->forward_early_termination = 1;
 }
 
 static int build_tables(neus2_ctx* ctx) {
@@ -491,14 +491,19 @@ int neus2_train_step_begin(neus2_ctx* ctx, void* stream_, uint32_t rank, uint32_
 	                                       ctx->cone_angle_constant, max_inference, ctx->numsteps_all, ctx->base, ctx->slot, ctx->ray_indices, ctx->rays,
 	                                       ctx->numsteps, ctx->coords, ctx->counters, ctx->windows, ctx->n_windows, ctx->ray_setup));
 	stage_end(ctx, ST_GEN, stream);
-	stage_begin(ctx, ST_FWD, stream);
-	CHECK(launch_network_forward(stream, ctx->gm, ctx->pl, ctx->params, ctx->coords, ctx->counters + 1, max_inference, c.sdf_bias, ctx->mlp_out));   // :3854
-	stage_end(ctx, ST_FWD, stream);
 	LossParamsDev lp;
 	lp.loss_scale = c.loss_scale; memcpy(lp.background_color, c.background_color, sizeof(lp.background_color));
 	lp.random_bg_color = c.random_bg_color; lp.snap_to_pixel_centers = c.snap_to_pixel_centers;
 	lp.mask_loss_weight = c.mask_loss_weight; lp.ek_loss_weight = c.ek_loss_weight;
 	lp.cos_anneal_ratio = c.anneal_end == 0 ? 1.0f : (float)std::min(1.0, (double)((float)ctx->training_step / c.anneal_end));   // nerf_network.h:1119-1128
+	stage_begin(ctx, ST_FWD, stream);
+	if (c.forward_early_termination) {
+		CHECK(launch_network_forward_rays(stream, ctx->gm, ctx->pl, ctx->params, c.sdf_bias, lp.cos_anneal_ratio, ctx->counters + 0, ctx->numsteps, ctx->coords,
+		                                  max_inference, ctx->mlp_out, ctx->counters + 4));
+	} else {
+		CHECK(launch_network_forward(stream, ctx->gm, ctx->pl, ctx->params, ctx->coords, ctx->counters + 1, max_inference, c.sdf_bias, ctx->mlp_out));   // :3854
+	}
+	stage_end(ctx, ST_FWD, stream);
 	stage_begin(ctx, ST_LOSS, stream);
 	CHECK(launch_compute_loss(stream, n_local, R, n_rays_total, st, ctx->ds, ctx->aabb, ctx->gmv, lp, rows_local, ctx->counters + 0, ctx->mlp_out, ctx->ray_indices,
 	                          ctx->rays, ctx->numsteps, ctx->coords, ctx->ray_tmp, ctx->scan_tmp, ctx->coords_compacted, ctx->dloss, ctx->loss, ctx->ek_loss,

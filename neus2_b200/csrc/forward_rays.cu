@@ -1,0 +1,83 @@
+// forward_rays.cu -- the training step's FIRST network pass, ray by ray, stopping where the loss stops (compiled with
+// -fmad=false like loss.cu, whose transmittance recurrence it must reproduce bit for bit).
+//
+// Reference: train_nerf_step runs NerfNetwork::inference_mixed_precision over ALL marched samples (src/testbed_nerf.cu:3854), and
+// compute_loss_kernel_train_nerf_with_global_movement then walks each ray front to back and stops as soon as the transmittance
+// falls below 1e-4 (:1567-1571): in steady state ~60 % of the evaluated samples lie behind that point and are never read.
+//
+// Here one warp owns a RAY (dynamic queue): it evaluates the ray's samples 16 at a time (the same forward_tile pipeline as
+// k_network_forward), multiplies the tile's (1 - alpha) into the running transmittance in sample order with the loss kernel's own
+// arithmetic (eval_sample), and drops the rest of the ray once T is below the loss threshold.  Every sample the loss reads has
+// been evaluated, with identical bits; rows behind the cut keep stale values nobody looks at.
+#include "network.cuh"
+#include "ngp_common.cuh"
+#include "ngp_kernels.h"
+#include "kernels.h"
+
+#define FR_WARPS 8
+static constexpr int FR_SMEM = WeightSmem::FWD_END * 2 + FR_WARPS * WarpSlab::FWD_END;
+
+__global__ void __launch_bounds__(FR_WARPS * 32, 2)
+k_network_forward_rays(GridMeta gm, ParamLayout pl, const __half* __restrict__ params, float sdf_bias, float cos_anneal_ratio,
+                       const uint32_t* __restrict__ n_kept_ptr, const uint32_t* __restrict__ numsteps, const float* __restrict__ coords,
+                       uint32_t max_samples, __half* __restrict__ out, uint32_t* __restrict__ work_counter /* [0] next ray, [1] samples evaluated */) {
+	extern __shared__ __align__(16) unsigned char smem[];
+	__half* sw = reinterpret_cast<__half*>(smem);
+	stage_weights(sw, params, pl, false, threadIdx.x, blockDim.x);
+	__syncthreads();
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	unsigned char* slab = smem + WeightSmem::FWD_END * 2 + warp * WarpSlab::FWD_END;
+	float* sCoord = reinterpret_cast<float*>(slab + WarpSlab::COORD);
+	const __half* sOUT = reinterpret_cast<const __half*>(slab + WarpSlab::OUT);
+	const uint32_t n_kept = *n_kept_ptr;
+	const float EPSILON = 1e-4f;      // testbed_nerf.cu:1567
+	uint32_t evaluated = 0;
+	FwdState st;
+	while (true) {
+		uint32_t ray = 0;
+		if (lane == 0) ray = atomicAdd(work_counter, 1u);
+		ray = __shfl_sync(0xffffffffu, ray, 0);
+		if (ray >= n_kept) break;
+		const uint32_t ns = numsteps[ray * 2 + 0], base = numsteps[ray * 2 + 1];
+		if (base >= max_samples) continue;
+		const uint32_t n = min(ns, max_samples - base);
+		float T = 1.f;
+		float dir[3] = {0.f, 0.f, 1.f};
+		for (uint32_t s0 = 0; s0 < n; s0 += TILE) {
+			const uint32_t n_valid = min((uint32_t)TILE, n - s0);
+			const float* src = coords + (size_t)(base + s0) * 7;
+			for (int i = lane; i < 16 * 7; i += 32) sCoord[i] = (uint32_t)(i / 7) < n_valid ? src[i] : 0.f;
+			__syncwarp();
+			forward_tile<false>(gm, params, pl, sw, slab, sdf_bias, lane, st);
+			{   // 16 rows x 32 B, coalesced 16-byte stores
+				const uint32_t r = lane >> 1;
+				if (r < n_valid) reinterpret_cast<uint4*>(out)[(size_t)(base + s0 + r) * 2 + (lane & 1)] = reinterpret_cast<const uint4*>(sOUT)[lane];
+			}
+			evaluated += n_valid;
+			if (s0 == 0) {   // BENT_DIR (:1583-1588): the view direction the loss uses comes from sample 0's output
+				const float dv[3] = {__half2float(sOUT[8]) * 2.0f - 1.0f, __half2float(sOUT[9]) * 2.0f - 1.0f, __half2float(sOUT[10]) * 2.0f - 1.0f};
+				normalize3(dv, dir);
+			}
+			float alpha = 0.f;
+			if (lane < (int)n_valid) alpha = eval_sample(sOUT + lane * 16, sCoord + lane * 7, dir, cos_anneal_ratio).alpha;
+			for (uint32_t k = 0; k < n_valid; ++k) T *= (1.f - __shfl_sync(0xffffffffu, alpha, (int)k));   // T *= (1 - alpha), sample order (:1626)
+			__syncwarp();
+			// the loss breaks BEFORE a sample once T < 1e-4; T never grows, so nothing behind this tile is read.  The factor keeps
+			// a tile of slack against any last-ulp difference between the two evaluations (there is none when both are compiled alike).
+			if (T < EPSILON * 0.5f) break;
+		}
+	}
+	if (lane == 0 && evaluated) atomicAdd(work_counter + 1, evaluated);
+}
+
+int launch_network_forward_rays(cudaStream_t stream, const GridMeta& gm, const ParamLayout& pl, const __half* params, float sdf_bias, float cos_anneal_ratio,
+                                const uint32_t* n_kept_ptr, const uint32_t* numsteps, const float* coords, uint32_t max_samples, __half* out, uint32_t* work_counter) {
+	static bool attr[NEUS_MAX_DEVICES] = {};
+	if (ensure_dynamic_smem(k_network_forward_rays, FR_SMEM, attr)) return -1;
+	CUDA_CHECK(cudaMemsetAsync(work_counter, 0, 2 * sizeof(uint32_t), stream));
+	k_network_forward_rays<<<device_sm_count() * 2, FR_WARPS * 32, FR_SMEM, stream>>>(gm, pl, params, sdf_bias, cos_anneal_ratio, n_kept_ptr, numsteps, coords,
+	                                                                                 max_samples, out, work_counter);
+	COUNT_LAUNCH(1);
+	CUDA_CHECK(cudaGetLastError());
+	return 0;
+}

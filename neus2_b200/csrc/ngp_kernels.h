@@ -75,3 +75,7 @@ int launch_marching_cubes_emit(cudaStream_t stream, const uint32_t res[3], const
 int launch_mesh_normals(cudaStream_t stream, uint32_t n_verts, uint32_t n_tris, const uint32_t* indices, const float* verts, float* normals);
 int launch_mesh_color_inputs(cudaStream_t stream, uint32_t n_verts, const float* verts, const Aabb& train_aabb, float* coords);
 int launch_mesh_extract_colors(cudaStream_t stream, uint32_t n_verts, const __half* out16, int from_linear, float* colors);
+
+// first network pass of the training step, ray by ray with the loss kernel's early termination (forward_rays.cu)
+int launch_network_forward_rays(cudaStream_t stream, const GridMeta& gm, const ParamLayout& pl, const __half* params, float sdf_bias, float cos_anneal_ratio,
+                                const uint32_t* n_kept_ptr, const uint32_t* numsteps, const float* coords, uint32_t max_samples, __half* out, uint32_t* work_counter);

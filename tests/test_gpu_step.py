@@ -17,13 +17,13 @@ B = 1 << 14
 G3 = 128 ** 3
 
 
-@pytest.fixture(scope="module")
-def stepped():
+@pytest.fixture(scope="module", params=[1, 0], ids=["early_termination", "full_forward"])
+def stepped(request):
     import torch
     import neus2_b200 as N
     from neus2_b200 import synthetic
     cfg = U.base_cfg()
-    ctx = N.Context(N.default_config(batch_size=B, mask_loss_weight=0.1))
+    ctx = N.Context(N.default_config(batch_size=B, mask_loss_weight=0.1, forward_early_termination=request.param))
     p = U.random_params(cfg, seed=2)
     # make the random network look like an SDF of a blob so that rays find occupied cells: bias the sdf output
     ctx.set_params(p)
@@ -39,7 +39,7 @@ def stepped():
     state0 = ctx.get_state()
     ctx.train_step_begin()
     torch.cuda.synchronize()
-    yield dict(ctx=ctx, cfg=cfg, p=p1, data=data, state0=state0, st_first=st_first, grid_before=grid_before)
+    yield dict(ctx=ctx, cfg=cfg, p=p1, data=data, state0=state0, st_first=st_first, grid_before=grid_before, early=bool(request.param))
     ctx.close()
 
 
@@ -122,6 +122,16 @@ def test_forward_stage(stepped):
     n = min(int(cnt[1]), max_inf)
     coords = _np(ctx.debug_buffer("coords", "<f4", (B * 16, 7)))[:n]
     sub = np.arange(0, min(n, int(ns[: R // 2].sum())), max(1, n // 4000))   # stay inside rows written by kept rays
+    if stepped["early"]:
+        # the first pass stops along each ray where the loss stops reading: the rows the loss consumed (the ray's first
+        # `compacted` samples, testbed_nerf.cu:1567-1571) must all be there; rows behind the cut are never looked at
+        g_ns = _np(ctx.debug_buffer("numsteps", "<u4", (R, 2)))[:k]          # rewritten by the loss: (compacted count, compacted base)
+        idx = _np(ctx.debug_buffer("ray_indices", "<u4", (R,)))[:k]
+        bases = np.concatenate([[0], np.cumsum(ns[idx])[:-1]])
+        rows = np.concatenate([np.arange(b, b + c) for b, c in zip(bases, g_ns[:, 0]) if c > 0])
+        assert len(rows) == int(cnt[2]) or int(cnt[2]) > B
+        sub = rows[:: max(1, len(rows) // 4000)]
+        sub = sub[sub < n]
     cfg0 = U.base_cfg(valid_level=3)       # training step 1: valid_level = ceil(0.2*14) = 3  (grid.h:2433)
     ref = O.net_forward(cfg0, np.ascontiguousarray(coords[sub]), U.to_half_bits(p))
     out = _np(ctx.debug_buffer("mlp_out", "<f2", (B * 16, 16)))[:n].view(np.uint16)[sub]
@@ -199,3 +209,62 @@ def test_step_end_and_training_progress(stepped):
         if s.loss_valid:
             losses.append(s.loss)
     assert all(np.isfinite(losses))
+
+
+def test_early_termination_changes_nothing_downstream():
+    """Two contexts, same seed / data / parameters, first network pass with and without the early cut: every buffer the loss
+    writes is bit-identical step after step (sample counts, compacted coordinates, dL/doutput, per-ray losses), and the first
+    pass evaluates far fewer samples."""
+    import torch
+    import neus2_b200 as N
+    from neus2_b200 import synthetic
+    data = synthetic.render_sphere_views(n_views=6, width=128, height=96, seed=5)
+    ctxs = []
+    for et in (1, 0):
+        c = N.Context(N.default_config(batch_size=B, forward_early_termination=et))
+        c.init_params()
+        p = c.get_params()
+        p[c.layout["variance"]:] = 0.55          # a sharp surface: rays saturate early, the cut has something to cut
+        c.set_params(p)
+        c.set_dataset(data["pixels"], data["focal"], data["principal"], data["xforms"])
+        ctxs.append(c)
+    try:
+        evaluated = []
+        for step in range(6):
+            outs = []
+            for c in ctxs:
+                params_before = c.buffers()[1].clone()
+                c.train_step_begin()
+                torch.cuda.synchronize()
+                cnt = _np(c.debug_buffer("counters", "<u4", (8,))).copy()
+                R = c.get_state()["rays_per_batch"]
+                k = int(cnt[0])
+                m = min(int(cnt[2]), B)
+                outs.append(dict(cnt=cnt[:3].copy(), work=cnt[4:6].copy(), numsteps=_np(c.debug_buffer("numsteps", "<u4", (R, 2)))[:k].copy(),
+                                 cc=_np(c.debug_buffer("coords_compacted", "<f4", (B, 7)))[:m].copy(), dl=_np(c.debug_buffer("dloss", "<f2", (B, 16)))[:m].view(np.uint16).copy(),
+                                 loss=_np(c.debug_buffer("loss", "<f4", (R,))).copy()))
+                # keep both replicas on the same trajectory: the early-cut context adopts nothing, both apply their own gradients;
+                # gradients differ only by fp32 atomic order, so re-synchronise the parameters after the step
+                c.train_step_end()
+            a, b = outs
+            assert np.array_equal(a["cnt"], b["cnt"]), (step, a["cnt"], b["cnt"])
+            assert np.array_equal(a["numsteps"], b["numsteps"])
+            assert np.array_equal(a["cc"].view(np.uint32), b["cc"].view(np.uint32))
+            assert np.array_equal(a["dl"], b["dl"])
+            assert np.array_equal(a["loss"].view(np.uint32), b["loss"].view(np.uint32))
+            evaluated.append((int(a["work"][1]), int(a["cnt"][1])))
+            ctxs[1].set_params(ctxs[0].get_params(), reset_optimizer=False)      # same fp32 master -> same fp16 parameters next step
+            for t_dst, t_src in zip(ctxs[1].buffers()[1:3], ctxs[0].buffers()[1:3]):
+                t_dst.copy_(t_src)
+            m1a, m2a, sa, _ = ctxs[0].optimizer_buffers()
+            m1b, m2b, sb, _ = ctxs[1].optimizer_buffers()
+            m1b.copy_(m1a); m2b.copy_(m2a); sb.copy_(sa)
+            ga = ctxs[0].debug_buffer("density_grid", "<f4", (G3,)); gb = ctxs[1].debug_buffer("density_grid", "<f4", (G3,))
+            gb.copy_(ga)
+            ctxs[1].set_bitfield(_np(ctxs[0].debug_buffer("bitfield", "|u1", (G3 // 8 * 8,))))
+        ev, tot = evaluated[-1]
+        assert 0 < ev <= tot
+        assert ev < 0.9 * tot, (ev, tot)          # the cut removes work
+    finally:
+        for c in ctxs:
+            c.close()
