@@ -323,7 +323,8 @@ def main():
                          "traffic": 422.4e6, "traffic_source": "profiles/r01_captureB.md: dram__bytes_read 111.6 MB + dram__bytes_write 310.8 MB per launch (ncu --set full)",
                          "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes, "avg_launch_ms": dom_ms, "l2": l2},
             "stage_ms": {k: round(v[0], 4) for k, v in stages.items()},
-            "per_step": {"rays": rays / K, "samples_before_compaction": n_u / K, "samples_compacted": n_c / K, "training_step": int(st.training_step)},
+            "per_step": {"rays": rays / K, "samples_before_compaction": n_u / K, "samples_compacted": n_c / K, "training_step": int(st.training_step),
+                         "first_pass_samples_evaluated_last_step": int(ctx.debug_buffer("counters", "<u4", (8,))[5].item())},
         }
         if not args.no_cpu_baseline:
             try:

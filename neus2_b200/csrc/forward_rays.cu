@@ -33,21 +33,37 @@ k_network_forward_rays(GridMeta gm, ParamLayout pl, const __half* __restrict__ p
 	const float EPSILON = 1e-4f;      // testbed_nerf.cu:1567
 	uint32_t evaluated = 0;
 	FwdState st;
-	while (true) {
-		uint32_t ray = 0;
-		if (lane == 0) ray = atomicAdd(work_counter, 1u);
-		ray = __shfl_sync(0xffffffffu, ray, 0);
-		if (ray >= n_kept) break;
-		const uint32_t ns = numsteps[ray * 2 + 0], base = numsteps[ray * 2 + 1];
-		if (base >= max_samples) continue;
-		const uint32_t n = min(ns, max_samples - base);
+	// one tile of coordinates is always in flight: the ray's next tile or, on its last tile, the first tile of the warp's NEXT ray
+	// (grabbed one ray ahead), so the HBM latency of the 448-byte tile hides behind a whole tile of work
+	float cr[4];
+	uint32_t pref_row = 0xffffffffu;
+	auto prefetch = [&](uint32_t row, uint32_t n_valid) {
+		const float* src = coords + (size_t)row * 7;
+		#pragma unroll
+		for (int k = 0; k < 4; ++k) { const int i = lane + 32 * k; cr[k] = (i < 16 * 7 && (uint32_t)(i / 7) < n_valid) ? src[i] : 0.f; }
+		pref_row = row;
+	};
+	auto grab = [&]() { uint32_t r = 0; if (lane == 0) r = atomicAdd(work_counter, 1u); return __shfl_sync(0xffffffffu, r, 0); };
+	auto ray_extent = [&](uint32_t r, uint32_t& base, uint32_t& n) {
+		base = 0; n = 0;
+		if (r < n_kept) { const uint32_t ns = numsteps[r * 2 + 0]; base = numsteps[r * 2 + 1]; n = base < max_samples ? min(ns, max_samples - base) : 0u; }
+	};
+	uint32_t next_ray = grab(), next_base, next_n;
+	ray_extent(next_ray, next_base, next_n);
+	while (next_ray < n_kept) {
+		const uint32_t base = next_base, n = next_n;
+		next_ray = grab();
+		ray_extent(next_ray, next_base, next_n);
 		float T = 1.f;
 		float dir[3] = {0.f, 0.f, 1.f};
 		for (uint32_t s0 = 0; s0 < n; s0 += TILE) {
 			const uint32_t n_valid = min((uint32_t)TILE, n - s0);
-			const float* src = coords + (size_t)(base + s0) * 7;
-			for (int i = lane; i < 16 * 7; i += 32) sCoord[i] = (uint32_t)(i / 7) < n_valid ? src[i] : 0.f;
+			if (pref_row != base + s0) prefetch(base + s0, n_valid);     // only after an early cut (the tile in flight belonged to the old ray)
+			#pragma unroll
+			for (int k = 0; k < 4; ++k) { const int i = lane + 32 * k; if (i < 16 * 7) sCoord[i] = cr[k]; }
 			__syncwarp();
+			if (s0 + TILE < n) prefetch(base + s0 + TILE, min((uint32_t)TILE, n - s0 - TILE));
+			else if (next_n) prefetch(next_base, min((uint32_t)TILE, next_n));
 			forward_tile<false>(gm, params, pl, sw, slab, sdf_bias, lane, st);
 			{   // 16 rows x 32 B, coalesced 16-byte stores
 				const uint32_t r = lane >> 1;

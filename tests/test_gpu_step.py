@@ -127,8 +127,8 @@ def test_forward_stage(stepped):
         # `compacted` samples, testbed_nerf.cu:1567-1571) must all be there; rows behind the cut are never looked at
         g_ns = _np(ctx.debug_buffer("numsteps", "<u4", (R, 2)))[:k]          # rewritten by the loss: (compacted count, compacted base)
         idx = _np(ctx.debug_buffer("ray_indices", "<u4", (R,)))[:k]
-        bases = np.concatenate([[0], np.cumsum(ns[idx])[:-1]])
-        rows = np.concatenate([np.arange(b, b + c) for b, c in zip(bases, g_ns[:, 0]) if c > 0])
+        bases = np.concatenate([[0], np.cumsum(ns[idx].astype(np.int64))[:-1]]).astype(np.int64)
+        rows = np.concatenate([np.arange(b, b + int(c), dtype=np.int64) for b, c in zip(bases, g_ns[:, 0]) if c > 0])
         assert len(rows) == int(cnt[2]) or int(cnt[2]) > B
         sub = rows[:: max(1, len(rows) // 4000)]
         sub = sub[sub < n]
