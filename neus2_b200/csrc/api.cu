@@ -498,8 +498,8 @@ int neus2_train_step_begin(neus2_ctx* ctx, void* stream_, uint32_t rank, uint32_
 	lp.cos_anneal_ratio = c.anneal_end == 0 ? 1.0f : (float)std::min(1.0, (double)((float)ctx->training_step / c.anneal_end));   // nerf_network.h:1119-1128
 	stage_begin(ctx, ST_FWD, stream);
 	if (c.forward_early_termination) {
-		CHECK(launch_network_forward_rays(stream, ctx->gm, ctx->pl, ctx->params, c.sdf_bias, lp.cos_anneal_ratio, ctx->counters + 0, ctx->numsteps, ctx->coords,
-		                                  max_inference, ctx->mlp_out, ctx->counters + 4));
+		CHECK(launch_network_forward_rays(stream, ctx->gm, ctx->pl, ctx->params, c.sdf_bias, lp.cos_anneal_ratio, ctx->counters + 0, ctx->counters + 6, ctx->numsteps,
+		                                  ctx->coords, max_inference, n_local, ctx->mlp_out, ctx->scan_tmp, ctx->counters + 4));   // scan_tmp: free until the loss's scan
 	} else {
 		CHECK(launch_network_forward(stream, ctx->gm, ctx->pl, ctx->params, ctx->coords, ctx->counters + 1, max_inference, c.sdf_bias, ctx->mlp_out));   // :3854
 	}

@@ -5,10 +5,13 @@
 // compute_loss_kernel_train_nerf_with_global_movement then walks each ray front to back and stops as soon as the transmittance
 // falls below 1e-4 (:1567-1571): in steady state ~60 % of the evaluated samples lie behind that point and are never read.
 //
-// Here one warp owns a RAY (dynamic queue): it evaluates the ray's samples 16 at a time (the same forward_tile pipeline as
-// k_network_forward), multiplies the tile's (1 - alpha) into the running transmittance in sample order with the loss kernel's own
-// arithmetic (eval_sample), and drops the rest of the ray once T is below the loss threshold.  Every sample the loss reads has
-// been evaluated, with identical bits; rows behind the cut keep stale values nobody looks at.
+// Here a work item is a SEGMENT of a ray (up to 4 tiles = 64 consecutive samples); a warp pulls items from a queue ordered
+// segment-major (every ray's first segment, then every ray's second ...).  It evaluates the segment 16 samples at a time (the same
+// forward_tile pipeline as k_network_forward), multiplies (1 - alpha) into a transmittance that starts at 1 for the segment, with the
+// loss kernel's own arithmetic (eval_sample), and stops -- and flags the ray as finished for all later segments -- once that product
+// is below the loss threshold.  The segment-local product bounds the true transmittance from above, so every sample the loss reads
+// has been evaluated (with identical bits); rows behind the cut keep stale values nobody looks at.  Segmenting bounds the serial
+// chain of a long ray that never saturates to 4 tiles.
 #include "network.cuh"
 #include "ngp_common.cuh"
 #include "ngp_kernels.h"
@@ -17,10 +20,13 @@
 #define FR_WARPS 8
 static constexpr int FR_SMEM = WeightSmem::FWD_END * 2 + FR_WARPS * WarpSlab::FWD_END;
 
+#define FR_SEGMENT 64u   // samples per work item
+
 __global__ void __launch_bounds__(FR_WARPS * 32, 2)
 k_network_forward_rays(GridMeta gm, ParamLayout pl, const __half* __restrict__ params, float sdf_bias, float cos_anneal_ratio,
-                       const uint32_t* __restrict__ n_kept_ptr, const uint32_t* __restrict__ numsteps, const float* __restrict__ coords,
-                       uint32_t max_samples, __half* __restrict__ out, uint32_t* __restrict__ work_counter /* [0] next ray, [1] samples evaluated */) {
+                       const uint32_t* __restrict__ n_kept_ptr, const uint32_t* __restrict__ longest_ptr, const uint32_t* __restrict__ numsteps,
+                       const float* __restrict__ coords, uint32_t max_samples, __half* __restrict__ out, uint32_t* __restrict__ ray_done,
+                       uint32_t* __restrict__ work_counter /* [0] next item, [1] samples evaluated */) {
 	extern __shared__ __align__(16) unsigned char smem[];
 	__half* sw = reinterpret_cast<__half*>(smem);
 	stage_weights(sw, params, pl, false, threadIdx.x, blockDim.x);
@@ -30,47 +36,37 @@ k_network_forward_rays(GridMeta gm, ParamLayout pl, const __half* __restrict__ p
 	float* sCoord = reinterpret_cast<float*>(slab + WarpSlab::COORD);
 	const __half* sOUT = reinterpret_cast<const __half*>(slab + WarpSlab::OUT);
 	const uint32_t n_kept = *n_kept_ptr;
+	const uint32_t n_segments = (min(*longest_ptr, (uint32_t)NERF_STEPS) + FR_SEGMENT - 1) / FR_SEGMENT;
+	const uint64_t n_items = (uint64_t)n_kept * n_segments;
 	const float EPSILON = 1e-4f;      // testbed_nerf.cu:1567
 	uint32_t evaluated = 0;
 	FwdState st;
-	// one tile of coordinates is always in flight: the ray's next tile or, on its last tile, the first tile of the warp's NEXT ray
-	// (grabbed one ray ahead), so the HBM latency of the 448-byte tile hides behind a whole tile of work
-	float cr[4];
-	uint32_t pref_row = 0xffffffffu;
-	auto prefetch = [&](uint32_t row, uint32_t n_valid) {
-		const float* src = coords + (size_t)row * 7;
-		#pragma unroll
-		for (int k = 0; k < 4; ++k) { const int i = lane + 32 * k; cr[k] = (i < 16 * 7 && (uint32_t)(i / 7) < n_valid) ? src[i] : 0.f; }
-		pref_row = row;
-	};
-	auto grab = [&]() { uint32_t r = 0; if (lane == 0) r = atomicAdd(work_counter, 1u); return __shfl_sync(0xffffffffu, r, 0); };
-	auto ray_extent = [&](uint32_t r, uint32_t& base, uint32_t& n) {
-		base = 0; n = 0;
-		if (r < n_kept) { const uint32_t ns = numsteps[r * 2 + 0]; base = numsteps[r * 2 + 1]; n = base < max_samples ? min(ns, max_samples - base) : 0u; }
-	};
-	uint32_t next_ray = grab(), next_base, next_n;
-	ray_extent(next_ray, next_base, next_n);
-	while (next_ray < n_kept) {
-		const uint32_t base = next_base, n = next_n;
-		next_ray = grab();
-		ray_extent(next_ray, next_base, next_n);
+	while (true) {
+		uint32_t item = 0;
+		if (lane == 0) item = atomicAdd(work_counter, 1u);
+		item = __shfl_sync(0xffffffffu, item, 0);
+		if (item >= n_items) break;
+		const uint32_t seg = item / n_kept, ray = item - seg * n_kept;
+		const uint32_t ns = numsteps[ray * 2 + 0], base = numsteps[ray * 2 + 1];
+		if (base >= max_samples) continue;
+		const uint32_t n = min(ns, max_samples - base);
+		const uint32_t s_begin = seg * FR_SEGMENT, s_end = min(n, s_begin + FR_SEGMENT);
+		if (s_begin >= n) continue;
+		if (seg > 0 && ray_done[ray]) continue;          // an earlier segment already pushed the transmittance below the threshold
 		float T = 1.f;
 		float dir[3] = {0.f, 0.f, 1.f};
-		for (uint32_t s0 = 0; s0 < n; s0 += TILE) {
-			const uint32_t n_valid = min((uint32_t)TILE, n - s0);
-			if (pref_row != base + s0) prefetch(base + s0, n_valid);     // only after an early cut (the tile in flight belonged to the old ray)
-			#pragma unroll
-			for (int k = 0; k < 4; ++k) { const int i = lane + 32 * k; if (i < 16 * 7) sCoord[i] = cr[k]; }
+		for (uint32_t s0 = s_begin; s0 < s_end; s0 += TILE) {
+			const uint32_t n_valid = min((uint32_t)TILE, s_end - s0);
+			const float* src = coords + (size_t)(base + s0) * 7;
+			for (int i = lane; i < 16 * 7; i += 32) sCoord[i] = (uint32_t)(i / 7) < n_valid ? src[i] : 0.f;
 			__syncwarp();
-			if (s0 + TILE < n) prefetch(base + s0 + TILE, min((uint32_t)TILE, n - s0 - TILE));
-			else if (next_n) prefetch(next_base, min((uint32_t)TILE, next_n));
 			forward_tile<false>(gm, params, pl, sw, slab, sdf_bias, lane, st);
 			{   // 16 rows x 32 B, coalesced 16-byte stores
 				const uint32_t r = lane >> 1;
 				if (r < n_valid) reinterpret_cast<uint4*>(out)[(size_t)(base + s0 + r) * 2 + (lane & 1)] = reinterpret_cast<const uint4*>(sOUT)[lane];
 			}
 			evaluated += n_valid;
-			if (s0 == 0) {   // BENT_DIR (:1583-1588): the view direction the loss uses comes from sample 0's output
+			if (s0 == s_begin) {   // BENT_DIR (:1583-1588): the loss takes the view direction from sample 0's output; every sample of a ray carries the same one
 				const float dv[3] = {__half2float(sOUT[8]) * 2.0f - 1.0f, __half2float(sOUT[9]) * 2.0f - 1.0f, __half2float(sOUT[10]) * 2.0f - 1.0f};
 				normalize3(dv, dir);
 			}
@@ -78,21 +74,23 @@ k_network_forward_rays(GridMeta gm, ParamLayout pl, const __half* __restrict__ p
 			if (lane < (int)n_valid) alpha = eval_sample(sOUT + lane * 16, sCoord + lane * 7, dir, cos_anneal_ratio).alpha;
 			for (uint32_t k = 0; k < n_valid; ++k) T *= (1.f - __shfl_sync(0xffffffffu, alpha, (int)k));   // T *= (1 - alpha), sample order (:1626)
 			__syncwarp();
-			// the loss breaks BEFORE a sample once T < 1e-4; T never grows, so nothing behind this tile is read.  The factor keeps
-			// a tile of slack against any last-ulp difference between the two evaluations (there is none when both are compiled alike).
-			if (T < EPSILON * 0.5f) break;
+			// the loss breaks BEFORE a sample once its transmittance (<= this segment-local product) is below 1e-4, and T never grows:
+			// nothing behind this tile is read.  The factor 0.5 is slack against any last-ulp difference between the two evaluations.
+			if (T < EPSILON * 0.5f) { if (lane == 0) ray_done[ray] = 1u; break; }
 		}
 	}
 	if (lane == 0 && evaluated) atomicAdd(work_counter + 1, evaluated);
 }
 
 int launch_network_forward_rays(cudaStream_t stream, const GridMeta& gm, const ParamLayout& pl, const __half* params, float sdf_bias, float cos_anneal_ratio,
-                                const uint32_t* n_kept_ptr, const uint32_t* numsteps, const float* coords, uint32_t max_samples, __half* out, uint32_t* work_counter) {
+                                const uint32_t* n_kept_ptr, const uint32_t* longest_ptr, const uint32_t* numsteps, const float* coords, uint32_t max_samples,
+                                uint32_t n_rays_max, __half* out, uint32_t* ray_done, uint32_t* work_counter) {
 	static bool attr[NEUS_MAX_DEVICES] = {};
 	if (ensure_dynamic_smem(k_network_forward_rays, FR_SMEM, attr)) return -1;
 	CUDA_CHECK(cudaMemsetAsync(work_counter, 0, 2 * sizeof(uint32_t), stream));
-	k_network_forward_rays<<<device_sm_count() * 2, FR_WARPS * 32, FR_SMEM, stream>>>(gm, pl, params, sdf_bias, cos_anneal_ratio, n_kept_ptr, numsteps, coords,
-	                                                                                 max_samples, out, work_counter);
+	CUDA_CHECK(cudaMemsetAsync(ray_done, 0, (size_t)n_rays_max * sizeof(uint32_t), stream));
+	k_network_forward_rays<<<device_sm_count() * 2, FR_WARPS * 32, FR_SMEM, stream>>>(gm, pl, params, sdf_bias, cos_anneal_ratio, n_kept_ptr, longest_ptr, numsteps,
+	                                                                                 coords, max_samples, out, ray_done, work_counter);
 	COUNT_LAUNCH(1);
 	CUDA_CHECK(cudaGetLastError());
 	return 0;

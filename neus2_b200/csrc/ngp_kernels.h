@@ -78,4 +78,5 @@ int launch_mesh_extract_colors(cudaStream_t stream, uint32_t n_verts, const __ha
 
 // first network pass of the training step, ray by ray with the loss kernel's early termination (forward_rays.cu)
 int launch_network_forward_rays(cudaStream_t stream, const GridMeta& gm, const ParamLayout& pl, const __half* params, float sdf_bias, float cos_anneal_ratio,
-                                const uint32_t* n_kept_ptr, const uint32_t* numsteps, const float* coords, uint32_t max_samples, __half* out, uint32_t* work_counter);
+                                const uint32_t* n_kept_ptr, const uint32_t* longest_ptr, const uint32_t* numsteps, const float* coords, uint32_t max_samples,
+                                uint32_t n_rays_max, __half* out, uint32_t* ray_done, uint32_t* work_counter);

@@ -162,14 +162,16 @@ k_scan_rays(uint32_t n, const uint32_t* __restrict__ counts, uint32_t max_sample
 	for (uint32_t i = b; i < e; ++i) s += counts[i];
 	uint32_t off = block_exclusive_scan(s, warp_sums, &total);
 	if (threadIdx.x == 0) counters[1] = total;
-	uint32_t kept = 0;
+	uint32_t kept = 0, longest = 0;
 	for (uint32_t i = b; i < e; ++i) {
 		const uint32_t c = counts[i];
 		base[i] = off;
 		const bool k = c > 0 && off + c <= max_samples;
 		kept += k ? 1u : 0u;
+		if (k) longest = max(longest, c);
 		off += c;
 	}
+	if (longest) atomicMax(counters + 6, longest);   // samples on the longest kept ray (sizes the first network pass's work list)
 	uint32_t soff = block_exclusive_scan(kept, warp_sums, &total);
 	if (threadIdx.x == 0) counters[0] = total;
 	for (uint32_t i = b; i < e; ++i) {
