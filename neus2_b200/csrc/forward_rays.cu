@@ -20,7 +20,9 @@
 #define FR_WARPS 8
 static constexpr int FR_SMEM = WeightSmem::FWD_END * 2 + FR_WARPS * WarpSlab::FWD_END;
 
+#ifndef FR_SEGMENT
 #define FR_SEGMENT 64u   // samples per work item
+#endif
 
 __global__ void __launch_bounds__(FR_WARPS * 32, 2)
 k_network_forward_rays(GridMeta gm, ParamLayout pl, const __half* __restrict__ params, float sdf_bias, float cos_anneal_ratio,
@@ -55,11 +57,20 @@ k_network_forward_rays(GridMeta gm, ParamLayout pl, const __half* __restrict__ p
 		if (seg > 0 && ray_done[ray]) continue;          // an earlier segment already pushed the transmittance below the threshold
 		float T = 1.f;
 		float dir[3] = {0.f, 0.f, 1.f};
+		float cr[4];   // the segment's next tile of coordinates, in flight while the current tile is processed
+		auto fetch = [&](uint32_t s0) {
+			const uint32_t nv = min((uint32_t)TILE, s_end - s0);
+			const float* src = coords + (size_t)(base + s0) * 7;
+			#pragma unroll
+			for (int k = 0; k < 4; ++k) { const int i = lane + 32 * k; cr[k] = (i < 16 * 7 && (uint32_t)(i / 7) < nv) ? src[i] : 0.f; }
+		};
+		fetch(s_begin);
 		for (uint32_t s0 = s_begin; s0 < s_end; s0 += TILE) {
 			const uint32_t n_valid = min((uint32_t)TILE, s_end - s0);
-			const float* src = coords + (size_t)(base + s0) * 7;
-			for (int i = lane; i < 16 * 7; i += 32) sCoord[i] = (uint32_t)(i / 7) < n_valid ? src[i] : 0.f;
+			#pragma unroll
+			for (int k = 0; k < 4; ++k) { const int i = lane + 32 * k; if (i < 16 * 7) sCoord[i] = cr[k]; }
 			__syncwarp();
+			if (s0 + TILE < s_end) fetch(s0 + TILE);
 			forward_tile<false>(gm, params, pl, sw, slab, sdf_bias, lane, st);
 			{   // 16 rows x 32 B, coalesced 16-byte stores
 				const uint32_t r = lane >> 1;
