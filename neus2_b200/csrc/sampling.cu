@@ -55,10 +55,19 @@ __device__ __forceinline__ uint32_t march_ray_warp(const Aabb& bb, const float r
 	while (!done) {
 		// chain positions of this window (sequential fp32 adds, identical in every lane)
 		float tl = t_start, t_mine = t_start;
-		#pragma unroll
-		for (int L = 0; L < 32; ++L) {
-			if (lane == L) t_mine = tl;
-			tl += calc_dt(tl, cone_angle);
+		if (cone_angle == 0.0f) {   // aabb_scale 1 (testbed_nerf.cu:3090): calc_dt(t, 0) = clamp(t * 0) is the constant minimum step -> 32 plain adds
+			const float dt0 = calc_dt(t_start, 0.0f);
+			#pragma unroll
+			for (int L = 0; L < 32; ++L) {
+				if (lane == L) t_mine = tl;
+				tl += dt0;
+			}
+		} else {
+			#pragma unroll
+			for (int L = 0; L < 32; ++L) {
+				if (lane == L) t_mine = tl;
+				tl += calc_dt(tl, cone_angle);
+			}
 		}
 		float pos[3];
 		#pragma unroll
@@ -80,9 +89,15 @@ __device__ __forceinline__ uint32_t march_ray_warp(const Aabb& bb, const float r
 		while (cur < 32) {
 			if (!((inside_mask >> cur) & 1u) || j >= limit) { done = true; break; }
 			if ((occ_mask >> cur) & 1u) {
-				if (lane == cur) my_j = (int)j;
-				++j;
-				++cur;
+				// a run of consecutive occupied positions inside the box becomes samples j, j+1, ... in one go (the serial loop
+				// would visit them one by one with the same outcome); the run ends at the first empty / outside position or at `limit`
+				const uint32_t run_bits = (occ_mask & inside_mask) >> cur;          // bit 0 is set
+				uint32_t run = (uint32_t)__ffs((int)~run_bits) - 1u;               // ~run_bits has a set bit at or below position 32 - cur
+				if (run_bits == 0xffffffffu) run = 32u;
+				run = min(run, limit - j);
+				if (lane >= cur && lane < cur + (int)run) my_j = (int)j + (lane - cur);
+				j += run;
+				cur += (int)run;
 			} else {
 				const float tt = __shfl_sync(0xffffffffu, t_target, cur);
 				const uint32_t reach = __ballot_sync(0xffffffffu, lane > cur && t_mine >= tt);
@@ -212,10 +227,19 @@ k_rays_emit(uint32_t n_rays, uint32_t ray_offset, Aabb bb, float cone_angle, con
 	for (uint32_t wi = 0; wi < nw; ++wi) {
 		const WindowRec rec = w[wi];
 		float tl = rec.t_start, t_mine = rec.t_start;
-		#pragma unroll
-		for (int L = 0; L < 32; ++L) {
-			if (lane == L) t_mine = tl;
-			tl += calc_dt(tl, cone_angle);
+		if (cone_angle == 0.0f) {   // constant step, as in the count pass
+			const float dt0 = calc_dt(rec.t_start, 0.0f);
+			#pragma unroll
+			for (int L = 0; L < 32; ++L) {
+				if (lane == L) t_mine = tl;
+				tl += dt0;
+			}
+		} else {
+			#pragma unroll
+			for (int L = 0; L < 32; ++L) {
+				if (lane == L) t_mine = tl;
+				tl += calc_dt(tl, cone_angle);
+			}
 		}
 		if ((rec.mask >> lane) & 1u) {
 			const uint32_t my_j = j + __popc(rec.mask & ((1u << lane) - 1u));

@@ -9,7 +9,11 @@
 
 #define WG_THREADS 128
 #define WG_ROWS 64            // rows (K) per shared-memory tile
-#define WG_CTAS_PER_JOB 148
+// CTAs per job, proportional to the bytes a job streams per row (160 / 256 / 224 / 160 / 384 B): all jobs finish together.
+// Sum = 5 x 148; the partial buffer has WG_MAX_CTAS slots per parameter, slots a job never writes stay zero (allocated zeroed).
+#define WG_MAX_CTAS 240
+__constant__ uint32_t c_wg_ctas[5] = {100, 160, 140, 100, 240};
+static const uint32_t h_wg_ctas[5] = {100, 160, 140, 100, 240};
 
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_ptr) {
 	uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem_ptr);
@@ -116,11 +120,14 @@ k_weight_gradients(ParamLayout pl, StagedOperands so, const __half* __restrict__
 	if (threadIdx.x < 64) s_w1row0[threadIdx.x] = params[pl.off_w1 + threadIdx.x];
 	__syncthreads();
 	const uint32_t n = (*n_in_ptr == 0) ? 0 : n_rows;
+	uint32_t job = 0, part = blockIdx.x;
+	while (job < 4 && part >= c_wg_ctas[job]) { part -= c_wg_ctas[job]; ++job; }
+	const uint32_t n_parts = c_wg_ctas[job];
 	const uint32_t tiles = (n + WG_ROWS - 1) / WG_ROWS;
-	const uint32_t per = (tiles + gridDim.x - 1) / gridDim.x;
-	const uint32_t rb = min(n, blockIdx.x * per * WG_ROWS), re = min(n, (blockIdx.x + 1) * per * WG_ROWS);
-	float* p = partials + (size_t)blockIdx.x * n_mlp;
-	switch (blockIdx.y) {
+	const uint32_t per = (tiles + n_parts - 1) / n_parts;
+	const uint32_t rb = min(n, part * per * WG_ROWS), re = min(n, (part + 1) * per * WG_ROWS);
+	float* p = partials + (size_t)part * n_mlp;
+	switch (job) {
 		case 0: wgrad_job<16, 64>(so.dOUT, so.H2, nullptr, nullptr, nullptr, rb, re, n, p + pl.off_c2, smem); break;
 		case 1: wgrad_job<64, 64>(so.dH2, so.H1, nullptr, nullptr, nullptr, rb, re, n, p + pl.off_c1, smem); break;
 		case 2: wgrad_job<64, 48>(so.dH1, so.CIN, nullptr, nullptr, nullptr, rb, re, n, p + pl.off_c0, smem); break;
@@ -142,14 +149,16 @@ __global__ void k_reduce_partials(ParamLayout pl, const float* __restrict__ part
 	if (i == 0) grads[pl.off_var] = round_h(*var_acc);
 }
 
-uint32_t weight_gradient_partials() { return WG_CTAS_PER_JOB; }
+uint32_t weight_gradient_partials() { return WG_MAX_CTAS; }
 
 int launch_weight_gradients(cudaStream_t stream, const ParamLayout& pl, const StagedOperands& so, const __half* params,
                             const uint32_t* n_in_ptr, uint32_t n_rows, float* partials, uint32_t n_partials,
                             const float* var_acc, const float* w1row0_acc, float* grads) {
 	const uint32_t n_mlp = pl.off_grid;
 	const int smem = 2 * (WG_ROWS * (64 + 8) * 2) * 2;   // two stages of (dY tile + X tile)
-	dim3 grid(n_partials, 5);
+	if (n_partials != WG_MAX_CTAS) { neus_set_error("partials buffer must hold weight_gradient_partials() slots", __FILE__, __LINE__); return -1; }
+	uint32_t grid = 0;
+	for (int j = 0; j < 5; ++j) grid += h_wg_ctas[j];
 	k_weight_gradients<<<grid, WG_THREADS, smem, stream>>>(pl, so, params, n_in_ptr, n_rows, partials, n_mlp);
 	COUNT_LAUNCH(1);
 	CUDA_CHECK(cudaGetLastError());

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--mc", type=int, default=256)
     ap.add_argument("--json", default=None)
     ap.add_argument("--mask-weight", type=float, default=0.0)
+    ap.add_argument("--full-forward", action="store_true", help="evaluate every marched sample in the first pass (reference behaviour) instead of the early cut")
     args = ap.parse_args()
 
     import torch
@@ -36,7 +37,7 @@ def main():
     from neus2_b200 import synthetic
 
     data = synthetic.render_sphere_views(n_views=args.views, width=args.res, height=args.res, seed=0, elevation_deg=(-55.0, 65.0))
-    ctx = N.Context(N.default_config(mask_loss_weight=args.mask_weight))
+    ctx = N.Context(N.default_config(mask_loss_weight=args.mask_weight, forward_early_termination=0 if args.full_forward else 1))
     ctx.init_params()
     ctx.set_dataset(data["pixels"], data["focal"], data["principal"], data["xforms"])
     torch.cuda.synchronize()
