@@ -34,7 +34,7 @@ def camera_ring(n_views, radius=1.3, center=(0.5, 0.5, 0.5), elevation_deg=(15.0
 
 
 def render_sphere_views(n_views=16, width=256, height=256, focal=None, sphere_radius=0.25, center=(0.5, 0.5, 0.5),
-                        cam_radius=1.3, seed=0, second_sphere=True, principal=(0.5, 0.5), elevation_deg=(15.0, 50.0)):
+                        cam_radius=1.3, seed=0, second_sphere=True, principal=(0.5, 0.5), elevation_deg=(15.0, 50.0), spheres=None):
     """Returns dict(pixels uint8 [n,h,w,4], focal [n,2], principal [n,2], xforms [n,3,4])."""
     if focal is None:
         focal = 1.1 * width * cam_radius / (4 * sphere_radius) / 1.3
@@ -43,9 +43,12 @@ def render_sphere_views(n_views=16, width=256, height=256, focal=None, sphere_ra
     cx, cy = principal
     ys, xs = np.meshgrid((np.arange(height) + 0.5) / height, (np.arange(width) + 0.5) / width, indexing="ij")
     d_cam = np.stack([(xs - cx) * width / fx, (ys - cy) * height / fy, np.ones_like(xs)], axis=-1)
-    spheres = [(np.asarray(center, dtype=np.float64), sphere_radius)]
-    if second_sphere:
-        spheres.append((np.asarray(center, dtype=np.float64) + np.array([0.18, 0.05, 0.1]), sphere_radius * 0.45))
+    if spheres is None:
+        spheres = [(np.asarray(center, dtype=np.float64), sphere_radius)]
+        if second_sphere:
+            spheres.append((np.asarray(center, dtype=np.float64) + np.array([0.18, 0.05, 0.1]), sphere_radius * 0.45))
+    else:
+        spheres = [(np.asarray(c, dtype=np.float64), float(r)) for c, r in spheres]
     pixels = np.zeros((n_views, height, width, 4), dtype=np.uint8)
     light = np.array([0.3, 0.5, 0.8]) / np.linalg.norm([0.3, 0.5, 0.8])
     for v in range(n_views):
