@@ -137,6 +137,11 @@ class Testbed:
         if int(batch_size) != int(ctx.cfg.batch_size):
             raise RuntimeError(f"the context was created for batch_size {ctx.cfg.batch_size}")
         st = ctx.train_step()
+        if st.measured_batch_size == 0:
+            # train_nerf (testbed_nerf.cu:3540-3546): "Nerf training generated 0 samples. Aborting training."
+            self.loss = self.ek_loss = self.mask_loss = 0.0
+            self.shall_train = False
+            return st
         if st.loss_valid:
             self.loss, self.ek_loss, self.mask_loss = float(st.loss), float(st.ek_loss), float(st.mask_loss)
         return st

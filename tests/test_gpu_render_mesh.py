@@ -213,3 +213,31 @@ def test_marching_cubes_empty_and_full(scene):
         dens = torch.full((16, 16, 16), val, device="cuda")
         v, f = ctx.marching_cubes(dens)
         assert len(v) == 0 and len(f) == 0
+
+
+def test_render_camera_facing_away_is_pure_background(scene):
+    """No ray enters the box: the queue stays empty, the persistent kernel exits at once, every pixel is the (sRGB -> linear -> sRGB)
+    background with the background's alpha."""
+    import torch
+    ctx = scene["ctx"]
+    cam = scene["xforms"][0].copy()
+    cam[:, 2] *= -1.0          # look the other way
+    cam[:, 0] *= -1.0          # keep the frame right-handed
+    rp = ctx.render_params(W, H, camera_matrix=cam, focal_length=(70.0, 70.0), background_color=(0.25, 0.5, 0.75, 1.0), use_inference_params=0)
+    img = ctx.render(rp).cpu().numpy()
+    assert ctx.render_stats() == dict(rays_alive=0, samples=0)
+    ref, _ = O.render_shade_accumulate_tonemap(np.zeros((1, 4), np.float32), np.zeros(1, np.float32), np.zeros((1, 4), np.float32), 0.0, (0.25, 0.5, 0.75, 1.0), 0.0, True)
+    assert np.allclose(img.reshape(-1, 4), ref[0], atol=1e-6)
+    assert np.array_equal(img, np.broadcast_to(img[0, 0], img.shape))
+
+
+def test_operators_accept_empty_and_single_sample_batches(scene):
+    import torch
+    ctx = scene["ctx"]
+    empty = torch.zeros((0, 7), dtype=torch.float32, device="cuda")
+    assert ctx.forward(empty).shape == (0, 16)
+    one = torch.from_numpy(U.random_coords(1, seed=3)).cuda()
+    many = torch.from_numpy(U.random_coords(40, seed=3)).cuda()
+    many[0] = one[0]
+    assert torch.equal(ctx.forward(one)[0].view(torch.int16), ctx.forward(many)[0].view(torch.int16))
+    assert ctx.sdf(one[:, :3].contiguous()).shape == (1,)
