@@ -215,6 +215,14 @@ int neus2_get_counters(neus2_ctx* ctx, uint32_t out[4]);
 /* load_snapshot's density-grid restore (testbed.cu:3222-3240): uploads the grid and rebuilds mean + occupancy bitfield. */
 int neus2_set_density_grid(neus2_ctx* ctx, void* stream, const float* density_grid_host, uint64_t n, uint32_t ema_step);
 
+/* ---- sequences (the part that needs no global-movement network) -------------------------------------------
+ * Testbed::training_network_next_frame (src/testbed.cu:2001-2082) with "predict_global_movement": false: call after
+ * neus2_set_dataset installed the next frame's images.  The model continues from its inference (EMA) weights with a fresh
+ * optimizer, step counters at zero, rays_per_batch 4096, m_rng re-seeded; the parameters stay frozen for the first
+ * `frozen_steps` steps (predict_global_movement_training_step) and the learning rate becomes `after_learning_rate` (> 0). */
+int neus2_next_frame(neus2_ctx* ctx, void* stream, float after_learning_rate, uint32_t frozen_steps);
+int neus2_get_time_frame(const neus2_ctx* ctx, uint32_t* current_training_time_frame, float* learning_rate);
+
 #ifdef __cplusplus
 }
 #endif

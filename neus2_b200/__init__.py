@@ -246,6 +246,15 @@ class Context:
         check(self._lib.neus2_mesh_attributes(self._h, _stream(stream), _ptr(nrm), _ptr(col), C.c_int(int(use_inference_params))))
         return nrm, col
 
+    def next_frame(self, after_learning_rate=0.0, frozen_steps=0, stream=None):
+        """Testbed::training_network_next_frame without global-movement prediction (call after set_dataset with the new frame)."""
+        check(self._lib.neus2_next_frame(self._h, _stream(stream), C.c_float(after_learning_rate), C.c_uint32(frozen_steps)))
+
+    def time_frame(self):
+        tf, lr = C.c_uint32(), C.c_float()
+        check(self._lib.neus2_get_time_frame(self._h, C.byref(tf), C.byref(lr)))
+        return int(tf.value), float(lr.value)
+
     def optimizer_buffers(self):
         """(first moments fp32, second moments fp32, per-parameter steps int32, current_step) -- zero-copy device views."""
         torch = _torch()

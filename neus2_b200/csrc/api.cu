@@ -70,6 +70,10 @@ struct neus2_ctx {
 	Pcg32 rng, density_grid_rng;
 	uint32_t training_step, rays_per_batch, n_rays_total, measured_before;
 	uint32_t step_rays, step_rays_local, step_n_rays_total;   // of the step in flight
+	// incremental (per-frame) training of a sequence: Testbed::training_network_next_frame (src/testbed.cu:2001-2082)
+	uint32_t time_frame;            // current_training_time_frame
+	uint32_t frozen_steps;          // predict_global_movement_training_step: canonical parameters are frozen for the first steps of frames >= 1
+	float learning_rate;            // current Adam learning rate (after_learning_rate from frame 1 on)
 	bool step_density_updated;
 	uint32_t* h_counters;       // pinned
 	int profiling;              // record CUDA events around the stages of a step
@@ -231,6 +235,7 @@ int neus2_ctx_create(const neus2_config* cfg, int device, neus2_ctx** out) {
 	ctx->measured_before = 0;
 	ctx->training_step = 0;
 	ctx->n_rays_total = 0;
+	ctx->time_frame = 0; ctx->frozen_steps = 0; ctx->learning_rate = cfg->learning_rate;
 	*out = ctx;
 	return 0;
 }
@@ -282,6 +287,11 @@ int neus2_buffers(neus2_ctx* ctx, float** master, void** params, void** ema, flo
 __global__ void k_cast_params(uint64_t n, const float* __restrict__ master, __half* __restrict__ params) {
 	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n) params[i] = __float2half_rn(master[i]);
+}
+
+__global__ void k_widen_params(uint64_t n, const __half* __restrict__ params, float* __restrict__ master) {
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) master[i] = __half2float(params[i]);
 }
 
 int neus2_set_params(neus2_ctx* ctx, const float* master_host, uint64_t n, int reset_optimizer) {
@@ -397,8 +407,9 @@ int neus2_optimizer_step(neus2_ctx* ctx, void* stream, float loss_scale) {
 	const neus2_config& c = ctx->cfg;
 	++ctx->adam_step;
 	stage_begin(ctx, ST_OPT, (cudaStream_t)stream);
-	const int rc_ = launch_adam_ema((cudaStream_t)stream, ctx->n_params, ctx->pl.off_grid, loss_scale, c.learning_rate, c.beta1, c.beta2, c.epsilon, c.l2_reg,
-	                       c.ema_decay, ctx->adam_step, ctx->grads, ctx->master, ctx->params, ctx->m1, ctx->m2, ctx->steps, ctx->ema, ctx->adam_bias_table, ADAM_BIAS_TABLE);
+	const int frozen = ctx->time_frame >= 1 && ctx->training_step < ctx->frozen_steps;   // m_train_canonical = false (testbed.cu:2659-2667)
+	const int rc_ = launch_adam_ema((cudaStream_t)stream, ctx->n_params, ctx->pl.off_grid, loss_scale, ctx->learning_rate, c.beta1, c.beta2, c.epsilon, c.l2_reg,
+	                       c.ema_decay, ctx->adam_step, ctx->grads, ctx->master, ctx->params, ctx->m1, ctx->m2, ctx->steps, ctx->ema, ctx->adam_bias_table, ADAM_BIAS_TABLE, frozen);
 	stage_end(ctx, ST_OPT, (cudaStream_t)stream);
 	return rc_;
 }
@@ -456,7 +467,7 @@ int neus2_train_step_begin(neus2_ctx* ctx, void* stream_, uint32_t rank, uint32_
 	if (!ctx->d_pixels) FAIL("no training data: call neus2_set_dataset first");
 	if (world_size != ctx->cfg.world_size || rank >= world_size) FAIL("rank / world_size do not match the context's config.world_size");
 	const neus2_config& c = ctx->cfg;
-	neus2_set_training_step(ctx, (int32_t)ctx->training_step);                          // testbed.cu:2651-2657
+	neus2_set_training_step(ctx, ctx->time_frame >= 1 ? (int32_t)ctx->training_step - (int32_t)ctx->frozen_steps : (int32_t)ctx->training_step);   // testbed.cu:2651-2657
 	const uint32_t n_prep_to_skip = std::min(std::max(ctx->training_step / 16u, 1u), 16u);   // :2669
 	ctx->step_density_updated = false;
 	stage_begin(ctx, ST_STEP, stream);
@@ -791,8 +802,9 @@ int neus2_optimizer_step_sharded(neus2_ctx* ctx, void* stream, float loss_scale)
 	const neus2_config& c = ctx->cfg;
 	++ctx->adam_step;
 	stage_begin(ctx, ST_OPT, (cudaStream_t)stream);
-	const int rc_ = launch_adam_ema_p2p((cudaStream_t)stream, ctx->n_params, ctx->pl.off_grid, ctx->peer_rank, ctx->peer_world, loss_scale, c.learning_rate, c.beta1, c.beta2,
-	                                    c.epsilon, c.l2_reg, c.ema_decay, ctx->adam_step, ctx->peer_grads, ctx->peer_params, ctx->peer_ema, ctx->master, ctx->m1, ctx->m2, ctx->steps, ctx->adam_bias_table, ADAM_BIAS_TABLE);
+	const int frozen = ctx->time_frame >= 1 && ctx->training_step < ctx->frozen_steps;
+	const int rc_ = launch_adam_ema_p2p((cudaStream_t)stream, ctx->n_params, ctx->pl.off_grid, ctx->peer_rank, ctx->peer_world, loss_scale, ctx->learning_rate, c.beta1, c.beta2,
+	                                    c.epsilon, c.l2_reg, c.ema_decay, ctx->adam_step, ctx->peer_grads, ctx->peer_params, ctx->peer_ema, ctx->master, ctx->m1, ctx->m2, ctx->steps, ctx->adam_bias_table, ADAM_BIAS_TABLE, frozen);
 	stage_end(ctx, ST_OPT, (cudaStream_t)stream);
 	ctx->optimizer_done = true;
 	return rc_;
@@ -851,6 +863,46 @@ int neus2_mesh_attributes(neus2_ctx* ctx, void* stream_, float* normals_out, flo
 
 int neus2_get_counters(neus2_ctx* ctx, uint32_t out[4]) {
 	out[0] = ctx->n_rays_total; out[1] = ctx->measured_before; out[2] = ctx->density_grid_ema_step; out[3] = ctx->adam_step;
+	return 0;
+}
+
+// Testbed::training_network_next_frame (src/testbed.cu:2001-2082) without global-movement prediction: the next frame's images have
+// been installed with neus2_set_dataset; the model continues from its INFERENCE (EMA) weights (save_snapshot_incremental /
+// load_snapshot_incremental round trip, :2059-2060 -> Trainer::deserialize, tcnn trainer.h:295-304), with a fresh optimizer
+// (:2043), the frame's step counters at zero, rays_per_batch back at 4096 and m_rng re-seeded (reset_network_incremental,
+// :2351-2361).  For the first `frozen_steps` steps of the new frame the canonical parameters do not move (m_train_canonical =
+// false until m_training_step == m_predict_global_movement_training_step, :2659-2667) and the progressive-level schedule counts
+// from there; `after_learning_rate` replaces the learning rate (:2688-2690).
+int neus2_next_frame(neus2_ctx* ctx, void* stream_, float after_learning_rate, uint32_t frozen_steps) {
+	cudaStream_t stream = (cudaStream_t)stream_;
+	CUDA_CHECK(cudaSetDevice(ctx->device));
+	const uint64_t n = ctx->n_params;
+	if (ctx->adam_step > 0) {
+		CUDA_CHECK(cudaMemcpyAsync(ctx->params, ctx->ema, n * sizeof(__half), cudaMemcpyDeviceToDevice, stream));
+		k_widen_params<<<(uint32_t)((n + 255) / 256), 256, 0, stream>>>(n, ctx->params, ctx->master);
+		COUNT_LAUNCH(1);
+		CUDA_CHECK(cudaGetLastError());
+	}
+	CUDA_CHECK(cudaMemsetAsync(ctx->m1, 0, n * sizeof(float), stream));
+	CUDA_CHECK(cudaMemsetAsync(ctx->m2, 0, n * sizeof(float), stream));
+	CUDA_CHECK(cudaMemsetAsync(ctx->steps, 0, n * sizeof(uint32_t), stream));
+	CUDA_CHECK(cudaMemsetAsync(ctx->ema, 0, n * sizeof(__half), stream));
+	CUDA_CHECK(cudaStreamSynchronize(stream));
+	ctx->adam_step = 0;
+	ctx->time_frame += 1;
+	ctx->frozen_steps = frozen_steps;
+	if (after_learning_rate > 0.f) ctx->learning_rate = after_learning_rate;
+	ctx->training_step = 0;
+	ctx->n_rays_total = 0;
+	ctx->rays_per_batch = 1u << 12;
+	ctx->measured_before = 0;
+	ctx->rng = Pcg32(ctx->cfg.seed);
+	return 0;
+}
+
+int neus2_get_time_frame(const neus2_ctx* ctx, uint32_t* time_frame, float* learning_rate) {
+	if (time_frame) *time_frame = ctx->time_frame;
+	if (learning_rate) *learning_rate = ctx->learning_rate;
 	return 0;
 }
 

@@ -27,14 +27,14 @@ int launch_compute_loss(cudaStream_t stream, uint32_t n_rays_local, uint32_t n_r
 
 int launch_adam_ema(cudaStream_t stream, uint64_t n, uint64_t n_matrix, float loss_scale, float lr, float beta1, float beta2, float eps, float l2_reg,
                     float ema_decay, uint32_t ema_step, const float* grads, float* master, __half* params, float* m1, float* m2, uint32_t* steps, __half* ema,
-                    float* bias_table, uint32_t bias_table_size);
+                    float* bias_table, uint32_t bias_table_size, int frozen);
 int launch_adam_bias_table(cudaStream_t stream, float beta1, float beta2, uint32_t last, float* bias_table, uint32_t bias_table_size);
 
 #define NEUS2_MAX_PEERS 8
 void optimizer_shard(uint64_t n_quads, uint32_t rank, uint32_t world, uint64_t* q0, uint64_t* q1);
 int launch_adam_ema_p2p(cudaStream_t stream, uint64_t n, uint64_t n_matrix, uint32_t rank, uint32_t world, float loss_scale, float lr, float beta1, float beta2,
                         float eps, float l2_reg, float ema_decay, uint32_t ema_step, const float* const* grads_peers, __half* const* params_peers,
-                        __half* const* ema_peers, float* master, float* m1, float* m2, uint32_t* steps, float* bias_table, uint32_t bias_table_size);
+                        __half* const* ema_peers, float* master, float* m1, float* m2, uint32_t* steps, float* bias_table, uint32_t bias_table_size, int frozen);
 
 int launch_density_grid_samples(cudaStream_t stream, uint32_t n, const uint64_t rng_state[2], uint32_t step, const Aabb& bb, const float* grid_in,
                                 uint32_t n_cascades, float thresh, float* positions, uint32_t* indices);

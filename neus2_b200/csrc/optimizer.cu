@@ -6,7 +6,8 @@
 #include "ngp_kernels.h"
 
 struct AdamHyper { float loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, ema_debias_old, ema_debias_new;
-                   uint32_t cur_step; const float* bias_table; uint32_t bias_table_size; };
+                   uint32_t cur_step; const float* bias_table; uint32_t bias_table_size;
+                   int frozen; };   // frozen: optimize_canonical_params = false (adam.h:92-94) -- every parameter returns early, only the EMA moves
 
 // Bias correction of adam_step (adam.h:149-150) for a parameter whose private step counter reads `cs`:
 // sqrt(1 - beta2^cs) / (1 - beta1^cs).  Two powf per parameter made the kernel issue-bound (83 % issue-active, 40 % of HBM peak
@@ -56,7 +57,7 @@ k_adam_ema(uint64_t n4, uint64_t n_matrix4, AdamHyper h, const float* __restrict
 	uint2 pw = reinterpret_cast<const uint2*>(params)[q];
 	__half* ph = reinterpret_cast<__half*>(&pw);
 	const float g[4] = {g4.x, g4.y, g4.z, g4.w};
-	if (is_matrix || g4.x != 0.f || g4.y != 0.f || g4.z != 0.f || g4.w != 0.f) {
+	if (!h.frozen && (is_matrix || g4.x != 0.f || g4.y != 0.f || g4.z != 0.f || g4.w != 0.f)) {
 		const float cur_factor = adam_bias_factor(h, h.cur_step);
 		float4 w4 = reinterpret_cast<const float4*>(master)[q];
 		float4 a4 = reinterpret_cast<const float4*>(m1)[q];
@@ -91,11 +92,11 @@ k_adam_ema(uint64_t n4, uint64_t n_matrix4, AdamHyper h, const float* __restrict
 
 int launch_adam_ema(cudaStream_t stream, uint64_t n, uint64_t n_matrix, float loss_scale, float lr, float beta1, float beta2, float eps, float l2_reg,
                     float ema_decay, uint32_t ema_step, const float* grads, float* master, __half* params, float* m1, float* m2, uint32_t* steps, __half* ema,
-                    float* bias_table, uint32_t bias_table_size) {
+                    float* bias_table, uint32_t bias_table_size, int frozen) {
 	const float ema_debias_old = 1 - (float)pow((double)ema_decay, (double)(ema_step - 1));
 	const float ema_debias_new = 1.0f / (1 - (float)pow((double)ema_decay, (double)ema_step));
 	if (n % 4 != 0 || n_matrix % 4 != 0) { neus_set_error("parameter counts must be multiples of 4", __FILE__, __LINE__); return -1; }
-	AdamHyper h = {loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, ema_debias_old, ema_debias_new, ema_step, bias_table, bias_table_size};
+	AdamHyper h = {loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, ema_debias_old, ema_debias_new, ema_step, bias_table, bias_table_size, frozen};
 	if (bias_table && ema_step < bias_table_size) { k_adam_bias_table<<<1, 32, 0, stream>>>(h, ema_step, ema_step, bias_table); COUNT_LAUNCH(1); }
 	const uint64_t n4 = n / 4;
 	const uint32_t blocks = (uint32_t)((n4 + 255) / 256);
@@ -131,7 +132,7 @@ k_adam_ema_p2p(uint64_t q0, uint64_t q1, uint64_t n_matrix4, AdamHyper h, int wo
 	uint2 pw = reinterpret_cast<const uint2*>(peers.params[0])[q];     // slot 0 is always this rank's own buffer
 	__half* ph = reinterpret_cast<__half*>(&pw);
 	const float g[4] = {g4.x, g4.y, g4.z, g4.w};
-	if (is_matrix || g4.x != 0.f || g4.y != 0.f || g4.z != 0.f || g4.w != 0.f) {
+	if (!h.frozen && (is_matrix || g4.x != 0.f || g4.y != 0.f || g4.z != 0.f || g4.w != 0.f)) {
 		const float cur_factor = adam_bias_factor(h, h.cur_step);
 		float4 w4 = reinterpret_cast<const float4*>(master)[q];
 		float4 a4 = reinterpret_cast<const float4*>(m1)[q];
@@ -168,12 +169,12 @@ k_adam_ema_p2p(uint64_t q0, uint64_t q1, uint64_t n_matrix4, AdamHyper h, int wo
 
 int launch_adam_ema_p2p(cudaStream_t stream, uint64_t n, uint64_t n_matrix, uint32_t rank, uint32_t world, float loss_scale, float lr, float beta1, float beta2,
                         float eps, float l2_reg, float ema_decay, uint32_t ema_step, const float* const* grads_peers, __half* const* params_peers,
-                        __half* const* ema_peers, float* master, float* m1, float* m2, uint32_t* steps, float* bias_table, uint32_t bias_table_size) {
+                        __half* const* ema_peers, float* master, float* m1, float* m2, uint32_t* steps, float* bias_table, uint32_t bias_table_size, int frozen) {
 	const float ema_debias_old = 1 - (float)pow((double)ema_decay, (double)(ema_step - 1));
 	const float ema_debias_new = 1.0f / (1 - (float)pow((double)ema_decay, (double)ema_step));
 	if (n % 4 != 0 || n_matrix % 4 != 0) { neus_set_error("parameter counts must be multiples of 4", __FILE__, __LINE__); return -1; }
 	if (world < 1 || world > NEUS2_MAX_PEERS || rank >= world) { neus_set_error("bad rank / world size for the sharded optimizer", __FILE__, __LINE__); return -1; }
-	AdamHyper h = {loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, ema_debias_old, ema_debias_new, ema_step, bias_table, bias_table_size};
+	AdamHyper h = {loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, ema_debias_old, ema_debias_new, ema_step, bias_table, bias_table_size, frozen};
 	if (bias_table && ema_step < bias_table_size) { k_adam_bias_table<<<1, 32, 0, stream>>>(h, ema_step, ema_step, bias_table); COUNT_LAUNCH(1); }
 	uint64_t q0, q1;
 	optimizer_shard(n / 4, rank, world, &q0, &q1);

@@ -60,6 +60,13 @@ class Testbed:
         self.camera_matrix = np.array([[1, 0, 0, 0.5], [0, -1, 0, 0.5], [0, 0, -1, 2.0]], dtype=np.float32)
         self.fov = 50.625
         self.first_frame_max_training_step = 2000
+        self.next_frame_max_training_step = 2000
+        self.predict_global_movement = False
+        self.predict_global_movement_training_step = 50
+        self.after_learning_rate = 0.0
+        self.current_training_time_frame = 0
+        self.all_training_time_frame = 1
+        self._json_paths = []
         self.loss = 0.0
         self.ek_loss = 0.0
         self.mask_loss = 0.0
@@ -85,6 +92,13 @@ class Testbed:
         self._cfg_kwargs = loader.config_from_json(cfg_json)
         hp = cfg_json.get("hyperparams", {})
         self.first_frame_max_training_step = int(hp.get("first_frame_max_training_step", self.first_frame_max_training_step))
+        self.next_frame_max_training_step = int(hp.get("next_frame_max_training_step", self.next_frame_max_training_step))
+        self.predict_global_movement = bool(hp.get("predict_global_movement", False))          # testbed.cu:2129
+        self.predict_global_movement_training_step = int(hp.get("predict_global_movement_training_step", 50))
+        leaf = cfg_json.get("optimizer", {})
+        while "nested" in leaf:
+            leaf = leaf["nested"]
+        self.after_learning_rate = float(leaf.get("after_learning_rate", leaf.get("learning_rate", 1e-3)))
         self.nerf.training.linear_colors = bool(hp.get("linear_color", False))
         if self.nerf.training.linear_colors:
             raise RuntimeError("train_in_linear_colors is not built (base.json trains in sRGB)")
@@ -92,7 +106,11 @@ class Testbed:
 
     def load_training_data(self, path):
         """Testbed::load_training_data (testbed.cu:196-262) for Nerf mode."""
-        self._data = loader.load_nerf(path)
+        # a directory of jsons is a SEQUENCE: one json per time frame, the first one is loaded now (Testbed::load_nerf, testbed_nerf.cu:2964-3002)
+        self._json_paths = [p for p in loader.list_json_paths(path) if "downsample" not in os.path.basename(p)]
+        self.all_training_time_frame = len(self._json_paths)
+        self.current_training_time_frame = 0
+        self._data = loader.load_nerf(self._json_paths[0])
         if self._data["aabb_scale"] != 1:
             raise RuntimeError("aabb_scale != 1 is not built (NeuS2 object-centric scenes use 1)")
         self.nerf.training.n_images_for_training = len(self._data["paths"])
@@ -126,11 +144,41 @@ class Testbed:
     def training_step(self):
         return 0 if self._ctx is None else self._ctx.get_state()["training_step"]
 
+    def _max_step(self):
+        return self.first_frame_max_training_step if self.current_training_time_frame == 0 else self.next_frame_max_training_step
+
     def frame(self):
-        """Testbed::frame (testbed.cu:1700-1850) without a window: one training step while shall_train, returns True."""
-        if self.shall_train and self._ctx is not None and self.training_step < self.first_frame_max_training_step:
-            self.train(1 << 18)
+        """Testbed::frame (testbed.cu:1700-1850) without a window: when the current time frame has had its steps, move on to the
+        next one (testbed.cu:1750-1756), then one training step while shall_train.  Unlike the reference, which leaves stopping to
+        its scripts, the last frame simply stops training at its step budget.  Returns True."""
+        if self._ctx is None or not self.shall_train:
+            return True
+        if self.training_step >= self._max_step():
+            if self.current_training_time_frame >= self.all_training_time_frame - 1:
+                return True
+            self.training_network_next_frame()
+        self.train(1 << 18)
         return True
+
+    def training_network_next_frame(self):
+        """Testbed::training_network_next_frame (testbed.cu:2001-2082) for "predict_global_movement": false."""
+        if self.current_training_time_frame >= self.all_training_time_frame - 1:
+            return False                                              # "alread last frame"
+        if self.predict_global_movement:
+            raise RuntimeError("global movement prediction (DeltaNetwork / rotation-6d) is not built: set hyperparams.predict_global_movement to false")
+        ctx = self._need_ctx()
+        self.current_training_time_frame += 1
+        self._data = loader.load_nerf(self._json_paths[self.current_training_time_frame])
+        d = self._data
+        ctx.set_dataset(d["pixels"], d["focal"], d["principal"], d["xforms"])
+        ctx.next_frame(after_learning_rate=self.after_learning_rate, frozen_steps=self.predict_global_movement_training_step)
+        return True
+
+    def change_to_frame(self, i):
+        """python_api.cu `change_to_frame`: load the images / cameras of time frame i (for rendering and evaluation)."""
+        if not 0 <= i < self.all_training_time_frame:
+            raise RuntimeError("frame index out of range")
+        self._data = loader.load_nerf(self._json_paths[i])
 
     def train(self, batch_size=1 << 18):
         ctx = self._need_ctx()
