@@ -28,7 +28,7 @@ def _worker(rank, world, port, out_dir, mode, steps):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
     B = 1 << 15
-    ctx = N.Context(N.default_config(batch_size=B, world_size=world, max_rays_per_batch=1 << 16), device=rank)
+    ctx = N.Context(N.default_config(batch_size=B * (world // 2), world_size=world, max_rays_per_batch=(1 << 15) * world), device=rank)
     data = synthetic.render_sphere_views(n_views=6, width=128, height=96, seed=2)
     ctx.set_dataset(data["pixels"], data["focal"], data["principal"], data["xforms"])
     ctx.init_params()
@@ -55,17 +55,21 @@ def runs(tmp_path_factory):
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
+    world = min(torch.cuda.device_count(), 8)            # every GPU of the box: 2 on the small lease, 8 on the full one
     out = tmp_path_factory.mktemp("dp")
     for mode in ("nccl", "p2p"):
-        mp.spawn(_worker, args=(2, _free_port(), str(out), mode, 24), nprocs=2, join=True)
-    return {f"{m}_r{r}": np.load(out / f"{m}_r{r}.npz") for m in ("nccl", "p2p") for r in (0, 1)}
+        mp.spawn(_worker, args=(world, _free_port(), str(out), mode, 24), nprocs=world, join=True)
+    runs = {f"{m}_r{r}": np.load(out / f"{m}_r{r}.npz") for m in ("nccl", "p2p") for r in range(world)}
+    runs["world"] = world
+    return runs
 
 
 def test_ranks_hold_identical_parameters(runs):
     for m in ("nccl", "p2p"):
-        assert np.array_equal(runs[f"{m}_r0"]["params"], runs[f"{m}_r1"]["params"])
-        assert np.array_equal(runs[f"{m}_r0"]["ema"], runs[f"{m}_r1"]["ema"])
-        assert np.array_equal(runs[f"{m}_r0"]["stats"], runs[f"{m}_r1"]["stats"])
+        for r in range(1, runs["world"]):
+            assert np.array_equal(runs[f"{m}_r0"]["params"], runs[f"{m}_r{r}"]["params"]), (m, r)
+            assert np.array_equal(runs[f"{m}_r0"]["ema"], runs[f"{m}_r{r}"]["ema"]), (m, r)
+            assert np.array_equal(runs[f"{m}_r0"]["stats"], runs[f"{m}_r{r}"]["stats"]), (m, r)
 
 
 def test_fused_peer_optimizer_equals_allreduce_then_adam(runs):
@@ -83,9 +87,11 @@ def test_fused_peer_optimizer_equals_allreduce_then_adam(runs):
 
 
 def test_shards_partition_the_parameters(runs):
-    s0, s1 = runs["p2p_r0"]["shard"], runs["p2p_r1"]["shard"]
-    assert s0[0] == 0 and s0[1] == s1[0] and s1[1] == 10559396 and s0[1] % 4 == 0
+    W = runs["world"]
+    shards = [runs[f"p2p_r{r}"]["shard"] for r in range(W)]
+    assert shards[0][0] == 0 and shards[-1][1] == 10559396
+    assert all(shards[r][1] == shards[r + 1][0] and shards[r][1] % 4 == 0 for r in range(W - 1))
     # each rank's fp32 master slice rounds to the fp16 parameters every rank holds
-    for r, s in ((0, s0), (1, s1)):
+    for r, s in enumerate(shards):
         m = runs[f"p2p_r{r}"]["master_shard"]
         assert np.array_equal(m.astype(np.float16).view(np.uint16), runs["p2p_r0"]["params"][s[0]:s[1]])
