@@ -9,8 +9,8 @@
 // B200 design: three launches per frame and no host synchronisation.
 //   k_render_init    one thread per pixel: camera ray, box entry, Sobol start jitter, skip to the first occupied cell;
 //                    rays that survive are appended to a compact queue (warp-aggregated counter).
-//   k_render_march   persistent; every warp owns 16 ray slots (lanes 0..15).  Per iteration each slot marches to its next
-//                    sample, the warp runs the whole network on the 16 samples with the same register/shared-memory
+//   k_render_march   persistent; every warp owns 32 ray slots (one per lane).  Per iteration each slot marches to its next
+//                    sample, the warp runs the whole network on the samples 16 at a time with the same register/shared-memory
 //                    pipeline as the training forward (forward_tile), and each lane composites its own sample.  A slot
 //                    whose ray leaves the box or saturates pulls the next ray from the queue, so tiles stay full until the
 //                    queue drains.  Sample coordinates and the 16-wide network outputs never touch HBM.
@@ -164,7 +164,8 @@ k_render_march(GridMeta gm, ParamLayout pl, const __half* __restrict__ params, f
 	const uint32_t n_queue = counters[0];
 	const float tdiag[3] = {train_aabb.mx[0] - train_aabb.mn[0], train_aabb.mx[1] - train_aabb.mn[1], train_aabb.mx[2] - train_aabb.mn[2]};
 
-	// per-lane ray slot (lanes 0..15)
+	// per-lane ray slot: ALL 32 lanes own a ray (marching and compositing are per-lane work); the network runs twice per
+	// iteration, on the samples of lanes 0..15 and then of lanes 16..31 (a half with no live ray is skipped)
 	bool have = false;
 	float o[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 1.f}, idir[3] = {0.f, 0.f, 1.f}, t = 0.f;
 	float rgba[4] = {0.f, 0.f, 0.f, 0.f}, depth = 0.f, max_weight = 0.f;
@@ -173,90 +174,97 @@ k_render_march(GridMeta gm, ParamLayout pl, const __half* __restrict__ params, f
 	FwdState st;
 
 	while (true) {
-		if (lane < 16) {
-			while (true) {
-				if (!have) {
-					if (exhausted) break;
-					const uint32_t r = atomicAdd(counters + 1, 1u);
-					if (r >= n_queue) { exhausted = true; break; }
-					const float4* q = reinterpret_cast<const float4*>(queue + r);
-					const float4 a = q[0], b = q[1];
-					o[0] = a.x; o[1] = a.y; o[2] = a.z; d[0] = a.w; d[1] = b.x; d[2] = b.y; t = b.z; idx = __float_as_uint(b.w);
-					idir[0] = 1.0f / d[0]; idir[1] = 1.0f / d[1]; idir[2] = 1.0f / d[2];
-					rgba[0] = rgba[1] = rgba[2] = rgba[3] = 0.f; depth = 0.f; max_weight = 0.f; n_samples = 0;
-					have = true;
-				}
-				// generate_next_nerf_network_inputs, one step (:919-936)
-				float pos[3], dt = 0.f;
-				bool inside = true;
-				while (true) {
-					#pragma unroll
-					for (int k = 0; k < 3; ++k) pos[k] = fmaf(d[k], t, o[k]);
-					if (!aabb_contains(render_aabb, pos)) { inside = false; break; }
-					dt = calc_dt(t, cone_angle);
-					const uint32_t mip = (uint32_t)mip_from_dt(dt, pos);
-					if (density_grid_occupied_at(pos, bitfield, mip)) break;
-					t = advance_to_next_voxel(t, cone_angle, pos, d, idir, NERF_GRIDSIZE >> mip);
-				}
-				if (!inside) {   // the ray left the box: it is compacted away (compact_kernel_nerf :2183-2204)
-					if (rgba[3] > 0.001f) { ray_rgba[idx] = make_float4(rgba[0], rgba[1], rgba[2], rgba[3]); ray_depth[idx] = depth; }
-					if (ray_samples) ray_samples[idx] = n_samples;
-					have = false;
-					continue;
-				}
-				float* c = sCoord + lane * 7;
-				#pragma unroll
-				for (int k = 0; k < 3; ++k) c[k] = (pos[k] - train_aabb.mn[k]) / tdiag[k];
-				c[3] = warp_dt(dt);
-				#pragma unroll
-				for (int k = 0; k < 3; ++k) c[4 + k] = (d[k] + 1.0f) * 0.5f;
-				t += dt;
-				break;
-			}
+		float c[7];   // this lane's sample (NerfCoordinate), kept in registers until its half's turn
+		while (true) {
 			if (!have) {
-				float* c = sCoord + lane * 7;
-				#pragma unroll
-				for (int k = 0; k < 7; ++k) c[k] = 0.5f;
+				if (exhausted) break;
+				const uint32_t r = atomicAdd(counters + 1, 1u);
+				if (r >= n_queue) { exhausted = true; break; }
+				const float4* q = reinterpret_cast<const float4*>(queue + r);
+				const float4 a = q[0], b = q[1];
+				o[0] = a.x; o[1] = a.y; o[2] = a.z; d[0] = a.w; d[1] = b.x; d[2] = b.y; t = b.z; idx = __float_as_uint(b.w);
+				idir[0] = 1.0f / d[0]; idir[1] = 1.0f / d[1]; idir[2] = 1.0f / d[2];
+				rgba[0] = rgba[1] = rgba[2] = rgba[3] = 0.f; depth = 0.f; max_weight = 0.f; n_samples = 0;
+				have = true;
 			}
-		}
-		const uint32_t active = __ballot_sync(0xffffffffu, lane < 16 && have);
-		if (!active) break;
-		__syncwarp();
-		forward_tile<false>(gm, params, pl, sw, slab, sdf_bias, lane, st);
-		// composite_kernel_nerf (:939-1168), one sample
-		if (lane < 16 && have) {
-			const __half* orow = sOUT + lane * 16;
-			const float* cin = sCoord + lane * 7;
-			float dv[3] = {__half2float(orow[8]) * 2.0f - 1.0f, __half2float(orow[9]) * 2.0f - 1.0f, __half2float(orow[10]) * 2.0f - 1.0f}, dir[3];   // BENT_DIR
-			normalize3(dv, dir);
-			const SampleEval e = eval_sample(orow, cin, dir, cos_anneal_ratio);
-			const float T = 1.f - rgba[3];
-			const float weight = e.alpha * T;
-			#pragma unroll
-			for (int k = 0; k < 3; ++k) rgba[k] = fmaf(e.rgb[k], weight, rgba[k]);
-			rgba[3] += weight;
-			++n_samples; ++total_samples;
-			if (weight > max_weight) {
-				max_weight = weight;
-				float pos[3];
+			// generate_next_nerf_network_inputs, one step (:919-936)
+			float pos[3], dt = 0.f;
+			bool inside = true;
+			while (true) {
 				#pragma unroll
-				for (int k = 0; k < 3; ++k) pos[k] = fmaf(cin[k], tdiag[k], train_aabb.mn[k]);
-				depth = fmaf(cam_fwd2, pos[2] - cam_pos2, fmaf(cam_fwd1, pos[1] - cam_pos1, cam_fwd0 * (pos[0] - cam_pos0)));
+				for (int k = 0; k < 3; ++k) pos[k] = fmaf(d[k], t, o[k]);
+				if (!aabb_contains(render_aabb, pos)) { inside = false; break; }
+				dt = calc_dt(t, cone_angle);
+				const uint32_t mip = (uint32_t)mip_from_dt(dt, pos);
+				if (density_grid_occupied_at(pos, bitfield, mip)) break;
+				t = advance_to_next_voxel(t, cone_angle, pos, d, idir, NERF_GRIDSIZE >> mip);
 			}
-			if (rgba[3] > (1.0f - min_transmittance)) {
-				const float w = rgba[3];
-				if (w > 0.001f) { ray_rgba[idx] = make_float4(rgba[0] / w, rgba[1] / w, rgba[2] / w, w / w); ray_depth[idx] = depth; }
+			if (!inside) {   // the ray left the box: it is compacted away (compact_kernel_nerf :2183-2204)
+				if (rgba[3] > 0.001f) { ray_rgba[idx] = make_float4(rgba[0], rgba[1], rgba[2], rgba[3]); ray_depth[idx] = depth; }
 				if (ray_samples) ray_samples[idx] = n_samples;
 				have = false;
+				continue;
 			}
+			#pragma unroll
+			for (int k = 0; k < 3; ++k) c[k] = (pos[k] - train_aabb.mn[k]) / tdiag[k];
+			c[3] = warp_dt(dt);
+			#pragma unroll
+			for (int k = 0; k < 3; ++k) c[4 + k] = (d[k] + 1.0f) * 0.5f;
+			t += dt;
+			break;
 		}
-		__syncwarp();
+		if (!have) {
+			#pragma unroll
+			for (int k = 0; k < 7; ++k) c[k] = 0.5f;
+		}
+		const uint32_t active = __ballot_sync(0xffffffffu, have);
+		if (!active) break;
+		#pragma unroll 1
+		for (int half = 0; half < 2; ++half) {
+			if (!((active >> (16 * half)) & 0xffffu)) continue;        // warp-uniform
+			const bool mine = (lane >> 4) == half;
+			if (mine) {
+				float* cs = sCoord + (lane & 15) * 7;
+				#pragma unroll
+				for (int k = 0; k < 7; ++k) cs[k] = c[k];
+			}
+			__syncwarp();
+			forward_tile<false>(gm, params, pl, sw, slab, sdf_bias, lane, st);
+			// composite_kernel_nerf (:939-1168), one sample
+			if (mine && have) {
+				const __half* orow = sOUT + (lane & 15) * 16;
+				float dv[3] = {__half2float(orow[8]) * 2.0f - 1.0f, __half2float(orow[9]) * 2.0f - 1.0f, __half2float(orow[10]) * 2.0f - 1.0f}, dir[3];   // BENT_DIR
+				normalize3(dv, dir);
+				const SampleEval e = eval_sample(orow, c, dir, cos_anneal_ratio);
+				const float T = 1.f - rgba[3];
+				const float weight = e.alpha * T;
+				#pragma unroll
+				for (int k = 0; k < 3; ++k) rgba[k] = fmaf(e.rgb[k], weight, rgba[k]);
+				rgba[3] += weight;
+				++n_samples; ++total_samples;
+				if (weight > max_weight) {
+					max_weight = weight;
+					float pos[3];
+					#pragma unroll
+					for (int k = 0; k < 3; ++k) pos[k] = fmaf(c[k], tdiag[k], train_aabb.mn[k]);
+					depth = fmaf(cam_fwd2, pos[2] - cam_pos2, fmaf(cam_fwd1, pos[1] - cam_pos1, cam_fwd0 * (pos[0] - cam_pos0)));
+				}
+				if (rgba[3] > (1.0f - min_transmittance)) {
+					const float w = rgba[3];
+					if (w > 0.001f) { ray_rgba[idx] = make_float4(rgba[0] / w, rgba[1] / w, rgba[2] / w, w / w); ray_depth[idx] = depth; }
+					if (ray_samples) ray_samples[idx] = n_samples;
+					have = false;
+				}
+			}
+			__syncwarp();
+		}
 	}
 	// statistics: samples pushed through the network
 	total_samples += __shfl_xor_sync(0xffffffffu, total_samples, 1);
 	total_samples += __shfl_xor_sync(0xffffffffu, total_samples, 2);
 	total_samples += __shfl_xor_sync(0xffffffffu, total_samples, 4);
 	total_samples += __shfl_xor_sync(0xffffffffu, total_samples, 8);
+	total_samples += __shfl_xor_sync(0xffffffffu, total_samples, 16);
 	if (lane == 0 && total_samples) atomicAdd(counters + 2, total_samples);
 }
 
