@@ -226,6 +226,9 @@ __device__ __forceinline__ void level_geom(const GridMeta& gm, int l, float x, f
 #ifndef GATHER_BATCH_FWD
 #define GATHER_BATCH_FWD 2      // inference kernels: registers are free during the gather
 #endif
+#ifndef GATHER_BATCH_SDF
+#define GATHER_BATCH_SDF 4      // SDF-only kernels (occupancy refresh, lattice): nothing else is live, 4 levels in flight measured fastest
+#endif
 #ifndef GATHER_BATCH_TRAIN
 #define GATHER_BATCH_TRAIN 2    // training kernel: per-warp accumulators are live across the gather
 #endif
@@ -475,7 +478,7 @@ __device__ __forceinline__ void sdf_tile(const GridMeta& gm, const __half* __res
 		for (int d = 0; d < 3; ++d) sX0[lane * LD_X0 + d] = __hsub(__float2half_rn(sCoord[lane * 7 + d]), __float2half_rn(0.5f));
 		for (int k = 3 + 2 * (int)gm.n_levels; k < SDF_IN; ++k) sX0[lane * LD_X0 + k] = __float2half(0.f);
 	}
-	gather_tile<false, GATHER_BATCH_FWD>(gm, grid, sCoord, sX0, nullptr, lane);
+	gather_tile<false, GATHER_BATCH_SDF>(gm, grid, sCoord, sX0, nullptr, lane);
 	__syncwarp();
 	uint32_t xa[2][4], h0a[4][4];
 	load_a_frag(xa[0], sX0, LD_X0, 0, g, t);
