@@ -169,6 +169,9 @@ typedef struct neus2_render_params {
 	int32_t to_srgb;                 /* render(linear=False) */
 	int32_t use_inference_params;    /* 1 = EMA weights, as the reference renders */
 	int32_t tile_x0, tile_y0, tile_w, tile_h;   /* 0, 0, width, height = whole image; tiles of one image are independent */
+	/* interleaved rows (one call renders a GPU's share of a frame that is dealt in row blocks): tile row ry is image row
+	 * tile_y0 + (ry / row_block) * row_block * row_stride + ry % row_block.  row_block = 0: contiguous rows. */
+	int32_t row_block, row_stride;
 } neus2_render_params;
 void neus2_default_render_params(neus2_render_params* p, int32_t width, int32_t height);
 /* rgba_out_dev: [tile_h][tile_w][4] float (the surface render_to_cpu copies out); depth_out_dev: [tile_h][tile_w] float or NULL. */

@@ -44,6 +44,7 @@ class RenderParams(C.Structure):
         ("camera_matrix", C.c_float * 12), ("sample_index", C.c_uint32), ("snap_to_pixel_centers", C.c_int32),
         ("min_transmittance", C.c_float), ("background_color", C.c_float * 4), ("exposure", C.c_float), ("to_srgb", C.c_int32),
         ("use_inference_params", C.c_int32), ("tile_x0", C.c_int32), ("tile_y0", C.c_int32), ("tile_w", C.c_int32), ("tile_h", C.c_int32),
+        ("row_block", C.c_int32), ("row_stride", C.c_int32),
     ]
 
 

@@ -681,8 +681,14 @@ int neus2_render(neus2_ctx* ctx, void* stream_, const neus2_render_params* p, fl
 	cudaStream_t stream = (cudaStream_t)stream_;
 	CUDA_CHECK(cudaSetDevice(ctx->device));
 	if (!p || !rgba_out) FAIL("null argument");
-	if (p->width <= 0 || p->height <= 0 || p->tile_w < 0 || p->tile_h < 0 || p->tile_x0 < 0 || p->tile_y0 < 0 ||
-	    p->tile_x0 + p->tile_w > p->width || p->tile_y0 + p->tile_h > p->height) FAIL("render tile outside the image");
+	if (p->width <= 0 || p->height <= 0 || p->tile_w < 0 || p->tile_h < 0 || p->tile_x0 < 0 || p->tile_y0 < 0 || p->row_block < 0 ||
+	    p->tile_x0 + p->tile_w > p->width) FAIL("render tile outside the image");
+	{   // last image row the tile touches
+		const int ry = p->tile_h - 1;
+		const int last = p->tile_h == 0 ? p->tile_y0 : p->tile_y0 + (p->row_block > 0 ? (ry / p->row_block) * p->row_block * p->row_stride + ry % p->row_block : ry);
+		if (p->row_block > 0 && p->row_stride < 1) FAIL("row_stride must be >= 1");
+		if (last >= p->height) FAIL("render tile outside the image");
+	}
 	if (!(p->focal_length[0] > 0.f) || !(p->focal_length[1] > 0.f)) FAIL("focal length must be positive");
 	const size_t n = (size_t)p->tile_w * p->tile_h;
 	if (n == 0) return 0;
@@ -697,6 +703,7 @@ int neus2_render(neus2_ctx* ctx, void* stream_, const neus2_render_params* p, fl
 	memcpy(r.background_color, p->background_color, sizeof(r.background_color));
 	r.exposure = p->exposure; r.to_srgb = p->to_srgb;
 	r.tile_x0 = p->tile_x0; r.tile_y0 = p->tile_y0; r.tile_w = p->tile_w; r.tile_h = p->tile_h;
+	r.row_block = p->row_block; r.row_stride = p->row_stride;
 	const neus2_config& c = ctx->cfg;
 	const float cos_anneal_ratio = c.anneal_end == 0 ? 1.0f : (float)std::min(1.0, (double)((float)ctx->training_step / c.anneal_end));
 	// m_render_aabb == m_aabb unless the user crops (testbed_nerf.cu:3077)

@@ -55,6 +55,7 @@ struct RenderLaunch {
 	float exposure;
 	int32_t to_srgb;
 	int32_t tile_x0, tile_y0, tile_w, tile_h;
+	int32_t row_block, row_stride;   // interleaved rows, see neus2_render_params
 };
 // queue: 32 B per tile pixel; counters: 4 x u32; ray_rgba / accumulate / out: float4 per tile pixel; ray_depth, depth_out (nullable): float;
 // ray_samples (nullable): u32 per tile pixel = samples composited along the ray.

@@ -73,6 +73,7 @@ struct RenderView {
 	float pixel_offset[2];      // ld_random_pixel_offset(snap ? 0 : spp): the same for every pixel of a frame, evaluated once on the host (integer + exact float ops)
 	uint32_t sample_index;
 	int32_t x0, y0, w, h;       // tile
+	int32_t row_block, row_stride;
 };
 
 struct RayPayload { float o[3], d[3], t; uint32_t idx; };   // 32 bytes
@@ -88,7 +89,8 @@ k_render_init(RenderView v, Aabb render_aabb, GlobalMove gmv, const uint8_t* __r
 	if (in_tile) {
 		ray_rgba[tp] = make_float4(0.f, 0.f, 0.f, 0.f);
 		ray_depth[tp] = 0.f;
-		const int px = v.x0 + (int)(tp % (uint32_t)v.w), py = v.y0 + (int)(tp / (uint32_t)v.w);
+		const int ry = (int)(tp / (uint32_t)v.w);
+		const int px = v.x0 + (int)(tp % (uint32_t)v.w), py = v.y0 + (v.row_block > 0 ? (ry / v.row_block) * v.row_block * v.row_stride + ry % v.row_block : ry);
 		const uint32_t idx = (uint32_t)px + (uint32_t)v.width * (uint32_t)py;
 		// pixel_to_ray (common_device.cuh:246-299)
 		const float off[2] = {v.pixel_offset[0], v.pixel_offset[1]};
@@ -311,6 +313,7 @@ int launch_render(cudaStream_t stream, const GridMeta& gm, const ParamLayout& pl
 		for (int k = 0; k < 2; ++k) { const float o = (0.5f - a[k]) + b[k]; v.pixel_offset[k] = o - floorf(o); }
 	}
 	v.x0 = r.tile_x0; v.y0 = r.tile_y0; v.w = r.tile_w; v.h = r.tile_h;
+	v.row_block = r.row_block; v.row_stride = r.row_stride;
 	CUDA_CHECK(cudaMemsetAsync(counters, 0, 4 * sizeof(uint32_t), stream));
 	k_render_init<<<(n + 127) / 128, 128, 0, stream>>>(v, render_aabb, gmv, bitfield, cone_angle, (RayPayload*)queue, counters, (float4*)ray_rgba, ray_depth);
 	const int sms = device_sm_count();

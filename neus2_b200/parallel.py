@@ -102,28 +102,29 @@ def interleaved_rows(n_rows, rank, world_size, chunk=16):
 
 
 def render(ctx, params, spp=1, rank=0, world_size=1, group=None, chunk=16):
-    """Testbed::render_to_cpu with the image rows dealt across GPUs (tiles of a frame are independent: every pixel's ray,
-    Sobol jitter and colour depend only on its own index).  Returns the whole [H, W, 4] image on every rank."""
+    """Testbed::render_to_cpu with the image rows dealt across GPUs in blocks of `chunk` rows, round-robin (tiles of a frame are
+    independent: every pixel's ray, Sobol jitter and colour depend only on its own index).  A rank renders its whole share in ONE
+    call (interleaved-row tile): the persistent march kernel needs thousands of rays in flight, a 16-row strip alone would be
+    latency-bound.  Returns the whole [H, W, 4] image on every rank."""
     import torch
     import torch.distributed as dist
     if world_size == 1:
         params.tile_x0, params.tile_y0, params.tile_w, params.tile_h = 0, 0, params.width, params.height
+        params.row_block, params.row_stride = 0, 0
         return ctx.render(params, spp=spp)
-    mine = []
-    for (y0, y1) in interleaved_rows(params.height, rank, world_size, chunk):
-        params.tile_x0, params.tile_w, params.tile_y0, params.tile_h = 0, params.width, y0, y1 - y0
-        mine.append(ctx.render(params, spp=spp).clone())
-    rows_max = max(sum(y1 - y0 for y0, y1 in interleaved_rows(params.height, r, world_size, chunk)) for r in range(world_size))
-    ref = mine[0] if mine else None
-    if ref is None:
+    mine = interleaved_rows(params.height, rank, world_size, chunk)
+    if not mine:
         raise ValueError("more ranks than row chunks: lower `chunk`")
-    pad = torch.zeros((rows_max, params.width, 4), dtype=ref.dtype, device=ref.device)
-    if mine:
-        local = torch.cat(mine, dim=0)
-        pad[: local.shape[0]] = local
+    params.tile_x0, params.tile_w = 0, params.width
+    params.tile_y0, params.tile_h = mine[0][0], sum(y1 - y0 for y0, y1 in mine)
+    params.row_block, params.row_stride = chunk, world_size
+    local = ctx.render(params, spp=spp)
+    rows_max = max(sum(y1 - y0 for y0, y1 in interleaved_rows(params.height, r, world_size, chunk)) for r in range(world_size))
+    pad = torch.zeros((rows_max, params.width, 4), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
     parts = [torch.empty_like(pad) for _ in range(world_size)]
     dist.all_gather(parts, pad, group=group)
-    out = torch.empty((params.height, params.width, 4), dtype=ref.dtype, device=ref.device)
+    out = torch.empty((params.height, params.width, 4), dtype=local.dtype, device=local.device)
     for r in range(world_size):
         off = 0
         for (y0, y1) in interleaved_rows(params.height, r, world_size, chunk):

@@ -126,7 +126,9 @@ class _FakeCtx:
     pixel / lattice index, which is the property the real kernels have (tests/test_gpu_render_mesh.py proves it on the GPU)."""
 
     def render(self, p, spp=1):
-        ys = torch.arange(p.tile_y0, p.tile_y0 + p.tile_h, dtype=torch.float32)[:, None, None]
+        ry = torch.arange(p.tile_h)
+        rows = p.tile_y0 + ((ry // p.row_block) * p.row_block * p.row_stride + ry % p.row_block if getattr(p, "row_block", 0) else ry)
+        ys = rows.to(torch.float32)[:, None, None]
         xs = torch.arange(p.tile_x0, p.tile_x0 + p.tile_w, dtype=torch.float32)[None, :, None]
         return (ys * 1000 + xs + torch.arange(4, dtype=torch.float32)[None, None, :] * 0.25) * spp
 
@@ -140,6 +142,7 @@ class _FakeCtx:
 class _P:
     width, height = 13, 11
     tile_x0 = tile_y0 = tile_w = tile_h = 0
+    row_block = row_stride = 0
 
 
 def _infer_worker(rank, world, port, out_dir):

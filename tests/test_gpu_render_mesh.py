@@ -241,3 +241,21 @@ def test_operators_accept_empty_and_single_sample_batches(scene):
     many[0] = one[0]
     assert torch.equal(ctx.forward(one)[0].view(torch.int16), ctx.forward(many)[0].view(torch.int16))
     assert ctx.sdf(one[:, :3].contiguous()).shape == (1,)
+
+
+def test_render_interleaved_rows_equal_whole_image(scene):
+    """One call renders a GPU's share of a frame dealt in row blocks (row_block / row_stride): bit-identical to those rows of the whole."""
+    import torch
+    ctx = scene["ctx"]
+    rp, _ = _params(scene, view=0)
+    whole = ctx.render(rp, spp=1).clone()
+    block, stride = 6, 3
+    for r in range(stride):
+        rows = [y for y in range(H) if (y // block) % stride == r]
+        rp.tile_x0, rp.tile_w, rp.tile_y0, rp.tile_h = 0, W, r * block, len(rows)
+        rp.row_block, rp.row_stride = block, stride
+        part = ctx.render(rp, spp=1)
+        assert torch.equal(part, whole[torch.tensor(rows, device="cuda")])
+    rp.tile_h += block * stride            # runs past the last image row
+    with pytest.raises(Exception):
+        ctx.render(rp)
