@@ -9,6 +9,9 @@
 
 static constexpr int FWD_SMEM = WeightSmem::FWD_END * 2 + WARPS_PER_CTA * WarpSlab::FWD_END;
 #define WARPS_BWD 12
+#ifndef MERGE_MAX_HEADS
+#define MERGE_MAX_HEADS 10     // pre-reduce a level's atomics in the warp when its 16 samples fall into <= this many runs of equal cells
+#endif
 static constexpr int BWD_SMEM = WeightSmem::BWD_END * 2 + WARPS_BWD * WarpSlab::BWD_END;
 
 // A tile's coords (16 x 7 floats) travel global -> registers -> warp slab: the loads for the NEXT tile are issued before the
@@ -355,7 +358,7 @@ k_network_fwdbwd(GridMeta gm, ParamLayout pl, const __half* __restrict__ params,
 				const bool head = (s == 0) || ka != pa || kb != pb;
 				const uint32_t heads = __ballot_sync(half_mask, head);
 				bool issue = active;
-				if (__popc(heads) <= 10) {   // enough merging to pay for the reduction (coarse levels); uniform per half-warp
+				if (__popc(heads) <= MERGE_MAX_HEADS) {   // enough merging to pay for the reduction (coarse levels); uniform per half-warp
 					const uint32_t hs16 = (heads >> (lane & 16)) & 0xffffu;
 					const int run = __popc(hs16 & ((2u << s) - 1u));
 					#pragma unroll

@@ -54,21 +54,18 @@ __device__ __forceinline__ uint32_t march_ray_warp(const Aabb& bb, const float r
 	bool done = false;
 	while (!done) {
 		// chain positions of this window (sequential fp32 adds, identical in every lane)
-		float tl = t_start, t_mine = t_start;
-		if (cone_angle == 0.0f) {   // aabb_scale 1 (testbed_nerf.cu:3090): calc_dt(t, 0) = clamp(t * 0) is the constant minimum step -> 32 plain adds
+		// lane L takes the first L steps of the chain (predicated adds: the same sequence of fp32 additions in every lane)
+		float t_mine = t_start;
+		if (cone_angle == 0.0f) {   // aabb_scale 1 (testbed_nerf.cu:3090): calc_dt(t, 0) = clamp(t * 0) is the constant minimum step
 			const float dt0 = calc_dt(t_start, 0.0f);
 			#pragma unroll
-			for (int L = 0; L < 32; ++L) {
-				if (lane == L) t_mine = tl;
-				tl += dt0;
-			}
+			for (int k = 0; k < 31; ++k) if (k < lane) t_mine += dt0;
 		} else {
 			#pragma unroll
-			for (int L = 0; L < 32; ++L) {
-				if (lane == L) t_mine = tl;
-				tl += calc_dt(tl, cone_angle);
-			}
+			for (int k = 0; k < 31; ++k) if (k < lane) t_mine += calc_dt(t_mine, cone_angle);
 		}
+		float tl = __shfl_sync(0xffffffffu, t_mine, 31);
+		tl += calc_dt(tl, cone_angle);   // chain position 32 = start of the next window
 		float pos[3];
 		#pragma unroll
 		for (int k = 0; k < 3; ++k) pos[k] = fmaf(t_mine, dir[k], ray_o[k]);
@@ -226,20 +223,14 @@ k_rays_emit(uint32_t n_rays, uint32_t ray_offset, Aabb bb, float cone_angle, con
 	uint32_t j = 0;
 	for (uint32_t wi = 0; wi < nw; ++wi) {
 		const WindowRec rec = w[wi];
-		float tl = rec.t_start, t_mine = rec.t_start;
+		float t_mine = rec.t_start;
 		if (cone_angle == 0.0f) {   // constant step, as in the count pass
 			const float dt0 = calc_dt(rec.t_start, 0.0f);
 			#pragma unroll
-			for (int L = 0; L < 32; ++L) {
-				if (lane == L) t_mine = tl;
-				tl += dt0;
-			}
+			for (int k = 0; k < 31; ++k) if (k < lane) t_mine += dt0;
 		} else {
 			#pragma unroll
-			for (int L = 0; L < 32; ++L) {
-				if (lane == L) t_mine = tl;
-				tl += calc_dt(tl, cone_angle);
-			}
+			for (int k = 0; k < 31; ++k) if (k < lane) t_mine += calc_dt(t_mine, cone_angle);
 		}
 		if ((rec.mask >> lane) & 1u) {
 			const uint32_t my_j = j + __popc(rec.mask & ((1u << lane) - 1u));
