@@ -88,3 +88,69 @@ class RefMlp:
         if rc != 0:
             raise RuntimeError(lib().ref_last_error().decode())
         return dict(out=out, dL_din=din, wgrad=wgrad, ms=ms.value)
+
+
+class RefOptimizer:
+    """The reference's Ema{ExponentialDecay{Adam}} as configs/nerf/base.json builds it (tcnn optimizers/{ema,exponential_decay,adam}.h),
+    over `n_params` parameters of which the first `n_matrix` are matrix weights."""
+
+    def __init__(self, n_params, n_matrix, learning_rate=1e-3, beta1=0.9, beta2=0.99, epsilon=1e-15, l2_reg=1e-6, ema_decay=0.95):
+        cfg = dict(otype="Ema", decay=ema_decay, nested=dict(otype="ExponentialDecay", decay_start=20000, decay_interval=10000, decay_base=0.33,
+                   nested=dict(otype="Adam", learning_rate=learning_rate, beta1=beta1, beta2=beta2, epsilon=epsilon, l2_reg=l2_reg)))
+        lib().ref_opt_create.restype = C.c_void_p
+        self.h = C.c_void_p(lib().ref_opt_create(json.dumps(cfg).encode(), C.c_uint64(n_params), C.c_uint64(n_matrix)))
+        if not self.h:
+            raise RuntimeError(lib().ref_last_error().decode())
+        self.n = n_params
+
+    def step(self, loss_scale, master, params_h, grads_h):
+        """master: cuda float32, params_h / grads_h: cuda half (updated in place).  Returns the EMA weights as a cuda half tensor copy."""
+        import torch
+        ema_ptr = C.c_void_p()
+        rc = lib().ref_opt_step(self.h, C.c_float(loss_scale), _p(master), _p(params_h), _p(grads_h), C.byref(ema_ptr))
+        if rc != 0:
+            raise RuntimeError(lib().ref_last_error().decode())
+        out = torch.empty(self.n, dtype=torch.float16, device=master.device)
+        torch.cuda.synchronize()
+        # device-to-device copy of the optimizer-owned EMA buffer through torch's raw-pointer view
+        class _Dev:
+            def __init__(s, ptr, n):
+                s.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f2", "data": (int(ptr), False), "version": 3, "strides": None}
+        out.copy_(torch.as_tensor(_Dev(ema_ptr.value, self.n), device=master.device))
+        return out
+
+    def close(self):
+        if self.h:
+            lib().ref_opt_destroy.argtypes = [C.c_void_p]
+            lib().ref_opt_destroy(self.h)
+            self.h = None
+
+
+def morton3D(x, y, z):
+    lib().ref_morton3D.restype = C.c_uint32
+    return int(lib().ref_morton3D(C.c_uint32(x), C.c_uint32(y), C.c_uint32(z)))
+
+
+def morton3D_invert(x):
+    lib().ref_morton3D_invert.restype = C.c_uint32
+    return int(lib().ref_morton3D_invert(C.c_uint32(x)))
+
+
+def pcg32_sequence(seed, advance, n):
+    import numpy as np
+    u = np.zeros(n, dtype=np.uint32)
+    f = np.zeros(n, dtype=np.float32)
+    lib().ref_pcg32_sequence(C.c_uint64(seed), C.c_int64(advance), C.c_uint32(n), u.ctypes.data_as(C.c_void_p), f.ctypes.data_as(C.c_void_p))
+    return u, f
+
+
+def generate_random_uniform(seed, n, lower, upper):
+    """Returns (values float32 [n] as numpy, rng state after as (state, inc))."""
+    import numpy as np
+    import torch
+    out = torch.empty(n, dtype=torch.float32, device="cuda")
+    st = np.zeros(2, dtype=np.uint64)
+    rc = lib().ref_generate_random_uniform(C.c_uint64(seed), C.c_uint64(n), _p(out), C.c_float(lower), C.c_float(upper), st.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise RuntimeError(lib().ref_last_error().decode())
+    return out.cpu().numpy(), (int(st[0]), int(st[1]))

@@ -18,6 +18,11 @@
 #include <memory>
 #include <string>
 
+#include <tiny-cuda-nn/optimizer.h>
+#include <tiny-cuda-nn/random.h>
+#include <tiny-cuda-nn/common_device.h>
+#include <pcg32/pcg32.h>
+
 using namespace tcnn;
 using T = __half;
 
@@ -151,5 +156,66 @@ int ref_mlp_eval(void* h, uint32_t n, uint32_t in_w, int in_soa, const T* in, T*
 }
 
 void ref_free_temporary_memory() { free_all_gpu_memory_arenas(); }
+
+// ---- optimizer: the reference's Ema{Adam} exactly as Trainer drives it (trainer.h:170-178; adam.h:52-160,266-324; ema.h:64-147) ----
+// A ParametricObject that only describes the parameter layout the optimizer asks for: `n_matrix` leading parameters are covered by
+// one "layer" (matrix params: L2 regularisation, always updated), the rest are non-matrix (hash-grid style: skipped when g == 0).
+struct RefLayout : public ParametricObject<T> {
+	size_t n, n_matrix;
+	RefLayout(size_t n_, size_t nm) : n(n_), n_matrix(nm) {}
+	void set_params(T*, T*, T*, T*) override {}
+	void initialize_params(pcg32&, float*, T*, T*, T*, T*, float) override {}
+	size_t n_params() const override { return n; }
+	std::vector<std::pair<uint32_t, uint32_t>> layer_sizes() const override {
+		if (!n_matrix) return {};
+		return {{(uint32_t)n_matrix, 1u}};
+	}
+	json hyperparams() const override { return {{"otype", "RefLayout"}}; }
+};
+struct RefOpt { std::shared_ptr<Optimizer<T>> opt; std::shared_ptr<RefLayout> layout; };
+
+void* ref_opt_create(const char* cfg_json, uint64_t n_params, uint64_t n_matrix) {
+	try {
+		auto* o = new RefOpt;
+		o->opt.reset(create_optimizer<T>(json::parse(cfg_json)));
+		o->layout = std::make_shared<RefLayout>((size_t)n_params, (size_t)n_matrix);
+		o->opt->allocate(o->layout);
+		return o;
+	} catch (const std::exception& e) { g_err = e.what(); fprintf(stderr, "ref_shim: %s\n", e.what()); return nullptr; }
+}
+void ref_opt_destroy(void* h) { delete (RefOpt*)h; }
+// one Trainer::optimizer_step: master (fp32), params (fp16) and gradients (fp16) are DEVICE pointers; returns the optimizer's
+// inference weights (EMA) pointer through ema_out (device, owned by the optimizer)
+int ref_opt_step(void* h, float loss_scale, float* master, T* params, const T* grads, T** ema_out) {
+	REF_TRY
+	auto* o = (RefOpt*)h;
+	o->opt->step(nullptr, loss_scale, master, params, grads);
+	CUDA_CHECK_THROW(cudaDeviceSynchronize());
+	if (ema_out) *ema_out = o->opt->custom_weights();
+	return 0;
+	REF_CATCH
+}
+
+// ---- integer / RNG primitives of the ngp layer that live in Eigen-free headers ----
+uint32_t ref_morton3D(uint32_t x, uint32_t y, uint32_t z) { return morton3D(x, y, z); }                 // common_device.h:347-353
+uint32_t ref_morton3D_invert(uint32_t x) { return morton3D_invert(x); }                                  // :355-362
+// pcg32 (dependencies/pcg32/pcg32.h): seed, jump ahead, then n draws of each kind
+void ref_pcg32_sequence(uint64_t seed, int64_t advance, uint32_t n, uint32_t* uints, float* floats) {
+	pcg32 rng{seed};
+	rng.advance(advance);
+	pcg32 r2 = rng;
+	for (uint32_t i = 0; i < n; ++i) uints[i] = rng.next_uint();
+	for (uint32_t i = 0; i < n; ++i) floats[i] = r2.next_float();
+}
+// generate_random_uniform (random.h:67-99): what Trainer::initialize_params fills the hash grid with; out is a DEVICE pointer
+int ref_generate_random_uniform(uint64_t seed, uint64_t n, float* out_dev, float lower, float upper, uint64_t* state_after) {
+	REF_TRY
+	pcg32 rng{seed};
+	generate_random_uniform<float>(rng, (size_t)n, out_dev, lower, upper);
+	CUDA_CHECK_THROW(cudaDeviceSynchronize());
+	if (state_after) { state_after[0] = rng.state; state_after[1] = rng.inc; }
+	return 0;
+	REF_CATCH
+}
 
 }  // extern "C"

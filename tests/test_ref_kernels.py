@@ -83,3 +83,68 @@ def test_reference_mlp_matches_oracle(n_in, hl, soa):
     assert np.linalg.norm(rd - _h(din)) / np.linalg.norm(_h(din)) < 3e-2   # fp16 HMMA accumulation in the reference
     rw = r["wgrad"].cpu().numpy().astype(np.float32)
     assert np.linalg.norm(rw - wg) / np.linalg.norm(wg) < 3e-2
+
+
+# ---- more of the reference's own code behind the oracle: optimizer, RNG, Morton codes -------------------------------------------
+def test_reference_pcg32_and_morton_match_oracle():
+    """pcg32 (tcnn/dependencies/pcg32/pcg32.h) and morton3D (tcnn common_device.h:339-362) are Eigen-free headers: the oracle's
+    restatements are compared with the reference's own code, bit for bit."""
+    from oracle import ref_kernels as R
+    for seed, adv in ((1337, 0), (1337, 8 * 12345), (42, (1 << 32) + 17), (7, 3)):
+        u, f = R.pcg32_sequence(seed, adv, 64)
+        a = O.Pcg32(seed=seed); a.advance(adv)
+        b = a.copy()
+        assert [a.next_uint() for _ in range(64)] == [int(x) for x in u]
+        assert np.array_equal(np.array([b.next_float() for _ in range(64)], dtype=np.float32).view(np.uint32), f.view(np.uint32))
+    rs = np.random.RandomState(0)
+    for x, y, z in rs.randint(0, 1024, (200, 3)):
+        m = R.morton3D(int(x), int(y), int(z))
+        assert m == O.lib().orc_morton3D(int(x), int(y), int(z))
+        assert (R.morton3D_invert(m), R.morton3D_invert(m >> 1), R.morton3D_invert(m >> 2)) == (x, y, z)
+        assert R.morton3D_invert(m) == O.lib().orc_morton3D_invert(m)
+
+
+def test_reference_generate_random_uniform_matches_oracle():
+    """The hash-grid initialisation (tcnn random.h:67-99 via grid.h:2375-2380): values and the generator state afterwards."""
+    from oracle import ref_kernels as R
+    n = 100003
+    ref, state = R.generate_random_uniform(1337, n, -1e-4, 1e-4)
+    rng = O.Pcg32(seed=1337)
+    got = O.generate_random_uniform(rng, n, -1e-4, 1e-4)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    assert (int(rng.st[0]), int(rng.st[1])) == state
+
+
+def test_reference_adam_ema_matches_oracle():
+    """Trainer::optimizer_step with base.json's Ema{ExponentialDecay{Adam}}: matrix weights (L2, always stepped) followed by
+    hash-grid style weights (skipped when the gradient is exactly zero, private step counters), five steps with a moving sparsity
+    pattern.  The reference takes fp16 gradients; they are exactly representable, so the oracle's fp32 input is the same number."""
+    import torch
+    from oracle import ref_kernels as R
+    n, n_matrix = 40000, 11264
+    rs = np.random.RandomState(3)
+    master0 = rs.normal(0, 0.1, n).astype(np.float32)
+    opt = R.RefOptimizer(n, n_matrix)
+    master = torch.from_numpy(master0.copy()).cuda()
+    params = master.half()
+    mm = master0.copy(); ph = master0.astype(np.float16).view(np.uint16).copy()
+    m1 = np.zeros(n, np.float32); m2 = np.zeros(n, np.float32); steps = np.zeros(n, np.uint32); ema = np.zeros(n, np.uint16)
+    try:
+        for step in range(1, 6):
+            g16 = np.zeros(n, dtype=np.float16)
+            touched = rs.choice(n - n_matrix, size=6000, replace=False) + n_matrix
+            g16[touched] = rs.normal(0, 2.0, touched.size).astype(np.float16)
+            g16[:n_matrix] = rs.normal(0, 2.0, n_matrix).astype(np.float16)
+            ref_ema = opt.step(128.0, master, params, torch.from_numpy(g16).cuda())
+            O.adam_ema_step(n_matrix, 128.0, 1e-3, 0.9, 0.99, 1e-15, 1e-6, 0.95, step, g16.astype(np.float32), mm, ph, m1, m2, steps, ema)
+            dm = np.abs(master.cpu().numpy() - mm)
+            # fp32 master: the reference's nvcc build contracts a*b+c into FMAs where the oracle rounds twice -> a few ulp
+            assert np.max(dm / np.maximum(np.abs(mm), 1e-6)) < 2e-6, (step, np.max(dm))
+            assert np.mean(params.cpu().numpy().view(np.uint16) != ph) < 1e-3, step      # fp16 params: identical but for rounding ties
+            d = U.half_ulp_diff(ref_ema.cpu().numpy().view(np.uint16), ema)
+            assert d.max() <= 1 and np.mean(d > 0) < 5e-3, (step, d.max(), np.mean(d > 0))
+            # untouched hash-grid style weights did not move and kept their step counter
+            idle = np.ones(n, bool); idle[:n_matrix] = False; idle[touched] = False
+            assert np.array_equal(master.cpu().numpy()[idle & (steps == 0)], master0[idle & (steps == 0)])
+    finally:
+        opt.close()
