@@ -112,7 +112,8 @@ void orc_generate_random_uniform(uint64_t* st, uint64_t n, float* out, float low
 			uint64_t idx = i + n_threads * j;
 			if (idx >= n) break;
 			float v = r.next_float();
-			out[idx] = v * (upper - lower) + lower;  // lambda in random.h:95 (no contraction possible to differ: see note)
+			out[idx] = fmaf(v, upper - lower, lower);  // lambda in random.h:95: `val * (upper - lower) + lower` is ONE FFMA under nvcc's default
+			                                           // -fmad=true (pinned against the reference kernel by tests/test_ref_kernels.py)
 		}
 	}
 	base.advance((int64_t)n);

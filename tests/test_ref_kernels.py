@@ -148,3 +148,26 @@ def test_reference_adam_ema_matches_oracle():
             assert np.array_equal(master.cpu().numpy()[idle & (steps == 0)], master0[idle & (steps == 0)])
     finally:
         opt.close()
+
+
+def test_product_grid_initialisation_follows_the_reference_stream():
+    """neus2_init_params: Trainer rng (std::seed_seq{1337} -> pcg32, trainer.h:56-59), Xavier draws for the two MLPs (11,264 floats,
+    nerf_network.h:819-870), then the hash grid from generate_random_uniform(-1e-4, 1e-4) -- the same values as the reference kernel."""
+    import neus2_b200 as N
+    from oracle import ref_kernels as R
+    ctx = N.Context(N.default_config(batch_size=1 << 14))
+    try:
+        ctx.init_params()
+        p = ctx.get_params()
+        g0, g1 = ctx.layout["grid"], ctx.layout["variance"]
+        rng = O.Pcg32(seed=int(O.lib().orc_trainer_seed_word(1337)))
+        rng.advance(g0)                                    # one draw per MLP weight
+        want = O.generate_random_uniform(rng, g1 - g0, -1e-4, 1e-4)
+        assert np.array_equal(p[g0:g1].view(np.uint32), want.view(np.uint32))
+        # and the oracle's generator equals the reference kernel on that very stream
+        ref, _ = R.generate_random_uniform(1337, 4096, -1e-4, 1e-4)
+        chk = O.generate_random_uniform(O.Pcg32(seed=1337), 4096, -1e-4, 1e-4)
+        assert np.array_equal(ref.view(np.uint32), chk.view(np.uint32))
+        assert np.all(p[g1:] == np.float32(0.3))
+    finally:
+        ctx.close()
