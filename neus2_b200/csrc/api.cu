@@ -126,6 +126,23 @@ template <typename T> static int regrow(T** p, size_t* cap, size_t need) {
 	return 0;
 }
 
+// Bias correction of adam_step (adam.h:149-150), sqrt(1 - beta2^k) / (1 - beta1^k), tabulated per step count k.  Lives here because
+// this translation unit is compiled with nvcc's default FMA contraction, as the reference's optimizer is: libdevice's powf then
+// compiles to the same instruction sequence as inside the reference's adam_step.
+__global__ void k_adam_bias_table(float beta1, float beta2, uint32_t first, uint32_t last, float* __restrict__ table) {
+	const uint32_t cs = first + blockIdx.x * blockDim.x + threadIdx.x;
+	if (cs <= last) table[cs] = sqrtf(1 - powf(beta2, (float)cs)) / (1 - powf(beta1, (float)cs));
+}
+int launch_adam_bias_table(cudaStream_t stream, float beta1, float beta2, uint32_t first, uint32_t last, float* bias_table, uint32_t bias_table_size) {
+	if (!bias_table || !bias_table_size || last < first) return 0;
+	if (last >= bias_table_size) last = bias_table_size - 1;
+	if (first > last) return 0;
+	k_adam_bias_table<<<(last - first + 256) / 256, 256, 0, stream>>>(beta1, beta2, first, last, bias_table);
+	COUNT_LAUNCH(1);
+	CUDA_CHECK(cudaGetLastError());
+	return 0;
+}
+
 extern "C" {
 
 const char* neus2_last_error(void) { return g_error.c_str(); }
@@ -829,7 +846,7 @@ int neus2_optimizer_buffers(neus2_ctx* ctx, float** m1_dev, float** m2_dev, uint
 int neus2_set_optimizer_step(neus2_ctx* ctx, uint32_t current_step) {
 	CUDA_CHECK(cudaSetDevice(ctx->device));
 	ctx->adam_step = current_step;
-	CHECK(launch_adam_bias_table(nullptr, ctx->cfg.beta1, ctx->cfg.beta2, current_step, ctx->adam_bias_table, ADAM_BIAS_TABLE));
+	CHECK(launch_adam_bias_table(nullptr, ctx->cfg.beta1, ctx->cfg.beta2, 1, current_step, ctx->adam_bias_table, ADAM_BIAS_TABLE));
 	CUDA_CHECK(cudaDeviceSynchronize());
 	return 0;
 }

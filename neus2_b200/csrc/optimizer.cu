@@ -1,7 +1,10 @@
 // optimizer.cu -- fused Adam (+ per-parameter step counters, sparse skip, L2 on the MLP weights) and fp16 EMA.
 // Restates adam_step (tcnn optimizers/adam.h:52-160) and ema_step_half_precision (optimizers/ema.h:64-77,112-147)
 // as ONE pass over the parameters (the reference launches two kernels and re-reads the fp16 params).
-// Compiled with -fmad=false so the update is bit-identical to oracle/neus_oracle.cpp:orc_adam_ema_step.
+// Compiled with -fmad=false; the fused multiply-adds written out below are exactly the ones nvcc's default -fmad=true puts into
+// the reference's kernels (read off their SASS), so the update is bit-identical to the reference's Ema{Adam} and to
+// oracle/neus_oracle.cpp:orc_adam_ema_step.  The bias-correction factors (powf) come from a table filled by a kernel that lives in an
+// FMA-enabled translation unit (api.cu), so that libdevice's powf is compiled the way it is inside the reference build.
 #include "ngp_common.cuh"
 #include "ngp_kernels.h"
 
@@ -11,33 +14,28 @@ struct AdamHyper { float loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, e
 
 // Bias correction of adam_step (adam.h:149-150) for a parameter whose private step counter reads `cs`:
 // sqrt(1 - beta2^cs) / (1 - beta1^cs).  Two powf per parameter made the kernel issue-bound (83 % issue-active, 40 % of HBM peak
-// in the first ncu capture), so the factor is looked up instead: almost every touched parameter is on the CURRENT step
-// (computed once per thread), older counters index a table that k_adam_bias_table extends by one entry per step with the very
-// same expression -- identical bits, 8x fewer transcendental calls.
+// in the first ncu capture), so the factor is looked up in a table that k_adam_bias_table (api.cu) extends by one entry per step;
+// the inline evaluation below is only the fallback for counters beyond the table (> 2^20 steps).
 __device__ __forceinline__ float adam_bias_factor(const AdamHyper& h, uint32_t cs) {
 	return sqrtf(1 - powf(h.beta2, (float)cs)) / (1 - powf(h.beta1, (float)cs));
 }
-__global__ void k_adam_bias_table(AdamHyper h, uint32_t first, uint32_t last, float* __restrict__ table) {
-	const uint32_t cs = first + blockIdx.x * blockDim.x + threadIdx.x;
-	if (cs <= last) table[cs] = adam_bias_factor(h, cs);
-}
 
-__device__ __forceinline__ __half adam_one(bool is_matrix, float g_raw, const AdamHyper& h, float cur_factor, float& w, float& m1, float& m2, uint32_t& step, __half p, bool& touched) {
+__device__ __forceinline__ __half adam_one(bool is_matrix, float g_raw, const AdamHyper& h, float& w, float& m1, float& m2, uint32_t& step, __half p, bool& touched) {
 	float gradient = g_raw / h.loss_scale;
 	touched = false;
 	if (is_matrix || gradient != 0) {            // adam.h:109-112: non-matrix params with zero gradient are skipped entirely
 		touched = true;
-		if (is_matrix) gradient += h.l2_reg * w;   // adam.h:132-135
+		if (is_matrix) gradient = fmaf(h.l2_reg, w, gradient);   // adam.h:132-135
 		const float gsq = gradient * gradient;
-		const float fm = h.beta1 * m1 + (1 - h.beta1) * gradient;
-		const float sm = h.beta2 * m2 + (1 - h.beta2) * gsq;
+		const float fm = fmaf(h.beta1, m1, (1 - h.beta1) * gradient);
+		const float sm = fmaf(h.beta2, m2, (1 - h.beta2) * gsq);
 		m1 = fm; m2 = sm;
 		float learning_rate = h.lr;
 		const uint32_t cs = ++step;
-		learning_rate *= cs == h.cur_step ? cur_factor : (cs < h.bias_table_size ? h.bias_table[cs] : adam_bias_factor(h, cs));
+		learning_rate *= cs < h.bias_table_size ? h.bias_table[cs] : adam_bias_factor(h, cs);
 		const float eff = fminf(fmaxf(learning_rate / (sqrtf(sm) + h.eps), 0.f), 3.402823466e+38f);
 		const float decayed = (1 - 0.f * learning_rate) * w - copysignf(0.f * learning_rate, w);
-		const float nw = decayed - eff * fm;
+		const float nw = fmaf(-eff, fm, decayed);
 		w = nw;
 		p = __float2half_rn(nw);
 	}
@@ -58,7 +56,6 @@ k_adam_ema(uint64_t n4, uint64_t n_matrix4, AdamHyper h, const float* __restrict
 	__half* ph = reinterpret_cast<__half*>(&pw);
 	const float g[4] = {g4.x, g4.y, g4.z, g4.w};
 	if (!h.frozen && (is_matrix || g4.x != 0.f || g4.y != 0.f || g4.z != 0.f || g4.w != 0.f)) {
-		const float cur_factor = adam_bias_factor(h, h.cur_step);
 		float4 w4 = reinterpret_cast<const float4*>(master)[q];
 		float4 a4 = reinterpret_cast<const float4*>(m1)[q];
 		float4 b4 = reinterpret_cast<const float4*>(m2)[q];
@@ -69,7 +66,7 @@ k_adam_ema(uint64_t n4, uint64_t n_matrix4, AdamHyper h, const float* __restrict
 		#pragma unroll
 		for (int k = 0; k < 4; ++k) {
 			bool touched;
-			ph[k] = adam_one(is_matrix, g[k], h, cur_factor, w[k], a[k], b[k], st[k], ph[k], touched);
+			ph[k] = adam_one(is_matrix, g[k], h, w[k], a[k], b[k], st[k], ph[k], touched);
 			any |= touched;
 		}
 		if (any) {
@@ -84,7 +81,7 @@ k_adam_ema(uint64_t n4, uint64_t n_matrix4, AdamHyper h, const float* __restrict
 	__half* eh = reinterpret_cast<__half*>(&ew);
 	#pragma unroll
 	for (int k = 0; k < 4; ++k) {
-		const float filtered = (__half2float(eh[k]) * h.ema_decay * h.ema_debias_old + __half2float(ph[k]) * (1 - h.ema_decay)) * h.ema_debias_new;
+		const float filtered = fmaf(__half2float(eh[k]) * h.ema_decay, h.ema_debias_old, __half2float(ph[k]) * (1 - h.ema_decay)) * h.ema_debias_new;
 		eh[k] = __float2half_rn(filtered);
 	}
 	reinterpret_cast<uint2*>(ema)[q] = ew;
@@ -97,7 +94,7 @@ int launch_adam_ema(cudaStream_t stream, uint64_t n, uint64_t n_matrix, float lo
 	const float ema_debias_new = 1.0f / (1 - (float)pow((double)ema_decay, (double)ema_step));
 	if (n % 4 != 0 || n_matrix % 4 != 0) { neus_set_error("parameter counts must be multiples of 4", __FILE__, __LINE__); return -1; }
 	AdamHyper h = {loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, ema_debias_old, ema_debias_new, ema_step, bias_table, bias_table_size, frozen};
-	if (bias_table && ema_step < bias_table_size) { k_adam_bias_table<<<1, 32, 0, stream>>>(h, ema_step, ema_step, bias_table); COUNT_LAUNCH(1); }
+	if (bias_table && ema_step < bias_table_size) { if (launch_adam_bias_table(stream, beta1, beta2, ema_step, ema_step, bias_table, bias_table_size)) return -1; }
 	const uint64_t n4 = n / 4;
 	const uint32_t blocks = (uint32_t)((n4 + 255) / 256);
 	k_adam_ema<<<blocks, 256, 0, stream>>>(n4, n_matrix / 4, h, grads, master, params, m1, m2, steps, ema);
@@ -133,7 +130,6 @@ k_adam_ema_p2p(uint64_t q0, uint64_t q1, uint64_t n_matrix4, AdamHyper h, int wo
 	__half* ph = reinterpret_cast<__half*>(&pw);
 	const float g[4] = {g4.x, g4.y, g4.z, g4.w};
 	if (!h.frozen && (is_matrix || g4.x != 0.f || g4.y != 0.f || g4.z != 0.f || g4.w != 0.f)) {
-		const float cur_factor = adam_bias_factor(h, h.cur_step);
 		float4 w4 = reinterpret_cast<const float4*>(master)[q];
 		float4 a4 = reinterpret_cast<const float4*>(m1)[q];
 		float4 b4 = reinterpret_cast<const float4*>(m2)[q];
@@ -144,7 +140,7 @@ k_adam_ema_p2p(uint64_t q0, uint64_t q1, uint64_t n_matrix4, AdamHyper h, int wo
 		#pragma unroll
 		for (int k = 0; k < 4; ++k) {
 			bool touched;
-			ph[k] = adam_one(is_matrix, g[k], h, cur_factor, w[k], a[k], b[k], st[k], ph[k], touched);
+			ph[k] = adam_one(is_matrix, g[k], h, w[k], a[k], b[k], st[k], ph[k], touched);
 			any |= touched;
 		}
 		if (any) {
@@ -160,7 +156,7 @@ k_adam_ema_p2p(uint64_t q0, uint64_t q1, uint64_t n_matrix4, AdamHyper h, int wo
 	__half* eh = reinterpret_cast<__half*>(&ew);
 	#pragma unroll
 	for (int k = 0; k < 4; ++k) {
-		const float filtered = (__half2float(eh[k]) * h.ema_decay * h.ema_debias_old + __half2float(ph[k]) * (1 - h.ema_decay)) * h.ema_debias_new;
+		const float filtered = fmaf(__half2float(eh[k]) * h.ema_decay, h.ema_debias_old, __half2float(ph[k]) * (1 - h.ema_decay)) * h.ema_debias_new;
 		eh[k] = __float2half_rn(filtered);
 	}
 	#pragma unroll
@@ -175,7 +171,7 @@ int launch_adam_ema_p2p(cudaStream_t stream, uint64_t n, uint64_t n_matrix, uint
 	if (n % 4 != 0 || n_matrix % 4 != 0) { neus_set_error("parameter counts must be multiples of 4", __FILE__, __LINE__); return -1; }
 	if (world < 1 || world > NEUS2_MAX_PEERS || rank >= world) { neus_set_error("bad rank / world size for the sharded optimizer", __FILE__, __LINE__); return -1; }
 	AdamHyper h = {loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, ema_debias_old, ema_debias_new, ema_step, bias_table, bias_table_size, frozen};
-	if (bias_table && ema_step < bias_table_size) { k_adam_bias_table<<<1, 32, 0, stream>>>(h, ema_step, ema_step, bias_table); COUNT_LAUNCH(1); }
+	if (bias_table && ema_step < bias_table_size) { if (launch_adam_bias_table(stream, beta1, beta2, ema_step, ema_step, bias_table, bias_table_size)) return -1; }
 	uint64_t q0, q1;
 	optimizer_shard(n / 4, rank, world, &q0, &q1);
 	PeerPtrs pp;
@@ -200,13 +196,3 @@ void optimizer_shard(uint64_t n_quads, uint32_t rank, uint32_t world, uint64_t* 
 	*q1 = *q0 + base + (rank < extra ? 1 : 0);
 }
 
-// (re)build the bias-correction table for counters 1..last (after a snapshot restore)
-int launch_adam_bias_table(cudaStream_t stream, float beta1, float beta2, uint32_t last, float* bias_table, uint32_t bias_table_size) {
-	if (!bias_table || !bias_table_size || !last) return 0;
-	if (last >= bias_table_size) last = bias_table_size - 1;
-	AdamHyper h = {}; h.beta1 = beta1; h.beta2 = beta2;
-	k_adam_bias_table<<<(last + 255) / 256, 256, 0, stream>>>(h, 1, last, bias_table);
-	COUNT_LAUNCH(1);
-	CUDA_CHECK(cudaGetLastError());
-	return 0;
-}

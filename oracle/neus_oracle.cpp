@@ -761,6 +761,9 @@ void orc_net_sdf(const NetCfg* cp, uint32_t n, const float* pos, uint32_t stride
 
 // ----------------------------------------------------------------------------
 // Adam + EMA (tcnn optimizers/adam.h:52-160, ema.h:64-77,112-147).
+// The fused multiply-adds below are the ones nvcc's default -fmad=true puts into the reference's adam_step / ema_step_half_precision
+// (read off the SASS of oracle/_ref/obj/optimizer.o: FFMA for g + l2*w, for both moments, for w - lr*m, and for the EMA blend);
+// tests/test_ref_kernels.py::test_reference_adam_ema_matches_oracle compares against the reference's own optimizer objects.
 // ----------------------------------------------------------------------------
 void orc_adam_ema_step(uint64_t n, uint64_t n_matrix, float loss_scale, float lr, float beta1, float beta2, float eps, float l2_reg,
                        float ema_decay, uint32_t ema_step /* nested step count after increment */,
@@ -776,21 +779,21 @@ void orc_adam_ema_step(uint64_t n, uint64_t n_matrix, float loss_scale, float lr
 		if (!is_matrix && gradient == 0) skip = true;     // adam.h:109-112
 		if (!skip) {
 			const float w = master[i];
-			if (is_matrix) gradient += l2_reg * w;        // adam.h:132-135
+			if (is_matrix) gradient = fmaf(l2_reg, w, gradient);   // adam.h:132-135
 			const float gsq = gradient * gradient;
-			float fm = m1[i] = beta1 * m1[i] + (1 - beta1) * gradient;
-			const float sm = m2[i] = beta2 * m2[i] + (1 - beta2) * gsq;
+			float fm = m1[i] = fmaf(beta1, m1[i], (1 - beta1) * gradient);
+			const float sm = m2[i] = fmaf(beta2, m2[i], (1 - beta2) * gsq);
 			float learning_rate = lr;
 			const uint32_t cs = ++steps[i];
 			learning_rate *= sqrtf(1 - powf(beta2, (float)cs)) / (1 - powf(beta1, (float)cs));
 			const float eff = fminf(fmaxf(learning_rate / (sqrtf(sm) + eps), 0.f), std::numeric_limits<float>::max());
 			const float decayed = (1 - 0.f * learning_rate) * w - copysignf(0.f * learning_rate, w);
-			const float nw = decayed - eff * fm;
+			const float nw = fmaf(-eff, fm, decayed);
 			master[i] = nw;
 			params[i] = f2h(nw);
 		}
 		// EMA over ALL params (ema.h:64-77)
-		float filtered = (h2f(ema[i]) * ema_decay * ema_debias_old + h2f(params[i]) * (1 - ema_decay)) * ema_debias_new;
+		float filtered = fmaf(h2f(ema[i]) * ema_decay, ema_debias_old, h2f(params[i]) * (1 - ema_decay)) * ema_debias_new;
 		ema[i] = f2h(filtered);
 	}
 }

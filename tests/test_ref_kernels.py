@@ -137,10 +137,12 @@ def test_reference_adam_ema_matches_oracle():
             g16[:n_matrix] = rs.normal(0, 2.0, n_matrix).astype(np.float16)
             ref_ema = opt.step(128.0, master, params, torch.from_numpy(g16).cuda())
             O.adam_ema_step(n_matrix, 128.0, 1e-3, 0.9, 0.99, 1e-15, 1e-6, 0.95, step, g16.astype(np.float32), mm, ph, m1, m2, steps, ema)
-            dm = np.abs(master.cpu().numpy() - mm)
-            # fp32 master: the reference's nvcc build contracts a*b+c into FMAs where the oracle rounds twice -> a few ulp
-            assert np.max(dm / np.maximum(np.abs(mm), 1e-6)) < 2e-6, (step, np.max(dm))
-            assert np.mean(params.cpu().numpy().view(np.uint16) != ph) < 1e-3, step      # fp16 params: identical but for rounding ties
+            # the oracle writes the reference's FMAs out explicitly; what is left is powf (glibc here, libdevice there) in the bias
+            # correction: at most an ulp of the update, i.e. far below an ulp of most weights
+            got = master.cpu().numpy()
+            assert np.mean(got.view(np.uint32) != mm.view(np.uint32)) < 2e-2, (step, np.mean(got != mm))
+            assert np.max(np.abs(got - mm)) <= 2.0 ** -24 * np.max(np.abs(mm)), (step, np.max(np.abs(got - mm)))
+            assert np.mean(params.cpu().numpy().view(np.uint16) != ph) < 1e-3, step
             d = U.half_ulp_diff(ref_ema.cpu().numpy().view(np.uint16), ema)
             assert d.max() <= 1 and np.mean(d > 0) < 5e-3, (step, d.max(), np.mean(d > 0))
             # untouched hash-grid style weights did not move and kept their step counter
@@ -170,4 +172,39 @@ def test_product_grid_initialisation_follows_the_reference_stream():
         assert np.array_equal(ref.view(np.uint32), chk.view(np.uint32))
         assert np.all(p[g1:] == np.float32(0.3))
     finally:
+        ctx.close()
+
+
+def test_product_adam_ema_is_bit_identical_to_the_reference_optimizer():
+    """The PRODUCT's fused Adam+EMA kernel against the reference's own Ema{ExponentialDecay{Adam}} objects on the full 10.56 M
+    parameter vector (11,264 matrix weights, then the hash grid), four steps with a moving sparse gradient: fp32 master weights,
+    fp16 weights and the EMA copy must agree bit for bit."""
+    import torch
+    import neus2_b200 as N
+    from oracle import ref_kernels as R
+    ctx = N.Context(N.default_config(batch_size=1 << 14))
+    opt = None
+    try:
+        ctx.init_params()
+        master, params, ema, grads = ctx.buffers()
+        n, n_matrix = ctx.n_params, ctx.layout["grid"]
+        opt = R.RefOptimizer(n, n_matrix)
+        r_master = master.clone()
+        r_params = params.clone()
+        gen = torch.Generator(device="cuda").manual_seed(7)
+        for step in range(1, 5):
+            g16 = torch.zeros(n, dtype=torch.float16, device="cuda")
+            idx = torch.randint(n_matrix, n, (300000,), device="cuda", generator=gen)
+            g16[idx] = torch.randn(idx.numel(), device="cuda", generator=gen).half() * 3
+            g16[:n_matrix] = torch.randn(n_matrix, device="cuda", generator=gen).half()
+            grads.copy_(g16.float())
+            ctx.optimizer_step(128.0)
+            r_ema = opt.step(128.0, r_master, r_params, g16)
+            torch.cuda.synchronize()
+            assert torch.equal(master.view(torch.int32), r_master.view(torch.int32)), (step, (master != r_master).sum().item())
+            assert torch.equal(params.view(torch.int16), r_params.view(torch.int16)), step
+            assert torch.equal(ema.view(torch.int16), r_ema.view(torch.int16)), (step, (ema != r_ema).sum().item())
+    finally:
+        if opt is not None:
+            opt.close()
         ctx.close()
