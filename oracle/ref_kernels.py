@@ -154,3 +154,12 @@ def generate_random_uniform(seed, n, lower, upper):
     if rc != 0:
         raise RuntimeError(lib().ref_last_error().decode())
     return out.cpu().numpy(), (int(st[0]), int(st[1]))
+
+
+def fill_rollover(n_elements, n_input, dloss_h=None, coords=None):
+    """In place on cuda tensors: dloss_h half [n_elements,16] (wrapped copies rescaled by n_input/n_elements), coords float32 [n_elements,7]."""
+    import torch
+    n_in = torch.tensor([n_input], dtype=torch.int32, device="cuda")
+    rc = lib().ref_fill_rollover(C.c_uint32(n_elements), _p(n_in), _p(dloss_h), _p(coords))
+    if rc != 0:
+        raise RuntimeError(lib().ref_last_error().decode())

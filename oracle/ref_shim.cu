@@ -218,4 +218,15 @@ int ref_generate_random_uniform(uint64_t seed, uint64_t n, float* out_dev, float
 	REF_CATCH
 }
 
+// fill_rollover_and_rescale<half> on the dL/doutput rows and fill_rollover<float> on the coordinates, as train_nerf_step launches them
+// (src/testbed_nerf.cu:3922-3930; kernels: tcnn common_device.h:514-534).  All pointers are DEVICE pointers.
+int ref_fill_rollover(uint32_t n_elements, const uint32_t* n_input_dev, T* dloss16 /*[n][16]*/, float* coords7 /*[n][7]*/) {
+	REF_TRY
+	if (dloss16) fill_rollover_and_rescale<T><<<n_blocks_linear(n_elements * 16), n_threads_linear>>>(n_elements, 16, n_input_dev, dloss16);
+	if (coords7) fill_rollover<float><<<n_blocks_linear(n_elements * 7), n_threads_linear>>>(n_elements, 7, n_input_dev, coords7);
+	CUDA_CHECK_THROW(cudaDeviceSynchronize());
+	return 0;
+	REF_CATCH
+}
+
 }  // extern "C"

@@ -208,3 +208,25 @@ def test_product_adam_ema_is_bit_identical_to_the_reference_optimizer():
         if opt is not None:
             opt.close()
         ctx.close()
+
+
+def test_reference_fill_rollover_matches_oracle():
+    """a8: the batch is padded to exactly B rows by modular copy and the dL/doutput copies are rescaled by n_in / B
+    (tcnn common_device.h:514-534, launched at testbed_nerf.cu:3922-3930)."""
+    import torch
+    from oracle import ref_kernels as R
+    rs = np.random.RandomState(9)
+    n, n_in = 4096, 1537
+    dl = (rs.normal(0, 1, (n, 16)) * (rs.rand(n, 16) < 0.7)).astype(np.float16)
+    co = rs.rand(n, 7).astype(np.float32)
+    dl_t, co_t = torch.from_numpy(dl.copy()).cuda(), torch.from_numpy(co.copy()).cuda()
+    R.fill_rollover(n, n_in, dl_t, co_t)
+    dl_o, co_o = dl.view(np.uint16).copy(), co.copy()
+    O.fill_rollover(n, n_in, dl_o, co_o)
+    assert np.array_equal(dl_t.cpu().numpy().view(np.uint16), dl_o)
+    assert np.array_equal(co_t.cpu().numpy().view(np.uint32), co_o.view(np.uint32))
+    # nothing to do when the batch is already full or empty
+    for k in (0, n):
+        d2 = torch.from_numpy(dl.copy()).cuda()
+        R.fill_rollover(n, k, d2, None)
+        assert np.array_equal(d2.cpu().numpy().view(np.uint16), dl.view(np.uint16))
