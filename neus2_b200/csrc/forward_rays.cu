@@ -8,7 +8,8 @@
 // Here a work item is a SEGMENT of a ray (up to 4 tiles = 64 consecutive samples); a warp pulls items from a queue ordered
 // segment-major (every ray's first segment, then every ray's second ...).  It evaluates the segment 16 samples at a time (the same
 // forward_tile pipeline as k_network_forward), multiplies (1 - alpha) into a transmittance that starts at 1 for the segment, with the
-// loss kernel's own arithmetic (eval_sample), and stops -- and flags the ray as finished for all later segments -- once that product
+// loss kernel's own arithmetic (eval_sample), and stops -- and records its segment index as the ray's terminating segment, which lets
+// LATER segments of that ray be skipped -- once that product
 // is below the loss threshold.  The segment-local product bounds the true transmittance from above, so every sample the loss reads
 // has been evaluated (with identical bits); rows behind the cut keep stale values nobody looks at.  Segmenting bounds the serial
 // chain of a long ray that never saturates to 4 tiles.
@@ -54,7 +55,7 @@ k_network_forward_rays(GridMeta gm, ParamLayout pl, const __half* __restrict__ p
 		const uint32_t n = min(ns, max_samples - base);
 		const uint32_t s_begin = seg * FR_SEGMENT, s_end = min(n, s_begin + FR_SEGMENT);
 		if (s_begin >= n) continue;
-		if (seg > 0 && ray_done[ray]) continue;          // an earlier segment already pushed the transmittance below the threshold
+		if (seg > 0 && ray_done[ray] < seg) continue;    // an EARLIER segment already pushed the transmittance below the threshold
 		float T = 1.f;
 		float dir[3] = {0.f, 0.f, 1.f};
 		float cr[4];   // the segment's next tile of coordinates, in flight while the current tile is processed
@@ -87,7 +88,7 @@ k_network_forward_rays(GridMeta gm, ParamLayout pl, const __half* __restrict__ p
 			__syncwarp();
 			// the loss breaks BEFORE a sample once its transmittance (<= this segment-local product) is below 1e-4, and T never grows:
 			// nothing behind this tile is read.  The factor 0.5 is slack against any last-ulp difference between the two evaluations.
-			if (T < EPSILON * 0.5f) { if (lane == 0) ray_done[ray] = 1u; break; }
+			if (T < EPSILON * 0.5f) { if (lane == 0) atomicMin(ray_done + ray, seg); break; }   // lowest terminating segment: only later ones may be skipped
 		}
 	}
 	if (lane == 0 && evaluated) atomicAdd(work_counter + 1, evaluated);
@@ -99,7 +100,7 @@ int launch_network_forward_rays(cudaStream_t stream, const GridMeta& gm, const P
 	static bool attr[NEUS_MAX_DEVICES] = {};
 	if (ensure_dynamic_smem(k_network_forward_rays, FR_SMEM, attr)) return -1;
 	CUDA_CHECK(cudaMemsetAsync(work_counter, 0, 2 * sizeof(uint32_t), stream));
-	CUDA_CHECK(cudaMemsetAsync(ray_done, 0, (size_t)n_rays_max * sizeof(uint32_t), stream));
+	CUDA_CHECK(cudaMemsetAsync(ray_done, 0xff, (size_t)n_rays_max * sizeof(uint32_t), stream));   // 0xffffffff = no segment has terminated the ray
 	k_network_forward_rays<<<device_sm_count() * 2, FR_WARPS * 32, FR_SMEM, stream>>>(gm, pl, params, sdf_bias, cos_anneal_ratio, n_kept_ptr, longest_ptr, numsteps,
 	                                                                                 coords, max_samples, out, ray_done, work_counter);
 	COUNT_LAUNCH(1);
