@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--res", type=int, default=256)
     ap.add_argument("--mc", type=int, default=256)
     ap.add_argument("--json", default=None)
+    ap.add_argument("--dtu", action="store_true", help="BASELINE.json configs[1]: the DTU-Scan24-shaped scene (49 views 1600x1200, cameras on a cap above the object)")
     ap.add_argument("--mask-weight", type=float, default=0.0)
     ap.add_argument("--full-forward", action="store_true", help="evaluate every marched sample in the first pass (reference behaviour) instead of the early cut")
     args = ap.parse_args()
@@ -36,7 +37,12 @@ def main():
     import neus2_b200 as N
     from neus2_b200 import synthetic
 
-    data = synthetic.render_sphere_views(n_views=args.views, width=args.res, height=args.res, seed=0, elevation_deg=(-55.0, 65.0))
+    if args.dtu:
+        data = synthetic.dtu_like_views(n_views=49, width=1600, height=1200, seed=0)
+        args.views = 49
+    else:
+        data = synthetic.render_sphere_views(n_views=args.views, width=args.res, height=args.res, seed=0, elevation_deg=(-55.0, 65.0))
+    H, W = data["pixels"].shape[1:3]
     ctx = N.Context(N.default_config(mask_loss_weight=args.mask_weight, forward_early_termination=0 if args.full_forward else 1))
     ctx.init_params()
     ctx.set_dataset(data["pixels"], data["focal"], data["principal"], data["xforms"])
@@ -57,7 +63,7 @@ def main():
     psnr = []
     t0 = time.perf_counter()
     for v in range(args.views):
-        rp = ctx.training_view_params(data["xforms"][v], data["focal"][v], data["principal"][v], (args.res, args.res), min_transmittance=1e-4,
+        rp = ctx.training_view_params(data["xforms"][v], data["focal"][v], data["principal"][v], (W, H), min_transmittance=1e-4,
                                       background_color=(0, 0, 0, 1), to_srgb=1)
         img = ctx.render(rp, spp=1)
         gt = torch.from_numpy(data["pixels"][v]).cuda().float() / 255.0
@@ -78,6 +84,10 @@ def main():
     torch.cuda.synchronize()
     t_mc = time.perf_counter() - t0
     V = verts.cpu().numpy().astype(np.float64)
+    if args.dtu and len(V):
+        # the cameras sit on a cap above the object: the underside is never observed, judge the surface they see (z above the lowest camera ray)
+        seen = V[:, 2] > 0.5 - 0.05
+        V = V[seen]
     d_mesh_to_gt = np.abs(synthetic.sphere_sdf(V, data["spheres"]))
     # analytic surface samples (area-weighted over the spheres, outside the other spheres)
     rs = np.random.RandomState(0)
@@ -89,10 +99,12 @@ def main():
         pts.append(c + r * d)
     P = np.concatenate(pts)
     P = P[np.abs(synthetic.sphere_sdf(P, data["spheres"])) < 1e-9]
+    if args.dtu:
+        P = P[P[:, 2] > 0.5 - 0.05]
     d_gt_to_mesh = cKDTree(V).query(P)[0] if len(V) else np.full(len(P), np.inf)
     chamfer = 0.5 * (d_mesh_to_gt.mean() + d_gt_to_mesh.mean())
 
-    out = dict(steps=args.steps, views=args.views, res=args.res, train_s=t_train, ms_per_step=1e3 * t_train / args.steps, rays_per_s=rays / t_train,
+    out = dict(steps=args.steps, views=args.views, res=[int(W), int(H)], scene="dtu-shaped" if args.dtu else "two spheres, cameras all around", train_s=t_train, ms_per_step=1e3 * t_train / args.steps, rays_per_s=rays / t_train,
                psnr_mean=float(np.mean(psnr)), psnr_min=float(np.min(psnr)), render_s_per_view=t_render / args.views,
                render_last_view=rstats, mc_res=args.mc, lattice_s=t_lattice, mc_s=t_mc, n_verts=int(len(V)), n_faces=int(len(faces)),
                mesh_to_gt_mean=float(d_mesh_to_gt.mean()), mesh_to_gt_p99=float(np.percentile(d_mesh_to_gt, 99)) if len(V) else None,
