@@ -95,8 +95,14 @@ struct neus2_ctx {
 	uint32_t mc_n_verts, mc_n_indices;
 };
 
+// Trainer::params_inference(): the optimizer's EMA copy once it has stepped, the training parameters before that (trainer.h:78-109, 170-178:
+// m_params_inference is only redirected to the optimizer's custom weights by the first optimizer_step)
+static const __half* inference_or_training_params(const neus2_ctx* ctx, int use_inference_params);
 static void stage_begin(neus2_ctx* ctx, int st, cudaStream_t s);
 static void stage_end(neus2_ctx* ctx, int st, cudaStream_t s);
+static const __half* inference_or_training_params(const neus2_ctx* ctx, int use_inference_params) {
+	return (use_inference_params && ctx->adam_step > 0) ? ctx->ema : ctx->params;
+}
 static int dmalloc(void** p, size_t bytes) {
 	CUDA_CHECK(cudaMalloc(p, bytes));
 	CUDA_CHECK(cudaMemset(*p, 0, bytes));
@@ -394,12 +400,12 @@ int neus2_set_training_step(neus2_ctx* ctx, int32_t step) {   // grid.h:2427-244
 
 int neus2_forward(neus2_ctx* ctx, void* stream, const float* coords, uint32_t n, void* out, int use_inference_params) {
 	CUDA_CHECK(cudaSetDevice(ctx->device));
-	return launch_network_forward((cudaStream_t)stream, ctx->gm, ctx->pl, use_inference_params ? ctx->ema : ctx->params, coords, nullptr, n, ctx->cfg.sdf_bias, (__half*)out);
+	return launch_network_forward((cudaStream_t)stream, ctx->gm, ctx->pl, inference_or_training_params(ctx, use_inference_params), coords, nullptr, n, ctx->cfg.sdf_bias, (__half*)out);
 }
 
 int neus2_sdf(neus2_ctx* ctx, void* stream, const float* pos, uint32_t stride, uint32_t n, void* out, int as_density, int use_inference_params) {
 	CUDA_CHECK(cudaSetDevice(ctx->device));
-	return launch_network_sdf((cudaStream_t)stream, ctx->gm, ctx->pl, use_inference_params ? ctx->ema : ctx->params, pos, stride, n, ctx->cfg.sdf_bias, as_density, (__half*)out, nullptr);
+	return launch_network_sdf((cudaStream_t)stream, ctx->gm, ctx->pl, inference_or_training_params(ctx, use_inference_params), pos, stride, n, ctx->cfg.sdf_bias, as_density, (__half*)out, nullptr);
 }
 
 int neus2_backward(neus2_ctx* ctx, void* stream_, const float* coords, const void* dL_dout, const uint32_t* n_in_dev, uint32_t n_rows, uint32_t indeed_batch_size) {
@@ -724,7 +730,7 @@ int neus2_render(neus2_ctx* ctx, void* stream_, const neus2_render_params* p, fl
 	const neus2_config& c = ctx->cfg;
 	const float cos_anneal_ratio = c.anneal_end == 0 ? 1.0f : (float)std::min(1.0, (double)((float)ctx->training_step / c.anneal_end));
 	// m_render_aabb == m_aabb unless the user crops (testbed_nerf.cu:3077)
-	return launch_render(stream, ctx->gm, ctx->pl, p->use_inference_params ? ctx->ema : ctx->params, c.sdf_bias, r, ctx->aabb, ctx->aabb, ctx->gmv, ctx->bitfield,
+	return launch_render(stream, ctx->gm, ctx->pl, inference_or_training_params(ctx, p->use_inference_params), c.sdf_bias, r, ctx->aabb, ctx->aabb, ctx->gmv, ctx->bitfield,
 	                     ctx->cone_angle_constant, cos_anneal_ratio, ctx->r_queue, ctx->r_counters, ctx->r_ray_rgba, ctx->r_ray_depth, ctx->r_ray_samples,
 	                     ctx->r_accumulate, rgba_out, depth_out);
 }
@@ -744,7 +750,7 @@ int neus2_sdf_lattice(neus2_ctx* ctx, void* stream, const uint32_t res[3], const
 	if (!res || !aabb || !out) FAIL("null argument");
 	if (!res[0] || !res[1] || !res[2] || z0 > z1 || z1 > res[2]) FAIL("bad lattice extent");
 	Aabb bb; for (int k = 0; k < 3; ++k) { bb.mn[k] = aabb[k]; bb.mx[k] = aabb[3 + k]; }
-	return launch_sdf_lattice((cudaStream_t)stream, ctx->gm, ctx->pl, use_inference_params ? ctx->ema : ctx->params, ctx->cfg.sdf_bias, res, bb, ctx->aabb, z0, z1, out);
+	return launch_sdf_lattice((cudaStream_t)stream, ctx->gm, ctx->pl, inference_or_training_params(ctx, use_inference_params), ctx->cfg.sdf_bias, res, bb, ctx->aabb, z0, z1, out);
 }
 
 int neus2_marching_cubes(neus2_ctx* ctx, void* stream_, const uint32_t res[3], const float aabb[6], float thresh, const float* density, uint32_t* n_verts, uint32_t* n_indices) {
@@ -877,7 +883,7 @@ int neus2_mesh_attributes(neus2_ctx* ctx, void* stream_, float* normals_out, flo
 		CUDA_CHECK(cudaMallocAsync((void**)&coords, (size_t)nv * 7 * sizeof(float), stream));
 		CUDA_CHECK(cudaMallocAsync((void**)&out16, (size_t)nv * 16 * sizeof(__half), stream));
 		int rc = launch_mesh_color_inputs(stream, nv, ctx->mc_verts, ctx->aabb, coords);
-		if (!rc) rc = launch_network_forward(stream, ctx->gm, ctx->pl, use_inference_params ? ctx->ema : ctx->params, coords, nullptr, nv, ctx->cfg.sdf_bias, out16);
+		if (!rc) rc = launch_network_forward(stream, ctx->gm, ctx->pl, inference_or_training_params(ctx, use_inference_params), coords, nullptr, nv, ctx->cfg.sdf_bias, out16);
 		if (!rc) rc = launch_mesh_extract_colors(stream, nv, out16, 0 /* train_in_linear_colors = false */, colors_out);
 		cudaFreeAsync(coords, stream); cudaFreeAsync(out16, stream);
 		if (rc) return rc;

@@ -259,3 +259,14 @@ def test_render_interleaved_rows_equal_whole_image(scene):
     rp.tile_h += block * stride            # runs past the last image row
     with pytest.raises(Exception):
         ctx.render(rp)
+
+
+def test_inference_params_before_the_first_optimizer_step(scene):
+    """Trainer::params_inference() is the training copy until the optimizer has stepped once (tcnn trainer.h:78-109): a freshly
+    initialised model renders / meshes the same with either parameter selection."""
+    import torch
+    ctx = scene["ctx"]
+    assert ctx.get_state()["optimizer_step"] == 0
+    c = torch.from_numpy(U.random_coords(100, seed=8)).cuda()
+    assert torch.equal(ctx.forward(c, use_inference_params=True).view(torch.int16), ctx.forward(c, use_inference_params=False).view(torch.int16))
+    assert torch.equal(ctx.sdf_lattice((16, 16, 16), use_inference_params=True), ctx.sdf_lattice((16, 16, 16), use_inference_params=False))
