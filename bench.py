@@ -348,7 +348,7 @@ def main():
                          "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes, "avg_launch_ms": dom_ms, "l2": l2},
             "stage_ms": {k: round(v[0], 4) for k, v in stages.items()},
             "per_step": {"rays": rays / K, "samples_before_compaction": n_u / K, "samples_compacted": n_c / K, "training_step": int(st.training_step),
-                         "first_pass_samples_evaluated_last_step": int(ctx.debug_buffer("counters", "<u4", (8,))[5].item())},
+                         "first_pass_samples_evaluated_last_step": int(st.first_pass_samples)},
         }
         if not args.no_cpu_baseline:
             try:

@@ -72,6 +72,7 @@ typedef struct neus2_step_stats {
 	float loss, ek_loss, mask_loss;      /* valid when loss_valid (refreshed every 16 steps, testbed.cu:2714) */
 	int32_t loss_valid;
 	int32_t density_grid_updated;
+	uint32_t first_pass_samples;         /* samples this rank's first network pass evaluated (<= N_u with forward_early_termination) */
 } neus2_step_stats;
 
 const char* neus2_last_error(void);

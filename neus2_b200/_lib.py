@@ -34,7 +34,7 @@ class StepStats(C.Structure):
         ("training_step", C.c_uint32), ("rays_per_batch", C.c_uint32), ("rays_per_batch_next", C.c_uint32),
         ("n_rays_kept", C.c_uint32), ("measured_batch_size_before_compaction", C.c_uint32), ("measured_batch_size", C.c_uint32),
         ("loss", C.c_float), ("ek_loss", C.c_float), ("mask_loss", C.c_float), ("loss_valid", C.c_int32),
-        ("density_grid_updated", C.c_int32),
+        ("density_grid_updated", C.c_int32), ("first_pass_samples", C.c_uint32),
     ]
 
 

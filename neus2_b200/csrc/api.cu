@@ -86,6 +86,8 @@ struct neus2_ctx {
 	uint32_t peer_world, peer_rank;
 	float* peer_grads[NEUS2_MAX_PEERS]; __half* peer_params[NEUS2_MAX_PEERS]; __half* peer_ema[NEUS2_MAX_PEERS];
 	bool optimizer_done;        // the sharded optimizer already ran for the step in flight
+	bool scratch_zeroed;        // train_step_end already enqueued the next step's zero-fills (counters, per-ray losses, gradients) behind its read-back
+	cudaEvent_t readback_event; // marks the end of train_step_end's device->host copies
 	// inference render scratch (sized on first use / growth, then reused)
 	size_t render_cap;          // tile pixels
 	void* r_queue; uint32_t* r_counters; float *r_ray_rgba, *r_ray_depth, *r_accumulate; uint32_t* r_ray_samples;
@@ -247,7 +249,7 @@ int neus2_ctx_create(const neus2_config* cfg, int device, neus2_ctx** out) {
 	CDM(ctx->density_grid, G3n * ctx->n_cascades); CDM(ctx->density_grid_tmp, G3n * ctx->n_cascades);
 	CDM(ctx->grid_positions, 3 * G3n * ctx->n_cascades); CDM(ctx->grid_indices, G3n * ctx->n_cascades); CDM(ctx->grid_density, G3n * ctx->n_cascades);
 	CDM(ctx->bitfield, G3n / 8 * NERF_CASCADES); CDM(ctx->density_grid_mean, 1);
-	if (cudaMallocHost((void**)&ctx->h_counters, 8 * sizeof(uint32_t)) != cudaSuccess || cudaMallocHost((void**)&ctx->h_scalars, 4 * sizeof(float)) != cudaSuccess) {
+	if (cudaMallocHost((void**)&ctx->h_counters, 16 * sizeof(uint32_t)) != cudaSuccess || cudaMallocHost((void**)&ctx->h_scalars, 4 * sizeof(float)) != cudaSuccess) {
 		neus2_ctx_destroy(ctx); FAIL("cudaMallocHost failed");
 	}
 	// reset_network state (testbed.cu:2087-2101)
@@ -279,6 +281,7 @@ void neus2_ctx_destroy(neus2_ctx* ctx) {
 	void* more[] = {ctx->r_queue, ctx->r_counters, ctx->r_ray_rgba, ctx->r_ray_depth, ctx->r_accumulate, ctx->r_ray_samples,
 		ctx->mc_block_counts, ctx->mc_counts, ctx->mc_vert_prefix, ctx->mc_indices, ctx->mc_verts};
 	for (void* p : more) if (p) cudaFree(p);
+	if (ctx->readback_event) cudaEventDestroy(ctx->readback_event);
 	if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
 	if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
 	delete ctx;
@@ -319,6 +322,7 @@ __global__ void k_widen_params(uint64_t n, const __half* __restrict__ params, fl
 
 int neus2_set_params(neus2_ctx* ctx, const float* master_host, uint64_t n, int reset_optimizer) {
 	if (n != ctx->n_params) FAIL("parameter count mismatch");
+	ctx->scratch_zeroed = false;
 	CUDA_CHECK(cudaSetDevice(ctx->device));
 	CUDA_CHECK(cudaMemcpy(ctx->master, master_host, n * sizeof(float), cudaMemcpyHostToDevice));
 	k_cast_params<<<(uint32_t)((n + 255) / 256), 256>>>(n, ctx->master, ctx->params);
@@ -408,13 +412,14 @@ int neus2_sdf(neus2_ctx* ctx, void* stream, const float* pos, uint32_t stride, u
 	return launch_network_sdf((cudaStream_t)stream, ctx->gm, ctx->pl, inference_or_training_params(ctx, use_inference_params), pos, stride, n, ctx->cfg.sdf_bias, as_density, (__half*)out, nullptr);
 }
 
-int neus2_backward(neus2_ctx* ctx, void* stream_, const float* coords, const void* dL_dout, const uint32_t* n_in_dev, uint32_t n_rows, uint32_t indeed_batch_size) {
-	cudaStream_t stream = (cudaStream_t)stream_;
-	CUDA_CHECK(cudaSetDevice(ctx->device));
+static int backward_on_stream(neus2_ctx* ctx, cudaStream_t stream, const float* coords, const void* dL_dout, const uint32_t* n_in_dev, uint32_t n_rows,
+                              uint32_t indeed_batch_size, bool grads_zeroed) {
 	if (n_rows > ctx->B_local) FAIL("n_rows exceeds the context's (local) batch size");
-	CUDA_CHECK(cudaMemsetAsync(ctx->grads, 0, ctx->n_params * sizeof(float), stream));   // EGradientMode::Overwrite
-	CUDA_CHECK(cudaMemsetAsync(ctx->var_acc, 0, sizeof(float), stream));
-	CUDA_CHECK(cudaMemsetAsync(ctx->w1row0_acc, 0, 64 * sizeof(float), stream));
+	if (!grads_zeroed) {
+		CUDA_CHECK(cudaMemsetAsync(ctx->grads, 0, ctx->n_params * sizeof(float), stream));   // EGradientMode::Overwrite
+		CUDA_CHECK(cudaMemsetAsync(ctx->var_acc, 0, sizeof(float), stream));
+		CUDA_CHECK(cudaMemsetAsync(ctx->w1row0_acc, 0, 64 * sizeof(float), stream));
+	}
 	stage_begin(ctx, ST_FWDBWD, stream);
 	CHECK(launch_network_fwdbwd(stream, ctx->gm, ctx->pl, ctx->params, coords, (const __half*)dL_dout, n_in_dev, n_rows, ctx->cfg.sdf_bias, indeed_batch_size,
 	                            ctx->grads, ctx->var_acc, ctx->w1row0_acc, ctx->so));
@@ -423,6 +428,21 @@ int neus2_backward(neus2_ctx* ctx, void* stream_, const float* coords, const voi
 	CHECK(launch_weight_gradients(stream, ctx->pl, ctx->so, ctx->params, n_in_dev, n_rows, ctx->partials, weight_gradient_partials(), ctx->var_acc, ctx->w1row0_acc, ctx->grads));
 	stage_end(ctx, ST_WGRAD, stream);
 	return 0;
+}
+
+// the zero-fills a step starts from: Counters::prepare_for_training_steps (testbed_nerf.cu:3399-3410) + EGradientMode::Overwrite
+static int zero_step_scratch(neus2_ctx* ctx, cudaStream_t stream, uint32_t n_rays) {
+	CUDA_CHECK(cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(uint32_t), stream));
+	CUDA_CHECK(cudaMemsetAsync(ctx->loss, 0, sizeof(float) * n_rays, stream));
+	CUDA_CHECK(cudaMemsetAsync(ctx->ek_loss, 0, sizeof(float) * n_rays, stream));
+	CUDA_CHECK(cudaMemsetAsync(ctx->mask_loss, 0, sizeof(float) * n_rays, stream));
+	return 0;
+}
+
+int neus2_backward(neus2_ctx* ctx, void* stream_, const float* coords, const void* dL_dout, const uint32_t* n_in_dev, uint32_t n_rows, uint32_t indeed_batch_size) {
+	CUDA_CHECK(cudaSetDevice(ctx->device));
+	ctx->scratch_zeroed = false;   // an explicit operator call owns the gradient buffer again
+	return backward_on_stream(ctx, (cudaStream_t)stream_, coords, dL_dout, n_in_dev, n_rows, indeed_batch_size, false);
 }
 
 int neus2_optimizer_step(neus2_ctx* ctx, void* stream, float loss_scale) {
@@ -503,10 +523,9 @@ int neus2_train_step_begin(neus2_ctx* ctx, void* stream_, uint32_t rank, uint32_
 
 	// Counters::prepare_for_training_steps (:3399-3410)
 	const uint32_t R = ctx->rays_per_batch;
-	CUDA_CHECK(cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(uint32_t), stream));
-	CUDA_CHECK(cudaMemsetAsync(ctx->loss, 0, sizeof(float) * R, stream));
-	CUDA_CHECK(cudaMemsetAsync(ctx->ek_loss, 0, sizeof(float) * R, stream));
-	CUDA_CHECK(cudaMemsetAsync(ctx->mask_loss, 0, sizeof(float) * R, stream));
+	const bool pre_zeroed = ctx->scratch_zeroed;   // train_step_end of the previous step already queued these fills on this stream
+	ctx->scratch_zeroed = false;
+	if (!pre_zeroed) CHECK(zero_step_scratch(ctx, stream, R));
 
 	// train_nerf_step (:3723-4001)
 	const uint32_t n_local = R / world_size, ray_offset = rank * n_local;
@@ -543,7 +562,7 @@ int neus2_train_step_begin(neus2_ctx* ctx, void* stream_, uint32_t rank, uint32_
 	                          ctx->rays, ctx->numsteps, ctx->coords, ctx->ray_tmp, ctx->scan_tmp, ctx->coords_compacted, ctx->dloss, ctx->loss, ctx->ek_loss,
 	                          ctx->mask_loss, ctx->counters + 2));
 	stage_end(ctx, ST_LOSS, stream);
-	CHECK(neus2_backward(ctx, stream_, ctx->coords_compacted, ctx->dloss, ctx->counters + 2, rows_local, ctx->B));   // :3941-3946
+	CHECK(backward_on_stream(ctx, stream, ctx->coords_compacted, ctx->dloss, ctx->counters + 2, rows_local, ctx->B, /*grads_zeroed=*/pre_zeroed));   // :3941-3946
 	CUDA_CHECK(cudaMemcpyAsync(ctx->counts_global, ctx->counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
 	return 0;
 }
@@ -579,7 +598,17 @@ int neus2_train_step_end(neus2_ctx* ctx, void* stream_, const uint32_t* counts_g
 	// the one structurally required host sync per step (:3412-3416): local counters + the (possibly all-reduced) global ones
 	CUDA_CHECK(cudaMemcpyAsync(ctx->h_counters, ctx->counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
 	CUDA_CHECK(cudaMemcpyAsync(ctx->h_counters + 4, ctx->counts_global, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-	CUDA_CHECK(cudaStreamSynchronize(stream));
+	CUDA_CHECK(cudaMemcpyAsync(ctx->h_counters + 8, ctx->counters + 4, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));   // first-pass work counters
+	if (!ctx->readback_event) CUDA_CHECK(cudaEventCreateWithFlags(&ctx->readback_event, cudaEventDisableTiming));
+	CUDA_CHECK(cudaEventRecord(ctx->readback_event, stream));
+	// While the host waits for that read-back and prepares the next step, the GPU already zero-fills what the next step starts from
+	// (42 MB of gradients + per-ray scratch): stream-ordered behind the copies above and, data-parallel, behind the peers' barrier.
+	CHECK(zero_step_scratch(ctx, stream, ctx->max_rays));
+	CUDA_CHECK(cudaMemsetAsync(ctx->grads, 0, ctx->n_params * sizeof(float), stream));
+	CUDA_CHECK(cudaMemsetAsync(ctx->var_acc, 0, sizeof(float), stream));
+	CUDA_CHECK(cudaMemsetAsync(ctx->w1row0_acc, 0, 64 * sizeof(float), stream));
+	ctx->scratch_zeroed = true;
+	CUDA_CHECK(cudaEventSynchronize(ctx->readback_event));
 	stage_collect(ctx);
 	const uint32_t n_kept_local = ctx->h_counters[0];
 	uint32_t counts[3] = {ctx->h_counters[4], ctx->h_counters[5], ctx->h_counters[6]};
@@ -593,6 +622,7 @@ int neus2_train_step_end(neus2_ctx* ctx, void* stream_, const uint32_t* counts_g
 	s.rays_per_batch = ctx->step_rays;
 	s.n_rays_kept = have_global ? counts[0] : n_kept_local;
 	s.density_grid_updated = ctx->step_density_updated;
+	s.first_pass_samples = ctx->cfg.forward_early_termination ? ctx->h_counters[9] : std::min(ctx->h_counters[1], ctx->max_samples);
 	// Counters::update_after_training (:3412-3438)
 	if (counts[1] == 0 || counts[2] == 0) {
 		s.measured_batch_size = 0; s.measured_batch_size_before_compaction = 0;
