@@ -238,7 +238,8 @@ int neus2_ctx_create(const neus2_config* cfg, int device, neus2_ctx** out) {
 	CDM(ctx->master, N); CDM(ctx->params, N); CDM(ctx->ema, N); CDM(ctx->grads, N); CDM(ctx->m1, N); CDM(ctx->m2, N); CDM(ctx->steps, N); CDM(ctx->adam_bias_table, ADAM_BIAS_TABLE);
 	CDM(ctx->numsteps_all, R); CDM(ctx->base, R); CDM(ctx->slot, R); CDM(ctx->ray_indices, R); CDM(ctx->numsteps, 2 * (size_t)R); CDM(ctx->scan_tmp, 2 * (size_t)R);
 	CDM(ctx->n_windows, R); CDM(ctx->windows, sampling_window_bytes_per_ray() * (size_t)R); CDM(ctx->ray_setup, 12 * (size_t)R);
-	CDM(ctx->counters, 8); CDM(ctx->counts_global, 4); CDM(ctx->rays, 6 * (size_t)R); CDM(ctx->coords, 7 * (size_t)S); CDM(ctx->ray_tmp, 12 * (size_t)R);
+	CDM(ctx->counters, 12); ctx->counts_global = ctx->counters + 8;   // one 48-byte read-back per step covers both
+	CDM(ctx->rays, 6 * (size_t)R); CDM(ctx->coords, 7 * (size_t)S); CDM(ctx->ray_tmp, 12 * (size_t)R);
 	CDM(ctx->coords_compacted, 7 * (size_t)B); CDM(ctx->loss, R); CDM(ctx->ek_loss, R); CDM(ctx->mask_loss, R);
 	CDM(ctx->mlp_out, 16 * (size_t)S); CDM(ctx->dloss, 16 * (size_t)B);
 	CDM(ctx->so.dOUT, 16 * (size_t)B); CDM(ctx->so.H2, 64 * (size_t)B); CDM(ctx->so.dH2, 64 * (size_t)B); CDM(ctx->so.H1, 64 * (size_t)B); CDM(ctx->so.dH1, 64 * (size_t)B);
@@ -269,7 +270,7 @@ void neus2_ctx_destroy(neus2_ctx* ctx) {
 	if (!ctx) return;
 	void* ptrs[] = {ctx->master, ctx->params, ctx->ema, ctx->grads, ctx->m1, ctx->m2, ctx->steps, ctx->adam_bias_table, ctx->d_pixels, ctx->d_focal, ctx->d_principal, ctx->d_xforms,
 		ctx->numsteps_all, ctx->base, ctx->slot, ctx->ray_indices, ctx->numsteps, ctx->scan_tmp, ctx->counters, ctx->n_windows, ctx->windows, ctx->ray_setup, ctx->rays, ctx->coords, ctx->ray_tmp,
-		ctx->coords_compacted, ctx->loss, ctx->ek_loss, ctx->mask_loss, ctx->mlp_out, ctx->dloss, ctx->counts_global, ctx->so.dOUT, ctx->so.H2, ctx->so.dH2, ctx->so.H1, ctx->so.dH1,
+		ctx->coords_compacted, ctx->loss, ctx->ek_loss, ctx->mask_loss, ctx->mlp_out, ctx->dloss, ctx->so.dOUT, ctx->so.H2, ctx->so.dH2, ctx->so.H1, ctx->so.dH1,
 		ctx->so.CIN, ctx->so.dSO, ctx->so.H0, ctx->so.dH0, ctx->so.X0, ctx->so.dI, ctx->partials, ctx->var_acc, ctx->w1row0_acc, ctx->scalar_tmp,
 		ctx->density_grid, ctx->density_grid_tmp, ctx->grid_positions, ctx->grid_indices, ctx->grid_density, ctx->bitfield, ctx->density_grid_mean};
 	for (void* p : ptrs) if (p) cudaFree(p);
@@ -596,9 +597,8 @@ int neus2_train_step_end(neus2_ctx* ctx, void* stream_, const uint32_t* counts_g
 	}
 	stage_end(ctx, ST_STEP, stream);
 	// the one structurally required host sync per step (:3412-3416): local counters + the (possibly all-reduced) global ones
-	CUDA_CHECK(cudaMemcpyAsync(ctx->h_counters, ctx->counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-	CUDA_CHECK(cudaMemcpyAsync(ctx->h_counters + 4, ctx->counts_global, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-	CUDA_CHECK(cudaMemcpyAsync(ctx->h_counters + 8, ctx->counters + 4, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));   // first-pass work counters
+	// counters[0..3] local {kept, N_u, compacted}, [4..7] first-pass work counters, [8..11] the (all-reduced) global counts
+	CUDA_CHECK(cudaMemcpyAsync(ctx->h_counters, ctx->counters, 12 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
 	if (!ctx->readback_event) CUDA_CHECK(cudaEventCreateWithFlags(&ctx->readback_event, cudaEventDisableTiming));
 	CUDA_CHECK(cudaEventRecord(ctx->readback_event, stream));
 	// While the host waits for that read-back and prepares the next step, the GPU already zero-fills what the next step starts from
@@ -611,7 +611,7 @@ int neus2_train_step_end(neus2_ctx* ctx, void* stream_, const uint32_t* counts_g
 	CUDA_CHECK(cudaEventSynchronize(ctx->readback_event));
 	stage_collect(ctx);
 	const uint32_t n_kept_local = ctx->h_counters[0];
-	uint32_t counts[3] = {ctx->h_counters[4], ctx->h_counters[5], ctx->h_counters[6]};
+	uint32_t counts[3] = {ctx->h_counters[8], ctx->h_counters[9], ctx->h_counters[10]};
 	if (counts_global) { counts[0] = counts_global[0]; counts[1] = counts_global[1]; counts[2] = counts_global[2]; }
 	const bool have_global = counts_global != nullptr || ctx->cfg.world_size > 1;
 	++ctx->training_step;
@@ -622,7 +622,7 @@ int neus2_train_step_end(neus2_ctx* ctx, void* stream_, const uint32_t* counts_g
 	s.rays_per_batch = ctx->step_rays;
 	s.n_rays_kept = have_global ? counts[0] : n_kept_local;
 	s.density_grid_updated = ctx->step_density_updated;
-	s.first_pass_samples = ctx->cfg.forward_early_termination ? ctx->h_counters[9] : std::min(ctx->h_counters[1], ctx->max_samples);
+	s.first_pass_samples = ctx->cfg.forward_early_termination ? ctx->h_counters[5] : std::min(ctx->h_counters[1], ctx->max_samples);
 	// Counters::update_after_training (:3412-3438)
 	if (counts[1] == 0 || counts[2] == 0) {
 		s.measured_batch_size = 0; s.measured_batch_size_before_compaction = 0;
@@ -658,7 +658,7 @@ int neus2_debug_buffer(neus2_ctx* ctx, const char* name, void** ptr, uint64_t* n
 	const E table[] = {
 		{"numsteps_all", ctx->numsteps_all, R * 4}, {"ray_indices", ctx->ray_indices, R * 4}, {"rays", ctx->rays, R * 24}, {"numsteps", ctx->numsteps, R * 8},
 		{"coords", ctx->coords, S * 28}, {"mlp_out", ctx->mlp_out, S * 32}, {"coords_compacted", ctx->coords_compacted, B * 28}, {"dloss", ctx->dloss, B * 32},
-		{"loss", ctx->loss, R * 4}, {"ek_loss", ctx->ek_loss, R * 4}, {"mask_loss", ctx->mask_loss, R * 4}, {"counters", ctx->counters, 32},
+		{"loss", ctx->loss, R * 4}, {"ek_loss", ctx->ek_loss, R * 4}, {"mask_loss", ctx->mask_loss, R * 4}, {"counters", ctx->counters, 48},
 		{"density_grid", ctx->density_grid, G3n * ctx->n_cascades * 4}, {"bitfield", ctx->bitfield, G3n / 8 * NERF_CASCADES}, {"density_grid_mean", ctx->density_grid_mean, 4},
 		{"grid_positions", ctx->grid_positions, G3n * ctx->n_cascades * 12}, {"grid_indices", ctx->grid_indices, G3n * ctx->n_cascades * 4},
 		{"grid_density", ctx->grid_density, G3n * ctx->n_cascades * 2},
