@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--res", type=int, default=256)
     ap.add_argument("--mc", type=int, default=256)
     ap.add_argument("--json", default=None)
+    ap.add_argument("--box", action="store_true", help="a box with a sphere on top instead of the two spheres: flat faces, sharp edges, a concave junction")
     ap.add_argument("--dtu", action="store_true", help="BASELINE.json configs[1]: the DTU-Scan24-shaped scene (49 views 1600x1200, cameras on a cap above the object)")
     ap.add_argument("--mask-weight", type=float, default=0.0)
     ap.add_argument("--full-forward", action="store_true", help="evaluate every marched sample in the first pass (reference behaviour) instead of the early cut")
@@ -40,9 +41,12 @@ def main():
     if args.dtu:
         data = synthetic.dtu_like_views(n_views=49, width=1600, height=1200, seed=0)
         args.views = 49
+    elif args.box:
+        data = synthetic.render_box_views(n_views=args.views, width=args.res, height=args.res, seed=0)
     else:
         data = synthetic.render_sphere_views(n_views=args.views, width=args.res, height=args.res, seed=0, elevation_deg=(-55.0, 65.0))
     H, W = data["pixels"].shape[1:3]
+    true_sdf = (lambda pts: synthetic.box_scene_sdf(pts, data["scene"])) if args.box else (lambda pts: synthetic.sphere_sdf(pts, data["spheres"]))
     ctx = N.Context(N.default_config(mask_loss_weight=args.mask_weight, forward_early_termination=0 if args.full_forward else 1))
     ctx.init_params()
     ctx.set_dataset(data["pixels"], data["focal"], data["principal"], data["xforms"])
@@ -88,23 +92,33 @@ def main():
         # the cameras sit on a cap above the object: the underside is never observed, judge the surface they see (z above the lowest camera ray)
         seen = V[:, 2] > 0.5 - 0.05
         V = V[seen]
-    d_mesh_to_gt = np.abs(synthetic.sphere_sdf(V, data["spheres"]))
-    # analytic surface samples (area-weighted over the spheres, outside the other spheres)
+    d_mesh_to_gt = np.abs(true_sdf(V))
+    # analytic surface samples
     rs = np.random.RandomState(0)
-    pts = []
-    for c, r in data["spheres"]:
-        n = int(40000 * (r / data["spheres"][0][1]) ** 2)
-        d = rs.normal(size=(n, 3))
-        d /= np.linalg.norm(d, axis=1, keepdims=True)
-        pts.append(c + r * d)
-    P = np.concatenate(pts)
-    P = P[np.abs(synthetic.sphere_sdf(P, data["spheres"])) < 1e-9]
-    if args.dtu:
-        P = P[P[:, 2] > 0.5 - 0.05]
+    if args.box:
+        # rejection: project random points near the surface along the numerical SDF gradient
+        P = rs.uniform(0.2, 0.8, (400000, 3))
+        P = P[np.abs(true_sdf(P)) < 0.02]
+        for _ in range(3):
+            e = 1e-4
+            g = np.stack([(true_sdf(P + np.eye(3)[k] * e) - true_sdf(P - np.eye(3)[k] * e)) / (2 * e) for k in range(3)], -1)
+            P = P - true_sdf(P)[:, None] * g / np.maximum(np.linalg.norm(g, axis=1, keepdims=True), 1e-9)
+        P = P[np.abs(true_sdf(P)) < 1e-5]
+    else:
+        pts = []
+        for c, r in data["spheres"]:
+            n = int(40000 * (r / data["spheres"][0][1]) ** 2)
+            d = rs.normal(size=(n, 3))
+            d /= np.linalg.norm(d, axis=1, keepdims=True)
+            pts.append(c + r * d)
+        P = np.concatenate(pts)
+        P = P[np.abs(true_sdf(P)) < 1e-9]
+        if args.dtu:
+            P = P[P[:, 2] > 0.5 - 0.05]
     d_gt_to_mesh = cKDTree(V).query(P)[0] if len(V) else np.full(len(P), np.inf)
     chamfer = 0.5 * (d_mesh_to_gt.mean() + d_gt_to_mesh.mean())
 
-    out = dict(steps=args.steps, views=args.views, res=[int(W), int(H)], scene="dtu-shaped" if args.dtu else "two spheres, cameras all around", train_s=t_train, ms_per_step=1e3 * t_train / args.steps, rays_per_s=rays / t_train,
+    out = dict(steps=args.steps, views=args.views, res=[int(W), int(H)], scene="dtu-shaped" if args.dtu else ("box + sphere" if args.box else "two spheres, cameras all around"), train_s=t_train, ms_per_step=1e3 * t_train / args.steps, rays_per_s=rays / t_train,
                psnr_mean=float(np.mean(psnr)), psnr_min=float(np.min(psnr)), render_s_per_view=t_render / args.views,
                render_last_view=rstats, mc_res=args.mc, lattice_s=t_lattice, mc_s=t_mc, n_verts=int(len(V)), n_faces=int(len(faces)),
                mesh_to_gt_mean=float(d_mesh_to_gt.mean()), mesh_to_gt_p99=float(np.percentile(d_mesh_to_gt, 99)) if len(V) else None,
