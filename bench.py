@@ -37,6 +37,7 @@ def parse():
     ap.add_argument("--width", type=int, default=1600)
     ap.add_argument("--height", type=int, default=1200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--global-movement", action="store_true", help="secondary measurement: time the step of frames >= 1 of a dynamic sequence (DeltaNetwork in the network kernels, delta gradients, global-move Adam)")
     ap.add_argument("--dp", default="p2p", choices=["p2p", "nccl"], help="N>1: optimizer fused with the gradient reduction over NVLink peer memory (p2p) or NCCL all-reduce + replicated Adam")
     return ap.parse_args()
 
@@ -223,6 +224,7 @@ def workload_config(args, n_gpus):
         "batch_samples_per_gpu": 1 << 18, "global_batch_samples": (1 << 18) * n_gpus, "parallelism": (f"dp{n_gpus} (rays sharded; " + ("Adam fused with the gradient reduction over NVLink peer memory, 1/N of the optimizer state per GPU)" if args.dp == "p2p" else "NCCL all-reduce of fp32 grads + replicated Adam)")) if n_gpus > 1 else "single GPU",
         "l2_policy": "per-step working set (>=470 MB of sample/activation buffers) exceeds the 126 MB L2; no explicit flush",
         "preroll_steps": args.preroll,
+        **({"global_movement": "DeltaNetwork on (frames >= 1 of a dynamic sequence)"} if args.global_movement else {}),
     }
 
 
@@ -270,7 +272,11 @@ def main():
     def step():
         return parallel.train_step(ctx, rank, world)   # world > 1: NCCL all-reduce of the 10.56 M fp32 gradients over NVLink
 
-    for _ in range(args.preroll + args.warmup):
+    for _ in range(args.preroll):
+        st = step()
+    if args.global_movement:
+        ctx.begin_global_movement()                # m_use_delta = m_train_delta = true from here on
+    for _ in range(args.warmup):
         st = step()
     torch.cuda.synchronize()
     if world > 1:

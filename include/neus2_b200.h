@@ -60,6 +60,14 @@ typedef struct neus2_config {
 	/* 1 (default): the step's first network pass stops along each ray where the loss stops reading (T < 1e-4, testbed_nerf.cu:1567);
 	 * 0: evaluate every marched sample like the reference.  Same loss, gradients and counters either way (tests/test_gpu_step.py). */
 	int32_t forward_early_termination;
+	/* "globalmove" optimizer (configs/nerf/base.json:135-158: Ema{ExponentialDecay{Adam}}) of the DeltaNetwork's own trainer
+	 * (src/testbed.cu:2320-2328).  The Ema wrapper's inference copy has no consumer (the network always reads params()), so it is not kept. */
+	float delta_learning_rate;       /* 1e-4 */
+	float delta_beta1, delta_beta2;  /* 0.9, 0.99 */
+	float delta_epsilon;             /* 1e-10 */
+	uint32_t delta_decay_start;      /* 50 */
+	uint32_t delta_decay_interval;   /* 25 (0 = no decay) */
+	float delta_decay_base;          /* 0.99 */
 } neus2_config;
 
 typedef struct neus2_step_stats {
@@ -226,6 +234,32 @@ int neus2_set_density_grid(neus2_ctx* ctx, void* stream, const float* density_gr
  * `frozen_steps` steps (predict_global_movement_training_step) and the learning rate becomes `after_learning_rate` (> 0). */
 int neus2_next_frame(neus2_ctx* ctx, void* stream, float after_learning_rate, uint32_t frozen_steps);
 int neus2_get_time_frame(const neus2_ctx* ctx, uint32_t* current_training_time_frame, float* learning_rate);
+
+/* ---- global rigid motion of dynamic scenes ("predict_global_movement": true) -------------------------------
+ * The reference keeps an ACCUMULATED rotation (3x3) + transition applied to every ray (global_movement_with_rotation_6d,
+ * src/testbed_nerf.cu:194-213, 1377-1387, 2287-2294) and, for frames >= 1, a DeltaNetwork (include/neural-graphics-primitives/
+ * transform_network.h:23-480): 6d rotation + transition applied to every SAMPLE inside the network (add_global_movement_with_rotation_6d,
+ * common_operation.cuh:416-470; nerf_network.h:162-181, 663-674) and trained by its own Adam from the position gradients
+ * (nerf_network.h:604-651; transform_network.h:110-250).
+ *
+ * neus2_begin_global_movement: Testbed::training_network_next_frame's global-movement part (src/testbed.cu:2054, 2076-2078 and the
+ * trainer reset at :2569-2577): accumulated <- delta o accumulated (accumulate_global_movement_rotation_6d_kernel,
+ * common_operation.cuh:551-580), delta <- identity with a fresh optimizer, m_use_delta = m_train_delta = 1.  Call it next to
+ * neus2_next_frame.  While the mode is on, every entry point that evaluates the network (train step, forward, sdf, render,
+ * sdf_lattice, mesh attributes, density-grid refresh) deforms its sample positions / directions first, the backward pass also
+ * produces the 9 delta gradients and neus2_optimizer_step / _sharded also steps the delta parameters.
+ * neus2_set_delta_mode(0): "finetune_global_movement": false at step predict_global_movement_training_step (src/testbed.cu:2659-2663). */
+int neus2_begin_global_movement(neus2_ctx* ctx, void* stream);
+int neus2_set_delta_mode(neus2_ctx* ctx, int use_delta);
+/* save_global_movement / load_global_movement / load_local_movement (nerf_network.h:1180-1278), Testbed::save_transform
+ * (src/testbed.cu:3119-3142).  Null pointers are skipped. */
+int neus2_get_global_movement(neus2_ctx* ctx, void* stream, float accumulated_rotation[9], float accumulated_transition[3],
+                              float delta_rotation_6d[6], float delta_transition[3], int* use_delta);
+int neus2_set_global_movement(neus2_ctx* ctx, void* stream, const float accumulated_rotation[9], const float accumulated_transition[3],
+                              const float delta_rotation_6d[6], const float delta_transition[3], const float first_frame_offset[3]);
+/* Device address of the 12-float gradient accumulator of the delta parameters ([transition 3 | rotation-6d 6 | 0 0 0]): a
+ * data-parallel caller all-reduces it between neus2_train_step_begin and the optimizer step. */
+int neus2_delta_gradients_device(neus2_ctx* ctx, float** acc_dev);
 
 #ifdef __cplusplus
 }

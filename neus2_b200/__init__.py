@@ -59,6 +59,7 @@ class Context:
         check(self._lib.neus2_ctx_create(C.byref(self.cfg), C.c_int(device), C.byref(h)))
         self._h = h
         self.peers_attached = False
+        self.global_movement_active = False   # m_use_delta (mirrors the context's flag for the data-parallel step)
         self.n_params = int(self._lib.neus2_n_params(self._h))
         lay = (C.c_uint32 * 8)()
         check(self._lib.neus2_param_layout(self._h, lay))
@@ -249,6 +250,41 @@ class Context:
     def next_frame(self, after_learning_rate=0.0, frozen_steps=0, stream=None):
         """Testbed::training_network_next_frame without global-movement prediction (call after set_dataset with the new frame)."""
         check(self._lib.neus2_next_frame(self._h, _stream(stream), C.c_float(after_learning_rate), C.c_uint32(frozen_steps)))
+
+    # ---- global rigid motion of dynamic scenes (hyperparams.predict_global_movement) ---------------------------------
+    def begin_global_movement(self, stream=None):
+        """accumulated <- delta o accumulated, delta <- identity with a fresh optimizer, m_use_delta = m_train_delta = True
+        (the global-movement part of Testbed::training_network_next_frame)."""
+        check(self._lib.neus2_begin_global_movement(self._h, _stream(stream)))
+        self.global_movement_active = True
+
+    def set_delta_mode(self, use_delta):
+        check(self._lib.neus2_set_delta_mode(self._h, C.c_int(int(bool(use_delta)))))
+        self.global_movement_active = bool(use_delta)
+
+    def global_movement(self, stream=None):
+        """dict(rotation [3,3], transition [3] (accumulated, as stored in half), delta_rotation_6d [6], delta_transition [3], use_delta)."""
+        R, t, r6, dt, use = (C.c_float * 9)(), (C.c_float * 3)(), (C.c_float * 6)(), (C.c_float * 3)(), C.c_int()
+        check(self._lib.neus2_get_global_movement(self._h, _stream(stream), R, t, r6, dt, C.byref(use)))
+        return dict(rotation=np.array(R, dtype=np.float32).reshape(3, 3), transition=np.array(t, dtype=np.float32),
+                    delta_rotation_6d=np.array(r6, dtype=np.float32), delta_transition=np.array(dt, dtype=np.float32), use_delta=bool(use.value))
+
+    def set_global_movement(self, rotation=None, transition=None, delta_rotation_6d=None, delta_transition=None, first_frame_offset=None, stream=None):
+        def arr(v, n):
+            if v is None:
+                return None
+            a = np.ascontiguousarray(np.asarray(v, dtype=np.float32).reshape(-1))
+            assert a.size == n
+            return (C.c_float * n)(*a.tolist())
+        check(self._lib.neus2_set_global_movement(self._h, _stream(stream), arr(rotation, 9), arr(transition, 3), arr(delta_rotation_6d, 6),
+                                                  arr(delta_transition, 3), arr(first_frame_offset, 3)))
+
+    def delta_gradients(self):
+        """Zero-copy device view of the 12-float delta-gradient accumulator ([transition 3 | rotation-6d 6 | 0 0 0])."""
+        torch = _torch()
+        a = C.c_void_p()
+        check(self._lib.neus2_delta_gradients_device(self._h, C.byref(a)))
+        return torch.as_tensor(_DevArray(a.value, (12,), "<f4", None), device=f"cuda:{self.device}")
 
     def time_frame(self):
         tf, lr = C.c_uint32(), C.c_float()

@@ -74,6 +74,12 @@ struct neus2_ctx {
 	uint32_t time_frame;            // current_training_time_frame
 	uint32_t frozen_steps;          // predict_global_movement_training_step: canonical parameters are frozen for the first steps of frames >= 1
 	float learning_rate;            // current Adam learning rate (after_learning_rate from frame 1 on)
+	// DeltaNetwork: the per-frame rigid motion (transform_network.h:23-480) with its own trainer (testbed.cu:2320-2328).
+	// Parameter order [transition 4 | rotation-6d 8] (DeltaNetwork::set_params).  d_xform is what the kernels read.
+	float *d_xform, *d_acc, *d_master, *d_m1, *d_m2; uint32_t* d_steps; __half* d_params;
+	bool use_delta;             // m_use_delta == m_train_delta for frames >= 1 (testbed.cu:2704-2710)
+	uint32_t delta_opt_step;    // the global-move Adam's step count (drives its ExponentialDecay)
+	float delta_lr_factor;
 	bool step_density_updated;
 	uint32_t* h_counters;       // pinned
 	int profiling;              // record CUDA events around the stages of a step
@@ -151,6 +157,93 @@ int launch_adam_bias_table(cudaStream_t stream, float beta1, float beta2, uint32
 	return 0;
 }
 
+// ---- DeltaNetwork parameters -------------------------------------------------------------------------------------------
+// One warp.  Optionally one Adam step of the global-move trainer on the 12 parameters (adam_step, tcnn optimizers/adam.h:52-160:
+// no matrix parameters, so zero gradients are skipped and there is no L2 term; the gradient is the fp32 batch sum rounded to half,
+// transform_network.h:214-243), then the float image the kernels read is rebuilt from the half parameters
+// (rotation_6d_to_matrix, common_operation.cuh:37-60) and the gradient accumulators are cleared.
+__global__ void k_delta_update(int do_step, float loss_scale, float lr, float beta1, float beta2, float eps, float off0, float off1, float off2,
+                               float* __restrict__ acc, float* __restrict__ master, __half* __restrict__ params, float* __restrict__ m1, float* __restrict__ m2,
+                               uint32_t* __restrict__ steps, float* __restrict__ xform) {
+	const int k = threadIdx.x;
+	if (do_step && k < 12) {
+		const int ai = k < 3 ? k : (k >= 4 && k < 10 ? k - 1 : -1);
+		const float g_half = ai >= 0 ? __half2float(__float2half_rn(acc[ai])) : 0.f;
+		const float gradient = g_half / loss_scale;
+		if (gradient != 0) {
+			const float w = master[k];
+			const float gsq = __fmul_rn(gradient, gradient);
+			const float fm = fmaf(beta1, m1[k], __fmul_rn(1 - beta1, gradient));
+			const float sm = fmaf(beta2, m2[k], __fmul_rn(1 - beta2, gsq));
+			m1[k] = fm; m2[k] = sm;
+			const uint32_t cs = ++steps[k];
+			const float learning_rate = __fmul_rn(lr, sqrtf(1 - powf(beta2, (float)cs)) / (1 - powf(beta1, (float)cs)));
+			const float eff = fminf(fmaxf(learning_rate / (sqrtf(sm) + eps), 0.f), 3.402823466e+38f);
+			const float nw = fmaf(-eff, fm, w);
+			master[k] = nw;
+			params[k] = __float2half_rn(nw);
+		}
+	}
+	__syncwarp();
+	if (k == 0) {
+		float a1[3], a2[3], b1[3], u2[3], b2[3], b3[3];
+		#pragma unroll
+		for (int d = 0; d < 3; ++d) { a1[d] = __half2float(params[4 + d]); a2[d] = __half2float(params[7 + d]); }
+		normalize3(a1, b1);
+		const float dd = fmaf(b1[2], a2[2], fmaf(b1[1], a2[1], __fmul_rn(b1[0], a2[0])));
+		#pragma unroll
+		for (int d = 0; d < 3; ++d) u2[d] = fmaf(-dd, b1[d], a2[d]);
+		normalize3(u2, b2);
+		b3[0] = fmaf(b1[1], b2[2], -__fmul_rn(b1[2], b2[1]));
+		b3[1] = fmaf(b1[2], b2[0], -__fmul_rn(b1[0], b2[2]));
+		b3[2] = fmaf(b1[0], b2[1], -__fmul_rn(b1[1], b2[0]));
+		const float off[3] = {off0, off1, off2};
+		#pragma unroll
+		for (int d = 0; d < 3; ++d) {
+			xform[DELTA_R + d * 3 + 0] = b1[d]; xform[DELTA_R + d * 3 + 1] = b2[d]; xform[DELTA_R + d * 3 + 2] = b3[d];
+			const float t = __half2float(params[d]);
+			xform[DELTA_T + d] = t; xform[DELTA_TMO + d] = __fsub_rn(t, off[d]); xform[DELTA_OFF + d] = off[d];
+			xform[DELTA_A1 + d] = a1[d]; xform[DELTA_A2 + d] = a2[d]; xform[DELTA_U2 + d] = u2[d];
+		}
+	}
+	if (k < 12) acc[k] = 0.f;
+}
+
+static int launch_delta_update(neus2_ctx* ctx, cudaStream_t stream, int do_step, float loss_scale, float lr) {
+	const neus2_config& c = ctx->cfg;
+	k_delta_update<<<1, 32, 0, stream>>>(do_step, loss_scale, lr, c.delta_beta1, c.delta_beta2, c.delta_epsilon, ctx->gmv.first_frame_offset[0],
+	                                     ctx->gmv.first_frame_offset[1], ctx->gmv.first_frame_offset[2], ctx->d_acc, ctx->d_master, ctx->d_params, ctx->d_m1, ctx->d_m2,
+	                                     ctx->d_steps, ctx->d_xform);
+	COUNT_LAUNCH(1);
+	CUDA_CHECK(cudaGetLastError());
+	return 0;
+}
+// A fresh global-move trainer (reset_network_incremental, testbed.cu:2569-2577 -> DeltaNetwork::initialize_params,
+// transform_network.h:352-396): transition 0, rotation-6d (1,0,0, 0,1,0), optimizer state cleared.
+static int reset_delta(neus2_ctx* ctx, cudaStream_t stream) {
+	const float init[12] = {0, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
+	__half init_h[12];
+	for (int k = 0; k < 12; ++k) init_h[k] = __float2half_rn(init[k]);
+	CUDA_CHECK(cudaMemcpyAsync(ctx->d_master, init, sizeof(init), cudaMemcpyHostToDevice, stream));
+	CUDA_CHECK(cudaMemcpyAsync(ctx->d_params, init_h, sizeof(init_h), cudaMemcpyHostToDevice, stream));
+	CUDA_CHECK(cudaMemsetAsync(ctx->d_m1, 0, 12 * sizeof(float), stream));
+	CUDA_CHECK(cudaMemsetAsync(ctx->d_m2, 0, 12 * sizeof(float), stream));
+	CUDA_CHECK(cudaMemsetAsync(ctx->d_steps, 0, 12 * sizeof(uint32_t), stream));
+	CUDA_CHECK(cudaMemsetAsync(ctx->d_acc, 0, 12 * sizeof(float), stream));
+	CUDA_CHECK(cudaStreamSynchronize(stream));   // the host arrays above live on this stack frame
+	ctx->delta_opt_step = 0; ctx->delta_lr_factor = 1.0f;
+	return launch_delta_update(ctx, stream, 0, 1.f, 0.f);
+}
+// ExponentialDecayOptimizer::step (tcnn optimizers/exponential_decay.h:60-71) around the Adam step of the global-move trainer
+static int delta_optimizer_step(neus2_ctx* ctx, cudaStream_t stream, float loss_scale) {
+	const neus2_config& c = ctx->cfg;
+	const uint32_t st = ctx->delta_opt_step;
+	if (st == 0) ctx->delta_lr_factor = 1.0f;
+	if (c.delta_decay_interval && st >= c.delta_decay_start && (st - c.delta_decay_start) % c.delta_decay_interval == 0) ctx->delta_lr_factor *= c.delta_decay_base;
+	++ctx->delta_opt_step;
+	return launch_delta_update(ctx, stream, 1, loss_scale, c.delta_learning_rate * ctx->delta_lr_factor);
+}
+
 extern "C" {
 
 const char* neus2_last_error(void) { return g_error.c_str(); }
@@ -166,6 +259,9 @@ void neus2_default_config(neus2_config* c) {
 	c->background_color[0] = c->background_color[1] = c->background_color[2] = 0.f;
 	c->density_grid_decay = 0.95f; c->loss_scale = 128.f;
 	c->world_size = 1; c->max_rays_per_batch = 1u << 18; c->forward_early_termination = 1;
+	// "globalmove" optimizer of configs/nerf/base.json:135-158 (Ema{ExponentialDecay{Adam}})
+	c->delta_learning_rate = 1e-4f; c->delta_beta1 = 0.9f; c->delta_beta2 = 0.99f; c->delta_epsilon = 1e-10f;
+	c->delta_decay_start = 50; c->delta_decay_interval = 25; c->delta_decay_base = 0.99f;
 }
 
 static int build_tables(neus2_ctx* ctx) {
@@ -250,6 +346,8 @@ int neus2_ctx_create(const neus2_config* cfg, int device, neus2_ctx** out) {
 	CDM(ctx->density_grid, G3n * ctx->n_cascades); CDM(ctx->density_grid_tmp, G3n * ctx->n_cascades);
 	CDM(ctx->grid_positions, 3 * G3n * ctx->n_cascades); CDM(ctx->grid_indices, G3n * ctx->n_cascades); CDM(ctx->grid_density, G3n * ctx->n_cascades);
 	CDM(ctx->bitfield, G3n / 8 * NERF_CASCADES); CDM(ctx->density_grid_mean, 1);
+	CDM(ctx->d_xform, DELTA_XFORM_FLOATS); CDM(ctx->d_acc, 12); CDM(ctx->d_master, 12); CDM(ctx->d_m1, 12); CDM(ctx->d_m2, 12); CDM(ctx->d_steps, 12); CDM(ctx->d_params, 12);
+	CTXCHECK(reset_delta(ctx, 0));
 	if (cudaMallocHost((void**)&ctx->h_counters, 16 * sizeof(uint32_t)) != cudaSuccess || cudaMallocHost((void**)&ctx->h_scalars, 4 * sizeof(float)) != cudaSuccess) {
 		neus2_ctx_destroy(ctx); FAIL("cudaMallocHost failed");
 	}
@@ -272,7 +370,8 @@ void neus2_ctx_destroy(neus2_ctx* ctx) {
 		ctx->numsteps_all, ctx->base, ctx->slot, ctx->ray_indices, ctx->numsteps, ctx->scan_tmp, ctx->counters, ctx->n_windows, ctx->windows, ctx->ray_setup, ctx->rays, ctx->coords, ctx->ray_tmp,
 		ctx->coords_compacted, ctx->loss, ctx->ek_loss, ctx->mask_loss, ctx->mlp_out, ctx->dloss, ctx->so.dOUT, ctx->so.H2, ctx->so.dH2, ctx->so.H1, ctx->so.dH1,
 		ctx->so.CIN, ctx->so.dSO, ctx->so.H0, ctx->so.dH0, ctx->so.X0, ctx->so.dI, ctx->partials, ctx->var_acc, ctx->w1row0_acc, ctx->scalar_tmp,
-		ctx->density_grid, ctx->density_grid_tmp, ctx->grid_positions, ctx->grid_indices, ctx->grid_density, ctx->bitfield, ctx->density_grid_mean};
+		ctx->density_grid, ctx->density_grid_tmp, ctx->grid_positions, ctx->grid_indices, ctx->grid_density, ctx->bitfield, ctx->density_grid_mean,
+		ctx->d_xform, ctx->d_acc, ctx->d_master, ctx->d_m1, ctx->d_m2, ctx->d_steps, ctx->d_params};
 	for (void* p : ptrs) if (p) cudaFree(p);
 	for (uint32_t r = 0; r < ctx->peer_world; ++r) if (r != ctx->peer_rank) {
 		if (ctx->peer_grads[r]) cudaIpcCloseMemHandle(ctx->peer_grads[r]);
@@ -423,7 +522,7 @@ static int backward_on_stream(neus2_ctx* ctx, cudaStream_t stream, const float* 
 	}
 	stage_begin(ctx, ST_FWDBWD, stream);
 	CHECK(launch_network_fwdbwd(stream, ctx->gm, ctx->pl, ctx->params, coords, (const __half*)dL_dout, n_in_dev, n_rows, ctx->cfg.sdf_bias, indeed_batch_size,
-	                            ctx->grads, ctx->var_acc, ctx->w1row0_acc, ctx->so));
+	                            ctx->grads, ctx->var_acc, ctx->w1row0_acc, ctx->so, ctx->use_delta ? ctx->d_acc : nullptr));
 	stage_end(ctx, ST_FWDBWD, stream);
 	stage_begin(ctx, ST_WGRAD, stream);
 	CHECK(launch_weight_gradients(stream, ctx->pl, ctx->so, ctx->params, n_in_dev, n_rows, ctx->partials, weight_gradient_partials(), ctx->var_acc, ctx->w1row0_acc, ctx->grads));
@@ -454,6 +553,7 @@ int neus2_optimizer_step(neus2_ctx* ctx, void* stream, float loss_scale) {
 	const int frozen = ctx->time_frame >= 1 && ctx->training_step < ctx->frozen_steps;   // m_train_canonical = false (testbed.cu:2659-2667)
 	const int rc_ = launch_adam_ema((cudaStream_t)stream, ctx->n_params, ctx->pl.off_grid, loss_scale, ctx->learning_rate, c.beta1, c.beta2, c.epsilon, c.l2_reg,
 	                       c.ema_decay, ctx->adam_step, ctx->grads, ctx->master, ctx->params, ctx->m1, ctx->m2, ctx->steps, ctx->ema, ctx->adam_bias_table, ADAM_BIAS_TABLE, frozen);
+	if (rc_ == 0 && ctx->use_delta) CHECK(delta_optimizer_step(ctx, (cudaStream_t)stream, loss_scale));   // m_global_move.trainer->optimizer_step (testbed_nerf.cu:3506-3508)
 	stage_end(ctx, ST_OPT, (cudaStream_t)stream);
 	return rc_;
 }
@@ -865,6 +965,7 @@ int neus2_optimizer_step_sharded(neus2_ctx* ctx, void* stream, float loss_scale)
 	const int frozen = ctx->time_frame >= 1 && ctx->training_step < ctx->frozen_steps;
 	const int rc_ = launch_adam_ema_p2p((cudaStream_t)stream, ctx->n_params, ctx->pl.off_grid, ctx->peer_rank, ctx->peer_world, loss_scale, ctx->learning_rate, c.beta1, c.beta2,
 	                                    c.epsilon, c.l2_reg, c.ema_decay, ctx->adam_step, ctx->peer_grads, ctx->peer_params, ctx->peer_ema, ctx->master, ctx->m1, ctx->m2, ctx->steps, ctx->adam_bias_table, ADAM_BIAS_TABLE, frozen);
+	if (rc_ == 0 && ctx->use_delta) CHECK(delta_optimizer_step(ctx, (cudaStream_t)stream, loss_scale));   // every rank steps its replica on the all-reduced sums
 	stage_end(ctx, ST_OPT, (cudaStream_t)stream);
 	ctx->optimizer_done = true;
 	return rc_;
@@ -957,6 +1058,87 @@ int neus2_next_frame(neus2_ctx* ctx, void* stream_, float after_learning_rate, u
 	ctx->rays_per_batch = 1u << 12;
 	ctx->measured_before = 0;
 	ctx->rng = Pcg32(ctx->cfg.seed);
+	return 0;
+}
+
+// ---- global rigid motion of dynamic scenes ("predict_global_movement", src/testbed.cu:2054, 2076-2078, 2659-2667, 2704-2710) ----
+// Start the new frame's motion estimate: fold the delta trained on the previous frame into the accumulated motion
+// (NerfNetwork::accumulate_global_movement, nerf_network.h:1163-1178; accumulate_global_movement_rotation_6d_kernel,
+// common_operation.cuh:551-580: R_acc <- R_d R_acc, t_acc <- R_d (t_acc + t_d), stored in half), reset the delta to the identity
+// with a fresh optimizer, and route every network evaluation through it (m_use_delta = m_train_delta = true).
+int neus2_begin_global_movement(neus2_ctx* ctx, void* stream_) {
+	cudaStream_t stream = (cudaStream_t)stream_;
+	CUDA_CHECK(cudaSetDevice(ctx->device));
+	float x[DELTA_XFORM_FLOATS];
+	CUDA_CHECK(cudaMemcpyAsync(x, ctx->d_xform, sizeof(x), cudaMemcpyDeviceToHost, stream));
+	CUDA_CHECK(cudaStreamSynchronize(stream));
+	const float* R = x + DELTA_R; const float* t = x + DELTA_T;
+	float after[9], sum[3];
+	for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j)
+		after[i * 3 + j] = fmaf(R[i * 3 + 2], ctx->gmv.R[6 + j], fmaf(R[i * 3 + 1], ctx->gmv.R[3 + j], R[i * 3] * ctx->gmv.R[j]));
+	for (int k = 0; k < 3; ++k) sum[k] = ctx->gmv.T[k] + t[k];
+	for (int k = 0; k < 9; ++k) ctx->gmv.R[k] = __half2float(__float2half_rn(after[k]));
+	for (int k = 0; k < 3; ++k) ctx->gmv.T[k] = __half2float(__float2half_rn(fmaf(R[k * 3 + 2], sum[2], fmaf(R[k * 3 + 1], sum[1], R[k * 3] * sum[0]))));
+	CHECK(reset_delta(ctx, stream));
+	ctx->use_delta = true;
+	ctx->gm.delta_xform = ctx->d_xform;
+	return 0;
+}
+
+// m_use_delta / m_train_delta (they are equal whenever the frame index is >= 1).  Switching off keeps the delta parameters: the next
+// neus2_begin_global_movement still accumulates them ("finetune_global_movement": false drops the delta from the network after
+// predict_global_movement_training_step steps, testbed.cu:2659-2663).
+int neus2_set_delta_mode(neus2_ctx* ctx, int use_delta) {
+	ctx->use_delta = use_delta != 0;
+	ctx->gm.delta_xform = ctx->use_delta ? ctx->d_xform : nullptr;
+	return 0;
+}
+
+// Snapshot / inspection access.  accumulated_*: what ray generation applies (values as stored in half); delta: the 6d rotation and the
+// transition of the current frame's DeltaNetwork (fp32 master copy).  Null pointers are skipped.
+int neus2_get_global_movement(neus2_ctx* ctx, void* stream_, float accumulated_rotation[9], float accumulated_transition[3], float delta_rotation_6d[6],
+                              float delta_transition[3], int* use_delta) {
+	cudaStream_t stream = (cudaStream_t)stream_;
+	CUDA_CHECK(cudaSetDevice(ctx->device));
+	if (accumulated_rotation) memcpy(accumulated_rotation, ctx->gmv.R, 9 * sizeof(float));
+	if (accumulated_transition) memcpy(accumulated_transition, ctx->gmv.T, 3 * sizeof(float));
+	if (delta_rotation_6d || delta_transition) {
+		float m[12];
+		CUDA_CHECK(cudaMemcpyAsync(m, ctx->d_master, sizeof(m), cudaMemcpyDeviceToHost, stream));
+		CUDA_CHECK(cudaStreamSynchronize(stream));
+		if (delta_transition) memcpy(delta_transition, m, 3 * sizeof(float));
+		if (delta_rotation_6d) memcpy(delta_rotation_6d, m + 4, 6 * sizeof(float));
+	}
+	if (use_delta) *use_delta = ctx->use_delta ? 1 : 0;
+	return 0;
+}
+
+int neus2_set_global_movement(neus2_ctx* ctx, void* stream_, const float accumulated_rotation[9], const float accumulated_transition[3],
+                              const float delta_rotation_6d[6], const float delta_transition[3], const float first_frame_offset[3]) {
+	cudaStream_t stream = (cudaStream_t)stream_;
+	CUDA_CHECK(cudaSetDevice(ctx->device));
+	if (accumulated_rotation) for (int k = 0; k < 9; ++k) ctx->gmv.R[k] = __half2float(__float2half_rn(accumulated_rotation[k]));
+	if (accumulated_transition) for (int k = 0; k < 3; ++k) ctx->gmv.T[k] = __half2float(__float2half_rn(accumulated_transition[k]));
+	if (first_frame_offset) memcpy(ctx->gmv.first_frame_offset, first_frame_offset, 3 * sizeof(float));
+	if (delta_rotation_6d || delta_transition) {
+		float m[12]; __half h[12];
+		CUDA_CHECK(cudaMemcpyAsync(m, ctx->d_master, sizeof(m), cudaMemcpyDeviceToHost, stream));
+		CUDA_CHECK(cudaStreamSynchronize(stream));
+		if (delta_transition) memcpy(m, delta_transition, 3 * sizeof(float));
+		if (delta_rotation_6d) memcpy(m + 4, delta_rotation_6d, 6 * sizeof(float));
+		for (int k = 0; k < 12; ++k) h[k] = __float2half_rn(m[k]);
+		CUDA_CHECK(cudaMemcpyAsync(ctx->d_master, m, sizeof(m), cudaMemcpyHostToDevice, stream));
+		CUDA_CHECK(cudaMemcpyAsync(ctx->d_params, h, sizeof(h), cudaMemcpyHostToDevice, stream));
+		CUDA_CHECK(cudaStreamSynchronize(stream));
+	}
+	return launch_delta_update(ctx, stream, 0, 1.f, 0.f);
+}
+
+// The 9 gradient sums of the DeltaNetwork ([transition 3 | rotation-6d 6], fp32, 12 slots): a data-parallel caller all-reduces them in
+// place between the backward pass and the optimizer step.
+int neus2_delta_gradients_device(neus2_ctx* ctx, float** acc_dev) {
+	if (!acc_dev) FAIL("null argument");
+	*acc_dev = ctx->d_acc;
 	return 0;
 }
 

@@ -14,7 +14,20 @@ struct GridMeta {
 	uint32_t offset[NEUS_MAX_LEVELS + 1]; // in entries (x2 features)
 	uint32_t res[NEUS_MAX_LEVELS];
 	float scale[NEUS_MAX_LEVELS];         // == res-1 (integer valued, grid.h:1477)
+	const float* delta_xform;             // DeltaNetwork in use (m_use_delta): device float[DELTA_XFORM_FLOATS], else nullptr
 };
+
+// Device-resident float image of the DeltaNetwork's 12 half parameters (transform_network.h:23-480), rebuilt after every
+// update of them: R row-major (columns = Gram-Schmidt of the 6d rotation), t, t - first_frame_offset, first_frame_offset,
+// and the Gram-Schmidt inputs the backward needs (a1, a2, u2 = a2 - (b1.a2) b1).
+#define DELTA_R 0
+#define DELTA_T 9
+#define DELTA_TMO 12
+#define DELTA_OFF 15
+#define DELTA_A1 18
+#define DELTA_A2 21
+#define DELTA_U2 24
+#define DELTA_XFORM_FLOATS 28
 
 // Parameter layout in the reference order (nerf_network.h:741-785): [sdf-MLP | colour-MLP | grid | variance(4)].
 struct ParamLayout {

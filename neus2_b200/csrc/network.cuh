@@ -57,6 +57,10 @@ struct WarpSlab {
 	static constexpr int V = DI + 16 * LD_X0 * 2;            // float [16][3]       v = dL/d normal
 	static constexpr int VN = V + 16 * 3 * 4;                // half  [16][8]       colour-input grad cols 32..39
 	static constexpr int BWD_END = VN + 16 * 8 * 2;
+	// DeltaNetwork training extras (k_network_fwdbwd<true> only)
+	static constexpr int DORIG = BWD_END;                    // float [16][3]       un-deformed positions of the tile
+	static constexpr int DACC = DORIG + 16 * 3 * 4;          // float [16][9]       per-lane sums of the 9 delta gradients
+	static constexpr int DELTA_END = DACC + 16 * 9 * 4;
 };
 
 __device__ __forceinline__ void stage_matrix(__half* dst, int ld_dst, const __half* __restrict__ src, int rows, int cols, int tid, int nthreads) {
@@ -304,6 +308,90 @@ __device__ __forceinline__ void gather_tile(const GridMeta& gm, const __half* __
 	}
 }
 
+// DeltaNetwork forward (add_global_movement_with_rotation_6d, common_operation.cuh:416-470) in place on the warp's 16
+// coordinates: pos' = R (pos + t - off) + off on lanes 0..15; the warped direction is un-warped, rotated and warped again on
+// lanes 16..31.  Same expression order as oracle/neus_oracle.cpp:delta_apply.
+__device__ __forceinline__ void delta_tile(const float* __restrict__ dx, float* sCoord, int lane, bool with_dir) {
+	const int s = lane & 15;
+	float R[9];
+	#pragma unroll
+	for (int k = 0; k < 9; ++k) R[k] = __ldg(dx + DELTA_R + k);
+	if (lane < 16) {
+		const float q0 = __fadd_rn(sCoord[s * 7 + 0], __ldg(dx + DELTA_TMO + 0)), q1 = __fadd_rn(sCoord[s * 7 + 1], __ldg(dx + DELTA_TMO + 1)),
+		            q2 = __fadd_rn(sCoord[s * 7 + 2], __ldg(dx + DELTA_TMO + 2));
+		#pragma unroll
+		for (int k = 0; k < 3; ++k) {
+			const float r = fmaf(R[k * 3 + 2], q2, fmaf(R[k * 3 + 1], q1, __fmul_rn(R[k * 3], q0)));
+			sCoord[s * 7 + k] = __fadd_rn(r, __ldg(dx + DELTA_OFF + k));
+		}
+	} else if (with_dir) {
+		const float u0 = fmaf(sCoord[s * 7 + 4], 2.0f, -1.0f), u1 = fmaf(sCoord[s * 7 + 5], 2.0f, -1.0f), u2 = fmaf(sCoord[s * 7 + 6], 2.0f, -1.0f);
+		#pragma unroll
+		for (int k = 0; k < 3; ++k) {
+			const float r = fmaf(R[k * 3 + 2], u2, fmaf(R[k * 3 + 1], u1, __fmul_rn(R[k * 3], u0)));
+			sCoord[s * 7 + 4 + k] = __fmul_rn(__fadd_rn(r, 1.0f), 0.5f);
+		}
+	}
+	__syncwarp();
+}
+
+// gradients_for_normalize (common_operation.cuh:62-90)
+__device__ __forceinline__ float dot3f(const float a[3], const float b[3]) { return fmaf(a[2], b[2], fmaf(a[1], b[1], __fmul_rn(a[0], b[0]))); }
+__device__ __forceinline__ void grad_normalize(const float in[3], const float go[3], float gi[3]) {
+	const float nrm = sqrtf(dot3f(in, in));
+	const float n3 = __fmul_rn(__fmul_rn(nrm, nrm), nrm);
+	const float xx = __fdiv_rn(fmaf(in[2], in[2], __fmul_rn(in[1], in[1])), n3), yy = __fdiv_rn(fmaf(in[2], in[2], __fmul_rn(in[0], in[0])), n3),
+	            zz = __fdiv_rn(fmaf(in[1], in[1], __fmul_rn(in[0], in[0])), n3);
+	const float xy = __fdiv_rn(__fmul_rn(-in[0], in[1]), n3), xz = __fdiv_rn(__fmul_rn(-in[0], in[2]), n3), yz = __fdiv_rn(__fmul_rn(-in[1], in[2]), n3);
+	gi[0] = fmaf(go[2], xz, fmaf(go[1], xy, __fmul_rn(go[0], xx)));
+	gi[1] = fmaf(go[2], yz, fmaf(go[1], yy, __fmul_rn(go[0], xy)));
+	gi[2] = fmaf(go[2], zz, fmaf(go[1], yz, __fmul_rn(go[0], xz)));
+}
+// One sample of DeltaNetwork::backward_impl (add_loss_to_rotation_6d_each<half, float> + gradient_rotation_matrix_to_6d<half>,
+// common_operation.cuh:92-150, 788-840): out[0..2] = d/d transition, out[3..8] = d/d rotation-6d, each rounded to half as the
+// reference's per-sample matrices are.  L = dL/d(deformed position), xin = un-deformed position.  Mirrors
+// oracle/neus_oracle.cpp:delta_backward_sample expression by expression.
+__device__ __forceinline__ void delta_backward_sample(const float* __restrict__ dx, const float L[3], const float xin[3], float out[9]) {
+	float R[9], a1[3], a2[3], u2[3], b1[3], b2[3], iv[3];
+	#pragma unroll
+	for (int k = 0; k < 9; ++k) R[k] = __ldg(dx + DELTA_R + k);
+	#pragma unroll
+	for (int k = 0; k < 3; ++k) {
+		a1[k] = __ldg(dx + DELTA_A1 + k); a2[k] = __ldg(dx + DELTA_A2 + k); u2[k] = __ldg(dx + DELTA_U2 + k);
+		b1[k] = R[k * 3 + 0]; b2[k] = R[k * 3 + 1];
+		iv[k] = __fadd_rn(xin[k], __ldg(dx + DELTA_T + k));
+	}
+	#pragma unroll
+	for (int j = 0; j < 3; ++j) out[j] = round_h(fmaf(R[6 + j], L[2], fmaf(R[3 + j], L[1], __fmul_rn(R[j], L[0]))));
+	float G[3][3];
+	#pragma unroll
+	for (int a = 0; a < 3; ++a) {
+		#pragma unroll
+		for (int b = 0; b < 3; ++b) G[a][b] = __fmul_rn(L[a], iv[b]);
+	}
+	float db1[3], db2[3];
+	#pragma unroll
+	for (int k = 0; k < 3; ++k) { db1[k] = round_h(G[k][0]); db2[k] = round_h(G[k][1]); }
+	db1[0] = round_h(__fadd_rn(db1[0], round_h(fmaf(b2[1], G[2][2], -__fmul_rn(b2[2], G[1][2])))));
+	db1[1] = round_h(__fadd_rn(db1[1], round_h(fmaf(b2[2], G[0][2], -__fmul_rn(b2[0], G[2][2])))));
+	db1[2] = round_h(__fadd_rn(db1[2], round_h(fmaf(b2[0], G[1][2], -__fmul_rn(b2[1], G[0][2])))));
+	db2[0] = round_h(__fadd_rn(db2[0], round_h(fmaf(b1[2], G[1][2], -__fmul_rn(b1[1], G[2][2])))));
+	db2[1] = round_h(__fadd_rn(db2[1], round_h(fmaf(b1[0], G[2][2], -__fmul_rn(b1[2], G[0][2])))));
+	db2[2] = round_h(__fadd_rn(db2[2], round_h(fmaf(b1[1], G[0][2], -__fmul_rn(b1[0], G[1][2])))));
+	float r[3];
+	grad_normalize(u2, db2, r);
+	const float rb = dot3f(r, b1), ba = dot3f(b1, a2);
+	float da2[3], db1f[3], da1[3];
+	#pragma unroll
+	for (int k = 0; k < 3; ++k) {
+		da2[k] = __fsub_rn(r[k], __fmul_rn(b1[k], rb));
+		db1f[k] = __fsub_rn(__fsub_rn(db1[k], __fmul_rn(r[k], ba)), __fmul_rn(a2[k], rb));
+	}
+	grad_normalize(a1, db1f, da1);
+	#pragma unroll
+	for (int k = 0; k < 3; ++k) { out[3 + k] = round_h(da1[k]); out[6 + k] = round_h(da2[k]); }
+}
+
 // SH degree 4 on the warped direction (tcnn encodings/spherical_harmonics.h:47-100); 16 halves.
 __device__ __forceinline__ void sh4(float dx, float dy, float dz, __half* out) {
 	const float x = fmaf(dx, 2.f, -1.f), y = fmaf(dy, 2.f, -1.f), z = fmaf(dz, 2.f, -1.f);
@@ -349,6 +437,7 @@ __device__ __forceinline__ void forward_tile(const GridMeta& gm, const __half* _
 	float* sNRM = reinterpret_cast<float*>(slab + WarpSlab::NRM);
 	float* sDY = reinterpret_cast<float*>(slab + WarpSlab::DY);
 
+	if (gm.delta_xform) delta_tile(gm.delta_xform, sCoord, lane, true);   // m_use_delta (nerf_network.h:162-181)
 	// --- SDF-MLP input: [half(x)-half(0.5) | enc | 0]  (nerf_network.h:206-212)
 	if (lane < 16) {
 		#pragma unroll
@@ -473,6 +562,7 @@ __device__ __forceinline__ void sdf_tile(const GridMeta& gm, const __half* __res
 	float* sCoord = reinterpret_cast<float*>(slab + WarpSlab::COORD);
 	__half* sX0 = reinterpret_cast<__half*>(slab + WarpSlab::X0);
 	__half* sSDF = reinterpret_cast<__half*>(slab + WarpSlab::SDF);
+	if (gm.delta_xform) delta_tile(gm.delta_xform, sCoord, lane, false);   // nerf_network.h:663-674
 	if (lane < 16) {
 		#pragma unroll
 		for (int d = 0; d < 3; ++d) sX0[lane * LD_X0 + d] = __hsub(__float2half_rn(sCoord[lane * 7 + d]), __float2half_rn(0.5f));

@@ -13,6 +13,8 @@ static constexpr int FWD_SMEM = WeightSmem::FWD_END * 2 + WARPS_PER_CTA * WarpSl
 #define MERGE_MAX_HEADS 10     // pre-reduce a level's atomics in the warp when its 16 samples fall into <= this many runs of equal cells
 #endif
 static constexpr int BWD_SMEM = WeightSmem::BWD_END * 2 + WARPS_BWD * WarpSlab::BWD_END;
+static constexpr int BWD_SMEM_DELTA = WeightSmem::BWD_END * 2 + WARPS_BWD * WarpSlab::DELTA_END;
+static_assert(BWD_SMEM_DELTA <= 227 * 1024, "training kernel (delta variant) exceeds the 227 KB shared-memory limit");
 
 // A tile's coords (16 x 7 floats) travel global -> registers -> warp slab: the loads for the NEXT tile are issued before the
 // current tile is processed, so their HBM latency hides behind a whole tile of work.  Rows >= n are zero-filled; `wrap` maps
@@ -125,22 +127,34 @@ k_network_sdf(GridMeta gm, ParamLayout pl, const __half* __restrict__ params, co
 //   w1row0_acc[64]        += column sums of the forward-mode sweep (second-order term of W1 row 0)
 //   staged operand matrices (half, row-major [n_rows][w]) for the weight-gradient GEMMs.
 // ------------------------------------------------------------------------------------------------
+// DELTA (m_train_delta && m_use_delta, nerf_network.h:604-651 + DeltaNetwork::backward_impl, transform_network.h:110-250):
+// the tile's coordinates pass through the DeltaNetwork inside forward_tile; the gradient that reaches its output
+// (grid backward w.r.t. the position + the xyz rows of both MLP input gradients) is turned into the 9 parameter gradients
+// per sample and summed: per lane in shared memory, per warp at the end, one atomicAdd per warp into delta_acc[9].
+template <bool DELTA>
 __global__ void __launch_bounds__(WARPS_BWD * 32, 1)
 k_network_fwdbwd(GridMeta gm, ParamLayout pl, const __half* __restrict__ params, const float* __restrict__ coords,
                  const __half* __restrict__ dL_dout, const uint32_t* __restrict__ n_in_ptr, uint32_t n_rows, float sdf_bias,
-                 float batch_f, float* __restrict__ grads, float* __restrict__ var_acc, float* __restrict__ w1row0_acc, StagedOperands so, int dbg) {
+                 float batch_f, float* __restrict__ grads, float* __restrict__ var_acc, float* __restrict__ w1row0_acc, StagedOperands so, int dbg,
+                 float* __restrict__ delta_acc) {
 	extern __shared__ __align__(16) unsigned char smem[];
 	__half* sw = reinterpret_cast<__half*>(smem);
 	stage_weights(sw, params, pl, true, threadIdx.x, blockDim.x);
 	__syncthreads();
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int g = lane >> 2, t = lane & 3;
-	unsigned char* slab = smem + WeightSmem::BWD_END * 2 + warp * WarpSlab::BWD_END;
+	unsigned char* slab = smem + WeightSmem::BWD_END * 2 + warp * (DELTA ? WarpSlab::DELTA_END : WarpSlab::BWD_END);
 	float* sCoord = reinterpret_cast<float*>(slab + WarpSlab::COORD);
 	__half* sX0 = reinterpret_cast<__half*>(slab + WarpSlab::X0);
 	__half* sDIN = reinterpret_cast<__half*>(slab + WarpSlab::DIN);
 	__half* sCIN = reinterpret_cast<__half*>(slab + WarpSlab::CIN);
 	float* sDY = reinterpret_cast<float*>(slab + WarpSlab::DY);
+	float* sORIG = reinterpret_cast<float*>(slab + WarpSlab::DORIG);
+	float* sDACC = reinterpret_cast<float*>(slab + WarpSlab::DACC);
+	if (DELTA && lane < 16) {
+		#pragma unroll
+		for (int k = 0; k < 9; ++k) sDACC[lane * 9 + k] = 0.f;
+	}
 	__half* sDL = reinterpret_cast<__half*>(slab + WarpSlab::DL);
 	__half* sDX = reinterpret_cast<__half*>(slab + WarpSlab::DX);
 	__half* sDI = reinterpret_cast<__half*>(slab + WarpSlab::DI);
@@ -189,6 +203,10 @@ k_network_fwdbwd(GridMeta gm, ParamLayout pl, const __half* __restrict__ params,
 		}
 		__syncwarp();
 		if (tile + tile_stride < n_tiles) { prefetch_coords(cr, coords, (tile + tile_stride) * TILE, n_rows, n_in, lane); prefetch_dl((tile + tile_stride) * TILE); }
+		if (DELTA && lane < 16) {   // forward_tile deforms sCoord in place; the DeltaNetwork backward needs its input
+			#pragma unroll
+			for (int d = 0; d < 3; ++d) sORIG[lane * 3 + d] = sCoord[lane * 7 + d];
+		}
 		forward_tile<true>(gm, params, pl, sw, slab, sdf_bias, lane, st);
 
 		// ---- colour MLP backward (fully_fused_mlp.cu:968-1085) -----------------------------------
@@ -294,6 +312,27 @@ k_network_fwdbwd(GridMeta gm, ParamLayout pl, const __half* __restrict__ params,
 			}
 			for (int k = 3 + E; k < SDF_IN; ++k) sDI[s * LD_X0 + k] = __float2half(0.f);
 			if (s < n_valid) var_local += __half2float(sDL[s * 16 + 7]);
+			if (DELTA && s < n_valid) {
+				// dL/d(deformed position): kernel_grid_backward_input on the first-order dL/d enc (nerf_network.h:423-442), then
+				// += colour-input xyz rows, += sdf-MLP-input xyz rows (add_positions_view<float, T>, :607-626)
+				float L[3] = {0.f, 0.f, 0.f};
+				for (int k = 0; k < E; ++k) {
+					const float dl = __half2float(sDX[s * LD_X0 + 3 + k]);
+					L[0] = fmaf(dl, sDY[s * LD_DY + 3 * k + 0], L[0]);
+					L[1] = fmaf(dl, sDY[s * LD_DY + 3 * k + 1], L[1]);
+					L[2] = fmaf(dl, sDY[s * LD_DY + 3 * k + 2], L[2]);
+				}
+				float xin[3], o9[9];
+				#pragma unroll
+				for (int d = 0; d < 3; ++d) {
+					L[d] = __fadd_rn(L[d], __half2float(sVN[s * 8 + d]));
+					L[d] = __fadd_rn(L[d], __half2float(sDX[s * LD_X0 + d]));
+					xin[d] = sORIG[s * 3 + d];
+				}
+				delta_backward_sample(gm.delta_xform, L, xin, o9);
+				#pragma unroll
+				for (int k = 0; k < 9; ++k) sDACC[s * 9 + k] += o9[k];
+			}
 		}
 		__syncwarp();
 		// ---- second-order sdf-MLP sweeps (fully_fused_mlp.cu:1089-1198)
@@ -402,6 +441,18 @@ k_network_fwdbwd(GridMeta gm, ParamLayout pl, const __half* __restrict__ params,
 	var_local += __shfl_xor_sync(0xffffffffu, var_local, 8);
 	var_local += __shfl_xor_sync(0xffffffffu, var_local, 16);
 	if (lane == 0 && var_local != 0.f) atomicAdd(var_acc, var_local);
+	if (DELTA) {
+		__syncwarp();
+		#pragma unroll
+		for (int k = 0; k < 9; ++k) {
+			float v = lane < 16 ? sDACC[lane * 9 + k] : 0.f;
+			v += __shfl_xor_sync(0xffffffffu, v, 1);
+			v += __shfl_xor_sync(0xffffffffu, v, 2);
+			v += __shfl_xor_sync(0xffffffffu, v, 4);
+			v += __shfl_xor_sync(0xffffffffu, v, 8);
+			if (lane == 0 && v != 0.f) atomicAdd(delta_acc + k, v);
+		}
+	}
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -441,9 +492,10 @@ int launch_network_sdf(cudaStream_t stream, const GridMeta& gm, const ParamLayou
 
 int launch_network_fwdbwd(cudaStream_t stream, const GridMeta& gm, const ParamLayout& pl, const __half* params, const float* coords,
                           const __half* dL_dout, const uint32_t* n_in_ptr, uint32_t n_rows, float sdf_bias, uint32_t indeed_batch_size,
-                          float* grads, float* var_acc, float* w1row0_acc, const StagedOperands& so) {
-	static bool attr[NEUS_MAX_DEVICES] = {};
-	if (ensure_dynamic_smem(k_network_fwdbwd, BWD_SMEM, attr)) return -1;
+                          float* grads, float* var_acc, float* w1row0_acc, const StagedOperands& so, float* delta_acc) {
+	static bool attr[NEUS_MAX_DEVICES] = {}, attr_delta[NEUS_MAX_DEVICES] = {};
+	const bool delta = gm.delta_xform != nullptr && delta_acc != nullptr;
+	if (delta ? ensure_dynamic_smem(k_network_fwdbwd<true>, BWD_SMEM_DELTA, attr_delta) : ensure_dynamic_smem(k_network_fwdbwd<false>, BWD_SMEM, attr)) return -1;
 	if (n_rows == 0) return 0;
 	const uint32_t n_tiles = (n_rows + TILE - 1) / TILE;
 	uint32_t grid = (uint32_t)num_sms();
@@ -451,8 +503,12 @@ int launch_network_fwdbwd(cudaStream_t stream, const GridMeta& gm, const ParamLa
 	if (need < grid) grid = need;
 	static int dbg = -1;
 	if (dbg < 0) { const char* e = getenv("NEUS2_DBG"); dbg = e ? atoi(e) : 0; }
-	k_network_fwdbwd<<<grid, WARPS_BWD * 32, BWD_SMEM, stream>>>(gm, pl, params, coords, dL_dout, n_in_ptr, n_rows, sdf_bias,
-		(float)indeed_batch_size, grads, var_acc, w1row0_acc, so, dbg);
+	if (delta)
+		k_network_fwdbwd<true><<<grid, WARPS_BWD * 32, BWD_SMEM_DELTA, stream>>>(gm, pl, params, coords, dL_dout, n_in_ptr, n_rows, sdf_bias,
+			(float)indeed_batch_size, grads, var_acc, w1row0_acc, so, dbg, delta_acc);
+	else
+		k_network_fwdbwd<false><<<grid, WARPS_BWD * 32, BWD_SMEM, stream>>>(gm, pl, params, coords, dL_dout, n_in_ptr, n_rows, sdf_bias,
+			(float)indeed_batch_size, grads, var_acc, w1row0_acc, so, dbg, nullptr);
 	COUNT_LAUNCH(1);
 	CUDA_CHECK(cudaGetLastError());
 	return 0;

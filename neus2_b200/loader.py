@@ -290,6 +290,19 @@ def config_from_json(cfg_json):
     for src, dst in (("learning_rate", "learning_rate"), ("beta1", "beta1"), ("beta2", "beta2"), ("epsilon", "epsilon"), ("l2_reg", "l2_reg")):
         if src in opt:
             kw[dst] = float(opt[src])
+    # the DeltaNetwork's own trainer: config["globalmove"]["optimizer"], else the main optimizer config (testbed.cu:2320-2323)
+    gopt = cfg_json.get("globalmove", {}).get("optimizer", cfg_json.get("optimizer", {}))
+    while True:
+        if gopt.get("otype", "") == "ExponentialDecay":
+            kw["delta_decay_start"] = int(gopt.get("decay_start", 10000))
+            kw["delta_decay_interval"] = int(gopt.get("decay_interval", 10000))
+            kw["delta_decay_base"] = float(gopt.get("decay_base", 0.1))
+        if "nested" not in gopt:
+            break
+        gopt = gopt["nested"]
+    for src, dst in (("learning_rate", "delta_learning_rate"), ("beta1", "delta_beta1"), ("beta2", "delta_beta2"), ("epsilon", "delta_epsilon")):
+        if src in gopt:
+            kw[dst] = float(gopt[src])
     hp = cfg_json.get("hyperparams", {})
     for src, dst in (("mask_loss_weight", "mask_loss_weight"), ("ek_loss_weight", "ek_loss_weight")):
         if src in hp:

@@ -6,7 +6,8 @@ optimizers/ema.h:182-194, exponential_decay.h:128-140, adam.h:424-445): the netw
               base_learning_rate, first_moments_binary, second_moments_binary, param_steps_binary }, learning_rate,
               learning_rate_factor }, weights_ema_binary }, density_grid_size: 128, density_grid_binary (fp16),
               nerf: { aabb_scale, rgb: { rays_per_batch, measured_batch_size, measured_batch_size_before_compaction } },
-              training_step, loss, rotation, transition (fp16 global rigid motion: identity for static scenes) }
+              training_step, loss, rotation (12 halves), transition (4), local_rotation (8), local_transition (4): the accumulated
+              global rigid motion and the current DeltaNetwork (nerf_network.h:1180-1278) }
 
 Loading follows Trainer::deserialize: the fp16 blob becomes BOTH the training and the inference parameters and the fp32
 master copy is its widening (trainer.h:263-275).  Host logic only.
@@ -45,8 +46,14 @@ def save(ctx, path, network_config, include_optimizer_state=False, loss=0.0, aab
     snap["training_step"] = int(state["training_step"])
     snap["n_rays_total"] = int(state["n_rays_total"])                       # extension (image round-robin position)
     snap["loss"] = float(loss)
-    snap["rotation"] = np.array([1, 0, 0, 0, 1, 0], dtype=np.float16).tobytes()
-    snap["transition"] = np.zeros(3, dtype=np.float16).tobytes()
+    # save_global_movement / save_local_movement (nerf_network.h:1180-1247): the accumulated motion (12 halves: 3x3 row-major + pad;
+    # 4 halves) and the current DeltaNetwork (8 halves: 6d rotation + pad; 4 halves)
+    gm = ctx.global_movement()
+    snap["rotation"] = np.concatenate([gm["rotation"].reshape(9), np.zeros(3, np.float32)]).astype(np.float16).tobytes()
+    snap["transition"] = np.concatenate([gm["transition"], np.zeros(1, np.float32)]).astype(np.float16).tobytes()
+    snap["local_rotation"] = np.concatenate([gm["delta_rotation_6d"], np.zeros(2, np.float32)]).astype(np.float16).tobytes()
+    snap["local_transition"] = np.concatenate([gm["delta_transition"], np.zeros(1, np.float32)]).astype(np.float16).tobytes()
+    snap["use_delta"] = bool(gm["use_delta"])                               # extension: the reference re-derives it from the frame index
     out = dict(network_config)
     out["snapshot"] = snap
     with open(path, "wb") as f:
@@ -60,10 +67,16 @@ def restore(ctx, snap):
     p16 = np.frombuffer(snap["params_binary"], dtype=np.float16)
     if p16.size != ctx.n_params:
         raise RuntimeError("Can't set params because CPU buffer has the wrong size.")
-    rot = np.frombuffer(snap.get("rotation", np.array([1, 0, 0, 0, 1, 0], np.float16).tobytes()), dtype=np.float16)
-    tr = np.frombuffer(snap.get("transition", np.zeros(3, np.float16).tobytes()), dtype=np.float16)
-    if not (np.array_equal(rot[:6], np.array([1, 0, 0, 0, 1, 0], np.float16)) and not np.any(tr[:3])):
-        raise RuntimeError("snapshots with a non-identity global movement (dynamic scenes) are not built")
+    # load_global_movement / load_local_movement (nerf_network.h:1207-1278)
+    eye12 = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], np.float16)
+    rot = np.frombuffer(snap.get("rotation", eye12.tobytes()), dtype=np.float16).astype(np.float32)
+    if rot.size < 9:
+        rot = eye12.astype(np.float32)                                   # files of earlier builds stored a 6-value identity placeholder
+    tr = np.frombuffer(snap.get("transition", np.zeros(4, np.float16).tobytes()), dtype=np.float16).astype(np.float32)
+    lrot = np.frombuffer(snap.get("local_rotation", np.array([1, 0, 0, 0, 1, 0, 0, 0], np.float16).tobytes()), dtype=np.float16).astype(np.float32)
+    ltr = np.frombuffer(snap.get("local_transition", np.zeros(4, np.float16).tobytes()), dtype=np.float16).astype(np.float32)
+    ctx.set_global_movement(rotation=rot[:9], transition=tr[:3], delta_rotation_6d=lrot[:6], delta_transition=ltr[:3])
+    ctx.set_delta_mode(bool(snap.get("use_delta", False)))
     import torch
     ctx.set_params(p16.astype(np.float32), reset_optimizer=True)     # master = widened fp16, params = fp16, optimizer cleared
     master, params, ema, _ = ctx.buffers()

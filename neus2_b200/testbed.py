@@ -14,6 +14,15 @@ import numpy as np
 from . import Context, default_config, loader, snapshot as _snapshot, mesh as _mesh
 
 
+def _rotation_6d_to_matrix(r6):
+    """rotation_6d_to_matrix (common_operation.cuh:37-60): Gram-Schmidt of the two 3-vectors, columns b1, b2, b1 x b2."""
+    a1, a2 = np.asarray(r6[:3], np.float32), np.asarray(r6[3:6], np.float32)
+    b1 = a1 / np.linalg.norm(a1)
+    u2 = a2 - np.dot(b1, a2) * b1
+    b2 = u2 / np.linalg.norm(u2)
+    return np.stack([b1, b2, np.cross(b1, b2)], axis=1).astype(np.float32)
+
+
 class TestbedMode(enum.Enum):
     Nerf = 0
     Sdf = 1
@@ -63,6 +72,7 @@ class Testbed:
         self.next_frame_max_training_step = 2000
         self.predict_global_movement = False
         self.predict_global_movement_training_step = 50
+        self.finetune_global_movement = True
         self.after_learning_rate = 0.0
         self.current_training_time_frame = 0
         self.all_training_time_frame = 1
@@ -94,7 +104,10 @@ class Testbed:
         self.first_frame_max_training_step = int(hp.get("first_frame_max_training_step", self.first_frame_max_training_step))
         self.next_frame_max_training_step = int(hp.get("next_frame_max_training_step", self.next_frame_max_training_step))
         self.predict_global_movement = bool(hp.get("predict_global_movement", False))          # testbed.cu:2129
-        self.predict_global_movement_training_step = int(hp.get("predict_global_movement_training_step", 50))
+        self.predict_global_movement_training_step = int(hp.get("predict_global_movement_training_step", 300))   # :2130
+        if not self.predict_global_movement:
+            self.predict_global_movement_training_step = 0                                      # :2131-2133
+        self.finetune_global_movement = bool(hp.get("finetune_global_movement", True))          # :2125
         leaf = cfg_json.get("optimizer", {})
         while "nested" in leaf:
             leaf = leaf["nested"]
@@ -161,16 +174,18 @@ class Testbed:
         return True
 
     def training_network_next_frame(self):
-        """Testbed::training_network_next_frame (testbed.cu:2001-2082) for "predict_global_movement": false."""
+        """Testbed::training_network_next_frame (testbed.cu:2001-2082).  With "predict_global_movement" the delta trained on the
+        frame that just ended is folded into the accumulated rigid motion and a fresh DeltaNetwork (identity, own Adam) is trained
+        alone for predict_global_movement_training_step steps, then together with the canonical model (:2054, 2076-2078, 2659-2667)."""
         if self.current_training_time_frame >= self.all_training_time_frame - 1:
             return False                                              # "alread last frame"
-        if self.predict_global_movement:
-            raise RuntimeError("global movement prediction (DeltaNetwork / rotation-6d) is not built: set hyperparams.predict_global_movement to false")
         ctx = self._need_ctx()
         self.current_training_time_frame += 1
         self._data = loader.load_nerf(self._json_paths[self.current_training_time_frame])
         d = self._data
         ctx.set_dataset(d["pixels"], d["focal"], d["principal"], d["xforms"])
+        if self.predict_global_movement:
+            ctx.begin_global_movement()
         ctx.next_frame(after_learning_rate=self.after_learning_rate, frozen_steps=self.predict_global_movement_training_step)
         return True
 
@@ -184,6 +199,9 @@ class Testbed:
         ctx = self._need_ctx()
         if int(batch_size) != int(ctx.cfg.batch_size):
             raise RuntimeError(f"the context was created for batch_size {ctx.cfg.batch_size}")
+        if (self.predict_global_movement and not self.finetune_global_movement and self.current_training_time_frame >= 1
+                and self.training_step == self.predict_global_movement_training_step):
+            ctx.set_delta_mode(False)                                 # m_train_delta = false (:2659-2663): the delta leaves the network
         st = ctx.train_step()
         if st.measured_batch_size == 0:
             # train_nerf (testbed_nerf.cu:3540-3546): "Nerf training generated 0 samples. Aborting training."
@@ -242,7 +260,33 @@ class Testbed:
         res = [(int(r) + 15) // 16 * 16 for r in np.broadcast_to(np.asarray(resolution), (3,))]      # testbed_nerf.cu:4176-4178
         bb = (0, 0, 0, 1, 1, 1) if aabb is None else tuple(float(v) for v in np.asarray(aabb).reshape(-1))
         self._mesh = _mesh.extract(ctx, res, bb, float(thresh))
-        return {k: v.cpu().numpy() for k, v in self._mesh.items()}
+        out = {k: v.cpu().numpy() for k, v in self._mesh.items()}
+        gm = ctx.global_movement()
+        if not (np.array_equal(gm["rotation"], np.eye(3, dtype=np.float32)) and not gm["transition"].any()):
+            # transform_mesh_with_6d (testbed_nerf.cu:108-135, 4190-4196): v <- R_acc^-1 (v - t_acc), back into the frame's world space.
+            # (The reference shades the moved vertices; here normals / colours are taken at the extracted positions and the normals rotated.)
+            Rinv = np.linalg.inv(gm["rotation"].astype(np.float64))
+            out["V"] = ((out["V"].astype(np.float64) - gm["transition"].astype(np.float64)) @ Rinv.T).astype(np.float32)
+            out["N"] = (out["N"].astype(np.float64) @ Rinv.T).astype(np.float32)
+        return out
+
+    def save_transform(self, path):
+        """Testbed::save_transform (testbed.cu:3117-3142): the rigid motion a snapshot taken now would hold (delta o accumulated,
+        save_global_movement_rotation_6d_kernel, common_operation.cuh:582-617), as 3 rows of the rotation + the transition."""
+        R, t = self.global_transform()
+        with open(path, "w") as f:
+            for r in R:
+                f.write("%f %f %f\n" % tuple(float(v) for v in r))
+            f.write("%f %f %f\n\n" % tuple(float(v) for v in t))
+
+    def global_transform(self):
+        """(R [3,3], t [3]) = delta o accumulated: ray_canonical = R ray + t (positions additionally through the per-sample delta)."""
+        gm = self._need_ctx().global_movement()
+        Rd = _rotation_6d_to_matrix(gm["delta_rotation_6d"].astype(np.float16).astype(np.float32))
+        td = gm["delta_transition"].astype(np.float16).astype(np.float32)
+        R = (Rd @ gm["rotation"]).astype(np.float16).astype(np.float32)
+        t = (Rd @ (gm["transition"] + td)).astype(np.float16).astype(np.float32)
+        return R, t
 
     def compute_and_save_marching_cubes_mesh(self, filename, resolution=(256, 256, 256), aabb=None, thresh=0.0, generate_uvs_for_obj_file=False):
         """Testbed::compute_and_save_marching_cubes_mesh (testbed.cu:308-316): OBJ or PLY in DATASET coordinates."""

@@ -661,9 +661,12 @@ void orc_net_forward_debug(const NetCfg* c, uint32_t n, const float* coords, con
 // backward_impl (nerf_network.h:330-601), m_train_canonical=true, m_use_delta=false.
 // dL_dout [n][16] half.  grads: fp32 [n_params], OVERWRITTEN (EGradientMode::Overwrite at testbed_nerf.cu:3946).
 // indeed_batch_size: the eikonal normaliser (nerf_network.h:490-496; set at testbed_nerf.cu:3941).
-void orc_net_backward(const NetCfg* cp, uint32_t n, const float* coords, const h16* params, const h16* dL_dout,
-                      uint32_t indeed_batch_size, float* grads) {
-	const NetCfg& c = *cp;
+// dL_dpos (nullable, [n][3] fp32): the gradient that reaches the DeltaNetwork's output when m_train_delta && m_use_delta
+// (nerf_network.h:604-632): grid backward w.r.t. its input + colour-input xyz rows + sdf-MLP-input xyz rows; the second-order
+// d(normal)/d(position) term is NOT part of it in the reference.
+static void net_backward(const NetCfg& c, uint32_t n, const float* coords, const h16* params, const h16* dL_dout,
+                         uint32_t indeed_batch_size, float* grads, float* dL_dpos) {
+	const NetCfg* cp = &c;
 	const uint32_t E = n_enc(c), SI = sdf_in_w(c), RI = 48;
 	const size_t NP = orc_net_n_params(cp);
 	std::memset(grads, 0, NP * sizeof(float));
@@ -697,6 +700,14 @@ void orc_net_backward(const NetCfg* cp, uint32_t n, const float* coords, const h
 	std::vector<h16> dl_denc((size_t)E * n);
 	for (uint32_t i = 0; i < n; ++i) for (uint32_t k = 0; k < E; ++k) dl_denc[(size_t)k * n + i] = dL_dsdf_in[(size_t)i * SI + 3 + k];
 	orc_grid_backward(n, coords, 7, dl_denc.data(), c.n_levels, c.offsets, c.resolutions, c.scales, c.valid_level, g_grid);
+	if (dL_dpos) {
+		// :430-440 dL_dpos_encoding_input (kernel_grid_backward_input), then :607-626 the two add_positions_view<float, T>
+		orc_grid_backward_input(n, E, dl_denc.data(), ctx.dy_dx.data(), dL_dpos);
+		for (uint32_t i = 0; i < n; ++i) for (int d = 0; d < 3; ++d) {
+			dL_dpos[(size_t)i * 3 + d] += h2f(dL_drgb_in[(size_t)i * RI + 32 + d]);
+			dL_dpos[(size_t)i * 3 + d] += h2f(dL_dsdf_in[(size_t)i * SI + d]);
+		}
+	}
 
 	// :463-474 variance gradient: fp32 sum of row 7, rounded once to half (reduce_sum -> T)
 	{
@@ -728,6 +739,152 @@ void orc_net_backward(const NetCfg* cp, uint32_t n, const float* coords, const h
 	std::vector<h16> seed((size_t)n * 16, 0);
 	for (uint32_t i = 0; i < n; ++i) seed[(size_t)i * 16] = f2h(1.0f);
 	orc_mlp_bwdbwd(n, SI, c.sdf_hidden_layers, 16, p_sdf, ctx.sdf_hidden.data(), d_in.data(), seed.data(), g_sdf);
+}
+
+void orc_net_backward(const NetCfg* cp, uint32_t n, const float* coords, const h16* params, const h16* dL_dout,
+                      uint32_t indeed_batch_size, float* grads) {
+	net_backward(*cp, n, coords, params, dL_dout, indeed_batch_size, grads, nullptr);
+}
+
+// ----------------------------------------------------------------------------
+// DeltaNetwork: the per-frame rigid motion of dynamic scenes (include/neural-graphics-primitives/transform_network.h:23-480,
+// common_operation.cuh:37-160, 416-470, 551-580, 788-840).  Parameters (half, with an fp32 master in their own Trainer):
+// transition[4] (3 used) then rotation[8] (6 used, the "6d" representation: two 3-vectors, Gram-Schmidt -> columns of R).
+// ngp layer => parity unpinned; FMA contraction written the way nvcc fuses the Eigen expressions.
+// ----------------------------------------------------------------------------
+struct DeltaXform { float R[9]; float t[3]; float tmo[3]; float off[3]; };   // R row-major
+
+static inline float dot3(const float a[3], const float b[3]) { return fmaf(a[2], b[2], fmaf(a[1], b[1], a[0] * b[0])); }
+static inline void normalize3_(const float v[3], float out[3]) {   // Eigen normalized(): v / sqrt(squaredNorm) when > 0
+	float n2 = dot3(v, v);
+	float nn = sqrtf(n2);
+	if (n2 > 0) { out[0] = v[0] / nn; out[1] = v[1] / nn; out[2] = v[2] / nn; } else { out[0] = v[0]; out[1] = v[1]; out[2] = v[2]; }
+}
+// rotation_6d_to_matrix (common_operation.cuh:37-60); also returns the Gram-Schmidt intermediates the backward needs
+static inline void rotation_6d_basis(const h16* r6, float a1[3], float a2[3], float b1[3], float u2[3], float b2[3], float b3[3]) {
+	for (int k = 0; k < 3; ++k) { a1[k] = h2f(r6[k]); a2[k] = h2f(r6[3 + k]); }
+	normalize3_(a1, b1);
+	const float dd = dot3(b1, a2);
+	for (int k = 0; k < 3; ++k) u2[k] = fmaf(-dd, b1[k], a2[k]);
+	normalize3_(u2, b2);
+	b3[0] = fmaf(b1[1], b2[2], -(b1[2] * b2[1]));
+	b3[1] = fmaf(b1[2], b2[0], -(b1[0] * b2[2]));
+	b3[2] = fmaf(b1[0], b2[1], -(b1[1] * b2[0]));
+}
+static inline void delta_xform(const h16* rot6, const h16* trans, const float* off, DeltaXform& x) {
+	float a1[3], a2[3], b1[3], u2[3], b2[3], b3[3];
+	rotation_6d_basis(rot6, a1, a2, b1, u2, b2, b3);
+	for (int k = 0; k < 3; ++k) {
+		x.R[k * 3 + 0] = b1[k]; x.R[k * 3 + 1] = b2[k]; x.R[k * 3 + 2] = b3[k];
+		x.t[k] = h2f(trans[k]);
+		x.off[k] = off ? off[k] : 0.f;
+		x.tmo[k] = x.t[k] - x.off[k];
+	}
+}
+static inline void matvec3(const float R[9], const float v[3], float out[3]) {
+	for (int k = 0; k < 3; ++k) out[k] = fmaf(R[k * 3 + 2], v[2], fmaf(R[k * 3 + 1], v[1], R[k * 3] * v[0]));
+}
+// add_global_movement_with_rotation_6d (common_operation.cuh:416-470): pos' = R (pos + t - off) + off; the direction is stored
+// warped ((d+1)/2), un-warped, rotated, warped again.
+static inline void delta_apply(const DeltaXform& x, const float* in /*[7]*/, float* out /*[7]*/) {
+	float q[3], r[3];
+	for (int k = 0; k < 3; ++k) q[k] = in[k] + x.tmo[k];
+	matvec3(x.R, q, r);
+	for (int k = 0; k < 3; ++k) out[k] = r[k] + x.off[k];
+	out[3] = in[3];
+	float u[3];
+	for (int k = 0; k < 3; ++k) u[k] = fmaf(in[4 + k], 2.0f, -1.0f);
+	matvec3(x.R, u, r);
+	for (int k = 0; k < 3; ++k) out[4 + k] = (r[k] + 1.0f) * 0.5f;
+}
+void orc_delta_matrix(const h16* rot6, const h16* trans, float* R9, float* t3) {
+	DeltaXform x; delta_xform(rot6, trans, nullptr, x);
+	std::memcpy(R9, x.R, sizeof(x.R)); std::memcpy(t3, x.t, sizeof(x.t));
+}
+void orc_delta_apply(uint32_t n, const float* coords_in, const h16* rot6, const h16* trans, const float* off, float* coords_out) {
+	DeltaXform x; delta_xform(rot6, trans, off, x);
+	for (uint32_t i = 0; i < n; ++i) delta_apply(x, coords_in + (size_t)i * 7, coords_out + (size_t)i * 7);
+}
+
+// gradients_for_normalize (common_operation.cuh:62-90)
+static inline void grad_normalize(const float in[3], const float go[3], float gi[3]) {
+	const float nrm = sqrtf(dot3(in, in));
+	const float n3 = nrm * nrm * nrm;
+	const float xx = fmaf(in[2], in[2], in[1] * in[1]) / n3, yy = fmaf(in[2], in[2], in[0] * in[0]) / n3, zz = fmaf(in[1], in[1], in[0] * in[0]) / n3;
+	const float xy = -in[0] * in[1] / n3, xz = -in[0] * in[2] / n3, yz = -in[1] * in[2] / n3;
+	gi[0] = fmaf(go[2], xz, fmaf(go[1], xy, go[0] * xx));
+	gi[1] = fmaf(go[2], yz, fmaf(go[1], yy, go[0] * xy));
+	gi[2] = fmaf(go[2], zz, fmaf(go[1], yz, go[0] * xz));
+}
+// One sample of add_loss_to_rotation_6d_each<T = half, TIn = float> (common_operation.cuh:788-840) with
+// gradient_rotation_matrix_to_6d<half> (:92-150): out[0..2] = d/d transition, out[3..8] = d/d rotation-6d, each rounded to half.
+// L = dL/d(deformed position), xin = the un-deformed position.  The d_b1 / d_b2 accumulators are HALF in the reference (T d_b1_x ...).
+static inline void delta_backward_sample(const h16* rot6, const DeltaXform& x, const float L[3], const float xin[3], float out[9]) {
+	float a1[3], a2[3], b1[3], u2[3], b2[3], b3[3];
+	rotation_6d_basis(rot6, a1, a2, b1, u2, b2, b3);
+	float iv[3];
+	for (int k = 0; k < 3; ++k) iv[k] = xin[k] + x.t[k];
+	// R^-1 L (R orthonormal: inverse == transpose up to rounding)
+	for (int j = 0; j < 3; ++j) out[j] = rh(fmaf(x.R[6 + j], L[2], fmaf(x.R[3 + j], L[1], x.R[j] * L[0])));
+	float G[3][3];
+	for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) G[a][b] = L[a] * iv[b];
+	float db1[3], db2[3];
+	for (int k = 0; k < 3; ++k) { db1[k] = rh(G[k][0]); db2[k] = rh(G[k][1]); }
+	db1[0] = rh(db1[0] + rh(fmaf(b2[1], G[2][2], -(b2[2] * G[1][2]))));
+	db1[1] = rh(db1[1] + rh(fmaf(b2[2], G[0][2], -(b2[0] * G[2][2]))));
+	db1[2] = rh(db1[2] + rh(fmaf(b2[0], G[1][2], -(b2[1] * G[0][2]))));
+	db2[0] = rh(db2[0] + rh(fmaf(b1[2], G[1][2], -(b1[1] * G[2][2]))));
+	db2[1] = rh(db2[1] + rh(fmaf(b1[0], G[2][2], -(b1[2] * G[0][2]))));
+	db2[2] = rh(db2[2] + rh(fmaf(b1[1], G[0][2], -(b1[0] * G[1][2]))));
+	float r[3];
+	grad_normalize(u2, db2, r);   // d_b2_remove_normalized
+	float da2[3];
+	for (int k = 0; k < 3; ++k) da2[k] = r[k] - b1[k] * dot3(r, b1);              // (I - b1 b1^T) r
+	const float ba = dot3(b1, a2);
+	float db1f[3];
+	for (int k = 0; k < 3; ++k) db1f[k] = db1[k] - r[k] * ba - a2[k] * dot3(r, b1);   // d(-(b1.a2) b1)/d b1 applied to r
+	float da1[3];
+	grad_normalize(a1, db1f, da1);
+	for (int k = 0; k < 3; ++k) { out[3 + k] = rh(da1[k]); out[6 + k] = rh(da2[k]); }
+}
+// DeltaNetwork::backward_impl (transform_network.h:110-250): per-sample gradients in half, tcnn::reduce_sum (fp32) over the
+// batch, the sum rounded once to half.  grad[12] = [transition 3 | 0 | rotation-6d 6 | 0 0] as (float)half.
+void orc_delta_backward(uint32_t n, const float* coords_in, const float* dL_dpos, const h16* rot6, const h16* trans,
+                        const float* off, float* grad) {
+	DeltaXform x; delta_xform(rot6, trans, off, x);
+	double acc[9] = {0};
+	for (uint32_t i = 0; i < n; ++i) {
+		float o[9];
+		delta_backward_sample(rot6, x, dL_dpos + (size_t)i * 3, coords_in + (size_t)i * 7, o);
+		for (int k = 0; k < 9; ++k) acc[k] += o[k];
+	}
+	for (int k = 0; k < 12; ++k) grad[k] = 0.f;
+	for (int k = 0; k < 3; ++k) grad[k] = rh((float)acc[k]);
+	for (int k = 0; k < 6; ++k) grad[4 + k] = rh((float)acc[3 + k]);
+}
+// backward_impl with m_use_delta && m_train_delta: the network runs on the deformed coordinates.
+void orc_net_backward_delta(const NetCfg* cp, uint32_t n, const float* coords, const h16* params, const h16* dL_dout,
+                            uint32_t indeed_batch_size, const h16* rot6, const h16* trans, const float* off,
+                            float* grads, float* delta_grad /*[12]*/, float* dL_dpos_out /*nullable [n][3]*/) {
+	std::vector<float> deformed((size_t)n * 7), dpos((size_t)n * 3);
+	orc_delta_apply(n, coords, rot6, trans, off, deformed.data());
+	net_backward(*cp, n, deformed.data(), params, dL_dout, indeed_batch_size, grads, dpos.data());
+	orc_delta_backward(n, coords, dpos.data(), rot6, trans, off, delta_grad);
+	if (dL_dpos_out) std::memcpy(dL_dpos_out, dpos.data(), dpos.size() * sizeof(float));
+}
+// accumulate_global_movement_rotation_6d_kernel (common_operation.cuh:551-580): R_acc <- R_delta R_acc,
+// t_acc <- R_delta (t_acc + t_delta); both stored in half (9 of 12 / 3 of 4 slots used).
+void orc_accumulate_global_movement(const h16* rot6, const h16* trans, h16* acc_rot /*[9]*/, h16* acc_trans /*[3]*/) {
+	DeltaXform x; delta_xform(rot6, trans, nullptr, x);
+	float before[9], after[9];
+	for (int k = 0; k < 9; ++k) before[k] = h2f(acc_rot[k]);
+	for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j)
+		after[i * 3 + j] = fmaf(x.R[i * 3 + 2], before[6 + j], fmaf(x.R[i * 3 + 1], before[3 + j], x.R[i * 3] * before[j]));
+	for (int k = 0; k < 9; ++k) acc_rot[k] = f2h(after[k]);
+	float s[3], r[3];
+	for (int k = 0; k < 3; ++k) s[k] = h2f(acc_trans[k]) + x.t[k];
+	matvec3(x.R, s, r);
+	for (int k = 0; k < 3; ++k) acc_trans[k] = f2h(r[k]);
 }
 
 // sdf() and density() (nerf_network.h:656-739; common_operation.cuh:293-324).  pos: [n][stride] floats.

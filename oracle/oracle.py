@@ -286,6 +286,60 @@ def net_backward(cfg, coords, params_h, dL_dout_h, indeed_batch_size):
     return grads
 
 
+def _h(a):
+    """float array -> the half bit patterns the reference stores (uint16)."""
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float32).astype(np.float16).view(np.uint16))
+
+
+def delta_matrix(rot6, trans):
+    """rotation_6d_to_matrix + the transition as floats: (R [3][3] row-major, t [3])."""
+    R = np.zeros(9, dtype=np.float32); t = np.zeros(3, dtype=np.float32)
+    lib().orc_delta_matrix(_p(_h(rot6), h16p), _p(_h(trans), h16p), _p(R, f32p), _p(t, f32p))
+    return R.reshape(3, 3), t
+
+
+def delta_apply(coords, rot6, trans, first_frame_offset=None):
+    """DeltaNetwork forward on [n][7] coordinates (position, dt, warped direction)."""
+    coords = np.ascontiguousarray(coords, dtype=np.float32)
+    out = np.zeros_like(coords)
+    off = None if first_frame_offset is None else np.ascontiguousarray(first_frame_offset, dtype=np.float32)
+    lib().orc_delta_apply(C.c_uint32(coords.shape[0]), _p(coords, f32p), _p(_h(rot6), h16p), _p(_h(trans), h16p),
+                          _p(off, f32p) if off is not None else None, _p(out, f32p))
+    return out
+
+
+def delta_backward(coords, dL_dpos, rot6, trans, first_frame_offset=None):
+    """DeltaNetwork backward: grad[12] = [d transition 3 | 0 | d rotation-6d 6 | 0 0] as (float)half."""
+    coords = np.ascontiguousarray(coords, dtype=np.float32)
+    dL_dpos = np.ascontiguousarray(dL_dpos, dtype=np.float32)
+    off = None if first_frame_offset is None else np.ascontiguousarray(first_frame_offset, dtype=np.float32)
+    grad = np.zeros(12, dtype=np.float32)
+    lib().orc_delta_backward(C.c_uint32(coords.shape[0]), _p(coords, f32p), _p(dL_dpos, f32p), _p(_h(rot6), h16p), _p(_h(trans), h16p),
+                             _p(off, f32p) if off is not None else None, _p(grad, f32p))
+    return grad
+
+
+def net_backward_delta(cfg, coords, params_h, dL_dout_h, indeed_batch_size, rot6, trans, first_frame_offset=None):
+    """backward_impl with m_use_delta && m_train_delta: (canonical grads, delta grad[12], dL/d deformed position [n][3])."""
+    n = coords.shape[0]
+    coords = np.ascontiguousarray(coords, dtype=np.float32)
+    grads = np.zeros(net_n_params(cfg), dtype=np.float32)
+    dgrad = np.zeros(12, dtype=np.float32)
+    dpos = np.zeros((n, 3), dtype=np.float32)
+    off = None if first_frame_offset is None else np.ascontiguousarray(first_frame_offset, dtype=np.float32)
+    lib().orc_net_backward_delta(C.byref(cfg), C.c_uint32(n), _p(coords, f32p), _p(params_h, h16p), _p(dL_dout_h, h16p),
+                                 C.c_uint32(indeed_batch_size), _p(_h(rot6), h16p), _p(_h(trans), h16p),
+                                 _p(off, f32p) if off is not None else None, _p(grads, f32p), _p(dgrad, f32p), _p(dpos, f32p))
+    return grads, dgrad, dpos
+
+
+def accumulate_global_movement(rot6, trans, acc_rot, acc_trans):
+    """accumulated <- delta o accumulated; returns (R [3][3], t [3]) as the floats of the stored halves."""
+    r = _h(np.asarray(acc_rot, dtype=np.float32).reshape(9)); t = _h(acc_trans)
+    lib().orc_accumulate_global_movement(_p(_h(rot6), h16p), _p(_h(trans), h16p), _p(r, h16p), _p(t, h16p))
+    return r.view(np.float16).astype(np.float32).reshape(3, 3), t.view(np.float16).astype(np.float32)
+
+
 def net_sdf(cfg, pos, params_h, as_density=False):
     n = pos.shape[0]
     out = np.zeros(n, dtype=np.uint16)

@@ -42,8 +42,16 @@ def _worker(rank, world, port, out_dir, mode, steps):
     dist.barrier()
     master, params, ema, _ = ctx.buffers()
     lo, hi = ctx.optimizer_shard(rank, world)
-    np.savez(os.path.join(out_dir, f"{mode}_r{rank}.npz"), params=params.cpu().numpy().view(np.uint16), ema=ema.cpu().numpy().view(np.uint16),
-             master_shard=master[lo:hi].cpu().numpy(), shard=np.array([lo, hi]), stats=np.array(stats, dtype=np.int64))
+    saved = dict(params=params.cpu().numpy().view(np.uint16), ema=ema.cpu().numpy().view(np.uint16),
+                 master_shard=master[lo:hi].cpu().numpy(), shard=np.array([lo, hi]), stats=np.array(stats, dtype=np.int64))
+    # global-movement mode: every rank back-propagates its rows into its own 9 delta-gradient sums; they are all-reduced (48 bytes)
+    # and each rank steps its replica of the DeltaNetwork's parameters
+    ctx.begin_global_movement()
+    for _ in range(6):
+        parallel.train_step(ctx, rank, world)
+    gm = ctx.global_movement()
+    saved["delta"] = np.concatenate([gm["delta_transition"], gm["delta_rotation_6d"]])
+    np.savez(os.path.join(out_dir, f"{mode}_r{rank}.npz"), **saved)
     dist.barrier()
     ctx.close()
     dist.destroy_process_group()
@@ -98,3 +106,12 @@ def test_shards_partition_the_parameters(runs):
     for r, s in enumerate(shards):
         m = runs[f"p2p_r{r}"]["master_shard"]
         assert np.array_equal(m.astype(np.float16).view(np.uint16), runs["p2p_r0"]["params"][s[0]:s[1]])
+
+
+def test_delta_network_replicas_agree(runs):
+    for m in ("nccl", "p2p"):
+        d0 = runs[f"{m}_r0"]["delta"]
+        assert np.abs(d0 - np.array([0, 0, 0, 1, 0, 0, 0, 1, 0])).max() > 1e-5        # it moved
+        for r in range(1, runs["world"]):
+            assert np.array_equal(d0.view(np.uint32), runs[f"{m}_r{r}"]["delta"].view(np.uint32)), (m, r)
+    assert np.abs(runs["nccl_r0"]["delta"] - runs["p2p_r0"]["delta"]).max() < 2e-4    # 6 Adam steps of 1e-4: same direction on both paths

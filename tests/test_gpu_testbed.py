@@ -129,14 +129,13 @@ def test_errors_mirror_the_reference(tmp_path):
 
 def test_sequence_incremental_training(tmp_path):
     """A directory of jsons is a sequence (one json per time frame).  With "predict_global_movement": false the next frame
-    continues from the inference weights with a fresh optimizer; the parameters stay frozen for the first 50 steps
-    (testbed.cu:2659-2667), then fine-tune to the moved object."""
+    continues from the inference weights with a fresh optimizer and trains from its first step
+    (m_predict_global_movement_training_step = 0, testbed.cu:2131-2133)."""
     import sys
     import torch
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
     import run_per_frame
     from neus2_b200.testbed import Testbed, TestbedMode
-    from neus2_b200 import synthetic
     run_per_frame.write_synthetic_sequence(str(tmp_path), 2, views=8, res=96)
     tb = Testbed(TestbedMode.Nerf)
     tb.load_training_data(str(tmp_path))
@@ -145,18 +144,18 @@ def test_sequence_incremental_training(tmp_path):
            "hyperparams": {"first_frame_max_training_step": 400, "next_frame_max_training_step": 300, "predict_global_movement": False,
                            "predict_global_movement_training_step": 50}}
     tb.reload_network_from_json(cfg)
+    assert tb.predict_global_movement_training_step == 0
     while not (tb.current_training_time_frame == 0 and tb.training_step == 400):
         tb.frame()
     ema0 = tb._ctx.buffers()[2].clone()
-    tb.frame()                                           # switches to frame 1 and takes its first (frozen) step
-    assert tb.current_training_time_frame == 1 and tb.training_step == 1
+    st = tb._ctx.get_state()
+    tb.training_network_next_frame()
+    assert tb.current_training_time_frame == 1 and tb.training_step == 0
     assert tb._ctx.time_frame() == (1, pytest.approx(5e-4))
-    assert torch.equal(tb._ctx.buffers()[1], ema0)       # training weights = previous inference weights, untouched by the frozen step
-    for _ in range(48):
-        tb.frame()
-    assert tb.training_step == 49 and torch.equal(tb._ctx.buffers()[1], ema0)
-    tb.frame(); tb.frame()
-    assert not torch.equal(tb._ctx.buffers()[1], ema0)   # step 50 onwards trains
+    assert torch.equal(tb._ctx.buffers()[1], ema0)       # training weights = previous inference weights
+    assert not tb._ctx.global_movement()["use_delta"]
+    tb.frame()
+    assert tb.training_step == 1 and not torch.equal(tb._ctx.buffers()[1], ema0)   # no frozen phase without global-movement prediction
     while tb.training_step < 300:
         tb.frame()
     tb.frame()
@@ -165,7 +164,4 @@ def test_sequence_incremental_training(tmp_path):
     m = tb.compute_marching_cubes_mesh([96, 96, 96])
     big = np.linalg.norm(m["V"] - np.array([0.51, 0.5, 0.5]), axis=1)
     assert np.median(np.abs(big[big < 0.3] - 0.25)) < 4e-3
-    tb.predict_global_movement = True
-    tb.current_training_time_frame = 0
-    with pytest.raises(RuntimeError):
-        tb.training_network_next_frame()
+    assert tb.training_network_next_frame() is False     # "alread last frame"

@@ -26,7 +26,16 @@ def test_config_json_with_comments():
     kw = loader.config_from_json(js)
     assert kw == {"n_levels": 14, "log2_hashmap_size": 19, "base_resolution": 16, "valid_level_scale": 0.02, "base_valid_level_scale": 0.2,
                   "base_training_step": 100, "top_resolution": 2048.0, "ema_decay": 0.95, "learning_rate": 1e-3, "beta1": 0.9, "beta2": 0.99,
-                  "epsilon": 1e-15, "l2_reg": 1e-6, "mask_loss_weight": 0.0, "ek_loss_weight": 0.01}
+                  "epsilon": 1e-15, "l2_reg": 1e-6, "mask_loss_weight": 0.0, "ek_loss_weight": 0.01,
+                  # no "globalmove" section: the DeltaNetwork's trainer is built from the main optimizer config (testbed.cu:2320-2323)
+                  "delta_decay_start": 20000, "delta_decay_interval": 10000, "delta_decay_base": 0.1,
+                  "delta_learning_rate": 1e-3, "delta_beta1": 0.9, "delta_beta2": 0.99, "delta_epsilon": 1e-15}
+    gm = json.loads(loader._strip_json_comments(BASE_JSON))
+    gm["globalmove"] = {"optimizer": {"otype": "Ema", "decay": 0.95, "nested": {"otype": "ExponentialDecay", "decay_start": 50, "decay_interval": 25,
+                        "decay_base": 0.99, "nested": {"otype": "Adam", "learning_rate": 1e-4, "beta1": 0.9, "beta2": 0.99, "epsilon": 1e-10}}}}
+    kw = loader.config_from_json(gm)
+    assert (kw["delta_learning_rate"], kw["delta_epsilon"], kw["delta_decay_start"], kw["delta_decay_interval"], kw["delta_decay_base"]) == (1e-4, 1e-10, 50, 25, 0.99)
+    assert kw["learning_rate"] == 1e-3
     bad = json.loads(loader._strip_json_comments(BASE_JSON))
     bad["network"]["n_neurons"] = 128
     with pytest.raises(RuntimeError):
