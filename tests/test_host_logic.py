@@ -129,3 +129,21 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     import pytest
     with pytest.raises(_lib.Neus2Error):
         _lib.load()
+
+
+def test_testbed_global_movement_hyperparams():
+    """hyperparams of the dynamic-scene schedule as Testbed::reload_network reads them (src/testbed.cu:2118-2139); host logic, no GPU."""
+    from neus2_b200.testbed import Testbed, TestbedMode, _rotation_6d_to_matrix
+    from oracle import oracle as O
+    tb = Testbed(TestbedMode.Nerf)
+    tb.reload_network_from_json({"hyperparams": {"predict_global_movement": True}})
+    assert tb.predict_global_movement and tb.predict_global_movement_training_step == 300 and tb.finetune_global_movement      # code defaults
+    tb.reload_network_from_json({"hyperparams": {"predict_global_movement": True, "predict_global_movement_training_step": 50,
+                                                 "finetune_global_movement": False, "next_frame_max_training_step": 1300}})
+    assert tb.predict_global_movement_training_step == 50 and not tb.finetune_global_movement and tb.next_frame_max_training_step == 1300
+    tb.reload_network_from_json({"hyperparams": {"predict_global_movement": False, "predict_global_movement_training_step": 50}})
+    assert tb.predict_global_movement_training_step == 0                       # :2131-2133: no frozen phase without prediction
+    # the host-side 6d -> matrix used by save_transform agrees with the oracle's
+    r6 = np.array([1.0, 0.03, -0.02, 0.01, 0.98, 0.05], np.float32).astype(np.float16).astype(np.float32)
+    R, _ = O.delta_matrix(r6, [0, 0, 0])
+    assert np.abs(_rotation_6d_to_matrix(r6) - R).max() < 2e-7
