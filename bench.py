@@ -37,6 +37,7 @@ def parse():
     ap.add_argument("--width", type=int, default=1600)
     ap.add_argument("--height", type=int, default=1200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-prefetch", action="store_true", help="A/B: the reference's in-order step (config.prefetch_next_samples = 0) instead of the pipelined one")
     ap.add_argument("--global-movement", action="store_true", help="secondary measurement: time the step of frames >= 1 of a dynamic sequence (DeltaNetwork in the network kernels, delta gradients, global-move Adam)")
     ap.add_argument("--dp", default="p2p", choices=["p2p", "nccl"], help="N>1: optimizer fused with the gradient reduction over NVLink peer memory (p2p) or NCCL all-reduce + replicated Adam")
     return ap.parse_args()
@@ -225,6 +226,7 @@ def workload_config(args, n_gpus):
         "l2_policy": "per-step working set (>=470 MB of sample/activation buffers) exceeds the 126 MB L2; no explicit flush",
         "preroll_steps": args.preroll,
         **({"global_movement": "DeltaNetwork on (frames >= 1 of a dynamic sequence)"} if args.global_movement else {}),
+        "step_order": "in-order (prefetch_next_samples=0)" if args.no_prefetch else "pipelined: the next step's sample generation overlaps this step's backward tail, weight gradients and optimizer; no host sync at the end of a step",
     }
 
 
@@ -250,7 +252,7 @@ def main():
 
     data = make_data(args)
     B = (1 << 18) * world                      # weak scaling: every GPU back-propagates 2^18 samples per step
-    cfg = N.default_config(batch_size=B, world_size=world, max_rays_per_batch=(1 << 18) * world)
+    cfg = N.default_config(batch_size=B, world_size=world, max_rays_per_batch=(1 << 18) * world, prefetch_next_samples=0 if args.no_prefetch else 1)
     ctx = N.Context(cfg, device=local_rank)
     ctx.init_params()
     # pinned host copy of the dataset: the upload is part of the end-to-end number
@@ -314,6 +316,10 @@ def main():
     if rank == 0:
         K = args.steps
         value = rays / (ms * 1e-3)
+        # a number taken on a mis-sized batch is invalid: rays_per_batch is adapted so that the compacted batch tracks 2^18 samples per GPU
+        fill = (n_c / K) / B
+        if not 0.96 < fill < 1.04:
+            raise SystemExit(f"bench invalid: compacted batch is {fill:.2f} of its target over the timed steps")
         # end to end through the public API (Context.train_step): wall clock of the K steps incl. the per-step device->host
         # read of the counters/loss, plus the host->device upload of the training images from pinned memory, amortised over
         # the 2000-step schedule the metric is defined on.
@@ -353,7 +359,7 @@ def main():
                          "traffic": 422.4e6, "traffic_source": "profiles/r01_captureB.md: dram__bytes_read 111.6 MB + dram__bytes_write 310.8 MB per launch (ncu --set full)",
                          "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes, "avg_launch_ms": dom_ms, "l2": l2},
             "stage_ms": {k: round(v[0], 4) for k, v in stages.items()},
-            "per_step": {"rays": rays / K, "samples_before_compaction": n_u / K, "samples_compacted": n_c / K, "training_step": int(st.training_step),
+            "per_step": {"rays": rays / K, "samples_before_compaction": n_u / K, "samples_compacted": n_c / K, "batch_fill": fill, "training_step": int(st.training_step),
                          "first_pass_samples_evaluated_last_step": int(st.first_pass_samples)},
         }
         if not args.no_cpu_baseline:

@@ -60,6 +60,13 @@ typedef struct neus2_config {
 	/* 1 (default): the step's first network pass stops along each ray where the loss stops reading (T < 1e-4, testbed_nerf.cu:1567);
 	 * 0: evaluate every marched sample like the reference.  Same loss, gradients and counters either way (tests/test_gpu_step.py). */
 	int32_t forward_early_termination;
+	/* 1 (default, single-GPU contexts): pipelined step.  The step's only host read-back (the sample counts, final after the loss kernel)
+	 * is taken BEFORE the backward pass is queued; while the GPU runs backward pass + optimizer the host computes the next step's
+	 * rays_per_batch and enqueues its sample generation on a second stream behind the fused forward+backward kernel, so it overlaps the
+	 * weight-gradient GEMMs and Adam, and the GPU never waits for the host between steps.  Same arithmetic, same order of random
+	 * numbers, same results (tests/test_gpu_step.py); the sample buffers then hold the NEXT step's rays after a step returns.
+	 * 0: the reference's order (generate, forward, loss, backward, optimizer, read back). */
+	int32_t prefetch_next_samples;
 	/* "globalmove" optimizer (configs/nerf/base.json:135-158: Ema{ExponentialDecay{Adam}}) of the DeltaNetwork's own trainer
 	 * (src/testbed.cu:2320-2328).  The Ema wrapper's inference copy has no consumer (the network always reads params()), so it is not kept. */
 	float delta_learning_rate;       /* 1e-4 */
@@ -81,6 +88,7 @@ typedef struct neus2_step_stats {
 	int32_t loss_valid;
 	int32_t density_grid_updated;
 	uint32_t first_pass_samples;         /* samples this rank's first network pass evaluated (<= N_u with forward_early_termination) */
+	int32_t samples_prefetched;          /* 1: this step's samples had been generated during the previous step (prefetch_next_samples) */
 } neus2_step_stats;
 
 const char* neus2_last_error(void);
@@ -140,6 +148,10 @@ int neus2_train_step_begin(neus2_ctx* ctx, void* stream, uint32_t rank, uint32_t
  * neus2_counts_device (begin() leaves this rank's counts there; a data-parallel caller all-reduces the 4 x uint32 in place,
  * stream-ordered, between begin and end -- no host round trip; with world_size 1 they are simply the local counts). */
 int neus2_train_step_end(neus2_ctx* ctx, void* stream, const uint32_t* counts_global_host, neus2_step_stats* stats);
+/* Data-parallel pipelining (config.prefetch_next_samples): call after the all-reduce of neus2_counts_device() has been enqueued on
+ * `stream`.  Takes the step's host read-back there (ahead of the optimizer and its collectives); neus2_train_step_end then does not
+ * synchronise at the end of the step and generates the next step's samples on a second stream beside the optimizer. */
+int neus2_train_step_counts_ready(neus2_ctx* ctx, void* stream);
 int neus2_local_counts(neus2_ctx* ctx, void* stream, uint32_t counts_host[3]);
 int neus2_counts_device(neus2_ctx* ctx, uint32_t** counts_dev);
 /* convenience: begin + end on one GPU */

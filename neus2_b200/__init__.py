@@ -67,7 +67,8 @@ class Context:
 
     def close(self):
         if getattr(self, "_h", None):
-            self._buffers = self._counts = None
+            self._buffers = None
+            self.__dict__.pop("_counts_views", None)
             self._lib.neus2_ctx_destroy(self._h)
             self._h = None
 
@@ -181,11 +182,12 @@ class Context:
 
     def counts_device(self):
         """int32[4] device view of {kept rays, samples, compacted samples, 0} of the step in flight (all-reduce it in place)."""
-        if getattr(self, "_counts", None) is None:
-            p = C.c_void_p()
-            check(self._lib.neus2_counts_device(self._h, C.byref(p)))
-            self._counts = _torch().as_tensor(_DevArray(p.value, (4,), "<i4", None), device=f"cuda:{self.device}")
-        return self._counts
+        p = C.c_void_p()
+        check(self._lib.neus2_counts_device(self._h, C.byref(p)))     # the counters ping-pong between two buffers (pipelined step)
+        views = self.__dict__.setdefault("_counts_views", {})
+        if p.value not in views:
+            views[p.value] = _torch().as_tensor(_DevArray(p.value, (4,), "<i4", None), device=f"cuda:{self.device}")
+        return views[p.value]
 
     # ---- data-parallel peers (fused gradient reduction + Adam over NVLink peer memory) ------------------------------------
     def ipc_export(self):
@@ -208,6 +210,10 @@ class Context:
 
     def optimizer_step_sharded(self, loss_scale=128.0, stream=None):
         check(self._lib.neus2_optimizer_step_sharded(self._h, _stream(stream), C.c_float(loss_scale)))
+
+    def train_step_counts_ready(self, stream=None):
+        """Data-parallel: the all-reduce of counts_device() is enqueued; take the step's host read-back here (pipelined step)."""
+        check(self._lib.neus2_train_step_counts_ready(self._h, _stream(stream)))
 
     def train_step_end(self, counts_global=None, stream=None):
         st = StepStats()

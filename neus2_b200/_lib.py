@@ -25,7 +25,7 @@ class Config(C.Structure):
         ("batch_size", C.c_uint32),
         ("aabb_scale", C.c_int32), ("seed", C.c_uint32), ("random_bg_color", C.c_int32), ("snap_to_pixel_centers", C.c_int32),
         ("background_color", C.c_float * 3), ("density_grid_decay", C.c_float), ("loss_scale", C.c_float),
-        ("world_size", C.c_uint32), ("max_rays_per_batch", C.c_uint32), ("forward_early_termination", C.c_int32),
+        ("world_size", C.c_uint32), ("max_rays_per_batch", C.c_uint32), ("forward_early_termination", C.c_int32), ("prefetch_next_samples", C.c_int32),
         ("delta_learning_rate", C.c_float), ("delta_beta1", C.c_float), ("delta_beta2", C.c_float), ("delta_epsilon", C.c_float),
         ("delta_decay_start", C.c_uint32), ("delta_decay_interval", C.c_uint32), ("delta_decay_base", C.c_float),
     ]
@@ -36,7 +36,7 @@ class StepStats(C.Structure):
         ("training_step", C.c_uint32), ("rays_per_batch", C.c_uint32), ("rays_per_batch_next", C.c_uint32),
         ("n_rays_kept", C.c_uint32), ("measured_batch_size_before_compaction", C.c_uint32), ("measured_batch_size", C.c_uint32),
         ("loss", C.c_float), ("ek_loss", C.c_float), ("mask_loss", C.c_float), ("loss_valid", C.c_int32),
-        ("density_grid_updated", C.c_int32), ("first_pass_samples", C.c_uint32),
+        ("density_grid_updated", C.c_int32), ("first_pass_samples", C.c_uint32), ("samples_prefetched", C.c_int32),
     ]
 
 
@@ -59,7 +59,7 @@ EXPORTS = [
     "neus2_default_render_params", "neus2_render", "neus2_render_stats", "neus2_sdf_lattice", "neus2_marching_cubes", "neus2_mesh_buffers", "neus2_counts_device",
     "neus2_ipc_export", "neus2_ipc_attach", "neus2_optimizer_shard", "neus2_optimizer_step_sharded",
     "neus2_optimizer_buffers", "neus2_set_optimizer_step", "neus2_set_density_grid", "neus2_mesh_attributes", "neus2_get_counters", "neus2_next_frame", "neus2_get_time_frame",
-    "neus2_begin_global_movement", "neus2_set_delta_mode", "neus2_get_global_movement", "neus2_set_global_movement", "neus2_delta_gradients_device",
+    "neus2_train_step_counts_ready", "neus2_begin_global_movement", "neus2_set_delta_mode", "neus2_get_global_movement", "neus2_set_global_movement", "neus2_delta_gradients_device",
 ]
 
 _lib = None

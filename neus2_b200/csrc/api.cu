@@ -83,10 +83,24 @@ struct neus2_ctx {
 	bool step_density_updated;
 	uint32_t* h_counters;       // pinned
 	int profiling;              // record CUDA events around the stages of a step
-	cudaEvent_t ev[2 * NEUS2_N_STAGES];
+	cudaEvent_t ev[2][2 * NEUS2_N_STAGES];   // two sets, alternating per step: a set is read back one step later, without a sync
+	int ev_set;
 	float stage_ms_sum[NEUS2_N_STAGES];
 	uint32_t stage_count[NEUS2_N_STAGES];
-	bool stage_pending[NEUS2_N_STAGES];
+	bool stage_pending[2][NEUS2_N_STAGES];
+	// Pipelined single-GPU step (config.prefetch_next_samples): the step's one host read-back (sample counts) happens right after the
+	// loss kernel, so while the GPU runs backward pass + optimizer the host already knows rays_per_batch of the NEXT step and
+	// enqueues its sample generation on aux_stream, ordered behind this step's fused forward+backward kernel (which owns every
+	// SM's register file) -- it overlaps the weight-gradient GEMMs and Adam.  The counters ping-pong between two buffers.
+	struct StepPlan { uint32_t R, n_local, ray_offset, max_inference, n_rays_total, training_step; uint64_t rng_state, rng_inc; };
+	cudaStream_t aux_stream;
+	cudaEvent_t ev_counts, ev_fwdbwd_done, ev_gen_done;
+	uint32_t* counters_buf[2]; int counters_cur;
+	bool prefetched; StepPlan prefetch_plan; uint64_t prefetch_epoch;
+	bool step_pipelined;        // the step in flight took the pipelined path (its counts were read back after the loss kernel)
+	bool step_used_prefetch;    // ... and its samples had been generated during the previous step
+	uint32_t step_rank, step_world;
+	uint64_t state_epoch;       // bumped by every call that changes what sample generation reads (dataset, bitfield, rigid motion, step state)
 	float* h_scalars;           // pinned
 	// data-parallel peers (CUDA IPC mappings of every rank's gradient / fp16 parameter / EMA buffers; slot [rank] = own)
 	uint32_t peer_world, peer_rank;
@@ -118,16 +132,24 @@ static int dmalloc(void** p, size_t bytes) {
 }
 #define DMALLOC(ptr, count) CHECK(dmalloc((void**)&(ptr), sizeof(*(ptr)) * (size_t)(count)))
 
-static void stage_begin(neus2_ctx* ctx, int st, cudaStream_t s) { if (ctx->profiling) cudaEventRecord(ctx->ev[2 * st], s); }
-static void stage_end(neus2_ctx* ctx, int st, cudaStream_t s) { if (ctx->profiling) { cudaEventRecord(ctx->ev[2 * st + 1], s); ctx->stage_pending[st] = true; } }
-static void stage_collect(neus2_ctx* ctx) {   // call after the stream has been synchronised
+static void stage_begin_set(neus2_ctx* ctx, int set, int st, cudaStream_t s) { if (ctx->profiling) cudaEventRecord(ctx->ev[set][2 * st], s); }
+static void stage_end_set(neus2_ctx* ctx, int set, int st, cudaStream_t s) { if (ctx->profiling) { cudaEventRecord(ctx->ev[set][2 * st + 1], s); ctx->stage_pending[set][st] = true; } }
+static void stage_begin(neus2_ctx* ctx, int st, cudaStream_t s) { stage_begin_set(ctx, ctx->ev_set, st, s); }
+static void stage_end(neus2_ctx* ctx, int st, cudaStream_t s) { stage_end_set(ctx, ctx->ev_set, st, s); }
+static void stage_collect(neus2_ctx* ctx, int set) {   // call once the set's events have completed
 	if (!ctx->profiling) return;
 	for (int st = 0; st < NEUS2_N_STAGES; ++st) {
-		if (!ctx->stage_pending[st]) continue;
+		if (!ctx->stage_pending[set][st]) continue;
 		float ms = 0.f;
-		if (cudaEventElapsedTime(&ms, ctx->ev[2 * st], ctx->ev[2 * st + 1]) == cudaSuccess) { ctx->stage_ms_sum[st] += ms; ctx->stage_count[st]++; }
-		ctx->stage_pending[st] = false;
+		if (cudaEventElapsedTime(&ms, ctx->ev[set][2 * st], ctx->ev[set][2 * st + 1]) == cudaSuccess) { ctx->stage_ms_sum[st] += ms; ctx->stage_count[st]++; }
+		ctx->stage_pending[set][st] = false;
 	}
+}
+// Anything that changes what sample generation reads makes samples generated ahead of time stale; wait for them before the
+// caller touches the buffers they read.
+static void invalidate_prefetch(neus2_ctx* ctx) {
+	++ctx->state_epoch;
+	if (ctx->prefetched) { cudaEventSynchronize(ctx->ev_gen_done); ctx->prefetched = false; }
 }
 
 template <typename T> static int regrow(T** p, size_t* cap, size_t need) {
@@ -258,7 +280,7 @@ void neus2_default_config(neus2_config* c) {
 	c->aabb_scale = 1; c->seed = 1337; c->random_bg_color = 1; c->snap_to_pixel_centers = 1;
 	c->background_color[0] = c->background_color[1] = c->background_color[2] = 0.f;
 	c->density_grid_decay = 0.95f; c->loss_scale = 128.f;
-	c->world_size = 1; c->max_rays_per_batch = 1u << 18; c->forward_early_termination = 1;
+	c->world_size = 1; c->max_rays_per_batch = 1u << 18; c->forward_early_termination = 1; c->prefetch_next_samples = 1;
 	// "globalmove" optimizer of configs/nerf/base.json:135-158 (Ema{ExponentialDecay{Adam}})
 	c->delta_learning_rate = 1e-4f; c->delta_beta1 = 0.9f; c->delta_beta2 = 0.99f; c->delta_epsilon = 1e-10f;
 	c->delta_decay_start = 50; c->delta_decay_interval = 25; c->delta_decay_base = 0.99f;
@@ -334,7 +356,12 @@ int neus2_ctx_create(const neus2_config* cfg, int device, neus2_ctx** out) {
 	CDM(ctx->master, N); CDM(ctx->params, N); CDM(ctx->ema, N); CDM(ctx->grads, N); CDM(ctx->m1, N); CDM(ctx->m2, N); CDM(ctx->steps, N); CDM(ctx->adam_bias_table, ADAM_BIAS_TABLE);
 	CDM(ctx->numsteps_all, R); CDM(ctx->base, R); CDM(ctx->slot, R); CDM(ctx->ray_indices, R); CDM(ctx->numsteps, 2 * (size_t)R); CDM(ctx->scan_tmp, 2 * (size_t)R);
 	CDM(ctx->n_windows, R); CDM(ctx->windows, sampling_window_bytes_per_ray() * (size_t)R); CDM(ctx->ray_setup, 12 * (size_t)R);
-	CDM(ctx->counters, 12); ctx->counts_global = ctx->counters + 8;   // one 48-byte read-back per step covers both
+	CDM(ctx->counters_buf[0], 12); CDM(ctx->counters_buf[1], 12);
+	ctx->counters = ctx->counters_buf[0]; ctx->counts_global = ctx->counters + 8;   // one 48-byte read-back per step covers both
+	if (cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_counts, cudaEventDisableTiming) != cudaSuccess ||
+	    cudaEventCreateWithFlags(&ctx->ev_fwdbwd_done, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_gen_done, cudaEventDisableTiming) != cudaSuccess) {
+		neus2_ctx_destroy(ctx); FAIL("stream / event creation failed");
+	}
 	CDM(ctx->rays, 6 * (size_t)R); CDM(ctx->coords, 7 * (size_t)S); CDM(ctx->ray_tmp, 12 * (size_t)R);
 	CDM(ctx->coords_compacted, 7 * (size_t)B); CDM(ctx->loss, R); CDM(ctx->ek_loss, R); CDM(ctx->mask_loss, R);
 	CDM(ctx->mlp_out, 16 * (size_t)S); CDM(ctx->dloss, 16 * (size_t)B);
@@ -366,12 +393,16 @@ int neus2_ctx_create(const neus2_config* cfg, int device, neus2_ctx** out) {
 
 void neus2_ctx_destroy(neus2_ctx* ctx) {
 	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
+	for (cudaEvent_t e : {ctx->ev_counts, ctx->ev_fwdbwd_done, ctx->ev_gen_done}) if (e) cudaEventDestroy(e);
+	ctx->counters = nullptr;   // freed through counters_buf below
 	void* ptrs[] = {ctx->master, ctx->params, ctx->ema, ctx->grads, ctx->m1, ctx->m2, ctx->steps, ctx->adam_bias_table, ctx->d_pixels, ctx->d_focal, ctx->d_principal, ctx->d_xforms,
 		ctx->numsteps_all, ctx->base, ctx->slot, ctx->ray_indices, ctx->numsteps, ctx->scan_tmp, ctx->counters, ctx->n_windows, ctx->windows, ctx->ray_setup, ctx->rays, ctx->coords, ctx->ray_tmp,
 		ctx->coords_compacted, ctx->loss, ctx->ek_loss, ctx->mask_loss, ctx->mlp_out, ctx->dloss, ctx->so.dOUT, ctx->so.H2, ctx->so.dH2, ctx->so.H1, ctx->so.dH1,
 		ctx->so.CIN, ctx->so.dSO, ctx->so.H0, ctx->so.dH0, ctx->so.X0, ctx->so.dI, ctx->partials, ctx->var_acc, ctx->w1row0_acc, ctx->scalar_tmp,
 		ctx->density_grid, ctx->density_grid_tmp, ctx->grid_positions, ctx->grid_indices, ctx->grid_density, ctx->bitfield, ctx->density_grid_mean,
-		ctx->d_xform, ctx->d_acc, ctx->d_master, ctx->d_m1, ctx->d_m2, ctx->d_steps, ctx->d_params};
+		ctx->d_xform, ctx->d_acc, ctx->d_master, ctx->d_m1, ctx->d_m2, ctx->d_steps, ctx->d_params, ctx->counters_buf[0], ctx->counters_buf[1]};
 	for (void* p : ptrs) if (p) cudaFree(p);
 	for (uint32_t r = 0; r < ctx->peer_world; ++r) if (r != ctx->peer_rank) {
 		if (ctx->peer_grads[r]) cudaIpcCloseMemHandle(ctx->peer_grads[r]);
@@ -524,6 +555,7 @@ static int backward_on_stream(neus2_ctx* ctx, cudaStream_t stream, const float* 
 	CHECK(launch_network_fwdbwd(stream, ctx->gm, ctx->pl, ctx->params, coords, (const __half*)dL_dout, n_in_dev, n_rows, ctx->cfg.sdf_bias, indeed_batch_size,
 	                            ctx->grads, ctx->var_acc, ctx->w1row0_acc, ctx->so, ctx->use_delta ? ctx->d_acc : nullptr));
 	stage_end(ctx, ST_FWDBWD, stream);
+	CUDA_CHECK(cudaEventRecord(ctx->ev_fwdbwd_done, stream));
 	stage_begin(ctx, ST_WGRAD, stream);
 	CHECK(launch_weight_gradients(stream, ctx->pl, ctx->so, ctx->params, n_in_dev, n_rows, ctx->partials, weight_gradient_partials(), ctx->var_acc, ctx->w1row0_acc, ctx->grads));
 	stage_end(ctx, ST_WGRAD, stream);
@@ -559,6 +591,7 @@ int neus2_optimizer_step(neus2_ctx* ctx, void* stream, float loss_scale) {
 }
 
 int neus2_set_dataset(neus2_ctx* ctx, uint32_t n_images, int32_t width, int32_t height, const uint8_t* pixels, const float* focal, const float* principal, const float* xforms) {
+	invalidate_prefetch(ctx);
 	CUDA_CHECK(cudaSetDevice(ctx->device));
 	if (!n_images || width <= 0 || height <= 0) FAIL("empty dataset");
 	if (ctx->d_pixels) { cudaFree(ctx->d_pixels); cudaFree(ctx->d_focal); cudaFree(ctx->d_principal); cudaFree(ctx->d_xforms); }
@@ -576,9 +609,14 @@ int neus2_set_dataset(neus2_ctx* ctx, uint32_t n_images, int32_t width, int32_t 
 	return 0;
 }
 
+static int update_density_grid_on_stream(neus2_ctx* ctx, cudaStream_t stream);
 int neus2_update_density_grid(neus2_ctx* ctx, void* stream_) {   // training_prep_nerf (:4003-4016) -> update_density_grid_nerf (:3293-3375)
-	cudaStream_t stream = (cudaStream_t)stream_;
 	CUDA_CHECK(cudaSetDevice(ctx->device));
+	invalidate_prefetch(ctx);   // the occupancy bitfield changes
+	return update_density_grid_on_stream(ctx, (cudaStream_t)stream_);
+}
+static int update_density_grid_on_stream(neus2_ctx* ctx, cudaStream_t stream) {
+	void* stream_ = (void*)stream; (void)stream_;
 	const uint32_t G3n = NERF_GRIDSIZE * NERF_GRIDSIZE * NERF_GRIDSIZE;
 	const uint32_t n_elements = G3n * ctx->n_cascades;
 	uint32_t n_uniform, n_nonuniform;
@@ -605,46 +643,92 @@ int neus2_update_density_grid(neus2_ctx* ctx, void* stream_) {   // training_pre
 	return 0;
 }
 
+static int enqueue_loss_scalars(neus2_ctx* ctx, cudaStream_t stream) {
+	CHECK(launch_reduce_sum(stream, ctx->loss, ctx->step_rays, ctx->scalar_tmp + 0));
+	CHECK(launch_reduce_sum(stream, ctx->ek_loss, ctx->step_rays, ctx->scalar_tmp + 1));
+	CHECK(launch_reduce_sum(stream, ctx->mask_loss, ctx->step_rays, ctx->scalar_tmp + 2));
+	CUDA_CHECK(cudaMemcpyAsync(ctx->h_scalars, ctx->scalar_tmp, 3 * sizeof(float), cudaMemcpyDeviceToHost, stream));
+	return 0;
+}
+
+// Where the next step's sample generation may start: 0 = as soon as this step's loss kernel is done (nothing after it reads or writes
+// the sample buffers); its blocks then fill the SMs the persistent forward+backward kernel frees at its tail and run on beside the
+// weight-gradient GEMMs and Adam.  1 = only after the forward+backward kernel has completed.
+#ifndef NEUS2_GEN_AFTER_FWDBWD
+#define NEUS2_GEN_AFTER_FWDBWD 0
+#endif
+// What sample generation of the next train step will be launched with: a pure function of the context's step state, so that the
+// end of step k can generate step k+1's samples ahead of time and step k+1 can verify that they are the ones it would have made.
+static void plan_step(const neus2_ctx* ctx, uint32_t rank, uint32_t world_size, neus2_ctx::StepPlan& p) {
+	memset(&p, 0, sizeof(p));
+	p.R = ctx->rays_per_batch;
+	p.n_local = p.R / world_size; p.ray_offset = rank * p.n_local;
+	p.max_inference = ctx->measured_before == 0 ? ctx->max_samples : (std::min(ctx->measured_before, ctx->max_samples) + 127u) / 128u * 128u;   // :3770-3775
+	p.n_rays_total = ctx->training_step == 0 ? 0 : ctx->n_rays_total;                    // :3785-3787
+	p.training_step = ctx->training_step;
+	p.rng_state = ctx->rng.state; p.rng_inc = ctx->rng.inc;
+}
+static int launch_gen(neus2_ctx* ctx, cudaStream_t stream, const neus2_ctx::StepPlan& p, uint32_t* counters) {
+	const uint64_t st[2] = {p.rng_state, p.rng_inc};
+	return launch_generate_training_samples(stream, p.n_local, p.ray_offset, p.R, p.n_rays_total, st, ctx->ds, ctx->aabb, ctx->gmv, ctx->bitfield, ctx->cfg.snap_to_pixel_centers,
+	                                        ctx->cone_angle_constant, p.max_inference, ctx->numsteps_all, ctx->base, ctx->slot, ctx->ray_indices, ctx->rays,
+	                                        ctx->numsteps, ctx->coords, counters, ctx->windows, ctx->n_windows, ctx->ray_setup);
+}
+static bool density_grid_due(uint32_t training_step) {
+	const uint32_t n_prep_to_skip = std::min(std::max(training_step / 16u, 1u), 16u);   // testbed.cu:2669
+	return training_step % n_prep_to_skip == 0;
+}
+
 int neus2_train_step_begin(neus2_ctx* ctx, void* stream_, uint32_t rank, uint32_t world_size) {
 	cudaStream_t stream = (cudaStream_t)stream_;
 	CUDA_CHECK(cudaSetDevice(ctx->device));
 	if (!ctx->d_pixels) FAIL("no training data: call neus2_set_dataset first");
 	if (world_size != ctx->cfg.world_size || rank >= world_size) FAIL("rank / world_size do not match the context's config.world_size");
 	const neus2_config& c = ctx->cfg;
+	const bool pipelined = world_size == 1 && c.prefetch_next_samples;   // world > 1: neus2_train_step_counts_ready switches the step to the pipelined end
+	ctx->ev_set ^= 1;
 	neus2_set_training_step(ctx, ctx->time_frame >= 1 ? (int32_t)ctx->training_step - (int32_t)ctx->frozen_steps : (int32_t)ctx->training_step);   // testbed.cu:2651-2657
-	const uint32_t n_prep_to_skip = std::min(std::max(ctx->training_step / 16u, 1u), 16u);   // :2669
 	ctx->step_density_updated = false;
 	stage_begin(ctx, ST_STEP, stream);
-	if (ctx->training_step % n_prep_to_skip == 0) {
+	if (density_grid_due(ctx->training_step)) {
 		stage_begin(ctx, ST_GRID, stream);
-		CHECK(neus2_update_density_grid(ctx, stream_));
+		CHECK(update_density_grid_on_stream(ctx, stream));
 		stage_end(ctx, ST_GRID, stream);
 		ctx->step_density_updated = true;
 	}
 
 	// Counters::prepare_for_training_steps (:3399-3410)
-	const uint32_t R = ctx->rays_per_batch;
 	const bool pre_zeroed = ctx->scratch_zeroed;   // train_step_end of the previous step already queued these fills on this stream
 	ctx->scratch_zeroed = false;
-	if (!pre_zeroed) CHECK(zero_step_scratch(ctx, stream, R));
 
 	// train_nerf_step (:3723-4001)
-	const uint32_t n_local = R / world_size, ray_offset = rank * n_local;
+	neus2_ctx::StepPlan plan;
+	plan_step(ctx, rank, world_size, plan);
+	const uint32_t R = plan.R, n_local = plan.n_local, max_inference = plan.max_inference, n_rays_total = plan.n_rays_total;
 	const uint32_t rows_local = ctx->B_local;
-	const uint32_t max_samples = ctx->max_samples;
-	uint32_t max_inference;
-	if (ctx->measured_before == 0) { ctx->measured_before = max_inference = max_samples; }
-	else { max_inference = (std::min(ctx->measured_before, max_samples) + 127u) / 128u * 128u; }   // :3770-3775
-	if (ctx->training_step == 0) ctx->n_rays_total = 0;                                  // :3785-3787
-	const uint32_t n_rays_total = ctx->n_rays_total;
+	bool have_samples = false;
+	if (ctx->prefetched) {
+		// step k-1 generated samples ahead of time on the aux stream; they are this step's iff nothing they depend on changed
+		CUDA_CHECK(cudaStreamWaitEvent(stream, ctx->ev_gen_done, 0));
+		ctx->prefetched = false;
+		if (c.prefetch_next_samples && pre_zeroed && !ctx->step_density_updated && ctx->prefetch_epoch == ctx->state_epoch && !memcmp(&plan, &ctx->prefetch_plan, sizeof(plan))) {
+			ctx->counters_cur ^= 1;
+			ctx->counters = ctx->counters_buf[ctx->counters_cur]; ctx->counts_global = ctx->counters + 8;
+			have_samples = true;
+		}
+	}
+	ctx->step_used_prefetch = have_samples;
+	if (!have_samples && !pre_zeroed) CHECK(zero_step_scratch(ctx, stream, R));
+	if (ctx->measured_before == 0) ctx->measured_before = ctx->max_samples;
+	if (ctx->training_step == 0) ctx->n_rays_total = 0;
 	ctx->n_rays_total += R;
 	ctx->step_rays = R; ctx->step_rays_local = n_local; ctx->step_n_rays_total = n_rays_total;
-	const uint64_t st[2] = {ctx->rng.state, ctx->rng.inc};
-	stage_begin(ctx, ST_GEN, stream);
-	CHECK(launch_generate_training_samples(stream, n_local, ray_offset, R, n_rays_total, st, ctx->ds, ctx->aabb, ctx->gmv, ctx->bitfield, c.snap_to_pixel_centers,
-	                                       ctx->cone_angle_constant, max_inference, ctx->numsteps_all, ctx->base, ctx->slot, ctx->ray_indices, ctx->rays,
-	                                       ctx->numsteps, ctx->coords, ctx->counters, ctx->windows, ctx->n_windows, ctx->ray_setup));
-	stage_end(ctx, ST_GEN, stream);
+	const uint64_t st[2] = {plan.rng_state, plan.rng_inc};
+	if (!have_samples) {
+		stage_begin(ctx, ST_GEN, stream);
+		CHECK(launch_gen(ctx, stream, plan, ctx->counters));
+		stage_end(ctx, ST_GEN, stream);
+	}
 	LossParamsDev lp;
 	lp.loss_scale = c.loss_scale; memcpy(lp.background_color, c.background_color, sizeof(lp.background_color));
 	lp.random_bg_color = c.random_bg_color; lp.snap_to_pixel_centers = c.snap_to_pixel_centers;
@@ -663,8 +747,18 @@ int neus2_train_step_begin(neus2_ctx* ctx, void* stream_, uint32_t rank, uint32_
 	                          ctx->rays, ctx->numsteps, ctx->coords, ctx->ray_tmp, ctx->scan_tmp, ctx->coords_compacted, ctx->dloss, ctx->loss, ctx->ek_loss,
 	                          ctx->mask_loss, ctx->counters + 2));
 	stage_end(ctx, ST_LOSS, stream);
+	ctx->step_pipelined = pipelined;
+	ctx->step_rank = rank; ctx->step_world = world_size;
+	if (pipelined) {
+		// every number the host needs from this step exists now: read it back BEFORE the backward pass is queued, so that the host's
+		// turnaround (and the next step's sample generation) hides behind the backward pass instead of following it
+		CUDA_CHECK(cudaMemcpyAsync(ctx->counts_global, ctx->counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
+		if (ctx->training_step % 16 == 0) CHECK(enqueue_loss_scalars(ctx, stream));
+		CUDA_CHECK(cudaMemcpyAsync(ctx->h_counters, ctx->counters, 12 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+		CUDA_CHECK(cudaEventRecord(ctx->ev_counts, stream));
+	}
 	CHECK(backward_on_stream(ctx, stream, ctx->coords_compacted, ctx->dloss, ctx->counters + 2, rows_local, ctx->B, /*grads_zeroed=*/pre_zeroed));   // :3941-3946
-	CUDA_CHECK(cudaMemcpyAsync(ctx->counts_global, ctx->counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
+	if (!pipelined) CUDA_CHECK(cudaMemcpyAsync(ctx->counts_global, ctx->counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
 	return 0;
 }
 
@@ -682,34 +776,53 @@ int neus2_local_counts(neus2_ctx* ctx, void* stream_, uint32_t counts[3]) {
 	return 0;
 }
 
+// Data-parallel callers: call right after the all-reduce of neus2_counts_device() has been enqueued (it follows the backward pass).
+// The read-back of the global counts is taken here, ahead of the optimizer / its collectives, and the step ends like the pipelined
+// single-GPU step: no host sync at its end, the next step's samples are generated beside the optimizer.  No-op without
+// config.prefetch_next_samples.
+int neus2_train_step_counts_ready(neus2_ctx* ctx, void* stream_) {
+	cudaStream_t stream = (cudaStream_t)stream_;
+	CUDA_CHECK(cudaSetDevice(ctx->device));
+	if (!ctx->cfg.prefetch_next_samples || ctx->step_pipelined) return 0;
+	if (ctx->training_step % 16 == 0) CHECK(enqueue_loss_scalars(ctx, stream));
+	CUDA_CHECK(cudaMemcpyAsync(ctx->h_counters, ctx->counters, 12 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+	CUDA_CHECK(cudaEventRecord(ctx->ev_counts, stream));
+	ctx->step_pipelined = true;
+	return 0;
+}
+
 int neus2_train_step_end(neus2_ctx* ctx, void* stream_, const uint32_t* counts_global, neus2_step_stats* stats) {
 	cudaStream_t stream = (cudaStream_t)stream_;
 	CUDA_CHECK(cudaSetDevice(ctx->device));
 	const neus2_config& c = ctx->cfg;
 	const bool get_loss_scalar = ctx->training_step % 16 == 0;                           // testbed.cu:2714
+	const bool pipelined = ctx->step_pipelined;
 	if (!ctx->optimizer_done) CHECK(neus2_optimizer_step(ctx, stream_, c.loss_scale));   // testbed_nerf.cu:3503-3505
 	ctx->optimizer_done = false;
-	if (get_loss_scalar) {
-		CHECK(launch_reduce_sum(stream, ctx->loss, ctx->step_rays, ctx->scalar_tmp + 0));
-		CHECK(launch_reduce_sum(stream, ctx->ek_loss, ctx->step_rays, ctx->scalar_tmp + 1));
-		CHECK(launch_reduce_sum(stream, ctx->mask_loss, ctx->step_rays, ctx->scalar_tmp + 2));
-		CUDA_CHECK(cudaMemcpyAsync(ctx->h_scalars, ctx->scalar_tmp, 3 * sizeof(float), cudaMemcpyDeviceToHost, stream));
+	if (!pipelined) {
+		if (get_loss_scalar) CHECK(enqueue_loss_scalars(ctx, stream));
+		stage_end(ctx, ST_STEP, stream);
+		// the one structurally required host sync per step (:3412-3416): local counters + the (possibly all-reduced) global ones
+		// counters[0..3] local {kept, N_u, compacted}, [4..7] first-pass work counters, [8..11] the (all-reduced) global counts
+		CUDA_CHECK(cudaMemcpyAsync(ctx->h_counters, ctx->counters, 12 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+		if (!ctx->readback_event) CUDA_CHECK(cudaEventCreateWithFlags(&ctx->readback_event, cudaEventDisableTiming));
+		CUDA_CHECK(cudaEventRecord(ctx->readback_event, stream));
 	}
-	stage_end(ctx, ST_STEP, stream);
-	// the one structurally required host sync per step (:3412-3416): local counters + the (possibly all-reduced) global ones
-	// counters[0..3] local {kept, N_u, compacted}, [4..7] first-pass work counters, [8..11] the (all-reduced) global counts
-	CUDA_CHECK(cudaMemcpyAsync(ctx->h_counters, ctx->counters, 12 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-	if (!ctx->readback_event) CUDA_CHECK(cudaEventCreateWithFlags(&ctx->readback_event, cudaEventDisableTiming));
-	CUDA_CHECK(cudaEventRecord(ctx->readback_event, stream));
-	// While the host waits for that read-back and prepares the next step, the GPU already zero-fills what the next step starts from
-	// (42 MB of gradients + per-ray scratch): stream-ordered behind the copies above and, data-parallel, behind the peers' barrier.
+	// While the host waits for the read-back and prepares the next step, the GPU already zero-fills what the next step starts from
+	// (42 MB of gradients + per-ray scratch): stream-ordered behind the optimizer and, data-parallel, behind the peers' barrier.
 	CHECK(zero_step_scratch(ctx, stream, ctx->max_rays));
 	CUDA_CHECK(cudaMemsetAsync(ctx->grads, 0, ctx->n_params * sizeof(float), stream));
 	CUDA_CHECK(cudaMemsetAsync(ctx->var_acc, 0, sizeof(float), stream));
 	CUDA_CHECK(cudaMemsetAsync(ctx->w1row0_acc, 0, 64 * sizeof(float), stream));
 	ctx->scratch_zeroed = true;
-	CUDA_CHECK(cudaEventSynchronize(ctx->readback_event));
-	stage_collect(ctx);
+	if (pipelined) {
+		stage_end(ctx, ST_STEP, stream);
+		CUDA_CHECK(cudaEventSynchronize(ctx->ev_counts));      // recorded right after the loss kernel: the backward pass is still running
+		stage_collect(ctx, ctx->ev_set ^ 1);                   // the previous step's events have all completed by now
+	} else {
+		CUDA_CHECK(cudaEventSynchronize(ctx->readback_event));
+		stage_collect(ctx, 0); stage_collect(ctx, 1);
+	}
 	const uint32_t n_kept_local = ctx->h_counters[0];
 	uint32_t counts[3] = {ctx->h_counters[8], ctx->h_counters[9], ctx->h_counters[10]};
 	if (counts_global) { counts[0] = counts_global[0]; counts[1] = counts_global[1]; counts[2] = counts_global[2]; }
@@ -722,6 +835,7 @@ int neus2_train_step_end(neus2_ctx* ctx, void* stream_, const uint32_t* counts_g
 	s.rays_per_batch = ctx->step_rays;
 	s.n_rays_kept = have_global ? counts[0] : n_kept_local;
 	s.density_grid_updated = ctx->step_density_updated;
+	s.samples_prefetched = ctx->step_used_prefetch ? 1 : 0;
 	s.first_pass_samples = ctx->cfg.forward_early_termination ? ctx->h_counters[5] : std::min(ctx->h_counters[1], ctx->max_samples);
 	// Counters::update_after_training (:3412-3438)
 	if (counts[1] == 0 || counts[2] == 0) {
@@ -740,6 +854,20 @@ int neus2_train_step_end(neus2_ctx* ctx, void* stream_, const uint32_t* counts_g
 		const uint32_t gran = 128u * ctx->cfg.world_size;
 		rpb = std::min((rpb + gran - 1) / gran * gran, ctx->cfg.max_rays_per_batch);
 		ctx->rays_per_batch = rpb;
+		if (pipelined && !density_grid_due(ctx->training_step)) {
+			// Generate the NEXT step's samples now, on the aux stream, behind this step's fused forward+backward kernel (which leaves no
+			// registers for anyone else) and concurrently with its weight-gradient GEMMs, optimizer and zero-fills.  They land in the
+			// other counter buffer; the sample buffers themselves were last read by this step's loss kernel, long done.
+			plan_step(ctx, ctx->step_rank, ctx->step_world, ctx->prefetch_plan);
+			uint32_t* next_counters = ctx->counters_buf[ctx->counters_cur ^ 1];
+			CUDA_CHECK(cudaStreamWaitEvent(ctx->aux_stream, NEUS2_GEN_AFTER_FWDBWD ? ctx->ev_fwdbwd_done : ctx->ev_counts, 0));
+			CUDA_CHECK(cudaMemsetAsync(next_counters, 0, 8 * sizeof(uint32_t), ctx->aux_stream));
+			stage_begin_set(ctx, ctx->ev_set ^ 1, ST_GEN, ctx->aux_stream);
+			CHECK(launch_gen(ctx, ctx->aux_stream, ctx->prefetch_plan, next_counters));
+			stage_end_set(ctx, ctx->ev_set ^ 1, ST_GEN, ctx->aux_stream);
+			CUDA_CHECK(cudaEventRecord(ctx->ev_gen_done, ctx->aux_stream));
+			ctx->prefetched = true; ctx->prefetch_epoch = ctx->state_epoch;
+		}
 	}
 	s.rays_per_batch_next = ctx->rays_per_batch;
 	if (stats) *stats = s;
@@ -777,11 +905,13 @@ int neus2_get_state(neus2_ctx* ctx, uint32_t* training_step, uint32_t* rays_per_
 }
 
 int neus2_set_state(neus2_ctx* ctx, uint32_t training_step, uint32_t rays_per_batch, uint32_t n_rays_total, uint32_t measured_before) {
+	invalidate_prefetch(ctx);
 	ctx->training_step = training_step; ctx->rays_per_batch = rays_per_batch; ctx->n_rays_total = n_rays_total; ctx->measured_before = measured_before;
 	return 0;
 }
 
 int neus2_set_bitfield(neus2_ctx* ctx, const uint8_t* bitfield_host, uint64_t n_bytes) {
+	invalidate_prefetch(ctx);
 	const uint64_t want = (uint64_t)NERF_GRIDSIZE * NERF_GRIDSIZE * NERF_GRIDSIZE / 8 * NERF_CASCADES;
 	if (n_bytes != want) FAIL("bitfield size mismatch");
 	CUDA_CHECK(cudaSetDevice(ctx->device));
@@ -790,13 +920,17 @@ int neus2_set_bitfield(neus2_ctx* ctx, const uint8_t* bitfield_host, uint64_t n_
 }
 
 int neus2_set_profiling(neus2_ctx* ctx, int enable) {
-	if (enable && !ctx->ev[0]) { for (int i = 0; i < 2 * NEUS2_N_STAGES; ++i) CUDA_CHECK(cudaEventCreate(&ctx->ev[i])); }
+	CUDA_CHECK(cudaSetDevice(ctx->device));
+	if (enable && !ctx->ev[0][0]) { for (int k = 0; k < 2; ++k) for (int i = 0; i < 2 * NEUS2_N_STAGES; ++i) CUDA_CHECK(cudaEventCreate(&ctx->ev[k][i])); }
+	CUDA_CHECK(cudaDeviceSynchronize());   // events of steps still in flight belong to the old setting
 	ctx->profiling = enable;
-	for (int i = 0; i < NEUS2_N_STAGES; ++i) { ctx->stage_ms_sum[i] = 0.f; ctx->stage_count[i] = 0; ctx->stage_pending[i] = false; }
+	for (int i = 0; i < NEUS2_N_STAGES; ++i) { ctx->stage_ms_sum[i] = 0.f; ctx->stage_count[i] = 0; ctx->stage_pending[0][i] = ctx->stage_pending[1][i] = false; }
 	return 0;
 }
 
 int neus2_get_stage_times(neus2_ctx* ctx, float ms_sum[8], uint32_t count[8]) {
+	CUDA_CHECK(cudaSetDevice(ctx->device));
+	if (ctx->profiling) { CUDA_CHECK(cudaDeviceSynchronize()); stage_collect(ctx, 0); stage_collect(ctx, 1); }   // the pipelined step reads a set back one step late
 	for (int i = 0; i < NEUS2_N_STAGES; ++i) { ms_sum[i] = ctx->stage_ms_sum[i]; count[i] = ctx->stage_count[i]; }
 	return 0;
 }
@@ -990,6 +1124,7 @@ int neus2_set_optimizer_step(neus2_ctx* ctx, uint32_t current_step) {
 
 // density_grid: n floats (128^3 per cascade); recomputes mean + bitfield like load_snapshot does (testbed.cu:3232-3236)
 int neus2_set_density_grid(neus2_ctx* ctx, void* stream_, const float* density_grid_host, uint64_t n, uint32_t ema_step) {
+	invalidate_prefetch(ctx);
 	cudaStream_t stream = (cudaStream_t)stream_;
 	CUDA_CHECK(cudaSetDevice(ctx->device));
 	const uint64_t want = (uint64_t)NERF_GRIDSIZE * NERF_GRIDSIZE * NERF_GRIDSIZE * ctx->n_cascades;
@@ -1035,6 +1170,7 @@ int neus2_get_counters(neus2_ctx* ctx, uint32_t out[4]) {
 // false until m_training_step == m_predict_global_movement_training_step, :2659-2667) and the progressive-level schedule counts
 // from there; `after_learning_rate` replaces the learning rate (:2688-2690).
 int neus2_next_frame(neus2_ctx* ctx, void* stream_, float after_learning_rate, uint32_t frozen_steps) {
+	invalidate_prefetch(ctx);
 	cudaStream_t stream = (cudaStream_t)stream_;
 	CUDA_CHECK(cudaSetDevice(ctx->device));
 	const uint64_t n = ctx->n_params;
@@ -1067,6 +1203,7 @@ int neus2_next_frame(neus2_ctx* ctx, void* stream_, float after_learning_rate, u
 // common_operation.cuh:551-580: R_acc <- R_d R_acc, t_acc <- R_d (t_acc + t_d), stored in half), reset the delta to the identity
 // with a fresh optimizer, and route every network evaluation through it (m_use_delta = m_train_delta = true).
 int neus2_begin_global_movement(neus2_ctx* ctx, void* stream_) {
+	invalidate_prefetch(ctx);
 	cudaStream_t stream = (cudaStream_t)stream_;
 	CUDA_CHECK(cudaSetDevice(ctx->device));
 	float x[DELTA_XFORM_FLOATS];
@@ -1115,6 +1252,7 @@ int neus2_get_global_movement(neus2_ctx* ctx, void* stream_, float accumulated_r
 
 int neus2_set_global_movement(neus2_ctx* ctx, void* stream_, const float accumulated_rotation[9], const float accumulated_transition[3],
                               const float delta_rotation_6d[6], const float delta_transition[3], const float first_frame_offset[3]) {
+	invalidate_prefetch(ctx);
 	cudaStream_t stream = (cudaStream_t)stream_;
 	CUDA_CHECK(cudaSetDevice(ctx->device));
 	if (accumulated_rotation) for (int k = 0; k < 9; ++k) ctx->gmv.R[k] = __half2float(__float2half_rn(accumulated_rotation[k]));

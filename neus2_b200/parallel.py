@@ -57,6 +57,7 @@ def train_step(ctx, rank=0, world_size=1, group=None):
     # everything below is enqueued behind the backward pass on the step's stream: no host round trip between begin and end
     counts = ctx.counts_device()
     allreduce_sum_(counts, group)                # {rays kept, samples, compacted}; also orders "all backward passes done" before the peer loads
+    ctx.train_step_counts_ready()                # pipelined step: the host read-back is taken here; the next step's samples are generated beside the optimizer
     if ctx.global_movement_active:
         # the DeltaNetwork's 9 gradient sums (48 bytes): every rank then steps its replica of the 12 parameters identically
         allreduce_sum_(ctx.delta_gradients(), group)

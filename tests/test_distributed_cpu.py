@@ -166,3 +166,74 @@ def test_render_bands_and_lattice_slabs_reassemble(tmp_path, world):
     for r in range(world):
         got = torch.load(tmp_path / f"r{r}.pt")
         assert torch.equal(got["img"], whole_img) and torch.equal(got["lat"], whole_lat)
+
+
+class _FakeTrainCtx:
+    """Records the order in which parallel.train_step drives a context, with CPU tensors standing in for the device buffers."""
+
+    def __init__(self, rank, peers, delta):
+        self.rank, self.peers_attached, self.global_movement_active = rank, peers, delta
+        self.calls = []
+        self.counts = torch.tensor([10 + rank, 100 + rank, 50 + rank, 0], dtype=torch.int32)
+        self.grads = torch.full((8,), float(rank + 1))
+        self.dgrads = torch.arange(12, dtype=torch.float32) * (rank + 1)
+
+        class _Cfg:
+            loss_scale = 128.0
+        self.cfg = _Cfg()
+
+    def train_step_begin(self, rank, world):
+        self.calls.append(("begin", rank, world))
+
+    def counts_device(self):
+        return self.counts
+
+    def train_step_counts_ready(self):
+        self.calls.append(("counts_ready", self.counts.tolist()))
+
+    def delta_gradients(self):
+        return self.dgrads
+
+    def optimizer_step_sharded(self, loss_scale):
+        self.calls.append(("sharded", self.dgrads.tolist()))
+
+    def buffers(self):
+        return None, None, None, self.grads
+
+    def train_step_end(self):
+        self.calls.append(("end", self.grads.tolist()))
+        return "stats"
+
+
+def _train_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    out = {}
+    for peers in (True, False):
+        ctx = _FakeTrainCtx(rank, peers, delta=True)
+        assert parallel.train_step(ctx, rank, world) == "stats"
+        out[peers] = ctx.calls
+    torch.save(out, os.path.join(out_dir, f"t{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_step_choreography(tmp_path):
+    """world_size 2 over gloo: the sample counts are all-reduced BEFORE the host read-back point (counts_ready), the 12 delta
+    gradients before the optimizer, and the 42 MB gradient all-reduce only happens on the path without peer memory."""
+    port = _free_port()
+    mp.spawn(_train_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        got = torch.load(tmp_path / f"t{r}.pt")
+        p2p, nccl = got[True], got[False]
+        assert [c[0] for c in p2p] == ["begin", "counts_ready", "sharded", "end"]
+        assert [c[0] for c in nccl] == ["begin", "counts_ready", "end"]
+        assert p2p[0] == ("begin", r, 2)
+        assert p2p[1][1] == [21, 201, 101, 0] and nccl[1][1] == [21, 201, 101, 0]      # global counts at the read-back point
+        assert p2p[2][1] == [3.0 * k for k in range(12)]                                 # summed delta gradients reach the optimizer
+        assert p2p[3][1] == [float(r + 1)] * 8                                           # peer path: no gradient all-reduce
+        assert nccl[2][1] == [3.0] * 8                                                   # NCCL path: gradients summed before Adam
+    # single rank: one call, no collectives
+    class _One:
+        def train_step(self):
+            return "one"
+    assert parallel.train_step(_One(), 0, 1) == "one"

@@ -268,3 +268,57 @@ def test_early_termination_changes_nothing_downstream():
     finally:
         for c in ctxs:
             c.close()
+
+
+def test_pipelined_step_generates_the_same_samples():
+    """config.prefetch_next_samples (default on): the samples of step k+1 are generated during step k on a second stream, from the
+    step state the host already knows after step k's loss kernel.  They must be exactly what the in-order step generates: checked
+    against the oracle on steps that used the prefetch, and the schedule of prefetched steps is the complement of the
+    occupancy-refresh schedule (a refresh changes the bitfield the samples depend on)."""
+    import torch
+    import neus2_b200 as N
+    from neus2_b200 import synthetic
+    data = synthetic.render_sphere_views(n_views=6, width=128, height=96, seed=5)
+    ds = O.make_dataset(data["pixels"], data["focal"], data["principal"], data["xforms"])
+    c = N.Context(N.default_config(batch_size=B))
+    assert c.cfg.prefetch_next_samples == 1
+    try:
+        c.init_params()
+        c.set_dataset(data["pixels"], data["focal"], data["principal"], data["xforms"])
+        checked = 0
+        for step in range(45):
+            due = step % min(max(step // 16, 1), 16) == 0
+            st0 = c.get_state()
+            assert st0["training_step"] == step
+            check = (not due) and step in (33, 37, 43)
+            if check:
+                bitfield = _np(c.debug_buffer("bitfield", "<u1", (G3 // 8 * 8,))).copy()
+            c.train_step_begin()
+            if check:
+                torch.cuda.synchronize()
+                R = st0["rays_per_batch"]
+                max_inf = (min(st0["measured_before"], B * 16) + 127) // 128 * 128
+                ref = O.generate_training_samples(R, max_inf, st0["n_rays_total"], O.Pcg32(state=st0["rng_state"]), ds, bitfield)
+                cnt = _np(c.debug_buffer("counters", "<u4", (8,)))
+                assert int(cnt[0]) == ref["n_kept"] and int(cnt[1]) == ref["n_samples"] and ref["n_kept"] > 20
+                assert np.array_equal(_np(c.debug_buffer("numsteps_all", "<u4", (R,))), ref["numsteps_all"])
+                k = ref["n_kept"]
+                assert np.array_equal(_np(c.debug_buffer("ray_indices", "<u4", (R,)))[:k], ref["ray_indices"][:k])
+                assert np.array_equal(_np(c.debug_buffer("rays", "<f4", (R, 6)))[:k].view(np.uint32), ref["rays"][:k].view(np.uint32))
+                last = ref["numsteps"][k - 1]
+                g_coords = _np(c.debug_buffer("coords", "<f4", (B * 16, 7)))[:int(last[0] + last[1])]
+                for i in range(k):
+                    n_i, b_i = ref["numsteps"][i]
+                    assert np.array_equal(g_coords[b_i:b_i + n_i].view(np.uint32), ref["coords"][b_i:b_i + n_i].view(np.uint32))
+                checked += 1
+            st = c.train_step_end()
+            assert st.measured_batch_size > 0
+            assert st.samples_prefetched == (0 if (due or step == 0) else 1), (step, due, st.samples_prefetched)
+            assert st.density_grid_updated == int(due)
+        assert checked == 3
+        # step 45's samples are in flight now; a call that changes what sample generation reads discards them
+        c.set_state(**{k: c.get_state()[k] for k in ("training_step", "rays_per_batch", "n_rays_total", "measured_before")})
+        flags = [c.train_step().samples_prefetched for _ in range(3)]       # 45: discarded, 46: occupancy refresh, 47: prefetched again
+        assert flags == [0, 0, 1], flags
+    finally:
+        c.close()
