@@ -100,6 +100,8 @@ struct neus2_ctx {
 	bool step_pipelined;        // the step in flight took the pipelined path (its counts were read back after the loss kernel)
 	bool step_used_prefetch;    // ... and its samples had been generated during the previous step
 	uint32_t step_rank, step_world;
+	bool fuse_zero_into_adam;   // set by train_step_end around its optimizer call (single-GPU pipelined step)
+	bool aux_pending;           // work is in flight on aux_stream that the next step must wait for (ev_gen_done)
 	uint64_t state_epoch;       // bumped by every call that changes what sample generation reads (dataset, bitfield, rigid motion, step state)
 	float* h_scalars;           // pinned
 	// data-parallel peers (CUDA IPC mappings of every rank's gradient / fp16 parameter / EMA buffers; slot [rank] = own)
@@ -373,6 +375,7 @@ int neus2_ctx_create(const neus2_config* cfg, int device, neus2_ctx** out) {
 	CDM(ctx->density_grid, G3n * ctx->n_cascades); CDM(ctx->density_grid_tmp, G3n * ctx->n_cascades);
 	CDM(ctx->grid_positions, 3 * G3n * ctx->n_cascades); CDM(ctx->grid_indices, G3n * ctx->n_cascades); CDM(ctx->grid_density, G3n * ctx->n_cascades);
 	CDM(ctx->bitfield, G3n / 8 * NERF_CASCADES); CDM(ctx->density_grid_mean, 1);
+	CTXCHECK(launch_adam_bias_table(nullptr, ctx->cfg.beta1, ctx->cfg.beta2, 1, ADAM_BIAS_TABLE - 1, ctx->adam_bias_table, ADAM_BIAS_TABLE));   // once: the optimizer only looks it up
 	CDM(ctx->d_xform, DELTA_XFORM_FLOATS); CDM(ctx->d_acc, 12); CDM(ctx->d_master, 12); CDM(ctx->d_m1, 12); CDM(ctx->d_m2, 12); CDM(ctx->d_steps, 12); CDM(ctx->d_params, 12);
 	CTXCHECK(reset_delta(ctx, 0));
 	if (cudaMallocHost((void**)&ctx->h_counters, 16 * sizeof(uint32_t)) != cudaSuccess || cudaMallocHost((void**)&ctx->h_scalars, 4 * sizeof(float)) != cudaSuccess) {
@@ -583,8 +586,14 @@ int neus2_optimizer_step(neus2_ctx* ctx, void* stream, float loss_scale) {
 	++ctx->adam_step;
 	stage_begin(ctx, ST_OPT, (cudaStream_t)stream);
 	const int frozen = ctx->time_frame >= 1 && ctx->training_step < ctx->frozen_steps;   // m_train_canonical = false (testbed.cu:2659-2667)
+	// inside a pipelined train step the kernel also clears what the next step starts from (consumed gradients, the small accumulators,
+	// this step's counters): no zero-fill launches are left between the optimizer and the next step's first kernel
+	const int fuse = ctx->fuse_zero_into_adam ? 1 : 0;
+	uint32_t* const zp[3] = {(uint32_t*)ctx->var_acc, (uint32_t*)ctx->w1row0_acc, ctx->counters};
+	const uint32_t zn[3] = {1u, 64u, 8u};
 	const int rc_ = launch_adam_ema((cudaStream_t)stream, ctx->n_params, ctx->pl.off_grid, loss_scale, ctx->learning_rate, c.beta1, c.beta2, c.epsilon, c.l2_reg,
-	                       c.ema_decay, ctx->adam_step, ctx->grads, ctx->master, ctx->params, ctx->m1, ctx->m2, ctx->steps, ctx->ema, ctx->adam_bias_table, ADAM_BIAS_TABLE, frozen);
+	                       c.ema_decay, ctx->adam_step, ctx->grads, ctx->master, ctx->params, ctx->m1, ctx->m2, ctx->steps, ctx->ema, ctx->adam_bias_table, ADAM_BIAS_TABLE, frozen,
+	                       fuse, zp, zn);
 	if (rc_ == 0 && ctx->use_delta) CHECK(delta_optimizer_step(ctx, (cudaStream_t)stream, loss_scale));   // m_global_move.trainer->optimizer_step (testbed_nerf.cu:3506-3508)
 	stage_end(ctx, ST_OPT, (cudaStream_t)stream);
 	return rc_;
@@ -707,9 +716,9 @@ int neus2_train_step_begin(neus2_ctx* ctx, void* stream_, uint32_t rank, uint32_
 	const uint32_t R = plan.R, n_local = plan.n_local, max_inference = plan.max_inference, n_rays_total = plan.n_rays_total;
 	const uint32_t rows_local = ctx->B_local;
 	bool have_samples = false;
+	if (ctx->aux_pending) { CUDA_CHECK(cudaStreamWaitEvent(stream, ctx->ev_gen_done, 0)); ctx->aux_pending = false; }
 	if (ctx->prefetched) {
 		// step k-1 generated samples ahead of time on the aux stream; they are this step's iff nothing they depend on changed
-		CUDA_CHECK(cudaStreamWaitEvent(stream, ctx->ev_gen_done, 0));
 		ctx->prefetched = false;
 		if (c.prefetch_next_samples && pre_zeroed && !ctx->step_density_updated && ctx->prefetch_epoch == ctx->state_epoch && !memcmp(&plan, &ctx->prefetch_plan, sizeof(plan))) {
 			ctx->counters_cur ^= 1;
@@ -797,7 +806,16 @@ int neus2_train_step_end(neus2_ctx* ctx, void* stream_, const uint32_t* counts_g
 	const neus2_config& c = ctx->cfg;
 	const bool get_loss_scalar = ctx->training_step % 16 == 0;                           // testbed.cu:2714
 	const bool pipelined = ctx->step_pipelined;
-	if (!ctx->optimizer_done) CHECK(neus2_optimizer_step(ctx, stream_, c.loss_scale));   // testbed_nerf.cu:3503-3505
+	// single-GPU pipelined step: our own Adam kernel runs next and also clears what the next step starts from
+	static int no_fused_zero = -1;   // NEUS2_NO_FUSED_ZERO=1: A/B switch (zero-fill launches behind the optimizer instead)
+	if (no_fused_zero < 0) { const char* e = getenv("NEUS2_NO_FUSED_ZERO"); no_fused_zero = e ? atoi(e) : 0; }
+	const bool fused_zero = pipelined && c.world_size == 1 && !ctx->optimizer_done && !no_fused_zero;
+	if (!ctx->optimizer_done) {
+		ctx->fuse_zero_into_adam = fused_zero;
+		const int rc_opt = neus2_optimizer_step(ctx, stream_, c.loss_scale);            // testbed_nerf.cu:3503-3505
+		ctx->fuse_zero_into_adam = false;
+		CHECK(rc_opt);
+	}
 	ctx->optimizer_done = false;
 	if (!pipelined) {
 		if (get_loss_scalar) CHECK(enqueue_loss_scalars(ctx, stream));
@@ -810,10 +828,12 @@ int neus2_train_step_end(neus2_ctx* ctx, void* stream_, const uint32_t* counts_g
 	}
 	// While the host waits for the read-back and prepares the next step, the GPU already zero-fills what the next step starts from
 	// (42 MB of gradients + per-ray scratch): stream-ordered behind the optimizer and, data-parallel, behind the peers' barrier.
-	CHECK(zero_step_scratch(ctx, stream, ctx->max_rays));
-	CUDA_CHECK(cudaMemsetAsync(ctx->grads, 0, ctx->n_params * sizeof(float), stream));
-	CUDA_CHECK(cudaMemsetAsync(ctx->var_acc, 0, sizeof(float), stream));
-	CUDA_CHECK(cudaMemsetAsync(ctx->w1row0_acc, 0, 64 * sizeof(float), stream));
+	if (!fused_zero) {
+		CHECK(zero_step_scratch(ctx, stream, ctx->max_rays));
+		CUDA_CHECK(cudaMemsetAsync(ctx->grads, 0, ctx->n_params * sizeof(float), stream));
+		CUDA_CHECK(cudaMemsetAsync(ctx->var_acc, 0, sizeof(float), stream));
+		CUDA_CHECK(cudaMemsetAsync(ctx->w1row0_acc, 0, 64 * sizeof(float), stream));
+	}   // else: gradients / accumulators / counters were cleared by the Adam kernel, the per-ray loss arrays are cleared on the aux stream below
 	ctx->scratch_zeroed = true;
 	if (pipelined) {
 		stage_end(ctx, ST_STEP, stream);
@@ -866,8 +886,20 @@ int neus2_train_step_end(neus2_ctx* ctx, void* stream_, const uint32_t* counts_g
 			CHECK(launch_gen(ctx, ctx->aux_stream, ctx->prefetch_plan, next_counters));
 			stage_end_set(ctx, ctx->ev_set ^ 1, ST_GEN, ctx->aux_stream);
 			CUDA_CHECK(cudaEventRecord(ctx->ev_gen_done, ctx->aux_stream));
+			ctx->aux_pending = true;
 			ctx->prefetched = true; ctx->prefetch_epoch = ctx->state_epoch;
 		}
+	}
+	if (fused_zero) {
+		// The per-ray loss arrays were last read by the loss-scalar reduction right behind the loss kernel.  They are cleared on the aux
+		// stream, BEHIND the prefetched sample generation: memset kernels in front of it would sit in the queue until the persistent
+		// forward+backward kernel frees an SM and hold the generation kernels back with them (measured: +2 % per step).
+		CUDA_CHECK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_counts, 0));
+		CUDA_CHECK(cudaMemsetAsync(ctx->loss, 0, sizeof(float) * ctx->max_rays, ctx->aux_stream));
+		CUDA_CHECK(cudaMemsetAsync(ctx->ek_loss, 0, sizeof(float) * ctx->max_rays, ctx->aux_stream));
+		CUDA_CHECK(cudaMemsetAsync(ctx->mask_loss, 0, sizeof(float) * ctx->max_rays, ctx->aux_stream));
+		CUDA_CHECK(cudaEventRecord(ctx->ev_gen_done, ctx->aux_stream));
+		ctx->aux_pending = true;
 	}
 	s.rays_per_batch_next = ctx->rays_per_batch;
 	if (stats) *stats = s;

@@ -26,8 +26,8 @@ int launch_compute_loss(cudaStream_t stream, uint32_t n_rays_local, uint32_t n_r
                         float* loss_output, float* ek_loss_output, float* mask_loss_output, uint32_t* out_counter);
 
 int launch_adam_ema(cudaStream_t stream, uint64_t n, uint64_t n_matrix, float loss_scale, float lr, float beta1, float beta2, float eps, float l2_reg,
-                    float ema_decay, uint32_t ema_step, const float* grads, float* master, __half* params, float* m1, float* m2, uint32_t* steps, __half* ema,
-                    float* bias_table, uint32_t bias_table_size, int frozen);
+                    float ema_decay, uint32_t ema_step, float* grads, float* master, __half* params, float* m1, float* m2, uint32_t* steps, __half* ema,
+                    float* bias_table, uint32_t bias_table_size, int frozen, int zero_grads, uint32_t* const zero_ptrs[3], const uint32_t zero_counts[3]);
 // table[k] = sqrt(1 - beta2^k) / (1 - beta1^k) for k in [first, last] (api.cu: compiled with FMA contraction like the reference's adam_step)
 int launch_adam_bias_table(cudaStream_t stream, float beta1, float beta2, uint32_t first, uint32_t last, float* bias_table, uint32_t bias_table_size);
 

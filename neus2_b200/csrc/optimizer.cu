@@ -10,11 +10,14 @@
 
 struct AdamHyper { float loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, ema_debias_old, ema_debias_new;
                    uint32_t cur_step; const float* bias_table; uint32_t bias_table_size;
-                   int frozen; };   // frozen: optimize_canonical_params = false (adam.h:92-94) -- every parameter returns early, only the EMA moves
+                   int frozen;      // frozen: optimize_canonical_params = false (adam.h:92-94) -- every parameter returns early, only the EMA moves
+                   int zero_grads; };   // also clear the gradients that were consumed (the next step starts from zeros; only touched quads are rewritten)
+// Small accumulators of the step that the next step expects cleared (variance / W1-row-0 sums, the step's counters): block 0 clears them.
+struct AdamZero { uint32_t* p[3]; uint32_t n[3]; };
 
 // Bias correction of adam_step (adam.h:149-150) for a parameter whose private step counter reads `cs`:
 // sqrt(1 - beta2^cs) / (1 - beta1^cs).  Two powf per parameter made the kernel issue-bound (83 % issue-active, 40 % of HBM peak
-// in the first ncu capture), so the factor is looked up in a table that k_adam_bias_table (api.cu) extends by one entry per step;
+// in the first ncu capture), so the factor is looked up in a table that k_adam_bias_table (api.cu) fills once when the context is created;
 // the inline evaluation below is only the fallback for counters beyond the table (> 2^20 steps).
 __device__ __forceinline__ float adam_bias_factor(const AdamHyper& h, uint32_t cs) {
 	return sqrtf(1 - powf(h.beta2, (float)cs)) / (1 - powf(h.beta1, (float)cs));
@@ -45,13 +48,18 @@ __device__ __forceinline__ __half adam_one(bool is_matrix, float g_raw, const Ad
 // 4 consecutive parameters per thread (n and n_matrix are multiples of 4): 16-byte gradient loads; the optimizer state of an
 // untouched quad (the common case for the sparse hash-grid levels) is never read.
 __global__ void __launch_bounds__(256)
-k_adam_ema(uint64_t n4, uint64_t n_matrix4, AdamHyper h, const float* __restrict__ grads,
+k_adam_ema(uint64_t n4, uint64_t n_matrix4, AdamHyper h, float* __restrict__ grads,
            float* __restrict__ master, __half* __restrict__ params, float* __restrict__ m1, float* __restrict__ m2,
-           uint32_t* __restrict__ steps, __half* __restrict__ ema) {
+           uint32_t* __restrict__ steps, __half* __restrict__ ema, AdamZero z) {
+	if (h.zero_grads && blockIdx.x == 0) {
+		#pragma unroll
+		for (int a = 0; a < 3; ++a) for (uint32_t i = threadIdx.x; i < z.n[a]; i += blockDim.x) z.p[a][i] = 0u;
+	}
 	const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (q >= n4) return;
 	const bool is_matrix = q < n_matrix4;
 	const float4 g4 = reinterpret_cast<const float4*>(grads)[q];
+	if (h.zero_grads && (g4.x != 0.f || g4.y != 0.f || g4.z != 0.f || g4.w != 0.f)) reinterpret_cast<float4*>(grads)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
 	uint2 pw = reinterpret_cast<const uint2*>(params)[q];
 	__half* ph = reinterpret_cast<__half*>(&pw);
 	const float g[4] = {g4.x, g4.y, g4.z, g4.w};
@@ -88,16 +96,17 @@ k_adam_ema(uint64_t n4, uint64_t n_matrix4, AdamHyper h, const float* __restrict
 }
 
 int launch_adam_ema(cudaStream_t stream, uint64_t n, uint64_t n_matrix, float loss_scale, float lr, float beta1, float beta2, float eps, float l2_reg,
-                    float ema_decay, uint32_t ema_step, const float* grads, float* master, __half* params, float* m1, float* m2, uint32_t* steps, __half* ema,
-                    float* bias_table, uint32_t bias_table_size, int frozen) {
+                    float ema_decay, uint32_t ema_step, float* grads, float* master, __half* params, float* m1, float* m2, uint32_t* steps, __half* ema,
+                    float* bias_table, uint32_t bias_table_size, int frozen, int zero_grads, uint32_t* const zero_ptrs[3], const uint32_t zero_counts[3]) {
 	const float ema_debias_old = 1 - (float)pow((double)ema_decay, (double)(ema_step - 1));
 	const float ema_debias_new = 1.0f / (1 - (float)pow((double)ema_decay, (double)ema_step));
 	if (n % 4 != 0 || n_matrix % 4 != 0) { neus_set_error("parameter counts must be multiples of 4", __FILE__, __LINE__); return -1; }
-	AdamHyper h = {loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, ema_debias_old, ema_debias_new, ema_step, bias_table, bias_table_size, frozen};
-	if (bias_table && ema_step < bias_table_size) { if (launch_adam_bias_table(stream, beta1, beta2, ema_step, ema_step, bias_table, bias_table_size)) return -1; }
+	AdamHyper h = {loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, ema_debias_old, ema_debias_new, ema_step, bias_table, bias_table_size, frozen, zero_grads};
+	AdamZero z = {};
+	if (zero_grads) for (int a = 0; a < 3; ++a) { z.p[a] = zero_ptrs ? zero_ptrs[a] : nullptr; z.n[a] = (zero_ptrs && zero_ptrs[a]) ? zero_counts[a] : 0u; }
 	const uint64_t n4 = n / 4;
 	const uint32_t blocks = (uint32_t)((n4 + 255) / 256);
-	k_adam_ema<<<blocks, 256, 0, stream>>>(n4, n_matrix / 4, h, grads, master, params, m1, m2, steps, ema);
+	k_adam_ema<<<blocks, 256, 0, stream>>>(n4, n_matrix / 4, h, grads, master, params, m1, m2, steps, ema, z);
 	COUNT_LAUNCH(1);
 	CUDA_CHECK(cudaGetLastError());
 	return 0;
@@ -171,7 +180,6 @@ int launch_adam_ema_p2p(cudaStream_t stream, uint64_t n, uint64_t n_matrix, uint
 	if (n % 4 != 0 || n_matrix % 4 != 0) { neus_set_error("parameter counts must be multiples of 4", __FILE__, __LINE__); return -1; }
 	if (world < 1 || world > NEUS2_MAX_PEERS || rank >= world) { neus_set_error("bad rank / world size for the sharded optimizer", __FILE__, __LINE__); return -1; }
 	AdamHyper h = {loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, ema_debias_old, ema_debias_new, ema_step, bias_table, bias_table_size, frozen};
-	if (bias_table && ema_step < bias_table_size) { if (launch_adam_bias_table(stream, beta1, beta2, ema_step, ema_step, bias_table, bias_table_size)) return -1; }
 	uint64_t q0, q1;
 	optimizer_shard(n / 4, rank, world, &q0, &q1);
 	PeerPtrs pp;
