@@ -247,6 +247,11 @@ int neus2_set_density_grid(neus2_ctx* ctx, void* stream, const float* density_gr
 int neus2_next_frame(neus2_ctx* ctx, void* stream, float after_learning_rate, uint32_t frozen_steps);
 int neus2_get_time_frame(const neus2_ctx* ctx, uint32_t* current_training_time_frame, float* learning_rate);
 
+/* "incremental_reinit_sdf_mlp" (src/testbed.cu:2065-2068; NerfNetwork::initialize_sdf_mlp_params, nerf_network.h:888-908): every
+ * incremental_reinit_sdf_mlp_iters frames the fp32 master copy of the SDF MLP goes back to its geometric initialisation
+ * (sdf_mlp_weights: 64*32 + 16*64 floats as for neus2_init_params, or NULL for the built-in generator).  Call after neus2_next_frame. */
+int neus2_reinit_sdf_mlp(neus2_ctx* ctx, void* stream, const float* sdf_mlp_weights);
+
 /* ---- global rigid motion of dynamic scenes ("predict_global_movement": true) -------------------------------
  * The reference keeps an ACCUMULATED rotation (3x3) + transition applied to every ray (global_movement_with_rotation_6d,
  * src/testbed_nerf.cu:194-213, 1377-1387, 2287-2294) and, for frames >= 1, a DeltaNetwork (include/neural-graphics-primitives/

@@ -292,6 +292,14 @@ class Context:
         check(self._lib.neus2_delta_gradients_device(self._h, C.byref(a)))
         return torch.as_tensor(_DevArray(a.value, (12,), "<f4", None), device=f"cuda:{self.device}")
 
+    def reinit_sdf_mlp(self, sdf_mlp_weights=None, stream=None):
+        """hyperparams.incremental_reinit_sdf_mlp: the fp32 master copy of the SDF MLP goes back to its geometric initialisation."""
+        w = None
+        if sdf_mlp_weights is not None:
+            w = np.ascontiguousarray(sdf_mlp_weights, dtype=np.float32)
+            assert w.size == 64 * 32 + 16 * 64
+        check(self._lib.neus2_reinit_sdf_mlp(self._h, _stream(stream), w.ctypes.data_as(C.c_void_p) if w is not None else None))
+
     def time_frame(self):
         tf, lr = C.c_uint32(), C.c_float()
         check(self._lib.neus2_get_time_frame(self._h, C.byref(tf), C.byref(lr)))

@@ -481,6 +481,34 @@ int neus2_get_params(neus2_ctx* ctx, float* master_host, uint64_t n) {
 	return 0;
 }
 
+// geometric init of the SDF MLP (geometry_init_save_weights.py:318-331) with our own generator (the reference's weight file is not in the snapshot)
+static void geometric_init_sdf_mlp(float* w0 /*[64][32]*/, float* w1 /*[16][64]*/) {
+	Pcg32 g{0x9e0u};
+	auto normal = [&]() {
+		float u1 = g.next_float(), u2 = g.next_float();
+		if (u1 < 1e-7f) u1 = 1e-7f;
+		return std::sqrt(-2.0f * std::log(u1)) * std::cos(6.283185307179586f * u2);
+	};
+	for (uint32_t o = 0; o < 64; ++o) for (uint32_t i = 0; i < 32; ++i) w0[o * 32 + i] = i < 3 ? normal() * (std::sqrt(2.0f) / std::sqrt(64.0f)) : 0.f;
+	for (uint32_t i = 0; i < 16 * 64; ++i) w1[i] = std::sqrt(3.14159265358979f) / std::sqrt(64.0f) + 1e-5f * normal();
+}
+
+// NerfNetwork::initialize_sdf_mlp_params (nerf_network.h:888-908), used by "incremental_reinit_sdf_mlp" every
+// incremental_reinit_sdf_mlp_iters frames (src/testbed.cu:2065-2068): the fp32 MASTER copy of the SDF MLP is reset to its geometric
+// initialisation; like the reference, the fp16 training / inference copies are left alone and follow at the next optimizer step.
+int neus2_reinit_sdf_mlp(neus2_ctx* ctx, void* stream_, const float* sdf_mlp_weights_host) {
+	cudaStream_t stream = (cudaStream_t)stream_;
+	CUDA_CHECK(cudaSetDevice(ctx->device));
+	const ParamLayout& pl = ctx->pl;
+	if (pl.off_w1 != pl.off_w0 + 64 * 32) FAIL("unexpected SDF-MLP layout");
+	std::vector<float> w(64 * 32 + 16 * 64);
+	if (sdf_mlp_weights_host) memcpy(w.data(), sdf_mlp_weights_host, w.size() * sizeof(float));
+	else geometric_init_sdf_mlp(w.data(), w.data() + 64 * 32);
+	CUDA_CHECK(cudaMemcpyAsync(ctx->master + pl.off_w0, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+	CUDA_CHECK(cudaStreamSynchronize(stream));
+	return 0;
+}
+
 int neus2_init_params(neus2_ctx* ctx, const float* sdf_mlp_weights_host) {
 	const ParamLayout& pl = ctx->pl;
 	std::vector<float> p(ctx->n_params, 0.f);
@@ -498,15 +526,7 @@ int neus2_init_params(neus2_ctx* ctx, const float* sdf_mlp_weights_host) {
 	if (sdf_mlp_weights_host) {
 		memcpy(&p[pl.off_w0], sdf_mlp_weights_host, sizeof(float) * (64 * 32 + 16 * 64));
 	} else {
-		// geometric init (geometry_init_save_weights.py:318-331) with our own generator (the reference file is not in the snapshot)
-		Pcg32 g{0x9e0u};
-		auto normal = [&]() {
-			float u1 = g.next_float(), u2 = g.next_float();
-			if (u1 < 1e-7f) u1 = 1e-7f;
-			return std::sqrt(-2.0f * std::log(u1)) * std::cos(6.283185307179586f * u2);
-		};
-		for (uint32_t o = 0; o < 64; ++o) for (uint32_t i = 0; i < 32; ++i) p[pl.off_w0 + o * 32 + i] = i < 3 ? normal() * (std::sqrt(2.0f) / std::sqrt(64.0f)) : 0.f;
-		for (uint32_t i = 0; i < 16 * 64; ++i) p[pl.off_w1 + i] = std::sqrt(3.14159265358979f) / std::sqrt(64.0f) + 1e-5f * normal();
+		geometric_init_sdf_mlp(&p[pl.off_w0], &p[pl.off_w1]);
 	}
 	xavier(&p[pl.off_c0], 64, 48); xavier(&p[pl.off_c1], 64, 64); xavier(&p[pl.off_c2], 16, 64);
 	{   // grid: generate_random_uniform(-1e-4, 1e-4) (grid.h:2375-2380; random.h:67-99)

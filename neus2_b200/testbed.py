@@ -73,6 +73,8 @@ class Testbed:
         self.predict_global_movement = False
         self.predict_global_movement_training_step = 50
         self.finetune_global_movement = True
+        self.incremental_reinit_sdf_mlp = False
+        self.incremental_reinit_sdf_mlp_iters = 10
         self.after_learning_rate = 0.0
         self.current_training_time_frame = 0
         self.all_training_time_frame = 1
@@ -108,6 +110,8 @@ class Testbed:
         if not self.predict_global_movement:
             self.predict_global_movement_training_step = 0                                      # :2131-2133
         self.finetune_global_movement = bool(hp.get("finetune_global_movement", True))          # :2125
+        self.incremental_reinit_sdf_mlp = bool(hp.get("incremental_reinit_sdf_mlp", False))
+        self.incremental_reinit_sdf_mlp_iters = max(1, int(hp.get("incremental_reinit_sdf_mlp_iters", 10)))
         leaf = cfg_json.get("optimizer", {})
         while "nested" in leaf:
             leaf = leaf["nested"]
@@ -187,6 +191,8 @@ class Testbed:
         if self.predict_global_movement:
             ctx.begin_global_movement()
         ctx.next_frame(after_learning_rate=self.after_learning_rate, frozen_steps=self.predict_global_movement_training_step)
+        if self.incremental_reinit_sdf_mlp and self.current_training_time_frame % self.incremental_reinit_sdf_mlp_iters == 0:
+            ctx.reinit_sdf_mlp()                                      # testbed.cu:2065-2068
         return True
 
     def change_to_frame(self, i):

@@ -203,3 +203,36 @@ def test_global_movement_recovers_a_rigid_motion(tmp_path):
     tb.save_transform(os.path.join(str(tmp_path), "transform.txt"))
     rows = [l.split() for l in open(os.path.join(str(tmp_path), "transform.txt")).read().strip().splitlines()]
     assert len(rows) == 4 and np.allclose(np.array(rows[:3], dtype=np.float32), R, atol=1e-6)
+
+
+def test_reinit_sdf_mlp_resets_the_master_copy_only():
+    """incremental_reinit_sdf_mlp (src/testbed.cu:2065-2068): the fp32 master of the SDF MLP returns to its geometric initialisation, the
+    fp16 copies follow at the next optimizer step (NerfNetwork::initialize_sdf_mlp_params writes params_full_precision only)."""
+    import torch
+    import neus2_b200 as N
+    c = N.Context(N.default_config(batch_size=1 << 14))
+    try:
+        c.init_params()
+        init = c.get_params().copy()
+        lay = c.layout
+        a, b = lay["W0"], lay["C0"]                                      # the SDF MLP block [W0 | W1]
+        assert b - a == 64 * 32 + 16 * 64
+        moved = init.copy()
+        moved[a:b] += 0.25
+        moved[b:b + 100] += 0.125
+        c.set_params(moved)
+        half_before = c.buffers()[1].clone()
+        c.reinit_sdf_mlp()
+        after = c.get_params()
+        assert np.array_equal(after[a:b], init[a:b])                     # SDF MLP master: geometric init again
+        assert np.array_equal(after[b:], moved[b:])                      # nothing else moved
+        assert torch.equal(c.buffers()[1], half_before)                  # fp16 copy untouched until the optimizer steps
+        c.buffers()[3].zero_()
+        c.optimizer_step(128.0)                                          # matrix parameters always step (L2 term): fp16 follows the master
+        w16 = c.buffers()[1][a:b].float().cpu().numpy()
+        assert np.abs(w16 - init[a:b]).max() < 2e-3
+        custom = np.linspace(-1, 1, b - a).astype(np.float32)
+        c.reinit_sdf_mlp(custom)
+        assert np.array_equal(c.get_params()[a:b], custom)
+    finally:
+        c.close()

@@ -141,6 +141,9 @@ def test_testbed_global_movement_hyperparams():
     tb.reload_network_from_json({"hyperparams": {"predict_global_movement": True, "predict_global_movement_training_step": 50,
                                                  "finetune_global_movement": False, "next_frame_max_training_step": 1300}})
     assert tb.predict_global_movement_training_step == 50 and not tb.finetune_global_movement and tb.next_frame_max_training_step == 1300
+    assert not tb.incremental_reinit_sdf_mlp and tb.incremental_reinit_sdf_mlp_iters == 10
+    tb.reload_network_from_json({"hyperparams": {"incremental_reinit_sdf_mlp": True, "incremental_reinit_sdf_mlp_iters": 3}})
+    assert tb.incremental_reinit_sdf_mlp and tb.incremental_reinit_sdf_mlp_iters == 3
     tb.reload_network_from_json({"hyperparams": {"predict_global_movement": False, "predict_global_movement_training_step": 50}})
     assert tb.predict_global_movement_training_step == 0                       # :2131-2133: no frozen phase without prediction
     # the host-side 6d -> matrix used by save_transform agrees with the oracle's
