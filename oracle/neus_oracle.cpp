@@ -750,7 +750,10 @@ void orc_net_backward(const NetCfg* cp, uint32_t n, const float* coords, const h
 // DeltaNetwork: the per-frame rigid motion of dynamic scenes (include/neural-graphics-primitives/transform_network.h:23-480,
 // common_operation.cuh:37-160, 416-470, 551-580, 788-840).  Parameters (half, with an fp32 master in their own Trainer):
 // transition[4] (3 used) then rotation[8] (6 used, the "6d" representation: two 3-vectors, Gram-Schmidt -> columns of R).
-// ngp layer => parity unpinned; FMA contraction written the way nvcc fuses the Eigen expressions.
+// PINNED against the reference's own source: common_operation.cuh compiled as host code from where it lies (oracle/Makefile.ref ->
+// oracle/_ref/libref_delta_host.so, stand-in headers in oracle/ref_host_shim/); tests/test_golden_delta.py checks this restatement against
+// golden vectors frozen from it (tests/golden/delta_reference.npz): matrices / positions to a few 1e-7, per-sample half gradients and the
+// accumulated halves to the bit except on rounding boundaries.  FMA contraction is written the way nvcc fuses the Eigen expressions.
 // ----------------------------------------------------------------------------
 struct DeltaXform { float R[9]; float t[3]; float tmo[3]; float off[3]; };   // R row-major
 
@@ -861,6 +864,12 @@ void orc_delta_backward(uint32_t n, const float* coords_in, const float* dL_dpos
 	for (int k = 0; k < 12; ++k) grad[k] = 0.f;
 	for (int k = 0; k < 3; ++k) grad[k] = rh((float)acc[k]);
 	for (int k = 0; k < 6; ++k) grad[4 + k] = rh((float)acc[3 + k]);
+}
+// per-sample outputs of the same (what the reference's add_loss_to_rotation_6d_each writes before the reductions):
+// out[n][9] = [d transition 3 | d rotation-6d 6] as (float)half
+void orc_delta_backward_each(uint32_t n, const float* coords_in, const float* dL_dpos, const h16* rot6, const h16* trans, const float* off, float* out) {
+	DeltaXform x; delta_xform(rot6, trans, off, x);
+	for (uint32_t i = 0; i < n; ++i) delta_backward_sample(rot6, x, dL_dpos + (size_t)i * 3, coords_in + (size_t)i * 7, out + (size_t)i * 9);
 }
 // backward_impl with m_use_delta && m_train_delta: the network runs on the deformed coordinates.
 void orc_net_backward_delta(const NetCfg* cp, uint32_t n, const float* coords, const h16* params, const h16* dL_dout,

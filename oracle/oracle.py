@@ -319,6 +319,17 @@ def delta_backward(coords, dL_dpos, rot6, trans, first_frame_offset=None):
     return grad
 
 
+def delta_backward_each(coords, dL_dpos, rot6, trans, first_frame_offset=None):
+    """Per-sample DeltaNetwork gradients [n][9] = [d transition 3 | d rotation-6d 6], each as (float)half (before the batch sum)."""
+    coords = np.ascontiguousarray(coords, dtype=np.float32)
+    dL_dpos = np.ascontiguousarray(dL_dpos, dtype=np.float32)
+    off = None if first_frame_offset is None else np.ascontiguousarray(first_frame_offset, dtype=np.float32)
+    out = np.zeros((coords.shape[0], 9), dtype=np.float32)
+    lib().orc_delta_backward_each(C.c_uint32(coords.shape[0]), _p(coords, f32p), _p(dL_dpos, f32p), _p(_h(rot6), h16p), _p(_h(trans), h16p),
+                                  _p(off, f32p) if off is not None else None, _p(out, f32p))
+    return out
+
+
 def net_backward_delta(cfg, coords, params_h, dL_dout_h, indeed_batch_size, rot6, trans, first_frame_offset=None):
     """backward_impl with m_use_delta && m_train_delta: (canonical grads, delta grad[12], dL/d deformed position [n][3])."""
     n = coords.shape[0]

@@ -1,7 +1,7 @@
 """CPU checks of the oracle's DeltaNetwork restatement (include/neural-graphics-primitives/transform_network.h:23-480,
 common_operation.cuh:37-160, 416-470, 551-580, 788-840): the 6d-rotation forward against a float64 reference, the hand-derived
-backward (gradient_rotation_matrix_to_6d) against torch autograd, and the accumulation of frame-to-frame motions.  The ngp layer
-cannot be compiled here (Eigen/Core is missing), so this is "parity unpinned": the checks pin the MATH."""
+backward (gradient_rotation_matrix_to_6d) against torch autograd, and the accumulation of frame-to-frame motions.  These pin the
+MATH; the pin against the reference's own source is tests/test_golden_delta.py."""
 import numpy as np
 import pytest
 import torch
