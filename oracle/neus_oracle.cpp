@@ -1100,6 +1100,15 @@ static inline void normalize3(const float v[3], float out[3]) {
 	float n = sqrtf(n2);
 	if (n2 > 0) { out[0] = v[0] / n; out[1] = v[1] / n; out[2] = v[2] / n; } else { out[0] = v[0]; out[1] = v[1]; out[2] = v[2]; }
 }
+// thin exports of the helpers above, for the pin against the reference's own headers (tests/test_golden_ngp_helpers.py)
+extern "C" void orc_ray_intersect(const float* aabb6, const float* o, const float* d, float* out2);
+extern "C" int orc_aabb_contains(const float* aabb6, const float* p);
+extern "C" void orc_image_pos(const float* xy, int w, int h, int* out2) { image_pos(xy, w, h, &out2[0], &out2[1]); }
+extern "C" void orc_read_rgba(const Dataset* ds, uint32_t img, int px, int py, float* out4) { read_rgba(*ds, img, px, py, out4); }
+extern "C" void orc_make_ray(const Dataset* ds, uint32_t img, const float* xy, float* out6) {
+	Ray r; make_ray(*ds, img, xy, r);
+	for (int k = 0; k < 3; ++k) { out6[k] = r.o[k]; out6[3 + k] = r.d[k]; }
+}
 // global_movement_with_rotation_6d (:194-213): o = R o + t, d = R d; R (9) and t (3) stored in half.
 static inline void global_move(const h16* rot, const h16* trans, float o[3], float d[3]) {
 	float R[9]; for (int k = 0; k < 9; ++k) R[k] = h2f(rot[k]);
@@ -1131,6 +1140,8 @@ static inline void ray_intersect(const float bmin[3], const float bmax[3], const
 static inline bool aabb_contains(const float bmin[3], const float bmax[3], const float p[3]) {
 	return p[0] >= bmin[0] && p[0] <= bmax[0] && p[1] >= bmin[1] && p[1] <= bmax[1] && p[2] >= bmin[2] && p[2] <= bmax[2];
 }
+void orc_ray_intersect(const float* aabb6, const float* o, const float* d, float* out2) { ray_intersect(aabb6, aabb6 + 3, o, d, &out2[0], &out2[1]); }
+int orc_aabb_contains(const float* aabb6, const float* p) { return aabb_contains(aabb6, aabb6 + 3, p) ? 1 : 0; }
 static inline float warp_dt(float dt) {   // :484-487
 	float max_stepsize = MIN_CONE_STEPSIZE() * (1 << (NERF_CASCADES - 1));
 	return (dt - MIN_CONE_STEPSIZE()) / (max_stepsize - MIN_CONE_STEPSIZE());

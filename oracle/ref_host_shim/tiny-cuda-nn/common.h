@@ -41,7 +41,18 @@ inline __half& operator-=(__half& a, const __half& b) { a = a - b; return a; }
 inline float __expf(float x) { return expf(x); }
 template <typename T> inline T atomicAdd(T* p, T v) { T old = *p; *p = old + v; return old; }
 
+struct float2 { float x, y; }; struct float3 { float x, y, z; }; struct float4 { float x, y, z, w; };
+struct __half2 { __half x, y; };
+#define TCNN_HOST_DEVICE
+#define TCNN_NAMESPACE_BEGIN namespace tcnn {
+#define TCNN_NAMESPACE_END }
+inline void sincosf_(float x, float* s, float* c) { *s = sinf(x); *c = cosf(x); }
 namespace tcnn {
+using network_precision_t = __half;
+template <typename T> inline void host_device_swap(T& a, T& b) { T c(a); a = b; b = c; }
+template <typename T> inline T clamp(T v, T lo, T hi) { return v < lo ? lo : (hi < v ? hi : v); }   // tcnn common.h:250 (same comparison order as the oracle's clampf)
+template <typename T> struct GPUMemory;   // only named in declarations
+template <typename T, uint32_t N> struct vector_t { T data[N]; T& operator[](uint32_t i) { return data[i]; } const T& operator[](uint32_t i) const { return data[i]; } };
 template <typename T>
 struct MatrixView {   // same indexing as tcnn::MatrixView: element (i, j) at data[i * stride_i + j * stride_j]
 	T* data = nullptr; uint32_t stride_i = 0, stride_j = 0;
@@ -53,68 +64,5 @@ struct MatrixView {   // same indexing as tcnn::MatrixView: element (i, j) at da
 template <typename T> inline T logistic(const T x) { return T(1.0f / (1.0f + expf(-(float)x))); }
 }
 
-// ---- the subset of Eigen the header uses ------------------------------------------------------------------------------------
-namespace Eigen {
-enum { ColMajor = 0, RowMajor = 1 };
-struct Vector3f {
-	float v[3];
-	Vector3f() : v{0.f, 0.f, 0.f} {}
-	Vector3f(float a, float b, float c) : v{a, b, c} {}
-	float& operator[](int i) { return v[i]; }
-	const float& operator[](int i) const { return v[i]; }
-	float dot(const Vector3f& o) const { return v[0] * o.v[0] + v[1] * o.v[1] + v[2] * o.v[2]; }
-	float squaredNorm() const { return dot(*this); }
-	float norm() const { return std::sqrt(squaredNorm()); }
-	Vector3f cross(const Vector3f& o) const { return Vector3f(v[1] * o.v[2] - v[2] * o.v[1], v[2] * o.v[0] - v[0] * o.v[2], v[0] * o.v[1] - v[1] * o.v[0]); }
-	Vector3f operator+(const Vector3f& o) const { return Vector3f(v[0] + o.v[0], v[1] + o.v[1], v[2] + o.v[2]); }
-	Vector3f operator-(const Vector3f& o) const { return Vector3f(v[0] - o.v[0], v[1] - o.v[1], v[2] - o.v[2]); }
-	Vector3f operator*(float s) const { return Vector3f(v[0] * s, v[1] * s, v[2] * s); }
-	Vector3f operator/(float s) const { return Vector3f(v[0] / s, v[1] / s, v[2] / s); }
-	Vector3f& operator+=(const Vector3f& o) { for (int k = 0; k < 3; ++k) v[k] += o.v[k]; return *this; }
-	Vector3f& operator-=(const Vector3f& o) { for (int k = 0; k < 3; ++k) v[k] -= o.v[k]; return *this; }
-	Vector3f normalized() const { const float z = squaredNorm(); return z > 0.f ? *this / std::sqrt(z) : *this; }   // Eigen: v / sqrt(squaredNorm) when > 0
-	static Vector3f Constant(float c) { return Vector3f(c, c, c); }
-	static Vector3f Ones() { return Constant(1.f); }
-	static Vector3f Zero() { return Constant(0.f); }
-};
-inline Vector3f operator*(float s, const Vector3f& a) { return a * s; }
-
-template <int Order>
-struct Mat33 {
-	float d[9];
-	Mat33() { for (float& x : d) x = 0.f; }
-	template <int O2> Mat33(const Mat33<O2>& o) { for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) (*this)(r, c) = o(r, c); }
-	float& operator()(int r, int c) { return d[Order == RowMajor ? r * 3 + c : c * 3 + r]; }
-	const float& operator()(int r, int c) const { return d[Order == RowMajor ? r * 3 + c : c * 3 + r]; }
-	float* data() { return d; }
-	const float* data() const { return d; }
-	struct Comma {   // Eigen's comma initialiser fills row by row whatever the storage order
-		Mat33& m; int k;
-		Comma& operator,(float x) { m(k / 3, k % 3) = x; ++k; return *this; }
-	};
-	Comma operator<<(float x) { (*this)(0, 0) = x; return Comma{*this, 1}; }
-	Mat33 inverse() const {   // cofactor formula, as Eigen's fixed-size 3x3 inverse
-		const Mat33& a = *this;
-		Mat33 c;
-		c(0, 0) = a(1, 1) * a(2, 2) - a(1, 2) * a(2, 1); c(0, 1) = a(0, 2) * a(2, 1) - a(0, 1) * a(2, 2); c(0, 2) = a(0, 1) * a(1, 2) - a(0, 2) * a(1, 1);
-		c(1, 0) = a(1, 2) * a(2, 0) - a(1, 0) * a(2, 2); c(1, 1) = a(0, 0) * a(2, 2) - a(0, 2) * a(2, 0); c(1, 2) = a(0, 2) * a(1, 0) - a(0, 0) * a(1, 2);
-		c(2, 0) = a(1, 0) * a(2, 1) - a(1, 1) * a(2, 0); c(2, 1) = a(0, 1) * a(2, 0) - a(0, 0) * a(2, 1); c(2, 2) = a(0, 0) * a(1, 1) - a(0, 1) * a(1, 0);
-		const float det = a(0, 0) * c(0, 0) + a(0, 1) * c(1, 0) + a(0, 2) * c(2, 0);
-		const float inv = 1.0f / det;
-		for (float& x : c.d) x *= inv;
-		return c;
-	}
-};
-template <int O>
-inline Vector3f operator*(const Mat33<O>& m, const Vector3f& x) {
-	return Vector3f(m(0, 0) * x[0] + m(0, 1) * x[1] + m(0, 2) * x[2], m(1, 0) * x[0] + m(1, 1) * x[1] + m(1, 2) * x[2], m(2, 0) * x[0] + m(2, 1) * x[1] + m(2, 2) * x[2]);
-}
-template <int A, int B>
-inline Mat33<A> operator*(const Mat33<A>& a, const Mat33<B>& b) {
-	Mat33<A> r;
-	for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r(i, j) = a(i, 0) * b(0, j) + a(i, 1) * b(1, j) + a(i, 2) * b(2, j);
-	return r;
-}
-using Matrix3f = Mat33<ColMajor>;
-template <typename Scalar, int Rows, int Cols, int Order = ColMajor> using Matrix = Mat33<Order>;   // only float 3x3 is ever named
-}
+// ---- the subset of Eigen the reference headers use --------------------------------------------------------------------------
+#include <Eigen/Dense>
