@@ -12,6 +12,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <sstream>
+#include <string>
+#include <vector>
 
 #define __global__
 #define __device__
@@ -39,7 +42,24 @@ inline __half operator/(const __half& a, const __half& b) { return __half((float
 inline __half& operator+=(__half& a, const __half& b) { a = a + b; return a; }
 inline __half& operator-=(__half& a, const __half& b) { a = a - b; return a; }
 inline float __expf(float x) { return expf(x); }
-template <typename T> inline T atomicAdd(T* p, T v) { T old = *p; *p = old + v; return old; }
+inline float __frcp_rn(float x) { return 1.0f / x; }
+inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline uint32_t atomicMax(uint32_t* p, uint32_t v) { uint32_t old = *p; if (v > old) *p = v; return old; }
+template <typename T, typename U> inline T atomicAdd(T* p, U v) { T old = *p; *p = old + (T)v; return old; }
+// CUDA's global min / max overloads
+inline float min(float a, float b) { return fminf(a, b); }
+inline float max(float a, float b) { return fmaxf(a, b); }
+inline int min(int a, int b) { return a < b ? a : b; }
+inline int max(int a, int b) { return a > b ? a : b; }
+inline uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
+inline uint32_t max(uint32_t a, uint32_t b) { return a > b ? a : b; }
+inline uint32_t min(uint32_t a, int b) { return min(a, (uint32_t)b); }
+inline uint32_t min(int a, uint32_t b) { return min((uint32_t)a, b); }
+inline uint32_t max(uint32_t a, int b) { return max(a, (uint32_t)b); }
+inline uint32_t max(int a, uint32_t b) { return max((uint32_t)a, b); }
+inline float min(float a, double b) { return fminf(a, (float)b); }
+inline float max(float a, double b) { return fmaxf(a, (float)b); }
 
 struct float2 { float x, y; }; struct float3 { float x, y, z; }; struct float4 { float x, y, z, w; };
 struct __half2 { __half x, y; };
@@ -52,6 +72,22 @@ using network_precision_t = __half;
 template <typename T> inline void host_device_swap(T& a, T& b) { T c(a); a = b; b = c; }
 template <typename T> inline T clamp(T v, T lo, T hi) { return v < lo ? lo : (hi < v ? hi : v); }   // tcnn common.h:250 (same comparison order as the oracle's clampf)
 template <typename T> struct GPUMemory;   // only named in declarations
+template <typename T>
+struct PitchedPtr {   // pointer + byte stride, as tcnn::PitchedPtr (common.h:433-460)
+	T* ptr; uint32_t stride_in_bytes;
+	PitchedPtr() : ptr(nullptr), stride_in_bytes(sizeof(T)) {}
+	PitchedPtr(T* p, size_t stride_in_elements, size_t offset = 0, size_t extra_stride_bytes = 0) : ptr(p + offset), stride_in_bytes((uint32_t)(stride_in_elements * sizeof(T) + extra_stride_bytes)) {}
+	template <typename U> explicit PitchedPtr(PitchedPtr<U> o) : ptr((T*)o.ptr), stride_in_bytes(o.stride_in_bytes) {}
+	T* operator()(uint32_t y) const { return (T*)((const char*)ptr + y * stride_in_bytes); }
+	void operator+=(uint32_t y) { ptr = (T*)((const char*)ptr + y * stride_in_bytes); }
+	void operator-=(uint32_t y) { ptr = (T*)((const char*)ptr - y * stride_in_bytes); }
+	explicit operator bool() const { return ptr; }
+};
+// Morton helpers: stand-ins (the published bit tricks); the oracle's own copies are pinned bit for bit against the reference's compiled
+// tiny-cuda-nn in tests/test_ref_kernels.py
+inline uint32_t expand_bits(uint32_t v) { v = (v * 0x00010001u) & 0xFF0000FFu; v = (v * 0x00000101u) & 0x0F00F00Fu; v = (v * 0x00000011u) & 0xC30C30C3u; v = (v * 0x00000005u) & 0x49249249u; return v; }
+inline uint32_t morton3D(uint32_t x, uint32_t y, uint32_t z) { return expand_bits(x) | (expand_bits(y) << 1) | (expand_bits(z) << 2); }
+inline uint32_t morton3D_invert(uint32_t x) { x = x & 0x49249249; x = (x | (x >> 2)) & 0xc30c30c3; x = (x | (x >> 4)) & 0x0f00f00f; x = (x | (x >> 8)) & 0xff0000ff; x = (x | (x >> 16)) & 0x0000ffff; return x; }
 template <typename T, uint32_t N> struct vector_t { T data[N]; T& operator[](uint32_t i) { return data[i]; } const T& operator[](uint32_t i) const { return data[i]; } };
 template <typename T>
 struct MatrixView {   // same indexing as tcnn::MatrixView: element (i, j) at data[i * stride_i + j * stride_j]
