@@ -65,3 +65,23 @@ def compute_loss(n_rays, n_kept, n_rays_total, rng_state, max_samples_compacted,
                             _p(_c(rays, np.float32)), _p(ns), _p(_c(coords, np.float32)), _p(cc), _p(dl), _p(loss), _p(ek), _p(ml),
                             _p(_c(rotation, np.uint16)), _p(_c(transition, np.uint16)), _p(off), _p(comp))
     return dict(numsteps=ns, coords_compacted=cc, dloss=dl, loss=loss, ek_loss=ek, mask_loss=ml, n_compacted=int(comp[0]))
+
+
+def grid_samples(n, rng_state, step, grid_in, n_cascades, thresh, aabb=UNIT_AABB):
+    pos = np.zeros((n, 3), np.float32); idx = np.zeros(n, np.uint32)
+    lib().refk_grid_samples(C.c_uint32(n), C.c_uint64(int(rng_state[0])), C.c_uint64(int(rng_state[1])), C.c_uint32(step), _p(_c(aabb, np.float32)),
+                            _p(_c(grid_in, np.float32)), C.c_uint32(n_cascades), C.c_float(thresh), _p(pos), _p(idx))
+    return pos, idx
+
+
+def splat_ema(indices, density_bits, decay, grid, ema_step=0):
+    """in place on `grid` (float32 [n_elements])"""
+    tmp = np.zeros(grid.shape[0], np.float32)
+    lib().refk_splat_ema(C.c_uint32(len(indices)), _p(_c(indices, np.uint32)), _p(_c(density_bits, np.uint16)), C.c_uint32(grid.shape[0]), C.c_float(decay),
+                         C.c_uint32(ema_step), _p(tmp), _p(grid))
+
+
+def bitfield(grid, n_cascades_used, mean):
+    out = np.zeros(128 ** 3 // 8 * 8, np.uint8)
+    lib().refk_bitfield(_p(_c(grid, np.float32)), C.c_uint32(n_cascades_used), C.c_float(mean), _p(out))
+    return out
