@@ -85,3 +85,22 @@ def bitfield(grid, n_cascades_used, mean):
     out = np.zeros(128 ** 3 // 8 * 8, np.uint8)
     lib().refk_bitfield(_p(_c(grid, np.float32)), C.c_uint32(n_cascades_used), C.c_float(mean), _p(out))
     return out
+
+
+def render_trace(net_forward, width, height, sample_index, focal, camera, screen_center, bitfield, snap=False, min_transmittance=0.01, variance=0.3,
+                 cos_anneal_ratio=1.0, cone_angle=0.0, rotation=IDENTITY_ROT_H, transition=ZERO_TRANS_H, first_frame_offset=None,
+                 render_aabb=UNIT_AABB, train_aabb=UNIT_AABB):
+    """init_rays_with_payload_kernel_nerf + advance_pos_nerf + the trace loop (compact / generate_next_nerf_network_inputs / network /
+    composite_kernel_nerf).  net_forward(n, coords_ptr, out_ptr) is called with ctypes pointers: coords float [n][7] -> out half [n][16]."""
+    NETFN = C.CFUNCTYPE(None, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_uint16))
+    cb = NETFN(net_forward)
+    n = width * height
+    off = np.zeros(3, np.float32) if first_frame_offset is None else _c(first_frame_offset, np.float32)
+    pay = np.zeros((n, 8), np.float32); rgba = np.zeros((n, 4), np.float32); depth = np.zeros(n, np.float32); ns = np.zeros(n, np.uint32)
+    f = lib().refk_render_trace
+    f.restype = C.c_uint32
+    hits = f(width, height, C.c_uint32(sample_index), _p(_c(focal, np.float32)), _p(_c(np.asarray(camera, np.float32).reshape(12), np.float32)),
+             _p(_c(screen_center, np.float32)), 1 if snap else 0, _p(_c(render_aabb, np.float32)), _p(_c(train_aabb, np.float32)), _p(_c(rotation, np.uint16)),
+             _p(_c(transition, np.uint16)), _p(off), _p(_c(bitfield, np.uint8)), C.c_float(cone_angle), C.c_float(min_transmittance), C.c_float(variance),
+             C.c_float(cos_anneal_ratio), cb, _p(pay), _p(rgba), _p(depth), _p(ns))
+    return dict(payload=pay, rgba=rgba, depth=depth, n_steps=ns, n_hit=int(hits))

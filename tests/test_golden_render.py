@@ -1,0 +1,58 @@
+"""CPU pin of the oracle's inference tracer against golden vectors produced by the REFERENCE's own tracer kernels
+(src/testbed_nerf.cu: init_rays_with_payload_kernel_nerf, advance_pos_nerf, compact_kernel_nerf, generate_next_nerf_network_inputs,
+composite_kernel_nerf) compiled as host code from where they lie (oracle/Makefile.ref, tests/golden/make_render_golden.py), with the
+oracle's network forward as the network on both sides.  Which pixels hit the occupancy grid, where their rays start and which rays reach
+the shading stage are exact; ray set-up and depth agree to float rounding; colours to the network's half precision (the reference
+marches several steps per compaction with plain IEEE position updates, the oracle one step with fused ones: a sample position that moves
+by one ulp can move a half-precision network output by one half-ulp)."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from oracle import ref_nerf_host as RK
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden", "render_reference.npz")
+
+
+def _mod():
+    spec = importlib.util.spec_from_file_location("make_render_golden", os.path.join(HERE, "golden", "make_render_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_tracer_matches_reference_kernels():
+    g, mod = np.load(GOLD), _mod()
+    s = mod.setup()
+    for k, v in enumerate(s["views"]):
+        rc = O.make_render_cam(mod.W, mod.H, v["focal"], v["screen_center"], v["camera"], sample_index=v["spp"], snap=v["snap"], min_transmittance=v["min_transmittance"])
+        pay = O.render_init_rays(rc, s["bitfield"])
+        ref_pay = g[f"v{k}_payload"]
+        assert np.array_equal(pay[:, 7], ref_pay[:, 7]) and 200 < pay[:, 7].sum() < mod.W * mod.H      # the same pixels enter the occupancy grid
+        alive = pay[:, 7] > 0
+        assert np.abs(pay[alive] - ref_pay[alive]).max() < 5e-7                                        # origin, direction, start t
+        rgba, depth, ns = O.render_trace(s["cfg"], s["params"], rc, s["bitfield"], pay)
+        ref_rgba, ref_depth = g[f"v{k}_rgba"], g[f"v{k}_depth"]
+        assert np.array_equal(rgba[:, 3] > 0, ref_rgba[:, 3] > 0) and int((rgba[:, 3] > 0).sum()) == int(g[f"v{k}_n_hit"])   # the same rays reach shade_kernel_nerf
+        d = np.abs(rgba - ref_rgba)
+        assert np.percentile(d, 99.9) < 2e-3 and d.max() < 2e-2, (np.percentile(d, [50, 99, 99.9]), d.max())
+        dd = np.abs(depth - ref_depth)                                                                 # depth of the maximum-weight sample: two samples of
+        assert np.percentile(dd, 99.5) < 2e-6 and dd.max() < 2e-2, (np.percentile(dd, 99.5), dd.max()) # near-equal weight may swap on a half-ulp of colour
+        # the reference's payload.n_steps also counts the marching step on which a ray leaves the box or saturates
+        hit = ref_rgba[:, 3] > 0
+        assert np.all(np.abs(g[f"v{k}_n_steps"][hit].astype(np.int64) - ns[hit].astype(np.int64)) <= 8)
+
+
+@pytest.mark.skipif(not RK.available(), reason="needs the reference tree (oracle/_ref/libref_nerf_host.so)")
+def test_committed_fixture_is_what_the_reference_source_produces(tmp_path):
+    g, mod = np.load(GOLD), _mod()
+    fresh_path = str(tmp_path / "fresh.npz")
+    mod.main(fresh_path)
+    fresh = np.load(fresh_path)
+    assert sorted(fresh.files) == sorted(g.files)
+    for name in g.files:
+        assert np.array_equal(fresh[name], g[name]), name
