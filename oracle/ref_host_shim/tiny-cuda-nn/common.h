@@ -72,6 +72,8 @@ using network_precision_t = __half;
 template <typename T> inline void host_device_swap(T& a, T& b) { T c(a); a = b; b = c; }
 template <typename T> inline T clamp(T v, T lo, T hi) { return v < lo ? lo : (hi < v ? hi : v); }   // tcnn common.h:250 (same comparison order as the oracle's clampf)
 template <typename T> struct GPUMemory;   // only named in declarations
+template <typename T> inline T next_multiple(T val, T divisor) { return (val + divisor - 1) / divisor * divisor; }
+template <typename T> inline T div_round_up(T val, T divisor) { return (val + divisor - 1) / divisor; }
 template <typename T>
 struct PitchedPtr {   // pointer + byte stride, as tcnn::PitchedPtr (common.h:433-460)
 	T* ptr; uint32_t stride_in_bytes;
