@@ -14,10 +14,18 @@
 //     reference's own kernels (oracle/_ref/libtcnn_ref.so, built from the
 //     sources in place by oracle/Makefile.ref) by tests/test_ref_kernels.py
 //     on the GPU box.
-//   * ngp layer (sample generation, loss, occupancy grid): PARITY UNPINNED by
-//     any reference artefact -- the ngp sources do not compile here (Eigen/Core
-//     is missing from the snapshot) and the reference ships no golden vectors.
-//     The restatement below follows the cited lines operation by operation.
+//   * ngp layer: pinned against the reference's own SOURCE compiled as host
+//     code.  The ngp sources do not compile as CUDA here (Eigen/Core is missing
+//     from the snapshot), but oracle/Makefile.ref builds the device headers
+//     (random_val.cuh, common_device.cuh, bounding_box.cuh, common_operation.cuh)
+//     and the kernel parts of src/testbed_nerf.cu (lines 1-2396) and
+//     src/marching_cubes.cu (lines 1-719) with g++ against the stand-in headers
+//     of oracle/ref_host_shim/ and runs the kernels one simulated thread at a
+//     time.  Golden vectors frozen from them (tests/golden/make_*_golden.py) pin
+//     sample generation, the loss stage, the occupancy-grid update and marching
+//     cubes bit for bit in their integer / half outputs, the tracer and the
+//     DeltaNetwork to float rounding (tests/test_golden_*.py).  Unpinned:
+//     shade / accumulate / tonemap and the lattice sampling kernels.
 //
 // Floating-point conventions (stated once, used by oracle AND product):
 //   * compiled with -ffp-contract=off; a fused multiply-add appears exactly
