@@ -16,6 +16,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 W, H = 40, 30
+LATTICES = [((8, 12, 6), (0, 0, 0, 1, 1, 1), (0, 0, 0, 1, 1, 1)), ((12, 8, 8), (0.1, 0.2, 0.0, 0.9, 0.8, 1.0), (0, 0, 0, 1, 1, 1)),
+            ((8, 8, 8), (0.25, 0.25, 0.25, 0.75, 0.75, 0.75), (-0.5, -0.5, -0.5, 1.5, 1.5, 1.5))]
 
 
 def setup():
@@ -48,6 +50,12 @@ def main(out_path):
             out[f"v{k}_{name}"] = r[name]
         out[f"v{k}_n_hit"] = np.array(r["n_hit"])
         print("view", k, "alive", int(r["payload"][:, 7].sum()), "hits", r["n_hit"])
+    # generate_grid_samples_nerf_uniform (:596-609): the lattice the SDF is evaluated on for marching cubes
+    for k, (res, ra, ta) in enumerate(LATTICES):
+        pos = np.zeros((res[2], res[1], res[0], 3), np.float32)
+        RK.lib().refk_lattice_positions(res[0], res[1], res[2], np.array(ra, np.float32).ctypes.data_as(C.c_void_p), np.array(ta, np.float32).ctypes.data_as(C.c_void_p),
+                                        pos.ctypes.data_as(C.c_void_p))
+        out[f"lattice{k}"] = pos
     np.savez_compressed(out_path, **out)
     print("wrote", out_path, os.path.getsize(out_path), "bytes")
 

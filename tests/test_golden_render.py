@@ -47,6 +47,22 @@ def test_tracer_matches_reference_kernels():
         assert np.all(np.abs(g[f"v{k}_n_steps"][hit].astype(np.int64) - ns[hit].astype(np.int64)) <= 8)
 
 
+def test_mesh_lattice_positions_match_reference_kernel():
+    """generate_grid_samples_nerf_uniform: where get_density_on_grid samples the SDF for marching cubes (cell corners, not centres)."""
+    import ctypes as C
+    g, mod = np.load(GOLD), _mod()
+    for k, (res, ra, ta) in enumerate(mod.LATTICES):
+        pos = np.zeros((res[2], res[1], res[0], 3), np.float32)
+        O.lib().orc_lattice_positions(np.array(res, np.uint32).ctypes.data_as(C.c_void_p), np.array(ra, np.float32).ctypes.data_as(C.c_void_p),
+                                      np.array(ta, np.float32).ctypes.data_as(C.c_void_p), pos.ctypes.data_as(C.c_void_p))
+        ref = g[f"lattice{k}"]
+        if k != 1:
+            assert np.array_equal(pos.view(np.uint32), ref.view(np.uint32))         # unit / power-of-two boxes: nothing to fuse
+        assert np.abs(pos - ref).max() <= 1.2e-7
+        first = (np.array(ra[:3], np.float32) - np.array(ta[:3], np.float32)) / (np.array(ta[3:], np.float32) - np.array(ta[:3], np.float32))
+        assert np.allclose(ref[0, 0, 0], first, atol=1e-7)                            # the first sample sits ON the render box's minimum
+
+
 @pytest.mark.skipif(not RK.available(), reason="needs the reference tree (oracle/_ref/libref_nerf_host.so)")
 def test_committed_fixture_is_what_the_reference_source_produces(tmp_path):
     g, mod = np.load(GOLD), _mod()
