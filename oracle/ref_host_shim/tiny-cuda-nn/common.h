@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -63,6 +64,10 @@ inline float max(float a, double b) { return fmaxf(a, (float)b); }
 
 struct float2 { float x, y; }; struct float3 { float x, y, z; }; struct float4 { float x, y, z, w; };
 struct __half2 { __half x, y; };
+// a "surface" is a plain float4 image here: tonemap_kernel's surf2Dwrite lands in host memory
+struct RefHostSurface { float4* data; int width; };
+typedef RefHostSurface* cudaSurfaceObject_t;
+inline void surf2Dwrite(float4 v, cudaSurfaceObject_t s, size_t x_bytes, int y) { s->data[(size_t)y * s->width + x_bytes / sizeof(float4)] = v; }
 #define TCNN_HOST_DEVICE
 #define TCNN_NAMESPACE_BEGIN namespace tcnn {
 #define TCNN_NAMESPACE_END }

@@ -63,6 +63,24 @@ def test_mesh_lattice_positions_match_reference_kernel():
         assert np.allclose(ref[0, 0, 0], first, atol=1e-7)                            # the first sample sits ON the render box's minimum
 
 
+def test_shade_accumulate_tonemap_match_reference_kernels():
+    """shade_kernel_nerf -> accumulate_kernel -> tonemap_kernel (linear colour space, identity curve): tests/golden/shade_reference.npz"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_shade_golden", os.path.join(HERE, "golden", "make_shade_golden.py"))
+    sm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sm)
+    g = np.load(os.path.join(HERE, "golden", "shade_reference.npz"))
+    rgba, depth, accs = sm.inputs()
+    for k, (sample_count, to_srgb, bg, expo) in enumerate(sm.CASES):
+        acc = accs[k].copy()
+        img, dout = O.render_shade_accumulate_tonemap(rgba, depth, acc, sample_count, bg, exposure=expo, to_srgb=bool(to_srgb))
+        assert np.array_equal(dout, g[f"s{k}_depth"])                                  # depth only where alpha > 0.2, 1e10 elsewhere
+        assert np.abs(acc - g[f"s{k}_accumulate"]).max() <= 1.2e-7                     # running mean: one fused multiply-add in the oracle
+        assert np.abs(img - g[f"s{k}_image"]).max() <= 5e-7
+        if sample_count == 0:
+            assert np.array_equal(img.view(np.uint32), g[f"s{k}_image"].view(np.uint32))   # first sample: nothing to fuse, bit-exact incl. the sRGB curve
+
+
 @pytest.mark.skipif(not RK.available(), reason="needs the reference tree (oracle/_ref/libref_nerf_host.so)")
 def test_committed_fixture_is_what_the_reference_source_produces(tmp_path):
     g, mod = np.load(GOLD), _mod()
@@ -70,5 +88,12 @@ def test_committed_fixture_is_what_the_reference_source_produces(tmp_path):
     mod.main(fresh_path)
     fresh = np.load(fresh_path)
     assert sorted(fresh.files) == sorted(g.files)
+    for name in g.files:
+        assert np.array_equal(fresh[name], g[name]), name
+    spec = importlib.util.spec_from_file_location("make_shade_golden", os.path.join(HERE, "golden", "make_shade_golden.py"))
+    sm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sm)
+    sm.main(fresh_path)
+    fresh, g = np.load(fresh_path), np.load(os.path.join(HERE, "golden", "shade_reference.npz"))
     for name in g.files:
         assert np.array_equal(fresh[name], g[name]), name
