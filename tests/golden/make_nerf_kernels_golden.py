@@ -20,6 +20,10 @@ sys.path.insert(0, ROOT)
 N_RAYS, MAX_SAMPLES, N_RAYS_TOTAL, B = 640, 1 << 16, 777 * 4096 + 5, 4096
 
 
+LOSS_VARIANTS = [dict(loss_scale=128.0, bg=(0.3, 0.6, 0.9), random_bg=False, mask_w=0.0, ek_w=0.01, cos_anneal=1.0),
+                 dict(loss_scale=64.0, bg=(0, 0, 0), random_bg=True, mask_w=0.05, ek_w=0.1, cos_anneal=0.35)]
+
+
 def scene():
     from neus2_b200 import synthetic
     return synthetic.render_sphere_views(n_views=4, width=64, height=48, seed=3)
@@ -99,6 +103,22 @@ def main(out_path):
                     pre + "coords_compacted_rows": _rows_of(lo["coords_compacted"][:m], g["coords"][:n]), pre + "loss": lo["loss"][:kk], pre + "ek_loss": lo["ek_loss"][:kk],
                     pre + "mask_loss": lo["mask_loss"][:kk]})
         print("case", k, "kept", kk, "samples", g["n_samples"], "compacted", lo["n_compacted"])
+    # loss-stage variants on case 0's samples: fixed background colour, cosine annealing in progress, another loss scale / eikonal weight
+    g0 = {k[3:]: v for k, v in out.items() if k.startswith("c0_")}
+    coords = np.zeros((MAX_SAMPLES, 7), np.float32); coords[: len(g0["coords"])] = g0["coords"]
+    kk = int(g0["n_kept"])
+    net = network_outputs(np.random.RandomState(10), kk, g0["numsteps"], coords, MAX_SAMPLES)
+    ri = np.zeros(N_RAYS, np.uint32); ri[:kk] = g0["ray_indices"]
+    rays = np.zeros((N_RAYS, 6), np.float32); rays[:kk] = g0["rays"]
+    ns = np.zeros((N_RAYS, 2), np.uint32); ns[:kk] = g0["numsteps"]
+    for k, v in enumerate(LOSS_VARIANTS):
+        lo = RK.compute_loss(N_RAYS, kk, N_RAYS_TOTAL, g0["rng_state"], B, data, net, ri, rays, ns, coords, loss_scale=v["loss_scale"], background_color=v["bg"],
+                             random_bg_color=v["random_bg"], mask_loss_weight=v["mask_w"], ek_loss_weight=v["ek_w"], cos_anneal_ratio=v["cos_anneal"])
+        m = min(lo["n_compacted"], B)
+        pre = f"l{k}_"
+        out.update({pre + "n_compacted": np.array(lo["n_compacted"]), pre + "numsteps_compacted": lo["numsteps"][:kk], pre + "dloss": lo["dloss"][:m],
+                    pre + "loss": lo["loss"][:kk], pre + "ek_loss": lo["ek_loss"][:kk], pre + "mask_loss": lo["mask_loss"][:kk]})
+        print("loss variant", k, "compacted", lo["n_compacted"])
     out["n_cases"] = np.array(len(cases))
     np.savez_compressed(out_path, **out)
     print("wrote", out_path, os.path.getsize(out_path), "bytes")
