@@ -1,6 +1,7 @@
 """Generates tests/golden/ngp_helpers_reference.npz from the REFERENCE's own device helper headers
 (include/neural-graphics-primitives/common_device.cuh: srgb_to_linear, linear_to_srgb, image_pos, read_rgba, pixel_to_ray,
-fov_to_focal_length, focal_length_to_fov; bounding_box.cuh: BoundingBox::ray_intersect, contains), compiled as host code from where they
+fov_to_focal_length, focal_length_to_fov; bounding_box.cuh: BoundingBox::ray_intersect, contains; nerf_loader.h: the NerfDataset matrix
+conventions), compiled as host code from where they
 lie into oracle/_ref/libref_ngp_host.so by oracle/Makefile.ref.  CPU only; needs /root/reference:
 
     make -f oracle/Makefile.ref all && python tests/golden/make_ngp_helpers_golden.py tests/golden/ngp_helpers_reference.npz
@@ -88,6 +89,18 @@ def main(out_path):
         for name, v in c.items():
             out[f"cam{k}_{name}"] = v
     out["n_cams"] = np.array(len(cams))
+    # dataset coordinate conventions (NerfDataset::nerf_matrix_to_ngp / ngp_matrix_to_nerf, nerf_loader.h:112-158): default axis cycle, from_na, from_mitsuba
+    LL = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_loader_host.so"))
+    LL.refl_nerf_scale.restype = C.c_float
+    out["nerf_scale"] = np.float32(LL.refl_nerf_scale())
+    mats = rs.normal(size=(9, 3, 4)).astype(np.float32)
+    offs = rs.uniform(0, 1, (9, 3)).astype(np.float32)
+    scs = rs.uniform(0.2, 2, 9).astype(np.float32)
+    fwd, inv = np.zeros((9, 12), np.float32), np.zeros((9, 12), np.float32)
+    for i in range(9):
+        LL.refl_matrix(_p(np.ascontiguousarray(mats[i].reshape(12))), C.c_float(float(scs[i])), _p(np.ascontiguousarray(offs[i])), i % 3, 0, _p(fwd[i]))
+        LL.refl_matrix(_p(np.ascontiguousarray(mats[i].reshape(12))), C.c_float(float(scs[i])), _p(np.ascontiguousarray(offs[i])), i % 3, 1, _p(inv[i]))
+    out.update(loader_mats=mats, loader_offsets=offs, loader_scales=scs, loader_to_ngp=fwd.reshape(9, 3, 4), loader_to_nerf=inv.reshape(9, 3, 4))
     np.savez_compressed(out_path, **out)
     print("wrote", out_path)
 

@@ -102,6 +102,19 @@ def test_pixel_to_ray_matches_reference(gold):
                 assert np.abs(tr - want[i]).max() <= 3e-6 * max(scale, 1.0)
 
 
+def test_dataset_matrix_conventions_bit_exact(gold):
+    """transforms.json camera matrices -> ngp coordinates and back (NerfDataset::nerf_matrix_to_ngp / ngp_matrix_to_nerf): axis cycle,
+    from_na, from_mitsuba -- what neus2_b200.loader applies to every frame of a dataset."""
+    assert np.float32(loader.NERF_SCALE) == gold["nerf_scale"]
+    for i in range(9):
+        kw = [dict(), dict(from_na=True), dict(from_mitsuba=True)][i % 3]
+        m, sc, off = gold["loader_mats"][i], gold["loader_scales"][i], gold["loader_offsets"][i]
+        a = np.asarray(loader.nerf_matrix_to_ngp(m, sc, off, **kw), np.float32)
+        b = np.asarray(loader.ngp_matrix_to_nerf(m, sc, off, **kw), np.float32)
+        assert np.array_equal(_bits(a), _bits(gold["loader_to_ngp"][i])), i
+        assert np.array_equal(_bits(b), _bits(gold["loader_to_nerf"][i])), i
+
+
 @pytest.mark.skipif(not (os.path.exists(REF_LIB) and os.path.isdir("/root/reference/include")), reason="needs the reference tree (oracle/_ref/libref_ngp_host.so)")
 def test_committed_fixture_is_what_the_reference_source_produces(gold, tmp_path):
     import importlib.util
