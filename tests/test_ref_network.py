@@ -1,0 +1,37 @@
+"""The product's fused network kernels and the CPU oracle against the REFERENCE's own ngp::NerfNetwork<__half> (nerf_network.h forward_impl /
+backward_impl incl. the DeltaNetwork branch), instantiated from the reference sources by `make -f oracle/Makefile.ref network`
+(oracle/ref_network_shim.cu -> oracle/_ref/libngp_network_ref.so).  The comparison itself lives in oracle/ref_network_check.py and runs in a
+subprocess, so that a fault inside the reference library cannot take the test session down."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from oracle import ref_network as RN
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SYMBOLS = ["refnet_last_error", "refnet_create", "refnet_destroy", "refnet_n_params", "refnet_set_params", "refnet_set_training_step",
+           "refnet_set_delta", "refnet_forward", "refnet_backward"]
+
+
+@pytest.mark.skipif(not RN.available(), reason="oracle/_ref/libngp_network_ref.so not built (make -f oracle/Makefile.ref network)")
+def test_reference_network_library_exports():
+    """CPU: the library links against libcuda and cannot be loaded here, so the dynamic symbol table is read instead."""
+    out = subprocess.run(["nm", "-D", "--defined-only", RN.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    names = {ln.split()[-1] for ln in out.splitlines() if ln.strip()}
+    assert not [s for s in SYMBOLS if s not in names]
+    # the reference's own template instantiations are in there (not a stub): NerfNetwork<__half>::forward_impl / backward_impl
+    assert any("NerfNetwork" in n and "forward_impl" in n for n in names) and any("NerfNetwork" in n and "backward_impl" in n for n in names)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not RN.available(), reason="oracle/_ref/libngp_network_ref.so not built (make -f oracle/Makefile.ref network)")
+@pytest.mark.xfail(strict=False, reason="new in round 1: the reference-network shim compiles and links, but has not had its first GPU run yet (GPU budget spent)")
+def test_product_and_oracle_match_reference_network():
+    r = subprocess.run([sys.executable, "-m", "oracle.ref_network_check", "--n", "4096"], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith('{"ref_network_check"')]
+    assert lines, (r.returncode, r.stdout[-2000:], r.stderr[-2000:])
+    res = json.loads(lines[-1])
+    assert res["ok"] and r.returncode == 0, (res["fails"], res["ref_network_check"])
