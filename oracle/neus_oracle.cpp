@@ -24,8 +24,13 @@
 //     time.  Golden vectors frozen from them (tests/golden/make_*_golden.py) pin
 //     sample generation, the loss stage, the occupancy-grid update and marching
 //     cubes bit for bit in their integer / half outputs, the tracer and the
-//     DeltaNetwork to float rounding (tests/test_golden_*.py).  Unpinned:
-//     shade / accumulate / tonemap and the lattice sampling kernels.
+//     DeltaNetwork, shade / accumulate / tonemap and the lattice sampling
+//     kernels to float rounding (tests/test_golden_*.py).
+//   * NerfNetwork (forward_impl / backward_impl, DeltaNetwork branch): pinned
+//     against the reference's own class, instantiated under nvcc from
+//     nerf_network.h on the reference's tiny-cuda-nn
+//     (oracle/ref_network_shim.cu, tests/test_ref_network.py, GPU box).
+//     Unpinned: mesh vertex colours and 1-ring normals.
 //
 // Floating-point conventions (stated once, used by oracle AND product):
 //   * compiled with -ffp-contract=off; a fused multiply-add appears exactly

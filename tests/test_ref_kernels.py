@@ -1,8 +1,8 @@
 """Pins the CPU oracle (and through it the product) against the REFERENCE's own kernels: dependencies/my_tcnn compiled
 for sm_100 from the reference sources in place (oracle/Makefile.ref -> oracle/_ref/libtcnn_ref.so).
 
-tcnn layer only (hash grid fwd / bwd / 2nd order, FullyFusedMLP fwd / bwd / 2nd order); the ngp layer does not compile
-here.  Tolerances: the reference accumulates MLP dot products in fp16 inside HMMA and grid gradients with
+tcnn layer only (hash grid fwd / bwd / 2nd order, FullyFusedMLP fwd / bwd / 2nd order); the reference's own NerfNetwork on
+top of them is compared in tests/test_ref_network.py.  Tolerances: the reference accumulates MLP dot products in fp16 inside HMMA and grid gradients with
 fp16 atomics, the oracle in fp32 -- BASELINE.json's 1e-3 (relative to the tensor's scale) for fp16 paths applies.
 """
 import numpy as np

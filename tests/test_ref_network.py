@@ -28,9 +28,8 @@ def test_reference_network_library_exports():
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not RN.available(), reason="oracle/_ref/libngp_network_ref.so not built (make -f oracle/Makefile.ref network)")
-@pytest.mark.xfail(strict=False, reason="new in round 1: the reference-network shim compiles and links, but has not had its first GPU run yet (GPU budget spent)")
 def test_product_and_oracle_match_reference_network():
-    r = subprocess.run([sys.executable, "-m", "oracle.ref_network_check", "--n", "4096"], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, "-m", "oracle.ref_network_check", "--n", "2048"], cwd=ROOT, capture_output=True, text=True, timeout=600)
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith('{"ref_network_check"')]
     assert lines, (r.returncode, r.stdout[-2000:], r.stderr[-2000:])
     res = json.loads(lines[-1])
