@@ -30,7 +30,8 @@
 //     against the reference's own class, instantiated under nvcc from
 //     nerf_network.h on the reference's tiny-cuda-nn
 //     (oracle/ref_network_shim.cu, tests/test_ref_network.py, GPU box).
-//     Unpinned: mesh vertex colours and 1-ring normals.
+//   * mesh vertex normals / colour inputs / colour extraction: pinned the same
+//     way as the ngp kernels (tests/test_golden_mesh_attributes.py).
 //
 // Floating-point conventions (stated once, used by oracle AND product):
 //   * compiled with -ffp-contract=off; a fused multiply-add appears exactly

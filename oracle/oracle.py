@@ -558,3 +558,28 @@ def marching_cubes(density, aabb=UNIT_AABB, thresh=0.0):
     idx = np.zeros(int(counts[1]), dtype=np.uint32)
     lib().orc_marching_cubes(_p(res, u32p), _p(aabb, f32p), C.c_float(thresh), _p(density, f32p), _p(counts, u32p), _p(verts, f32p), _p(idx, u32p))
     return verts, idx.reshape(-1, 3)
+
+
+def mesh_vertex_normals(verts, faces):
+    """compute_mesh_1ring's normals (marching_cubes.cu:331-366, 720-727): area-weighted, NOT normalised.  verts [nv,3] f32, faces [nt,3] u32."""
+    verts = np.ascontiguousarray(verts, dtype=np.float32)
+    idx = np.ascontiguousarray(faces, dtype=np.uint32).reshape(-1)
+    out = np.zeros((len(verts), 3), dtype=np.float32)
+    lib().orc_mesh_vertex_normals(C.c_uint32(len(verts)), C.c_uint32(idx.size // 3), _p(idx, u32p), _p(verts, f32p), _p(out, f32p))
+    return out
+
+
+def mesh_color_inputs(verts, train_aabb=UNIT_AABB):
+    """generate_nerf_network_inputs_from_positions (testbed_nerf.cu:847-853): NerfCoordinates [nv,7] for compute_mesh_vertex_colors."""
+    verts = np.ascontiguousarray(verts, dtype=np.float32)
+    out = np.zeros((len(verts), 7), dtype=np.float32)
+    lib().orc_mesh_color_inputs(C.c_uint32(len(verts)), _p(verts, f32p), _p(np.ascontiguousarray(train_aabb, dtype=np.float32), f32p), _p(out, f32p))
+    return out
+
+
+def mesh_extract_colors(out16_bits, from_linear=False):
+    """extract_srgb_with_activation (testbed_nerf.cu:532-545) on network outputs [n,16] (half bits) -> [n,3] float."""
+    o = np.ascontiguousarray(out16_bits, dtype=np.uint16)
+    out = np.zeros((len(o), 3), dtype=np.float32)
+    lib().orc_mesh_extract_colors(C.c_uint32(len(o)), _p(o, h16p), C.c_int(1 if from_linear else 0), _p(out, f32p))
+    return out

@@ -270,3 +270,23 @@ def test_inference_params_before_the_first_optimizer_step(scene):
     c = torch.from_numpy(U.random_coords(100, seed=8)).cuda()
     assert torch.equal(ctx.forward(c, use_inference_params=True).view(torch.int16), ctx.forward(c, use_inference_params=False).view(torch.int16))
     assert torch.equal(ctx.sdf_lattice((16, 16, 16), use_inference_params=True), ctx.sdf_lattice((16, 16, 16), use_inference_params=False))
+
+
+@pytest.mark.xfail(strict=False, reason="added after round 1's GPU budget was spent: first GPU run pending (the oracle side is pinned to the reference's "
+                                        "kernels on the CPU by tests/test_golden_mesh_attributes.py)")
+def test_mesh_attributes_match_oracle(scene):
+    """Vertex normals (compute_mesh_1ring) and vertex colours (compute_mesh_vertex_colors) of the extracted mesh, through the C ABI."""
+    ctx = scene["ctx"]
+    lat = ctx.sdf_lattice((32, 32, 32), use_inference_params=False).contiguous()
+    v, f = ctx.marching_cubes(lat, thresh=0.0)
+    nrm, col = ctx.mesh_attributes(len(v), use_inference_params=False)
+    vr, fr = v.cpu().numpy(), f.cpu().numpy().astype(np.uint32)
+    assert len(vr) > 500
+    n_ref = O.mesh_vertex_normals(vr, fr)
+    scale = np.abs(n_ref).max()
+    # same face normals (one fused multiply-add per component on both sides); the float atomics add them in arrival order
+    assert np.abs(nrm.cpu().numpy() - n_ref).max() <= 1e-5 * scale
+    coords = O.mesh_color_inputs(vr)                      # aabb_scale 1: the training box is the unit cube
+    c_ref = O.mesh_extract_colors(O.net_forward(scene["cfg"], coords, scene["ph"]), from_linear=False)
+    d = np.abs(col.cpu().numpy() - c_ref)
+    assert np.percentile(d, 99) <= 2e-3 and d.max() <= 3e-2, (np.percentile(d, [50, 99]), d.max())   # <= 2 half-ulps before the logistic
