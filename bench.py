@@ -191,7 +191,7 @@ def run_reference_arm(args):
         "config": workload_config(args, args.gpus),
         "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": desc + "; state: " + state_note},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference is CUDA-only and its ngp layer does not compile offline (Eigen/Core missing); this is the CPU port of its path",
+        "note": "the reference is CUDA-only (no CPU implementation of the path) and its application (src/*.cu) does not compile offline (Eigen/Core missing); this is the CPU port of its path, pinned to the reference's own kernels (DESIGN.md, Oracle)",
     }
     print(json.dumps(line))
 

@@ -42,6 +42,8 @@ def lib():
         _lib.refnet_set_delta.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         _lib.refnet_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         _lib.refnet_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        if hasattr(_lib, "refnet_time_step"):
+            _lib.refnet_time_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_float)]
     return _lib
 
 
@@ -144,3 +146,9 @@ class RefNetwork:
         self._ok(lib().refnet_backward(self.h, coords_dev, dL_dev, n, indeed_batch_size, out_dev, grads_half_dev,
                                        d.ctypes.data_as(C.c_void_p) if want_delta else None))
         return d.astype(np.float32)
+
+    def time_step(self, coords_dev, dL_dev, n_fwd, n_bwd, indeed_batch_size, warmup=3, iters=20):
+        """(ms of the inference pass over n_fwd samples, ms of forward + backward over n_bwd samples): the network part of one training step."""
+        ms = (C.c_float * 2)()
+        self._ok(lib().refnet_time_step(self.h, coords_dev, dL_dev, n_fwd, n_bwd, indeed_batch_size, warmup, iters, ms))
+        return float(ms[0]), float(ms[1])

@@ -121,4 +121,39 @@ int refnet_backward(void* h, const float* coords_dev, const void* dL_dout_half_d
 	REFNET_CATCH
 }
 
+// Timing of the reference's network part of one training step, with CUDA events on the legacy default stream (after `warmup` untimed rounds):
+// ms_out[0] = inference_mixed_precision over n_fwd samples (the pass over all generated samples, src/testbed_nerf.cu:3854),
+// ms_out[1] = forward + backward over n_bwd compacted samples (:3941-3946).  coords_dev / dL_dout_half_dev hold max(n_fwd, n_bwd) rows.
+int refnet_time_step(void* h, const float* coords_dev, const void* dL_dout_half_dev, uint32_t n_fwd, uint32_t n_bwd, uint32_t indeed_batch_size,
+                     int warmup, int iters, float* ms_out) {
+	REFNET_TRY
+	RefNet* r = (RefNet*)h;
+	const uint32_t n_max = n_fwd > n_bwd ? n_fwd : n_bwd;
+	GPUMemory<precision_t> out(n_max * 16);
+	GPUMatrix<float> in_f((float*)coords_dev, 7, n_fwd), in_b((float*)coords_dev, 7, n_bwd);
+	GPUMatrix<precision_t> out_f(out.data(), 16, n_fwd), out_b(out.data(), 16, n_bwd), dl_b((precision_t*)dL_dout_half_dev, 16, n_bwd);
+	r->net->indeed_batch_size = indeed_batch_size;
+	cudaEvent_t e0, e1, e2;
+	CUDA_CHECK_THROW(cudaEventCreate(&e0)); CUDA_CHECK_THROW(cudaEventCreate(&e1)); CUDA_CHECK_THROW(cudaEventCreate(&e2));
+	float ms_f = 0, ms_b = 0;
+	for (int it = -warmup; it < iters; ++it) {
+		CUDA_CHECK_THROW(cudaEventRecord(e0, nullptr));
+		r->net->inference_mixed_precision(nullptr, in_f, out_f, false);
+		CUDA_CHECK_THROW(cudaEventRecord(e1, nullptr));
+		{
+			auto ctx = r->net->forward(nullptr, in_b, &out_b, false, false);
+			r->net->backward(nullptr, *ctx, in_b, out_b, dl_b, nullptr, false, EGradientMode::Overwrite);
+			CUDA_CHECK_THROW(cudaEventRecord(e2, nullptr));
+			CUDA_CHECK_THROW(cudaEventSynchronize(e2));
+		}
+		float a = 0, b = 0;
+		CUDA_CHECK_THROW(cudaEventElapsedTime(&a, e0, e1)); CUDA_CHECK_THROW(cudaEventElapsedTime(&b, e1, e2));
+		if (it >= 0) { ms_f += a; ms_b += b; }
+	}
+	cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+	ms_out[0] = ms_f / iters; ms_out[1] = ms_b / iters;
+	return 0;
+	REFNET_CATCH
+}
+
 }  // extern "C"

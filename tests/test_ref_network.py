@@ -13,7 +13,7 @@ from oracle import ref_network as RN
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SYMBOLS = ["refnet_last_error", "refnet_create", "refnet_destroy", "refnet_n_params", "refnet_set_params", "refnet_set_training_step",
-           "refnet_set_delta", "refnet_forward", "refnet_backward"]
+           "refnet_set_delta", "refnet_forward", "refnet_backward", "refnet_time_step"]
 
 
 @pytest.mark.skipif(not RN.available(), reason="oracle/_ref/libngp_network_ref.so not built (make -f oracle/Makefile.ref network)")
