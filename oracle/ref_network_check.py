@@ -30,8 +30,10 @@ def _fwd_metrics(a_bits, b_bits):
     from tests import util as U
     a, b = _h(a_bits[:, :11]), _h(b_bits[:, :11])
     rel = np.abs(a - b) / (np.abs(b) + 1e-2)
-    return dict(ulp_p99=float(np.percentile(U.half_ulp_diff(a_bits[:, :11], b_bits[:, :11]), 99)), mean_rel=float(rel.mean()), max_rel=float(rel.max()),
-                copies_equal=bool(np.array_equal(a_bits[:, 7:11], b_bits[:, 7:11])))
+    # per output column, relative to the column's scale (BASELINE.json states its fp16 tolerance that way): rgb 0..2, sdf 3, normal 4..6
+    col = (np.abs(a - b).mean(axis=0) / (np.abs(b).mean(axis=0) + 1e-30))[:7]
+    return dict(ulp_p99=float(np.percentile(U.half_ulp_diff(a_bits[:, :11], b_bits[:, :11]), 99)), mean_rel=float(rel.mean()), median_rel=float(np.median(rel)),
+                max_rel=float(rel.max()), mean_abs_over_column_scale=[float(x) for x in col], copies_equal=bool(np.array_equal(a_bits[:, 7:11], b_bits[:, 7:11])))
 
 
 def _seg_rel(x, y, lay):
