@@ -42,6 +42,8 @@ def lib():
         _lib.refnet_set_delta.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         _lib.refnet_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         _lib.refnet_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        if hasattr(_lib, "refnet_sdf"):
+            _lib.refnet_sdf.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int]
         if hasattr(_lib, "refnet_time_step"):
             _lib.refnet_time_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_float)]
     return _lib
@@ -152,3 +154,7 @@ class RefNetwork:
         ms = (C.c_float * 2)()
         self._ok(lib().refnet_time_step(self.h, coords_dev, dL_dev, n_fwd, n_bwd, indeed_batch_size, warmup, iters, ms))
         return float(ms[0]), float(ms[1])
+
+    def sdf(self, pos_dev, n, out_half_dev, as_density=False):
+        """NerfNetwork::sdf / ::density with the training parameters: pos_dev [n][3] float -> out_half_dev [n] half."""
+        self._ok(lib().refnet_sdf(self.h, pos_dev, n, out_half_dev, int(bool(as_density))))

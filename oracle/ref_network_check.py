@@ -50,6 +50,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=4096, help="samples (multiple of 128)")
     ap.add_argument("--no-oracle", action="store_true", help="skip the CPU oracle legs")
+    ap.add_argument("--sdf", action="store_true", help="also compare NerfNetwork::sdf / ::density (lattice and occupancy-grid queries)")
     args = ap.parse_args()
     n = args.n
     assert n % 128 == 0
@@ -132,6 +133,26 @@ def main():
         for who, mm in r.items():
             for seg, v in mm.items():
                 bound(f"backward.{who}.{seg}", v, 5e-2)
+
+        # ---- NerfNetwork::sdf (marching-cubes lattice) and ::density (occupancy-grid update) -----------------------------------------
+        if args.sdf:
+            pos = np.random.RandomState(5).uniform(0, 1, (n, 3)).astype(np.float32)
+            d_pos, d_sp, d_sr = cuda.upload(pos), cuda.zeros(n * 2), cuda.zeros(n * 2)
+            for as_density in (False, True):
+                N.check(lib.neus2_sdf(ctx._h, None, C.c_void_p(d_pos), C.c_uint32(3), C.c_uint32(n), C.c_void_p(d_sp), C.c_int(int(as_density)), C.c_int(0)))
+                cuda.sync()
+                ref.sdf(d_pos, n, d_sr, as_density)
+                a, b = cuda.download(d_sp, (n,), np.uint16), cuda.download(d_sr, (n,), np.uint16)
+                legs = {"product_vs_reference": (a, b)}
+                if not args.no_oracle:
+                    legs["oracle_vs_reference"] = (O.net_sdf(cfg, pos, p_bits, as_density=as_density), b)
+                key = "density" if as_density else "sdf"
+                res[key] = {}
+                for who, (x, y) in legs.items():
+                    xf, yf = _h(x), _h(y)
+                    mm = dict(ulp_p99=float(np.percentile(U.half_ulp_diff(x, y), 99)), mean_abs_over_scale=float(np.abs(xf - yf).mean() / (np.abs(yf).mean() + 1e-30)))
+                    res[key][who] = mm
+                    bound(f"{key}.{who}.mean_abs_over_scale", mm["mean_abs_over_scale"], 5e-3)
 
         # ---- DeltaNetwork: deformation in the forward pass, 9 gradient sums in the backward pass ------------------------------
         try:

@@ -156,4 +156,21 @@ int refnet_time_step(void* h, const float* coords_dev, const void* dL_dout_half_
 	REFNET_CATCH
 }
 
+// NerfNetwork::sdf (nerf_network.h:645-713; marching-cubes lattice, src/testbed_nerf.cu:4127-4131) or ::density (:715-733; occupancy-grid
+// update, :3364-3366, training parameters): pos_dev [n][3] float (NerfPosition), out_half_dev [n] half -- row 0 of the reference's
+// row-major [padded_output_width][n] output.  n must be a multiple of 128.
+int refnet_sdf(void* h, const float* pos_dev, uint32_t n, void* out_half_dev, int as_density) {
+	REFNET_TRY
+	RefNet* r = (RefNet*)h;
+	const uint32_t w = r->net->padded_density_output_width();
+	GPUMemory<precision_t> out((size_t)w * n);
+	GPUMatrix<float> in_m((float*)pos_dev, 3, n);
+	GPUMatrix<precision_t, RM> out_m(out.data(), w, n);
+	if (as_density) r->net->density(nullptr, in_m, out_m, false); else r->net->sdf(nullptr, in_m, out_m, false);
+	CUDA_CHECK_THROW(cudaDeviceSynchronize());
+	CUDA_CHECK_THROW(cudaMemcpy(out_half_dev, out.data(), (size_t)n * sizeof(precision_t), cudaMemcpyDeviceToDevice));
+	return 0;
+	REFNET_CATCH
+}
+
 }  // extern "C"

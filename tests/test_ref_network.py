@@ -13,7 +13,7 @@ from oracle import ref_network as RN
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SYMBOLS = ["refnet_last_error", "refnet_create", "refnet_destroy", "refnet_n_params", "refnet_set_params", "refnet_set_training_step",
-           "refnet_set_delta", "refnet_forward", "refnet_backward", "refnet_time_step"]
+           "refnet_set_delta", "refnet_forward", "refnet_backward", "refnet_sdf", "refnet_time_step"]
 
 
 @pytest.mark.skipif(not RN.available(), reason="oracle/_ref/libngp_network_ref.so not built (make -f oracle/Makefile.ref network)")
@@ -33,4 +33,16 @@ def test_product_and_oracle_match_reference_network():
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith('{"ref_network_check"')]
     assert lines, (r.returncode, r.stdout[-2000:], r.stderr[-2000:])
     res = json.loads(lines[-1])
+    assert res["ok"] and r.returncode == 0, (res["fails"], res["ref_network_check"])
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not RN.available(), reason="oracle/_ref/libngp_network_ref.so not built (make -f oracle/Makefile.ref network)")
+@pytest.mark.xfail(strict=False, reason="NerfNetwork::sdf / ::density leg added after round 1's GPU budget was spent: first GPU run pending")
+def test_sdf_and_density_match_reference_network():
+    r = subprocess.run([sys.executable, "-m", "oracle.ref_network_check", "--n", "2048", "--sdf"], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith('{"ref_network_check"')]
+    assert lines, (r.returncode, r.stdout[-2000:], r.stderr[-2000:])
+    res = json.loads(lines[-1])
+    assert "sdf" in res["ref_network_check"] and "density" in res["ref_network_check"]
     assert res["ok"] and r.returncode == 0, (res["fails"], res["ref_network_check"])
