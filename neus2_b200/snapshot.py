@@ -27,7 +27,8 @@ def save(ctx, path, network_config, include_optimizer_state=False, loss=0.0, aab
     master, params, ema, _ = ctx.buffers()
     m1, m2, steps, current_step = ctx.optimizer_buffers()
     state = ctx.get_state()
-    torch.cuda.synchronize()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
     inference = ema if current_step > 0 else params          # before the first optimizer step the inference weights are the initial ones
     snap = {"n_params": int(ctx.n_params), "params_binary": inference.cpu().numpy().tobytes()}
     if include_optimizer_state:
@@ -99,5 +100,6 @@ def restore(ctx, snap):
         raise RuntimeError("Incompatible number of grid cascades.")
     rgb = snap["nerf"]["rgb"]
     ctx.set_state(int(snap["training_step"]), int(rgb["rays_per_batch"]), int(snap.get("n_rays_total", 0)), int(rgb["measured_batch_size_before_compaction"]))
-    torch.cuda.synchronize()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
     return float(snap.get("loss", 0.0))

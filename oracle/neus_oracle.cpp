@@ -32,6 +32,8 @@
 //     (oracle/ref_network_shim.cu, tests/test_ref_network.py, GPU box).
 //   * mesh vertex normals / colour inputs / colour extraction: pinned the same
 //     way as the ngp kernels (tests/test_golden_mesh_attributes.py).
+//   * Adam / ExponentialDecay / Ema also against the reference's optimizer
+//     OBJECTS compiled as host code (tests/test_golden_snapshot.py).
 //
 // Floating-point conventions (stated once, used by oracle AND product):
 //   * compiled with -ffp-contract=off; a fused multiply-add appears exactly

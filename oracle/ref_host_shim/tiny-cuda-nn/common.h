@@ -76,7 +76,9 @@ namespace tcnn {
 using network_precision_t = __half;
 template <typename T> inline void host_device_swap(T& a, T& b) { T c(a); a = b; b = c; }
 template <typename T> inline T clamp(T v, T lo, T hi) { return v < lo ? lo : (hi < v ? hi : v); }   // tcnn common.h:250 (same comparison order as the oracle's clampf)
+#ifndef REF_HOST_FUNCTIONAL_GPU_MEMORY   // oracle/ref_opt_shim brings a working one
 template <typename T> struct GPUMemory { T* data() const { return nullptr; } size_t size() const { return 0; } };   // never allocated on this path
+#endif
 template <typename T> inline T next_multiple(T val, T divisor) { return (val + divisor - 1) / divisor * divisor; }
 template <typename T> inline T div_round_up(T val, T divisor) { return (val + divisor - 1) / divisor; }
 template <typename T>

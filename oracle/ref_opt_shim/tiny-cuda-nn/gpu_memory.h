@@ -1,0 +1,22 @@
+// TEST INFRASTRUCTURE ONLY -- tcnn::GPUMemory<T> over host memory (see common.h in this directory): the members the optimizer headers use.
+#pragma once
+#include <tiny-cuda-nn/common.h>
+namespace tcnn {
+template <typename T>
+class GPUMemory {
+	T* m_data = nullptr; size_t m_size = 0;
+public:
+	GPUMemory() {}
+	explicit GPUMemory(size_t n) { resize(n); }
+	GPUMemory(const GPUMemory& o) { *this = o; }
+	GPUMemory(GPUMemory&& o) noexcept : m_data(o.m_data), m_size(o.m_size) { o.m_data = nullptr; o.m_size = 0; }
+	~GPUMemory() { std::free(m_data); }
+	GPUMemory& operator=(const GPUMemory& o) { if (this != &o) { resize(o.m_size); if (m_size) std::memcpy(m_data, o.m_data, get_bytes()); } return *this; }
+	GPUMemory& operator=(GPUMemory&& o) noexcept { if (this != &o) { std::free(m_data); m_data = o.m_data; m_size = o.m_size; o.m_data = nullptr; o.m_size = 0; } return *this; }
+	void resize(size_t n) { if (n != m_size) { std::free(m_data); m_data = n ? (T*)std::malloc(n * sizeof(T)) : nullptr; m_size = n; } }
+	void memset(int v) { if (m_size) std::memset(m_data, v, get_bytes()); }
+	T* data() const { return m_data; }
+	size_t size() const { return m_size; }
+	size_t get_bytes() const { return m_size * sizeof(T); }
+};
+}
