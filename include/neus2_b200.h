@@ -75,6 +75,12 @@ typedef struct neus2_config {
 	uint32_t delta_decay_start;      /* 50 */
 	uint32_t delta_decay_interval;   /* 25 (0 = no decay) */
 	float delta_decay_base;          /* 0.99 */
+	/* ExponentialDecay around the main Adam (configs/nerf/base.json:7-12; tcnn optimizers/exponential_decay.h:60-71): from optimizer step
+	 * decay_start on, every decay_interval steps (up to decay_end), the learning rate is multiplied by decay_base. */
+	uint32_t decay_start;            /* 20000 */
+	uint32_t decay_interval;         /* 10000 (0 = no decay) */
+	uint32_t decay_end;              /* 10000000 (the reference's default; base.json does not set it) */
+	float decay_base;                /* 0.33 */
 } neus2_config;
 
 typedef struct neus2_step_stats {
@@ -93,6 +99,10 @@ typedef struct neus2_step_stats {
 
 const char* neus2_last_error(void);
 void neus2_default_config(neus2_config* cfg);                       /* base.json values */
+/* m_learning_rate_factor of ExponentialDecayOptimizer (exponential_decay.h:60-71) when the nested Adam has done `optimizer_steps_done` steps and
+ * is about to do the next one: decay_base multiplied in once per trigger, in float like the reference.  Pure host arithmetic (no GPU needed);
+ * the optimizer entry points use it, so the factor needs no state of its own and survives snapshots through the optimizer step count. */
+float neus2_learning_rate_factor(const neus2_config* cfg, uint32_t optimizer_steps_done);
 
 /* Testbed::reset_network (src/testbed.cu:2084) for TestbedMode::Nerf: builds tables, allocates every buffer. */
 int neus2_ctx_create(const neus2_config* cfg, int device, neus2_ctx** out);

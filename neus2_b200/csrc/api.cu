@@ -290,6 +290,19 @@ void neus2_default_config(neus2_config* c) {
 	// "globalmove" optimizer of configs/nerf/base.json:135-158 (Ema{ExponentialDecay{Adam}})
 	c->delta_learning_rate = 1e-4f; c->delta_beta1 = 0.9f; c->delta_beta2 = 0.99f; c->delta_epsilon = 1e-10f;
 	c->delta_decay_start = 50; c->delta_decay_interval = 25; c->delta_decay_base = 0.99f;
+	c->decay_start = 20000; c->decay_interval = 10000; c->decay_end = 10000000; c->decay_base = 0.33f;
+}
+
+// ExponentialDecayOptimizer::step (tcnn optimizers/exponential_decay.h:60-71): with s = nested->step() BEFORE the nested step,
+// "if (s >= decay_start && (s - decay_start) % decay_interval == 0 && s <= decay_end) factor *= decay_base".  The factor after all triggers up to s.
+float neus2_learning_rate_factor(const neus2_config* c, uint32_t s) {
+	float factor = 1.0f;
+	if (!c->decay_interval || s < c->decay_start) return factor;
+	const uint32_t last = s < c->decay_end ? s : c->decay_end;
+	if (last < c->decay_start) return factor;
+	const uint32_t triggers = (last - c->decay_start) / c->decay_interval + 1;
+	for (uint32_t k = 0; k < triggers; ++k) factor *= c->decay_base;
+	return factor;
 }
 
 static int build_tables(neus2_ctx* ctx) {
@@ -621,7 +634,8 @@ int neus2_optimizer_step(neus2_ctx* ctx, void* stream, float loss_scale) {
 	const int fuse = ctx->fuse_zero_into_adam ? 1 : 0;
 	uint32_t* const zp[3] = {(uint32_t*)ctx->var_acc, (uint32_t*)ctx->w1row0_acc, ctx->counters};
 	const uint32_t zn[3] = {1u, 64u, 8u};
-	const int rc_ = launch_adam_ema((cudaStream_t)stream, ctx->n_params, ctx->pl.off_grid, loss_scale, ctx->learning_rate, c.beta1, c.beta2, c.epsilon, c.l2_reg,
+	const float lr = ctx->learning_rate * neus2_learning_rate_factor(&c, ctx->adam_step - 1);   // x 1.0f before decay_start: the same float
+	const int rc_ = launch_adam_ema((cudaStream_t)stream, ctx->n_params, ctx->pl.off_grid, loss_scale, lr, c.beta1, c.beta2, c.epsilon, c.l2_reg,
 	                       c.ema_decay, ctx->adam_step, ctx->grads, ctx->master, ctx->params, ctx->m1, ctx->m2, ctx->steps, ctx->ema, ctx->adam_bias_table, ADAM_BIAS_TABLE, frozen,
 	                       fuse, zp, zn);
 	if (rc_ == 0 && ctx->use_delta) CHECK(delta_optimizer_step(ctx, (cudaStream_t)stream, loss_scale));   // m_global_move.trainer->optimizer_step (testbed_nerf.cu:3506-3508)
@@ -1170,7 +1184,8 @@ int neus2_optimizer_step_sharded(neus2_ctx* ctx, void* stream, float loss_scale)
 	++ctx->adam_step;
 	stage_begin(ctx, ST_OPT, (cudaStream_t)stream);
 	const int frozen = ctx->time_frame >= 1 && ctx->training_step < ctx->frozen_steps;
-	const int rc_ = launch_adam_ema_p2p((cudaStream_t)stream, ctx->n_params, ctx->pl.off_grid, ctx->peer_rank, ctx->peer_world, loss_scale, ctx->learning_rate, c.beta1, c.beta2,
+	const float lr = ctx->learning_rate * neus2_learning_rate_factor(&c, ctx->adam_step - 1);
+	const int rc_ = launch_adam_ema_p2p((cudaStream_t)stream, ctx->n_params, ctx->pl.off_grid, ctx->peer_rank, ctx->peer_world, loss_scale, lr, c.beta1, c.beta2,
 	                                    c.epsilon, c.l2_reg, c.ema_decay, ctx->adam_step, ctx->peer_grads, ctx->peer_params, ctx->peer_ema, ctx->master, ctx->m1, ctx->m2, ctx->steps, ctx->adam_bias_table, ADAM_BIAS_TABLE, frozen);
 	if (rc_ == 0 && ctx->use_delta) CHECK(delta_optimizer_step(ctx, (cudaStream_t)stream, loss_scale));   // every rank steps its replica on the all-reduced sums
 	stage_end(ctx, ST_OPT, (cudaStream_t)stream);

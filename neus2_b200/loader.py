@@ -285,7 +285,14 @@ def config_from_json(cfg_json):
     opt = cfg_json.get("optimizer", {})
     if "decay" in opt:
         kw["ema_decay"] = float(opt["decay"])
-    while "nested" in opt:
+    while True:
+        if opt.get("otype", "") == "ExponentialDecay":       # defaults of exponential_decay.h:145-148
+            kw["decay_start"] = int(opt.get("decay_start", 10000))
+            kw["decay_interval"] = int(opt.get("decay_interval", 10000))
+            kw["decay_end"] = int(opt.get("decay_end", 10000000))
+            kw["decay_base"] = float(opt.get("decay_base", 0.1))
+        if "nested" not in opt:
+            break
         opt = opt["nested"]
     for src, dst in (("learning_rate", "learning_rate"), ("beta1", "beta1"), ("beta2", "beta2"), ("epsilon", "epsilon"), ("l2_reg", "l2_reg")):
         if src in opt:

@@ -12,6 +12,8 @@ optimizers/ema.h:182-194, exponential_decay.h:128-140, adam.h:424-445): the netw
 Loading follows Trainer::deserialize: the fp16 blob becomes BOTH the training and the inference parameters and the fp32
 master copy is its widening (trainer.h:263-275).  Host logic only.
 """
+import ctypes as C
+
 import numpy as np
 
 
@@ -35,7 +37,9 @@ def save(ctx, path, network_config, include_optimizer_state=False, loss=0.0, aab
         adam = {"current_step": int(current_step), "base_learning_rate": float(ctx.cfg.learning_rate),
                 "first_moments_binary": m1.cpu().numpy().tobytes(), "second_moments_binary": m2.cpu().numpy().tobytes(),
                 "param_steps_binary": steps.cpu().numpy().tobytes()}
-        snap["optimizer"] = {"nested": {"nested": adam, "learning_rate": float(ctx.cfg.learning_rate), "learning_rate_factor": 1.0},
+        from ._lib import load
+        factor = float(load().neus2_learning_rate_factor(C.byref(ctx.cfg), C.c_uint32(max(int(current_step), 1) - 1))) if hasattr(ctx.cfg, "decay_start") else 1.0
+        snap["optimizer"] = {"nested": {"nested": adam, "learning_rate": float(ctx.cfg.learning_rate), "learning_rate_factor": factor},
                              "weights_ema_binary": ema.cpu().numpy().tobytes()}
     grid = ctx.debug_buffer("density_grid", "<f4", (128 ** 3,)).cpu().numpy()
     snap["density_grid_size"] = 128

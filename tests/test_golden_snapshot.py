@@ -193,3 +193,32 @@ def test_committed_fixture_is_what_the_reference_source_produces(tmp_path):
     assert sorted(fresh.files) == sorted(g.files)
     for name in g.files:
         assert np.array_equal(fresh[name], g[name]), name
+
+
+def test_learning_rate_factor_of_the_library_is_the_reference_schedule():
+    """neus2_learning_rate_factor (C ABI, host arithmetic) == m_learning_rate_factor of the reference's ExponentialDecayOptimizer."""
+    import ctypes as C
+    import neus2_b200 as N
+    from neus2_b200 import _lib
+    g, mod = np.load(GOLD), _mod()
+    d = mod.OPTIMIZER["nested"]
+    cfg = N.default_config(decay_start=d["decay_start"], decay_interval=d["decay_interval"], decay_base=d["decay_base"])
+    f = lambda c, s: float(_lib.load().neus2_learning_rate_factor(C.byref(c), C.c_uint32(s)))
+    assert np.float32(f(cfg, mod.STEPS - 1)) == np.float32(g["learning_rate_factor"])           # after 45 steps: three decays, float products
+    assert f(cfg, 19) == 1.0 and f(cfg, 20) == f(cfg, 29) == float(np.float32(0.33)) and f(cfg, 30) == float(np.float32(0.33) * np.float32(0.33))
+    base = N.default_config()                                                                  # base.json: 20000 / 10000 / 0.33, no decay_end
+    assert (base.decay_start, base.decay_interval, base.decay_end) == (20000, 10000, 10000000) and abs(base.decay_base - 0.33) < 1e-7
+    assert f(base, 19999) == 1.0 and f(base, 20000) == float(np.float32(0.33)) and f(base, 29999) == float(np.float32(0.33))
+    ended = N.default_config(decay_start=5, decay_interval=5, decay_end=12, decay_base=0.5)
+    assert [f(ended, s) for s in (4, 5, 9, 10, 14, 15, 100)] == [1.0, 0.5, 0.5, 0.25, 0.25, 0.25, 0.25]    # no trigger past decay_end
+    assert f(N.default_config(decay_interval=0), 10 ** 6) == 1.0
+    if RS.available():      # step by step against the live reference objects
+        master, grads = mod.inputs()
+        st = RS.Stack(mod.OPTIMIZER, mod.N_DENSITY, mod.N_RGB, mod.N_GRID, mod.N_VARIANCE, mod.LAYERS)
+        try:
+            st.set_params_full_precision(master)
+            for k in range(mod.STEPS):
+                st.optimizer_step(mod.LOSS_SCALE, grads[k])
+                assert np.float32(st.state()["learning_rate_factor"]) == np.float32(f(cfg, k)), k
+        finally:
+            st.close()

@@ -27,6 +27,8 @@ def test_config_json_with_comments():
     assert kw == {"n_levels": 14, "log2_hashmap_size": 19, "base_resolution": 16, "valid_level_scale": 0.02, "base_valid_level_scale": 0.2,
                   "base_training_step": 100, "top_resolution": 2048.0, "ema_decay": 0.95, "learning_rate": 1e-3, "beta1": 0.9, "beta2": 0.99,
                   "epsilon": 1e-15, "l2_reg": 1e-6, "mask_loss_weight": 0.0, "ek_loss_weight": 0.01,
+                  # ExponentialDecay around the main Adam; what the json leaves out takes exponential_decay.h's defaults
+                  "decay_start": 20000, "decay_interval": 10000, "decay_end": 10000000, "decay_base": 0.1,
                   # no "globalmove" section: the DeltaNetwork's trainer is built from the main optimizer config (testbed.cu:2320-2323)
                   "delta_decay_start": 20000, "delta_decay_interval": 10000, "delta_decay_base": 0.1,
                   "delta_learning_rate": 1e-3, "delta_beta1": 0.9, "delta_beta2": 0.99, "delta_epsilon": 1e-15}
