@@ -125,3 +125,43 @@ def test_adam_ema_bit_exact(ctx_and_params):
         assert np.array_equal(ema_h.cpu().numpy().view(np.uint16), ema)
     finally:
         ctx.set_params(p)
+
+
+@pytest.mark.xfail(strict=False, reason="added after round 1's GPU budget was spent: first GPU run pending (the schedule itself is checked on the CPU against the "
+                                        "reference's ExponentialDecayOptimizer, tests/test_golden_snapshot.py)")
+def test_learning_rate_decay_reaches_the_adam_kernel():
+    """ExponentialDecay around the main Adam: with decay_start 2 / interval 2 / base 0.5 the optimizer steps 1..6 run at lr x {1, 1, .5, .5, .25, .25}."""
+    import ctypes as C
+    import torch
+    import neus2_b200 as N
+    from neus2_b200 import _lib
+    cfg = U.base_cfg()
+    lay = O.param_layout(cfg)
+    c = N.default_config(batch_size=1 << 14, decay_start=2, decay_interval=2, decay_base=0.5)
+    ctx = N.Context(c)
+    try:
+        p = U.random_params(cfg, seed=2)
+        ctx.set_params(p)
+        n = lay["total"]
+        master, params_h, ema_h, grads = ctx.buffers()
+        rs = np.random.RandomState(4)
+        g = np.zeros(n, dtype=np.float32)
+        touched = rs.choice(n, size=100000, replace=False)
+        g[touched] = rs.normal(0, 1, touched.size).astype(np.float32)
+        g[: lay["grid"]] = rs.normal(0, 1, lay["grid"])
+        m1 = np.zeros(n, np.float32); m2 = np.zeros(n, np.float32); steps = np.zeros(n, np.uint32)
+        mm = master.cpu().numpy().copy(); ema = np.zeros(n, np.uint16); ph = mm.astype(np.float16).view(np.uint16).copy()
+        factors = []
+        for step in range(1, 7):
+            f = np.float32(_lib.load().neus2_learning_rate_factor(C.byref(c), C.c_uint32(step - 1)))
+            factors.append(float(f))
+            grads.copy_(torch.from_numpy(g))
+            ctx.optimizer_step(128.0)
+            O.adam_ema_step(lay["grid"], 128.0, np.float32(1e-3) * f, 0.9, 0.99, 1e-15, 1e-6, 0.95, step, g, mm, ph, m1, m2, steps, ema)
+            g = np.roll(g, 4321)
+        torch.cuda.synchronize()
+        assert factors == [1.0, 1.0, 0.5, 0.5, 0.25, 0.25]
+        assert np.array_equal(master.cpu().numpy().view(np.uint32), mm.view(np.uint32))
+        assert np.array_equal(params_h.cpu().numpy().view(np.uint16), ph) and np.array_equal(ema_h.cpu().numpy().view(np.uint16), ema)
+    finally:
+        ctx.close()
