@@ -3,7 +3,7 @@
 Restates `load_nerf` (src/nerf_loader.cu:196-745) and `NerfDataset::nerf_matrix_to_ngp`
 (include/neural-graphics-primitives/nerf_loader.h:112-135) for the NeuS2 data convention (README.md:77-148):
 8-bit RGBA images, per-frame `transform_matrix` (camera-to-world) and optional 4x4 `intrinsic_matrix`, global
-`from_na`, `scale`, `offset`, `aabb_scale`, `w`, `h`, `fl_x` / `fl_y` / `camera_angle_x|y`, `cx`, `cy`, `n_frames`,
+`from_na`, `scale`, `offset`, `aabb_scale`, `w`, `h`, `fl_x` / `fl_y` / `camera_angle_x|y`, `n_frames` (`cx` / `cy` are ignored, as in the reference),
 `white_transparent`, `black_transparent`, `<file>.alpha.<ext>` side images and `dynamic_mask_<file>.png` masks.
 Images are decoded by a thread pool (PIL releases the GIL) into ONE pinned host buffer so that the upload to the GPU
 is a single asynchronous copy.  Everything is float32 arithmetic in the reference's order of operations.
@@ -148,11 +148,10 @@ def load_nerf(path, n_threads=None, pin=True):
         scale, offset = sc, off
         if "aabb_scale" in js:
             aabb_scale = int(js["aabb_scale"])
+        # The reference parses "cx" / "cy" (nerf_loader.cu:431-437) but never stores them: its assignment of the principal point to the image
+        # metadata is commented out (:703), so the centre stays at (0.5, 0.5) unless a frame carries an "intrinsic_matrix" (:678-686).
+        # Same here -- checked against the reference's own loader (tests/test_golden_loader.py).
         pp0 = np.array([0.5, 0.5], dtype=np.float32)
-        if "cx" in js:
-            pp0[0] = np.float32(js["cx"]) / np.float32(js["w"])
-        if "cy" in js:
-            pp0[1] = np.float32(js["cy"]) / np.float32(js["h"])
         for fr in frames:
             img_path = _resolve_image(base, fr["file_path"])
             root, ext = os.path.splitext(img_path)

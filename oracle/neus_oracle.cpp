@@ -33,7 +33,9 @@
 //   * mesh vertex normals / colour inputs / colour extraction: pinned the same
 //     way as the ngp kernels (tests/test_golden_mesh_attributes.py).
 //   * Adam / ExponentialDecay / Ema also against the reference's optimizer
-//     OBJECTS compiled as host code (tests/test_golden_snapshot.py).
+//     OBJECTS compiled as host code (tests/test_golden_snapshot.py); the
+//     dataset loader of the host layer against the reference's load_nerf
+//     (tests/test_golden_loader.py).
 //
 // Floating-point conventions (stated once, used by oracle AND product):
 //   * compiled with -ffp-contract=off; a fused multiply-add appears exactly
