@@ -18,6 +18,7 @@ public:
 	void enlarge(size_t n) { if (n > m_size) { T* d = (T*)std::malloc(n * sizeof(T)); if (m_size) std::memcpy((void*)d, (const void*)m_data, get_bytes()); std::free(m_data); m_data = d; m_size = n; } }
 	void free_memory() { std::free(m_data); m_data = nullptr; m_size = 0; }
 	void copy_from_host(const T* host) { if (m_size) std::memcpy((void*)m_data, (const void*)host, get_bytes()); }
+	void copy_to_host(std::vector<T>& host) const { if (host.size() < m_size) throw std::runtime_error{"copy_to_host: buffer too small"}; copy_to_host(host.data()); }
 	void copy_to_host(T* host) const { if (m_size) std::memcpy((void*)host, (const void*)m_data, get_bytes()); }
 	T* data() const { return m_data; }
 	size_t size() const { return m_size; }

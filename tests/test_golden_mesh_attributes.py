@@ -75,3 +75,37 @@ def test_committed_fixture_is_what_the_reference_source_produces(tmp_path):
     assert sorted(fresh.files) == sorted(g.files)
     for name in g.files:
         assert np.array_equal(fresh[name], g[name]), name
+
+
+# ---- the files: save_mesh (src/marching_cubes.cu:824-960) ------------------------------------------------------------------------------------
+REF_PLY_COMMENT = b"comment output from https://github.com/NVlabs/instant-ngp"
+
+
+def test_obj_and_ply_files_are_byte_identical_to_the_reference_writer(tmp_path):
+    """neus2_b200.mesh.save against the bytes the reference's own save_mesh wrote for the same seeded mesh (dataset coordinates (v - offset) / scale,
+    reversed winding, normalised normals, clamped colours, printf formats).  The one intended difference is the PLY comment line."""
+    import hashlib
+    from neus2_b200 import mesh
+    g, mod = np.load(os.path.join(HERE, "golden", "mesh_files_reference.npz")), _mod("make_mesh_files_golden")
+    V, N, Cc, F = mod.seeded_mesh()
+    for ext in ("obj", "ply"):
+        path = str(tmp_path / ("mesh." + ext))
+        mesh.save(path, V, N, Cc, F, nerf_scale=mod.NERF_SCALE, nerf_offset=mod.NERF_OFFSET)
+        data = open(path, "rb").read()
+        if ext == "ply":
+            assert b"comment output from neus2_b200" in data
+            data = data.replace(b"comment output from neus2_b200", REF_PLY_COMMENT)
+        assert len(data) == int(g[ext + "_size"]) and data[:1500] == g[ext + "_head"].tobytes()
+        assert np.array_equal(np.frombuffer(hashlib.sha256(data).digest(), np.uint8), g[ext + "_sha"])
+
+
+@pytest.mark.skipif(not (os.path.exists(os.path.join(os.path.dirname(HERE), "oracle", "_ref", "libref_savemesh_host.so")) and os.path.isdir("/root/reference/src")),
+                    reason="needs the reference tree (oracle/_ref/libref_savemesh_host.so)")
+def test_committed_mesh_file_fixture_is_what_the_reference_source_produces(tmp_path):
+    g, mod = np.load(os.path.join(HERE, "golden", "mesh_files_reference.npz")), _mod("make_mesh_files_golden")
+    fresh_path = str(tmp_path / "fresh.npz")
+    mod.main(fresh_path)
+    fresh = np.load(fresh_path)
+    assert sorted(fresh.files) == sorted(g.files)
+    for name in g.files:
+        assert np.array_equal(fresh[name], g[name]), name
