@@ -103,6 +103,8 @@ void neus2_default_config(neus2_config* cfg);                       /* base.json
  * is about to do the next one: decay_base multiplied in once per trigger, in float like the reference.  Pure host arithmetic (no GPU needed);
  * the optimizer entry points use it, so the factor needs no state of its own and survives snapshots through the optimizer step count. */
 float neus2_learning_rate_factor(const neus2_config* cfg, uint32_t optimizer_steps_done);
+/* rays_per_batch of the next step, Counters::update_after_training (src/testbed_nerf.cu:3435-3436).  Pure host arithmetic; the step uses it. */
+uint32_t neus2_next_rays_per_batch(uint32_t rays_per_batch, uint32_t target_batch_size, uint32_t measured_batch_size, uint32_t world_size, uint32_t max_rays_per_batch);
 
 /* Testbed::reset_network (src/testbed.cu:2084) for TestbedMode::Nerf: builds tables, allocates every buffer. */
 int neus2_ctx_create(const neus2_config* cfg, int device, neus2_ctx** out);

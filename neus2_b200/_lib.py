@@ -52,7 +52,7 @@ class RenderParams(C.Structure):
 
 
 EXPORTS = [
-    "neus2_last_error", "neus2_default_config", "neus2_learning_rate_factor", "neus2_ctx_create", "neus2_ctx_destroy", "neus2_n_params", "neus2_param_layout",
+    "neus2_last_error", "neus2_default_config", "neus2_learning_rate_factor", "neus2_next_rays_per_batch", "neus2_ctx_create", "neus2_ctx_destroy", "neus2_n_params", "neus2_param_layout",
     "neus2_grid_tables", "neus2_buffers", "neus2_init_params", "neus2_set_params", "neus2_get_params", "neus2_set_training_step",
     "neus2_forward", "neus2_sdf", "neus2_backward", "neus2_optimizer_step", "neus2_set_dataset", "neus2_update_density_grid",
     "neus2_train_step_begin", "neus2_train_step_end", "neus2_local_counts", "neus2_train_step", "neus2_debug_buffer",
@@ -79,6 +79,8 @@ def load():
     lib.neus2_n_params.restype = C.c_uint64
     lib.neus2_learning_rate_factor.restype = C.c_float
     lib.neus2_learning_rate_factor.argtypes = [C.c_void_p, C.c_uint32]
+    lib.neus2_next_rays_per_batch.restype = C.c_uint32
+    lib.neus2_next_rays_per_batch.argtypes = [C.c_uint32] * 5
     lib.neus2_launch_count.restype = C.c_uint64
     lib.neus2_n_params.argtypes = [C.c_void_p]
     lib.neus2_launch_count.argtypes = [C.c_void_p]

@@ -293,6 +293,14 @@ void neus2_default_config(neus2_config* c) {
 	c->decay_start = 20000; c->decay_interval = 10000; c->decay_end = 10000000; c->decay_base = 0.33f;
 }
 
+// Counters::update_after_training (src/testbed_nerf.cu:3435-3436): rays for the next step so that it yields target_batch_size compacted samples,
+// rounded up to the batch granularity (128 rays per rank here, tcnn::batch_size_granularity there) and capped (1 << 18 in the reference).
+uint32_t neus2_next_rays_per_batch(uint32_t rays_per_batch, uint32_t target_batch_size, uint32_t measured_batch_size, uint32_t world_size, uint32_t max_rays_per_batch) {
+	uint32_t rpb = (uint32_t)((float)rays_per_batch * (float)target_batch_size / (float)measured_batch_size);
+	const uint32_t gran = 128u * (world_size ? world_size : 1u);
+	return std::min((rpb + gran - 1) / gran * gran, max_rays_per_batch);
+}
+
 // ExponentialDecayOptimizer::step (tcnn optimizers/exponential_decay.h:60-71): with s = nested->step() BEFORE the nested step,
 // "if (s >= decay_start && (s - decay_start) % decay_interval == 0 && s <= decay_end) factor *= decay_base".  The factor after all triggers up to s.
 float neus2_learning_rate_factor(const neus2_config* c, uint32_t s) {
@@ -921,14 +929,11 @@ int neus2_train_step_end(neus2_ctx* ctx, void* stream_, const uint32_t* counts_g
 		s.measured_batch_size = counts[2];
 		ctx->measured_before = counts[1];
 		if (get_loss_scalar) {
-			const float f = (float)counts[2] / (float)ctx->B;
-			s.loss = ctx->h_scalars[0] * f; s.ek_loss = ctx->h_scalars[1] * f; s.mask_loss = ctx->h_scalars[2] * f;
+			const float m = (float)counts[2], t = (float)ctx->B;      // sum * measured / target, left to right (:3429-3431)
+			s.loss = ctx->h_scalars[0] * m / t; s.ek_loss = ctx->h_scalars[1] * m / t; s.mask_loss = ctx->h_scalars[2] * m / t;
 			s.loss_valid = 1;
 		}
-		uint32_t rpb = (uint32_t)((float)ctx->rays_per_batch * (float)ctx->B / (float)counts[2]);
-		const uint32_t gran = 128u * ctx->cfg.world_size;
-		rpb = std::min((rpb + gran - 1) / gran * gran, ctx->cfg.max_rays_per_batch);
-		ctx->rays_per_batch = rpb;
+		ctx->rays_per_batch = neus2_next_rays_per_batch(ctx->rays_per_batch, ctx->B, counts[2], ctx->cfg.world_size, ctx->cfg.max_rays_per_batch);
 		if (pipelined && !density_grid_due(ctx->training_step)) {
 			// Generate the NEXT step's samples now, on the aux stream, behind this step's fused forward+backward kernel (which leaves no
 			// registers for anyone else) and concurrently with its weight-gradient GEMMs, optimizer and zero-fills.  They land in the
