@@ -127,8 +127,6 @@ def test_adam_ema_bit_exact(ctx_and_params):
         ctx.set_params(p)
 
 
-@pytest.mark.xfail(strict=False, reason="added after round 1's GPU budget was spent: first GPU run pending (the schedule itself is checked on the CPU against the "
-                                        "reference's ExponentialDecayOptimizer, tests/test_golden_snapshot.py)")
 def test_learning_rate_decay_reaches_the_adam_kernel():
     """ExponentialDecay around the main Adam: with decay_start 2 / interval 2 / base 0.5 the optimizer steps 1..6 run at lr x {1, 1, .5, .5, .25, .25}."""
     import ctypes as C
