@@ -166,6 +166,10 @@ int neus2_train_step_end(neus2_ctx* ctx, void* stream, const uint32_t* counts_gl
 int neus2_train_step_counts_ready(neus2_ctx* ctx, void* stream);
 int neus2_local_counts(neus2_ctx* ctx, void* stream, uint32_t counts_host[3]);
 int neus2_counts_device(neus2_ctx* ctx, uint32_t** counts_dev);
+/* The step's loss sums {rgb, eikonal, mask, -} over THIS rank's rays (fp32, device), reduced right behind the loss kernel on steps
+ * with training_step % 16 == 0 (*due = 1): a data-parallel caller all-reduces them in place before neus2_train_step_counts_ready /
+ * neus2_train_step_end reads them back; otherwise the reported losses are this rank's share. */
+int neus2_loss_scalars_device(neus2_ctx* ctx, float** sums_dev, int* due);
 /* convenience: begin + end on one GPU */
 int neus2_train_step(neus2_ctx* ctx, void* stream, neus2_step_stats* stats);
 
@@ -231,23 +235,32 @@ int neus2_mesh_attributes(neus2_ctx* ctx, void* stream, float* normals_out_dev, 
  * The optimizer step fused with its collective: rank r owns a contiguous 1/W slice of the parameters, sums that slice of every
  * rank's gradient buffer through NVLink peer loads, applies Adam + EMA to it and stores the new fp16 parameters / EMA values
  * into every rank's buffers.  Set-up: each rank exports CUDA IPC handles of its {gradient, fp16 parameter, EMA} buffers, the
- * host side exchanges them (torch.distributed all_gather), every rank attaches all of them.  Per step:
- *   neus2_train_step_begin -> [stream-ordered barrier, e.g. the all-reduce of neus2_counts_device] -> neus2_optimizer_step_sharded
- *   -> [stream-ordered barrier] -> neus2_train_step_end (which then skips its own optimizer call).
- * The fp32 master copy / Adam moments of a rank are current only for its own slice (neus2_optimizer_shard). */
-#define NEUS2_IPC_BUFFERS 3
+ * host side exchanges them (torch.distributed all_gather), every rank attaches all of them.  A fourth mapped buffer is a small
+ * per-rank sync block (flags + payload slots written by the peers), which carries the step's two cross-rank ordering points
+ * without a collective library call.  Per step:
+ *   neus2_train_step_begin -> neus2_peer_exchange (all backward passes done; counts / loss sums / DeltaNetwork gradient sums
+ *   summed over ranks, in rank order) -> neus2_train_step_counts_ready -> neus2_optimizer_step_sharded -> neus2_peer_barrier
+ *   (all slices stored everywhere) -> neus2_train_step_end (which then skips its own optimizer call).
+ * A caller without peer mappings all-reduces neus2_counts_device (+ neus2_loss_scalars_device, neus2_delta_gradients_device and
+ * the gradient buffer) with its collective library instead and lets neus2_train_step_end run the replicated optimizer.
+ * The fp32 master copy / Adam moments of a rank are current only for its own slice (neus2_optimizer_shard): gather the slices
+ * before serialising optimizer state (neus2_b200.parallel.sync_optimizer_state). */
+#define NEUS2_IPC_BUFFERS 4
 #define NEUS2_IPC_HANDLE_BYTES 64
 int neus2_ipc_export(neus2_ctx* ctx, unsigned char* handles /* NEUS2_IPC_BUFFERS x NEUS2_IPC_HANDLE_BYTES */);
 int neus2_ipc_attach(neus2_ctx* ctx, uint32_t rank, uint32_t world_size, const unsigned char* all_handles /* [world_size][NEUS2_IPC_BUFFERS][64] */);
 int neus2_optimizer_shard(const neus2_ctx* ctx, uint32_t rank, uint32_t world_size, uint64_t* begin, uint64_t* end);   /* parameter index range */
 int neus2_optimizer_step_sharded(neus2_ctx* ctx, void* stream, float loss_scale);
+int neus2_peer_exchange(neus2_ctx* ctx, void* stream);
+int neus2_peer_barrier(neus2_ctx* ctx, void* stream);
 
 /* ---- snapshot support: the state Testbed::save_snapshot serialises (src/testbed.cu:3144-3178; tcnn trainer.h:281-304,
  * optimizers/adam.h:424-445, ema.h:182-194) beyond what neus2_buffers / neus2_get_state / neus2_debug_buffer already expose. */
 int neus2_optimizer_buffers(neus2_ctx* ctx, float** first_moments_dev, float** second_moments_dev, uint32_t** param_steps_dev, uint32_t* current_step);
 int neus2_set_optimizer_step(neus2_ctx* ctx, uint32_t current_step);
-/* {n_rays_total, measured_batch_size_before_compaction, density_grid_ema_step, optimizer current_step} (testbed.h:598-612, 640) */
-int neus2_get_counters(neus2_ctx* ctx, uint32_t out[4]);
+/* {n_rays_total, measured_batch_size_before_compaction, density_grid_ema_step, optimizer current_step, measured_batch_size,
+ * m_canonical_training_step} (testbed.h:598-612, 640, 877) */
+int neus2_get_counters(neus2_ctx* ctx, uint32_t out[6]);
 /* load_snapshot's density-grid restore (testbed.cu:3222-3240): uploads the grid and rebuilds mean + occupancy bitfield. */
 int neus2_set_density_grid(neus2_ctx* ctx, void* stream, const float* density_grid_host, uint64_t n, uint32_t ema_step);
 
@@ -258,6 +271,11 @@ int neus2_set_density_grid(neus2_ctx* ctx, void* stream, const float* density_gr
  * `frozen_steps` steps (predict_global_movement_training_step) and the learning rate becomes `after_learning_rate` (> 0). */
 int neus2_next_frame(neus2_ctx* ctx, void* stream, float after_learning_rate, uint32_t frozen_steps);
 int neus2_get_time_frame(const neus2_ctx* ctx, uint32_t* current_training_time_frame, float* learning_rate);
+/* m_canonical_training_step BEFORE the step with index `training_step` of time frame `time_frame` runs (src/testbed_nerf.cu:3512-3527;
+ * reset by training_network_next_frame, src/testbed.cu:2015, 2050); frozen_steps = predict_global_movement_training_step (0 without
+ * global-movement prediction).  Host arithmetic.  It drives the occupancy-grid cadence (testbed.cu:2669-2670), the uniform-sampling
+ * phase (testbed_nerf.cu:4011) and the restart of the image round-robin (testbed_nerf.cu:3785). */
+uint32_t neus2_canonical_training_step(uint32_t time_frame, uint32_t frozen_steps, uint32_t training_step);
 
 /* "incremental_reinit_sdf_mlp" (src/testbed.cu:2065-2068; NerfNetwork::initialize_sdf_mlp_params, nerf_network.h:888-908): every
  * incremental_reinit_sdf_mlp_iters frames the fp32 master copy of the SDF MLP goes back to its geometric initialisation

@@ -69,6 +69,7 @@ class Context:
         if getattr(self, "_h", None):
             self._buffers = None
             self.__dict__.pop("_counts_views", None)
+            self.__dict__.pop("_loss_views", None)
             self._lib.neus2_ctx_destroy(self._h)
             self._h = None
 
@@ -120,7 +121,14 @@ class Context:
         m = np.ascontiguousarray(master, dtype=np.float32)
         check(self._lib.neus2_set_params(self._h, m.ctypes.data_as(C.c_void_p), C.c_uint64(m.size), C.c_int(1 if reset_optimizer else 0)))
 
+    def _require_whole_optimizer_state(self, what):
+        """With the sharded optimizer a rank's fp32 master copy / moments / step counters are current only for its own slice."""
+        if self.peers_attached and getattr(self, "_opt_synced_step", None) != self.get_state()["optimizer_step"]:
+            raise Neus2Error(f"{what}: the optimizer state of this rank is current only for its own parameter slice "
+                             "(sharded optimizer); call neus2_b200.parallel.sync_optimizer_state on every rank first")
+
     def get_params(self):
+        self._require_whole_optimizer_state("get_params")
         m = np.empty(self.n_params, dtype=np.float32)
         check(self._lib.neus2_get_params(self._h, m.ctypes.data_as(C.c_void_p), C.c_uint64(m.size)))
         return m
@@ -190,15 +198,17 @@ class Context:
         return views[p.value]
 
     # ---- data-parallel peers (fused gradient reduction + Adam over NVLink peer memory) ------------------------------------
+    IPC_BUFFERS = 4     # NEUS2_IPC_BUFFERS: gradients, fp16 parameters, EMA, sync block
+
     def ipc_export(self):
-        h = (C.c_ubyte * (3 * 64))()
+        h = (C.c_ubyte * (self.IPC_BUFFERS * 64))()
         check(self._lib.neus2_ipc_export(self._h, h))
         return bytes(h)
 
     def ipc_attach(self, rank, world_size, all_handles):
         """all_handles: list of world_size `bytes` objects as returned by ipc_export on each rank, in rank order."""
         blob = b"".join(all_handles)
-        assert len(blob) == world_size * 3 * 64
+        assert len(blob) == world_size * self.IPC_BUFFERS * 64
         buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
         check(self._lib.neus2_ipc_attach(self._h, C.c_uint32(rank), C.c_uint32(world_size), buf))
         self.peers_attached = True
@@ -210,6 +220,23 @@ class Context:
 
     def optimizer_step_sharded(self, loss_scale=128.0, stream=None):
         check(self._lib.neus2_optimizer_step_sharded(self._h, _stream(stream), C.c_float(loss_scale)))
+
+    def peer_exchange(self, stream=None):
+        """All ranks' backward passes are done; counts_device() / the loss sums / delta_gradients() now hold the sums over ranks."""
+        check(self._lib.neus2_peer_exchange(self._h, _stream(stream)))
+
+    def peer_barrier(self, stream=None):
+        """Stream-ordered barrier over the attached peers (their earlier work, including peer stores, has completed)."""
+        check(self._lib.neus2_peer_barrier(self._h, _stream(stream)))
+
+    def loss_scalars_device(self):
+        """(float32[4] device view of the step's {rgb, eikonal, mask, -} loss sums over this rank's rays, due) -- due: this step reports losses."""
+        p, due = C.c_void_p(), C.c_int()
+        check(self._lib.neus2_loss_scalars_device(self._h, C.byref(p), C.byref(due)))
+        views = self.__dict__.setdefault("_loss_views", {})
+        if p.value not in views:
+            views[p.value] = _torch().as_tensor(_DevArray(p.value, (4,), "<f4", None), device=f"cuda:{self.device}")
+        return views[p.value], bool(due.value)
 
     def train_step_counts_ready(self, stream=None):
         """Data-parallel: the all-reduce of counts_device() is enqueued; take the step's host read-back here (pipelined step)."""
@@ -232,10 +259,11 @@ class Context:
         ts, rpb = C.c_uint32(), C.c_uint32()
         rng = (C.c_uint64 * 2)()
         check(self._lib.neus2_get_state(self._h, C.byref(ts), C.byref(rpb), rng))
-        c = (C.c_uint32 * 4)()
+        c = (C.c_uint32 * 6)()
         check(self._lib.neus2_get_counters(self._h, c))
         return dict(training_step=ts.value, rays_per_batch=rpb.value, rng_state=(int(rng[0]), int(rng[1])), n_rays_total=int(c[0]),
-                    measured_before=int(c[1]), density_grid_ema_step=int(c[2]), optimizer_step=int(c[3]))
+                    measured_before=int(c[1]), density_grid_ema_step=int(c[2]), optimizer_step=int(c[3]), measured_batch_size=int(c[4]),
+                    canonical_training_step=int(c[5]))
 
     def set_state(self, training_step, rays_per_batch, n_rays_total=0, measured_before=0):
         check(self._lib.neus2_set_state(self._h, C.c_uint32(training_step), C.c_uint32(rays_per_batch), C.c_uint32(n_rays_total), C.c_uint32(measured_before)))

@@ -61,6 +61,7 @@ EXPORTS = [
     "neus2_ipc_export", "neus2_ipc_attach", "neus2_optimizer_shard", "neus2_optimizer_step_sharded",
     "neus2_optimizer_buffers", "neus2_set_optimizer_step", "neus2_set_density_grid", "neus2_mesh_attributes", "neus2_get_counters", "neus2_next_frame", "neus2_get_time_frame",
     "neus2_train_step_counts_ready", "neus2_reinit_sdf_mlp", "neus2_begin_global_movement", "neus2_set_delta_mode", "neus2_get_global_movement", "neus2_set_global_movement", "neus2_delta_gradients_device",
+    "neus2_loss_scalars_device", "neus2_peer_exchange", "neus2_peer_barrier", "neus2_canonical_training_step",
 ]
 
 _lib = None
@@ -81,6 +82,8 @@ def load():
     lib.neus2_learning_rate_factor.argtypes = [C.c_void_p, C.c_uint32]
     lib.neus2_next_rays_per_batch.restype = C.c_uint32
     lib.neus2_next_rays_per_batch.argtypes = [C.c_uint32] * 5
+    lib.neus2_canonical_training_step.restype = C.c_uint32
+    lib.neus2_canonical_training_step.argtypes = [C.c_uint32] * 3
     lib.neus2_launch_count.restype = C.c_uint64
     lib.neus2_n_params.argtypes = [C.c_void_p]
     lib.neus2_launch_count.argtypes = [C.c_void_p]

@@ -69,6 +69,7 @@ struct neus2_ctx {
 	// Testbed state
 	Pcg32 rng, density_grid_rng;
 	uint32_t training_step, rays_per_batch, n_rays_total, measured_before;
+	uint32_t measured_after;    // counters_rgb.measured_batch_size of the last step (compacted samples)
 	uint32_t step_rays, step_rays_local, step_n_rays_total;   // of the step in flight
 	// incremental (per-frame) training of a sequence: Testbed::training_network_next_frame (src/testbed.cu:2001-2082)
 	uint32_t time_frame;            // current_training_time_frame
@@ -111,6 +112,11 @@ struct neus2_ctx {
 	// data-parallel peers (CUDA IPC mappings of every rank's gradient / fp16 parameter / EMA buffers; slot [rank] = own)
 	uint32_t peer_world, peer_rank;
 	float* peer_grads[NEUS2_MAX_PEERS]; __half* peer_params[NEUS2_MAX_PEERS]; __half* peer_ema[NEUS2_MAX_PEERS];
+	PeerSyncBlock* sync_block;  // this rank's flags + payload slots, written by the peers (peer_sync.cu)
+	PeerSyncPtrs peer_sync;     // every rank's block
+	uint32_t exchange_epoch, barrier_epoch;
+	bool sharded_zeroed;        // the sharded optimizer of the step in flight cleared the gradient quads it consumed (on every rank)
+	bool barrier_zeroed;        // ... and the peer barrier behind it cleared the step's small accumulators and counters
 	bool optimizer_done;        // the sharded optimizer already ran for the step in flight
 	bool scratch_zeroed;        // train_step_end already enqueued the next step's zero-fills (counters, per-ray losses, gradients) behind its read-back
 	cudaEvent_t readback_event; // marks the end of train_step_end's device->host copies
@@ -131,6 +137,17 @@ static void stage_end(neus2_ctx* ctx, int st, cudaStream_t s);
 static const __half* inference_or_training_params(const neus2_ctx* ctx, int use_inference_params) {
 	return (use_inference_params && ctx->adam_step > 0) ? ctx->ema : ctx->params;
 }
+// m_train_canonical == false (testbed.cu:2075, 2659-2667): frames >= 1 train only the DeltaNetwork for their first frozen_steps steps
+static bool canonical_frozen(const neus2_ctx* ctx) { return ctx->time_frame >= 1 && ctx->training_step < ctx->frozen_steps; }
+// m_canonical_training_step (testbed_nerf.cu:3512-3527; reset to 0 by training_network_next_frame, testbed.cu:2015, 2050): equal to the
+// training step except on frames >= 1 with global-movement prediction, where it stays 0 through the delta-only phase and counts from
+// there.  It drives the occupancy-grid cadence (testbed.cu:2669), the uniform-sampling phase (testbed_nerf.cu:4011) and the restart of
+// the image round-robin (testbed_nerf.cu:3785).
+extern "C" uint32_t neus2_canonical_training_step(uint32_t time_frame, uint32_t frozen_steps, uint32_t training_step) {
+	if (time_frame >= 1 && frozen_steps > 0) return training_step > frozen_steps ? training_step - frozen_steps : 0u;
+	return training_step;
+}
+static uint32_t canonical_training_step(const neus2_ctx* ctx) { return neus2_canonical_training_step(ctx->time_frame, ctx->frozen_steps, ctx->training_step); }
 static int dmalloc(void** p, size_t bytes) {
 	CUDA_CHECK(cudaMalloc(p, bytes));
 	CUDA_CHECK(cudaMemset(*p, 0, bytes));
@@ -404,6 +421,7 @@ int neus2_ctx_create(const neus2_config* cfg, int device, neus2_ctx** out) {
 	CDM(ctx->grid_positions, 3 * G3n * ctx->n_cascades); CDM(ctx->grid_indices, G3n * ctx->n_cascades); CDM(ctx->grid_density, G3n * ctx->n_cascades);
 	CDM(ctx->bitfield, G3n / 8 * NERF_CASCADES); CDM(ctx->density_grid_mean, 1);
 	CTXCHECK(launch_adam_bias_table(nullptr, ctx->cfg.beta1, ctx->cfg.beta2, 1, ADAM_BIAS_TABLE - 1, ctx->adam_bias_table, ADAM_BIAS_TABLE));   // once: the optimizer only looks it up
+	CDM(ctx->sync_block, 1);
 	CDM(ctx->d_xform, DELTA_XFORM_FLOATS); CDM(ctx->d_acc, 12); CDM(ctx->d_master, 12); CDM(ctx->d_m1, 12); CDM(ctx->d_m2, 12); CDM(ctx->d_steps, 12); CDM(ctx->d_params, 12);
 	CTXCHECK(reset_delta(ctx, 0));
 	if (cudaMallocHost((void**)&ctx->h_counters, 16 * sizeof(uint32_t)) != cudaSuccess || cudaMallocHost((void**)&ctx->h_scalars, 4 * sizeof(float)) != cudaSuccess) {
@@ -413,7 +431,7 @@ int neus2_ctx_create(const neus2_config* cfg, int device, neus2_ctx** out) {
 	ctx->rng = Pcg32(cfg->seed);
 	ctx->density_grid_rng = Pcg32(ctx->rng.next_uint());
 	(void)ctx->rng.next_uint();   // tv_loss_rng
-	ctx->rays_per_batch = 1u << 12;
+	ctx->rays_per_batch = std::min(1u << 12, ctx->cfg.max_rays_per_batch);   // testbed.h:606, within what the per-ray arrays hold
 	ctx->measured_before = 0;
 	ctx->training_step = 0;
 	ctx->n_rays_total = 0;
@@ -434,13 +452,14 @@ void neus2_ctx_destroy(neus2_ctx* ctx) {
 		ctx->coords_compacted, ctx->loss, ctx->ek_loss, ctx->mask_loss, ctx->mlp_out, ctx->dloss, ctx->so.dOUT, ctx->so.H2, ctx->so.dH2, ctx->so.H1, ctx->so.dH1,
 		ctx->so.CIN, ctx->so.dSO, ctx->so.H0, ctx->so.dH0, ctx->so.X0, ctx->so.dI, ctx->partials, ctx->var_acc, ctx->w1row0_acc, ctx->scalar_tmp,
 		ctx->density_grid, ctx->density_grid_tmp, ctx->grid_positions, ctx->grid_indices, ctx->grid_density, ctx->bitfield, ctx->density_grid_mean,
-		ctx->d_xform, ctx->d_acc, ctx->d_master, ctx->d_m1, ctx->d_m2, ctx->d_steps, ctx->d_params, ctx->counters_buf[0], ctx->counters_buf[1]};
-	for (void* p : ptrs) if (p) cudaFree(p);
-	for (uint32_t r = 0; r < ctx->peer_world; ++r) if (r != ctx->peer_rank) {
+		ctx->d_xform, ctx->d_acc, ctx->d_master, ctx->d_m1, ctx->d_m2, ctx->d_steps, ctx->d_params, ctx->counters_buf[0], ctx->counters_buf[1], ctx->sync_block};
+	for (uint32_t r = 0; r < ctx->peer_world; ++r) if (r != ctx->peer_rank) {   // unmap the peers' buffers before this rank's own are freed
 		if (ctx->peer_grads[r]) cudaIpcCloseMemHandle(ctx->peer_grads[r]);
 		if (ctx->peer_params[r]) cudaIpcCloseMemHandle(ctx->peer_params[r]);
 		if (ctx->peer_ema[r]) cudaIpcCloseMemHandle(ctx->peer_ema[r]);
+		if (ctx->peer_sync.block[r]) cudaIpcCloseMemHandle(ctx->peer_sync.block[r]);
 	}
+	for (void* p : ptrs) if (p) cudaFree(p);
 	void* more[] = {ctx->r_queue, ctx->r_counters, ctx->r_ray_rgba, ctx->r_ray_depth, ctx->r_accumulate, ctx->r_ray_samples,
 		ctx->mc_block_counts, ctx->mc_counts, ctx->mc_vert_prefix, ctx->mc_indices, ctx->mc_verts};
 	for (void* p : more) if (p) cudaFree(p);
@@ -634,9 +653,18 @@ int neus2_backward(neus2_ctx* ctx, void* stream_, const float* coords, const voi
 int neus2_optimizer_step(neus2_ctx* ctx, void* stream, float loss_scale) {
 	CUDA_CHECK(cudaSetDevice(ctx->device));
 	const neus2_config& c = ctx->cfg;
-	++ctx->adam_step;
 	stage_begin(ctx, ST_OPT, (cudaStream_t)stream);
-	const int frozen = ctx->time_frame >= 1 && ctx->training_step < ctx->frozen_steps;   // m_train_canonical = false (testbed.cu:2659-2667)
+	if (canonical_frozen(ctx)) {
+		// "if (m_train_canonical) m_trainer->optimizer_step(...)" (testbed_nerf.cu:3503-3505): while only the DeltaNetwork trains, the canonical
+		// optimizer does not run at all -- Adam's step count, the learning-rate decay and the EMA (and with it the switch of the inference
+		// weights to the EMA copy) start with the first joint step.  The caller's zero-fills clear the unused gradients.
+		int rc_f = 0;
+		if (ctx->use_delta) rc_f = delta_optimizer_step(ctx, (cudaStream_t)stream, loss_scale);
+		stage_end(ctx, ST_OPT, (cudaStream_t)stream);
+		return rc_f;
+	}
+	++ctx->adam_step;
+	const int frozen = 0;
 	// inside a pipelined train step the kernel also clears what the next step starts from (consumed gradients, the small accumulators,
 	// this step's counters): no zero-fill launches are left between the optimizer and the next step's first kernel
 	const int fuse = ctx->fuse_zero_into_adam ? 1 : 0;
@@ -681,7 +709,7 @@ static int update_density_grid_on_stream(neus2_ctx* ctx, cudaStream_t stream) {
 	const uint32_t G3n = NERF_GRIDSIZE * NERF_GRIDSIZE * NERF_GRIDSIZE;
 	const uint32_t n_elements = G3n * ctx->n_cascades;
 	uint32_t n_uniform, n_nonuniform;
-	if (ctx->training_step < 256) { n_uniform = G3n * ctx->n_cascades; n_nonuniform = 0; }
+	if (canonical_training_step(ctx) < 256) { n_uniform = G3n * ctx->n_cascades; n_nonuniform = 0; }   // training_prep_nerf (:4011)
 	else { n_uniform = G3n / 4 * ctx->n_cascades; n_nonuniform = G3n / 4 * ctx->n_cascades; }
 	if (ctx->training_step == 0) {
 		ctx->density_grid_ema_step = 0;
@@ -704,10 +732,18 @@ static int update_density_grid_on_stream(neus2_ctx* ctx, cudaStream_t stream) {
 	return 0;
 }
 
-static int enqueue_loss_scalars(neus2_ctx* ctx, cudaStream_t stream) {
-	CHECK(launch_reduce_sum(stream, ctx->loss, ctx->step_rays, ctx->scalar_tmp + 0));
-	CHECK(launch_reduce_sum(stream, ctx->ek_loss, ctx->step_rays, ctx->scalar_tmp + 1));
-	CHECK(launch_reduce_sum(stream, ctx->mask_loss, ctx->step_rays, ctx->scalar_tmp + 2));
+// Loss scalars of a step (every 16th, testbed.cu:2714): the three per-ray arrays are summed on the device right behind the loss kernel
+// (reduce_loss_scalars); a data-parallel caller all-reduces the three partial sums in place (neus2_loss_scalars_device) before the
+// read-back (read_back_loss_scalars) is enqueued.
+static int reduce_loss_scalars(neus2_ctx* ctx, cudaStream_t stream) {
+	// the per-ray arrays hold THIS rank's rays (max_rays = max_rays_per_batch / world_size entries)
+	const uint32_t n = std::min(ctx->step_rays_local, ctx->max_rays);
+	CHECK(launch_reduce_sum(stream, ctx->loss, n, ctx->scalar_tmp + 0));
+	CHECK(launch_reduce_sum(stream, ctx->ek_loss, n, ctx->scalar_tmp + 1));
+	CHECK(launch_reduce_sum(stream, ctx->mask_loss, n, ctx->scalar_tmp + 2));
+	return 0;
+}
+static int read_back_loss_scalars(neus2_ctx* ctx, cudaStream_t stream) {
 	CUDA_CHECK(cudaMemcpyAsync(ctx->h_scalars, ctx->scalar_tmp, 3 * sizeof(float), cudaMemcpyDeviceToHost, stream));
 	return 0;
 }
@@ -725,7 +761,7 @@ static void plan_step(const neus2_ctx* ctx, uint32_t rank, uint32_t world_size, 
 	p.R = ctx->rays_per_batch;
 	p.n_local = p.R / world_size; p.ray_offset = rank * p.n_local;
 	p.max_inference = ctx->measured_before == 0 ? ctx->max_samples : (std::min(ctx->measured_before, ctx->max_samples) + 127u) / 128u * 128u;   // :3770-3775
-	p.n_rays_total = ctx->training_step == 0 ? 0 : ctx->n_rays_total;                    // :3785-3787
+	p.n_rays_total = (ctx->training_step == 0 || canonical_training_step(ctx) == 0) ? 0 : ctx->n_rays_total;   // :3785-3787
 	p.training_step = ctx->training_step;
 	p.rng_state = ctx->rng.state; p.rng_inc = ctx->rng.inc;
 }
@@ -735,9 +771,9 @@ static int launch_gen(neus2_ctx* ctx, cudaStream_t stream, const neus2_ctx::Step
 	                                        ctx->cone_angle_constant, p.max_inference, ctx->numsteps_all, ctx->base, ctx->slot, ctx->ray_indices, ctx->rays,
 	                                        ctx->numsteps, ctx->coords, counters, ctx->windows, ctx->n_windows, ctx->ray_setup);
 }
-static bool density_grid_due(uint32_t training_step) {
-	const uint32_t n_prep_to_skip = std::min(std::max(training_step / 16u, 1u), 16u);   // testbed.cu:2669
-	return training_step % n_prep_to_skip == 0;
+static bool density_grid_due(uint32_t canonical_training_step) {
+	const uint32_t n_prep_to_skip = std::min(std::max(canonical_training_step / 16u, 1u), 16u);   // testbed.cu:2669-2670: m_canonical_training_step
+	return canonical_training_step % n_prep_to_skip == 0;
 }
 
 int neus2_train_step_begin(neus2_ctx* ctx, void* stream_, uint32_t rank, uint32_t world_size) {
@@ -751,7 +787,7 @@ int neus2_train_step_begin(neus2_ctx* ctx, void* stream_, uint32_t rank, uint32_
 	neus2_set_training_step(ctx, ctx->time_frame >= 1 ? (int32_t)ctx->training_step - (int32_t)ctx->frozen_steps : (int32_t)ctx->training_step);   // testbed.cu:2651-2657
 	ctx->step_density_updated = false;
 	stage_begin(ctx, ST_STEP, stream);
-	if (density_grid_due(ctx->training_step)) {
+	if (density_grid_due(canonical_training_step(ctx))) {
 		stage_begin(ctx, ST_GRID, stream);
 		CHECK(update_density_grid_on_stream(ctx, stream));
 		stage_end(ctx, ST_GRID, stream);
@@ -779,10 +815,10 @@ int neus2_train_step_begin(neus2_ctx* ctx, void* stream_, uint32_t rank, uint32_
 		}
 	}
 	ctx->step_used_prefetch = have_samples;
-	if (!have_samples && !pre_zeroed) CHECK(zero_step_scratch(ctx, stream, R));
+	if (n_local > ctx->max_rays) FAIL("rays_per_batch exceeds max_rays_per_batch");
+	if (!have_samples && !pre_zeroed) CHECK(zero_step_scratch(ctx, stream, n_local));
 	if (ctx->measured_before == 0) ctx->measured_before = ctx->max_samples;
-	if (ctx->training_step == 0) ctx->n_rays_total = 0;
-	ctx->n_rays_total += R;
+	ctx->n_rays_total = n_rays_total + R;   // reset first while the canonical step is 0 (:3785-3790)
 	ctx->step_rays = R; ctx->step_rays_local = n_local; ctx->step_n_rays_total = n_rays_total;
 	const uint64_t st[2] = {plan.rng_state, plan.rng_inc};
 	if (!have_samples) {
@@ -814,9 +850,11 @@ int neus2_train_step_begin(neus2_ctx* ctx, void* stream_, uint32_t rank, uint32_
 		// every number the host needs from this step exists now: read it back BEFORE the backward pass is queued, so that the host's
 		// turnaround (and the next step's sample generation) hides behind the backward pass instead of following it
 		CUDA_CHECK(cudaMemcpyAsync(ctx->counts_global, ctx->counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
-		if (ctx->training_step % 16 == 0) CHECK(enqueue_loss_scalars(ctx, stream));
+		if (ctx->training_step % 16 == 0) { CHECK(reduce_loss_scalars(ctx, stream)); CHECK(read_back_loss_scalars(ctx, stream)); }
 		CUDA_CHECK(cudaMemcpyAsync(ctx->h_counters, ctx->counters, 12 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
 		CUDA_CHECK(cudaEventRecord(ctx->ev_counts, stream));
+	} else if (ctx->training_step % 16 == 0) {
+		CHECK(reduce_loss_scalars(ctx, stream));   // read back by neus2_train_step_counts_ready / neus2_train_step_end, after the caller's all-reduce
 	}
 	// NEUS2_HP_STREAM=1 moves weight gradients + Adam to a highest-priority stream so that the block scheduler serves them before the
 	// prefetched sample generation.  Measured (B200, same box, 2 runs each): weight gradients 0.122 -> 0.111 ms, but the two extra
@@ -832,6 +870,15 @@ int neus2_train_step_begin(neus2_ctx* ctx, void* stream_, uint32_t rank, uint32_
 int neus2_counts_device(neus2_ctx* ctx, uint32_t** counts_dev) {
 	if (!counts_dev) FAIL("null argument");
 	*counts_dev = ctx->counts_global;
+	return 0;
+}
+
+// The step's three loss sums {rgb, eikonal, mask, -} (fp32, this rank's rays), valid between neus2_train_step_begin and the read-back on
+// steps where training_step % 16 == 0 (*due): a data-parallel caller all-reduces them in place next to the counts.
+int neus2_loss_scalars_device(neus2_ctx* ctx, float** sums_dev, int* due) {
+	if (!sums_dev) FAIL("null argument");
+	*sums_dev = ctx->scalar_tmp;
+	if (due) *due = ctx->training_step % 16 == 0 ? 1 : 0;
 	return 0;
 }
 
@@ -851,7 +898,7 @@ int neus2_train_step_counts_ready(neus2_ctx* ctx, void* stream_) {
 	cudaStream_t stream = (cudaStream_t)stream_;
 	CUDA_CHECK(cudaSetDevice(ctx->device));
 	if (!ctx->cfg.prefetch_next_samples || ctx->step_pipelined) return 0;
-	if (ctx->training_step % 16 == 0) CHECK(enqueue_loss_scalars(ctx, stream));
+	if (ctx->training_step % 16 == 0) CHECK(read_back_loss_scalars(ctx, stream));
 	CUDA_CHECK(cudaMemcpyAsync(ctx->h_counters, ctx->counters, 12 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
 	CUDA_CHECK(cudaEventRecord(ctx->ev_counts, stream));
 	ctx->step_pipelined = true;
@@ -867,7 +914,10 @@ int neus2_train_step_end(neus2_ctx* ctx, void* stream_, const uint32_t* counts_g
 	// single-GPU pipelined step: our own Adam kernel runs next and also clears what the next step starts from
 	static int no_fused_zero = -1;   // NEUS2_NO_FUSED_ZERO=1: A/B switch (zero-fill launches behind the optimizer instead)
 	if (no_fused_zero < 0) { const char* e = getenv("NEUS2_NO_FUSED_ZERO"); no_fused_zero = e ? atoi(e) : 0; }
-	const bool fused_zero = pipelined && c.world_size == 1 && !ctx->optimizer_done && !no_fused_zero;
+	// data-parallel: the sharded optimizer + the peer barrier behind it did the same (sharded_zeroed && barrier_zeroed)
+	const bool fused_zero = pipelined && !no_fused_zero && !canonical_frozen(ctx) &&
+	                        (ctx->optimizer_done ? (ctx->sharded_zeroed && ctx->barrier_zeroed) : c.world_size == 1);
+	ctx->sharded_zeroed = ctx->barrier_zeroed = false;
 	if (!ctx->optimizer_done) {
 		ctx->fuse_zero_into_adam = fused_zero;
 		const int rc_opt = neus2_optimizer_step(ctx, ctx->step_on_hp ? (void*)ctx->hp_stream : stream_, c.loss_scale);   // testbed_nerf.cu:3503-3505
@@ -881,7 +931,7 @@ int neus2_train_step_end(neus2_ctx* ctx, void* stream_, const uint32_t* counts_g
 	}
 	ctx->optimizer_done = false;
 	if (!pipelined) {
-		if (get_loss_scalar) CHECK(enqueue_loss_scalars(ctx, stream));
+		if (get_loss_scalar) CHECK(read_back_loss_scalars(ctx, stream));
 		stage_end(ctx, ST_STEP, stream);
 		// the one structurally required host sync per step (:3412-3416): local counters + the (possibly all-reduced) global ones
 		// counters[0..3] local {kept, N_u, compacted}, [4..7] first-pass work counters, [8..11] the (all-reduced) global counts
@@ -934,7 +984,7 @@ int neus2_train_step_end(neus2_ctx* ctx, void* stream_, const uint32_t* counts_g
 			s.loss_valid = 1;
 		}
 		ctx->rays_per_batch = neus2_next_rays_per_batch(ctx->rays_per_batch, ctx->B, counts[2], ctx->cfg.world_size, ctx->cfg.max_rays_per_batch);
-		if (pipelined && !density_grid_due(ctx->training_step)) {
+		if (pipelined && !density_grid_due(canonical_training_step(ctx))) {
 			// Generate the NEXT step's samples now, on the aux stream, behind this step's fused forward+backward kernel (which leaves no
 			// registers for anyone else) and concurrently with its weight-gradient GEMMs, optimizer and zero-fills.  They land in the
 			// other counter buffer; the sample buffers themselves were last read by this step's loss kernel, long done.
@@ -1145,7 +1195,7 @@ int neus2_ipc_export(neus2_ctx* ctx, unsigned char* handles) {
 	CUDA_CHECK(cudaSetDevice(ctx->device));
 	if (!handles) FAIL("null argument");
 	static_assert(sizeof(cudaIpcMemHandle_t) == NEUS2_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
-	void* bufs[NEUS2_IPC_BUFFERS] = {ctx->grads, ctx->params, ctx->ema};
+	void* bufs[NEUS2_IPC_BUFFERS] = {ctx->grads, ctx->params, ctx->ema, ctx->sync_block};
 	for (int k = 0; k < NEUS2_IPC_BUFFERS; ++k) {
 		cudaIpcMemHandle_t h;
 		CUDA_CHECK(cudaIpcGetMemHandle(&h, bufs[k]));
@@ -1161,16 +1211,17 @@ int neus2_ipc_attach(neus2_ctx* ctx, uint32_t rank, uint32_t world, const unsign
 	if (world > NEUS2_MAX_PEERS) FAIL("at most 8 peers (one NVSwitch domain)");
 	if (ctx->peer_world) FAIL("peers are already attached");
 	for (uint32_t r = 0; r < world; ++r) {
-		if (r == rank) { ctx->peer_grads[r] = ctx->grads; ctx->peer_params[r] = ctx->params; ctx->peer_ema[r] = ctx->ema; continue; }
+		if (r == rank) { ctx->peer_grads[r] = ctx->grads; ctx->peer_params[r] = ctx->params; ctx->peer_ema[r] = ctx->ema; ctx->peer_sync.block[r] = ctx->sync_block; continue; }
 		void* ptrs[NEUS2_IPC_BUFFERS];
 		for (int k = 0; k < NEUS2_IPC_BUFFERS; ++k) {
 			cudaIpcMemHandle_t h;
 			memcpy(&h, all_handles + ((size_t)r * NEUS2_IPC_BUFFERS + k) * NEUS2_IPC_HANDLE_BYTES, NEUS2_IPC_HANDLE_BYTES);
 			CUDA_CHECK(cudaIpcOpenMemHandle(&ptrs[k], h, cudaIpcMemLazyEnablePeerAccess));
 		}
-		ctx->peer_grads[r] = (float*)ptrs[0]; ctx->peer_params[r] = (__half*)ptrs[1]; ctx->peer_ema[r] = (__half*)ptrs[2];
+		ctx->peer_grads[r] = (float*)ptrs[0]; ctx->peer_params[r] = (__half*)ptrs[1]; ctx->peer_ema[r] = (__half*)ptrs[2]; ctx->peer_sync.block[r] = (PeerSyncBlock*)ptrs[3];
 	}
 	ctx->peer_world = world; ctx->peer_rank = rank;
+	ctx->exchange_epoch = ctx->barrier_epoch = 0;
 	return 0;
 }
 
@@ -1186,16 +1237,54 @@ int neus2_optimizer_step_sharded(neus2_ctx* ctx, void* stream, float loss_scale)
 	CUDA_CHECK(cudaSetDevice(ctx->device));
 	if (!ctx->peer_world) FAIL("no peers attached: call neus2_ipc_attach first");
 	const neus2_config& c = ctx->cfg;
-	++ctx->adam_step;
 	stage_begin(ctx, ST_OPT, (cudaStream_t)stream);
-	const int frozen = ctx->time_frame >= 1 && ctx->training_step < ctx->frozen_steps;
+	if (canonical_frozen(ctx)) {   // as in neus2_optimizer_step: the canonical optimizer is skipped, every rank steps its DeltaNetwork replica
+		int rc_f = 0;
+		if (ctx->use_delta) rc_f = delta_optimizer_step(ctx, (cudaStream_t)stream, loss_scale);
+		stage_end(ctx, ST_OPT, (cudaStream_t)stream);
+		ctx->optimizer_done = true;
+		return rc_f;
+	}
+	++ctx->adam_step;
+	const int frozen = 0;
 	const float lr = ctx->learning_rate * neus2_learning_rate_factor(&c, ctx->adam_step - 1);
+	// inside a pipelined data-parallel step (neus2_train_step_counts_ready has been called) the kernel also clears the gradient quads it
+	// consumed, on every rank: with the peer barrier's small zero-fills no memset is left between the optimizer and the next step
+	static int no_fused_zero = -1;
+	if (no_fused_zero < 0) { const char* e = getenv("NEUS2_NO_FUSED_ZERO"); no_fused_zero = e ? atoi(e) : 0; }
+	const int zero_grads = ctx->step_pipelined && !no_fused_zero ? 1 : 0;
 	const int rc_ = launch_adam_ema_p2p((cudaStream_t)stream, ctx->n_params, ctx->pl.off_grid, ctx->peer_rank, ctx->peer_world, loss_scale, lr, c.beta1, c.beta2,
-	                                    c.epsilon, c.l2_reg, c.ema_decay, ctx->adam_step, ctx->peer_grads, ctx->peer_params, ctx->peer_ema, ctx->master, ctx->m1, ctx->m2, ctx->steps, ctx->adam_bias_table, ADAM_BIAS_TABLE, frozen);
+	                                    c.epsilon, c.l2_reg, c.ema_decay, ctx->adam_step, ctx->peer_grads, ctx->peer_params, ctx->peer_ema, ctx->master, ctx->m1, ctx->m2, ctx->steps, ctx->adam_bias_table, ADAM_BIAS_TABLE, frozen, zero_grads);
+	ctx->sharded_zeroed = rc_ == 0 && zero_grads;
 	if (rc_ == 0 && ctx->use_delta) CHECK(delta_optimizer_step(ctx, (cudaStream_t)stream, loss_scale));   // every rank steps its replica on the all-reduced sums
 	stage_end(ctx, ST_OPT, (cudaStream_t)stream);
 	ctx->optimizer_done = true;
 	return rc_;
+}
+
+// The exchange of a data-parallel step: orders every rank's backward pass before anything that follows on the stream and leaves, on
+// every rank, the sums over ranks (taken in rank order: identical bits everywhere) of the step's counts in neus2_counts_device(), of
+// the loss sums (steps with training_step % 16 == 0) and of the DeltaNetwork's gradient sums (while global movement trains).
+// All ranks must call it the same number of times.  Replaces three stream-ordered NCCL all-reduces.
+int neus2_peer_exchange(neus2_ctx* ctx, void* stream) {
+	CUDA_CHECK(cudaSetDevice(ctx->device));
+	if (!ctx->peer_world) FAIL("no peers attached: call neus2_ipc_attach first");
+	return launch_peer_exchange((cudaStream_t)stream, ++ctx->exchange_epoch, ctx->peer_rank, ctx->peer_world, ctx->peer_sync, ctx->counters, ctx->counts_global,
+	                            ctx->scalar_tmp, ctx->training_step % 16 == 0 ? 1 : 0, ctx->use_delta ? ctx->d_acc : nullptr);
+}
+
+// Barrier over the peers, stream-ordered: everything the peers enqueued before THEIR call has completed (and its peer stores have landed)
+// before anything enqueued after this call starts.  Behind a sharded optimizer step that cleared its gradients it also clears the step's
+// small accumulators and counters.
+int neus2_peer_barrier(neus2_ctx* ctx, void* stream) {
+	CUDA_CHECK(cudaSetDevice(ctx->device));
+	if (!ctx->peer_world) FAIL("no peers attached: call neus2_ipc_attach first");
+	PeerZero z = {};
+	if (ctx->sharded_zeroed) {
+		z.p[0] = (uint32_t*)ctx->var_acc; z.n[0] = 1u; z.p[1] = (uint32_t*)ctx->w1row0_acc; z.n[1] = 64u; z.p[2] = ctx->counters; z.n[2] = 8u;
+		ctx->barrier_zeroed = true;
+	}
+	return launch_peer_barrier((cudaStream_t)stream, ++ctx->barrier_epoch, ctx->peer_rank, ctx->peer_world, ctx->peer_sync, z);
 }
 
 // ---- snapshot support (Testbed::save_snapshot / load_snapshot, src/testbed.cu:3144-3266; Trainer / Adam / EMA serialize) ----
@@ -1250,8 +1339,9 @@ int neus2_mesh_attributes(neus2_ctx* ctx, void* stream_, float* normals_out, flo
 	return 0;
 }
 
-int neus2_get_counters(neus2_ctx* ctx, uint32_t out[4]) {
+int neus2_get_counters(neus2_ctx* ctx, uint32_t out[6]) {
 	out[0] = ctx->n_rays_total; out[1] = ctx->measured_before; out[2] = ctx->density_grid_ema_step; out[3] = ctx->adam_step;
+	out[4] = ctx->measured_after; out[5] = canonical_training_step(ctx);
 	return 0;
 }
 
@@ -1284,7 +1374,7 @@ int neus2_next_frame(neus2_ctx* ctx, void* stream_, float after_learning_rate, u
 	if (after_learning_rate > 0.f) ctx->learning_rate = after_learning_rate;
 	ctx->training_step = 0;
 	ctx->n_rays_total = 0;
-	ctx->rays_per_batch = 1u << 12;
+	ctx->rays_per_batch = std::min(1u << 12, ctx->cfg.max_rays_per_batch);   // testbed.h:606, within what the per-ray arrays hold
 	ctx->measured_before = 0;
 	ctx->rng = Pcg32(ctx->cfg.seed);
 	return 0;

@@ -121,7 +121,7 @@ int launch_adam_ema(cudaStream_t stream, uint64_t n, uint64_t n_matrix, float lo
 // Ordering between ranks (backward finished before peers read; stores landed before peers' next forward) is the caller's:
 // a stream-ordered tiny collective on either side (neus2_b200/parallel.py).
 // ------------------------------------------------------------------------------------------------------------------------
-struct PeerPtrs { const float* grads[NEUS2_MAX_PEERS]; __half* params[NEUS2_MAX_PEERS]; __half* ema[NEUS2_MAX_PEERS]; };
+struct PeerPtrs { float* grads[NEUS2_MAX_PEERS]; __half* params[NEUS2_MAX_PEERS]; __half* ema[NEUS2_MAX_PEERS]; };
 
 __global__ void __launch_bounds__(256)
 k_adam_ema_p2p(uint64_t q0, uint64_t q1, uint64_t n_matrix4, AdamHyper h, int world, PeerPtrs peers,
@@ -135,6 +135,11 @@ k_adam_ema_p2p(uint64_t q0, uint64_t q1, uint64_t n_matrix4, AdamHyper h, int wo
 	float4 g4 = gr[0];
 	#pragma unroll
 	for (int r = 1; r < NEUS2_MAX_PEERS; ++r) if (r < world) { g4.x += gr[r].x; g4.y += gr[r].y; g4.z += gr[r].z; g4.w += gr[r].w; }
+	if (h.zero_grads) {   // nobody else reads this quad of any rank's buffer: clear the consumed ones in place (the next backward pass starts from zeros)
+		#pragma unroll
+		for (int r = 0; r < NEUS2_MAX_PEERS; ++r)
+			if (r < world && (gr[r].x != 0.f || gr[r].y != 0.f || gr[r].z != 0.f || gr[r].w != 0.f)) reinterpret_cast<float4*>(peers.grads[r])[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+	}
 	uint2 pw = reinterpret_cast<const uint2*>(peers.params[0])[q];     // slot 0 is always this rank's own buffer
 	__half* ph = reinterpret_cast<__half*>(&pw);
 	const float g[4] = {g4.x, g4.y, g4.z, g4.w};
@@ -173,13 +178,13 @@ k_adam_ema_p2p(uint64_t q0, uint64_t q1, uint64_t n_matrix4, AdamHyper h, int wo
 }
 
 int launch_adam_ema_p2p(cudaStream_t stream, uint64_t n, uint64_t n_matrix, uint32_t rank, uint32_t world, float loss_scale, float lr, float beta1, float beta2,
-                        float eps, float l2_reg, float ema_decay, uint32_t ema_step, const float* const* grads_peers, __half* const* params_peers,
-                        __half* const* ema_peers, float* master, float* m1, float* m2, uint32_t* steps, float* bias_table, uint32_t bias_table_size, int frozen) {
+                        float eps, float l2_reg, float ema_decay, uint32_t ema_step, float* const* grads_peers, __half* const* params_peers,
+                        __half* const* ema_peers, float* master, float* m1, float* m2, uint32_t* steps, float* bias_table, uint32_t bias_table_size, int frozen, int zero_grads) {
 	const float ema_debias_old = 1 - (float)pow((double)ema_decay, (double)(ema_step - 1));
 	const float ema_debias_new = 1.0f / (1 - (float)pow((double)ema_decay, (double)ema_step));
 	if (n % 4 != 0 || n_matrix % 4 != 0) { neus_set_error("parameter counts must be multiples of 4", __FILE__, __LINE__); return -1; }
 	if (world < 1 || world > NEUS2_MAX_PEERS || rank >= world) { neus_set_error("bad rank / world size for the sharded optimizer", __FILE__, __LINE__); return -1; }
-	AdamHyper h = {loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, ema_debias_old, ema_debias_new, ema_step, bias_table, bias_table_size, frozen};
+	AdamHyper h = {loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, ema_debias_old, ema_debias_new, ema_step, bias_table, bias_table_size, frozen, zero_grads};
 	uint64_t q0, q1;
 	optimizer_shard(n / 4, rank, world, &q0, &q1);
 	PeerPtrs pp;

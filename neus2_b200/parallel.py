@@ -32,39 +32,52 @@ def attach_peers(ctx, rank, world_size, group=None):
     ctx.ipc_attach(rank, world_size, handles)
 
 
-_barrier_token = {}
-
-
-def _stream_barrier(device, group=None):
-    """Stream-ordered cross-rank barrier: a 4-byte all-reduce enqueued behind the work already on the stream (no host wait)."""
+def sync_optimizer_state(ctx, rank, world_size, group=None):
+    """With the sharded optimizer (attach_peers) rank r keeps the fp32 master weights, both Adam moments and the per-parameter step
+    counters current only for ITS slice of the parameters.  Before anything reads them whole (snapshot.save with optimizer state,
+    Context.get_params) every rank calls this: each slice is broadcast from its owner, after which all ranks hold the complete,
+    identical optimizer state.  Collective; checkpoint-time cost (4 buffers x world_size broadcasts)."""
     import torch
-    t = _barrier_token.get(device)
-    if t is None:
-        t = _barrier_token[device] = torch.zeros(1, dtype=torch.int32, device=device)
-    allreduce_sum_(t, group)
+    import torch.distributed as dist
+    if world_size > 1 and ctx.peers_attached:
+        master = ctx.buffers()[0]
+        m1, m2, steps, _ = ctx.optimizer_buffers()
+        torch.cuda.synchronize(master.device)
+        for r in range(world_size):
+            b, e = ctx.optimizer_shard(r, world_size)
+            for buf in (master, m1, m2, steps):
+                dist.broadcast(buf[b:e], src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+        torch.cuda.synchronize(master.device)
+    ctx._opt_synced_step = ctx.get_state()["optimizer_step"]
 
 
 def train_step(ctx, rank=0, world_size=1, group=None):
-    """One data-parallel Testbed::train() step on this rank's Context.  Returns the step stats (global counts).
+    """One data-parallel Testbed::train() step on this rank's Context.  Returns the step stats (global counts, global losses).
 
-    With peers attached (attach_peers) the optimizer is fused with its collective: every rank sums its 1/W parameter slice of
-    all ranks' gradients through NVLink peer loads inside the Adam kernel and stores the new fp16 parameters into every
-    rank's buffers -- no all-reduce of the 42 MB gradient buffer, and 1/W of the optimizer-state traffic per GPU.  Without
-    peers it falls back to an NCCL all-reduce followed by the replicated Adam (same arithmetic, W = 2 bit-identical)."""
+    With peers attached (attach_peers) no collective library call is left on the step's path: the two cross-rank ordering points are
+    flag exchanges over mapped peer memory (a few microseconds; the first one also carries the sums of the step's counts, loss sums and
+    DeltaNetwork gradient sums), and the optimizer is fused with its collective: every rank sums its 1/W parameter slice of all ranks'
+    gradients through NVLink peer loads inside the Adam kernel, stores the new fp16 parameters into every rank's buffers and clears the
+    gradients it consumed -- no all-reduce of the 42 MB gradient buffer, 1/W of the optimizer-state traffic per GPU, no memsets.
+    Without peers it falls back to NCCL (or gloo) all-reduces followed by the replicated Adam (same arithmetic)."""
     if world_size == 1:
         return ctx.train_step()
     ctx.train_step_begin(rank, world_size)
     # everything below is enqueued behind the backward pass on the step's stream: no host round trip between begin and end
-    counts = ctx.counts_device()
-    allreduce_sum_(counts, group)                # {rays kept, samples, compacted}; also orders "all backward passes done" before the peer loads
-    ctx.train_step_counts_ready()                # pipelined step: the host read-back is taken here; the next step's samples are generated beside the optimizer
-    if ctx.global_movement_active:
-        # the DeltaNetwork's 9 gradient sums (48 bytes): every rank then steps its replica of the 12 parameters identically
-        allreduce_sum_(ctx.delta_gradients(), group)
     if ctx.peers_attached:
+        ctx.peer_exchange()                      # all backward passes done; {rays kept, samples, compacted}, loss sums, delta sums summed over ranks
+        ctx.train_step_counts_ready()            # pipelined step: the host read-back is taken here; the next step's samples are generated beside the optimizer
         ctx.optimizer_step_sharded(ctx.cfg.loss_scale)
-        _stream_barrier(counts.device, group)    # peers' stores have landed / peers are done reading before anyone starts the next step
+        ctx.peer_barrier()                       # peers' stores have landed / peers are done reading before anyone starts the next step
     else:
+        allreduce_sum_(ctx.counts_device(), group)
+        sums, due = ctx.loss_scalars_device()
+        if due:
+            allreduce_sum_(sums, group)          # every 16th step: the reported losses are those of the global batch
+        ctx.train_step_counts_ready()
+        if ctx.global_movement_active:
+            # the DeltaNetwork's 9 gradient sums (48 bytes): every rank then steps its replica of the 12 parameters identically
+            allreduce_sum_(ctx.delta_gradients(), group)
         allreduce_sum_(ctx.buffers()[3], group)  # 10,559,396 fp32 gradients over NVLink
     return ctx.train_step_end()
 

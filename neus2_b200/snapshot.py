@@ -23,7 +23,17 @@ def read(path):
         return msgpack.unpackb(f.read(), raw=False, strict_map_key=False)
 
 
-def save(ctx, path, network_config, include_optimizer_state=False, loss=0.0, aabb_scale=1):
+def _n_cascades(aabb_scale):
+    """m_nerf.max_cascade + 1 (testbed_nerf.cu:3069-3073): the smallest c with 2^c >= aabb_scale, plus one."""
+    c = 0
+    while (1 << c) < int(aabb_scale):
+        c += 1
+    return c + 1
+
+
+def save(ctx, path, network_config, include_optimizer_state=False, loss=0.0, aabb_scale=None):
+    """aabb_scale: defaults to the context's.  Not written: `nerf.dataset` (the reference stores the camera metadata so that a snapshot
+    can be rendered without its dataset, testbed.cu:3170; here a snapshot is always loaded next to the dataset it was trained on)."""
     import msgpack
     import torch
     master, params, ema, _ = ctx.buffers()
@@ -34,19 +44,24 @@ def save(ctx, path, network_config, include_optimizer_state=False, loss=0.0, aab
     inference = ema if current_step > 0 else params          # before the first optimizer step the inference weights are the initial ones
     snap = {"n_params": int(ctx.n_params), "params_binary": inference.cpu().numpy().tobytes()}
     if include_optimizer_state:
+        require_whole = getattr(ctx, "_require_whole_optimizer_state", None)    # sharded optimizer: parallel.sync_optimizer_state first
+        if require_whole is not None:
+            require_whole("snapshot.save(include_optimizer_state=True)")
         adam = {"current_step": int(current_step), "base_learning_rate": float(ctx.cfg.learning_rate),
                 "first_moments_binary": m1.cpu().numpy().tobytes(), "second_moments_binary": m2.cpu().numpy().tobytes(),
                 "param_steps_binary": steps.cpu().numpy().tobytes()}
         from ._lib import load
-        factor = float(load().neus2_learning_rate_factor(C.byref(ctx.cfg), C.c_uint32(max(int(current_step), 1) - 1))) if hasattr(ctx.cfg, "decay_start") else 1.0
+        # m_learning_rate_factor after current_step steps; a duck-typed config without the decay schedule (tests) has not decayed
+        factor = float(load().neus2_learning_rate_factor(C.byref(ctx.cfg), C.c_uint32(max(int(current_step), 1) - 1))) if isinstance(ctx.cfg, C.Structure) else 1.0
         snap["optimizer"] = {"nested": {"nested": adam, "learning_rate": float(ctx.cfg.learning_rate), "learning_rate_factor": factor},
                              "weights_ema_binary": ema.cpu().numpy().tobytes()}
-    grid = ctx.debug_buffer("density_grid", "<f4", (128 ** 3,)).cpu().numpy()
+    n_cascades = _n_cascades(ctx.cfg.aabb_scale)                              # the grid the context holds
+    grid = ctx.debug_buffer("density_grid", "<f4", (128 ** 3 * n_cascades,)).cpu().numpy()   # all cascades (testbed.cu:3163: m_nerf.density_grid)
     snap["density_grid_size"] = 128
     snap["density_grid_ema_step"] = int(state["density_grid_ema_step"])    # extension: the reference restarts its decay counter
     snap["density_grid_binary"] = grid.astype(np.float16).tobytes()
-    snap["nerf"] = {"aabb_scale": int(aabb_scale),
-                    "rgb": {"rays_per_batch": int(state["rays_per_batch"]), "measured_batch_size": int(ctx.cfg.batch_size),
+    snap["nerf"] = {"aabb_scale": int(aabb_scale if aabb_scale else ctx.cfg.aabb_scale),
+                    "rgb": {"rays_per_batch": int(state["rays_per_batch"]), "measured_batch_size": int(state.get("measured_batch_size", 0)),
                             "measured_batch_size_before_compaction": int(state.get("measured_before", 0))}}
     snap["training_step"] = int(state["training_step"])
     snap["n_rays_total"] = int(state["n_rays_total"])                       # extension (image round-robin position)
@@ -98,7 +113,7 @@ def restore(ctx, snap):
         ema.copy_(torch.from_numpy(np.frombuffer(opt["weights_ema_binary"], dtype=np.float16).copy()).to(dev))
         ctx.set_optimizer_step(int(adam["current_step"]))
     grid16 = np.frombuffer(snap["density_grid_binary"], dtype=np.float16)
-    if grid16.size == 128 ** 3:
+    if grid16.size == 128 ** 3 * _n_cascades(ctx.cfg.aabb_scale):                 # testbed.cu:3226-3230
         ctx.set_density_grid(grid16.astype(np.float32), ema_step=int(snap.get("density_grid_ema_step", 0)))
     elif grid16.size != 0:
         raise RuntimeError("Incompatible number of grid cascades.")

@@ -171,12 +171,14 @@ def test_render_bands_and_lattice_slabs_reassemble(tmp_path, world):
 class _FakeTrainCtx:
     """Records the order in which parallel.train_step drives a context, with CPU tensors standing in for the device buffers."""
 
-    def __init__(self, rank, peers, delta):
+    def __init__(self, rank, peers, delta, due=True):
         self.rank, self.peers_attached, self.global_movement_active = rank, peers, delta
         self.calls = []
         self.counts = torch.tensor([10 + rank, 100 + rank, 50 + rank, 0], dtype=torch.int32)
         self.grads = torch.full((8,), float(rank + 1))
         self.dgrads = torch.arange(12, dtype=torch.float32) * (rank + 1)
+        self.loss_sums = torch.tensor([1.0, 2.0, 3.0, 0.0]) * (rank + 1)
+        self.due = due
 
         class _Cfg:
             loss_scale = 128.0
@@ -189,7 +191,16 @@ class _FakeTrainCtx:
         return self.counts
 
     def train_step_counts_ready(self):
-        self.calls.append(("counts_ready", self.counts.tolist()))
+        self.calls.append(("counts_ready", self.counts.tolist(), self.loss_sums.tolist()))
+
+    def loss_scalars_device(self):
+        return self.loss_sums, self.due
+
+    def peer_exchange(self):
+        self.calls.append(("exchange",))
+
+    def peer_barrier(self):
+        self.calls.append(("barrier",))
 
     def delta_gradients(self):
         return self.dgrads
@@ -213,25 +224,32 @@ def _train_worker(rank, world, port, out_dir):
         ctx = _FakeTrainCtx(rank, peers, delta=True)
         assert parallel.train_step(ctx, rank, world) == "stats"
         out[peers] = ctx.calls
+    ctx = _FakeTrainCtx(rank, False, delta=False, due=False)
+    assert parallel.train_step(ctx, rank, world) == "stats"
+    out["not_due"] = ctx.calls
     torch.save(out, os.path.join(out_dir, f"t{rank}.pt"))
     dist.destroy_process_group()
 
 
 def test_data_parallel_step_choreography(tmp_path):
-    """world_size 2 over gloo: the sample counts are all-reduced BEFORE the host read-back point (counts_ready), the 12 delta
-    gradients before the optimizer, and the 42 MB gradient all-reduce only happens on the path without peer memory."""
+    """world_size 2 over gloo.  Peer-memory path: no collective library call at all -- exchange (counts / loss sums / delta gradients
+    summed on the device) -> host read-back point -> sharded optimizer -> barrier -> end.  Collective path: the sample counts and, on
+    reporting steps, the loss sums are all-reduced BEFORE the host read-back point (counts_ready), the 12 delta gradients and the 42 MB
+    gradient buffer before the replicated optimizer inside train_step_end."""
     port = _free_port()
     mp.spawn(_train_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     for r in range(2):
         got = torch.load(tmp_path / f"t{r}.pt")
-        p2p, nccl = got[True], got[False]
-        assert [c[0] for c in p2p] == ["begin", "counts_ready", "sharded", "end"]
+        p2p, nccl, not_due = got[True], got[False], got["not_due"]
+        assert [c[0] for c in p2p] == ["begin", "exchange", "counts_ready", "sharded", "barrier", "end"]
         assert [c[0] for c in nccl] == ["begin", "counts_ready", "end"]
         assert p2p[0] == ("begin", r, 2)
-        assert p2p[1][1] == [21, 201, 101, 0] and nccl[1][1] == [21, 201, 101, 0]      # global counts at the read-back point
-        assert p2p[2][1] == [3.0 * k for k in range(12)]                                 # summed delta gradients reach the optimizer
-        assert p2p[3][1] == [float(r + 1)] * 8                                           # peer path: no gradient all-reduce
-        assert nccl[2][1] == [3.0] * 8                                                   # NCCL path: gradients summed before Adam
+        assert p2p[2][1] == [10 + r, 100 + r, 50 + r, 0]                                 # peer path: the sums are taken by the exchange kernel, not here
+        assert p2p[5][1] == [float(r + 1)] * 8                                           # ... and no gradient all-reduce
+        assert nccl[1][1] == [21, 201, 101, 0]                                           # global counts at the read-back point
+        assert nccl[1][2] == [3.0, 6.0, 9.0, 0.0]                                        # global loss sums at the read-back point (reporting step)
+        assert nccl[2][1] == [3.0] * 8                                                   # gradients summed before Adam
+        assert not_due[1][1] == [21, 201, 101, 0] and not_due[1][2] == [1.0 * (r + 1), 2.0 * (r + 1), 3.0 * (r + 1), 0.0]   # no loss all-reduce off the reporting steps
     # single rank: one call, no collectives
     class _One:
         def train_step(self):

@@ -36,7 +36,7 @@ class FakeContext:
     def __init__(self, n_params, learning_rate=1e-2, batch_size=1 << 18):
         import torch
         self.n_params = n_params
-        self.cfg = types.SimpleNamespace(learning_rate=learning_rate, batch_size=batch_size)
+        self.cfg = types.SimpleNamespace(learning_rate=learning_rate, batch_size=batch_size, aabb_scale=1)
         self.master = torch.zeros(n_params); self.params = torch.zeros(n_params, dtype=torch.float16); self.ema = torch.zeros(n_params, dtype=torch.float16)
         self.grads = torch.zeros(n_params)
         self.m1 = torch.zeros(n_params); self.m2 = torch.zeros(n_params); self.steps = torch.zeros(n_params, dtype=torch.int32)
@@ -145,12 +145,12 @@ def test_file_written_by_this_repo_loads_through_the_reference_code(tmp_path):
     mod = _mod()
     n = mod.N_DENSITY + mod.N_RGB + mod.N_GRID + mod.N_VARIANCE
     rs = np.random.RandomState(3)
-    ctx = FakeContext(n, learning_rate=1e-2, batch_size=250000)
+    ctx = FakeContext(n, learning_rate=1e-2, batch_size=262144)
     ctx.master.copy_(torch.from_numpy(rs.normal(0, 0.1, n).astype(np.float32))); ctx.params.copy_(ctx.master.half())
     ctx.ema.copy_(torch.from_numpy(rs.normal(0, 0.1, n).astype(np.float16)))
     ctx.m1.copy_(torch.from_numpy(rs.normal(0, 1, n).astype(np.float32))); ctx.m2.copy_(torch.from_numpy(rs.uniform(0, 1, n).astype(np.float32)))
     ctx.steps.copy_(torch.from_numpy(rs.randint(0, 30, n).astype(np.int32))); ctx.current_step = 30
-    ctx.state.update(training_step=30, rays_per_batch=5120, measured_before=600000)
+    ctx.state.update(training_step=30, rays_per_batch=5120, measured_before=600000, measured_batch_size=250000)   # the MEASURED compacted count, not the target
     ctx.grid.copy_(torch.from_numpy(rs.uniform(0, 2, 128 ** 3).astype(np.float32)))
     ctx.gm.update(rotation=np.array([[0, -1, 0], [1, 0, 0], [0, 0, 1]], np.float32), transition=np.array([0.5, 0.25, -0.125], np.float32),
                   delta_rotation_6d=np.array([1, 0.125, 0, 0, 1, 0.25], np.float32), delta_transition=np.array([0, 0.0625, 0], np.float32))

@@ -163,17 +163,33 @@ def test_global_movement_recovers_a_rigid_motion(tmp_path):
     tb.frame()                                               # switches to frame 1, first delta-only step
     assert tb.current_training_time_frame == 1 and tb.training_step == 1 and tb._ctx.global_movement()["use_delta"]
     loss_start = None
-    for _ in range(49):
+    for _ in range(48):
         tb.frame()
         if loss_start is None:
             loss_start = tb.loss
+    st = tb.train(1 << 18)                                   # step 50 of the frame, the last delta-only one
     assert tb.training_step == 50 and torch.equal(tb._ctx.buffers()[1], ema0)      # canonical weights frozen while the delta trains
+    # while frozen the canonical optimizer does not run at all (testbed_nerf.cu:3503-3505): Adam's step count, the EMA and with it the
+    # switch of the inference weights to the EMA copy wait for the first joint step; m_canonical_training_step stays 0, so the occupancy
+    # grid was refreshed on every step (testbed.cu:2669) and the image round-robin restarted on every step (testbed_nerf.cu:3785)
+    s50 = tb._ctx.get_state()
+    assert s50["optimizer_step"] == 0 and s50["canonical_training_step"] == 0
+    assert st.density_grid_updated and s50["density_grid_ema_step"] == 50
+    assert s50["n_rays_total"] == st.rays_per_batch
+    assert not tb._ctx.buffers()[2].any()                    # EMA buffer untouched since the frame change
     # ray_canonical = R ray + t must carry frame 1's object centre c1 = (0.51, 0.5, 0.5) back onto frame 0's (0.5, 0.5, 0.5); identity is off by 0.01
     c0, c1 = np.array([0.5, 0.5, 0.5]), np.array([0.51, 0.5, 0.5])
     R, t = tb.global_transform()
     err50 = np.linalg.norm(R @ c1 + t - c0)
     print("after 50 delta-only steps:", tb._ctx.global_movement(), "centre error", err50)
     assert err50 < 0.006
+    st = tb.train(1 << 18)                                   # first joint step
+    s51 = tb._ctx.get_state()
+    assert s51["optimizer_step"] == 1 and s51["canonical_training_step"] == 1 and s51["n_rays_total"] == st.rays_per_batch
+    from tests import util as U                              # EMA step 1 is debiased to the parameters themselves (ema.h:64-77)
+    assert U.half_ulp_diff(tb._ctx.buffers()[2].cpu().numpy().view(np.uint16), tb._ctx.buffers()[1].cpu().numpy().view(np.uint16)).max() <= 1
+    tb.train(1 << 18)
+    assert tb._ctx.get_state()["n_rays_total"] > st.rays_per_batch     # the round-robin position accumulates again
     while tb.training_step < 400:
         tb.frame()
     assert not torch.equal(tb._ctx.buffers()[1], ema0)

@@ -19,7 +19,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out_dir, mode, steps):
+def _worker(rank, world, port, out_dir, mode, steps, total_world=None):
     import torch
     import torch.distributed as dist
     import neus2_b200 as N
@@ -28,20 +28,26 @@ def _worker(rank, world, port, out_dir, mode, steps):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
     B = 1 << 15
-    ctx = N.Context(N.default_config(batch_size=B * (world // 2), world_size=world, max_rays_per_batch=(1 << 15) * world,
+    total_world = total_world or world                   # "single*" modes: one rank stepping the SAME global batch the multi-rank runs split
+    # "*capped": rays_per_batch runs into max_rays_per_batch, i.e. every rank traces max_rays_per_batch / W rays -- exactly the size of its
+    # per-ray arrays (a reduction or zero-fill sized by the GLOBAL ray count would run off their end)
+    max_rays = 1024 * total_world if mode.endswith("capped") else (1 << 15) * total_world
+    ctx = N.Context(N.default_config(batch_size=B * (total_world // 2), world_size=world, max_rays_per_batch=max_rays, mask_loss_weight=0.1,
                                      prefetch_next_samples=0 if mode.endswith("_inorder") else 1), device=rank)
     data = synthetic.render_sphere_views(n_views=6, width=128, height=96, seed=2)
     ctx.set_dataset(data["pixels"], data["focal"], data["principal"], data["xforms"])
     ctx.init_params()
     if mode.startswith("p2p"):
         parallel.attach_peers(ctx, rank, world)
-    stats = []
+    stats, losses = [], []
     master, params, ema, _ = ctx.buffers()
     lo, hi = ctx.optimizer_shard(rank, world)
     saved = {}
     for i in range(steps):
         st = parallel.train_step(ctx, rank, world)
         stats.append((st.rays_per_batch, st.n_rays_kept, st.measured_batch_size_before_compaction, st.measured_batch_size))
+        if st.loss_valid:
+            losses.append((i, st.loss, st.ek_loss, st.mask_loss))
         if i == 23:      # the parameter comparison between the two optimizer paths is made here, while their trajectories are within rounding
             torch.cuda.synchronize()
             dist.barrier()
@@ -51,7 +57,34 @@ def _worker(rank, world, port, out_dir, mode, steps):
     torch.cuda.synchronize()
     dist.barrier()
     saved["stats"] = np.array(stats, dtype=np.int64)
+    saved["losses"] = np.array(losses, dtype=np.float64)
     saved["params_end"] = params.cpu().numpy().view(np.uint16)
+    if mode.startswith("single") or mode.endswith("capped"):
+        np.savez(os.path.join(out_dir, f"{mode}_r{rank}.npz"), **saved)
+        dist.barrier()
+        ctx.close()
+        dist.destroy_process_group()
+        return
+    if mode == "p2p":
+        # sharded optimizer: this rank's fp32 master / moments / step counters are current for ITS slice only.  Whole-state readers must
+        # refuse until the slices have been gathered (parallel.sync_optimizer_state), after which every rank holds the same, complete state.
+        try:
+            ctx.get_params()
+            saved["refused"] = np.array(0)
+        except N.Neus2Error:
+            saved["refused"] = np.array(1)
+        m1, m2, psteps, _ = ctx.optimizer_buffers()
+        stale = (master.half() != params).float().mean().item()
+        parallel.sync_optimizer_state(ctx, rank, world)
+        whole = ctx.get_params()
+        saved["stale_before_sync"] = np.array(stale)
+        saved["master_rounds_to_params"] = np.array(bool(np.array_equal(whole.astype(np.float16).view(np.uint16), saved["params_end"])))
+        saved["opt_digest"] = np.array([float(m1.double().sum().item()), float(m2.double().sum().item()), float(psteps.double().sum().item())])
+        from neus2_b200 import snapshot
+        path = os.path.join(out_dir, f"snap_r{rank}.msgpack")
+        snapshot.save(ctx, path, {}, include_optimizer_state=True)
+        adam = snapshot.read(path)["snapshot"]["optimizer"]["nested"]["nested"]
+        saved["snap_steps_sum"] = np.array(float(np.frombuffer(adam["param_steps_binary"], np.int32).astype(np.float64).sum()))
     # global-movement mode: every rank back-propagates its rows into its own 9 delta-gradient sums; they are all-reduced (48 bytes)
     # and each rank steps its replica of the DeltaNetwork's parameters
     ctx.begin_global_movement()
@@ -75,7 +108,13 @@ def runs(tmp_path_factory):
     out = tmp_path_factory.mktemp("dp")
     for mode in ("nccl", "p2p", "p2p_inorder"):
         mp.spawn(_worker, args=(world, _free_port(), str(out), mode, 42), nprocs=world, join=True)   # past step 32: every other step runs on prefetched samples
-    runs = {f"{m}_r{r}": np.load(out / f"{m}_r{r}.npz") for m in ("nccl", "p2p", "p2p_inorder") for r in range(world)}
+    for mode in ("p2p_capped", "nccl_capped"):
+        mp.spawn(_worker, args=(world, _free_port(), str(out), mode, 34), nprocs=world, join=True)
+    for mode in ("single", "single_capped"):
+        mp.spawn(_worker, args=(1, _free_port(), str(out), mode, 34, world), nprocs=1, join=True)
+    runs = {f"{m}_r{r}": np.load(out / f"{m}_r{r}.npz") for m in ("nccl", "p2p", "p2p_inorder", "p2p_capped", "nccl_capped") for r in range(world)}
+    runs["single_r0"] = np.load(out / "single_r0.npz")
+    runs["single_capped_r0"] = np.load(out / "single_capped_r0.npz")
     runs["world"] = world
     return runs
 
@@ -134,3 +173,44 @@ def test_delta_network_replicas_agree(runs):
         for r in range(1, runs["world"]):
             assert np.array_equal(d0.view(np.uint32), runs[f"{m}_r{r}"]["delta"].view(np.uint32)), (m, r)
     assert np.abs(runs["nccl_r0"]["delta"] - runs["p2p_r0"]["delta"]).max() < 2e-4    # 6 Adam steps of 1e-4: same direction on both paths
+
+
+def test_reported_losses_are_those_of_the_global_batch(runs):
+    """Every 16th step reports rgb / eikonal / mask losses.  Data-parallel they must be the losses of the GLOBAL batch on every rank
+    (partial sums exchanged before the read-back), i.e. what one GPU stepping the same global batch reports: identical rays at step 0
+    (same parameters), within the run-to-run drift of the fp32 atomics later."""
+    one = runs["single_r0"]["losses"]
+    assert one[:, 0].tolist() == [0, 16, 32] and np.all(one[:, 1] > 0) and np.all(one[:, 3] > 0)
+    for m in ("nccl", "p2p"):
+        l0 = runs[f"{m}_r0"]["losses"]
+        assert l0[:3, 0].tolist() == [0, 16, 32]
+        for r in range(1, runs["world"]):
+            assert np.array_equal(l0, runs[f"{m}_r{r}"]["losses"]), (m, r)      # same bits on every rank (sums taken in rank order)
+        assert np.allclose(l0[0, 1:], one[0, 1:], rtol=1e-4), (m, l0[0], one[0])   # step 0: the same rays, only the summation order differs
+        assert np.allclose(l0[:3, 1:], one[:3, 1:], rtol=0.1), (m, l0[:3], one[:3])
+
+
+def test_rays_per_batch_at_its_cap(runs):
+    """max_rays_per_batch reached: every rank traces exactly as many rays as its per-ray arrays hold (max_rays_per_batch / W)."""
+    W = runs["world"]
+    one = runs["single_capped_r0"]
+    assert one["stats"][-1][0] == 1024 * W                                              # the cap binds
+    for m in ("p2p_capped", "nccl_capped"):
+        a = runs[f"{m}_r0"]
+        assert a["stats"][-1][0] == 1024 * W
+        assert np.array_equal(a["stats"][:2], one["stats"][:2])
+        assert np.all(np.abs(a["stats"] - one["stats"]) <= 0.05 * np.maximum(one["stats"], 1) + 2)
+        assert np.all(np.isfinite(a["losses"])) and np.allclose(a["losses"][:, 1:], one["losses"][:, 1:], rtol=0.1), (m, a["losses"], one["losses"])
+        for r in range(1, W):
+            assert np.array_equal(a["params_end"], runs[f"{m}_r{r}"]["params_end"]), (m, r)
+
+
+def test_sharded_optimizer_state_is_gathered_before_it_is_serialised(runs):
+    W = runs["world"]
+    for r in range(W):
+        a = runs[f"p2p_r{r}"]
+        assert a["refused"] == 1                                   # whole-state read of a sharded optimizer refuses ...
+        assert a["stale_before_sync"] > 0.1                        # ... for a reason: most of this rank's master copy is stale
+        assert a["master_rounds_to_params"]                        # after the gather the fp32 master rounds to the fp16 parameters everywhere
+        assert np.array_equal(a["opt_digest"], runs["p2p_r0"]["opt_digest"])     # and every rank holds the same moments / step counters
+        assert a["snap_steps_sum"] == a["opt_digest"][2] and a["snap_steps_sum"] > 0

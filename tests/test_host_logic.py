@@ -150,3 +150,33 @@ def test_testbed_global_movement_hyperparams():
     r6 = np.array([1.0, 0.03, -0.02, 0.01, 0.98, 0.05], np.float32).astype(np.float16).astype(np.float32)
     R, _ = O.delta_matrix(r6, [0, 0, 0])
     assert np.abs(_rotation_6d_to_matrix(r6) - R).max() < 2e-7
+
+
+def test_canonical_training_step_follows_the_reference_counter():
+    """m_canonical_training_step is a stateful counter in the reference: reset by training_network_next_frame (src/testbed.cu:2015, 2050)
+    and updated at the end of every step (src/testbed_nerf.cu:3510-3527; the "still predicting" branch is a no-op comparison, :3518).
+    neus2_canonical_training_step is its closed form; simulate the reference's updates step by step over three frames and compare the
+    value each step STARTS with -- the one Testbed::train (grid cadence, testbed.cu:2669), training_prep_nerf (:4011) and
+    train_nerf_step (:3785) read."""
+    from neus2_b200 import _lib
+    f = _lib.load().neus2_canonical_training_step
+    for predict, P in ((True, 50), (True, 300), (True, 0), (False, 0)):
+        canonical, frame = 0, 0
+        for frame, n_steps in enumerate((400, 420, 333)):
+            if frame >= 1:
+                canonical = 0                                     # training_network_next_frame
+            for training_step in range(n_steps):
+                assert f(frame, P if predict else 0, training_step) == canonical, (predict, P, frame, training_step)
+                after = training_step + 1                         # ++m_training_step (:3510)
+                if predict:
+                    if frame == 0:
+                        canonical = after
+                    elif after < P:
+                        pass                                      # "==" instead of "=": the counter keeps its value
+                    else:
+                        canonical = after - P
+                else:
+                    canonical = after
+    # what hangs off it while the canonical model is frozen (frames >= 1, first P steps): the counter stays 0, so the occupancy grid is
+    # refreshed on every step (n_prep_to_skip = clamp(0 / 16, 1, 16) = 1) from uniform samples (< 256) and n_rays_total restarts each step
+    assert all(f(1, 50, s) == 0 for s in range(51)) and f(1, 50, 51) == 1 and f(1, 50, 306) == 256
