@@ -233,6 +233,10 @@ def workload_config(args, n_gpus):
 def main():
     args = parse()
     if args.impl == "reference":
+        # all host cores: torchrun exports OMP_NUM_THREADS=1 to its workers, which would time the OpenMP port on ONE core
+        # (round 1's N>1 reference lines were 10x slower than the N=1 line for exactly that reason); set before libgomp is loaded
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())
+        os.environ.pop("OMP_PROC_BIND", None)
         run_reference_arm(args)
         return
     import torch
@@ -362,7 +366,7 @@ def main():
             "per_step": {"rays": rays / K, "samples_before_compaction": n_u / K, "samples_compacted": n_c / K, "batch_fill": fill, "training_step": int(st.training_step),
                          "first_pass_samples_evaluated_last_step": int(st.first_pass_samples)},
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # reported on rank 0 at N = 1 only
             try:
                 bitfield = ctx.debug_buffer("bitfield", "<u1", (128 ** 3,)).cpu().numpy()
                 v, desc = cpu_port_rays_per_s(data, ctx.get_params(), bitfield, int(rays / K), n_u / K, n_c / K, 1 << 18, n_sample_rays=512)

@@ -99,6 +99,7 @@ struct neus2_ctx {
 	                            // block scheduler serves them before the next step's sample-generation blocks that share the GPU with them
 	cudaEvent_t ev_hp_done;
 	bool step_on_hp;            // the step in flight has its weight gradients (and will have its optimizer) on hp_stream
+	bool grid_adam_early;       // the step in flight already has the hash-grid part of its optimizer step running on hp_stream (beside the weight gradients)
 	cudaEvent_t ev_counts, ev_fwdbwd_done, ev_gen_done;
 	uint32_t* counters_buf[2]; int counters_cur;
 	bool prefetched; StepPlan prefetch_plan; uint64_t prefetch_epoch;
@@ -614,8 +615,9 @@ int neus2_sdf(neus2_ctx* ctx, void* stream, const float* pos, uint32_t stride, u
 	return launch_network_sdf((cudaStream_t)stream, ctx->gm, ctx->pl, inference_or_training_params(ctx, use_inference_params), pos, stride, n, ctx->cfg.sdf_bias, as_density, (__half*)out, nullptr);
 }
 
+static int launch_optimizer_part(neus2_ctx* ctx, cudaStream_t stream, float loss_scale, uint32_t adam_step, int fuse_zero, int part);
 static int backward_on_stream(neus2_ctx* ctx, cudaStream_t stream, const float* coords, const void* dL_dout, const uint32_t* n_in_dev, uint32_t n_rows,
-                              uint32_t indeed_batch_size, bool grads_zeroed, bool wgrad_on_hp = false) {
+                              uint32_t indeed_batch_size, bool grads_zeroed, bool wgrad_on_hp = false, int grid_adam_early = 0 /* 1: start it, 2: ... and it clears the gradients it consumes */) {
 	if (n_rows > ctx->B_local) FAIL("n_rows exceeds the context's (local) batch size");
 	ctx->step_on_hp = wgrad_on_hp;
 	if (!grads_zeroed) {
@@ -628,6 +630,14 @@ static int backward_on_stream(neus2_ctx* ctx, cudaStream_t stream, const float* 
 	                            ctx->grads, ctx->var_acc, ctx->w1row0_acc, ctx->so, ctx->use_delta ? ctx->d_acc : nullptr));
 	stage_end(ctx, ST_FWDBWD, stream);
 	CUDA_CHECK(cudaEventRecord(ctx->ev_fwdbwd_done, stream));
+	if (grid_adam_early && !wgrad_on_hp) {
+		// The hash-grid gradients (99.9 % of the parameters) are complete; the MLP weight gradients still need the GEMMs below.  The grid part
+		// of THIS step's Adam + EMA starts now on the side stream and streams its 250 MB of optimizer state beside the GEMMs' 290 MB of staged
+		// operands; neus2_optimizer_step adds the MLP part behind the GEMMs and joins the streams.
+		CUDA_CHECK(cudaStreamWaitEvent(ctx->hp_stream, ctx->ev_fwdbwd_done, 0));
+		CHECK(launch_optimizer_part(ctx, ctx->hp_stream, ctx->cfg.loss_scale, ctx->adam_step + 1, grid_adam_early == 2, 1));
+		ctx->grid_adam_early = true;
+	}
 	if (wgrad_on_hp) { CUDA_CHECK(cudaStreamWaitEvent(ctx->hp_stream, ctx->ev_fwdbwd_done, 0)); stream = ctx->hp_stream; }
 	stage_begin(ctx, ST_WGRAD, stream);
 	CHECK(launch_weight_gradients(stream, ctx->pl, ctx->so, ctx->params, n_in_dev, n_rows, ctx->partials, weight_gradient_partials(), ctx->var_acc, ctx->w1row0_acc, ctx->grads));
@@ -650,9 +660,22 @@ int neus2_backward(neus2_ctx* ctx, void* stream_, const float* coords, const voi
 	return backward_on_stream(ctx, (cudaStream_t)stream_, coords, dL_dout, n_in_dev, n_rows, indeed_batch_size, false);
 }
 
+// One launch of the fused Adam + EMA kernel for optimizer step `adam_step` (part: see launch_adam_ema)
+static int launch_optimizer_part(neus2_ctx* ctx, cudaStream_t stream, float loss_scale, uint32_t adam_step, int fuse_zero, int part) {
+	const neus2_config& c = ctx->cfg;
+	// inside a pipelined train step the kernel also clears what the next step starts from (consumed gradients, the small accumulators,
+	// this step's counters): no zero-fill launches are left between the optimizer and the next step's first kernel.  The small arrays are
+	// still read by the weight-gradient kernels, so only the launch that follows those (part 0 or 2) clears them.
+	uint32_t* const zp[3] = {(uint32_t*)ctx->var_acc, (uint32_t*)ctx->w1row0_acc, ctx->counters};
+	const uint32_t zn[3] = {1u, 64u, 8u};
+	const float lr = ctx->learning_rate * neus2_learning_rate_factor(&c, adam_step - 1);   // x 1.0f before decay_start: the same float
+	return launch_adam_ema(stream, ctx->n_params, ctx->pl.off_grid, loss_scale, lr, c.beta1, c.beta2, c.epsilon, c.l2_reg,
+	                       c.ema_decay, adam_step, ctx->grads, ctx->master, ctx->params, ctx->m1, ctx->m2, ctx->steps, ctx->ema, ctx->adam_bias_table, ADAM_BIAS_TABLE, 0,
+	                       fuse_zero, part == 1 ? nullptr : zp, zn, part);
+}
+
 int neus2_optimizer_step(neus2_ctx* ctx, void* stream, float loss_scale) {
 	CUDA_CHECK(cudaSetDevice(ctx->device));
-	const neus2_config& c = ctx->cfg;
 	stage_begin(ctx, ST_OPT, (cudaStream_t)stream);
 	if (canonical_frozen(ctx)) {
 		// "if (m_train_canonical) m_trainer->optimizer_step(...)" (testbed_nerf.cu:3503-3505): while only the DeltaNetwork trains, the canonical
@@ -664,16 +687,17 @@ int neus2_optimizer_step(neus2_ctx* ctx, void* stream, float loss_scale) {
 		return rc_f;
 	}
 	++ctx->adam_step;
-	const int frozen = 0;
-	// inside a pipelined train step the kernel also clears what the next step starts from (consumed gradients, the small accumulators,
-	// this step's counters): no zero-fill launches are left between the optimizer and the next step's first kernel
 	const int fuse = ctx->fuse_zero_into_adam ? 1 : 0;
-	uint32_t* const zp[3] = {(uint32_t*)ctx->var_acc, (uint32_t*)ctx->w1row0_acc, ctx->counters};
-	const uint32_t zn[3] = {1u, 64u, 8u};
-	const float lr = ctx->learning_rate * neus2_learning_rate_factor(&c, ctx->adam_step - 1);   // x 1.0f before decay_start: the same float
-	const int rc_ = launch_adam_ema((cudaStream_t)stream, ctx->n_params, ctx->pl.off_grid, loss_scale, lr, c.beta1, c.beta2, c.epsilon, c.l2_reg,
-	                       c.ema_decay, ctx->adam_step, ctx->grads, ctx->master, ctx->params, ctx->m1, ctx->m2, ctx->steps, ctx->ema, ctx->adam_bias_table, ADAM_BIAS_TABLE, frozen,
-	                       fuse, zp, zn);
+	int rc_;
+	if (ctx->grid_adam_early) {
+		// the hash-grid part has been running on hp_stream since the training kernel finished; the MLP weights + variance follow the
+		// weight-gradient kernels here, then the caller's stream joins the side stream
+		ctx->grid_adam_early = false;
+		rc_ = launch_optimizer_part(ctx, (cudaStream_t)stream, loss_scale, ctx->adam_step, fuse, 2);
+		if (rc_ == 0) { CUDA_CHECK(cudaEventRecord(ctx->ev_hp_done, ctx->hp_stream)); CUDA_CHECK(cudaStreamWaitEvent((cudaStream_t)stream, ctx->ev_hp_done, 0)); }
+	} else {
+		rc_ = launch_optimizer_part(ctx, (cudaStream_t)stream, loss_scale, ctx->adam_step, fuse, 0);
+	}
 	if (rc_ == 0 && ctx->use_delta) CHECK(delta_optimizer_step(ctx, (cudaStream_t)stream, loss_scale));   // m_global_move.trainer->optimizer_step (testbed_nerf.cu:3506-3508)
 	stage_end(ctx, ST_OPT, (cudaStream_t)stream);
 	return rc_;
@@ -782,7 +806,9 @@ int neus2_train_step_begin(neus2_ctx* ctx, void* stream_, uint32_t rank, uint32_
 	if (!ctx->d_pixels) FAIL("no training data: call neus2_set_dataset first");
 	if (world_size != ctx->cfg.world_size || rank >= world_size) FAIL("rank / world_size do not match the context's config.world_size");
 	const neus2_config& c = ctx->cfg;
-	const bool pipelined = world_size == 1 && c.prefetch_next_samples;   // world > 1: neus2_train_step_counts_ready switches the step to the pipelined end
+	// world > 1 without peer mappings: neus2_train_step_counts_ready switches the step to the pipelined end (behind the caller's all-reduce)
+	const bool peers = world_size > 1 && ctx->peer_world == world_size;
+	const bool pipelined = (world_size == 1 || peers) && c.prefetch_next_samples;
 	ctx->ev_set ^= 1;
 	neus2_set_training_step(ctx, ctx->time_frame >= 1 ? (int32_t)ctx->training_step - (int32_t)ctx->frozen_steps : (int32_t)ctx->training_step);   // testbed.cu:2651-2657
 	ctx->step_density_updated = false;
@@ -849,8 +875,16 @@ int neus2_train_step_begin(neus2_ctx* ctx, void* stream_, uint32_t rank, uint32_
 	if (pipelined) {
 		// every number the host needs from this step exists now: read it back BEFORE the backward pass is queued, so that the host's
 		// turnaround (and the next step's sample generation) hides behind the backward pass instead of following it
-		CUDA_CHECK(cudaMemcpyAsync(ctx->counts_global, ctx->counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
-		if (ctx->training_step % 16 == 0) { CHECK(reduce_loss_scalars(ctx, stream)); CHECK(read_back_loss_scalars(ctx, stream)); }
+		const bool loss_due = ctx->training_step % 16 == 0;
+		if (loss_due) CHECK(reduce_loss_scalars(ctx, stream));
+		if (peers) {
+			// data-parallel: the counts (and loss sums) of all ranks meet here, over peer memory, and every rank reads back the same sums
+			CHECK(launch_peer_exchange(stream, ++ctx->exchange_epoch, ctx->peer_rank, ctx->peer_world, ctx->peer_sync, ctx->counters, ctx->counts_global,
+			                           loss_due ? ctx->scalar_tmp : nullptr, nullptr));
+		} else {
+			CUDA_CHECK(cudaMemcpyAsync(ctx->counts_global, ctx->counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
+		}
+		if (loss_due) CHECK(read_back_loss_scalars(ctx, stream));
 		CUDA_CHECK(cudaMemcpyAsync(ctx->h_counters, ctx->counters, 12 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
 		CUDA_CHECK(cudaEventRecord(ctx->ev_counts, stream));
 	} else if (ctx->training_step % 16 == 0) {
@@ -861,8 +895,16 @@ int neus2_train_step_begin(neus2_ctx* ctx, void* stream_, uint32_t rank, uint32_
 	// cross-stream hops and the slower generation cost more: 0.9316 -> 0.9397 ms per step.  Off by default.
 	static int hp_mode = -1;
 	if (hp_mode < 0) { const char* e = getenv("NEUS2_HP_STREAM"); hp_mode = e ? atoi(e) : 0; }
+	// NEUS2_SPLIT_ADAM=1 (single-GPU pipelined step): the hash-grid part of the optimizer step starts right behind the training kernel, beside
+	// the weight-gradient GEMMs.  Negative result, off by default: both are HBM streams (290 MB of staged operands, 320 MB of optimizer
+	// state) and together they take exactly as long as one after the other -- weight gradients 0.123 -> 0.208 ms with the 0.087 ms
+	// optimizer inside, step 0.932 -> 0.949 ms (profiles/r02_bench_n1_split_adam.json / _nosplit.json).  The bytes have to go, not overlap.
+	static int split = -1, no_fused_zero_b = -1;
+	if (split < 0) { const char* e = getenv("NEUS2_SPLIT_ADAM"); split = e ? atoi(e) : 0; }
+	if (no_fused_zero_b < 0) { const char* e = getenv("NEUS2_NO_FUSED_ZERO"); no_fused_zero_b = e ? atoi(e) : 0; }
+	const int early = (pipelined && world_size == 1 && split && !hp_mode && !canonical_frozen(ctx)) ? (no_fused_zero_b ? 1 : 2) : 0;
 	CHECK(backward_on_stream(ctx, stream, ctx->coords_compacted, ctx->dloss, ctx->counters + 2, rows_local, ctx->B, /*grads_zeroed=*/pre_zeroed,
-	                         /*wgrad_on_hp=*/pipelined && hp_mode));   // :3941-3946
+	                         /*wgrad_on_hp=*/pipelined && hp_mode, early));   // :3941-3946
 	if (!pipelined) CUDA_CHECK(cudaMemcpyAsync(ctx->counts_global, ctx->counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
 	return 0;
 }
@@ -1262,15 +1304,17 @@ int neus2_optimizer_step_sharded(neus2_ctx* ctx, void* stream, float loss_scale)
 	return rc_;
 }
 
-// The exchange of a data-parallel step: orders every rank's backward pass before anything that follows on the stream and leaves, on
-// every rank, the sums over ranks (taken in rank order: identical bits everywhere) of the step's counts in neus2_counts_device(), of
-// the loss sums (steps with training_step % 16 == 0) and of the DeltaNetwork's gradient sums (while global movement trains).
-// All ranks must call it the same number of times.  Replaces three stream-ordered NCCL all-reduces.
+// The second exchange of a data-parallel step with peer mappings (the first one, counts + loss sums, sits behind the loss kernel inside
+// neus2_train_step_begin): call behind neus2_train_step_begin.  Orders every rank's backward pass before anything that follows on the
+// stream and leaves, on every rank, the sum over ranks (in rank order: identical bits everywhere) of the DeltaNetwork's gradient sums
+// while global movement trains.  All ranks must make the same sequence of calls.  If the step was begun without the pipelined path
+// (config.prefetch_next_samples = 0) it also carries the counts and loss sums.
 int neus2_peer_exchange(neus2_ctx* ctx, void* stream) {
 	CUDA_CHECK(cudaSetDevice(ctx->device));
 	if (!ctx->peer_world) FAIL("no peers attached: call neus2_ipc_attach first");
-	return launch_peer_exchange((cudaStream_t)stream, ++ctx->exchange_epoch, ctx->peer_rank, ctx->peer_world, ctx->peer_sync, ctx->counters, ctx->counts_global,
-	                            ctx->scalar_tmp, ctx->training_step % 16 == 0 ? 1 : 0, ctx->use_delta ? ctx->d_acc : nullptr);
+	const bool carry_counts = !ctx->step_pipelined;
+	return launch_peer_exchange((cudaStream_t)stream, ++ctx->exchange_epoch, ctx->peer_rank, ctx->peer_world, ctx->peer_sync, carry_counts ? ctx->counters : nullptr,
+	                            ctx->counts_global, carry_counts && ctx->training_step % 16 == 0 ? ctx->scalar_tmp : nullptr, ctx->use_delta ? ctx->d_acc : nullptr);
 }
 
 // Barrier over the peers, stream-ordered: everything the peers enqueued before THEIR call has completed (and its peer stores have landed)

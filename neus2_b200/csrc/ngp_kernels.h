@@ -27,7 +27,8 @@ int launch_compute_loss(cudaStream_t stream, uint32_t n_rays_local, uint32_t n_r
 
 int launch_adam_ema(cudaStream_t stream, uint64_t n, uint64_t n_matrix, float loss_scale, float lr, float beta1, float beta2, float eps, float l2_reg,
                     float ema_decay, uint32_t ema_step, float* grads, float* master, __half* params, float* m1, float* m2, uint32_t* steps, __half* ema,
-                    float* bias_table, uint32_t bias_table_size, int frozen, int zero_grads, uint32_t* const zero_ptrs[3], const uint32_t zero_counts[3]);
+                    float* bias_table, uint32_t bias_table_size, int frozen, int zero_grads, uint32_t* const zero_ptrs[3], const uint32_t zero_counts[3],
+                    int part = 0 /* 0 all parameters, 1 hash grid only, 2 MLP weights + variance only */);
 // table[k] = sqrt(1 - beta2^k) / (1 - beta1^k) for k in [first, last] (api.cu: compiled with FMA contraction like the reference's adam_step)
 int launch_adam_bias_table(cudaStream_t stream, float beta1, float beta2, uint32_t first, uint32_t last, float* bias_table, uint32_t bias_table_size);
 
@@ -45,7 +46,7 @@ struct PeerSyncBlock { PeerSlot exchange[2][NEUS2_MAX_PEERS]; PeerSlot barrier[N
 struct PeerSyncPtrs { PeerSyncBlock* block[NEUS2_MAX_PEERS]; };   // indexed by RANK (every rank's block as mapped into this process)
 struct PeerZero { uint32_t* p[3]; uint32_t n[3]; };
 int launch_peer_exchange(cudaStream_t stream, uint32_t epoch, uint32_t rank, uint32_t world, const PeerSyncPtrs& peers, const uint32_t* counts_local,
-                         uint32_t* counts_global, float* loss_sums, int with_loss, float* delta_acc);
+                         uint32_t* counts_global, float* loss_sums, float* delta_acc);   // null = not part of this call's payload
 int launch_peer_barrier(cudaStream_t stream, uint32_t epoch, uint32_t rank, uint32_t world, const PeerSyncPtrs& peers, const PeerZero& z);
 
 int launch_density_grid_samples(cudaStream_t stream, uint32_t n, const uint64_t rng_state[2], uint32_t step, const Aabb& bb, const float* grid_in,

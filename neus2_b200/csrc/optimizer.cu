@@ -47,16 +47,21 @@ __device__ __forceinline__ __half adam_one(bool is_matrix, float g_raw, const Ad
 
 // 4 consecutive parameters per thread (n and n_matrix are multiples of 4): 16-byte gradient loads; the optimizer state of an
 // untouched quad (the common case for the sparse hash-grid levels) is never read.
+// The launch covers the quads [q_begin, q_end) plus, if q_extra is a valid quad, that one (the variance quad behind the hash grid when
+// the launch covers the MLP weights only: the step then runs as two concurrent launches, see launch_adam_ema).
 __global__ void __launch_bounds__(256)
-k_adam_ema(uint64_t n4, uint64_t n_matrix4, AdamHyper h, float* __restrict__ grads,
+k_adam_ema(uint64_t q_begin, uint64_t q_end, uint64_t q_extra, uint64_t n_matrix4, AdamHyper h, float* __restrict__ grads,
            float* __restrict__ master, __half* __restrict__ params, float* __restrict__ m1, float* __restrict__ m2,
            uint32_t* __restrict__ steps, __half* __restrict__ ema, AdamZero z) {
 	if (h.zero_grads && blockIdx.x == 0) {
 		#pragma unroll
 		for (int a = 0; a < 3; ++a) for (uint32_t i = threadIdx.x; i < z.n[a]; i += blockDim.x) z.p[a][i] = 0u;
 	}
-	const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (q >= n4) return;
+	uint64_t q = q_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= q_end) {
+		if (q != q_end || q_extra == ~0ull) return;
+		q = q_extra;
+	}
 	const bool is_matrix = q < n_matrix4;
 	const float4 g4 = reinterpret_cast<const float4*>(grads)[q];
 	if (h.zero_grads && (g4.x != 0.f || g4.y != 0.f || g4.z != 0.f || g4.w != 0.f)) reinterpret_cast<float4*>(grads)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -97,16 +102,24 @@ k_adam_ema(uint64_t n4, uint64_t n_matrix4, AdamHyper h, float* __restrict__ gra
 
 int launch_adam_ema(cudaStream_t stream, uint64_t n, uint64_t n_matrix, float loss_scale, float lr, float beta1, float beta2, float eps, float l2_reg,
                     float ema_decay, uint32_t ema_step, float* grads, float* master, __half* params, float* m1, float* m2, uint32_t* steps, __half* ema,
-                    float* bias_table, uint32_t bias_table_size, int frozen, int zero_grads, uint32_t* const zero_ptrs[3], const uint32_t zero_counts[3]) {
+                    float* bias_table, uint32_t bias_table_size, int frozen, int zero_grads, uint32_t* const zero_ptrs[3], const uint32_t zero_counts[3], int part) {
 	const float ema_debias_old = 1 - (float)pow((double)ema_decay, (double)(ema_step - 1));
 	const float ema_debias_new = 1.0f / (1 - (float)pow((double)ema_decay, (double)ema_step));
 	if (n % 4 != 0 || n_matrix % 4 != 0) { neus_set_error("parameter counts must be multiples of 4", __FILE__, __LINE__); return -1; }
 	AdamHyper h = {loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, ema_debias_old, ema_debias_new, ema_step, bias_table, bias_table_size, frozen, zero_grads};
 	AdamZero z = {};
 	if (zero_grads) for (int a = 0; a < 3; ++a) { z.p[a] = zero_ptrs ? zero_ptrs[a] : nullptr; z.n[a] = (zero_ptrs && zero_ptrs[a]) ? zero_counts[a] : 0u; }
-	const uint64_t n4 = n / 4;
-	const uint32_t blocks = (uint32_t)((n4 + 255) / 256);
-	k_adam_ema<<<blocks, 256, 0, stream>>>(n4, n_matrix / 4, h, grads, master, params, m1, m2, steps, ema, z);
+	// part 0: everything.  part 1: the hash grid (all non-matrix parameters but the last quad).  part 2: the MLP weights + the last quad
+	// (variance).  Parts 1 and 2 touch disjoint parameters: the grid part only needs the training kernel's atomics, so it can run beside
+	// the weight-gradient GEMMs that part 2 waits for.
+	const uint64_t n4 = n / 4, nm4 = n_matrix / 4;
+	uint64_t q_begin = 0, q_end = n4, q_extra = ~0ull;
+	if (part == 1) { q_begin = nm4; q_end = n4 - 1; }
+	else if (part == 2) { q_begin = 0; q_end = nm4; q_extra = n4 - 1; }
+	if (part != 0 && (nm4 == 0 || nm4 >= n4 - 1)) { neus_set_error("split optimizer step needs matrix parameters, grid parameters and a trailing quad", __FILE__, __LINE__); return -1; }
+	const uint64_t count = q_end - q_begin + (q_extra != ~0ull ? 1 : 0);
+	const uint32_t blocks = (uint32_t)((count + 255) / 256);
+	k_adam_ema<<<blocks, 256, 0, stream>>>(q_begin, q_end, q_extra, nm4, h, grads, master, params, m1, m2, steps, ema, z);
 	COUNT_LAUNCH(1);
 	CUDA_CHECK(cudaGetLastError());
 	return 0;

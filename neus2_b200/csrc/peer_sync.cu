@@ -1,10 +1,11 @@
 // peer_sync.cu -- cross-GPU synchronisation of the data-parallel training step over NVLink peer memory (one NVSwitch domain).
 //
 // The reference is single-GPU; the data-parallel step needs two ordering points per step and one tiny reduction:
-//   exchange: "every rank's backward pass is complete" + the sum over ranks of {rays kept, samples, compacted samples},
-//             the three loss sums (every 16th step) and the DeltaNetwork's 9 gradient sums;
-//   barrier:  "every rank's optimizer slice has been stored into every rank's buffers" before anyone starts the next forward.
-// Both were stream-ordered 4..48-byte NCCL all-reduces (30-40 us each at 8 ranks).  Here each rank owns a small sync block that all
+//   exchange 1 (behind the loss kernel): the sum over ranks of {rays kept, samples, compacted samples} and, every 16th step, of the
+//             three loss sums -- what the host needs to size the next step, available while the backward pass still runs;
+//   exchange 2 (behind the backward pass): "every rank's gradients are complete" + the DeltaNetwork's 9 gradient sums;
+//   barrier   (behind the sharded optimizer): "every rank's slice has been stored into every rank's buffers" before the next forward.
+// These were stream-ordered 4..48-byte NCCL all-reduces (30-40 us each at 8 ranks).  Here each rank owns a small sync block that all
 // peers map (CUDA IPC): a rank stores its payload and then an epoch flag into ITS slot of every peer's block (st.release.sys over
 // NVLink) and spins on the W flags of its own block (ld.acquire.sys, local memory).  One CTA, one warp per peer, a few microseconds.
 // Sums are taken in rank order on every rank, so all ranks hold bit-identical results.
@@ -32,13 +33,15 @@ __device__ __forceinline__ void spin_until(const uint32_t* flag, uint32_t epoch,
 }
 
 // blockDim = 32 * world.  Warp w talks to peer w.
+// counts_local / loss_sums / delta_acc: null = that part of the payload is not exchanged by this call.
 __global__ void k_peer_exchange(uint32_t epoch, uint32_t rank, uint32_t world, PeerSyncPtrs peers, const uint32_t* __restrict__ counts_local,
-                                uint32_t* __restrict__ counts_global, float* __restrict__ loss_sums, int with_loss, float* __restrict__ delta_acc) {
+                                uint32_t* __restrict__ counts_global, float* __restrict__ loss_sums, float* __restrict__ delta_acc) {
 	const uint32_t w = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const uint32_t buf = epoch & 1u;
+	const bool with_loss = loss_sums != nullptr;
 	if (w < world) {
 		uint32_t v = 0u;
-		if (lane < 4) v = counts_local[lane];
+		if (lane < 4) v = counts_local ? counts_local[lane] : 0u;
 		else if (lane < 8) v = with_loss ? __float_as_uint(loss_sums[lane - 4]) : 0u;
 		else if (lane < PEER_PAYLOAD_WORDS) v = delta_acc ? __float_as_uint(delta_acc[lane - 8]) : 0u;
 		PeerSlot* dst = &peers.block[w]->exchange[buf][rank];
@@ -55,7 +58,7 @@ __global__ void k_peer_exchange(uint32_t epoch, uint32_t rank, uint32_t world, P
 		if (t < 4) {
 			uint32_t s = 0u;
 			for (uint32_t r = 0; r < world; ++r) s += ld_relaxed_sys(&mine[r].payload[t]);
-			counts_global[t] = s;
+			if (counts_local) counts_global[t] = s;
 		} else {
 			float s = 0.f;
 			for (uint32_t r = 0; r < world; ++r) s += __uint_as_float(ld_relaxed_sys(&mine[r].payload[t]));
@@ -80,9 +83,9 @@ __global__ void k_peer_barrier(uint32_t epoch, uint32_t rank, uint32_t world, Pe
 }
 
 int launch_peer_exchange(cudaStream_t stream, uint32_t epoch, uint32_t rank, uint32_t world, const PeerSyncPtrs& peers, const uint32_t* counts_local,
-                         uint32_t* counts_global, float* loss_sums, int with_loss, float* delta_acc) {
+                         uint32_t* counts_global, float* loss_sums, float* delta_acc) {
 	if (world < 1 || world > NEUS2_MAX_PEERS || rank >= world) { neus_set_error("bad rank / world size for the peer exchange", __FILE__, __LINE__); return -1; }
-	k_peer_exchange<<<1, 32 * world, 0, stream>>>(epoch, rank, world, peers, counts_local, counts_global, loss_sums, with_loss, delta_acc);
+	k_peer_exchange<<<1, 32 * world, 0, stream>>>(epoch, rank, world, peers, counts_local, counts_global, loss_sums, delta_acc);
 	COUNT_LAUNCH(1);
 	CUDA_CHECK(cudaGetLastError());
 	return 0;
