@@ -784,7 +784,10 @@ static void plan_step(const neus2_ctx* ctx, uint32_t rank, uint32_t world_size, 
 	memset(&p, 0, sizeof(p));
 	p.R = ctx->rays_per_batch;
 	p.n_local = p.R / world_size; p.ray_offset = rank * p.n_local;
-	p.max_inference = ctx->measured_before == 0 ? ctx->max_samples : (std::min(ctx->measured_before, ctx->max_samples) + 127u) / 128u * 128u;   // :3770-3775
+	// :3770-3775: the first pass is sized by the previous step's sample count, and rays whose samples do not fit are dropped (:1422-1424).
+	// Data-parallel, measured_before is the GLOBAL count and a rank's budget is its share of it (the scan over rays restarts on every rank).
+	const uint32_t before_share = (ctx->measured_before + world_size - 1) / world_size;
+	p.max_inference = ctx->measured_before == 0 ? ctx->max_samples : (std::min(before_share, ctx->max_samples) + 127u) / 128u * 128u;
 	p.n_rays_total = (ctx->training_step == 0 || canonical_training_step(ctx) == 0) ? 0 : ctx->n_rays_total;   // :3785-3787
 	p.training_step = ctx->training_step;
 	p.rng_state = ctx->rng.state; p.rng_inc = ctx->rng.inc;

@@ -16,27 +16,22 @@
 #define LD_X0 40               // 32 + 8 pad (halves)   -> conflict-free fragment loads
 #define LD_H 72                // 64 + 8 pad
 #define LD_C0 56               // 48 + 8 pad
-#define LD_T16 24              // 16 + 8 pad
 #define LD_DY 85               // 84 floats + 1 pad per sample
 #define SDF_IN 32
 #define RGB_IN 48
 
 // ---- shared-memory weight block (halves) -------------------------------------------------------
+// One copy per matrix, row = output unit, contiguous = input unit.  B fragments come from ldmatrix: plain for the forward
+// orientation (B(k,n) = W[n][k]), .trans for the transposed products of the backward pass (B(k,n) = W[k][n]) -- no transposed copies.
+// Row strides are odd multiples of 16 bytes: the 8 row addresses of an 8x8 ldmatrix tile fall into 8 different bank groups.
 struct WeightSmem {
-	// forward orientation: row = output unit, contiguous = input unit  (B(k,n) = W[n][k])
 	static constexpr int W0 = 0;                       // [64][LD_X0]
 	static constexpr int W1 = W0 + 64 * LD_X0;         // [16][LD_H]
 	static constexpr int C0 = W1 + 16 * LD_H;          // [64][LD_C0]
 	static constexpr int C1 = C0 + 64 * LD_C0;         // [64][LD_H]
 	static constexpr int C2 = C1 + 64 * LD_H;          // [16][LD_H]
-	static constexpr int W0T = C2 + 16 * LD_H;         // [32][LD_H]   W0T[i][j] = W0[j][i]
-	static constexpr int FWD_END = W0T + 32 * LD_H;
-	// backward-only transposes
-	static constexpr int W1T = FWD_END;                // [64][LD_T16] W1T[j][o] = W1[o][j]
-	static constexpr int C0T = W1T + 64 * LD_T16;      // [48][LD_H]
-	static constexpr int C1T = C0T + 48 * LD_H;        // [64][LD_H]
-	static constexpr int C2T = C1T + 64 * LD_H;        // [64][LD_T16]
-	static constexpr int BWD_END = C2T + 64 * LD_T16;
+	static constexpr int FWD_END = C2 + 16 * LD_H;
+	static constexpr int BWD_END = FWD_END;
 };
 
 // per-warp slab (bytes)
@@ -69,13 +64,6 @@ __device__ __forceinline__ void stage_matrix(__half* dst, int ld_dst, const __ha
 		dst[r * ld_dst + c] = src[i];
 	}
 }
-__device__ __forceinline__ void stage_matrix_T(__half* dst, int ld_dst, const __half* __restrict__ src, int rows, int cols, int tid, int nthreads) {
-	// dst[c][r] = src[r][c]
-	for (int i = tid; i < rows * cols; i += nthreads) {
-		int r = i / cols, c = i - r * cols;
-		dst[c * ld_dst + r] = src[i];
-	}
-}
 
 __device__ __forceinline__ void stage_weights(__half* sw, const __half* __restrict__ params, const ParamLayout& pl, bool train, int tid, int nthreads) {
 	stage_matrix(sw + WeightSmem::W0, LD_X0, params + pl.off_w0, 64, SDF_IN, tid, nthreads);
@@ -83,28 +71,59 @@ __device__ __forceinline__ void stage_weights(__half* sw, const __half* __restri
 	stage_matrix(sw + WeightSmem::C0, LD_C0, params + pl.off_c0, 64, RGB_IN, tid, nthreads);
 	stage_matrix(sw + WeightSmem::C1, LD_H, params + pl.off_c1, 64, 64, tid, nthreads);
 	stage_matrix(sw + WeightSmem::C2, LD_H, params + pl.off_c2, 16, 64, tid, nthreads);
-	stage_matrix_T(sw + WeightSmem::W0T, LD_H, params + pl.off_w0, 64, SDF_IN, tid, nthreads);
-	if (train) {
-		stage_matrix_T(sw + WeightSmem::W1T, LD_T16, params + pl.off_w1, 16, 64, tid, nthreads);
-		stage_matrix_T(sw + WeightSmem::C0T, LD_H, params + pl.off_c0, 64, RGB_IN, tid, nthreads);
-		stage_matrix_T(sw + WeightSmem::C1T, LD_H, params + pl.off_c1, 64, 64, tid, nthreads);
-		stage_matrix_T(sw + WeightSmem::C2T, LD_T16, params + pl.off_c2, 16, 64, tid, nthreads);
-	}
+	(void)train;
 }
 
 // ---- fragment helpers ------------------------------------------------------------------------------
-// c[NT][4] = A(regs a[KT][4]) x B, B(k,n) = W[n][k], W row stride ld (halves).
-template <int KT, int NT>
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const __half* p) {
+	const uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
+	asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const __half* p) {
+	const uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
+	asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t (&r)[2], const __half* p) {
+	const uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
+	asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];\n" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2_t(uint32_t (&r)[2], const __half* p) {
+	const uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
+	asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];\n" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+
+// c[NT][4] = A(regs a[KT][4]) x B.  W is a row-major [out][in] weight matrix, row stride ld (halves).
+//   TRANS = false: B(k,n) = W[n][k]   (forward: k = input unit, n = output unit)
+//   TRANS = true:  B(k,n) = W[k][n]   (backward: k = output unit, n = input unit)
+// One ldmatrix.x4 feeds two n-tiles of one k-tile (4 x fewer shared-memory instructions than 32-bit fragment loads).  Each c[nt]
+// accumulates its k-tiles in ascending order.
+template <int KT, int NT, bool TRANS = false>
 __device__ __forceinline__ void mma_layer(const uint32_t (&a)[KT][4], const __half* W, int ld, float (&c)[NT][4], int g, int t) {
+	const int lane = g * 4 + t, q = lane >> 3, r = lane & 7;
 	#pragma unroll
-	for (int nt = 0; nt < NT; ++nt) {
-		c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;
-		const __half* wrow = W + (8 * nt + g) * ld + 2 * t;
+	for (int nt = 0; nt < NT; ++nt) c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;
+	#pragma unroll
+	for (int p = 0; p < NT / 2; ++p) {
+		// tiles of the x4 load: (n-tile 2p, k lo) (n-tile 2p, k hi) (n-tile 2p+1, k lo) (n-tile 2p+1, k hi)
+		const __half* base = TRANS ? W + ((q & 1) * 8 + r) * ld + 8 * (2 * p + (q >> 1))
+		                           : W + (8 * (2 * p + (q >> 1)) + r) * ld + (q & 1) * 8;
 		#pragma unroll
 		for (int kt = 0; kt < KT; ++kt) {
-			uint32_t b0 = *reinterpret_cast<const uint32_t*>(wrow + 16 * kt);
-			uint32_t b1 = *reinterpret_cast<const uint32_t*>(wrow + 16 * kt + 8);
-			mma16816(c[nt], a[kt], b0, b1);
+			uint32_t b[4];
+			if (TRANS) ldsm_x4_t(b, base + 16 * kt * ld); else ldsm_x4(b, base + 16 * kt);
+			mma16816(c[2 * p], a[kt], b[0], b[1]);
+			mma16816(c[2 * p + 1], a[kt], b[2], b[3]);
+		}
+	}
+	if (NT & 1) {   // last n-tile alone: x2 (lanes 0..15 supply the row addresses)
+		constexpr int nt = NT - 1;
+		const int q2 = q & 1;
+		const __half* base = TRANS ? W + (q2 * 8 + r) * ld + 8 * nt : W + (8 * nt + r) * ld + q2 * 8;
+		#pragma unroll
+		for (int kt = 0; kt < KT; ++kt) {
+			uint32_t b[2];
+			if (TRANS) ldsm_x2_t(b, base + 16 * kt * ld); else ldsm_x2(b, base + 16 * kt);
+			mma16816(c[nt], a[kt], b[0], b[1]);
 		}
 	}
 }
@@ -482,7 +501,7 @@ __device__ __forceinline__ void forward_tile(const GridMeta& gm, const __half* _
 			gh[kt][3] = whi & relu_mask2(h0a[kt][3]);
 		}
 		float c[4][4];
-		mma_layer<4, 4>(gh, sw + WeightSmem::W0T, LD_H, c, g, t);
+		mma_layer<4, 4, true>(gh, sw + WeightSmem::W0, LD_X0, c, g, t);
 		store_c_smem<4>(c, sDIN, LD_X0, g, t);
 	}
 	__syncwarp();
@@ -529,22 +548,24 @@ __device__ __forceinline__ void forward_tile(const GridMeta& gm, const __half* _
 		mma_layer<4, 8>(h1a, sw + WeightSmem::C1, LD_H, c, g, t);
 		pack_frags<8, true>(c, h2a);
 	}
-	{
-		float c[2][4];
-		mma_layer<4, 2>(h2a, sw + WeightSmem::C2, LD_H, c, g, t);
-		store_c_smem<2>(c, sOUT, 16, g, t);
+	if (!KEEP) {   // the training kernel needs the activations, not the outputs: the loss gradient arrives from outside
+		{
+			float c[2][4];
+			mma_layer<4, 2>(h2a, sw + WeightSmem::C2, LD_H, c, g, t);
+			store_c_smem<2>(c, sOUT, 16, g, t);
+		}
+		__syncwarp();
+		// --- output assembly (nerf_network.h:287-325)
+		if (lane < 16) {
+			const int s = lane;
+			__half* o = sOUT + s * 16;
+			o[3] = __hadd(sSDF[s], __float2half_rn(sdf_bias));
+			o[4] = __float2half_rn(sNRM[s * 3 + 0]); o[5] = __float2half_rn(sNRM[s * 3 + 1]); o[6] = __float2half_rn(sNRM[s * 3 + 2]);
+			o[7] = params[pl.off_var];
+			o[8] = __float2half_rn(sCoord[s * 7 + 4]); o[9] = __float2half_rn(sCoord[s * 7 + 5]); o[10] = __float2half_rn(sCoord[s * 7 + 6]);
+		}
+		__syncwarp();
 	}
-	__syncwarp();
-	// --- output assembly (nerf_network.h:287-325)
-	if (lane < 16) {
-		const int s = lane;
-		__half* o = sOUT + s * 16;
-		o[3] = __hadd(sSDF[s], __float2half_rn(sdf_bias));
-		o[4] = __float2half_rn(sNRM[s * 3 + 0]); o[5] = __float2half_rn(sNRM[s * 3 + 1]); o[6] = __float2half_rn(sNRM[s * 3 + 2]);
-		o[7] = params[pl.off_var];
-		o[8] = __float2half_rn(sCoord[s * 7 + 4]); o[9] = __float2half_rn(sCoord[s * 7 + 5]); o[10] = __float2half_rn(sCoord[s * 7 + 6]);
-	}
-	__syncwarp();
 	if (KEEP) {
 		#pragma unroll
 		for (int kt = 0; kt < 4; ++kt) {

@@ -230,14 +230,14 @@ k_network_fwdbwd(GridMeta gm, ParamLayout pl, const __half* __restrict__ params,
 		uint32_t dh2a[4][4], dh1a[4][4];
 		{
 			float c[8][4];
-			mma_layer<1, 8>(dout, sw + WeightSmem::C2T, LD_T16, c, g, t);
+			mma_layer<1, 8, true>(dout, sw + WeightSmem::C2, LD_H, c, g, t);
 			pack_frags_masked<8>(c, st.h2a, dh2a);
 		}
 		if (!(dbg & 2)) store_a_global<4>(st.h2a, so.H2, 64, row0, n_valid, g, t);
 		if (!(dbg & 2)) store_a_global<4>(dh2a, so.dH2, 64, row0, n_valid, g, t);
 		{
 			float c[8][4];
-			mma_layer<4, 8>(dh2a, sw + WeightSmem::C1T, LD_H, c, g, t);
+			mma_layer<4, 8, true>(dh2a, sw + WeightSmem::C1, LD_H, c, g, t);
 			pack_frags_masked<8>(c, st.h1a, dh1a);
 		}
 		if (!(dbg & 2)) store_a_global<4>(st.h1a, so.H1, 64, row0, n_valid, g, t);
@@ -245,7 +245,7 @@ k_network_fwdbwd(GridMeta gm, ParamLayout pl, const __half* __restrict__ params,
 		uint32_t dso[1][4];
 		{
 			float c[6][4];
-			mma_layer<4, 6>(dh1a, sw + WeightSmem::C0T, LD_H, c, g, t);
+			mma_layer<4, 6, true>(dh1a, sw + WeightSmem::C0, LD_C0, c, g, t);
 			// cols 0..15 -> gradient of the sdf-MLP output; + dL/dsdf on column 0 (add_density_gradient, nerf_network.h:401-408)
 			float c00 = round_h(c[0][0]), c02 = round_h(c[0][2]);
 			if (t == 0) {
@@ -273,7 +273,7 @@ k_network_fwdbwd(GridMeta gm, ParamLayout pl, const __half* __restrict__ params,
 		uint32_t dh0a[4][4];
 		{
 			float c[8][4];
-			mma_layer<1, 8>(dso, sw + WeightSmem::W1T, LD_T16, c, g, t);
+			mma_layer<1, 8, true>(dso, sw + WeightSmem::W1, LD_H, c, g, t);
 			pack_frags_masked<8>(c, st.h0a, dh0a);
 		}
 		store_a_global<1>(dso, so.dSO, 16, row0, n_valid, g, t);
@@ -281,7 +281,7 @@ k_network_fwdbwd(GridMeta gm, ParamLayout pl, const __half* __restrict__ params,
 		if (!(dbg & 2)) store_a_global<4>(dh0a, so.dH0, 64, row0, n_valid, g, t);
 		{
 			float c[4][4];
-			mma_layer<4, 4>(dh0a, sw + WeightSmem::W0T, LD_H, c, g, t);
+			mma_layer<4, 4, true>(dh0a, sw + WeightSmem::W0, LD_X0, c, g, t);
 			store_c_smem<4>(c, sDX, LD_X0, g, t);
 		}
 		// sdf-MLP input [n][32]
