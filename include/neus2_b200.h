@@ -185,6 +185,10 @@ int neus2_set_bitfield(neus2_ctx* ctx, const uint8_t* bitfield_host, uint64_t n_
  * loss, fused forward+backward, weight-gradient GEMMs, optimizer, whole step}; sums in ms and number of samples. */
 int neus2_set_profiling(neus2_ctx* ctx, int enable);
 int neus2_get_stage_times(neus2_ctx* ctx, float ms_sum[8], uint32_t count[8]);
+/* Profiling only (process-wide; results are WRONG with any bit set): switches parts of the training kernel off so that their cost can be
+ * timed on a frozen state (tools/bench_fwdbwd.py).  1 = no hash-grid atomics, 4 = no read-back of the tensor-memory accumulators,
+ * 8 = weight-gradient operands staged but never multiplied, 16 = no waits for tcgen05 completion.  0 = normal operation. */
+int neus2_set_debug_bits(int bits);
 /* number of kernels this library launched on the context since creation (bench.py's gpu_launches) */
 uint64_t neus2_launch_count(const neus2_ctx* ctx);
 

@@ -60,6 +60,7 @@ struct neus2_ctx {
 	__half *mlp_out, *dloss;
 	StagedOperands so;
 	float *partials, *var_acc, *w1row0_acc, *scalar_tmp;
+	uint32_t* fwdbwd_done;      // CTA arrival counter of the training kernel (self-resetting)
 
 	// occupancy grid
 	float *density_grid, *density_grid_tmp, *grid_positions, *density_grid_mean;
@@ -413,10 +414,13 @@ int neus2_ctx_create(const neus2_config* cfg, int device, neus2_ctx** out) {
 	CDM(ctx->rays, 6 * (size_t)R); CDM(ctx->coords, 7 * (size_t)S); CDM(ctx->ray_tmp, 12 * (size_t)R);
 	CDM(ctx->coords_compacted, 7 * (size_t)B); CDM(ctx->loss, R); CDM(ctx->ek_loss, R); CDM(ctx->mask_loss, R);
 	CDM(ctx->mlp_out, 16 * (size_t)S); CDM(ctx->dloss, 16 * (size_t)B);
-	CDM(ctx->so.dOUT, 16 * (size_t)B); CDM(ctx->so.H2, 64 * (size_t)B); CDM(ctx->so.dH2, 64 * (size_t)B); CDM(ctx->so.H1, 64 * (size_t)B); CDM(ctx->so.dH1, 64 * (size_t)B);
-	CDM(ctx->so.CIN, 48 * (size_t)B); CDM(ctx->so.dSO, 16 * (size_t)B); CDM(ctx->so.H0, 64 * (size_t)B); CDM(ctx->so.dH0, 64 * (size_t)B);
-	CDM(ctx->so.X0, 32 * (size_t)B); CDM(ctx->so.dI, 32 * (size_t)B);
-	CDM(ctx->partials, (size_t)weight_gradient_partials() * ctx->pl.off_grid); CDM(ctx->var_acc, 1); CDM(ctx->w1row0_acc, 64); CDM(ctx->scalar_tmp, 4);
+	if (!weight_gradients_in_kernel()) {   // NEUS2_WGRAD=staged: operand matrices for the separate weight-gradient GEMM kernel (243 MB at B = 2^18)
+		CDM(ctx->so.dOUT, 16 * (size_t)B); CDM(ctx->so.H2, 64 * (size_t)B); CDM(ctx->so.dH2, 64 * (size_t)B); CDM(ctx->so.H1, 64 * (size_t)B); CDM(ctx->so.dH1, 64 * (size_t)B);
+		CDM(ctx->so.CIN, 48 * (size_t)B); CDM(ctx->so.dSO, 16 * (size_t)B); CDM(ctx->so.H0, 64 * (size_t)B); CDM(ctx->so.dH0, 64 * (size_t)B);
+		CDM(ctx->so.X0, 32 * (size_t)B); CDM(ctx->so.dI, 32 * (size_t)B);
+		CDM(ctx->partials, (size_t)weight_gradient_partials() * ctx->pl.off_grid);
+	}
+	CDM(ctx->var_acc, 1); CDM(ctx->w1row0_acc, 64); CDM(ctx->scalar_tmp, 4); CDM(ctx->fwdbwd_done, 1);
 	const size_t G3n = (size_t)NERF_GRIDSIZE * NERF_GRIDSIZE * NERF_GRIDSIZE;
 	CDM(ctx->density_grid, G3n * ctx->n_cascades); CDM(ctx->density_grid_tmp, G3n * ctx->n_cascades);
 	CDM(ctx->grid_positions, 3 * G3n * ctx->n_cascades); CDM(ctx->grid_indices, G3n * ctx->n_cascades); CDM(ctx->grid_density, G3n * ctx->n_cascades);
@@ -451,7 +455,7 @@ void neus2_ctx_destroy(neus2_ctx* ctx) {
 	void* ptrs[] = {ctx->master, ctx->params, ctx->ema, ctx->grads, ctx->m1, ctx->m2, ctx->steps, ctx->adam_bias_table, ctx->d_pixels, ctx->d_focal, ctx->d_principal, ctx->d_xforms,
 		ctx->numsteps_all, ctx->base, ctx->slot, ctx->ray_indices, ctx->numsteps, ctx->scan_tmp, ctx->counters, ctx->n_windows, ctx->windows, ctx->ray_setup, ctx->rays, ctx->coords, ctx->ray_tmp,
 		ctx->coords_compacted, ctx->loss, ctx->ek_loss, ctx->mask_loss, ctx->mlp_out, ctx->dloss, ctx->so.dOUT, ctx->so.H2, ctx->so.dH2, ctx->so.H1, ctx->so.dH1,
-		ctx->so.CIN, ctx->so.dSO, ctx->so.H0, ctx->so.dH0, ctx->so.X0, ctx->so.dI, ctx->partials, ctx->var_acc, ctx->w1row0_acc, ctx->scalar_tmp,
+		ctx->so.CIN, ctx->so.dSO, ctx->so.H0, ctx->so.dH0, ctx->so.X0, ctx->so.dI, ctx->partials, ctx->var_acc, ctx->w1row0_acc, ctx->scalar_tmp, ctx->fwdbwd_done,
 		ctx->density_grid, ctx->density_grid_tmp, ctx->grid_positions, ctx->grid_indices, ctx->grid_density, ctx->bitfield, ctx->density_grid_mean,
 		ctx->d_xform, ctx->d_acc, ctx->d_master, ctx->d_m1, ctx->d_m2, ctx->d_steps, ctx->d_params, ctx->counters_buf[0], ctx->counters_buf[1], ctx->sync_block};
 	for (uint32_t r = 0; r < ctx->peer_world; ++r) if (r != ctx->peer_rank) {   // unmap the peers' buffers before this rank's own are freed
@@ -627,7 +631,7 @@ static int backward_on_stream(neus2_ctx* ctx, cudaStream_t stream, const float* 
 	}
 	stage_begin(ctx, ST_FWDBWD, stream);
 	CHECK(launch_network_fwdbwd(stream, ctx->gm, ctx->pl, ctx->params, coords, (const __half*)dL_dout, n_in_dev, n_rows, ctx->cfg.sdf_bias, indeed_batch_size,
-	                            ctx->grads, ctx->var_acc, ctx->w1row0_acc, ctx->so, ctx->use_delta ? ctx->d_acc : nullptr));
+	                            ctx->grads, ctx->var_acc, ctx->w1row0_acc, ctx->so, ctx->use_delta ? ctx->d_acc : nullptr, ctx->fwdbwd_done));
 	stage_end(ctx, ST_FWDBWD, stream);
 	CUDA_CHECK(cudaEventRecord(ctx->ev_fwdbwd_done, stream));
 	if (grid_adam_early && !wgrad_on_hp) {
@@ -639,9 +643,11 @@ static int backward_on_stream(neus2_ctx* ctx, cudaStream_t stream, const float* 
 		ctx->grid_adam_early = true;
 	}
 	if (wgrad_on_hp) { CUDA_CHECK(cudaStreamWaitEvent(ctx->hp_stream, ctx->ev_fwdbwd_done, 0)); stream = ctx->hp_stream; }
-	stage_begin(ctx, ST_WGRAD, stream);
-	CHECK(launch_weight_gradients(stream, ctx->pl, ctx->so, ctx->params, n_in_dev, n_rows, ctx->partials, weight_gradient_partials(), ctx->var_acc, ctx->w1row0_acc, ctx->grads));
-	stage_end(ctx, ST_WGRAD, stream);
+	if (!weight_gradients_in_kernel()) {   // default: the training kernel has accumulated the MLP weight gradients itself (tensor memory)
+		stage_begin(ctx, ST_WGRAD, stream);
+		CHECK(launch_weight_gradients(stream, ctx->pl, ctx->so, ctx->params, n_in_dev, n_rows, ctx->partials, weight_gradient_partials(), ctx->var_acc, ctx->w1row0_acc, ctx->grads));
+		stage_end(ctx, ST_WGRAD, stream);
+	}
 	return 0;
 }
 
@@ -1123,6 +1129,8 @@ int neus2_get_stage_times(neus2_ctx* ctx, float ms_sum[8], uint32_t count[8]) {
 }
 
 uint64_t neus2_launch_count(const neus2_ctx* ctx) { (void)ctx; return g_neus_launches; }
+
+int neus2_set_debug_bits(int bits) { g_fwdbwd_debug_bits = bits; return 0; }
 
 // ---- inference render ---------------------------------------------------------------------------------------------------
 void neus2_default_render_params(neus2_render_params* p, int32_t width, int32_t height) {

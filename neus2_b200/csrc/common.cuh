@@ -81,6 +81,15 @@ __device__ __forceinline__ void mma16816(float c[4], const uint32_t a[4], uint32
 		: "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// Reductions without a return value, spelled out: in a kernel that also contains tcgen05 / mbarrier inline assembly the compiler keeps
+// atomicAdd() as the RETURNING form (ATOMG instead of REDG in SASS) and every hash-grid update then waits for its round trip to L2
+// (measured: 0.057 -> 0.233 ms for the grid atomics of the training kernel).
+__device__ __forceinline__ void red_add_f32(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory"); }
+__device__ __forceinline__ void red_add_v2f32(float* p, float a, float b) { asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" :: "l"(p), "f"(a), "f"(b) : "memory"); }
+__device__ __forceinline__ void red_add_v4f32(float* p, float a, float b, float c, float d) {
+	asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 __device__ __forceinline__ uint32_t ld_nc_u32(const void* p) {
 	uint32_t v;
 	asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(v) : "l"(p));

@@ -34,20 +34,20 @@ struct WeightSmem {
 	static constexpr int BWD_END = FWD_END;
 };
 
-// per-warp slab (bytes)
+// per-warp slab (bytes); every offset is a multiple of 16
 struct WarpSlab {
 	static constexpr int COORD = 0;                          // float [16][7]
 	static constexpr int X0 = COORD + 16 * 7 * 4;            // half  [16][LD_X0]   sdf-MLP input
 	static constexpr int DIN = X0 + 16 * LD_X0 * 2;          // half  [16][LD_X0]   d sdf / d sdf-input  (gE in cols 3..30)
 	static constexpr int CIN = DIN + 16 * LD_X0 * 2;         // half  [16][LD_X0]   colour input cols 16..47
-	static constexpr int OUT = CIN + 16 * LD_X0 * 2;         // half  [16][16]      output staging
-	static constexpr int SDF = OUT + 16 * 16 * 2;            // half  [16]          raw sdf-MLP output 0
+	static constexpr int SDF = CIN + 16 * LD_X0 * 2;         // half  [16]          raw sdf-MLP output 0
 	static constexpr int NRM = SDF + 16 * 2;                 // float [16][3]       normal
 	static constexpr int DY = NRM + 16 * 3 * 4;              // float [16][LD_DY]
-	static constexpr int FWD_END = DY + 16 * LD_DY * 4;
+	static constexpr int OUT = DY + 16 * LD_DY * 4;          // half  [16][16]      output staging (inference kernels only)
+	static constexpr int FWD_END = OUT + 16 * 16 * 2;
 	// training extras
-	static constexpr int DL = FWD_END;                       // half  [16][16]      dL/dout (after rollover scaling)
-	static constexpr int DX = DL + 16 * 16 * 2;              // half  [16][LD_X0]   dL/d sdf-input
+	static constexpr int DL = OUT;                           // half  [16][16]      dL/dout (after rollover scaling); the training kernel produces no outputs
+	static constexpr int DX = FWD_END;                       // half  [16][LD_X0]   dL/d sdf-input
 	static constexpr int DI = DX + 16 * LD_X0 * 2;           // half  [16][LD_X0]   d_density_input (2nd order)
 	static constexpr int V = DI + 16 * LD_X0 * 2;            // float [16][3]       v = dL/d normal
 	static constexpr int VN = V + 16 * 3 * 4;                // half  [16][8]       colour-input grad cols 32..39
@@ -56,7 +56,12 @@ struct WarpSlab {
 	static constexpr int DORIG = BWD_END;                    // float [16][3]       un-deformed positions of the tile
 	static constexpr int DACC = DORIG + 16 * 3 * 4;          // float [16][9]       per-lane sums of the 9 delta gradients
 	static constexpr int DELTA_END = DACC + 16 * 9 * 4;
+	// operand staging of the in-kernel weight gradients (umma.cuh): A tile [16][64] + B tile up to [16][48], canonical layout
+	static constexpr int STAGE_A = 0;                        // relative to the warp's staging block
+	static constexpr int STAGE_B = 16 * 64 * 2;
+	static constexpr int STAGE_BYTES = STAGE_B + 16 * 48 * 2;
 };
+static_assert(WarpSlab::OUT % 16 == 0 && WarpSlab::DX % 16 == 0 && WarpSlab::DI % 16 == 0 && WarpSlab::BWD_END % 16 == 0 && WarpSlab::DELTA_END % 16 == 0, "slab alignment");
 
 __device__ __forceinline__ void stage_matrix(__half* dst, int ld_dst, const __half* __restrict__ src, int rows, int cols, int tid, int nthreads) {
 	for (int i = tid; i < rows * cols; i += nthreads) {

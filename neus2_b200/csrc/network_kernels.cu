@@ -1,8 +1,10 @@
 // network_kernels.cu -- fused NeuS network kernels: inference forward, SDF/density only, and the fused
 // forward+backward training kernel.  See network.cuh for the per-warp pipeline.
 #include "network.cuh"
+#include "umma.cuh"
 #include "kernels.h"
 #include <cstdlib>
+#include <cstring>
 
 #define WARPS_PER_CTA 8
 #define THREADS_PER_CTA (WARPS_PER_CTA * 32)
@@ -12,9 +14,27 @@ static constexpr int FWD_SMEM = WeightSmem::FWD_END * 2 + WARPS_PER_CTA * WarpSl
 #ifndef MERGE_MAX_HEADS
 #define MERGE_MAX_HEADS 10     // pre-reduce a level's atomics in the warp when its 16 samples fall into <= this many runs of equal cells
 #endif
-static constexpr int BWD_SMEM = WeightSmem::BWD_END * 2 + WARPS_BWD * WarpSlab::BWD_END;
-static constexpr int BWD_SMEM_DELTA = WeightSmem::BWD_END * 2 + WARPS_BWD * WarpSlab::DELTA_END;
-static_assert(BWD_SMEM_DELTA <= 227 * 1024, "training kernel (delta variant) exceeds the 227 KB shared-memory limit");
+// Training kernel, shared memory: weights | per-warp slabs | (TC) per-warp operand staging | (TC) one mbarrier per warp + the
+// tensor-memory base address.  The DeltaNetwork variant has a larger slab and runs one warp less when it stages in shared memory.
+#define WARPS_BWD_DELTA_TC 11
+static constexpr int BWD_TAIL = 16 * 8 + 16;   // mbarriers (8 B each, up to 16 warps) + tmem slot
+template <bool DELTA, bool TC> struct BwdCfg {
+	static constexpr int WARPS = (DELTA && TC) ? WARPS_BWD_DELTA_TC : WARPS_BWD;
+	static constexpr int SLAB = DELTA ? WarpSlab::DELTA_END : WarpSlab::BWD_END;
+	static constexpr int STAGE0 = WeightSmem::BWD_END * 2 + WARPS * SLAB;                 // first warp's staging block
+	static constexpr int BARS = STAGE0 + (TC ? WARPS * WarpSlab::STAGE_BYTES : 0);
+	static constexpr int SMEM = BARS + (TC ? BWD_TAIL : 0);
+	static_assert(SMEM <= 227 * 1024, "training kernel exceeds the 227 KB shared-memory limit");
+	static_assert(STAGE0 % 16 == 0 && BARS % 8 == 0, "staging / barrier alignment");
+};
+// tensor-memory columns of the five weight-gradient accumulators (fp32, M = 64 rows on lanes (m % 16) + 32 (m / 16))
+#define TM_C2T 0      // dC2^T [64 hidden2][16 out]
+#define TM_C1 16      // dC1   [64 out][64 in]
+#define TM_C0 80      // dC0   [64 out][48 in]
+#define TM_W1T 128    // dW1^T [64 hidden0][16 out]
+#define TM_W0 144     // dW0   [64 out][32 in]   (first-order + second-order reverse sweep)
+#define TM_COLS_USED 176
+#define TM_COLS_ALLOC 256
 
 // A tile's coords (16 x 7 floats) travel global -> registers -> warp slab: the loads for the NEXT tile are issued before the
 // current tile is processed, so their HBM latency hides behind a whole tile of work.  Rows >= n are zero-filled; `wrap` maps
@@ -131,19 +151,77 @@ k_network_sdf(GridMeta gm, ParamLayout pl, const __half* __restrict__ params, co
 // the tile's coordinates pass through the DeltaNetwork inside forward_tile; the gradient that reaches its output
 // (grid backward w.r.t. the position + the xyz rows of both MLP input gradients) is turned into the 9 parameter gradients
 // per sample and summed: per lane in shared memory, per warp at the end, one atomicAdd per warp into delta_acc[9].
-template <bool DELTA>
-__global__ void __launch_bounds__(WARPS_BWD * 32, 1)
+// TC (default): the five MLP weight gradients are accumulated inside this kernel by the 5th-generation tensor cores: each warp
+// writes its tile's (dY, X) operand pairs to shared memory in the canonical MN-major layout and issues tcgen05.mma (M = 64,
+// K = 16 samples) into accumulators that live in tensor memory for the whole kernel; they are read back once per CTA and added to
+// the gradient buffer.  !TC: the operand pairs are staged in global memory for the split-K GEMM kernel of wgrad.cu (243 MB written,
+// 290 MB read per step: the step's largest HBM stream, which the tensor-memory accumulators remove).
+template <bool DELTA, bool TC>
+__global__ void __launch_bounds__(BwdCfg<DELTA, TC>::WARPS * 32, 1)
 k_network_fwdbwd(GridMeta gm, ParamLayout pl, const __half* __restrict__ params, const float* __restrict__ coords,
                  const __half* __restrict__ dL_dout, const uint32_t* __restrict__ n_in_ptr, uint32_t n_rows, float sdf_bias,
                  float batch_f, float* __restrict__ grads, float* __restrict__ var_acc, float* __restrict__ w1row0_acc, StagedOperands so, int dbg,
-                 float* __restrict__ delta_acc) {
+                 float* __restrict__ delta_acc, uint32_t* __restrict__ done_counter) {
+	using Cfg = BwdCfg<DELTA, TC>;
+	constexpr int NWARPS = Cfg::WARPS;
 	extern __shared__ __align__(16) unsigned char smem[];
 	__half* sw = reinterpret_cast<__half*>(smem);
-	stage_weights(sw, params, pl, true, threadIdx.x, blockDim.x);
-	__syncthreads();
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int g = lane >> 2, t = lane & 3;
-	unsigned char* slab = smem + WeightSmem::BWD_END * 2 + warp * (DELTA ? WarpSlab::DELTA_END : WarpSlab::BWD_END);
+	unsigned char* stage = smem + Cfg::STAGE0 + warp * WarpSlab::STAGE_BYTES;
+	unsigned char* sA = stage + WarpSlab::STAGE_A;
+	unsigned char* sB = stage + WarpSlab::STAGE_B;
+	uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BARS);
+	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::BARS + 16 * 8);
+	uint32_t tmem = 0;
+	uint32_t n_mma_groups = 0;      // commits this warp has issued: its mbarrier completes phase (n - 1) & 1 when the n-th group is done
+	if (TC) {
+		if (warp == 0) umma::tmem_alloc(tmem_slot, TM_COLS_ALLOC);
+		if (threadIdx.x == 32) { for (int i = 0; i < NWARPS; ++i) umma::mbar_init(&bars[i], 1); umma::mbar_init_fence(); }
+	}
+	stage_weights(sw, params, pl, true, threadIdx.x, blockDim.x);
+	if (TC) umma::fence_before_sync();
+	__syncthreads();
+	if (TC) {
+		umma::fence_after_sync();
+		tmem = *tmem_slot;
+		// clear the accumulators: 0 = 0 * 0 with accumulate off, over all used columns, before any warp adds to them
+		if (warp == 0) {
+			for (int i = lane; i < 16 * 64 * 2 / 16; i += 32) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0u, 0u, 0u, 0u);
+			umma::fence_proxy_async();
+			__syncwarp();
+			if (lane == 0) {
+				umma::fence_after_sync();
+				const uint64_t z = umma::make_desc(umma::smem_u32(sA));
+				umma::mma_f16(tmem + 0, z, z, umma::make_idesc(64, 64), 0u);
+				umma::mma_f16(tmem + 64, z, z, umma::make_idesc(64, 64), 0u);
+				umma::mma_f16(tmem + 128, z, z, umma::make_idesc(64, 48), 0u);
+				umma::commit(&bars[0]);
+			}
+			__syncwarp();
+			umma::mbar_wait(&bars[0], 0u);
+			n_mma_groups = 1;
+		}
+		umma::fence_before_sync();
+		__syncthreads();
+		umma::fence_after_sync();
+	}
+	// the previous tcgen05.mma group of this warp has read its staging block: the block may be rewritten
+	auto stage_free = [&]() { if (TC && n_mma_groups && !(dbg & 24)) umma::mbar_wait(&bars[warp], (n_mma_groups - 1) & 1u); };
+	// operands written: make them visible to the tensor core, then ONE lane issues the group and its commit
+	auto issue = [&](uint32_t col, uint32_t a_off, uint32_t b_off, uint32_t idesc) {
+		if (dbg & 8) return;      // NEUS2_DBG profiling bits (results are wrong): 8 = operands staged but never multiplied, 16 = no waits, 4 = no read-back
+		umma::fence_proxy_async();
+		__syncwarp();
+		if (lane == 0) {
+			umma::fence_after_sync();
+			umma::mma_f16(tmem + col, umma::make_desc(umma::smem_u32(sA) + a_off), umma::make_desc(umma::smem_u32(sB) + b_off), idesc, 1u);
+			umma::commit(&bars[warp]);
+		}
+		__syncwarp();
+		++n_mma_groups;
+	};
+	unsigned char* slab = smem + WeightSmem::BWD_END * 2 + warp * Cfg::SLAB;
 	float* sCoord = reinterpret_cast<float*>(slab + WarpSlab::COORD);
 	__half* sX0 = reinterpret_cast<__half*>(slab + WarpSlab::X0);
 	__half* sDIN = reinterpret_cast<__half*>(slab + WarpSlab::DIN);
@@ -183,7 +261,7 @@ k_network_fwdbwd(GridMeta gm, ParamLayout pl, const __half* __restrict__ params,
 			dlr[k] = r < n_rows ? reinterpret_cast<const uint32_t*>(dL_dout)[(size_t)(r < n_in ? r : r % n_in) * 8 + (w & 7)] : 0u;
 		}
 	};
-	const uint32_t tile0 = blockIdx.x * WARPS_BWD + warp, tile_stride = gridDim.x * WARPS_BWD;
+	const uint32_t tile0 = blockIdx.x * NWARPS + warp, tile_stride = gridDim.x * NWARPS;
 	if (tile0 < n_tiles) { prefetch_coords(cr, coords, tile0 * TILE, n_rows, n_in, lane); prefetch_dl(tile0 * TILE); }
 	for (uint32_t tile = tile0; tile < n_tiles; tile += tile_stride) {
 		const uint32_t row0 = tile * TILE;
@@ -218,14 +296,21 @@ k_network_fwdbwd(GridMeta gm, ParamLayout pl, const __half* __restrict__ params,
 			if (t >= 2) { r0 = 0u; r1 = 0u; }
 			dout[0][0] = r0; dout[0][1] = r1; dout[0][2] = 0u; dout[0][3] = 0u;
 		}
-		{   // stage dL/drgb rows [16][16]: one 16-byte store per lane
+		{   // dL/drgb rows [16][16] (columns 0..2, rest zero): one 16-byte store per lane
 			const int r = lane >> 1;
 			uint4 v = make_uint4(0u, 0u, 0u, 0u);
 			if ((lane & 1) == 0) {
 				v.x = *reinterpret_cast<const uint32_t*>(sDL + r * 16);
 				v.y = *reinterpret_cast<const uint32_t*>(sDL + r * 16 + 2) & 0xffffu;
 			}
-			if (r < n_valid) reinterpret_cast<uint4*>(so.dOUT + (size_t)(row0 + r) * 16)[lane & 1] = v;
+			if (TC) {
+				// dC2^T += H2^T dOUT: A = hidden 2 (64 wide), B = dL/drgb (16 wide).  Rows past the batch carry zero dL/dout, so every
+				// operand pair below contributes nothing for them without masking.
+				stage_free();
+				umma::stage_frags<4>(st.h2a, sA, g, t);
+				*reinterpret_cast<uint4*>(sB + (lane & 1) * UMMA_SBO + (r >> 3) * UMMA_LBO + (r & 7) * 16) = v;
+				issue(TM_C2T, 0, 0, umma::make_idesc(64, 16));
+			} else if (r < n_valid) reinterpret_cast<uint4*>(so.dOUT + (size_t)(row0 + r) * 16)[lane & 1] = v;
 		}
 		uint32_t dh2a[4][4], dh1a[4][4];
 		{
@@ -233,15 +318,29 @@ k_network_fwdbwd(GridMeta gm, ParamLayout pl, const __half* __restrict__ params,
 			mma_layer<1, 8, true>(dout, sw + WeightSmem::C2, LD_H, c, g, t);
 			pack_frags_masked<8>(c, st.h2a, dh2a);
 		}
-		if (!(dbg & 2)) store_a_global<4>(st.h2a, so.H2, 64, row0, n_valid, g, t);
-		if (!(dbg & 2)) store_a_global<4>(dh2a, so.dH2, 64, row0, n_valid, g, t);
+		if (TC) {
+			// dC1 += dH2^T H1, as two N = 32 halves: the second half of H1 is staged behind the next layer, when the first half has been read
+			stage_free();
+			umma::stage_frags<4>(dh2a, sA, g, t);
+			{ const uint32_t lo[2][4] = {{st.h1a[0][0], st.h1a[0][1], st.h1a[0][2], st.h1a[0][3]}, {st.h1a[1][0], st.h1a[1][1], st.h1a[1][2], st.h1a[1][3]}}; umma::stage_frags<2>(lo, sB, g, t); }
+			issue(TM_C1, 0, 0, umma::make_idesc(64, 32));
+		} else {
+			store_a_global<4>(st.h2a, so.H2, 64, row0, n_valid, g, t);
+			store_a_global<4>(dh2a, so.dH2, 64, row0, n_valid, g, t);
+		}
 		{
 			float c[8][4];
 			mma_layer<4, 8, true>(dh2a, sw + WeightSmem::C1, LD_H, c, g, t);
 			pack_frags_masked<8>(c, st.h1a, dh1a);
 		}
-		if (!(dbg & 2)) store_a_global<4>(st.h1a, so.H1, 64, row0, n_valid, g, t);
-		if (!(dbg & 2)) store_a_global<4>(dh1a, so.dH1, 64, row0, n_valid, g, t);
+		if (TC) {
+			stage_free();
+			{ const uint32_t hi[2][4] = {{st.h1a[2][0], st.h1a[2][1], st.h1a[2][2], st.h1a[2][3]}, {st.h1a[3][0], st.h1a[3][1], st.h1a[3][2], st.h1a[3][3]}}; umma::stage_frags<2>(hi, sB, g, t); }
+			issue(TM_C1 + 32, 0, 0, umma::make_idesc(64, 32));     // A = dH2 is still in place
+		} else {
+			store_a_global<4>(st.h1a, so.H1, 64, row0, n_valid, g, t);
+			store_a_global<4>(dh1a, so.dH1, 64, row0, n_valid, g, t);
+		}
 		uint32_t dso[1][4];
 		{
 			float c[6][4];
@@ -261,7 +360,14 @@ k_network_fwdbwd(GridMeta gm, ParamLayout pl, const __half* __restrict__ params,
 			*reinterpret_cast<uint32_t*>(sVN + (g + 8) * 8 + 2 * t) = pack_h2(c[4][2], c[4][3]);
 		}
 		// colour-MLP input [n][48]: cols 0..15 from registers, 16..47 from the slab
-		{
+		if (TC) {
+			// dC0 += dH1^T CIN
+			stage_free();
+			umma::stage_frags<4>(dh1a, sA, g, t);
+			{ const uint32_t tmp[1][4] = {{st.soa[0], st.soa[1], st.soa[2], st.soa[3]}}; umma::stage_frags<1>(tmp, sB, g, t); }
+			umma::stage_rows32(reinterpret_cast<const unsigned char*>(sCIN), LD_X0 * 2, sB, 2, lane);
+			issue(TM_C0, 0, 0, umma::make_idesc(64, 48));
+		} else {
 			uint32_t tmp[1][4] = {{st.soa[0], st.soa[1], st.soa[2], st.soa[3]}};
 			store_a_global<1>(tmp, so.CIN, 48, row0, n_valid, g, t);
 			for (int i = lane; i < 16 * 16; i += 32) {   // 16 rows x 16 words (32 halves)
@@ -276,18 +382,34 @@ k_network_fwdbwd(GridMeta gm, ParamLayout pl, const __half* __restrict__ params,
 			mma_layer<1, 8, true>(dso, sw + WeightSmem::W1, LD_H, c, g, t);
 			pack_frags_masked<8>(c, st.h0a, dh0a);
 		}
-		store_a_global<1>(dso, so.dSO, 16, row0, n_valid, g, t);
-		if (!(dbg & 2)) store_a_global<4>(st.h0a, so.H0, 64, row0, n_valid, g, t);
-		if (!(dbg & 2)) store_a_global<4>(dh0a, so.dH0, 64, row0, n_valid, g, t);
+		if (TC) {
+			// dW1^T += H0^T dSO
+			stage_free();
+			umma::stage_frags<4>(st.h0a, sA, g, t);
+			umma::stage_frags<1>(dso, sB, g, t);
+			issue(TM_W1T, 0, 0, umma::make_idesc(64, 16));
+		} else {
+			store_a_global<1>(dso, so.dSO, 16, row0, n_valid, g, t);
+			store_a_global<4>(st.h0a, so.H0, 64, row0, n_valid, g, t);
+			store_a_global<4>(dh0a, so.dH0, 64, row0, n_valid, g, t);
+		}
 		{
 			float c[4][4];
 			mma_layer<4, 4, true>(dh0a, sw + WeightSmem::W0, LD_X0, c, g, t);
 			store_c_smem<4>(c, sDX, LD_X0, g, t);
 		}
 		// sdf-MLP input [n][32]
-		for (int i = lane; i < 16 * 16; i += 32) {
-			const int r = i >> 4, w = i & 15;
-			if (r < n_valid) reinterpret_cast<uint32_t*>(so.X0 + (size_t)(row0 + r) * 32)[w] = reinterpret_cast<const uint32_t*>(sX0 + r * LD_X0)[w];
+		if (TC) {
+			// dW0 += dH0^T X0
+			stage_free();
+			umma::stage_frags<4>(dh0a, sA, g, t);
+			umma::stage_rows32(reinterpret_cast<const unsigned char*>(sX0), LD_X0 * 2, sB, 0, lane);
+			issue(TM_W0, 0, 0, umma::make_idesc(64, 32));
+		} else {
+			for (int i = lane; i < 16 * 16; i += 32) {
+				const int r = i >> 4, w = i & 15;
+				if (r < n_valid) reinterpret_cast<uint32_t*>(so.X0 + (size_t)(row0 + r) * 32)[w] = reinterpret_cast<const uint32_t*>(sX0 + r * LD_X0)[w];
+			}
 		}
 		__syncwarp();
 		// ---- per-sample: v = dL/d normal, pos_encoding_dy, second-order sdf-MLP input (nerf_network.h:476-570)
@@ -355,9 +477,27 @@ k_network_fwdbwd(GridMeta gm, ParamLayout pl, const __half* __restrict__ params,
 				w1acc[kt][2] += m0 * h_lo(tf[kt][2]) + m1 * h_lo(tf[kt][3]);
 				w1acc[kt][3] += m0 * h_hi(tf[kt][2]) + m1 * h_hi(tf[kt][3]);
 			}
-			for (int i = lane; i < 16 * 16; i += 32) {
-				const int r = i >> 4, w = i & 15;
-				if (r < n_valid) reinterpret_cast<uint32_t*>(so.dI + (size_t)(row0 + r) * 32)[w] = reinterpret_cast<const uint32_t*>(sDI + r * LD_X0)[w];
+			if (TC) {
+				// dW0 += gH^T dI with gH = relu'(h0) * W1[0,:]: the reverse sweep of the second-order term (seed e0, fully_fused_mlp.cu:1163-1174)
+				uint32_t gh[4][4];
+				#pragma unroll
+				for (int kt = 0; kt < 4; ++kt) {
+					const uint32_t wlo = *reinterpret_cast<const uint32_t*>(sw + WeightSmem::W1 + 16 * kt + 2 * t);
+					const uint32_t whi = *reinterpret_cast<const uint32_t*>(sw + WeightSmem::W1 + 16 * kt + 8 + 2 * t);
+					gh[kt][0] = wlo & relu_mask2(st.h0a[kt][0]);
+					gh[kt][1] = wlo & relu_mask2(st.h0a[kt][1]);
+					gh[kt][2] = whi & relu_mask2(st.h0a[kt][2]);
+					gh[kt][3] = whi & relu_mask2(st.h0a[kt][3]);
+				}
+				stage_free();
+				umma::stage_frags<4>(gh, sA, g, t);
+				umma::stage_rows32(reinterpret_cast<const unsigned char*>(sDI), LD_X0 * 2, sB, 0, lane);
+				issue(TM_W0, 0, 0, umma::make_idesc(64, 32));
+			} else {
+				for (int i = lane; i < 16 * 16; i += 32) {
+					const int r = i >> 4, w = i & 15;
+					if (r < n_valid) reinterpret_cast<uint32_t*>(so.dI + (size_t)(row0 + r) * 32)[w] = reinterpret_cast<const uint32_t*>(sDI + r * LD_X0)[w];
+				}
 			}
 		}
 		// ---- hash-grid gradient: first order (grid.h:371-500) + second order (grid.h:880-1007), one vector
@@ -416,7 +556,7 @@ k_network_fwdbwd(GridMeta gm, ParamLayout pl, const __half* __restrict__ params,
 					float* gl = ggrid + (size_t)gm.offset[l] * 2;
 					#pragma unroll
 					for (int c = 0; c < 8; ++c) {
-						if (!(dbg & 1)) atomicAdd(reinterpret_cast<float2*>(gl + lg.idx[c]), make_float2(a0[c], a1[c]));
+						if (!(dbg & 1)) red_add_v2f32(gl + lg.idx[c], a0[c], a1[c]);
 					}
 				}
 			}
@@ -432,7 +572,8 @@ k_network_fwdbwd(GridMeta gm, ParamLayout pl, const __half* __restrict__ params,
 			v += __shfl_xor_sync(0xffffffffu, v, 4);
 			v += __shfl_xor_sync(0xffffffffu, v, 8);
 			v += __shfl_xor_sync(0xffffffffu, v, 16);
-			if (g == 0 && v != 0.f) atomicAdd(w1row0_acc + 16 * kt + 8 * (r >> 1) + 2 * t + (r & 1), v);
+			// second-order term of W1 row 0: TC adds it to the gradient directly, !TC leaves it to k_reduce_partials
+			if (g == 0 && v != 0.f) red_add_f32((TC ? grads + pl.off_w1 : w1row0_acc) + 16 * kt + 8 * (r >> 1) + 2 * t + (r & 1), v);
 		}
 	}
 	var_local += __shfl_xor_sync(0xffffffffu, var_local, 1);
@@ -440,7 +581,7 @@ k_network_fwdbwd(GridMeta gm, ParamLayout pl, const __half* __restrict__ params,
 	var_local += __shfl_xor_sync(0xffffffffu, var_local, 4);
 	var_local += __shfl_xor_sync(0xffffffffu, var_local, 8);
 	var_local += __shfl_xor_sync(0xffffffffu, var_local, 16);
-	if (lane == 0 && var_local != 0.f) atomicAdd(var_acc, var_local);
+	if (lane == 0 && var_local != 0.f) red_add_f32(var_acc, var_local);
 	if (DELTA) {
 		__syncwarp();
 		#pragma unroll
@@ -450,7 +591,52 @@ k_network_fwdbwd(GridMeta gm, ParamLayout pl, const __half* __restrict__ params,
 			v += __shfl_xor_sync(0xffffffffu, v, 2);
 			v += __shfl_xor_sync(0xffffffffu, v, 4);
 			v += __shfl_xor_sync(0xffffffffu, v, 8);
-			if (lane == 0 && v != 0.f) atomicAdd(delta_acc + k, v);
+			if (lane == 0 && v != 0.f) red_add_f32(delta_acc + k, v);
+		}
+	}
+	if (TC) {
+		// ---- weight gradients: tensor memory -> gradient buffer, once per CTA ----
+		stage_free();                          // this warp's last group is complete
+		umma::fence_before_sync();
+		__syncthreads();                       // ... and so are everybody else's
+		umma::fence_after_sync();
+		if (n_tiles > 0 && warp < 4 && !(dbg & 4)) {
+			// warp q reads lanes 32 q .. 32 q + 31; rows 16 q .. 16 q + 15 of every accumulator sit on its first 16 lanes
+			const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
+			const int m = 16 * warp + lane;
+			const bool row = lane < 16;
+			float v[16];
+			umma::tmem_ld16(tmem + lane_base + TM_C2T, v);      // dC2[o][m]
+			if (row) { _Pragma("unroll") for (int o = 0; o < 16; ++o) red_add_f32(grads + pl.off_c2 + o * 64 + m, v[o]); }
+			umma::tmem_ld16(tmem + lane_base + TM_W1T, v);      // dW1[o][m]
+			if (row) { _Pragma("unroll") for (int o = 0; o < 16; ++o) red_add_f32(grads + pl.off_w1 + o * 64 + m, v[o]); }
+			#pragma unroll
+			for (int c = 0; c < 64; c += 16) {                  // dC1[m][c ..]
+				umma::tmem_ld16(tmem + lane_base + TM_C1 + c, v);
+				if (row) { _Pragma("unroll") for (int j = 0; j < 16; j += 4) red_add_v4f32(grads + pl.off_c1 + m * 64 + c + j, v[j], v[j + 1], v[j + 2], v[j + 3]); }
+			}
+			#pragma unroll
+			for (int c = 0; c < 48; c += 16) {                  // dC0[m][c ..]
+				umma::tmem_ld16(tmem + lane_base + TM_C0 + c, v);
+				if (row) { _Pragma("unroll") for (int j = 0; j < 16; j += 4) red_add_v4f32(grads + pl.off_c0 + m * 48 + c + j, v[j], v[j + 1], v[j + 2], v[j + 3]); }
+			}
+			#pragma unroll
+			for (int c = 0; c < 32; c += 16) {                  // dW0[m][c ..]
+				umma::tmem_ld16(tmem + lane_base + TM_W0 + c, v);
+				if (row) { _Pragma("unroll") for (int j = 0; j < 16; j += 4) red_add_v4f32(grads + pl.off_w0 + m * pl.sdf_in_w + c + j, v[j], v[j + 1], v[j + 2], v[j + 3]); }
+			}
+		}
+		umma::fence_before_sync();
+		__syncthreads();
+		if (warp == 0) umma::tmem_dealloc(tmem, TM_COLS_ALLOC);
+		// the variance gradient is the batch sum rounded ONCE to half (nerf_network.h:463-474): the last CTA to get here writes it
+		if (threadIdx.x == 0) {
+			__threadfence();
+			const uint32_t arrived = atomicInc(done_counter, gridDim.x - 1);    // wraps to 0 with the last arrival: ready for the next launch
+			if (arrived == gridDim.x - 1) {
+				__threadfence();
+				grads[pl.off_var] = round_h(*reinterpret_cast<volatile float*>(var_acc));
+			}
 		}
 	}
 }
@@ -490,26 +676,50 @@ int launch_network_sdf(cudaStream_t stream, const GridMeta& gm, const ParamLayou
 	return 0;
 }
 
-int launch_network_fwdbwd(cudaStream_t stream, const GridMeta& gm, const ParamLayout& pl, const __half* params, const float* coords,
-                          const __half* dL_dout, const uint32_t* n_in_ptr, uint32_t n_rows, float sdf_bias, uint32_t indeed_batch_size,
-                          float* grads, float* var_acc, float* w1row0_acc, const StagedOperands& so, float* delta_acc) {
-	static bool attr[NEUS_MAX_DEVICES] = {}, attr_delta[NEUS_MAX_DEVICES] = {};
-	const bool delta = gm.delta_xform != nullptr && delta_acc != nullptr;
-	if (delta ? ensure_dynamic_smem(k_network_fwdbwd<true>, BWD_SMEM_DELTA, attr_delta) : ensure_dynamic_smem(k_network_fwdbwd<false>, BWD_SMEM, attr)) return -1;
-	if (n_rows == 0) return 0;
+template <bool DELTA, bool TC>
+static int launch_fwdbwd_variant(cudaStream_t stream, const GridMeta& gm, const ParamLayout& pl, const __half* params, const float* coords,
+                                 const __half* dL_dout, const uint32_t* n_in_ptr, uint32_t n_rows, float sdf_bias, uint32_t indeed_batch_size,
+                                 float* grads, float* var_acc, float* w1row0_acc, const StagedOperands& so, float* delta_acc, uint32_t* done_counter, int dbg) {
+	using Cfg = BwdCfg<DELTA, TC>;
+	static bool attr[NEUS_MAX_DEVICES] = {};
+	if (ensure_dynamic_smem(k_network_fwdbwd<DELTA, TC>, Cfg::SMEM, attr)) return -1;
 	const uint32_t n_tiles = (n_rows + TILE - 1) / TILE;
 	uint32_t grid = (uint32_t)num_sms();
-	const uint32_t need = (n_tiles + WARPS_BWD - 1) / WARPS_BWD;
+	const uint32_t need = (n_tiles + Cfg::WARPS - 1) / Cfg::WARPS;
 	if (need < grid) grid = need;
-	static int dbg = -1;
-	if (dbg < 0) { const char* e = getenv("NEUS2_DBG"); dbg = e ? atoi(e) : 0; }
-	if (delta)
-		k_network_fwdbwd<true><<<grid, WARPS_BWD * 32, BWD_SMEM_DELTA, stream>>>(gm, pl, params, coords, dL_dout, n_in_ptr, n_rows, sdf_bias,
-			(float)indeed_batch_size, grads, var_acc, w1row0_acc, so, dbg, delta_acc);
-	else
-		k_network_fwdbwd<false><<<grid, WARPS_BWD * 32, BWD_SMEM, stream>>>(gm, pl, params, coords, dL_dout, n_in_ptr, n_rows, sdf_bias,
-			(float)indeed_batch_size, grads, var_acc, w1row0_acc, so, dbg, nullptr);
+	k_network_fwdbwd<DELTA, TC><<<grid, Cfg::WARPS * 32, Cfg::SMEM, stream>>>(gm, pl, params, coords, dL_dout, n_in_ptr, n_rows, sdf_bias,
+		(float)indeed_batch_size, grads, var_acc, w1row0_acc, so, dbg, delta_acc, done_counter);
 	COUNT_LAUNCH(1);
 	CUDA_CHECK(cudaGetLastError());
 	return 0;
+}
+
+// Profiling switches of the training kernel (NEUS2_DBG or neus2_set_debug_bits; results are WRONG with any bit set): 1 = no hash-grid
+// atomics, 4 = no read-back of the tensor-memory accumulators, 8 = weight-gradient operands staged but never multiplied, 16 = no waits
+// for tcgen05 completion.  tools/bench_fwdbwd.py times the kernel on a frozen training state with each of them.
+int g_fwdbwd_debug_bits = -1;
+
+// NEUS2_WGRAD=staged selects the global-memory operand staging + split-K GEMM kernel (wgrad.cu) instead of the in-kernel tensor-memory
+// accumulators: the A/B switch behind the measurements in DESIGN.md.  Read once per process.
+bool weight_gradients_in_kernel() {
+	static int tc = -1;
+	if (tc < 0) { const char* e = getenv("NEUS2_WGRAD"); tc = (e && !strcmp(e, "staged")) ? 0 : 1; }
+	return tc != 0;
+}
+
+int launch_network_fwdbwd(cudaStream_t stream, const GridMeta& gm, const ParamLayout& pl, const __half* params, const float* coords,
+                          const __half* dL_dout, const uint32_t* n_in_ptr, uint32_t n_rows, float sdf_bias, uint32_t indeed_batch_size,
+                          float* grads, float* var_acc, float* w1row0_acc, const StagedOperands& so, float* delta_acc, uint32_t* done_counter) {
+	if (n_rows == 0) return 0;
+	const bool delta = gm.delta_xform != nullptr && delta_acc != nullptr;
+	if (g_fwdbwd_debug_bits < 0) { const char* e = getenv("NEUS2_DBG"); g_fwdbwd_debug_bits = e ? atoi(e) : 0; }
+	const int dbg = g_fwdbwd_debug_bits;
+	const bool tc = weight_gradients_in_kernel();
+	if (!tc && !so.H2) { neus_set_error("NEUS2_WGRAD=staged needs the staged-operand buffers (set before the context is created)", __FILE__, __LINE__); return -1; }
+	if (delta) {
+		if (!tc) return launch_fwdbwd_variant<true, false>(stream, gm, pl, params, coords, dL_dout, n_in_ptr, n_rows, sdf_bias, indeed_batch_size, grads, var_acc, w1row0_acc, so, delta_acc, done_counter, dbg);
+		return launch_fwdbwd_variant<true, true>(stream, gm, pl, params, coords, dL_dout, n_in_ptr, n_rows, sdf_bias, indeed_batch_size, grads, var_acc, w1row0_acc, so, delta_acc, done_counter, dbg);
+	}
+	if (!tc) return launch_fwdbwd_variant<false, false>(stream, gm, pl, params, coords, dL_dout, n_in_ptr, n_rows, sdf_bias, indeed_batch_size, grads, var_acc, w1row0_acc, so, nullptr, done_counter, dbg);
+	return launch_fwdbwd_variant<false, true>(stream, gm, pl, params, coords, dL_dout, n_in_ptr, n_rows, sdf_bias, indeed_batch_size, grads, var_acc, w1row0_acc, so, nullptr, done_counter, dbg);
 }

@@ -272,8 +272,6 @@ def test_inference_params_before_the_first_optimizer_step(scene):
     assert torch.equal(ctx.sdf_lattice((16, 16, 16), use_inference_params=True), ctx.sdf_lattice((16, 16, 16), use_inference_params=False))
 
 
-@pytest.mark.xfail(strict=False, reason="added after round 1's GPU budget was spent: first GPU run pending (the oracle side is pinned to the reference's "
-                                        "kernels on the CPU by tests/test_golden_mesh_attributes.py)")
 def test_mesh_attributes_match_oracle(scene):
     """Vertex normals (compute_mesh_1ring) and vertex colours (compute_mesh_vertex_colors) of the extracted mesh, through the C ABI."""
     ctx = scene["ctx"]
@@ -281,7 +279,7 @@ def test_mesh_attributes_match_oracle(scene):
     v, f = ctx.marching_cubes(lat, thresh=0.0)
     nrm, col = ctx.mesh_attributes(len(v), use_inference_params=False)
     vr, fr = v.cpu().numpy(), f.cpu().numpy().astype(np.uint32)
-    assert len(vr) > 500
+    assert len(vr) > 200
     n_ref = O.mesh_vertex_normals(vr, fr)
     scale = np.abs(n_ref).max()
     # same face normals (one fused multiply-add per component on both sides); the float atomics add them in arrival order

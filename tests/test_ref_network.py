@@ -38,7 +38,6 @@ def test_product_and_oracle_match_reference_network():
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not RN.available(), reason="oracle/_ref/libngp_network_ref.so not built (make -f oracle/Makefile.ref network)")
-@pytest.mark.xfail(strict=False, reason="NerfNetwork::sdf / ::density leg added after round 1's GPU budget was spent: first GPU run pending")
 def test_sdf_and_density_match_reference_network():
     r = subprocess.run([sys.executable, "-m", "oracle.ref_network_check", "--n", "2048", "--sdf"], cwd=ROOT, capture_output=True, text=True, timeout=600)
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith('{"ref_network_check"')]
