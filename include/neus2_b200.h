@@ -151,7 +151,7 @@ int neus2_update_density_grid(neus2_ctx* ctx, void* stream);
 
 /* Testbed::train(batch) for one step (src/testbed.cu:2640-2740 -> testbed_nerf.cu:3440-4001), split so that a
  * data-parallel caller can all-reduce grads_f32 between the halves:
- *   begin: progressive level, occupancy refresh, sample generation for global rays [ray_offset, ray_offset+n_local)
+ *   begin: progressive level, occupancy refresh, sample generation for the global rays rank, rank + world_size, ... (n_local of them)
  *          of this step's rays_per_batch, forward, loss, backward on n_rows_local compacted rows.
  *   end:   optimizer step, counters read-back, rays_per_batch adaptation, rng advance.
  * world_size = 1: ray_offset = 0, n_local = 0 (= all rays), n_rows_local = 0 (= batch_size). */

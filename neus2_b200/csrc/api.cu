@@ -94,7 +94,7 @@ struct neus2_ctx {
 	// loss kernel, so while the GPU runs backward pass + optimizer the host already knows rays_per_batch of the NEXT step and
 	// enqueues its sample generation on aux_stream, ordered behind this step's fused forward+backward kernel (which owns every
 	// SM's register file) -- it overlaps the weight-gradient GEMMs and Adam.  The counters ping-pong between two buffers.
-	struct StepPlan { uint32_t R, n_local, ray_offset, max_inference, n_rays_total, training_step; uint64_t rng_state, rng_inc; };
+	struct StepPlan { uint32_t R, n_local, ray_offset, ray_stride, max_inference, n_rays_total, training_step; uint64_t rng_state, rng_inc; };
 	cudaStream_t aux_stream;
 	cudaStream_t hp_stream;     // highest priority: the step's weight-gradient GEMMs and Adam run here in the pipelined single-GPU step, so that the
 	                            // block scheduler serves them before the next step's sample-generation blocks that share the GPU with them
@@ -789,7 +789,7 @@ static int read_back_loss_scalars(neus2_ctx* ctx, cudaStream_t stream) {
 static void plan_step(const neus2_ctx* ctx, uint32_t rank, uint32_t world_size, neus2_ctx::StepPlan& p) {
 	memset(&p, 0, sizeof(p));
 	p.R = ctx->rays_per_batch;
-	p.n_local = p.R / world_size; p.ray_offset = rank * p.n_local;
+	p.n_local = p.R / world_size; p.ray_offset = rank; p.ray_stride = world_size;   // rank r traces the global rays r, r + W, r + 2 W, ...
 	// :3770-3775: the first pass is sized by the previous step's sample count, and rays whose samples do not fit are dropped (:1422-1424).
 	// Data-parallel, measured_before is the GLOBAL count and a rank's budget is its share of it (the scan over rays restarts on every rank).
 	const uint32_t before_share = (ctx->measured_before + world_size - 1) / world_size;
@@ -800,9 +800,10 @@ static void plan_step(const neus2_ctx* ctx, uint32_t rank, uint32_t world_size, 
 }
 static int launch_gen(neus2_ctx* ctx, cudaStream_t stream, const neus2_ctx::StepPlan& p, uint32_t* counters) {
 	const uint64_t st[2] = {p.rng_state, p.rng_inc};
-	return launch_generate_training_samples(stream, p.n_local, p.ray_offset, p.R, p.n_rays_total, st, ctx->ds, ctx->aabb, ctx->gmv, ctx->bitfield, ctx->cfg.snap_to_pixel_centers,
+	return launch_generate_training_samples(stream, p.n_local, p.ray_offset, p.ray_stride, p.R, p.n_rays_total, st, ctx->ds, ctx->aabb, ctx->gmv, ctx->bitfield, ctx->cfg.snap_to_pixel_centers,
 	                                        ctx->cone_angle_constant, p.max_inference, ctx->numsteps_all, ctx->base, ctx->slot, ctx->ray_indices, ctx->rays,
-	                                        ctx->numsteps, ctx->coords, counters, ctx->windows, ctx->n_windows, ctx->ray_setup);
+	                                        ctx->numsteps, ctx->coords, counters, ctx->windows, ctx->n_windows, ctx->ray_setup,
+	                                        ctx->cfg.forward_early_termination ? ctx->scan_tmp : nullptr);   // scan_tmp: free between the loss's scan of step k and of step k + 1
 }
 static bool density_grid_due(uint32_t canonical_training_step) {
 	const uint32_t n_prep_to_skip = std::min(std::max(canonical_training_step / 16u, 1u), 16u);   // testbed.cu:2669-2670: m_canonical_training_step
@@ -890,9 +891,7 @@ int neus2_train_step_begin(neus2_ctx* ctx, void* stream_, uint32_t rank, uint32_
 			// data-parallel: the counts (and loss sums) of all ranks meet here, over peer memory, and every rank reads back the same sums
 			CHECK(launch_peer_exchange(stream, ++ctx->exchange_epoch, ctx->peer_rank, ctx->peer_world, ctx->peer_sync, ctx->counters, ctx->counts_global,
 			                           loss_due ? ctx->scalar_tmp : nullptr, nullptr));
-		} else {
-			CUDA_CHECK(cudaMemcpyAsync(ctx->counts_global, ctx->counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
-		}
+		}   // one GPU: the global counts are the local ones, read back from counters[0..2] directly (no device-to-device copy)
 		if (loss_due) CHECK(read_back_loss_scalars(ctx, stream));
 		CUDA_CHECK(cudaMemcpyAsync(ctx->h_counters, ctx->counters, 12 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
 		CUDA_CHECK(cudaEventRecord(ctx->ev_counts, stream));
@@ -1008,7 +1007,8 @@ int neus2_train_step_end(neus2_ctx* ctx, void* stream_, const uint32_t* counts_g
 		stage_collect(ctx, 0); stage_collect(ctx, 1);
 	}
 	const uint32_t n_kept_local = ctx->h_counters[0];
-	uint32_t counts[3] = {ctx->h_counters[8], ctx->h_counters[9], ctx->h_counters[10]};
+	const int g0 = (pipelined && c.world_size == 1) ? 0 : 8;   // [8..10]: the (all-reduced / exchanged) global counts; one pipelined GPU: the local ones
+	uint32_t counts[3] = {ctx->h_counters[g0], ctx->h_counters[g0 + 1], ctx->h_counters[g0 + 2]};
 	if (counts_global) { counts[0] = counts_global[0]; counts[1] = counts_global[1]; counts[2] = counts_global[2]; }
 	const bool have_global = counts_global != nullptr || ctx->cfg.world_size > 1;
 	++ctx->training_step;

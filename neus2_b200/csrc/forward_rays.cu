@@ -99,8 +99,9 @@ int launch_network_forward_rays(cudaStream_t stream, const GridMeta& gm, const P
                                 uint32_t n_rays_max, __half* out, uint32_t* ray_done, uint32_t* work_counter) {
 	static bool attr[NEUS_MAX_DEVICES] = {};
 	if (ensure_dynamic_smem(k_network_forward_rays, FR_SMEM, attr)) return -1;
-	CUDA_CHECK(cudaMemsetAsync(work_counter, 0, 2 * sizeof(uint32_t), stream));
-	CUDA_CHECK(cudaMemsetAsync(ray_done, 0xff, (size_t)n_rays_max * sizeof(uint32_t), stream));   // 0xffffffff = no segment has terminated the ray
+	// Preconditions (no launches of their own): work_counter[0..1] are zero -- they are two of the step's counters, cleared with them -- and
+	// ray_done[slot] = 0xffffffff ("no segment has terminated the ray") for every kept ray, written by sample generation (k_rays_emit).
+	(void)n_rays_max;
 	k_network_forward_rays<<<device_sm_count() * 2, FR_WARPS * 32, FR_SMEM, stream>>>(gm, pl, params, sdf_bias, cos_anneal_ratio, n_kept_ptr, longest_ptr, numsteps,
 	                                                                                 coords, max_samples, out, ray_done, work_counter);
 	COUNT_LAUNCH(1);

@@ -292,14 +292,14 @@ __device__ __forceinline__ void gather_tile(const GridMeta& gm, const __half* __
 				continue;
 			}
 			const float wx[2] = {1.f - w[u][0], w[u][0]}, wy[2] = {1.f - w[u][1], w[u][1]}, wz[2] = {1.f - w[u][2], w[u][2]};
-			__half r0 = __float2half(0.f), r1 = __float2half(0.f);
+			// both features at once: one packed convert and one HADD2 per corner (each half of the pair rounds exactly as the scalar form)
+			__half2 r = __float2half2_rn(0.f);
 			#pragma unroll
 			for (int c = 0; c < 8; ++c) {
 				const float weight = (wx[c & 1] * wy[(c >> 1) & 1]) * wz[(c >> 2) & 1];
-				r0 = __hadd(r0, __float2half_rn(weight * h_lo(v[u][c])));
-				r1 = __hadd(r1, __float2half_rn(weight * h_hi(v[u][c])));
+				r = __hadd2(r, __floats2half2_rn(weight * h_lo(v[u][c]), weight * h_hi(v[u][c])));
 			}
-			xo[0] = r0; xo[1] = r1;
+			xo[0] = __low2half(r); xo[1] = __high2half(r);
 			if (WANT_DY) {
 				const float scale = gm.scale[l];
 				float g0[3] = {0.f, 0.f, 0.f}, g1[3] = {0.f, 0.f, 0.f};

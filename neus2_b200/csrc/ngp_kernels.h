@@ -12,10 +12,11 @@ struct LossParamsDev {
 	float cos_anneal_ratio;
 };
 
-int launch_generate_training_samples(cudaStream_t stream, uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, uint32_t n_rays_total, const uint64_t rng_state[2], const DatasetDev& ds,
+int launch_generate_training_samples(cudaStream_t stream, uint32_t n_rays, uint32_t ray_offset, uint32_t ray_stride, uint32_t n_rays_global, uint32_t n_rays_total, const uint64_t rng_state[2], const DatasetDev& ds,
                                      const Aabb& bb, const GlobalMove& gmv, const uint8_t* bitfield, int snap, float cone_angle, uint32_t max_samples,
                                      uint32_t* numsteps_all, uint32_t* base, uint32_t* slot, uint32_t* ray_indices, float* rays, uint32_t* numsteps,
-                                     float* coords, uint32_t* counters, void* windows, uint32_t* n_windows, float* ray_setup);
+                                     float* coords, uint32_t* counters, void* windows, uint32_t* n_windows, float* ray_setup,
+                                     uint32_t* ray_done /* nullable: per kept ray slot, set to 0xffffffff for the early-terminating first pass */);
 size_t sampling_window_bytes_per_ray();
 
 // counters: [0] = kept rays (device, from sample generation), out_counter = total compacted samples (un-clamped)

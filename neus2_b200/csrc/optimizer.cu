@@ -5,13 +5,15 @@
 // the reference's kernels (read off their SASS), so the update is bit-identical to the reference's Ema{Adam} and to
 // oracle/neus_oracle.cpp:orc_adam_ema_step.  The bias-correction factors (powf) come from a table filled by a kernel that lives in an
 // FMA-enabled translation unit (api.cu), so that libdevice's powf is compiled the way it is inside the reference build.
+#include <cmath>
 #include "ngp_common.cuh"
 #include "ngp_kernels.h"
 
 struct AdamHyper { float loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, ema_debias_old, ema_debias_new;
                    uint32_t cur_step; const float* bias_table; uint32_t bias_table_size;
                    int frozen;      // frozen: optimize_canonical_params = false (adam.h:92-94) -- every parameter returns early, only the EMA moves
-                   int zero_grads; };   // also clear the gradients that were consumed (the next step starts from zeros; only touched quads are rewritten)
+                   int zero_grads;   // also clear the gradients that were consumed (the next step starts from zeros; only touched quads are rewritten)
+                   float inv_loss_scale; };   // 1 / loss_scale when loss_scale is a power of two (the division is then an exact scaling: same bits, no IEEE divide), else 0
 // Small accumulators of the step that the next step expects cleared (variance / W1-row-0 sums, the step's counters): block 0 clears them.
 struct AdamZero { uint32_t* p[3]; uint32_t n[3]; };
 
@@ -24,7 +26,7 @@ __device__ __forceinline__ float adam_bias_factor(const AdamHyper& h, uint32_t c
 }
 
 __device__ __forceinline__ __half adam_one(bool is_matrix, float g_raw, const AdamHyper& h, float& w, float& m1, float& m2, uint32_t& step, __half p, bool& touched) {
-	float gradient = g_raw / h.loss_scale;
+	float gradient = h.inv_loss_scale != 0.f ? g_raw * h.inv_loss_scale : g_raw / h.loss_scale;
 	touched = false;
 	if (is_matrix || gradient != 0) {            // adam.h:109-112: non-matrix params with zero gradient are skipped entirely
 		touched = true;
@@ -43,6 +45,13 @@ __device__ __forceinline__ __half adam_one(bool is_matrix, float g_raw, const Ad
 		p = __float2half_rn(nw);
 	}
 	return p;
+}
+
+// 1 / x if x is a (normal) power of two with a normal reciprocal, else 0
+static float exact_reciprocal(float x) {
+	int e = 0;
+	if (!(x > 0.f) || std::frexp(x, &e) != 0.5f || e < -120 || e > 120) return 0.f;
+	return 1.0f / x;
 }
 
 // 4 consecutive parameters per thread (n and n_matrix are multiples of 4): 16-byte gradient loads; the optimizer state of an
@@ -106,7 +115,7 @@ int launch_adam_ema(cudaStream_t stream, uint64_t n, uint64_t n_matrix, float lo
 	const float ema_debias_old = 1 - (float)pow((double)ema_decay, (double)(ema_step - 1));
 	const float ema_debias_new = 1.0f / (1 - (float)pow((double)ema_decay, (double)ema_step));
 	if (n % 4 != 0 || n_matrix % 4 != 0) { neus_set_error("parameter counts must be multiples of 4", __FILE__, __LINE__); return -1; }
-	AdamHyper h = {loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, ema_debias_old, ema_debias_new, ema_step, bias_table, bias_table_size, frozen, zero_grads};
+	AdamHyper h = {loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, ema_debias_old, ema_debias_new, ema_step, bias_table, bias_table_size, frozen, zero_grads, exact_reciprocal(loss_scale)};
 	AdamZero z = {};
 	if (zero_grads) for (int a = 0; a < 3; ++a) { z.p[a] = zero_ptrs ? zero_ptrs[a] : nullptr; z.n[a] = (zero_ptrs && zero_ptrs[a]) ? zero_counts[a] : 0u; }
 	// part 0: everything.  part 1: the hash grid (all non-matrix parameters but the last quad).  part 2: the MLP weights + the last quad
@@ -197,7 +206,7 @@ int launch_adam_ema_p2p(cudaStream_t stream, uint64_t n, uint64_t n_matrix, uint
 	const float ema_debias_new = 1.0f / (1 - (float)pow((double)ema_decay, (double)ema_step));
 	if (n % 4 != 0 || n_matrix % 4 != 0) { neus_set_error("parameter counts must be multiples of 4", __FILE__, __LINE__); return -1; }
 	if (world < 1 || world > NEUS2_MAX_PEERS || rank >= world) { neus_set_error("bad rank / world size for the sharded optimizer", __FILE__, __LINE__); return -1; }
-	AdamHyper h = {loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, ema_debias_old, ema_debias_new, ema_step, bias_table, bias_table_size, frozen, zero_grads};
+	AdamHyper h = {loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, ema_debias_old, ema_debias_new, ema_step, bias_table, bias_table_size, frozen, zero_grads, exact_reciprocal(loss_scale)};
 	uint64_t q0, q1;
 	optimizer_shard(n / 4, rank, world, &q0, &q1);
 	PeerPtrs pp;

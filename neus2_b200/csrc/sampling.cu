@@ -2,7 +2,9 @@
 // Restates generate_training_samples_nerf_with_global_movement (src/testbed_nerf.cu:1263-1456), made
 // deterministic: instead of ordering rays by atomicAdd arrival (:1421,:1428) the sample base offsets and ray
 // slots come from exclusive scans in ray-index order.  Per-ray numsteps are unchanged.
-// Data-parallel sharding: a rank traces global rays [ray_offset, ray_offset + n_rays) of a batch of n_rays_global;
+// Data-parallel sharding: a rank traces the global rays ray_offset + i * ray_stride, i < n_rays (rank + i * world_size: every rank sees every
+// image in the same proportion, so the ranks' sample counts -- and with them the time to the next cross-rank exchange -- stay balanced),
+// of a batch of n_rays_global;
 // image / pixel / jitter are pure functions of the GLOBAL ray index (:1241-1261,:1304).
 #include "ngp_common.cuh"
 #include "ngp_kernels.h"
@@ -119,13 +121,13 @@ __device__ __forceinline__ uint32_t march_ray_warp(const Aabb& bb, const float r
 }
 
 __global__ void __launch_bounds__(128)
-k_rays_count(uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, uint32_t n_rays_total, Pcg32 rng, DatasetDev ds, Aabb bb, GlobalMove gmv,
+k_rays_count(uint32_t n_rays, uint32_t ray_offset, uint32_t ray_stride, uint32_t n_rays_global, uint32_t n_rays_total, Pcg32 rng, DatasetDev ds, Aabb bb, GlobalMove gmv,
              const uint8_t* __restrict__ bitfield, int snap, float cone_angle, uint32_t* __restrict__ numsteps_all,
              WindowRec* __restrict__ windows, uint32_t* __restrict__ n_windows, float* __restrict__ ray_setup) {
 	const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	const int lane = threadIdx.x & 31;
 	if (i >= n_rays) return;
-	RaySetup r = setup_ray(i + ray_offset, n_rays_global, n_rays_total, rng, ds, bb, gmv, snap != 0, cone_angle);
+	RaySetup r = setup_ray(i * ray_stride + ray_offset, n_rays_global, n_rays_total, rng, ds, bb, gmv, snap != 0, cone_angle);
 	uint32_t j = 0;
 	if (!r.skip) j = march_ray_warp(bb, r.ray_o, r.dir, r.startt, cone_angle, bitfield, NERF_STEPS, windows + (size_t)i * MAX_WINDOWS, n_windows + i, lane);
 	if (lane == 0) {
@@ -197,10 +199,11 @@ k_scan_rays(uint32_t n, const uint32_t* __restrict__ counts, uint32_t max_sample
 // Emit pass: replays the recorded windows (start of the window on the t-chain + bitmask of the positions that became
 // samples); no occupancy lookups, no control flow.  Positions are recomputed with the same arithmetic as the count pass.
 __global__ void __launch_bounds__(128)
-k_rays_emit(uint32_t n_rays, uint32_t ray_offset, Aabb bb, float cone_angle, const uint32_t* __restrict__ numsteps_all,
+k_rays_emit(uint32_t n_rays, uint32_t ray_offset, uint32_t ray_stride, Aabb bb, float cone_angle, const uint32_t* __restrict__ numsteps_all,
             const uint32_t* __restrict__ base, const uint32_t* __restrict__ slot, const WindowRec* __restrict__ windows,
             const uint32_t* __restrict__ n_windows, const float* __restrict__ ray_setup,
-            uint32_t* __restrict__ ray_indices, float* __restrict__ rays, uint32_t* __restrict__ numsteps, float* __restrict__ coords) {
+            uint32_t* __restrict__ ray_indices, float* __restrict__ rays, uint32_t* __restrict__ numsteps, float* __restrict__ coords,
+            uint32_t* __restrict__ ray_done) {
 	const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	const int lane = threadIdx.x & 31;
 	if (i >= n_rays) return;
@@ -210,7 +213,8 @@ k_rays_emit(uint32_t n_rays, uint32_t ray_offset, Aabb bb, float cone_angle, con
 	const uint32_t j_total = numsteps_all[i], b = base[i];
 	if (lane < 6) rays[(size_t)sl * 6 + lane] = rs[lane];
 	if (lane == 0) {
-		ray_indices[sl] = i + ray_offset;
+		ray_indices[sl] = i * ray_stride + ray_offset;
+		if (ray_done) ray_done[sl] = 0xffffffffu;   // first network pass: no segment has terminated this ray yet (forward_rays.cu)
 		numsteps[sl * 2 + 0] = j_total;
 		numsteps[sl * 2 + 1] = b;
 	}
@@ -246,22 +250,22 @@ k_rays_emit(uint32_t n_rays, uint32_t ray_offset, Aabb bb, float cone_angle, con
 
 size_t sampling_window_bytes_per_ray() { return sizeof(WindowRec) * MAX_WINDOWS; }
 
-int launch_generate_training_samples(cudaStream_t stream, uint32_t n_rays, uint32_t ray_offset, uint32_t n_rays_global, uint32_t n_rays_total, const uint64_t rng_state[2], const DatasetDev& ds,
+int launch_generate_training_samples(cudaStream_t stream, uint32_t n_rays, uint32_t ray_offset, uint32_t ray_stride, uint32_t n_rays_global, uint32_t n_rays_total, const uint64_t rng_state[2], const DatasetDev& ds,
                                      const Aabb& bb, const GlobalMove& gmv, const uint8_t* bitfield, int snap, float cone_angle, uint32_t max_samples,
                                      uint32_t* numsteps_all, uint32_t* base, uint32_t* slot, uint32_t* ray_indices, float* rays, uint32_t* numsteps,
-                                     float* coords, uint32_t* counters, void* windows, uint32_t* n_windows, float* ray_setup) {
+                                     float* coords, uint32_t* counters, void* windows, uint32_t* n_windows, float* ray_setup, uint32_t* ray_done) {
 	if (n_rays == 0) return 0;
 	Pcg32 rng; rng.state = rng_state[0]; rng.inc = rng_state[1];
 	const uint32_t blocks = (n_rays + 3) / 4;   // one warp per ray
-	k_rays_count<<<blocks, 128, 0, stream>>>(n_rays, ray_offset, n_rays_global, n_rays_total, rng, ds, bb, gmv, bitfield, snap, cone_angle, numsteps_all,
+	k_rays_count<<<blocks, 128, 0, stream>>>(n_rays, ray_offset, ray_stride, n_rays_global, n_rays_total, rng, ds, bb, gmv, bitfield, snap, cone_angle, numsteps_all,
 	                                        (WindowRec*)windows, n_windows, ray_setup);
 	COUNT_LAUNCH(1);
 	CUDA_CHECK(cudaGetLastError());
 	k_scan_rays<<<1, SCAN_THREADS, 0, stream>>>(n_rays, numsteps_all, max_samples, base, slot, counters);
 	COUNT_LAUNCH(1);
 	CUDA_CHECK(cudaGetLastError());
-	k_rays_emit<<<blocks, 128, 0, stream>>>(n_rays, ray_offset, bb, cone_angle, numsteps_all, base, slot, (const WindowRec*)windows, n_windows, ray_setup,
-	                                       ray_indices, rays, numsteps, coords);
+	k_rays_emit<<<blocks, 128, 0, stream>>>(n_rays, ray_offset, ray_stride, bb, cone_angle, numsteps_all, base, slot, (const WindowRec*)windows, n_windows, ray_setup,
+	                                       ray_indices, rays, numsteps, coords, ray_done);
 	COUNT_LAUNCH(1);
 	CUDA_CHECK(cudaGetLastError());
 	return 0;

@@ -2,15 +2,14 @@
 
 The reference is single-GPU (no collective anywhere); this is the build-out BASELINE.json asks for.  A ray's
 image / pixel / jitter / background colour are pure functions of its GLOBAL index and the step's RNG state
-(src/testbed_nerf.cu:1241-1261,1304,1632), so rank r simply traces global rays [r*R/W, (r+1)*R/W) and back-propagates its
-own B/W compacted rows; every loss normaliser uses the global ray count and batch size, hence the SUM of the per-rank
+(src/testbed_nerf.cu:1241-1261,1304,1632), so rank r simply traces the global rays r, r + W, r + 2W, ... (interleaved: consecutive
+ray indices walk through the images, and every rank should see every image) and back-propagates its own B/W compacted rows; every loss normaliser uses the global ray count and batch size, hence the SUM of the per-rank
 gradients is the gradient of the global batch, and one all-reduce(sum) before the fused Adam keeps all replicas identical.
 """
 
 
 def shard_range(n_total, rank, world_size):
-    """Contiguous shard [begin, end) of n_total items for `rank`; n_total must divide evenly (rays_per_batch is kept a
-    multiple of 128*world_size by the context)."""
+    """Contiguous shard [begin, end) of n_total items for `rank`; n_total must divide evenly."""
     assert n_total % world_size == 0, (n_total, world_size)
     per = n_total // world_size
     return rank * per, (rank + 1) * per
