@@ -320,7 +320,10 @@ def main():
     torch.cuda.synchronize()
     stages = ctx.stage_times()
     ctx.set_profiling(False)
+    stages_all = None
     if world > 1:
+        stages_all = [None] * world
+        dist.all_gather_object(stages_all, {k: round(v[0], 4) for k, v in stages.items()})
         dist.barrier()
 
     if rank == 0:
@@ -369,6 +372,7 @@ def main():
                          "traffic": 422.4e6, "traffic_source": "profiles/r01_captureB.md: dram__bytes_read 111.6 MB + dram__bytes_write 310.8 MB per launch (ncu --set full)",
                          "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes, "avg_launch_ms": dom_ms, "l2": l2},
             "stage_ms": {k: round(v[0], 4) for k, v in stages.items()},
+            **({"stage_ms_per_rank": stages_all} if stages_all else {}),
             "per_step": {"rays": rays / K, "samples_before_compaction": n_u / K, "samples_compacted": n_c / K, "batch_fill": fill, "training_step": int(st.training_step),
                          "first_pass_samples_evaluated_last_step": int(st.first_pass_samples)},
         }

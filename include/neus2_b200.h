@@ -185,6 +185,10 @@ int neus2_set_bitfield(neus2_ctx* ctx, const uint8_t* bitfield_host, uint64_t n_
  * loss, fused forward+backward, weight-gradient GEMMs, optimizer, whole step}; sums in ms and number of samples. */
 int neus2_set_profiling(neus2_ctx* ctx, int enable);
 int neus2_get_stage_times(neus2_ctx* ctx, float ms_sum[8], uint32_t count[8]);
+/* The same 8 stages followed by the data-parallel sync points: [8] counts exchange (behind the loss kernel), [9] gradient-ready exchange
+ * (behind the backward pass), [10] barrier behind the sharded optimizer, [11] unused.  Their time is almost entirely WAITING for the
+ * slowest peer. */
+int neus2_get_stage_times_ext(neus2_ctx* ctx, float ms_sum[12], uint32_t count[12]);
 /* Profiling only (process-wide; results are WRONG with any bit set): switches parts of the training kernel off so that their cost can be
  * timed on a frozen state (tools/bench_fwdbwd.py).  1 = no hash-grid atomics, 4 = no read-back of the tensor-memory accumulators,
  * 8 = weight-gradient operands staged but never multiplied, 16 = no waits for tcgen05 completion.  0 = normal operation. */

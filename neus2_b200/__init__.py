@@ -354,12 +354,14 @@ class Context:
     def set_profiling(self, enable=True):
         check(self._lib.neus2_set_profiling(self._h, C.c_int(int(enable))))
 
+    STAGES_EXT = STAGES + ["peer_exchange_counts", "peer_exchange_grads", "peer_barrier"]
+
     def stage_times(self):
-        """{stage: (mean ms, samples)} measured with CUDA events on the step's stream."""
-        ms = (C.c_float * 8)()
-        cnt = (C.c_uint32 * 8)()
-        check(self._lib.neus2_get_stage_times(self._h, ms, cnt))
-        return {s: ((ms[i] / cnt[i]) if cnt[i] else 0.0, int(cnt[i])) for i, s in enumerate(self.STAGES)}
+        """{stage: (mean ms, samples)} measured with CUDA events on the step's stream (data-parallel sync points included)."""
+        ms = (C.c_float * 12)()
+        cnt = (C.c_uint32 * 12)()
+        check(self._lib.neus2_get_stage_times_ext(self._h, ms, cnt))
+        return {s: ((ms[i] / cnt[i]) if cnt[i] else 0.0, int(cnt[i])) for i, s in enumerate(self.STAGES_EXT)}
 
     def launch_count(self):
         return int(self._lib.neus2_launch_count(self._h))

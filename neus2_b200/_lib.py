@@ -61,7 +61,7 @@ EXPORTS = [
     "neus2_ipc_export", "neus2_ipc_attach", "neus2_optimizer_shard", "neus2_optimizer_step_sharded",
     "neus2_optimizer_buffers", "neus2_set_optimizer_step", "neus2_set_density_grid", "neus2_mesh_attributes", "neus2_get_counters", "neus2_next_frame", "neus2_get_time_frame",
     "neus2_train_step_counts_ready", "neus2_reinit_sdf_mlp", "neus2_begin_global_movement", "neus2_set_delta_mode", "neus2_get_global_movement", "neus2_set_global_movement", "neus2_delta_gradients_device",
-    "neus2_loss_scalars_device", "neus2_peer_exchange", "neus2_peer_barrier", "neus2_canonical_training_step", "neus2_set_debug_bits",
+    "neus2_loss_scalars_device", "neus2_peer_exchange", "neus2_peer_barrier", "neus2_canonical_training_step", "neus2_set_debug_bits", "neus2_get_stage_times_ext",
 ]
 
 _lib = None

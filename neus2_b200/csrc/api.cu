@@ -23,9 +23,11 @@ void neus_set_error(const char* msg, const char* file, int line) {
 	snprintf(buf, sizeof(buf), "%s (%s:%d)", msg, file, line);
 	g_error = buf;
 }
-#define NEUS2_N_STAGES 8
+#define NEUS2_N_STAGES 12         // the first 8 are what neus2_get_stage_times reports; neus2_get_stage_times_ext adds the data-parallel sync points
+#define NEUS2_N_STAGES_BASE 8
 #define ADAM_BIAS_TABLE (1u << 20)
-enum { ST_GRID = 0, ST_GEN = 1, ST_FWD = 2, ST_LOSS = 3, ST_FWDBWD = 4, ST_WGRAD = 5, ST_OPT = 6, ST_STEP = 7 };
+enum { ST_GRID = 0, ST_GEN = 1, ST_FWD = 2, ST_LOSS = 3, ST_FWDBWD = 4, ST_WGRAD = 5, ST_OPT = 6, ST_STEP = 7,
+       ST_X_COUNTS = 8, ST_X_GRADS = 9, ST_BARRIER = 10, ST_SPARE = 11 };
 #define FAIL(msg) do { neus_set_error(msg, __FILE__, __LINE__); return -1; } while (0)
 #define CHECK(x) do { if ((x) != 0) return -1; } while (0)
 
@@ -117,6 +119,9 @@ struct neus2_ctx {
 	PeerSyncBlock* sync_block;  // this rank's flags + payload slots, written by the peers (peer_sync.cu)
 	PeerSyncPtrs peer_sync;     // every rank's block
 	uint32_t exchange_epoch, barrier_epoch;
+	uint32_t* sync_done;        // arrival counters (self-resetting) of the kernels that carry a sync point in their last block: [0] sharded optimizer
+	bool grads_exchange_fused;  // the training kernel of the step in flight carried the gradient-ready exchange: neus2_peer_exchange has nothing left to do
+	bool barrier_fused;         // the sharded optimizer of the step in flight carried the barrier: neus2_peer_barrier has nothing left to do
 	bool sharded_zeroed;        // the sharded optimizer of the step in flight cleared the gradient quads it consumed (on every rank)
 	bool barrier_zeroed;        // ... and the peer barrier behind it cleared the step's small accumulators and counters
 	bool optimizer_done;        // the sharded optimizer already ran for the step in flight
@@ -426,7 +431,7 @@ int neus2_ctx_create(const neus2_config* cfg, int device, neus2_ctx** out) {
 	CDM(ctx->grid_positions, 3 * G3n * ctx->n_cascades); CDM(ctx->grid_indices, G3n * ctx->n_cascades); CDM(ctx->grid_density, G3n * ctx->n_cascades);
 	CDM(ctx->bitfield, G3n / 8 * NERF_CASCADES); CDM(ctx->density_grid_mean, 1);
 	CTXCHECK(launch_adam_bias_table(nullptr, ctx->cfg.beta1, ctx->cfg.beta2, 1, ADAM_BIAS_TABLE - 1, ctx->adam_bias_table, ADAM_BIAS_TABLE));   // once: the optimizer only looks it up
-	CDM(ctx->sync_block, 1);
+	CDM(ctx->sync_block, 1); CDM(ctx->sync_done, 4);
 	CDM(ctx->d_xform, DELTA_XFORM_FLOATS); CDM(ctx->d_acc, 12); CDM(ctx->d_master, 12); CDM(ctx->d_m1, 12); CDM(ctx->d_m2, 12); CDM(ctx->d_steps, 12); CDM(ctx->d_params, 12);
 	CTXCHECK(reset_delta(ctx, 0));
 	if (cudaMallocHost((void**)&ctx->h_counters, 16 * sizeof(uint32_t)) != cudaSuccess || cudaMallocHost((void**)&ctx->h_scalars, 4 * sizeof(float)) != cudaSuccess) {
@@ -457,7 +462,7 @@ void neus2_ctx_destroy(neus2_ctx* ctx) {
 		ctx->coords_compacted, ctx->loss, ctx->ek_loss, ctx->mask_loss, ctx->mlp_out, ctx->dloss, ctx->so.dOUT, ctx->so.H2, ctx->so.dH2, ctx->so.H1, ctx->so.dH1,
 		ctx->so.CIN, ctx->so.dSO, ctx->so.H0, ctx->so.dH0, ctx->so.X0, ctx->so.dI, ctx->partials, ctx->var_acc, ctx->w1row0_acc, ctx->scalar_tmp, ctx->fwdbwd_done,
 		ctx->density_grid, ctx->density_grid_tmp, ctx->grid_positions, ctx->grid_indices, ctx->grid_density, ctx->bitfield, ctx->density_grid_mean,
-		ctx->d_xform, ctx->d_acc, ctx->d_master, ctx->d_m1, ctx->d_m2, ctx->d_steps, ctx->d_params, ctx->counters_buf[0], ctx->counters_buf[1], ctx->sync_block};
+		ctx->d_xform, ctx->d_acc, ctx->d_master, ctx->d_m1, ctx->d_m2, ctx->d_steps, ctx->d_params, ctx->counters_buf[0], ctx->counters_buf[1], ctx->sync_block, ctx->sync_done};
 	for (uint32_t r = 0; r < ctx->peer_world; ++r) if (r != ctx->peer_rank) {   // unmap the peers' buffers before this rank's own are freed
 		if (ctx->peer_grads[r]) cudaIpcCloseMemHandle(ctx->peer_grads[r]);
 		if (ctx->peer_params[r]) cudaIpcCloseMemHandle(ctx->peer_params[r]);
@@ -621,7 +626,8 @@ int neus2_sdf(neus2_ctx* ctx, void* stream, const float* pos, uint32_t stride, u
 
 static int launch_optimizer_part(neus2_ctx* ctx, cudaStream_t stream, float loss_scale, uint32_t adam_step, int fuse_zero, int part);
 static int backward_on_stream(neus2_ctx* ctx, cudaStream_t stream, const float* coords, const void* dL_dout, const uint32_t* n_in_dev, uint32_t n_rows,
-                              uint32_t indeed_batch_size, bool grads_zeroed, bool wgrad_on_hp = false, int grid_adam_early = 0 /* 1: start it, 2: ... and it clears the gradients it consumes */) {
+                              uint32_t indeed_batch_size, bool grads_zeroed, bool wgrad_on_hp = false, int grid_adam_early = 0 /* 1: start it, 2: ... and it clears the gradients it consumes */,
+                              bool fuse_grads_exchange = false) {
 	if (n_rows > ctx->B_local) FAIL("n_rows exceeds the context's (local) batch size");
 	ctx->step_on_hp = wgrad_on_hp;
 	if (!grads_zeroed) {
@@ -630,8 +636,14 @@ static int backward_on_stream(neus2_ctx* ctx, cudaStream_t stream, const float* 
 		CUDA_CHECK(cudaMemsetAsync(ctx->w1row0_acc, 0, 64 * sizeof(float), stream));
 	}
 	stage_begin(ctx, ST_FWDBWD, stream);
+	PeerXfer gx = {};
+	ctx->grads_exchange_fused = false;
+	if (fuse_grads_exchange) {   // data-parallel with peer mappings: the kernel's last CTA tells the peers that this rank's gradients are complete and waits for theirs
+		gx.peers = ctx->peer_sync; gx.epoch = ++ctx->exchange_epoch; gx.rank = ctx->peer_rank; gx.world = ctx->peer_world;
+		ctx->grads_exchange_fused = true;
+	}
 	CHECK(launch_network_fwdbwd(stream, ctx->gm, ctx->pl, ctx->params, coords, (const __half*)dL_dout, n_in_dev, n_rows, ctx->cfg.sdf_bias, indeed_batch_size,
-	                            ctx->grads, ctx->var_acc, ctx->w1row0_acc, ctx->so, ctx->use_delta ? ctx->d_acc : nullptr, ctx->fwdbwd_done));
+	                            ctx->grads, ctx->var_acc, ctx->w1row0_acc, ctx->so, ctx->use_delta ? ctx->d_acc : nullptr, ctx->fwdbwd_done, fuse_grads_exchange ? &gx : nullptr));
 	stage_end(ctx, ST_FWDBWD, stream);
 	CUDA_CHECK(cudaEventRecord(ctx->ev_fwdbwd_done, stream));
 	if (grid_adam_early && !wgrad_on_hp) {
@@ -889,8 +901,10 @@ int neus2_train_step_begin(neus2_ctx* ctx, void* stream_, uint32_t rank, uint32_
 		if (loss_due) CHECK(reduce_loss_scalars(ctx, stream));
 		if (peers) {
 			// data-parallel: the counts (and loss sums) of all ranks meet here, over peer memory, and every rank reads back the same sums
-			CHECK(launch_peer_exchange(stream, ++ctx->exchange_epoch, ctx->peer_rank, ctx->peer_world, ctx->peer_sync, ctx->counters, ctx->counts_global,
-			                           loss_due ? ctx->scalar_tmp : nullptr, nullptr));
+			stage_begin(ctx, ST_X_COUNTS, stream);
+			PeerXfer x1; x1.peers = ctx->peer_sync; x1.epoch = ++ctx->exchange_epoch; x1.rank = ctx->peer_rank; x1.world = ctx->peer_world;
+			CHECK(launch_peer_exchange(stream, x1, ctx->counters, ctx->counts_global, loss_due ? ctx->scalar_tmp : nullptr, nullptr));
+			stage_end(ctx, ST_X_COUNTS, stream);
 		}   // one GPU: the global counts are the local ones, read back from counters[0..2] directly (no device-to-device copy)
 		if (loss_due) CHECK(read_back_loss_scalars(ctx, stream));
 		CUDA_CHECK(cudaMemcpyAsync(ctx->h_counters, ctx->counters, 12 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
@@ -912,7 +926,7 @@ int neus2_train_step_begin(neus2_ctx* ctx, void* stream_, uint32_t rank, uint32_
 	if (no_fused_zero_b < 0) { const char* e = getenv("NEUS2_NO_FUSED_ZERO"); no_fused_zero_b = e ? atoi(e) : 0; }
 	const int early = (pipelined && world_size == 1 && split && !hp_mode && !canonical_frozen(ctx)) ? (no_fused_zero_b ? 1 : 2) : 0;
 	CHECK(backward_on_stream(ctx, stream, ctx->coords_compacted, ctx->dloss, ctx->counters + 2, rows_local, ctx->B, /*grads_zeroed=*/pre_zeroed,
-	                         /*wgrad_on_hp=*/pipelined && hp_mode, early));   // :3941-3946
+	                         /*wgrad_on_hp=*/pipelined && hp_mode, early, /*fuse_grads_exchange=*/peers && pipelined && weight_gradients_in_kernel()));   // :3941-3946
 	if (!pipelined) CUDA_CHECK(cudaMemcpyAsync(ctx->counts_global, ctx->counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
 	return 0;
 }
@@ -1041,7 +1055,9 @@ int neus2_train_step_end(neus2_ctx* ctx, void* stream_, const uint32_t* counts_g
 			// other counter buffer; the sample buffers themselves were last read by this step's loss kernel, long done.
 			plan_step(ctx, ctx->step_rank, ctx->step_world, ctx->prefetch_plan);
 			uint32_t* next_counters = ctx->counters_buf[ctx->counters_cur ^ 1];
-			CUDA_CHECK(cudaStreamWaitEvent(ctx->aux_stream, NEUS2_GEN_AFTER_FWDBWD ? ctx->ev_fwdbwd_done : ctx->ev_counts, 0));
+			static int gen_after_fwdbwd = -1;   // NEUS2_GEN_AFTER_FWDBWD=1/0 overrides the compile-time choice (A/B switch)
+			if (gen_after_fwdbwd < 0) { const char* e = getenv("NEUS2_GEN_AFTER_FWDBWD"); gen_after_fwdbwd = e ? atoi(e) : NEUS2_GEN_AFTER_FWDBWD; }
+			CUDA_CHECK(cudaStreamWaitEvent(ctx->aux_stream, gen_after_fwdbwd ? ctx->ev_fwdbwd_done : ctx->ev_counts, 0));
 			CUDA_CHECK(cudaMemsetAsync(next_counters, 0, 8 * sizeof(uint32_t), ctx->aux_stream));
 			stage_begin_set(ctx, ctx->ev_set ^ 1, ST_GEN, ctx->aux_stream);
 			CHECK(launch_gen(ctx, ctx->aux_stream, ctx->prefetch_plan, next_counters));
@@ -1124,6 +1140,13 @@ int neus2_set_profiling(neus2_ctx* ctx, int enable) {
 int neus2_get_stage_times(neus2_ctx* ctx, float ms_sum[8], uint32_t count[8]) {
 	CUDA_CHECK(cudaSetDevice(ctx->device));
 	if (ctx->profiling) { CUDA_CHECK(cudaDeviceSynchronize()); stage_collect(ctx, 0); stage_collect(ctx, 1); }   // the pipelined step reads a set back one step late
+	for (int i = 0; i < NEUS2_N_STAGES_BASE; ++i) { ms_sum[i] = ctx->stage_ms_sum[i]; count[i] = ctx->stage_count[i]; }
+	return 0;
+}
+
+int neus2_get_stage_times_ext(neus2_ctx* ctx, float ms_sum[12], uint32_t count[12]) {
+	CUDA_CHECK(cudaSetDevice(ctx->device));
+	if (ctx->profiling) { CUDA_CHECK(cudaDeviceSynchronize()); stage_collect(ctx, 0); stage_collect(ctx, 1); }
 	for (int i = 0; i < NEUS2_N_STAGES; ++i) { ms_sum[i] = ctx->stage_ms_sum[i]; count[i] = ctx->stage_count[i]; }
 	return 0;
 }
@@ -1306,9 +1329,17 @@ int neus2_optimizer_step_sharded(neus2_ctx* ctx, void* stream, float loss_scale)
 	static int no_fused_zero = -1;
 	if (no_fused_zero < 0) { const char* e = getenv("NEUS2_NO_FUSED_ZERO"); no_fused_zero = e ? atoi(e) : 0; }
 	const int zero_grads = ctx->step_pipelined && !no_fused_zero ? 1 : 0;
+	// ... and the barrier behind the optimizer ("every slice is stored everywhere") rides in the kernel's last block, together with the
+	// zero-fills of the step's small arrays: neus2_peer_barrier then has nothing left to launch
+	PeerXfer xb; xb.peers = ctx->peer_sync; xb.epoch = ++ctx->barrier_epoch; xb.rank = ctx->peer_rank; xb.world = ctx->peer_world;
+	PeerZero z = {};
+	if (zero_grads) { z.p[0] = (uint32_t*)ctx->var_acc; z.n[0] = 1u; z.p[1] = (uint32_t*)ctx->w1row0_acc; z.n[1] = 64u; z.p[2] = ctx->counters; z.n[2] = 8u; }
 	const int rc_ = launch_adam_ema_p2p((cudaStream_t)stream, ctx->n_params, ctx->pl.off_grid, ctx->peer_rank, ctx->peer_world, loss_scale, lr, c.beta1, c.beta2,
-	                                    c.epsilon, c.l2_reg, c.ema_decay, ctx->adam_step, ctx->peer_grads, ctx->peer_params, ctx->peer_ema, ctx->master, ctx->m1, ctx->m2, ctx->steps, ctx->adam_bias_table, ADAM_BIAS_TABLE, frozen, zero_grads);
+	                                    c.epsilon, c.l2_reg, c.ema_decay, ctx->adam_step, ctx->peer_grads, ctx->peer_params, ctx->peer_ema, ctx->master, ctx->m1, ctx->m2, ctx->steps, ctx->adam_bias_table, ADAM_BIAS_TABLE, frozen, zero_grads,
+	                                    &xb, &z, ctx->sync_done);
+	ctx->barrier_fused = rc_ == 0;
 	ctx->sharded_zeroed = rc_ == 0 && zero_grads;
+	ctx->barrier_zeroed = ctx->sharded_zeroed;
 	if (rc_ == 0 && ctx->use_delta) CHECK(delta_optimizer_step(ctx, (cudaStream_t)stream, loss_scale));   // every rank steps its replica on the all-reduced sums
 	stage_end(ctx, ST_OPT, (cudaStream_t)stream);
 	ctx->optimizer_done = true;
@@ -1323,9 +1354,14 @@ int neus2_optimizer_step_sharded(neus2_ctx* ctx, void* stream, float loss_scale)
 int neus2_peer_exchange(neus2_ctx* ctx, void* stream) {
 	CUDA_CHECK(cudaSetDevice(ctx->device));
 	if (!ctx->peer_world) FAIL("no peers attached: call neus2_ipc_attach first");
+	if (ctx->grads_exchange_fused) { ctx->grads_exchange_fused = false; return 0; }   // the training kernel's last CTA has done it
 	const bool carry_counts = !ctx->step_pipelined;
-	return launch_peer_exchange((cudaStream_t)stream, ++ctx->exchange_epoch, ctx->peer_rank, ctx->peer_world, ctx->peer_sync, carry_counts ? ctx->counters : nullptr,
-	                            ctx->counts_global, carry_counts && ctx->training_step % 16 == 0 ? ctx->scalar_tmp : nullptr, ctx->use_delta ? ctx->d_acc : nullptr);
+	stage_begin(ctx, ST_X_GRADS, (cudaStream_t)stream);
+	PeerXfer x2; x2.peers = ctx->peer_sync; x2.epoch = ++ctx->exchange_epoch; x2.rank = ctx->peer_rank; x2.world = ctx->peer_world;
+	const int rc_ = launch_peer_exchange((cudaStream_t)stream, x2, carry_counts ? ctx->counters : nullptr,
+	                                     ctx->counts_global, carry_counts && ctx->training_step % 16 == 0 ? ctx->scalar_tmp : nullptr, ctx->use_delta ? ctx->d_acc : nullptr);
+	stage_end(ctx, ST_X_GRADS, (cudaStream_t)stream);
+	return rc_;
 }
 
 // Barrier over the peers, stream-ordered: everything the peers enqueued before THEIR call has completed (and its peer stores have landed)
@@ -1334,12 +1370,17 @@ int neus2_peer_exchange(neus2_ctx* ctx, void* stream) {
 int neus2_peer_barrier(neus2_ctx* ctx, void* stream) {
 	CUDA_CHECK(cudaSetDevice(ctx->device));
 	if (!ctx->peer_world) FAIL("no peers attached: call neus2_ipc_attach first");
+	if (ctx->barrier_fused) { ctx->barrier_fused = false; return 0; }   // the sharded optimizer's last block has done it (and cleared the small arrays)
 	PeerZero z = {};
 	if (ctx->sharded_zeroed) {
 		z.p[0] = (uint32_t*)ctx->var_acc; z.n[0] = 1u; z.p[1] = (uint32_t*)ctx->w1row0_acc; z.n[1] = 64u; z.p[2] = ctx->counters; z.n[2] = 8u;
 		ctx->barrier_zeroed = true;
 	}
-	return launch_peer_barrier((cudaStream_t)stream, ++ctx->barrier_epoch, ctx->peer_rank, ctx->peer_world, ctx->peer_sync, z);
+	stage_begin(ctx, ST_BARRIER, (cudaStream_t)stream);
+	PeerXfer xb; xb.peers = ctx->peer_sync; xb.epoch = ++ctx->barrier_epoch; xb.rank = ctx->peer_rank; xb.world = ctx->peer_world;
+	const int rc_ = launch_peer_barrier((cudaStream_t)stream, xb, z);
+	stage_end(ctx, ST_BARRIER, (cudaStream_t)stream);
+	return rc_;
 }
 
 // ---- snapshot support (Testbed::save_snapshot / load_snapshot, src/testbed.cu:3144-3266; Trainer / Adam / EMA serialize) ----

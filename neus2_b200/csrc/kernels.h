@@ -23,7 +23,8 @@ int launch_network_sdf(cudaStream_t stream, const GridMeta& gm, const ParamLayou
                        uint32_t n, float sdf_bias, int as_density, __half* out_h, float* out_f);
 int launch_network_fwdbwd(cudaStream_t stream, const GridMeta& gm, const ParamLayout& pl, const __half* params, const float* coords,
                           const __half* dL_dout, const uint32_t* n_in_ptr, uint32_t n_rows, float sdf_bias, uint32_t indeed_batch_size,
-                          float* grads, float* var_acc, float* w1row0_acc, const StagedOperands& so, float* delta_acc, uint32_t* done_counter);
+                          float* grads, float* var_acc, float* w1row0_acc, const StagedOperands& so, float* delta_acc, uint32_t* done_counter,
+                          const struct PeerXfer* grads_ready_exchange = nullptr /* data-parallel: the kernel's last CTA runs this exchange (peer_sync.cuh) */);
 // true (default): the MLP weight gradients are accumulated inside the training kernel (tcgen05 + tensor memory), launch_weight_gradients is not
 // needed and the staged-operand buffers are not allocated; false (NEUS2_WGRAD=staged): the round-1 path through wgrad.cu
 bool weight_gradients_in_kernel();

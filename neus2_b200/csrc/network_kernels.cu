@@ -2,6 +2,7 @@
 // forward+backward training kernel.  See network.cuh for the per-warp pipeline.
 #include "network.cuh"
 #include "umma.cuh"
+#include "peer_sync.cuh"
 #include "kernels.h"
 #include <cstdlib>
 #include <cstring>
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(BwdCfg<DELTA, TC>::WARPS * 32, 1)
 k_network_fwdbwd(GridMeta gm, ParamLayout pl, const __half* __restrict__ params, const float* __restrict__ coords,
                  const __half* __restrict__ dL_dout, const uint32_t* __restrict__ n_in_ptr, uint32_t n_rows, float sdf_bias,
                  float batch_f, float* __restrict__ grads, float* __restrict__ var_acc, float* __restrict__ w1row0_acc, StagedOperands so, int dbg,
-                 float* __restrict__ delta_acc, uint32_t* __restrict__ done_counter) {
+                 float* __restrict__ delta_acc, uint32_t* __restrict__ done_counter, PeerXfer grads_ready) {
 	using Cfg = BwdCfg<DELTA, TC>;
 	constexpr int NWARPS = Cfg::WARPS;
 	extern __shared__ __align__(16) unsigned char smem[];
@@ -626,17 +627,27 @@ k_network_fwdbwd(GridMeta gm, ParamLayout pl, const __half* __restrict__ params,
 				if (row) { _Pragma("unroll") for (int j = 0; j < 16; j += 4) red_add_v4f32(grads + pl.off_w0 + m * pl.sdf_in_w + c + j, v[j], v[j + 1], v[j + 2], v[j + 3]); }
 			}
 		}
+		__threadfence();                       // every thread's gradient reductions are ordered before the arrival counter below
 		umma::fence_before_sync();
 		__syncthreads();
 		if (warp == 0) umma::tmem_dealloc(tmem, TM_COLS_ALLOC);
 		// the variance gradient is the batch sum rounded ONCE to half (nerf_network.h:463-474): the last CTA to get here writes it
+		__shared__ int s_last;
 		if (threadIdx.x == 0) {
 			__threadfence();
 			const uint32_t arrived = atomicInc(done_counter, gridDim.x - 1);    // wraps to 0 with the last arrival: ready for the next launch
-			if (arrived == gridDim.x - 1) {
+			s_last = arrived == gridDim.x - 1;
+			if (s_last) {
 				__threadfence();
 				grads[pl.off_var] = round_h(*reinterpret_cast<volatile float*>(var_acc));
 			}
+		}
+		// Data-parallel: "this rank's gradients are complete" is posted to the peers, and theirs awaited, by the same last CTA (+ the
+		// DeltaNetwork's gradient sums, summed over ranks in place): the sharded optimizer behind this kernel may read every peer's buffer.
+		// A kernel of its own would queue behind the next step's sample generation, which fills every SM this kernel frees.
+		if (grads_ready.world) {
+			__syncthreads();
+			if (s_last && warp == 0) { __threadfence_system(); peer_exchange_warp(grads_ready, nullptr, nullptr, nullptr, DELTA ? delta_acc : nullptr, lane); }
 		}
 	}
 }
@@ -679,7 +690,8 @@ int launch_network_sdf(cudaStream_t stream, const GridMeta& gm, const ParamLayou
 template <bool DELTA, bool TC>
 static int launch_fwdbwd_variant(cudaStream_t stream, const GridMeta& gm, const ParamLayout& pl, const __half* params, const float* coords,
                                  const __half* dL_dout, const uint32_t* n_in_ptr, uint32_t n_rows, float sdf_bias, uint32_t indeed_batch_size,
-                                 float* grads, float* var_acc, float* w1row0_acc, const StagedOperands& so, float* delta_acc, uint32_t* done_counter, int dbg) {
+                                 float* grads, float* var_acc, float* w1row0_acc, const StagedOperands& so, float* delta_acc, uint32_t* done_counter, int dbg,
+                                 const PeerXfer& grads_ready) {
 	using Cfg = BwdCfg<DELTA, TC>;
 	static bool attr[NEUS_MAX_DEVICES] = {};
 	if (ensure_dynamic_smem(k_network_fwdbwd<DELTA, TC>, Cfg::SMEM, attr)) return -1;
@@ -688,7 +700,7 @@ static int launch_fwdbwd_variant(cudaStream_t stream, const GridMeta& gm, const 
 	const uint32_t need = (n_tiles + Cfg::WARPS - 1) / Cfg::WARPS;
 	if (need < grid) grid = need;
 	k_network_fwdbwd<DELTA, TC><<<grid, Cfg::WARPS * 32, Cfg::SMEM, stream>>>(gm, pl, params, coords, dL_dout, n_in_ptr, n_rows, sdf_bias,
-		(float)indeed_batch_size, grads, var_acc, w1row0_acc, so, dbg, delta_acc, done_counter);
+		(float)indeed_batch_size, grads, var_acc, w1row0_acc, so, dbg, delta_acc, done_counter, grads_ready);
 	COUNT_LAUNCH(1);
 	CUDA_CHECK(cudaGetLastError());
 	return 0;
@@ -709,17 +721,22 @@ bool weight_gradients_in_kernel() {
 
 int launch_network_fwdbwd(cudaStream_t stream, const GridMeta& gm, const ParamLayout& pl, const __half* params, const float* coords,
                           const __half* dL_dout, const uint32_t* n_in_ptr, uint32_t n_rows, float sdf_bias, uint32_t indeed_batch_size,
-                          float* grads, float* var_acc, float* w1row0_acc, const StagedOperands& so, float* delta_acc, uint32_t* done_counter) {
-	if (n_rows == 0) return 0;
+                          float* grads, float* var_acc, float* w1row0_acc, const StagedOperands& so, float* delta_acc, uint32_t* done_counter,
+                          const PeerXfer* grads_ready_exchange) {
+	if (n_rows == 0 && !grads_ready_exchange) return 0;
+	if (n_rows == 0) { neus_set_error("a data-parallel rank cannot skip the training kernel: its peers wait for it", __FILE__, __LINE__); return -1; }
+	PeerXfer gx = {};
+	if (grads_ready_exchange) gx = *grads_ready_exchange;
 	const bool delta = gm.delta_xform != nullptr && delta_acc != nullptr;
 	if (g_fwdbwd_debug_bits < 0) { const char* e = getenv("NEUS2_DBG"); g_fwdbwd_debug_bits = e ? atoi(e) : 0; }
 	const int dbg = g_fwdbwd_debug_bits;
 	const bool tc = weight_gradients_in_kernel();
+	if (!tc && grads_ready_exchange) { neus_set_error("the gradient-ready exchange rides in the training kernel only with in-kernel weight gradients", __FILE__, __LINE__); return -1; }
 	if (!tc && !so.H2) { neus_set_error("NEUS2_WGRAD=staged needs the staged-operand buffers (set before the context is created)", __FILE__, __LINE__); return -1; }
 	if (delta) {
-		if (!tc) return launch_fwdbwd_variant<true, false>(stream, gm, pl, params, coords, dL_dout, n_in_ptr, n_rows, sdf_bias, indeed_batch_size, grads, var_acc, w1row0_acc, so, delta_acc, done_counter, dbg);
-		return launch_fwdbwd_variant<true, true>(stream, gm, pl, params, coords, dL_dout, n_in_ptr, n_rows, sdf_bias, indeed_batch_size, grads, var_acc, w1row0_acc, so, delta_acc, done_counter, dbg);
+		if (!tc) return launch_fwdbwd_variant<true, false>(stream, gm, pl, params, coords, dL_dout, n_in_ptr, n_rows, sdf_bias, indeed_batch_size, grads, var_acc, w1row0_acc, so, delta_acc, done_counter, dbg, gx);
+		return launch_fwdbwd_variant<true, true>(stream, gm, pl, params, coords, dL_dout, n_in_ptr, n_rows, sdf_bias, indeed_batch_size, grads, var_acc, w1row0_acc, so, delta_acc, done_counter, dbg, gx);
 	}
-	if (!tc) return launch_fwdbwd_variant<false, false>(stream, gm, pl, params, coords, dL_dout, n_in_ptr, n_rows, sdf_bias, indeed_batch_size, grads, var_acc, w1row0_acc, so, nullptr, done_counter, dbg);
-	return launch_fwdbwd_variant<false, true>(stream, gm, pl, params, coords, dL_dout, n_in_ptr, n_rows, sdf_bias, indeed_batch_size, grads, var_acc, w1row0_acc, so, nullptr, done_counter, dbg);
+	if (!tc) return launch_fwdbwd_variant<false, false>(stream, gm, pl, params, coords, dL_dout, n_in_ptr, n_rows, sdf_bias, indeed_batch_size, grads, var_acc, w1row0_acc, so, nullptr, done_counter, dbg, gx);
+	return launch_fwdbwd_variant<false, true>(stream, gm, pl, params, coords, dL_dout, n_in_ptr, n_rows, sdf_bias, indeed_batch_size, grads, var_acc, w1row0_acc, so, nullptr, done_counter, dbg, gx);
 }

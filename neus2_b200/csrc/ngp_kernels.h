@@ -35,20 +35,22 @@ int launch_adam_bias_table(cudaStream_t stream, float beta1, float beta2, uint32
 
 #define NEUS2_MAX_PEERS 8
 void optimizer_shard(uint64_t n_quads, uint32_t rank, uint32_t world, uint64_t* q0, uint64_t* q1);
-// zero_grads: every gradient quad this rank consumed (its slice of EVERY rank's buffer) is cleared through the same peer mapping, touched quads only
-int launch_adam_ema_p2p(cudaStream_t stream, uint64_t n, uint64_t n_matrix, uint32_t rank, uint32_t world, float loss_scale, float lr, float beta1, float beta2,
-                        float eps, float l2_reg, float ema_decay, uint32_t ema_step, float* const* grads_peers, __half* const* params_peers,
-                        __half* const* ema_peers, float* master, float* m1, float* m2, uint32_t* steps, float* bias_table, uint32_t bias_table_size, int frozen, int zero_grads);
-
 // ---- cross-GPU ordering points of the data-parallel step over peer memory (peer_sync.cu) ----
 #define PEER_PAYLOAD_WORDS 20   // {kept rays, samples, compacted, 0 | loss sums 4 | DeltaNetwork gradient sums 12}
 struct PeerSlot { uint32_t payload[PEER_PAYLOAD_WORDS]; uint32_t pad[11]; uint32_t flag; };   // one 128-byte line; written by exactly one peer
 struct PeerSyncBlock { PeerSlot exchange[2][NEUS2_MAX_PEERS]; PeerSlot barrier[NEUS2_MAX_PEERS]; };   // exchange slots alternate with the epoch's parity
 struct PeerSyncPtrs { PeerSyncBlock* block[NEUS2_MAX_PEERS]; };   // indexed by RANK (every rank's block as mapped into this process)
 struct PeerZero { uint32_t* p[3]; uint32_t n[3]; };
-int launch_peer_exchange(cudaStream_t stream, uint32_t epoch, uint32_t rank, uint32_t world, const PeerSyncPtrs& peers, const uint32_t* counts_local,
-                         uint32_t* counts_global, float* loss_sums, float* delta_acc);   // null = not part of this call's payload
-int launch_peer_barrier(cudaStream_t stream, uint32_t epoch, uint32_t rank, uint32_t world, const PeerSyncPtrs& peers, const PeerZero& z);
+struct PeerXfer { PeerSyncPtrs peers; uint32_t epoch, rank, world; };   // world == 0: no exchange (passed by value to the kernels that can carry one)
+int launch_peer_exchange(cudaStream_t stream, const PeerXfer& x, const uint32_t* counts_local, uint32_t* counts_global, float* loss_sums, float* delta_acc);   // null = not part of this call's payload
+int launch_peer_barrier(cudaStream_t stream, const PeerXfer& x, const PeerZero& z);
+
+// zero_grads: every gradient quad this rank consumed (its slice of EVERY rank's buffer) is cleared through the same peer mapping, touched quads only
+int launch_adam_ema_p2p(cudaStream_t stream, uint64_t n, uint64_t n_matrix, uint32_t rank, uint32_t world, float loss_scale, float lr, float beta1, float beta2,
+                        float eps, float l2_reg, float ema_decay, uint32_t ema_step, float* const* grads_peers, __half* const* params_peers,
+                        __half* const* ema_peers, float* master, float* m1, float* m2, uint32_t* steps, float* bias_table, uint32_t bias_table_size, int frozen, int zero_grads,
+                        const PeerXfer* barrier = nullptr /* the kernel's last block runs this barrier over the peers and then clears `zero` */, const PeerZero* zero = nullptr,
+                        uint32_t* done_counter = nullptr);
 
 int launch_density_grid_samples(cudaStream_t stream, uint32_t n, const uint64_t rng_state[2], uint32_t step, const Aabb& bb, const float* grid_in,
                                 uint32_t n_cascades, float thresh, float* positions, uint32_t* indices);

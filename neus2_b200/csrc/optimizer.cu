@@ -8,6 +8,7 @@
 #include <cmath>
 #include "ngp_common.cuh"
 #include "ngp_kernels.h"
+#include "peer_sync.cuh"
 
 struct AdamHyper { float loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, ema_debias_old, ema_debias_new;
                    uint32_t cur_step; const float* bias_table; uint32_t bias_table_size;
@@ -145,11 +146,35 @@ int launch_adam_ema(cudaStream_t stream, uint64_t n, uint64_t n_matrix, float lo
 // ------------------------------------------------------------------------------------------------------------------------
 struct PeerPtrs { float* grads[NEUS2_MAX_PEERS]; __half* params[NEUS2_MAX_PEERS]; __half* ema[NEUS2_MAX_PEERS]; };
 
+__device__ __forceinline__ void adam_ema_p2p_quad(uint64_t q, uint64_t n_matrix4, const AdamHyper& h, int world, const PeerPtrs& peers,
+                                                  float* __restrict__ master, float* __restrict__ m1, float* __restrict__ m2, uint32_t* __restrict__ steps);
+
 __global__ void __launch_bounds__(256)
 k_adam_ema_p2p(uint64_t q0, uint64_t q1, uint64_t n_matrix4, AdamHyper h, int world, PeerPtrs peers,
-               float* __restrict__ master, float* __restrict__ m1, float* __restrict__ m2, uint32_t* __restrict__ steps) {
+               float* __restrict__ master, float* __restrict__ m1, float* __restrict__ m2, uint32_t* __restrict__ steps,
+               PeerXfer barrier, PeerZero zero, uint32_t* __restrict__ done_counter) {
 	const uint64_t q = q0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (q >= q1) return;
+	if (q < q1) adam_ema_p2p_quad(q, n_matrix4, h, world, peers, master, m1, m2, steps);
+	if (barrier.world == 0) return;
+	// The barrier "every rank's slice is stored everywhere" rides in this kernel's LAST block (it owns its SM already: a kernel of its own
+	// would queue behind the next step's sample generation, which fills every SM the training kernel frees).  Peer stores of all blocks are
+	// ordered before the flags: fence.sys + arrival counter on the writers' side, counter + fence.sys + release on the last block's side.
+	__shared__ int s_last;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence_system();
+		s_last = atomicInc(done_counter, gridDim.x - 1) == gridDim.x - 1;   // wraps to 0 with the last arrival
+	}
+	__syncthreads();
+	if (!s_last) return;
+	if (threadIdx.x < 32) { __threadfence_system(); peer_barrier_warp(barrier, (int)threadIdx.x); }
+	__syncthreads();
+	#pragma unroll
+	for (int a = 0; a < 3; ++a) for (uint32_t i = threadIdx.x; i < zero.n[a]; i += blockDim.x) zero.p[a][i] = 0u;
+}
+
+__device__ __forceinline__ void adam_ema_p2p_quad(uint64_t q, uint64_t n_matrix4, const AdamHyper& h, int world, const PeerPtrs& peers,
+                                                  float* __restrict__ master, float* __restrict__ m1, float* __restrict__ m2, uint32_t* __restrict__ steps) {
 	const bool is_matrix = q < n_matrix4;
 	float4 gr[NEUS2_MAX_PEERS];
 	#pragma unroll
@@ -201,7 +226,8 @@ k_adam_ema_p2p(uint64_t q0, uint64_t q1, uint64_t n_matrix4, AdamHyper h, int wo
 
 int launch_adam_ema_p2p(cudaStream_t stream, uint64_t n, uint64_t n_matrix, uint32_t rank, uint32_t world, float loss_scale, float lr, float beta1, float beta2,
                         float eps, float l2_reg, float ema_decay, uint32_t ema_step, float* const* grads_peers, __half* const* params_peers,
-                        __half* const* ema_peers, float* master, float* m1, float* m2, uint32_t* steps, float* bias_table, uint32_t bias_table_size, int frozen, int zero_grads) {
+                        __half* const* ema_peers, float* master, float* m1, float* m2, uint32_t* steps, float* bias_table, uint32_t bias_table_size, int frozen, int zero_grads,
+                        const PeerXfer* barrier, const PeerZero* zero, uint32_t* done_counter) {
 	const float ema_debias_old = 1 - (float)pow((double)ema_decay, (double)(ema_step - 1));
 	const float ema_debias_new = 1.0f / (1 - (float)pow((double)ema_decay, (double)ema_step));
 	if (n % 4 != 0 || n_matrix % 4 != 0) { neus_set_error("parameter counts must be multiples of 4", __FILE__, __LINE__); return -1; }
@@ -215,9 +241,11 @@ int launch_adam_ema_p2p(cudaStream_t stream, uint64_t n, uint64_t n_matrix, uint
 	uint32_t slot = 0;
 	pp.grads[slot] = grads_peers[rank]; pp.params[slot] = params_peers[rank]; pp.ema[slot] = ema_peers[rank]; ++slot;
 	for (uint32_t r = 0; r < world; ++r) if (r != rank) { pp.grads[slot] = grads_peers[r]; pp.params[slot] = params_peers[r]; pp.ema[slot] = ema_peers[r]; ++slot; }
-	if (q1 > q0) {
-		const uint32_t blocks = (uint32_t)((q1 - q0 + 255) / 256);
-		k_adam_ema_p2p<<<blocks, 256, 0, stream>>>(q0, q1, n_matrix / 4, h, (int)world, pp, master, m1, m2, steps);
+	PeerXfer xb = {}; PeerZero z = {};
+	if (barrier) { if (!done_counter) { neus_set_error("the fused barrier needs an arrival counter", __FILE__, __LINE__); return -1; } xb = *barrier; if (zero) z = *zero; }
+	if (q1 > q0 || barrier) {
+		const uint32_t blocks = q1 > q0 ? (uint32_t)((q1 - q0 + 255) / 256) : 1u;
+		k_adam_ema_p2p<<<blocks, 256, 0, stream>>>(q0, q1, n_matrix / 4, h, (int)world, pp, master, m1, m2, steps, xb, z, done_counter);
 		COUNT_LAUNCH(1);
 	}
 	CUDA_CHECK(cudaGetLastError());
