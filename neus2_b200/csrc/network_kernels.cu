@@ -11,13 +11,16 @@
 #define THREADS_PER_CTA (WARPS_PER_CTA * 32)
 
 static constexpr int FWD_SMEM = WeightSmem::FWD_END * 2 + WARPS_PER_CTA * WarpSlab::FWD_END;
+#ifndef WARPS_BWD
 #define WARPS_BWD 12
+#endif
+#define WARPS_BWD_LAUNCH_BOUND 12   // registers are budgeted for 12 warps (168 each) whatever WARPS_BWD is
 #ifndef MERGE_MAX_HEADS
 #define MERGE_MAX_HEADS 10     // pre-reduce a level's atomics in the warp when its 16 samples fall into <= this many runs of equal cells
 #endif
 // Training kernel, shared memory: weights | per-warp slabs | (TC) per-warp operand staging | (TC) one mbarrier per warp + the
 // tensor-memory base address.  The DeltaNetwork variant has a larger slab and runs one warp less when it stages in shared memory.
-#define WARPS_BWD_DELTA_TC 11
+#define WARPS_BWD_DELTA_TC (WARPS_BWD < 11 ? WARPS_BWD : 11)
 static constexpr int BWD_TAIL = 16 * 8 + 16;   // mbarriers (8 B each, up to 16 warps) + tmem slot
 template <bool DELTA, bool TC> struct BwdCfg {
 	static constexpr int WARPS = (DELTA && TC) ? WARPS_BWD_DELTA_TC : WARPS_BWD;
@@ -158,7 +161,7 @@ k_network_sdf(GridMeta gm, ParamLayout pl, const __half* __restrict__ params, co
 // the gradient buffer.  !TC: the operand pairs are staged in global memory for the split-K GEMM kernel of wgrad.cu (243 MB written,
 // 290 MB read per step: the step's largest HBM stream, which the tensor-memory accumulators remove).
 template <bool DELTA, bool TC>
-__global__ void __launch_bounds__(BwdCfg<DELTA, TC>::WARPS * 32, 1)
+__global__ void __launch_bounds__(WARPS_BWD_LAUNCH_BOUND * 32, 1)
 k_network_fwdbwd(GridMeta gm, ParamLayout pl, const __half* __restrict__ params, const float* __restrict__ coords,
                  const __half* __restrict__ dL_dout, const uint32_t* __restrict__ n_in_ptr, uint32_t n_rows, float sdf_bias,
                  float batch_f, float* __restrict__ grads, float* __restrict__ var_acc, float* __restrict__ w1row0_acc, StagedOperands so, int dbg,
