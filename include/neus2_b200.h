@@ -81,6 +81,10 @@ typedef struct neus2_config {
 	uint32_t decay_interval;         /* 10000 (0 = no decay) */
 	uint32_t decay_end;              /* 10000000 (the reference's default; base.json does not set it) */
 	float decay_base;                /* 0.33 */
+	/* "reset_density_grid_after_global_movement" (src/testbed.cu:2123, 2664-2666; reset_density_grid_nerf, src/testbed_nerf.cu:3205-3291): on
+	 * frames >= 1, at the step where the canonical model starts training again (training_step == frozen_steps), the occupancy grid is rebuilt
+	 * from zero with one uniform pass over every cell.  The reference's code default is true, configs/nerf/base.json:130 sets false (the default here). */
+	int32_t reset_density_grid_after_global_movement;
 } neus2_config;
 
 typedef struct neus2_step_stats {

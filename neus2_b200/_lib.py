@@ -29,6 +29,7 @@ class Config(C.Structure):
         ("delta_learning_rate", C.c_float), ("delta_beta1", C.c_float), ("delta_beta2", C.c_float), ("delta_epsilon", C.c_float),
         ("delta_decay_start", C.c_uint32), ("delta_decay_interval", C.c_uint32), ("delta_decay_base", C.c_float),
         ("decay_start", C.c_uint32), ("decay_interval", C.c_uint32), ("decay_end", C.c_uint32), ("decay_base", C.c_float),
+        ("reset_density_grid_after_global_movement", C.c_int32),
     ]
 
 

@@ -740,20 +740,23 @@ int neus2_set_dataset(neus2_ctx* ctx, uint32_t n_images, int32_t width, int32_t 
 	return 0;
 }
 
-static int update_density_grid_on_stream(neus2_ctx* ctx, cudaStream_t stream);
+static int update_density_grid_on_stream(neus2_ctx* ctx, cudaStream_t stream, bool reset = false);
 int neus2_update_density_grid(neus2_ctx* ctx, void* stream_) {   // training_prep_nerf (:4003-4016) -> update_density_grid_nerf (:3293-3375)
 	CUDA_CHECK(cudaSetDevice(ctx->device));
 	invalidate_prefetch(ctx);   // the occupancy bitfield changes
 	return update_density_grid_on_stream(ctx, (cudaStream_t)stream_);
 }
-static int update_density_grid_on_stream(neus2_ctx* ctx, cudaStream_t stream) {
+// reset: Testbed::reset_density_grid_nerf (src/testbed_nerf.cu:3205-3291) -- the same update from a zeroed grid with one uniform sample in every cell
+static int update_density_grid_on_stream(neus2_ctx* ctx, cudaStream_t stream, bool reset) {
 	void* stream_ = (void*)stream; (void)stream_;
 	const uint32_t G3n = NERF_GRIDSIZE * NERF_GRIDSIZE * NERF_GRIDSIZE;
 	const uint32_t n_elements = G3n * ctx->n_cascades;
 	uint32_t n_uniform, n_nonuniform;
-	if (canonical_training_step(ctx) < 256) { n_uniform = G3n * ctx->n_cascades; n_nonuniform = 0; }   // training_prep_nerf (:4011)
+	if (reset || canonical_training_step(ctx) < 256) { n_uniform = G3n * ctx->n_cascades; n_nonuniform = 0; }   // training_prep_nerf (:4011)
 	else { n_uniform = G3n / 4 * ctx->n_cascades; n_nonuniform = G3n / 4 * ctx->n_cascades; }
-	if (ctx->training_step == 0) {
+	if (reset) {
+		CUDA_CHECK(cudaMemsetAsync(ctx->density_grid, 0, sizeof(float) * n_elements, stream));   // the decay counter keeps running (:3249, 3287)
+	} else if (ctx->training_step == 0) {
 		ctx->density_grid_ema_step = 0;
 		CUDA_CHECK(cudaMemsetAsync(ctx->density_grid, 0, sizeof(float) * n_elements, stream));
 	}
@@ -835,6 +838,11 @@ int neus2_train_step_begin(neus2_ctx* ctx, void* stream_, uint32_t rank, uint32_
 	neus2_set_training_step(ctx, ctx->time_frame >= 1 ? (int32_t)ctx->training_step - (int32_t)ctx->frozen_steps : (int32_t)ctx->training_step);   // testbed.cu:2651-2657
 	ctx->step_density_updated = false;
 	stage_begin(ctx, ST_STEP, stream);
+	if (c.reset_density_grid_after_global_movement && ctx->time_frame >= 1 && ctx->training_step == ctx->frozen_steps) {
+		// the canonical model starts training again (testbed.cu:2659-2666): rebuild the occupancy grid from zero before the regular refresh
+		CHECK(update_density_grid_on_stream(ctx, stream, /*reset=*/true));
+		ctx->step_density_updated = true;
+	}
 	if (density_grid_due(canonical_training_step(ctx))) {
 		stage_begin(ctx, ST_GRID, stream);
 		CHECK(update_density_grid_on_stream(ctx, stream));

@@ -315,4 +315,6 @@ def config_from_json(cfg_json):
             kw[dst] = float(hp[src])
     if "anneal_end" in hp:
         kw["anneal_end"] = int(hp["anneal_end"])
+    if hp:                                                  # src/testbed.cu:2123: the CODE default is true; configs/nerf/base.json sets false
+        kw["reset_density_grid_after_global_movement"] = int(bool(hp.get("reset_density_grid_after_global_movement", True)))
     return kw

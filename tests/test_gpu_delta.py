@@ -186,6 +186,9 @@ def test_global_movement_recovers_a_rigid_motion(tmp_path):
     st = tb.train(1 << 18)                                   # first joint step
     s51 = tb._ctx.get_state()
     assert s51["optimizer_step"] == 1 and s51["canonical_training_step"] == 1 and s51["n_rays_total"] == st.rays_per_batch
+    # "reset_density_grid_after_global_movement" (code default true, src/testbed.cu:2123, 2664-2666): at this step the occupancy grid was rebuilt
+    # from zero (one uniform pass, reset_density_grid_nerf) BEFORE the step's regular refresh: two updates in one step
+    assert s51["density_grid_ema_step"] == 52
     from tests import util as U                              # EMA step 1 is debiased to the parameters themselves (ema.h:64-77)
     assert U.half_ulp_diff(tb._ctx.buffers()[2].cpu().numpy().view(np.uint16), tb._ctx.buffers()[1].cpu().numpy().view(np.uint16)).max() <= 1
     tb.train(1 << 18)

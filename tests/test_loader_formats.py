@@ -31,7 +31,12 @@ def test_config_json_with_comments():
                   "decay_start": 20000, "decay_interval": 10000, "decay_end": 10000000, "decay_base": 0.1,
                   # no "globalmove" section: the DeltaNetwork's trainer is built from the main optimizer config (testbed.cu:2320-2323)
                   "delta_decay_start": 20000, "delta_decay_interval": 10000, "delta_decay_base": 0.1,
-                  "delta_learning_rate": 1e-3, "delta_beta1": 0.9, "delta_beta2": 0.99, "delta_epsilon": 1e-15}
+                  "delta_learning_rate": 1e-3, "delta_beta1": 0.9, "delta_beta2": 0.99, "delta_epsilon": 1e-15,
+                  # not in this json: the reference's CODE default is true (src/testbed.cu:2123); configs/nerf/base.json:130 sets false
+                  "reset_density_grid_after_global_movement": 1}
+    off = json.loads(loader._strip_json_comments(BASE_JSON))
+    off["hyperparams"]["reset_density_grid_after_global_movement"] = False
+    assert loader.config_from_json(off)["reset_density_grid_after_global_movement"] == 0
     gm = json.loads(loader._strip_json_comments(BASE_JSON))
     gm["globalmove"] = {"optimizer": {"otype": "Ema", "decay": 0.95, "nested": {"otype": "ExponentialDecay", "decay_start": 50, "decay_interval": 25,
                         "decay_base": 0.99, "nested": {"otype": "Adam", "learning_rate": 1e-4, "beta1": 0.9, "beta2": 0.99, "epsilon": 1e-10}}}}
