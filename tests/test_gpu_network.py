@@ -163,3 +163,16 @@ def test_learning_rate_decay_reaches_the_adam_kernel():
         assert np.array_equal(params_h.cpu().numpy().view(np.uint16), ph) and np.array_equal(ema_h.cpu().numpy().view(np.uint16), ema)
     finally:
         ctx.close()
+
+
+def test_staged_weight_gradient_path_still_matches_oracle():
+    """NEUS2_WGRAD=staged (round 1's path: operand staging in global memory + the split-K GEMM kernel) stays available as the A/B partner of
+    the in-kernel tensor-memory accumulators; the switch is read once per process, so the backward parity test above runs again in a child."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, NEUS2_WGRAD="staged")
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_network.py", "-q", "-x", "-m", "gpu", "-k", "test_backward_matches_oracle"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "3 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
