@@ -244,7 +244,7 @@ int neus2_mesh_buffers(neus2_ctx* ctx, float** verts_dev, uint32_t** indices_dev
 int neus2_mesh_attributes(neus2_ctx* ctx, void* stream, float* normals_out_dev, float* colors_out_dev, int use_inference_params);
 
 /* ---- data-parallel training over one NVSwitch domain (not in the reference, which is single-GPU) -----------------
- * The optimizer step fused with its collective: rank r owns a contiguous 1/W slice of the parameters, sums that slice of every
+ * The optimizer step fused with its collective: rank r owns every W-th block of 1024 parameters (1/W of them), sums those of every
  * rank's gradient buffer through NVLink peer loads, applies Adam + EMA to it and stores the new fp16 parameters / EMA values
  * into every rank's buffers.  Set-up: each rank exports CUDA IPC handles of its {gradient, fp16 parameter, EMA} buffers, the
  * host side exchanges them (torch.distributed all_gather), every rank attaches all of them.  A fourth mapped buffer is a small
@@ -261,7 +261,9 @@ int neus2_mesh_attributes(neus2_ctx* ctx, void* stream, float* normals_out_dev, 
 #define NEUS2_IPC_HANDLE_BYTES 64
 int neus2_ipc_export(neus2_ctx* ctx, unsigned char* handles /* NEUS2_IPC_BUFFERS x NEUS2_IPC_HANDLE_BYTES */);
 int neus2_ipc_attach(neus2_ctx* ctx, uint32_t rank, uint32_t world_size, const unsigned char* all_handles /* [world_size][NEUS2_IPC_BUFFERS][64] */);
-int neus2_optimizer_shard(const neus2_ctx* ctx, uint32_t rank, uint32_t world_size, uint64_t* begin, uint64_t* end);   /* parameter index range */
+/* Ownership of the sharded optimizer: blocks of *block_params consecutive parameters are dealt round-robin, parameter i belongs to rank
+ * (i / *block_params) % world_size; *n_owned = how many parameters that gives `rank`. */
+int neus2_optimizer_shard(const neus2_ctx* ctx, uint32_t rank, uint32_t world_size, uint64_t* block_params, uint64_t* n_owned);
 int neus2_optimizer_step_sharded(neus2_ctx* ctx, void* stream, float loss_scale);
 int neus2_peer_exchange(neus2_ctx* ctx, void* stream);
 int neus2_peer_barrier(neus2_ctx* ctx, void* stream);

@@ -214,6 +214,8 @@ class Context:
         self.peers_attached = True
 
     def optimizer_shard(self, rank, world_size):
+        """(block_params, n_owned): the sharded optimizer deals blocks of block_params parameters round-robin -- parameter i belongs to
+        rank (i // block_params) % world_size -- which gives `rank` n_owned parameters."""
         b, e = C.c_uint64(), C.c_uint64()
         check(self._lib.neus2_optimizer_shard(self._h, C.c_uint32(rank), C.c_uint32(world_size), C.byref(b), C.byref(e)))
         return int(b.value), int(e.value)

@@ -1309,11 +1309,12 @@ int neus2_ipc_attach(neus2_ctx* ctx, uint32_t rank, uint32_t world, const unsign
 	return 0;
 }
 
-int neus2_optimizer_shard(const neus2_ctx* ctx, uint32_t rank, uint32_t world, uint64_t* begin, uint64_t* end) {
-	if (!world || rank >= world || !begin || !end) FAIL("bad argument");
-	uint64_t q0, q1;
-	optimizer_shard(ctx->n_params / 4, rank, world, &q0, &q1);
-	*begin = q0 * 4; *end = q1 * 4;
+int neus2_optimizer_shard(const neus2_ctx* ctx, uint32_t rank, uint32_t world, uint64_t* block_params, uint64_t* n_owned) {
+	if (!world || rank >= world || !block_params || !n_owned) FAIL("bad argument");
+	const uint64_t bp = 4ull * OPTIMIZER_BLOCK_QUADS, n = ctx->n_params;
+	uint64_t owned = 0;
+	for (uint64_t b = rank; b * bp < n; b += world) owned += std::min(bp, n - b * bp);
+	*block_params = bp; *n_owned = owned;
 	return 0;
 }
 
@@ -1337,17 +1338,23 @@ int neus2_optimizer_step_sharded(neus2_ctx* ctx, void* stream, float loss_scale)
 	static int no_fused_zero = -1;
 	if (no_fused_zero < 0) { const char* e = getenv("NEUS2_NO_FUSED_ZERO"); no_fused_zero = e ? atoi(e) : 0; }
 	const int zero_grads = ctx->step_pipelined && !no_fused_zero ? 1 : 0;
-	// ... and the barrier behind the optimizer ("every slice is stored everywhere") rides in the kernel's last block, together with the
-	// zero-fills of the step's small arrays: neus2_peer_barrier then has nothing left to launch
+	// NEUS2_FUSED_BARRIER=1: the barrier behind the optimizer ("every slice is stored everywhere") rides in the kernel's last block, together
+	// with the zero-fills of the step's small arrays.  Off by default -- measured slower (2 GPUs: optimizer + barrier 0.10 -> 0.20 ms): every
+	// block then needs a system-scope fence behind its peer stores before it may count itself as arrived, i.e. it sits on its SM until its
+	// NVLink writes are acknowledged; a kernel boundary flushes them for free, and a ONE-warp barrier kernel behind it still finds a slot next
+	// to the prefetched sample generation (whose blocks fill the register file, not the thread slots)
+	static int fuse_barrier = -1;
+	if (fuse_barrier < 0) { const char* e = getenv("NEUS2_FUSED_BARRIER"); fuse_barrier = e ? atoi(e) : 0; }
 	PeerXfer xb; xb.peers = ctx->peer_sync; xb.epoch = ++ctx->barrier_epoch; xb.rank = ctx->peer_rank; xb.world = ctx->peer_world;
 	PeerZero z = {};
 	if (zero_grads) { z.p[0] = (uint32_t*)ctx->var_acc; z.n[0] = 1u; z.p[1] = (uint32_t*)ctx->w1row0_acc; z.n[1] = 64u; z.p[2] = ctx->counters; z.n[2] = 8u; }
 	const int rc_ = launch_adam_ema_p2p((cudaStream_t)stream, ctx->n_params, ctx->pl.off_grid, ctx->peer_rank, ctx->peer_world, loss_scale, lr, c.beta1, c.beta2,
 	                                    c.epsilon, c.l2_reg, c.ema_decay, ctx->adam_step, ctx->peer_grads, ctx->peer_params, ctx->peer_ema, ctx->master, ctx->m1, ctx->m2, ctx->steps, ctx->adam_bias_table, ADAM_BIAS_TABLE, frozen, zero_grads,
-	                                    &xb, &z, ctx->sync_done);
-	ctx->barrier_fused = rc_ == 0;
+	                                    fuse_barrier ? &xb : nullptr, fuse_barrier ? &z : nullptr, ctx->sync_done);
+	if (!fuse_barrier) --ctx->barrier_epoch;   // neus2_peer_barrier launches the one-warp kernel with this epoch
+	ctx->barrier_fused = rc_ == 0 && fuse_barrier;
 	ctx->sharded_zeroed = rc_ == 0 && zero_grads;
-	ctx->barrier_zeroed = ctx->sharded_zeroed;
+	ctx->barrier_zeroed = ctx->sharded_zeroed && fuse_barrier;
 	if (rc_ == 0 && ctx->use_delta) CHECK(delta_optimizer_step(ctx, (cudaStream_t)stream, loss_scale));   // every rank steps its replica on the all-reduced sums
 	stage_end(ctx, ST_OPT, (cudaStream_t)stream);
 	ctx->optimizer_done = true;

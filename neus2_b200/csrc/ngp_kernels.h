@@ -34,7 +34,8 @@ int launch_adam_ema(cudaStream_t stream, uint64_t n, uint64_t n_matrix, float lo
 int launch_adam_bias_table(cudaStream_t stream, float beta1, float beta2, uint32_t first, uint32_t last, float* bias_table, uint32_t bias_table_size);
 
 #define NEUS2_MAX_PEERS 8
-void optimizer_shard(uint64_t n_quads, uint32_t rank, uint32_t world, uint64_t* q0, uint64_t* q1);
+#define OPTIMIZER_BLOCK_QUADS 256   // the sharded optimizer deals blocks of 256 quads (1024 parameters) round-robin over the ranks
+uint32_t optimizer_block_owner(uint64_t param_index, uint32_t world);
 // ---- cross-GPU ordering points of the data-parallel step over peer memory (peer_sync.cu) ----
 #define PEER_PAYLOAD_WORDS 20   // {kept rays, samples, compacted, 0 | loss sums 4 | DeltaNetwork gradient sums 12}
 struct PeerSlot { uint32_t payload[PEER_PAYLOAD_WORDS]; uint32_t pad[11]; uint32_t flag; };   // one 128-byte line; written by exactly one peer

@@ -137,7 +137,7 @@ int launch_adam_ema(cudaStream_t stream, uint64_t n, uint64_t n_matrix, float lo
 
 // ------------------------------------------------------------------------------------------------------------------------
 // Data-parallel optimizer step fused with its collective: instead of all-reduce(grads) followed by a replicated
-// Adam, rank r owns the contiguous quad range [q0, q1) of the parameters, SUMS the gradients of all ranks for that range
+// Adam, rank r owns every W-th block of 1024 parameters, SUMS the gradients of all ranks for its blocks
 // straight out of the peers' gradient buffers (NVLink/NVSwitch P2P loads, fixed rank order), runs Adam + EMA on it, and
 // stores the refreshed fp16 parameters and EMA values into every rank's buffers (P2P stores).  Optimizer state (fp32 master,
 // moments, step counters) is touched for 1/W of the parameters per GPU; no gradient ever round-trips through a reduced copy.
@@ -150,11 +150,12 @@ __device__ __forceinline__ void adam_ema_p2p_quad(uint64_t q, uint64_t n_matrix4
                                                   float* __restrict__ master, float* __restrict__ m1, float* __restrict__ m2, uint32_t* __restrict__ steps);
 
 __global__ void __launch_bounds__(256)
-k_adam_ema_p2p(uint64_t q0, uint64_t q1, uint64_t n_matrix4, AdamHyper h, int world, PeerPtrs peers,
+k_adam_ema_p2p(uint64_t n4, uint32_t rank, uint64_t n_matrix4, AdamHyper h, int world, PeerPtrs peers,
                float* __restrict__ master, float* __restrict__ m1, float* __restrict__ m2, uint32_t* __restrict__ steps,
                PeerXfer barrier, PeerZero zero, uint32_t* __restrict__ done_counter) {
-	const uint64_t q = q0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (q < q1) adam_ema_p2p_quad(q, n_matrix4, h, world, peers, master, m1, m2, steps);
+	// rank r owns the parameter blocks r, r + W, r + 2W, ... (OPTIMIZER_BLOCK_QUADS quads each): this CTA takes this rank's blockIdx-th block
+	const uint64_t q = ((uint64_t)blockIdx.x * (uint32_t)world + rank) * OPTIMIZER_BLOCK_QUADS + threadIdx.x;
+	if (q < n4) adam_ema_p2p_quad(q, n_matrix4, h, world, peers, master, m1, m2, steps);
 	if (barrier.world == 0) return;
 	// The barrier "every rank's slice is stored everywhere" rides in this kernel's LAST block (it owns its SM already: a kernel of its own
 	// would queue behind the next step's sample generation, which fills every SM the training kernel frees).  Peer stores of all blocks are
@@ -233,8 +234,6 @@ int launch_adam_ema_p2p(cudaStream_t stream, uint64_t n, uint64_t n_matrix, uint
 	if (n % 4 != 0 || n_matrix % 4 != 0) { neus_set_error("parameter counts must be multiples of 4", __FILE__, __LINE__); return -1; }
 	if (world < 1 || world > NEUS2_MAX_PEERS || rank >= world) { neus_set_error("bad rank / world size for the sharded optimizer", __FILE__, __LINE__); return -1; }
 	AdamHyper h = {loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, ema_debias_old, ema_debias_new, ema_step, bias_table, bias_table_size, frozen, zero_grads, exact_reciprocal(loss_scale)};
-	uint64_t q0, q1;
-	optimizer_shard(n / 4, rank, world, &q0, &q1);
 	PeerPtrs pp;
 	for (uint32_t r = 0; r < NEUS2_MAX_PEERS; ++r) { pp.grads[r] = nullptr; pp.params[r] = nullptr; pp.ema[r] = nullptr; }
 	// slot 0 = own buffers, then the peers in ascending rank order: the sum order is the same on every step
@@ -243,19 +242,16 @@ int launch_adam_ema_p2p(cudaStream_t stream, uint64_t n, uint64_t n_matrix, uint
 	for (uint32_t r = 0; r < world; ++r) if (r != rank) { pp.grads[slot] = grads_peers[r]; pp.params[slot] = params_peers[r]; pp.ema[slot] = ema_peers[r]; ++slot; }
 	PeerXfer xb = {}; PeerZero z = {};
 	if (barrier) { if (!done_counter) { neus_set_error("the fused barrier needs an arrival counter", __FILE__, __LINE__); return -1; } xb = *barrier; if (zero) z = *zero; }
-	if (q1 > q0 || barrier) {
-		const uint32_t blocks = q1 > q0 ? (uint32_t)((q1 - q0 + 255) / 256) : 1u;
-		k_adam_ema_p2p<<<blocks, 256, 0, stream>>>(q0, q1, n_matrix / 4, h, (int)world, pp, master, m1, m2, steps, xb, z, done_counter);
-		COUNT_LAUNCH(1);
-	}
+	const uint64_t n_blocks = (n / 4 + OPTIMIZER_BLOCK_QUADS - 1) / OPTIMIZER_BLOCK_QUADS;
+	const uint32_t blocks = (uint32_t)((n_blocks + world - 1) / world);   // the last one may fall past the end on some ranks: its threads do nothing
+	static_assert(OPTIMIZER_BLOCK_QUADS == 256, "one CTA of 256 threads per parameter block");
+	k_adam_ema_p2p<<<blocks, 256, 0, stream>>>(n / 4, rank, n_matrix / 4, h, (int)world, pp, master, m1, m2, steps, xb, z, done_counter);
+	COUNT_LAUNCH(1);
 	CUDA_CHECK(cudaGetLastError());
 	return 0;
 }
 
-// quads [q0, q1) of rank `rank`: contiguous, sizes differ by at most one quad
-void optimizer_shard(uint64_t n_quads, uint32_t rank, uint32_t world, uint64_t* q0, uint64_t* q1) {
-	const uint64_t base = n_quads / world, extra = n_quads % world;
-	*q0 = rank * base + (rank < extra ? rank : extra);
-	*q1 = *q0 + base + (rank < extra ? 1 : 0);
-}
-
+// Ownership of the sharded optimizer: parameter blocks of OPTIMIZER_BLOCK_QUADS quads (1024 parameters) are dealt round-robin, block b
+// belongs to rank b % world.  (Contiguous slices gave the rank holding the finest hash-grid levels -- touched by every sample -- up to 25 %
+// more Adam work than the rank holding the sparsely touched coarse hashed levels, and the barrier behind the optimizer waits for the slowest.)
+uint32_t optimizer_block_owner(uint64_t param_index, uint32_t world) { return (uint32_t)((param_index / (4ull * OPTIMIZER_BLOCK_QUADS)) % world); }

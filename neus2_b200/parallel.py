@@ -42,10 +42,19 @@ def sync_optimizer_state(ctx, rank, world_size, group=None):
         master = ctx.buffers()[0]
         m1, m2, steps, _ = ctx.optimizer_buffers()
         torch.cuda.synchronize(master.device)
-        for r in range(world_size):
-            b, e = ctx.optimizer_shard(r, world_size)
-            for buf in (master, m1, m2, steps):
-                dist.broadcast(buf[b:e], src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+        block, _ = ctx.optimizer_shard(rank, world_size)          # blocks of `block` parameters are dealt round-robin over the ranks
+        n = master.numel()
+        full = n // block
+        for buf in (master, m1, m2, steps):
+            body = buf[: full * block].view(full, block)
+            for r in range(world_size):
+                src = dist.get_global_rank(group, r) if group is not None else r
+                part = body[r::world_size].contiguous()
+                dist.broadcast(part, src=src, group=group)
+                body[r::world_size].copy_(part)
+            if n > full * block:                                  # the last, partial block
+                r = full % world_size
+                dist.broadcast(buf[full * block:], src=dist.get_global_rank(group, r) if group is not None else r, group=group)
         torch.cuda.synchronize(master.device)
     ctx._opt_synced_step = ctx.get_state()["optimizer_step"]
 
