@@ -255,3 +255,57 @@ def test_data_parallel_step_choreography(tmp_path):
         def train_step(self):
             return "one"
     assert parallel.train_step(_One(), 0, 1) == "one"
+
+
+class _FakeShardedCtx:
+    """CPU stand-in for a context whose sharded optimizer keeps only ITS parameter blocks current (blocks of `block` parameters dealt
+    round-robin over the ranks): everything this rank does not own holds a stale marker."""
+    peers_attached = True
+
+    def __init__(self, rank, world, n, block):
+        self.rank, self.world, self.block = rank, world, block
+        idx = torch.arange(n)
+        own = (idx // block) % world == rank
+        truth = idx.float() * 0.5 + 1.0
+        self.master = torch.where(own, truth, torch.full((n,), -1.0))
+        self.m1 = torch.where(own, truth * 2, torch.full((n,), -2.0))
+        self.m2 = torch.where(own, truth * 3, torch.full((n,), -3.0))
+        self.steps = torch.where(own, idx.int() + 7, torch.full((n,), -4, dtype=torch.int32))
+
+    def buffers(self):
+        return self.master, None, None, None
+
+    def optimizer_buffers(self):
+        return self.m1, self.m2, self.steps, 5
+
+    def optimizer_shard(self, rank, world):
+        return self.block, 0
+
+    def get_state(self):
+        return {"optimizer_step": 5}
+
+
+def _sync_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import unittest.mock as mock
+    n, block = 10 * 16 + 5, 16                       # ten full blocks and a partial one
+    ctx = _FakeShardedCtx(rank, world, n, block)
+    with mock.patch("torch.cuda.synchronize", lambda *a, **k: None):
+        parallel.sync_optimizer_state(ctx, rank, world)
+    torch.save(dict(master=ctx.master, m1=ctx.m1, m2=ctx.m2, steps=ctx.steps, synced=ctx._opt_synced_step), os.path.join(out_dir, f"s{rank}.pt"))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sync_optimizer_state_gathers_the_round_robin_blocks(tmp_path, world):
+    """parallel.sync_optimizer_state over gloo: every rank ends up with every block's owner's values (fp32 master, both moments, step
+    counters), including the last, partial block -- what snapshot.save / get_params need after a run with the sharded optimizer."""
+    mp.spawn(_sync_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    n = 10 * 16 + 5
+    idx = torch.arange(n)
+    truth = idx.float() * 0.5 + 1.0
+    for r in range(world):
+        got = torch.load(tmp_path / f"s{r}.pt")
+        assert torch.equal(got["master"], truth) and torch.equal(got["m1"], truth * 2) and torch.equal(got["m2"], truth * 3)
+        assert torch.equal(got["steps"], idx.int() + 7) and got["synced"] == 5
