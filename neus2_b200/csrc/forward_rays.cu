@@ -22,7 +22,7 @@
 static constexpr int FR_SMEM = WeightSmem::FWD_END * 2 + FR_WARPS * WarpSlab::FWD_END;
 
 #ifndef FR_SEGMENT
-#define FR_SEGMENT 64u   // samples per work item
+#define FR_SEGMENT 32u   // samples per work item (2 tiles; measured 16 / 32 / 48 / 64 / 128: see DESIGN.md)
 #endif
 
 __global__ void __launch_bounds__(FR_WARPS * 32, 2)
