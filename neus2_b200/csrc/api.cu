@@ -98,11 +98,6 @@ struct neus2_ctx {
 	// SM's register file) -- it overlaps the weight-gradient GEMMs and Adam.  The counters ping-pong between two buffers.
 	struct StepPlan { uint32_t R, n_local, ray_offset, ray_stride, max_inference, n_rays_total, training_step; uint64_t rng_state, rng_inc; };
 	cudaStream_t aux_stream;
-	cudaStream_t hp_stream;     // highest priority: the step's weight-gradient GEMMs and Adam run here in the pipelined single-GPU step, so that the
-	                            // block scheduler serves them before the next step's sample-generation blocks that share the GPU with them
-	cudaEvent_t ev_hp_done;
-	bool step_on_hp;            // the step in flight has its weight gradients (and will have its optimizer) on hp_stream
-	bool grid_adam_early;       // the step in flight already has the hash-grid part of its optimizer step running on hp_stream (beside the weight gradients)
 	cudaEvent_t ev_counts, ev_fwdbwd_done, ev_gen_done;
 	uint32_t* counters_buf[2]; int counters_cur;
 	bool prefetched; StepPlan prefetch_plan; uint64_t prefetch_epoch;
@@ -409,10 +404,7 @@ int neus2_ctx_create(const neus2_config* cfg, int device, neus2_ctx** out) {
 	CDM(ctx->n_windows, R); CDM(ctx->windows, sampling_window_bytes_per_ray() * (size_t)R); CDM(ctx->ray_setup, 12 * (size_t)R);
 	CDM(ctx->counters_buf[0], 12); CDM(ctx->counters_buf[1], 12);
 	ctx->counters = ctx->counters_buf[0]; ctx->counts_global = ctx->counters + 8;   // one 48-byte read-back per step covers both
-	int prio_least = 0, prio_greatest = 0;
-	cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
-	if (cudaStreamCreateWithPriority(&ctx->hp_stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_hp_done, cudaEventDisableTiming) != cudaSuccess ||
-	    cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_counts, cudaEventDisableTiming) != cudaSuccess ||
+	if (cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_counts, cudaEventDisableTiming) != cudaSuccess ||
 	    cudaEventCreateWithFlags(&ctx->ev_fwdbwd_done, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_gen_done, cudaEventDisableTiming) != cudaSuccess) {
 		neus2_ctx_destroy(ctx); FAIL("stream / event creation failed");
 	}
@@ -454,8 +446,7 @@ void neus2_ctx_destroy(neus2_ctx* ctx) {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
-	if (ctx->hp_stream) { cudaStreamSynchronize(ctx->hp_stream); cudaStreamDestroy(ctx->hp_stream); }
-	for (cudaEvent_t e : {ctx->ev_counts, ctx->ev_fwdbwd_done, ctx->ev_gen_done, ctx->ev_hp_done}) if (e) cudaEventDestroy(e);
+	for (cudaEvent_t e : {ctx->ev_counts, ctx->ev_fwdbwd_done, ctx->ev_gen_done}) if (e) cudaEventDestroy(e);
 	ctx->counters = nullptr;   // freed through counters_buf below
 	void* ptrs[] = {ctx->master, ctx->params, ctx->ema, ctx->grads, ctx->m1, ctx->m2, ctx->steps, ctx->adam_bias_table, ctx->d_pixels, ctx->d_focal, ctx->d_principal, ctx->d_xforms,
 		ctx->numsteps_all, ctx->base, ctx->slot, ctx->ray_indices, ctx->numsteps, ctx->scan_tmp, ctx->counters, ctx->n_windows, ctx->windows, ctx->ray_setup, ctx->rays, ctx->coords, ctx->ray_tmp,
@@ -624,12 +615,9 @@ int neus2_sdf(neus2_ctx* ctx, void* stream, const float* pos, uint32_t stride, u
 	return launch_network_sdf((cudaStream_t)stream, ctx->gm, ctx->pl, inference_or_training_params(ctx, use_inference_params), pos, stride, n, ctx->cfg.sdf_bias, as_density, (__half*)out, nullptr);
 }
 
-static int launch_optimizer_part(neus2_ctx* ctx, cudaStream_t stream, float loss_scale, uint32_t adam_step, int fuse_zero, int part);
 static int backward_on_stream(neus2_ctx* ctx, cudaStream_t stream, const float* coords, const void* dL_dout, const uint32_t* n_in_dev, uint32_t n_rows,
-                              uint32_t indeed_batch_size, bool grads_zeroed, bool wgrad_on_hp = false, int grid_adam_early = 0 /* 1: start it, 2: ... and it clears the gradients it consumes */,
-                              bool fuse_grads_exchange = false) {
+                              uint32_t indeed_batch_size, bool grads_zeroed, bool fuse_grads_exchange = false) {
 	if (n_rows > ctx->B_local) FAIL("n_rows exceeds the context's (local) batch size");
-	ctx->step_on_hp = wgrad_on_hp;
 	if (!grads_zeroed) {
 		CUDA_CHECK(cudaMemsetAsync(ctx->grads, 0, ctx->n_params * sizeof(float), stream));   // EGradientMode::Overwrite
 		CUDA_CHECK(cudaMemsetAsync(ctx->var_acc, 0, sizeof(float), stream));
@@ -646,15 +634,6 @@ static int backward_on_stream(neus2_ctx* ctx, cudaStream_t stream, const float* 
 	                            ctx->grads, ctx->var_acc, ctx->w1row0_acc, ctx->so, ctx->use_delta ? ctx->d_acc : nullptr, ctx->fwdbwd_done, fuse_grads_exchange ? &gx : nullptr));
 	stage_end(ctx, ST_FWDBWD, stream);
 	CUDA_CHECK(cudaEventRecord(ctx->ev_fwdbwd_done, stream));
-	if (grid_adam_early && !wgrad_on_hp) {
-		// The hash-grid gradients (99.9 % of the parameters) are complete; the MLP weight gradients still need the GEMMs below.  The grid part
-		// of THIS step's Adam + EMA starts now on the side stream and streams its 250 MB of optimizer state beside the GEMMs' 290 MB of staged
-		// operands; neus2_optimizer_step adds the MLP part behind the GEMMs and joins the streams.
-		CUDA_CHECK(cudaStreamWaitEvent(ctx->hp_stream, ctx->ev_fwdbwd_done, 0));
-		CHECK(launch_optimizer_part(ctx, ctx->hp_stream, ctx->cfg.loss_scale, ctx->adam_step + 1, grid_adam_early == 2, 1));
-		ctx->grid_adam_early = true;
-	}
-	if (wgrad_on_hp) { CUDA_CHECK(cudaStreamWaitEvent(ctx->hp_stream, ctx->ev_fwdbwd_done, 0)); stream = ctx->hp_stream; }
 	if (!weight_gradients_in_kernel()) {   // default: the training kernel has accumulated the MLP weight gradients itself (tensor memory)
 		stage_begin(ctx, ST_WGRAD, stream);
 		CHECK(launch_weight_gradients(stream, ctx->pl, ctx->so, ctx->params, n_in_dev, n_rows, ctx->partials, weight_gradient_partials(), ctx->var_acc, ctx->w1row0_acc, ctx->grads));
@@ -678,20 +657,6 @@ int neus2_backward(neus2_ctx* ctx, void* stream_, const float* coords, const voi
 	return backward_on_stream(ctx, (cudaStream_t)stream_, coords, dL_dout, n_in_dev, n_rows, indeed_batch_size, false);
 }
 
-// One launch of the fused Adam + EMA kernel for optimizer step `adam_step` (part: see launch_adam_ema)
-static int launch_optimizer_part(neus2_ctx* ctx, cudaStream_t stream, float loss_scale, uint32_t adam_step, int fuse_zero, int part) {
-	const neus2_config& c = ctx->cfg;
-	// inside a pipelined train step the kernel also clears what the next step starts from (consumed gradients, the small accumulators,
-	// this step's counters): no zero-fill launches are left between the optimizer and the next step's first kernel.  The small arrays are
-	// still read by the weight-gradient kernels, so only the launch that follows those (part 0 or 2) clears them.
-	uint32_t* const zp[3] = {(uint32_t*)ctx->var_acc, (uint32_t*)ctx->w1row0_acc, ctx->counters};
-	const uint32_t zn[3] = {1u, 64u, 8u};
-	const float lr = ctx->learning_rate * neus2_learning_rate_factor(&c, adam_step - 1);   // x 1.0f before decay_start: the same float
-	return launch_adam_ema(stream, ctx->n_params, ctx->pl.off_grid, loss_scale, lr, c.beta1, c.beta2, c.epsilon, c.l2_reg,
-	                       c.ema_decay, adam_step, ctx->grads, ctx->master, ctx->params, ctx->m1, ctx->m2, ctx->steps, ctx->ema, ctx->adam_bias_table, ADAM_BIAS_TABLE, 0,
-	                       fuse_zero, part == 1 ? nullptr : zp, zn, part);
-}
-
 int neus2_optimizer_step(neus2_ctx* ctx, void* stream, float loss_scale) {
 	CUDA_CHECK(cudaSetDevice(ctx->device));
 	stage_begin(ctx, ST_OPT, (cudaStream_t)stream);
@@ -705,17 +670,16 @@ int neus2_optimizer_step(neus2_ctx* ctx, void* stream, float loss_scale) {
 		return rc_f;
 	}
 	++ctx->adam_step;
+	const neus2_config& c = ctx->cfg;
+	// inside a pipelined train step the kernel also clears what the next step starts from (consumed gradients, the small accumulators,
+	// this step's counters): no zero-fill launches are left between the optimizer and the next step's first kernel
 	const int fuse = ctx->fuse_zero_into_adam ? 1 : 0;
-	int rc_;
-	if (ctx->grid_adam_early) {
-		// the hash-grid part has been running on hp_stream since the training kernel finished; the MLP weights + variance follow the
-		// weight-gradient kernels here, then the caller's stream joins the side stream
-		ctx->grid_adam_early = false;
-		rc_ = launch_optimizer_part(ctx, (cudaStream_t)stream, loss_scale, ctx->adam_step, fuse, 2);
-		if (rc_ == 0) { CUDA_CHECK(cudaEventRecord(ctx->ev_hp_done, ctx->hp_stream)); CUDA_CHECK(cudaStreamWaitEvent((cudaStream_t)stream, ctx->ev_hp_done, 0)); }
-	} else {
-		rc_ = launch_optimizer_part(ctx, (cudaStream_t)stream, loss_scale, ctx->adam_step, fuse, 0);
-	}
+	uint32_t* const zp[3] = {(uint32_t*)ctx->var_acc, (uint32_t*)ctx->w1row0_acc, ctx->counters};
+	const uint32_t zn[3] = {1u, 64u, 8u};
+	const float lr = ctx->learning_rate * neus2_learning_rate_factor(&c, ctx->adam_step - 1);   // x 1.0f before decay_start: the same float
+	const int rc_ = launch_adam_ema((cudaStream_t)stream, ctx->n_params, ctx->pl.off_grid, loss_scale, lr, c.beta1, c.beta2, c.epsilon, c.l2_reg,
+	                                c.ema_decay, ctx->adam_step, ctx->grads, ctx->master, ctx->params, ctx->m1, ctx->m2, ctx->steps, ctx->ema, ctx->adam_bias_table, ADAM_BIAS_TABLE,
+	                                fuse, zp, zn);
 	if (rc_ == 0 && ctx->use_delta) CHECK(delta_optimizer_step(ctx, (cudaStream_t)stream, loss_scale));   // m_global_move.trainer->optimizer_step (testbed_nerf.cu:3506-3508)
 	stage_end(ctx, ST_OPT, (cudaStream_t)stream);
 	return rc_;
@@ -920,21 +884,8 @@ int neus2_train_step_begin(neus2_ctx* ctx, void* stream_, uint32_t rank, uint32_
 	} else if (ctx->training_step % 16 == 0) {
 		CHECK(reduce_loss_scalars(ctx, stream));   // read back by neus2_train_step_counts_ready / neus2_train_step_end, after the caller's all-reduce
 	}
-	// NEUS2_HP_STREAM=1 moves weight gradients + Adam to a highest-priority stream so that the block scheduler serves them before the
-	// prefetched sample generation.  Measured (B200, same box, 2 runs each): weight gradients 0.122 -> 0.111 ms, but the two extra
-	// cross-stream hops and the slower generation cost more: 0.9316 -> 0.9397 ms per step.  Off by default.
-	static int hp_mode = -1;
-	if (hp_mode < 0) { const char* e = getenv("NEUS2_HP_STREAM"); hp_mode = e ? atoi(e) : 0; }
-	// NEUS2_SPLIT_ADAM=1 (single-GPU pipelined step): the hash-grid part of the optimizer step starts right behind the training kernel, beside
-	// the weight-gradient GEMMs.  Negative result, off by default: both are HBM streams (290 MB of staged operands, 320 MB of optimizer
-	// state) and together they take exactly as long as one after the other -- weight gradients 0.123 -> 0.208 ms with the 0.087 ms
-	// optimizer inside, step 0.932 -> 0.949 ms (profiles/r02_bench_n1_split_adam.json / _nosplit.json).  The bytes have to go, not overlap.
-	static int split = -1, no_fused_zero_b = -1;
-	if (split < 0) { const char* e = getenv("NEUS2_SPLIT_ADAM"); split = e ? atoi(e) : 0; }
-	if (no_fused_zero_b < 0) { const char* e = getenv("NEUS2_NO_FUSED_ZERO"); no_fused_zero_b = e ? atoi(e) : 0; }
-	const int early = (pipelined && world_size == 1 && split && !hp_mode && !canonical_frozen(ctx)) ? (no_fused_zero_b ? 1 : 2) : 0;
 	CHECK(backward_on_stream(ctx, stream, ctx->coords_compacted, ctx->dloss, ctx->counters + 2, rows_local, ctx->B, /*grads_zeroed=*/pre_zeroed,
-	                         /*wgrad_on_hp=*/pipelined && hp_mode, early, /*fuse_grads_exchange=*/peers && pipelined && weight_gradients_in_kernel()));   // :3941-3946
+	                         /*fuse_grads_exchange=*/peers && pipelined && weight_gradients_in_kernel()));   // :3941-3946
 	if (!pipelined) CUDA_CHECK(cudaMemcpyAsync(ctx->counts_global, ctx->counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
 	return 0;
 }
@@ -992,14 +943,9 @@ int neus2_train_step_end(neus2_ctx* ctx, void* stream_, const uint32_t* counts_g
 	ctx->sharded_zeroed = ctx->barrier_zeroed = false;
 	if (!ctx->optimizer_done) {
 		ctx->fuse_zero_into_adam = fused_zero;
-		const int rc_opt = neus2_optimizer_step(ctx, ctx->step_on_hp ? (void*)ctx->hp_stream : stream_, c.loss_scale);   // testbed_nerf.cu:3503-3505
+		const int rc_opt = neus2_optimizer_step(ctx, stream_, c.loss_scale);   // testbed_nerf.cu:3503-3505
 		ctx->fuse_zero_into_adam = false;
 		CHECK(rc_opt);
-	}
-	if (ctx->step_on_hp) {   // everything later on the caller's stream follows the weight gradients + optimizer
-		CUDA_CHECK(cudaEventRecord(ctx->ev_hp_done, ctx->hp_stream));
-		CUDA_CHECK(cudaStreamWaitEvent(stream, ctx->ev_hp_done, 0));
-		ctx->step_on_hp = false;
 	}
 	ctx->optimizer_done = false;
 	if (!pipelined) {
@@ -1331,7 +1277,6 @@ int neus2_optimizer_step_sharded(neus2_ctx* ctx, void* stream, float loss_scale)
 		return rc_f;
 	}
 	++ctx->adam_step;
-	const int frozen = 0;
 	const float lr = ctx->learning_rate * neus2_learning_rate_factor(&c, ctx->adam_step - 1);
 	// inside a pipelined data-parallel step (neus2_train_step_counts_ready has been called) the kernel also clears the gradient quads it
 	// consumed, on every rank: with the peer barrier's small zero-fills no memset is left between the optimizer and the next step
@@ -1349,7 +1294,7 @@ int neus2_optimizer_step_sharded(neus2_ctx* ctx, void* stream, float loss_scale)
 	PeerZero z = {};
 	if (zero_grads) { z.p[0] = (uint32_t*)ctx->var_acc; z.n[0] = 1u; z.p[1] = (uint32_t*)ctx->w1row0_acc; z.n[1] = 64u; z.p[2] = ctx->counters; z.n[2] = 8u; }
 	const int rc_ = launch_adam_ema_p2p((cudaStream_t)stream, ctx->n_params, ctx->pl.off_grid, ctx->peer_rank, ctx->peer_world, loss_scale, lr, c.beta1, c.beta2,
-	                                    c.epsilon, c.l2_reg, c.ema_decay, ctx->adam_step, ctx->peer_grads, ctx->peer_params, ctx->peer_ema, ctx->master, ctx->m1, ctx->m2, ctx->steps, ctx->adam_bias_table, ADAM_BIAS_TABLE, frozen, zero_grads,
+	                                    c.epsilon, c.l2_reg, c.ema_decay, ctx->adam_step, ctx->peer_grads, ctx->peer_params, ctx->peer_ema, ctx->master, ctx->m1, ctx->m2, ctx->steps, ctx->adam_bias_table, ADAM_BIAS_TABLE, zero_grads,
 	                                    fuse_barrier ? &xb : nullptr, fuse_barrier ? &z : nullptr, ctx->sync_done);
 	if (!fuse_barrier) --ctx->barrier_epoch;   // neus2_peer_barrier launches the one-warp kernel with this epoch
 	ctx->barrier_fused = rc_ == 0 && fuse_barrier;

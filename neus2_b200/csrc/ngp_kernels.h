@@ -28,8 +28,7 @@ int launch_compute_loss(cudaStream_t stream, uint32_t n_rays_local, uint32_t n_r
 
 int launch_adam_ema(cudaStream_t stream, uint64_t n, uint64_t n_matrix, float loss_scale, float lr, float beta1, float beta2, float eps, float l2_reg,
                     float ema_decay, uint32_t ema_step, float* grads, float* master, __half* params, float* m1, float* m2, uint32_t* steps, __half* ema,
-                    float* bias_table, uint32_t bias_table_size, int frozen, int zero_grads, uint32_t* const zero_ptrs[3], const uint32_t zero_counts[3],
-                    int part = 0 /* 0 all parameters, 1 hash grid only, 2 MLP weights + variance only */);
+                    float* bias_table, uint32_t bias_table_size, int zero_grads, uint32_t* const zero_ptrs[3], const uint32_t zero_counts[3]);
 // table[k] = sqrt(1 - beta2^k) / (1 - beta1^k) for k in [first, last] (api.cu: compiled with FMA contraction like the reference's adam_step)
 int launch_adam_bias_table(cudaStream_t stream, float beta1, float beta2, uint32_t first, uint32_t last, float* bias_table, uint32_t bias_table_size);
 
@@ -49,7 +48,7 @@ int launch_peer_barrier(cudaStream_t stream, const PeerXfer& x, const PeerZero& 
 // zero_grads: every gradient quad this rank consumed (its slice of EVERY rank's buffer) is cleared through the same peer mapping, touched quads only
 int launch_adam_ema_p2p(cudaStream_t stream, uint64_t n, uint64_t n_matrix, uint32_t rank, uint32_t world, float loss_scale, float lr, float beta1, float beta2,
                         float eps, float l2_reg, float ema_decay, uint32_t ema_step, float* const* grads_peers, __half* const* params_peers,
-                        __half* const* ema_peers, float* master, float* m1, float* m2, uint32_t* steps, float* bias_table, uint32_t bias_table_size, int frozen, int zero_grads,
+                        __half* const* ema_peers, float* master, float* m1, float* m2, uint32_t* steps, float* bias_table, uint32_t bias_table_size, int zero_grads,
                         const PeerXfer* barrier = nullptr /* the kernel's last block runs this barrier over the peers and then clears `zero` */, const PeerZero* zero = nullptr,
                         uint32_t* done_counter = nullptr);
 

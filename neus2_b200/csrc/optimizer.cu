@@ -12,7 +12,6 @@
 
 struct AdamHyper { float loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, ema_debias_old, ema_debias_new;
                    uint32_t cur_step; const float* bias_table; uint32_t bias_table_size;
-                   int frozen;      // frozen: optimize_canonical_params = false (adam.h:92-94) -- every parameter returns early, only the EMA moves
                    int zero_grads;   // also clear the gradients that were consumed (the next step starts from zeros; only touched quads are rewritten)
                    float inv_loss_scale; };   // 1 / loss_scale when loss_scale is a power of two (the division is then an exact scaling: same bits, no IEEE divide), else 0
 // Small accumulators of the step that the next step expects cleared (variance / W1-row-0 sums, the step's counters): block 0 clears them.
@@ -57,28 +56,23 @@ static float exact_reciprocal(float x) {
 
 // 4 consecutive parameters per thread (n and n_matrix are multiples of 4): 16-byte gradient loads; the optimizer state of an
 // untouched quad (the common case for the sparse hash-grid levels) is never read.
-// The launch covers the quads [q_begin, q_end) plus, if q_extra is a valid quad, that one (the variance quad behind the hash grid when
-// the launch covers the MLP weights only: the step then runs as two concurrent launches, see launch_adam_ema).
 __global__ void __launch_bounds__(256)
-k_adam_ema(uint64_t q_begin, uint64_t q_end, uint64_t q_extra, uint64_t n_matrix4, AdamHyper h, float* __restrict__ grads,
+k_adam_ema(uint64_t n4, uint64_t n_matrix4, AdamHyper h, float* __restrict__ grads,
            float* __restrict__ master, __half* __restrict__ params, float* __restrict__ m1, float* __restrict__ m2,
            uint32_t* __restrict__ steps, __half* __restrict__ ema, AdamZero z) {
 	if (h.zero_grads && blockIdx.x == 0) {
 		#pragma unroll
 		for (int a = 0; a < 3; ++a) for (uint32_t i = threadIdx.x; i < z.n[a]; i += blockDim.x) z.p[a][i] = 0u;
 	}
-	uint64_t q = q_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (q >= q_end) {
-		if (q != q_end || q_extra == ~0ull) return;
-		q = q_extra;
-	}
+	const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= n4) return;
 	const bool is_matrix = q < n_matrix4;
 	const float4 g4 = reinterpret_cast<const float4*>(grads)[q];
 	if (h.zero_grads && (g4.x != 0.f || g4.y != 0.f || g4.z != 0.f || g4.w != 0.f)) reinterpret_cast<float4*>(grads)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
 	uint2 pw = reinterpret_cast<const uint2*>(params)[q];
 	__half* ph = reinterpret_cast<__half*>(&pw);
 	const float g[4] = {g4.x, g4.y, g4.z, g4.w};
-	if (!h.frozen && (is_matrix || g4.x != 0.f || g4.y != 0.f || g4.z != 0.f || g4.w != 0.f)) {
+	if ((is_matrix || g4.x != 0.f || g4.y != 0.f || g4.z != 0.f || g4.w != 0.f)) {
 		float4 w4 = reinterpret_cast<const float4*>(master)[q];
 		float4 a4 = reinterpret_cast<const float4*>(m1)[q];
 		float4 b4 = reinterpret_cast<const float4*>(m2)[q];
@@ -112,24 +106,16 @@ k_adam_ema(uint64_t q_begin, uint64_t q_end, uint64_t q_extra, uint64_t n_matrix
 
 int launch_adam_ema(cudaStream_t stream, uint64_t n, uint64_t n_matrix, float loss_scale, float lr, float beta1, float beta2, float eps, float l2_reg,
                     float ema_decay, uint32_t ema_step, float* grads, float* master, __half* params, float* m1, float* m2, uint32_t* steps, __half* ema,
-                    float* bias_table, uint32_t bias_table_size, int frozen, int zero_grads, uint32_t* const zero_ptrs[3], const uint32_t zero_counts[3], int part) {
+                    float* bias_table, uint32_t bias_table_size, int zero_grads, uint32_t* const zero_ptrs[3], const uint32_t zero_counts[3]) {
 	const float ema_debias_old = 1 - (float)pow((double)ema_decay, (double)(ema_step - 1));
 	const float ema_debias_new = 1.0f / (1 - (float)pow((double)ema_decay, (double)ema_step));
 	if (n % 4 != 0 || n_matrix % 4 != 0) { neus_set_error("parameter counts must be multiples of 4", __FILE__, __LINE__); return -1; }
-	AdamHyper h = {loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, ema_debias_old, ema_debias_new, ema_step, bias_table, bias_table_size, frozen, zero_grads, exact_reciprocal(loss_scale)};
+	AdamHyper h = {loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, ema_debias_old, ema_debias_new, ema_step, bias_table, bias_table_size, zero_grads, exact_reciprocal(loss_scale)};
 	AdamZero z = {};
 	if (zero_grads) for (int a = 0; a < 3; ++a) { z.p[a] = zero_ptrs ? zero_ptrs[a] : nullptr; z.n[a] = (zero_ptrs && zero_ptrs[a]) ? zero_counts[a] : 0u; }
-	// part 0: everything.  part 1: the hash grid (all non-matrix parameters but the last quad).  part 2: the MLP weights + the last quad
-	// (variance).  Parts 1 and 2 touch disjoint parameters: the grid part only needs the training kernel's atomics, so it can run beside
-	// the weight-gradient GEMMs that part 2 waits for.
-	const uint64_t n4 = n / 4, nm4 = n_matrix / 4;
-	uint64_t q_begin = 0, q_end = n4, q_extra = ~0ull;
-	if (part == 1) { q_begin = nm4; q_end = n4 - 1; }
-	else if (part == 2) { q_begin = 0; q_end = nm4; q_extra = n4 - 1; }
-	if (part != 0 && (nm4 == 0 || nm4 >= n4 - 1)) { neus_set_error("split optimizer step needs matrix parameters, grid parameters and a trailing quad", __FILE__, __LINE__); return -1; }
-	const uint64_t count = q_end - q_begin + (q_extra != ~0ull ? 1 : 0);
-	const uint32_t blocks = (uint32_t)((count + 255) / 256);
-	k_adam_ema<<<blocks, 256, 0, stream>>>(q_begin, q_end, q_extra, nm4, h, grads, master, params, m1, m2, steps, ema, z);
+	const uint64_t n4 = n / 4;
+	const uint32_t blocks = (uint32_t)((n4 + 255) / 256);
+	k_adam_ema<<<blocks, 256, 0, stream>>>(n4, n_matrix / 4, h, grads, master, params, m1, m2, steps, ema, z);
 	COUNT_LAUNCH(1);
 	CUDA_CHECK(cudaGetLastError());
 	return 0;
@@ -191,7 +177,7 @@ __device__ __forceinline__ void adam_ema_p2p_quad(uint64_t q, uint64_t n_matrix4
 	uint2 pw = reinterpret_cast<const uint2*>(peers.params[0])[q];     // slot 0 is always this rank's own buffer
 	__half* ph = reinterpret_cast<__half*>(&pw);
 	const float g[4] = {g4.x, g4.y, g4.z, g4.w};
-	if (!h.frozen && (is_matrix || g4.x != 0.f || g4.y != 0.f || g4.z != 0.f || g4.w != 0.f)) {
+	if ((is_matrix || g4.x != 0.f || g4.y != 0.f || g4.z != 0.f || g4.w != 0.f)) {
 		float4 w4 = reinterpret_cast<const float4*>(master)[q];
 		float4 a4 = reinterpret_cast<const float4*>(m1)[q];
 		float4 b4 = reinterpret_cast<const float4*>(m2)[q];
@@ -227,13 +213,13 @@ __device__ __forceinline__ void adam_ema_p2p_quad(uint64_t q, uint64_t n_matrix4
 
 int launch_adam_ema_p2p(cudaStream_t stream, uint64_t n, uint64_t n_matrix, uint32_t rank, uint32_t world, float loss_scale, float lr, float beta1, float beta2,
                         float eps, float l2_reg, float ema_decay, uint32_t ema_step, float* const* grads_peers, __half* const* params_peers,
-                        __half* const* ema_peers, float* master, float* m1, float* m2, uint32_t* steps, float* bias_table, uint32_t bias_table_size, int frozen, int zero_grads,
+                        __half* const* ema_peers, float* master, float* m1, float* m2, uint32_t* steps, float* bias_table, uint32_t bias_table_size, int zero_grads,
                         const PeerXfer* barrier, const PeerZero* zero, uint32_t* done_counter) {
 	const float ema_debias_old = 1 - (float)pow((double)ema_decay, (double)(ema_step - 1));
 	const float ema_debias_new = 1.0f / (1 - (float)pow((double)ema_decay, (double)ema_step));
 	if (n % 4 != 0 || n_matrix % 4 != 0) { neus_set_error("parameter counts must be multiples of 4", __FILE__, __LINE__); return -1; }
 	if (world < 1 || world > NEUS2_MAX_PEERS || rank >= world) { neus_set_error("bad rank / world size for the sharded optimizer", __FILE__, __LINE__); return -1; }
-	AdamHyper h = {loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, ema_debias_old, ema_debias_new, ema_step, bias_table, bias_table_size, frozen, zero_grads, exact_reciprocal(loss_scale)};
+	AdamHyper h = {loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, ema_debias_old, ema_debias_new, ema_step, bias_table, bias_table_size, zero_grads, exact_reciprocal(loss_scale)};
 	PeerPtrs pp;
 	for (uint32_t r = 0; r < NEUS2_MAX_PEERS; ++r) { pp.grads[r] = nullptr; pp.params[r] = nullptr; pp.ema[r] = nullptr; }
 	// slot 0 = own buffers, then the peers in ascending rank order: the sum order is the same on every step
