@@ -292,7 +292,7 @@ def main():
     launches0 = ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     rays = 0
-    n_u = n_c = 0
+    n_u = n_c = n_fp = 0
     t_wall0 = time.perf_counter()
     with ClockSampler(local_rank) as clocks:
         e0.record(stream)
@@ -301,6 +301,7 @@ def main():
             rays += st.rays_per_batch
             n_u += st.measured_batch_size_before_compaction
             n_c += st.measured_batch_size
+            n_fp += st.first_pass_samples
         e1.record(stream)
         torch.cuda.synchronize()
         t_wall = time.perf_counter() - t_wall0
@@ -351,7 +352,7 @@ def main():
         try:
             with open(os.path.join(ROOT, "profiles", "r01_l2_microbench.json")) as f:
                 mb = json.load(f)
-            gathers_fwd = (n_u / K) * 14 * 8
+            gathers_fwd = (n_fp / K) * 14 * 8      # samples the first pass actually evaluated (it stops where the loss stops), not all marched samples
             gathers_bwd, reds_bwd = rows * 14 * 8, rows * 14 * 8
             floor_bwd_ms = (gathers_bwd / mb["gather4B_hash_corners_Gops"] + reds_bwd / mb["red_v2f32_random_Gops"]) * 1e-6
             l2 = {"forward_gather_Gops": gathers_fwd / (stages["forward"][0] * 1e6), "gather_ceiling_Gops": mb["gather4B_hash_corners_Gops"],
@@ -373,7 +374,7 @@ def main():
                          "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes, "avg_launch_ms": dom_ms, "l2": l2},
             "stage_ms": {k: round(v[0], 4) for k, v in stages.items()},
             **({"stage_ms_per_rank": stages_all} if stages_all else {}),
-            "per_step": {"rays": rays / K, "samples_before_compaction": n_u / K, "samples_compacted": n_c / K, "batch_fill": fill, "training_step": int(st.training_step),
+            "per_step": {"rays": rays / K, "samples_before_compaction": n_u / K, "samples_compacted": n_c / K, "first_pass_samples_evaluated": n_fp / K, "batch_fill": fill, "training_step": int(st.training_step),
                          "first_pass_samples_evaluated_last_step": int(st.first_pass_samples)},
         }
         if not args.no_cpu_baseline and world == 1:      # reported on rank 0 at N = 1 only
