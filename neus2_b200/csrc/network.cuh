@@ -63,6 +63,9 @@ struct WarpSlab {
 };
 static_assert(WarpSlab::OUT % 16 == 0 && WarpSlab::DX % 16 == 0 && WarpSlab::DI % 16 == 0 && WarpSlab::BWD_END % 16 == 0 && WarpSlab::DELTA_END % 16 == 0, "slab alignment");
 
+#ifndef NEUS2_STAGE_WEIGHTS_TMA
+#define NEUS2_STAGE_WEIGHTS_TMA 1
+#endif
 __device__ __forceinline__ void stage_matrix(__half* dst, int ld_dst, const __half* __restrict__ src, int rows, int cols, int tid, int nthreads) {
 	for (int i = tid; i < rows * cols; i += nthreads) {
 		int r = i / cols, c = i - r * cols;
@@ -70,13 +73,48 @@ __device__ __forceinline__ void stage_matrix(__half* dst, int ld_dst, const __ha
 	}
 }
 
+// All five weight matrices: global -> shared memory with the bulk-copy engine (TMA, cp.async.bulk), one copy per (padded) row, issued by
+// the first warp and completed on an mbarrier that every thread of the CTA then waits for.  224 row copies of 64..128 bytes replace 11,264
+// scalar load/store pairs per CTA; rows and their destinations are 16-byte aligned by construction (row strides 80 / 112 / 144 bytes).
+// Must be called by ALL threads of the CTA, once, before the first use of `sw`; contains the block-wide synchronisation.
 __device__ __forceinline__ void stage_weights(__half* sw, const __half* __restrict__ params, const ParamLayout& pl, bool train, int tid, int nthreads) {
+	(void)train;
+#if !NEUS2_STAGE_WEIGHTS_TMA   // A/B switch: the thread-copy variant this replaced
 	stage_matrix(sw + WeightSmem::W0, LD_X0, params + pl.off_w0, 64, SDF_IN, tid, nthreads);
 	stage_matrix(sw + WeightSmem::W1, LD_H, params + pl.off_w1, 16, 64, tid, nthreads);
 	stage_matrix(sw + WeightSmem::C0, LD_C0, params + pl.off_c0, 64, RGB_IN, tid, nthreads);
 	stage_matrix(sw + WeightSmem::C1, LD_H, params + pl.off_c1, 64, 64, tid, nthreads);
 	stage_matrix(sw + WeightSmem::C2, LD_H, params + pl.off_c2, 16, 64, tid, nthreads);
-	(void)train;
+	return;   // every caller synchronises the block behind this call
+#endif
+	(void)nthreads;
+	__shared__ __align__(8) uint64_t bar;
+	const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(&bar);
+	if (tid == 0) {
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_addr));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	if (tid < 32) {
+		constexpr uint32_t total_bytes = (64 * SDF_IN + 16 * 64 + 64 * RGB_IN + 64 * 64 + 16 * 64) * 2;
+		if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_addr), "r"(total_bytes) : "memory");
+		__syncwarp();
+		// (matrix, row) pairs in one list: W0 64 rows, W1 16, C0 64, C1 64, C2 16 = 224 rows, 7 per lane
+		for (int i = tid; i < 224; i += 32) {
+			int r = i, dst_off, ld, cols; uint32_t src_off;
+			if (r < 64) { dst_off = WeightSmem::W0; ld = LD_X0; cols = SDF_IN; src_off = pl.off_w0; }
+			else if ((r -= 64) < 16) { dst_off = WeightSmem::W1; ld = LD_H; cols = 64; src_off = pl.off_w1; }
+			else if ((r -= 16) < 64) { dst_off = WeightSmem::C0; ld = LD_C0; cols = RGB_IN; src_off = pl.off_c0; }
+			else if ((r -= 64) < 64) { dst_off = WeightSmem::C1; ld = LD_H; cols = 64; src_off = pl.off_c1; }
+			else { r -= 64; dst_off = WeightSmem::C2; ld = LD_H; cols = 64; src_off = pl.off_c2; }
+			const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sw + dst_off + r * ld);
+			const __half* src = params + src_off + (size_t)r * cols;
+			asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+			             :: "r"(dst), "l"(src), "r"((uint32_t)(cols * 2)), "r"(bar_addr) : "memory");
+		}
+	}
+	uint32_t done = 0;
+	while (!done) asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(bar_addr) : "memory");
 }
 
 // ---- fragment helpers ------------------------------------------------------------------------------
