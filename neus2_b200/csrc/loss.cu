@@ -5,6 +5,7 @@
 // The reference's atomicAdd compaction (:1682) becomes an exclusive scan in ray-slot order (deterministic).
 #include "ngp_common.cuh"
 #include "ngp_kernels.h"
+#include "lookback.cuh"
 
 __device__ __forceinline__ void ray_dir_for_loss(const float* __restrict__ ray, const GlobalMove& gmv, float ray_o[3], float dir[3]) {
 	ray_o[0] = ray[0]; ray_o[1] = ray[1]; ray_o[2] = ray[2];
@@ -95,6 +96,126 @@ k_scan_compacted(const uint32_t* __restrict__ n_ptr, const uint32_t* __restrict_
 	for (uint32_t i = b; i < e; ++i) { base[i] = off; off += counts[i]; }
 }
 
+// ---- pieces shared by the two-kernel path (k_loss_composite / k_loss_gradient) and the fused kernel (k_loss_fused) ----
+// What the ray is compared against (:1629-1676): the training pixel under the ray, composited over the (random) background, in sRGB.
+struct RayTarget { float rgbtarget[3]; float bg[3]; float mask_gt; };
+__device__ __forceinline__ RayTarget ray_target(uint32_t ray_idx, uint32_t n_rays, uint32_t n_rays_total, Pcg32 rng, const DatasetDev& ds, const LossParamsDev& lp) {
+	RayTarget t;
+	rng.advance((int64_t)(uint32_t)(ray_idx * N_MAX_RANDOM_SAMPLES_PER_RAY));
+	const uint32_t img = image_idx(ray_idx, n_rays, n_rays_total, ds.n_images);
+	float xy[2];
+	random_image_pos_training(rng, ds.width, ds.height, lp.snap_to_pixel_centers != 0, xy);
+	t.bg[0] = lp.background_color[0]; t.bg[1] = lp.background_color[1]; t.bg[2] = lp.background_color[2];
+	if (lp.random_bg_color) { t.bg[0] = rng.next_float(); t.bg[1] = rng.next_float(); t.bg[2] = rng.next_float(); }
+	#pragma unroll
+	for (int k = 0; k < 3; ++k) t.bg[k] = srgb_to_linear(t.bg[k]);
+	int px, py; image_pos(xy, ds.width, ds.height, &px, &py);
+	float tex[4]; read_rgba(ds, img, px, py, tex);
+	#pragma unroll
+	for (int k = 0; k < 3; ++k) {
+		const float exposure_scale = expf(0.6931471805599453f * 0.0f);
+		t.rgbtarget[k] = exposure_scale * tex[k] + (1.0f - tex[3]) * t.bg[k];
+		t.rgbtarget[k] = linear_to_srgb(t.rgbtarget[k]);
+		t.bg[k] = linear_to_srgb(t.bg[k]);
+	}
+	t.mask_gt = (float)(tex[3] > 0.9999);
+	return t;
+}
+
+// Per-ray scalars of pass 2 (:1690-1760): Huber loss and its gradient per channel, the mask term's gradient through the weight sum.
+struct RayLoss { float rgb_ray[3]; float lg_grad[3]; float gradient_weight_sum, weight_sum, mean_loss, mask_loss; };
+__device__ __forceinline__ RayLoss ray_loss(const float rgb_ray[3], float weight_sum, const RayTarget& t, const LossParamsDev& lp) {
+	RayLoss r;
+	float lg_loss[3];
+	#pragma unroll
+	for (int k = 0; k < 3; ++k) {
+		const float alpha_h = 0.1f;
+		const float difference = rgb_ray[k] - t.rgbtarget[k];
+		const float abs_diff = fabsf(difference);
+		const float square = 0.5f / alpha_h * difference * difference;
+		lg_loss[k] = (abs_diff > alpha_h ? (abs_diff - 0.5f * alpha_h) : square) / 5.0f;
+		r.lg_grad[k] = (abs_diff > alpha_h ? (difference > 0 ? 1.0f : -1.0f) : (difference / alpha_h)) / 5.0f;
+		r.rgb_ray[k] = rgb_ray[k];
+	}
+	if (weight_sum >= 1.0 - 1e-4) { weight_sum = (float)(1.0 - 1e-4); r.gradient_weight_sum = 0.0f; }
+	else if (weight_sum <= 1e-4) { weight_sum = (float)1e-4; r.gradient_weight_sum = 0.0f; }
+	else {
+		const float sigmoid_weight_sum = 1.0f / (1.0f + expf(-weight_sum));
+		r.gradient_weight_sum = (t.mask_gt - sigmoid_weight_sum) * weight_sum * lp.mask_loss_weight;
+	}
+	r.weight_sum = weight_sum;
+	r.mean_loss = (lg_loss[0] + lg_loss[1] + lg_loss[2]) / 3.0f;
+	r.mask_loss = -(t.mask_gt * logf(weight_sum) + (1 - t.mask_gt) * logf(1 - weight_sum));
+	return r;
+}
+
+// dL/d(network output) of ONE sample (:1800-1957) from its evaluation `e`, its compositing weight, the transmittance right behind it (Tj)
+// and the colour accumulated up to and including it (my_r2); `o` is the sample's raw output row (the three colour logits are read again).
+// Writes the 16-half row; returns the sample's eikonal term (|grad sdf| - 1)^2.
+__device__ __forceinline__ float sample_gradient(const SampleEval& e, const __half* __restrict__ o, float weight, float Tj, const float my_r2[3], const RayLoss& rl,
+                                                 const float dir[3], const LossParamsDev& lp, float loss_scale, __half* __restrict__ dout_row) {
+	float suffix[3], dloss_by_drgb[3];
+	#pragma unroll
+	for (int k = 0; k < 3; ++k) { suffix[k] = rl.rgb_ray[k] - my_r2[k]; dloss_by_drgb[k] = weight * rl.lg_grad[k]; }
+	float local[16];
+	#pragma unroll
+	for (int k = 0; k < 16; ++k) local[k] = 0.f;
+	#pragma unroll
+	for (int k = 0; k < 3; ++k) {
+		const float ov = __half2float(o[k]);
+		const float density = logistic_f(ov);
+		const float deriv = density * (1 - density);
+		local[k] = loss_scale * (dloss_by_drgb[k] * deriv + fmaxf(0.0f, 0.0f * ov));
+	}
+	const float dot = rl.lg_grad[0] * (Tj * e.rgb[0] - suffix[0]) + rl.lg_grad[1] * (Tj * e.rgb[1] - suffix[1]) + rl.lg_grad[2] * (Tj * e.rgb[2] - suffix[2]);
+	const float dloss_dalpha = (float)((dot + rl.gradient_weight_sum * (1 - rl.weight_sum)) / (1.0f - e.alpha + 1e-5));
+	float dalpha_d_e_minus_sigmoidx, d_e_minus_sigmoidx_dsdf, d_e_minus_sigmoidx_dinvs, d_alpha_d_plus_e, d_plus_e_dinvs, d_plus_e_iter_cos, d_e_minus_sigmoidx_diter_cos;
+	if (e.p_div_c <= 0.0f || e.p_div_c >= 1.0f) {
+		dalpha_d_e_minus_sigmoidx = d_e_minus_sigmoidx_dsdf = d_e_minus_sigmoidx_dinvs = d_alpha_d_plus_e = d_plus_e_dinvs = d_plus_e_iter_cos = d_e_minus_sigmoidx_diter_cos = 0.0f;
+	} else {
+		const float plus_sigmoid_x = e.inv_s * e.iter_cos * e.dt;
+		const float plus_e = expf(plus_sigmoid_x);
+		const float e_minus_sigmoid = expf(-e.next_sdf * e.inv_s);
+		d_e_minus_sigmoidx_dsdf = -e.inv_s * e_minus_sigmoid;
+		d_e_minus_sigmoidx_dinvs = -e.next_sdf * e_minus_sigmoid;
+		const float a = 1 + e_minus_sigmoid;
+		const float b = 1 + plus_e * e_minus_sigmoid;
+		const float c = (float)(1e-5 + 1 / (1 + plus_e * e_minus_sigmoid));
+		const float delta = a * (b * b) * (c * c);
+		dalpha_d_e_minus_sigmoidx = -(plus_e / (delta) - 1 / (a * a * c));
+		d_alpha_d_plus_e = -e_minus_sigmoid / (delta);
+		d_plus_e_dinvs = plus_e * e.iter_cos * e.dt;
+		d_plus_e_iter_cos = plus_e * e.inv_s * e.dt;
+		d_e_minus_sigmoidx_diter_cos = (float)(-e.inv_s * e_minus_sigmoid * e.dt * 0.5);
+	}
+	const float dloss_dinvs = dloss_dalpha * (dalpha_d_e_minus_sigmoidx * d_e_minus_sigmoidx_dinvs + d_alpha_d_plus_e * d_plus_e_dinvs);
+	const float dloss_dvariance = dloss_dinvs * e.inv_s * 10;
+	const float d_iter_cos_true_cos = (e.true_cos >= 0) ? 0.0f : 1.0f;
+	const float gradient_norm = (float)sqrt((double)(e.g[0] * e.g[0] + e.g[1] * e.g[1] + e.g[2] * e.g[2]) + 1e-6);
+	const float pos_gradient_norm_inv = 1 - 1 / gradient_norm;
+	const float dloss_dnormal_norm = dloss_dalpha * (dalpha_d_e_minus_sigmoidx * d_e_minus_sigmoidx_diter_cos + d_plus_e_iter_cos * d_alpha_d_plus_e) * d_iter_cos_true_cos;
+	const float dloss_dsdf = dloss_dalpha * dalpha_d_e_minus_sigmoidx * d_e_minus_sigmoidx_dsdf;
+	local[3] = loss_scale * dloss_dsdf;
+	#pragma unroll
+	for (int k = 0; k < 3; ++k) local[4 + k] = lp.ek_loss_weight * 2 * lp.loss_scale * pos_gradient_norm_inv * e.g[k];
+	local[7] = loss_scale * dloss_dvariance;
+	#pragma unroll
+	for (int k = 0; k < 3; ++k) local[8 + k] = loss_scale * dloss_dnormal_norm * dir[k];
+	uint32_t packed[8];
+	#pragma unroll
+	for (int k = 0; k < 8; ++k) packed[k] = pack_h2(local[2 * k], local[2 * k + 1]);
+	reinterpret_cast<uint4*>(dout_row)[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+	reinterpret_cast<uint4*>(dout_row)[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+	return (gradient_norm - 1.0f) * (gradient_norm - 1.0f);
+}
+
+__device__ __forceinline__ SampleEval zero_eval() {
+	SampleEval e;
+	e.alpha = 0.f; e.rgb[0] = e.rgb[1] = e.rgb[2] = 0.f; e.p_div_c = 0.f; e.inv_s = 0.f; e.iter_cos = 0.f; e.dt = 0.f; e.next_sdf = 0.f; e.true_cos = 0.f; e.sdf = 0.f;
+	e.g[0] = e.g[1] = e.g[2] = 0.f;
+	return e;
+}
+
 // pass 2: loss + dL/doutput + compaction (:1629-1957), one WARP per ray (see k_loss_composite).
 __global__ void __launch_bounds__(128)
 k_loss_gradient(uint32_t n_rays, uint32_t n_rays_total, Pcg32 rng_in, DatasetDev ds, LossParamsDev lp, uint32_t max_samples_compacted,
@@ -115,29 +236,10 @@ k_loss_gradient(uint32_t n_rays, uint32_t n_rays_total, Pcg32 rng_in, DatasetDev
 	float T = rt[5];
 	const float dir[3] = {rt[6], rt[7], rt[8]};
 
-	const uint32_t ray_idx = ray_indices[i];
-	Pcg32 rng = rng_in;
-	rng.advance((int64_t)(uint32_t)(ray_idx * N_MAX_RANDOM_SAMPLES_PER_RAY));
-	const uint32_t img = image_idx(ray_idx, n_rays, n_rays_total, ds.n_images);
-	float xy[2];
-	random_image_pos_training(rng, ds.width, ds.height, lp.snap_to_pixel_centers != 0, xy);
-	float bg[3] = {lp.background_color[0], lp.background_color[1], lp.background_color[2]};
-	if (lp.random_bg_color) { bg[0] = rng.next_float(); bg[1] = rng.next_float(); bg[2] = rng.next_float(); }
-	#pragma unroll
-	for (int k = 0; k < 3; ++k) bg[k] = srgb_to_linear(bg[k]);
-	int px, py; image_pos(xy, ds.width, ds.height, &px, &py);
-	float tex[4]; read_rgba(ds, img, px, py, tex);
-	float rgbtarget[3];
-	#pragma unroll
-	for (int k = 0; k < 3; ++k) {
-		const float exposure_scale = expf(0.6931471805599453f * 0.0f);
-		rgbtarget[k] = exposure_scale * tex[k] + (1.0f - tex[3]) * bg[k];
-		rgbtarget[k] = linear_to_srgb(rgbtarget[k]);
-		bg[k] = linear_to_srgb(bg[k]);
-	}
+	const RayTarget tg = ray_target(ray_indices[i], n_rays, n_rays_total, rng_in, ds, lp);
 	if (compacted == ns) {
 		#pragma unroll
-		for (int k = 0; k < 3; ++k) rgb_ray[k] += T * bg[k];
+		for (int k = 0; k < 3; ++k) rgb_ray[k] += T * tg.bg[k];
 	}
 	__syncwarp();   // every lane has read numsteps before lane 0 rewrites it
 	const uint32_t compacted_base = compacted_base_arr[i];
@@ -150,29 +252,10 @@ k_loss_gradient(uint32_t n_rays, uint32_t n_rays_total, Pcg32 rng_in, DatasetDev
 
 	float* cout = coords_compacted + (size_t)compacted_base * 7;
 	__half* dout = dloss_doutput + (size_t)compacted_base * 16;
-
-	float lg_loss[3], lg_grad[3];
-	#pragma unroll
-	for (int k = 0; k < 3; ++k) {
-		const float alpha_h = 0.1f;
-		const float difference = rgb_ray[k] - rgbtarget[k];
-		const float abs_diff = fabsf(difference);
-		const float square = 0.5f / alpha_h * difference * difference;
-		lg_loss[k] = (abs_diff > alpha_h ? (abs_diff - 0.5f * alpha_h) : square) / 5.0f;
-		lg_grad[k] = (abs_diff > alpha_h ? (difference > 0 ? 1.0f : -1.0f) : (difference / alpha_h)) / 5.0f;
-	}
-	const float mask_gt = (float)(tex[3] > 0.9999);
-	float gradient_weight_sum;
-	if (weight_sum >= 1.0 - 1e-4) { weight_sum = (float)(1.0 - 1e-4); gradient_weight_sum = 0.0f; }
-	else if (weight_sum <= 1e-4) { weight_sum = (float)1e-4; gradient_weight_sum = 0.0f; }
-	else {
-		const float sigmoid_weight_sum = 1.0f / (1.0f + expf(-weight_sum));
-		gradient_weight_sum = (mask_gt - sigmoid_weight_sum) * weight_sum * lp.mask_loss_weight;
-	}
-	const float mean_loss = (lg_loss[0] + lg_loss[1] + lg_loss[2]) / 3.0f;
+	const RayLoss rl = ray_loss(rgb_ray, weight_sum, tg, lp);
 	if (lane == 0) {
-		loss_output[i] = mean_loss / (float)n_rays;
-		mask_loss_output[i] = -(mask_gt * logf(weight_sum) + (1 - mask_gt) * logf(1 - weight_sum));
+		loss_output[i] = rl.mean_loss / (float)n_rays;
+		mask_loss_output[i] = rl.mask_loss;
 	}
 	float ek_acc = 0.f;
 
@@ -185,9 +268,7 @@ k_loss_gradient(uint32_t n_rays, uint32_t n_rays_total, Pcg32 rng_in, DatasetDev
 		for (uint32_t k = lane; k < cnt * 7; k += 32) cout[(size_t)c0 * 7 + k] = cin[(size_t)c0 * 7 + k];
 		const uint32_t j = c0 + lane;
 		const bool valid = lane < (int)cnt;
-		SampleEval e;
-		e.alpha = 0.f; e.rgb[0] = e.rgb[1] = e.rgb[2] = 0.f; e.p_div_c = 0.f; e.inv_s = 0.f; e.iter_cos = 0.f; e.dt = 0.f; e.next_sdf = 0.f; e.true_cos = 0.f; e.sdf = 0.f;
-		e.g[0] = e.g[1] = e.g[2] = 0.f;
+		SampleEval e = zero_eval();
 		const __half* o = nout + (size_t)j * 16;
 		if (valid) e = eval_sample(o, cin + (size_t)j * 7, dir, lp.cos_anneal_ratio);
 		// replay the recurrences in sample order; lane L keeps the state right after its own sample
@@ -201,63 +282,150 @@ k_loss_gradient(uint32_t n_rays, uint32_t n_rays_total, Pcg32 rng_in, DatasetDev
 			if (lane == (int)L) { my_weight = weight; my_T = T; my_r2[0] = rgb_ray2[0]; my_r2[1] = rgb_ray2[1]; my_r2[2] = rgb_ray2[2]; }
 		}
 		if (!valid) continue;
-		const float weight = my_weight;
-		const float Tj = my_T;
-		float suffix[3], dloss_by_drgb[3];
-		#pragma unroll
-		for (int k = 0; k < 3; ++k) { suffix[k] = rgb_ray[k] - my_r2[k]; dloss_by_drgb[k] = weight * lg_grad[k]; }
-		float local[16];
-		#pragma unroll
-		for (int k = 0; k < 16; ++k) local[k] = 0.f;
-		#pragma unroll
-		for (int k = 0; k < 3; ++k) {
-			const float ov = __half2float(o[k]);
-			const float density = logistic_f(ov);
-			const float deriv = density * (1 - density);
-			local[k] = loss_scale * (dloss_by_drgb[k] * deriv + fmaxf(0.0f, 0.0f * ov));
-		}
-		const float dot = lg_grad[0] * (Tj * e.rgb[0] - suffix[0]) + lg_grad[1] * (Tj * e.rgb[1] - suffix[1]) + lg_grad[2] * (Tj * e.rgb[2] - suffix[2]);
-		const float dloss_dalpha = (float)((dot + gradient_weight_sum * (1 - weight_sum)) / (1.0f - e.alpha + 1e-5));
-		float dalpha_d_e_minus_sigmoidx, d_e_minus_sigmoidx_dsdf, d_e_minus_sigmoidx_dinvs, d_alpha_d_plus_e, d_plus_e_dinvs, d_plus_e_iter_cos, d_e_minus_sigmoidx_diter_cos;
-		if (e.p_div_c <= 0.0f || e.p_div_c >= 1.0f) {
-			dalpha_d_e_minus_sigmoidx = d_e_minus_sigmoidx_dsdf = d_e_minus_sigmoidx_dinvs = d_alpha_d_plus_e = d_plus_e_dinvs = d_plus_e_iter_cos = d_e_minus_sigmoidx_diter_cos = 0.0f;
-		} else {
-			const float plus_sigmoid_x = e.inv_s * e.iter_cos * e.dt;
-			const float plus_e = expf(plus_sigmoid_x);
-			const float e_minus_sigmoid = expf(-e.next_sdf * e.inv_s);
-			d_e_minus_sigmoidx_dsdf = -e.inv_s * e_minus_sigmoid;
-			d_e_minus_sigmoidx_dinvs = -e.next_sdf * e_minus_sigmoid;
-			const float a = 1 + e_minus_sigmoid;
-			const float b = 1 + plus_e * e_minus_sigmoid;
-			const float c = (float)(1e-5 + 1 / (1 + plus_e * e_minus_sigmoid));
-			const float delta = a * (b * b) * (c * c);
-			dalpha_d_e_minus_sigmoidx = -(plus_e / (delta) - 1 / (a * a * c));
-			d_alpha_d_plus_e = -e_minus_sigmoid / (delta);
-			d_plus_e_dinvs = plus_e * e.iter_cos * e.dt;
-			d_plus_e_iter_cos = plus_e * e.inv_s * e.dt;
-			d_e_minus_sigmoidx_diter_cos = (float)(-e.inv_s * e_minus_sigmoid * e.dt * 0.5);
-		}
-		const float dloss_dinvs = dloss_dalpha * (dalpha_d_e_minus_sigmoidx * d_e_minus_sigmoidx_dinvs + d_alpha_d_plus_e * d_plus_e_dinvs);
-		const float dloss_dvariance = dloss_dinvs * e.inv_s * 10;
-		const float d_iter_cos_true_cos = (e.true_cos >= 0) ? 0.0f : 1.0f;
-		const float gradient_norm = (float)sqrt((double)(e.g[0] * e.g[0] + e.g[1] * e.g[1] + e.g[2] * e.g[2]) + 1e-6);
-		const float pos_gradient_norm_inv = 1 - 1 / gradient_norm;
-		const float dloss_dnormal_norm = dloss_dalpha * (dalpha_d_e_minus_sigmoidx * d_e_minus_sigmoidx_diter_cos + d_plus_e_iter_cos * d_alpha_d_plus_e) * d_iter_cos_true_cos;
-		const float dloss_dsdf = dloss_dalpha * dalpha_d_e_minus_sigmoidx * d_e_minus_sigmoidx_dsdf;
-		local[3] = loss_scale * dloss_dsdf;
-		ek_acc += (gradient_norm - 1.0f) * (gradient_norm - 1.0f);
-		#pragma unroll
-		for (int k = 0; k < 3; ++k) local[4 + k] = lp.ek_loss_weight * 2 * lp.loss_scale * pos_gradient_norm_inv * e.g[k];
-		local[7] = loss_scale * dloss_dvariance;
-		#pragma unroll
-		for (int k = 0; k < 3; ++k) local[8 + k] = loss_scale * dloss_dnormal_norm * dir[k];
-		uint32_t packed[8];
-		#pragma unroll
-		for (int k = 0; k < 8; ++k) packed[k] = pack_h2(local[2 * k], local[2 * k + 1]);
-		reinterpret_cast<uint4*>(dout + (size_t)j * 16)[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-		reinterpret_cast<uint4*>(dout + (size_t)j * 16)[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+		ek_acc += sample_gradient(e, o, my_weight, my_T, my_r2, rl, dir, lp, loss_scale, dout + (size_t)j * 16);
 	}
 	// eikonal log value: warp reduction (the reference sums serially; fp32 order differs, it is a reported scalar only)
+	#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) ek_acc += __shfl_xor_sync(0xffffffffu, ek_acc, o);
+	if (lane == 0) ek_loss_output[i] = ek_acc / ((float)compacted * (float)n_rays);
+}
+
+// Both passes in ONE kernel: a block takes 8 consecutive kept rays (one warp each), composites them (pass 1 above), obtains the rays'
+// offsets into the compacted batch from a prefix sum across the blocks of this launch (lookback.cuh: same ray-slot order as
+// k_scan_compacted), and goes straight on to pass 2.  The first 32 samples of a ray -- all of them, for most rays -- keep their
+// evaluation and their running compositing state in registers between the passes: no second read of the network output, no second
+// exp / logistic / division chain, no per-ray scratch record, no scan kernel, one launch instead of three.  Every value is computed by
+// the same expressions in the same order as in the two-kernel path (the tests compare the two bit for bit).
+#define LF_RAYS 8
+__global__ void __launch_bounds__(LF_RAYS * 32)
+k_loss_fused(uint32_t n_rays, uint32_t n_rays_total, Pcg32 rng_in, DatasetDev ds, GlobalMove gmv, LossParamsDev lp, uint32_t max_samples_compacted,
+             const uint32_t* __restrict__ n_kept_ptr, const __half* __restrict__ network_output, const uint32_t* __restrict__ ray_indices,
+             const float* __restrict__ rays, uint32_t* __restrict__ numsteps, const float* __restrict__ coords, LookbackScan scan,
+             float* __restrict__ coords_compacted, __half* __restrict__ dloss_doutput, float* __restrict__ loss_output,
+             float* __restrict__ ek_loss_output, float* __restrict__ mask_loss_output, uint32_t* __restrict__ out_counter) {
+	__shared__ uint32_t s_tile, s_count[LF_RAYS], s_base[LF_RAYS];
+	if (threadIdx.x == 0) s_tile = lookback_take_ticket(scan);
+	__syncthreads();
+	const uint32_t tile = s_tile;
+	const uint32_t n_kept = *n_kept_ptr;
+	const uint32_t n_tiles = (n_kept + LF_RAYS - 1) / LF_RAYS;
+	if (tile >= n_tiles) {
+		if (n_kept == 0 && tile == 0 && threadIdx.x == 0) *out_counter = 0u;
+		return;
+	}
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const uint32_t i = tile * LF_RAYS + warp;
+	const bool active = i < n_kept;
+
+	// ---- pass 1 ----
+	uint32_t ns = 0, base = 0, compacted = 0;
+	const float* cin = coords; const __half* nout = network_output;
+	float T = 1.f, weight_sum = 0.f;
+	float rgb_ray[3] = {0.f, 0.f, 0.f};
+	float dir[3] = {0.f, 0.f, 0.f};
+	RayTarget tg;
+	SampleEval e0 = zero_eval();                              // evaluation of sample `lane` (first chunk)
+	float w0 = 0.f, T0 = 0.f, r0a[3] = {0.f, 0.f, 0.f};       // ... its weight, the transmittance behind it, the colour up to and including it
+	float T_chunk0 = 1.f, rgb_chunk0[3] = {0.f, 0.f, 0.f};    // state after the whole first chunk (where a longer ray's second chunk starts)
+	const float EPSILON = 1e-4f;
+	if (active) {
+		ns = numsteps[i * 2 + 0]; base = numsteps[i * 2 + 1];
+		cin = coords + (size_t)base * 7;
+		nout = network_output + (size_t)base * 16;
+		tg = ray_target(ray_indices[i], n_rays, n_rays_total, rng_in, ds, lp);   // independent of the network: its loads overlap pass 1
+		float ray_o[3];
+		ray_dir_for_loss(rays + (size_t)i * 6, gmv, ray_o, dir);
+		{   // BENT_DIR :1583-1588 (from sample 0)
+			float dv[3] = {__half2float(nout[8]) * 2.0f - 1.0f, __half2float(nout[9]) * 2.0f - 1.0f, __half2float(nout[10]) * 2.0f - 1.0f};
+			if (ns > 0) normalize3(dv, dir);
+		}
+		bool stop = false;
+		for (uint32_t c0 = 0; c0 < ns && !stop; c0 += 32) {
+			const uint32_t idx = c0 + lane;
+			SampleEval e = zero_eval();
+			if (idx < ns) e = eval_sample(nout + (size_t)idx * 16, cin + (size_t)idx * 7, dir, lp.cos_anneal_ratio);
+			if (c0 == 0) e0 = e;
+			const uint32_t cnt = min(32u, ns - c0);
+			for (uint32_t L = 0; L < cnt; ++L) {
+				if (T < EPSILON) { stop = true; break; }
+				const float a = __shfl_sync(0xffffffffu, e.alpha, L);
+				const float r0 = __shfl_sync(0xffffffffu, e.rgb[0], L), r1 = __shfl_sync(0xffffffffu, e.rgb[1], L), r2 = __shfl_sync(0xffffffffu, e.rgb[2], L);
+				const float weight = a * T;
+				rgb_ray[0] += weight * r0; rgb_ray[1] += weight * r1; rgb_ray[2] += weight * r2;
+				weight_sum += weight;
+				T *= (1.f - a);
+				++compacted;
+				if (c0 == 0 && lane == (int)L) { w0 = weight; T0 = T; r0a[0] = rgb_ray[0]; r0a[1] = rgb_ray[1]; r0a[2] = rgb_ray[2]; }
+			}
+			if (c0 == 0) { T_chunk0 = T; rgb_chunk0[0] = rgb_ray[0]; rgb_chunk0[1] = rgb_ray[1]; rgb_chunk0[2] = rgb_ray[2]; }
+		}
+	}
+
+	// ---- where the ray's samples go in the compacted batch ----
+	if (lane == 0) s_count[warp] = compacted;
+	__syncthreads();
+	if (warp == 0) {
+		const uint32_t c = lane < LF_RAYS ? s_count[lane] : 0u;
+		uint32_t inc = c;
+		#pragma unroll
+		for (int o = 1; o < LF_RAYS; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+		const uint32_t aggregate = __shfl_sync(0xffffffffu, inc, LF_RAYS - 1);
+		const uint32_t before = lookback_exclusive(scan, tile, aggregate, lane);
+		if (lane < LF_RAYS) s_base[lane] = before + inc - c;
+		if (tile == n_tiles - 1 && lane == 0) *out_counter = before + aggregate;   // total compacted samples (un-clamped), as k_scan_compacted
+	}
+	__syncthreads();
+	if (!active) return;
+
+	// ---- pass 2 ----
+	if (compacted == ns) {
+		#pragma unroll
+		for (int k = 0; k < 3; ++k) rgb_ray[k] += T * tg.bg[k];
+	}
+	const uint32_t compacted_base = s_base[warp];
+	compacted = min(max_samples_compacted - min(max_samples_compacted, compacted_base), compacted);
+	if (lane == 0) {
+		numsteps[i * 2 + 0] = compacted;
+		numsteps[i * 2 + 1] = compacted_base;
+	}
+	if (compacted == 0) return;
+
+	float* cout = coords_compacted + (size_t)compacted_base * 7;
+	__half* dout = dloss_doutput + (size_t)compacted_base * 16;
+	const RayLoss rl = ray_loss(rgb_ray, weight_sum, tg, lp);
+	if (lane == 0) {
+		loss_output[i] = rl.mean_loss / (float)n_rays;
+		mask_loss_output[i] = rl.mask_loss;
+	}
+	const float loss_scale = lp.loss_scale / n_rays;
+	float ek_acc = 0.f;
+	{   // first chunk: everything is still in registers
+		const uint32_t cnt = min(32u, compacted);
+		for (uint32_t k = lane; k < cnt * 7; k += 32) cout[k] = cin[k];
+		if (lane < (int)cnt) ek_acc += sample_gradient(e0, nout + (size_t)lane * 16, w0, T0, r0a, rl, dir, lp, loss_scale, dout + (size_t)lane * 16);
+	}
+	float rgb_ray2[3] = {rgb_chunk0[0], rgb_chunk0[1], rgb_chunk0[2]};
+	T = T_chunk0;
+	for (uint32_t c0 = 32; c0 < compacted; c0 += 32) {   // longer rays: as k_loss_gradient
+		const uint32_t cnt = min(32u, compacted - c0);
+		for (uint32_t k = lane; k < cnt * 7; k += 32) cout[(size_t)c0 * 7 + k] = cin[(size_t)c0 * 7 + k];
+		const uint32_t j = c0 + lane;
+		const bool valid = lane < (int)cnt;
+		SampleEval e = zero_eval();
+		const __half* o = nout + (size_t)j * 16;
+		if (valid) e = eval_sample(o, cin + (size_t)j * 7, dir, lp.cos_anneal_ratio);
+		float my_weight = 0.f, my_T = 0.f, my_r2[3] = {0.f, 0.f, 0.f};
+		for (uint32_t L = 0; L < cnt; ++L) {
+			const float a = __shfl_sync(0xffffffffu, e.alpha, L);
+			const float r0 = __shfl_sync(0xffffffffu, e.rgb[0], L), r1 = __shfl_sync(0xffffffffu, e.rgb[1], L), r2 = __shfl_sync(0xffffffffu, e.rgb[2], L);
+			const float weight = a * T;
+			rgb_ray2[0] += weight * r0; rgb_ray2[1] += weight * r1; rgb_ray2[2] += weight * r2;
+			T *= (1.f - a);
+			if (lane == (int)L) { my_weight = weight; my_T = T; my_r2[0] = rgb_ray2[0]; my_r2[1] = rgb_ray2[1]; my_r2[2] = rgb_ray2[2]; }
+		}
+		if (!valid) continue;
+		ek_acc += sample_gradient(e, o, my_weight, my_T, my_r2, rl, dir, lp, loss_scale, dout + (size_t)j * 16);
+	}
 	#pragma unroll
 	for (int o = 16; o > 0; o >>= 1) ek_acc += __shfl_xor_sync(0xffffffffu, ek_acc, o);
 	if (lane == 0) ek_loss_output[i] = ek_acc / ((float)compacted * (float)n_rays);
@@ -267,10 +435,19 @@ int launch_compute_loss(cudaStream_t stream, uint32_t n_rays_local, uint32_t n_r
                         const GlobalMove& gmv, const LossParamsDev& lp, uint32_t max_samples_compacted, const uint32_t* n_kept_ptr,
                         const __half* network_output, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps, const float* coords,
                         float* ray_tmp, uint32_t* scan_tmp, float* coords_compacted, __half* dloss_doutput,
-                        float* loss_output, float* ek_loss_output, float* mask_loss_output, uint32_t* out_counter) {
+                        float* loss_output, float* ek_loss_output, float* mask_loss_output, uint32_t* out_counter,
+                        unsigned long long* lookback_desc, uint32_t* lookback_ticket, uint32_t lookback_epoch) {
 	(void)bb;
 	if (n_rays_local == 0) return 0;
 	Pcg32 rng; rng.state = rng_state[0]; rng.inc = rng_state[1];
+	if (lookback_desc) {
+		LookbackScan scan = {lookback_desc, lookback_ticket, lookback_epoch};
+		k_loss_fused<<<(n_rays_local + LF_RAYS - 1) / LF_RAYS, LF_RAYS * 32, 0, stream>>>(n_rays, n_rays_total, rng, ds, gmv, lp, max_samples_compacted, n_kept_ptr, network_output,
+		        ray_indices, rays, numsteps, coords, scan, coords_compacted, dloss_doutput, loss_output, ek_loss_output, mask_loss_output, out_counter);
+		COUNT_LAUNCH(1);
+		CUDA_CHECK(cudaGetLastError());
+		return 0;
+	}
 	const uint32_t blocks = (n_rays_local + 3) / 4;   // one warp per ray
 	uint32_t* counts = scan_tmp;
 	uint32_t* cbase = scan_tmp + n_rays_local;

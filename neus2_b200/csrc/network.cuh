@@ -64,7 +64,7 @@ struct WarpSlab {
 static_assert(WarpSlab::OUT % 16 == 0 && WarpSlab::DX % 16 == 0 && WarpSlab::DI % 16 == 0 && WarpSlab::BWD_END % 16 == 0 && WarpSlab::DELTA_END % 16 == 0, "slab alignment");
 
 #ifndef NEUS2_STAGE_WEIGHTS_TMA
-#define NEUS2_STAGE_WEIGHTS_TMA 1
+#define NEUS2_STAGE_WEIGHTS_TMA 0   // measured (same box, profiles/r02_bench_n1_tma_ab.md): the bulk-copy variant costs 8 us in the first pass (224 small copies per CTA)
 #endif
 __device__ __forceinline__ void stage_matrix(__half* dst, int ld_dst, const __half* __restrict__ src, int rows, int cols, int tid, int nthreads) {
 	for (int i = tid; i < rows * cols; i += nthreads) {
