@@ -92,7 +92,20 @@ class ClockSampler:
 
 def make_data(args):
     from neus2_b200 import synthetic
-    return synthetic.dtu_like_views(n_views=args.views, width=args.width, height=args.height, seed=0)
+    # NEUS2_BENCH_DATA_CACHE=<file.npz>: back-to-back A/B runs on one box render the synthetic views once (untimed set-up either way)
+    cache = os.environ.get("NEUS2_BENCH_DATA_CACHE")
+    key = f"{args.views}x{args.width}x{args.height}"
+    if cache and os.path.exists(cache):
+        z = np.load(cache)
+        if str(z["key"]) == key:
+            data = {k: z[k] for k in ("pixels", "focal", "principal", "xforms")}
+            data["spheres"] = [(c, float(r)) for c, r in zip(z["sphere_centers"], z["sphere_radii"])]
+            return data
+    data = synthetic.dtu_like_views(n_views=args.views, width=args.width, height=args.height, seed=0)
+    if cache:
+        np.savez(cache, key=key, sphere_centers=np.array([c for c, _ in data["spheres"]]), sphere_radii=np.array([r for _, r in data["spheres"]]),
+                 **{k: data[k] for k in ("pixels", "focal", "principal", "xforms")})
+    return data
 
 
 # ------------------------------------------------------------------------------------------------------------------

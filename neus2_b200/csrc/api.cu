@@ -64,10 +64,9 @@ struct neus2_ctx {
 	float *partials, *var_acc, *w1row0_acc, *scalar_tmp;
 	uint32_t* fwdbwd_done;      // CTA arrival counter of the training kernel (self-resetting)
 	// prefix sums across the blocks of one launch (lookback.cuh): descriptors (never cleared, validated by epoch), ticket counters, launch epoch
-	unsigned long long *lb_loss_desc, *lb_gen_desc; uint32_t* lb_tickets; uint32_t lb_epoch;   // tickets: [0] loss, [1..2] sample generation
-	// step-tail kernel (optimizer.cu: this step's Adam + the next step's sample generation in one persistent launch)
-	void* tail_state; const GenArgs* tail_gen;   // tail_gen: set around the optimizer call that should carry the generation
-	bool counters_clean[2];                      // counters_buf[b] is known to hold zeros (cleared by a fused-zero Adam, not written since)
+	unsigned long long* lb_loss_desc; uint32_t* lb_tickets; uint32_t lb_epoch;
+	// the loss by samples (loss.cu): {alpha, r, g, b} per marched sample from the first pass, and the loss kernels' own scratch
+	float4* composite_in; LossScratch loss_ws;
 
 	// occupancy grid
 	float *density_grid, *density_grid_tmp, *grid_positions, *density_grid_mean;
@@ -103,7 +102,7 @@ struct neus2_ctx {
 	// SM's register file) -- it overlaps the weight-gradient GEMMs and Adam.  The counters ping-pong between two buffers.
 	struct StepPlan { uint32_t R, n_local, ray_offset, ray_stride, max_inference, n_rays_total, training_step; uint64_t rng_state, rng_inc; };
 	cudaStream_t aux_stream;
-	cudaEvent_t ev_counts, ev_fwdbwd_done, ev_gen_done;
+	cudaEvent_t ev_counts, ev_fwdbwd_done, ev_gen_done, ev_loss_done;
 	uint32_t* counters_buf[2]; int counters_cur;
 	bool prefetched; StepPlan prefetch_plan; uint64_t prefetch_epoch;
 	bool step_pipelined;        // the step in flight took the pipelined path (its counts were read back after the loss kernel)
@@ -410,7 +409,8 @@ int neus2_ctx_create(const neus2_config* cfg, int device, neus2_ctx** out) {
 	CDM(ctx->counters_buf[0], 12); CDM(ctx->counters_buf[1], 12);
 	ctx->counters = ctx->counters_buf[0]; ctx->counts_global = ctx->counters + 8;   // one 48-byte read-back per step covers both
 	if (cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_counts, cudaEventDisableTiming) != cudaSuccess ||
-	    cudaEventCreateWithFlags(&ctx->ev_fwdbwd_done, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_gen_done, cudaEventDisableTiming) != cudaSuccess) {
+	    cudaEventCreateWithFlags(&ctx->ev_fwdbwd_done, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_gen_done, cudaEventDisableTiming) != cudaSuccess ||
+	    cudaEventCreateWithFlags(&ctx->ev_loss_done, cudaEventDisableTiming) != cudaSuccess) {
 		neus2_ctx_destroy(ctx); FAIL("stream / event creation failed");
 	}
 	CDM(ctx->rays, 6 * (size_t)R); CDM(ctx->coords, 7 * (size_t)S); CDM(ctx->ray_tmp, 12 * (size_t)R);
@@ -423,8 +423,11 @@ int neus2_ctx_create(const neus2_config* cfg, int device, neus2_ctx** out) {
 		CDM(ctx->partials, (size_t)weight_gradient_partials() * ctx->pl.off_grid);
 	}
 	CDM(ctx->var_acc, 1); CDM(ctx->w1row0_acc, 64); CDM(ctx->scalar_tmp, 4); CDM(ctx->fwdbwd_done, 1);
-	CDM(ctx->lb_loss_desc, (size_t)R / 8 + 2); CDM(ctx->lb_gen_desc, 2 * ((size_t)R / 8 + 2)); CDM(ctx->lb_tickets, 4);
-	CTXCHECK(dmalloc(&ctx->tail_state, tail_state_bytes()));
+	if (ctx->cfg.forward_early_termination) {
+		CDM(ctx->composite_in, S); CDM(ctx->loss_ws.prefix4, S); CDM(ctx->loss_ws.prefix1, S);
+		CDM(ctx->loss_ws.slot_sample, B); CDM(ctx->loss_ws.slot_ray, B); CDM(ctx->loss_ws.ray_rec, 12 * (size_t)R);
+	}
+	CDM(ctx->lb_loss_desc, (size_t)R / 8 + 2); CDM(ctx->lb_tickets, 4);
 	const size_t G3n = (size_t)NERF_GRIDSIZE * NERF_GRIDSIZE * NERF_GRIDSIZE;
 	CDM(ctx->density_grid, G3n * ctx->n_cascades); CDM(ctx->density_grid_tmp, G3n * ctx->n_cascades);
 	CDM(ctx->grid_positions, 3 * G3n * ctx->n_cascades); CDM(ctx->grid_indices, G3n * ctx->n_cascades); CDM(ctx->grid_density, G3n * ctx->n_cascades);
@@ -453,14 +456,14 @@ void neus2_ctx_destroy(neus2_ctx* ctx) {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
-	for (cudaEvent_t e : {ctx->ev_counts, ctx->ev_fwdbwd_done, ctx->ev_gen_done}) if (e) cudaEventDestroy(e);
+	for (cudaEvent_t e : {ctx->ev_counts, ctx->ev_fwdbwd_done, ctx->ev_gen_done, ctx->ev_loss_done}) if (e) cudaEventDestroy(e);
 	ctx->counters = nullptr;   // freed through counters_buf below
 	void* ptrs[] = {ctx->master, ctx->params, ctx->ema, ctx->grads, ctx->m1, ctx->m2, ctx->steps, ctx->adam_bias_table, ctx->d_pixels, ctx->d_focal, ctx->d_principal, ctx->d_xforms,
 		ctx->numsteps_all, ctx->base, ctx->slot, ctx->ray_indices, ctx->numsteps, ctx->scan_tmp, ctx->counters, ctx->n_windows, ctx->windows, ctx->ray_setup, ctx->rays, ctx->coords, ctx->ray_tmp,
 		ctx->coords_compacted, ctx->loss, ctx->ek_loss, ctx->mask_loss, ctx->mlp_out, ctx->dloss, ctx->so.dOUT, ctx->so.H2, ctx->so.dH2, ctx->so.H1, ctx->so.dH1,
 		ctx->so.CIN, ctx->so.dSO, ctx->so.H0, ctx->so.dH0, ctx->so.X0, ctx->so.dI, ctx->partials, ctx->var_acc, ctx->w1row0_acc, ctx->scalar_tmp, ctx->fwdbwd_done,
 		ctx->density_grid, ctx->density_grid_tmp, ctx->grid_positions, ctx->grid_indices, ctx->grid_density, ctx->bitfield, ctx->density_grid_mean,
-		ctx->d_xform, ctx->d_acc, ctx->d_master, ctx->d_m1, ctx->d_m2, ctx->d_steps, ctx->d_params, ctx->counters_buf[0], ctx->counters_buf[1], ctx->sync_block, ctx->sync_done, ctx->lb_loss_desc, ctx->lb_gen_desc, ctx->lb_tickets, ctx->tail_state};
+		ctx->d_xform, ctx->d_acc, ctx->d_master, ctx->d_m1, ctx->d_m2, ctx->d_steps, ctx->d_params, ctx->counters_buf[0], ctx->counters_buf[1], ctx->sync_block, ctx->sync_done, ctx->lb_loss_desc, ctx->lb_tickets, ctx->composite_in, ctx->loss_ws.prefix4, ctx->loss_ws.prefix1, ctx->loss_ws.slot_sample, ctx->loss_ws.slot_ray, ctx->loss_ws.ray_rec};
 	for (uint32_t r = 0; r < ctx->peer_world; ++r) if (r != ctx->peer_rank) {   // unmap the peers' buffers before this rank's own are freed
 		if (ctx->peer_grads[r]) cudaIpcCloseMemHandle(ctx->peer_grads[r]);
 		if (ctx->peer_params[r]) cudaIpcCloseMemHandle(ctx->peer_params[r]);
@@ -686,8 +689,7 @@ int neus2_optimizer_step(neus2_ctx* ctx, void* stream, float loss_scale) {
 	const float lr = ctx->learning_rate * neus2_learning_rate_factor(&c, ctx->adam_step - 1);   // x 1.0f before decay_start: the same float
 	const int rc_ = launch_adam_ema((cudaStream_t)stream, ctx->n_params, ctx->pl.off_grid, loss_scale, lr, c.beta1, c.beta2, c.epsilon, c.l2_reg,
 	                                c.ema_decay, ctx->adam_step, ctx->grads, ctx->master, ctx->params, ctx->m1, ctx->m2, ctx->steps, ctx->ema, ctx->adam_bias_table, ADAM_BIAS_TABLE,
-	                                fuse, zp, zn, ctx->tail_gen, ctx->tail_state);
-	if (fuse) ctx->counters_clean[ctx->counters_cur] = true;
+	                                fuse, zp, zn);
 	if (rc_ == 0 && ctx->use_delta) CHECK(delta_optimizer_step(ctx, (cudaStream_t)stream, loss_scale));   // m_global_move.trainer->optimizer_step (testbed_nerf.cu:3506-3508)
 	stage_end(ctx, ST_OPT, (cudaStream_t)stream);
 	return rc_;
@@ -785,26 +787,12 @@ static void plan_step(const neus2_ctx* ctx, uint32_t rank, uint32_t world_size, 
 	p.training_step = ctx->training_step;
 	p.rng_state = ctx->rng.state; p.rng_inc = ctx->rng.inc;
 }
-static int launch_gen(neus2_ctx* ctx, cudaStream_t stream, const neus2_ctx::StepPlan& p, uint32_t* counters, bool fused) {
+static int launch_gen(neus2_ctx* ctx, cudaStream_t stream, const neus2_ctx::StepPlan& p, uint32_t* counters) {
 	const uint64_t st[2] = {p.rng_state, p.rng_inc};
-	const char* gen_fused_env = getenv("NEUS2_GEN_FUSED");   // A/B switch, read per launch: 1 / 0 force count + scans + emit as one kernel / as three
-	if (gen_fused_env) fused = atoi(gen_fused_env) != 0;
-	ctx->lb_epoch = ctx->lb_epoch % 0x3ffffffeu + 1u;
-	ctx->counters_clean[counters == ctx->counters_buf[0] ? 0 : 1] = false;
 	return launch_generate_training_samples(stream, p.n_local, p.ray_offset, p.ray_stride, p.R, p.n_rays_total, st, ctx->ds, ctx->aabb, ctx->gmv, ctx->bitfield, ctx->cfg.snap_to_pixel_centers,
 	                                        ctx->cone_angle_constant, p.max_inference, ctx->numsteps_all, ctx->base, ctx->slot, ctx->ray_indices, ctx->rays,
 	                                        ctx->numsteps, ctx->coords, counters, ctx->windows, ctx->n_windows, ctx->ray_setup,
-	                                        ctx->cfg.forward_early_termination ? ctx->scan_tmp : nullptr,   // scan_tmp: free between the loss's scan of step k and of step k + 1
-	                                        fused ? ctx->lb_gen_desc : nullptr, ctx->lb_tickets + 1, ctx->lb_epoch);
-}
-// the same launch as an argument block for the step-tail kernel
-static GenArgs tail_gen_args(neus2_ctx* ctx, const neus2_ctx::StepPlan& p, uint32_t* counters) {
-	const uint64_t st[2] = {p.rng_state, p.rng_inc};
-	ctx->lb_epoch = ctx->lb_epoch % 0x3ffffffeu + 1u;
-	ctx->counters_clean[counters == ctx->counters_buf[0] ? 0 : 1] = false;
-	return make_gen_args(p.n_local, p.ray_offset, p.ray_stride, p.R, p.n_rays_total, st, ctx->ds, ctx->aabb, ctx->gmv, ctx->bitfield, ctx->cfg.snap_to_pixel_centers, ctx->cone_angle_constant,
-	                     p.max_inference, ctx->numsteps_all, ctx->ray_indices, ctx->rays, ctx->numsteps, ctx->coords, counters,
-	                     ctx->cfg.forward_early_termination ? ctx->scan_tmp : nullptr, ctx->lb_gen_desc, ctx->lb_tickets + 1, ctx->lb_epoch);
+	                                        ctx->cfg.forward_early_termination ? ctx->scan_tmp : nullptr);   // scan_tmp: free between the loss's scan of step k and of step k + 1
 }
 static bool density_grid_due(uint32_t canonical_training_step) {
 	const uint32_t n_prep_to_skip = std::min(std::max(canonical_training_step / 16u, 1u), 16u);   // testbed.cu:2669-2670: m_canonical_training_step
@@ -865,7 +853,7 @@ int neus2_train_step_begin(neus2_ctx* ctx, void* stream_, uint32_t rank, uint32_
 	const uint64_t st[2] = {plan.rng_state, plan.rng_inc};
 	if (!have_samples) {
 		stage_begin(ctx, ST_GEN, stream);
-		CHECK(launch_gen(ctx, stream, plan, ctx->counters, /*fused=*/true));   // alone on the GPU: one kernel
+		CHECK(launch_gen(ctx, stream, plan, ctx->counters));
 		stage_end(ctx, ST_GEN, stream);
 	}
 	LossParamsDev lp;
@@ -876,18 +864,18 @@ int neus2_train_step_begin(neus2_ctx* ctx, void* stream_, uint32_t rank, uint32_
 	stage_begin(ctx, ST_FWD, stream);
 	if (c.forward_early_termination) {
 		CHECK(launch_network_forward_rays(stream, ctx->gm, ctx->pl, ctx->params, c.sdf_bias, lp.cos_anneal_ratio, ctx->counters + 0, ctx->counters + 6, ctx->numsteps,
-		                                  ctx->coords, max_inference, n_local, ctx->mlp_out, ctx->scan_tmp, ctx->counters + 4));   // scan_tmp: free until the loss's scan
+		                                  ctx->coords, max_inference, n_local, ctx->mlp_out, ctx->composite_in, ctx->scan_tmp, ctx->counters + 4));   // scan_tmp: free until the loss's scan
 	} else {
 		CHECK(launch_network_forward(stream, ctx->gm, ctx->pl, ctx->params, ctx->coords, ctx->counters + 1, max_inference, c.sdf_bias, ctx->mlp_out));   // :3854
 	}
 	stage_end(ctx, ST_FWD, stream);
 	stage_begin(ctx, ST_LOSS, stream);
-	const char* loss_fused_env = getenv("NEUS2_LOSS_FUSED");   // =0: A/B switch (composite / scan / gradient as three kernels); read per step
-	const int loss_fused = loss_fused_env ? atoi(loss_fused_env) : 1;
+	const char* loss_env = getenv("NEUS2_LOSS_BY_SAMPLES");   // =0: A/B switch (composite / scan / gradient kernels, one warp per ray); read per step
+	const bool by_samples = c.forward_early_termination && (loss_env ? atoi(loss_env) != 0 : true);   // needs what the early-terminating first pass stores
 	ctx->lb_epoch = ctx->lb_epoch % 0x3ffffffeu + 1u;
 	CHECK(launch_compute_loss(stream, n_local, R, n_rays_total, st, ctx->ds, ctx->aabb, ctx->gmv, lp, rows_local, ctx->counters + 0, ctx->mlp_out, ctx->ray_indices,
 	                          ctx->rays, ctx->numsteps, ctx->coords, ctx->ray_tmp, ctx->scan_tmp, ctx->coords_compacted, ctx->dloss, ctx->loss, ctx->ek_loss,
-	                          ctx->mask_loss, ctx->counters + 2, loss_fused ? ctx->lb_loss_desc : nullptr, ctx->lb_tickets + 0, ctx->lb_epoch));
+	                          ctx->mask_loss, ctx->counters + 2, by_samples ? ctx->composite_in : nullptr, &ctx->loss_ws, ctx->lb_loss_desc, ctx->lb_tickets + 0, ctx->lb_epoch));
 	stage_end(ctx, ST_LOSS, stream);
 	ctx->step_pipelined = pipelined;
 	ctx->step_rank = rank; ctx->step_world = world_size;
@@ -903,9 +891,17 @@ int neus2_train_step_begin(neus2_ctx* ctx, void* stream_, uint32_t rank, uint32_
 			CHECK(launch_peer_exchange(stream, x1, ctx->counters, ctx->counts_global, loss_due ? ctx->scalar_tmp : nullptr, nullptr));
 			stage_end(ctx, ST_X_COUNTS, stream);
 		}   // one GPU: the global counts are the local ones, read back from counters[0..2] directly (no device-to-device copy)
-		if (loss_due) CHECK(read_back_loss_scalars(ctx, stream));
-		CUDA_CHECK(cudaMemcpyAsync(ctx->h_counters, ctx->counters, 12 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-		CUDA_CHECK(cudaEventRecord(ctx->ev_counts, stream));
+		// ... on the second stream: a copy queued on the main stream would hold the training kernel back until it has landed in host memory
+		static int readback_main = -1;   // NEUS2_READBACK_MAIN=1: A/B switch (copies on the main stream)
+		if (readback_main < 0) { const char* e = getenv("NEUS2_READBACK_MAIN"); readback_main = e ? atoi(e) : 0; }
+		cudaStream_t rb = readback_main ? stream : ctx->aux_stream;
+		if (!readback_main) {
+			CUDA_CHECK(cudaEventRecord(ctx->ev_loss_done, stream));
+			CUDA_CHECK(cudaStreamWaitEvent(rb, ctx->ev_loss_done, 0));
+		}
+		if (loss_due) CHECK(read_back_loss_scalars(ctx, rb));
+		CUDA_CHECK(cudaMemcpyAsync(ctx->h_counters, ctx->counters, 12 * sizeof(uint32_t), cudaMemcpyDeviceToHost, rb));
+		CUDA_CHECK(cudaEventRecord(ctx->ev_counts, rb));
 	} else if (ctx->training_step % 16 == 0) {
 		CHECK(reduce_loss_scalars(ctx, stream));   // read back by neus2_train_step_counts_ready / neus2_train_step_end, after the caller's all-reduce
 	}
@@ -966,11 +962,8 @@ int neus2_train_step_end(neus2_ctx* ctx, void* stream_, const uint32_t* counts_g
 	const bool fused_zero = pipelined && !no_fused_zero && !canonical_frozen(ctx) &&
 	                        (ctx->optimizer_done ? (ctx->sharded_zeroed && ctx->barrier_zeroed) : c.world_size == 1);
 	ctx->sharded_zeroed = ctx->barrier_zeroed = false;
-	// Single GPU, pipelined: the optimizer is launched further down, once the host knows the next step's rays_per_batch, as ONE kernel with the
-	// next step's sample generation (optimizer.cu, k_tail_adam_gen).  The host's wait for the counts ends long before the training kernel does.
-	const char* tail_env = getenv("NEUS2_TAIL_MERGED");   // =0: A/B switch (optimizer here, generation on the second stream); read per step
-	bool tail_deferred = !ctx->optimizer_done && pipelined && c.world_size == 1 && fused_zero && !ctx->use_delta && (tail_env ? atoi(tail_env) != 0 : true);
-	if (!ctx->optimizer_done && !tail_deferred) {
+	if (pipelined) CUDA_CHECK(cudaStreamWaitEvent(stream, ctx->ev_counts, 0));   // the optimizer clears the counters the read-back (second stream) copies: long done, but say so
+	if (!ctx->optimizer_done) {
 		ctx->fuse_zero_into_adam = fused_zero;
 		const int rc_opt = neus2_optimizer_step(ctx, stream_, c.loss_scale);   // testbed_nerf.cu:3503-3505
 		ctx->fuse_zero_into_adam = false;
@@ -996,7 +989,7 @@ int neus2_train_step_end(neus2_ctx* ctx, void* stream_, const uint32_t* counts_g
 	}   // else: gradients / accumulators / counters were cleared by the Adam kernel, the per-ray loss arrays are cleared on the aux stream below
 	ctx->scratch_zeroed = true;
 	if (pipelined) {
-		if (!tail_deferred) stage_end(ctx, ST_STEP, stream);
+		stage_end(ctx, ST_STEP, stream);
 		CUDA_CHECK(cudaEventSynchronize(ctx->ev_counts));      // recorded right after the loss kernel: the backward pass is still running
 		stage_collect(ctx, ctx->ev_set ^ 1);                   // the previous step's events have all completed by now
 	} else {
@@ -1038,38 +1031,17 @@ int neus2_train_step_end(neus2_ctx* ctx, void* stream_, const uint32_t* counts_g
 			// other counter buffer; the sample buffers themselves were last read by this step's loss kernel, long done.
 			plan_step(ctx, ctx->step_rank, ctx->step_world, ctx->prefetch_plan);
 			uint32_t* next_counters = ctx->counters_buf[ctx->counters_cur ^ 1];
-			if (tail_deferred) {
-				// ... or rather on the main stream, inside the optimizer's kernel (see above).  The other counter buffer was cleared by the previous
-				// step's optimizer unless a prefetch into it was abandoned since.
-				if (!ctx->counters_clean[ctx->counters_cur ^ 1]) CUDA_CHECK(cudaMemsetAsync(next_counters, 0, 8 * sizeof(uint32_t), stream));
-				const GenArgs ga = tail_gen_args(ctx, ctx->prefetch_plan, next_counters);
-				ctx->tail_gen = &ga; ctx->fuse_zero_into_adam = true;
-				const int rc_tail = neus2_optimizer_step(ctx, stream_, c.loss_scale);
-				ctx->tail_gen = nullptr; ctx->fuse_zero_into_adam = false;
-				CHECK(rc_tail);
-				tail_deferred = false;
-				stage_end(ctx, ST_STEP, stream);
-				ctx->prefetched = true; ctx->prefetch_epoch = ctx->state_epoch;
-			} else {
 			static int gen_after_fwdbwd = -1;   // NEUS2_GEN_AFTER_FWDBWD=1/0 overrides the compile-time choice (A/B switch)
 			if (gen_after_fwdbwd < 0) { const char* e = getenv("NEUS2_GEN_AFTER_FWDBWD"); gen_after_fwdbwd = e ? atoi(e) : NEUS2_GEN_AFTER_FWDBWD; }
 			CUDA_CHECK(cudaStreamWaitEvent(ctx->aux_stream, gen_after_fwdbwd ? ctx->ev_fwdbwd_done : ctx->ev_counts, 0));
 			CUDA_CHECK(cudaMemsetAsync(next_counters, 0, 8 * sizeof(uint32_t), ctx->aux_stream));
 			stage_begin_set(ctx, ctx->ev_set ^ 1, ST_GEN, ctx->aux_stream);
-			CHECK(launch_gen(ctx, ctx->aux_stream, ctx->prefetch_plan, next_counters, /*fused=*/false));   // beside the optimizer: the three-kernel form leaves it more of every SM
+			CHECK(launch_gen(ctx, ctx->aux_stream, ctx->prefetch_plan, next_counters));
 			stage_end_set(ctx, ctx->ev_set ^ 1, ST_GEN, ctx->aux_stream);
 			CUDA_CHECK(cudaEventRecord(ctx->ev_gen_done, ctx->aux_stream));
 			ctx->aux_pending = true;
 			ctx->prefetched = true; ctx->prefetch_epoch = ctx->state_epoch;
-			}
 		}
-	}
-	if (tail_deferred) {   // no generation to carry (occupancy refresh due, or an empty step): the optimizer on its own
-		ctx->fuse_zero_into_adam = true;
-		const int rc_opt = neus2_optimizer_step(ctx, stream_, c.loss_scale);
-		ctx->fuse_zero_into_adam = false;
-		CHECK(rc_opt);
-		stage_end(ctx, ST_STEP, stream);
 	}
 	if (fused_zero) {
 		// The per-ray loss arrays were last read by the loss-scalar reduction right behind the loss kernel.  They are cleared on the aux

@@ -28,8 +28,8 @@ static constexpr int FR_SMEM = WeightSmem::FWD_END * 2 + FR_WARPS * WarpSlab::FW
 __global__ void __launch_bounds__(FR_WARPS * 32, 2)
 k_network_forward_rays(GridMeta gm, ParamLayout pl, const __half* __restrict__ params, float sdf_bias, float cos_anneal_ratio,
                        const uint32_t* __restrict__ n_kept_ptr, const uint32_t* __restrict__ longest_ptr, const uint32_t* __restrict__ numsteps,
-                       const float* __restrict__ coords, uint32_t max_samples, __half* __restrict__ out, uint32_t* __restrict__ ray_done,
-                       uint32_t* __restrict__ work_counter /* [0] next item, [1] samples evaluated */) {
+                       const float* __restrict__ coords, uint32_t max_samples, __half* __restrict__ out, float4* __restrict__ composite_in,
+                       uint32_t* __restrict__ ray_done, uint32_t* __restrict__ work_counter /* [0] next item, [1] samples evaluated */) {
 	extern __shared__ __align__(16) unsigned char smem[];
 	__half* sw = reinterpret_cast<__half*>(smem);
 	stage_weights(sw, params, pl, false, threadIdx.x, blockDim.x);
@@ -82,12 +82,22 @@ k_network_forward_rays(GridMeta gm, ParamLayout pl, const __half* __restrict__ p
 				const float dv[3] = {__half2float(sOUT[8]) * 2.0f - 1.0f, __half2float(sOUT[9]) * 2.0f - 1.0f, __half2float(sOUT[10]) * 2.0f - 1.0f};
 				normalize3(dv, dir);
 			}
-			float alpha = 0.f;
-			if (lane < (int)n_valid) alpha = eval_sample(sOUT + lane * 16, sCoord + lane * 7, dir, cos_anneal_ratio).alpha;
-			for (uint32_t k = 0; k < n_valid; ++k) T *= (1.f - __shfl_sync(0xffffffffu, alpha, (int)k));   // T *= (1 - alpha), sample order (:1626)
+			float keep = 1.f;   // 1 - alpha of this lane's sample
+			if (lane < (int)n_valid) {
+				const SampleEval e = eval_sample(sOUT + lane * 16, sCoord + lane * 7, dir, cos_anneal_ratio);
+				keep = 1.f - e.alpha;
+				// what the loss's compositing pass consumes per sample -- the very bits it would compute itself from the row just stored (same
+				// function, same inputs, this file is compiled without FMA contraction like loss.cu): it then only replays its recurrences
+				if (composite_in) composite_in[(size_t)base + s0 + lane] = make_float4(e.alpha, e.rgb[0], e.rgb[1], e.rgb[2]);
+			}
+			// T *= product of the tile's (1 - alpha) (:1626), as a tree: this segment-local T only has to BOUND the loss's own (serially
+			// multiplied) transmittance from above, which the factor 0.5 below guarantees against any difference in rounding
+			#pragma unroll
+			for (int o = 8; o > 0; o >>= 1) keep *= __shfl_xor_sync(0xffffffffu, keep, o);
+			T *= __shfl_sync(0xffffffffu, keep, 0);
 			__syncwarp();
 			// the loss breaks BEFORE a sample once its transmittance (<= this segment-local product) is below 1e-4, and T never grows:
-			// nothing behind this tile is read.  The factor 0.5 is slack against any last-ulp difference between the two evaluations.
+			// nothing behind this tile is read.
 			if (T < EPSILON * 0.5f) { if (lane == 0) atomicMin(ray_done + ray, seg); break; }   // lowest terminating segment: only later ones may be skipped
 		}
 	}
@@ -96,14 +106,14 @@ k_network_forward_rays(GridMeta gm, ParamLayout pl, const __half* __restrict__ p
 
 int launch_network_forward_rays(cudaStream_t stream, const GridMeta& gm, const ParamLayout& pl, const __half* params, float sdf_bias, float cos_anneal_ratio,
                                 const uint32_t* n_kept_ptr, const uint32_t* longest_ptr, const uint32_t* numsteps, const float* coords, uint32_t max_samples,
-                                uint32_t n_rays_max, __half* out, uint32_t* ray_done, uint32_t* work_counter) {
+                                uint32_t n_rays_max, __half* out, float4* composite_in, uint32_t* ray_done, uint32_t* work_counter) {
 	static bool attr[NEUS_MAX_DEVICES] = {};
 	if (ensure_dynamic_smem(k_network_forward_rays, FR_SMEM, attr)) return -1;
 	// Preconditions (no launches of their own): work_counter[0..1] are zero -- they are two of the step's counters, cleared with them -- and
 	// ray_done[slot] = 0xffffffff ("no segment has terminated the ray") for every kept ray, written by sample generation (k_rays_emit).
 	(void)n_rays_max;
 	k_network_forward_rays<<<device_sm_count() * 2, FR_WARPS * 32, FR_SMEM, stream>>>(gm, pl, params, sdf_bias, cos_anneal_ratio, n_kept_ptr, longest_ptr, numsteps,
-	                                                                                 coords, max_samples, out, ray_done, work_counter);
+	                                                                                 coords, max_samples, out, composite_in, ray_done, work_counter);
 	COUNT_LAUNCH(1);
 	CUDA_CHECK(cudaGetLastError());
 	return 0;

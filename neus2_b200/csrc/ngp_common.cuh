@@ -89,7 +89,7 @@ __device__ __forceinline__ float distance_to_next_voxel(const float pos[3], cons
 	float ty = (floorf(p[1] + 0.5f + 0.5f * signf1(dir[1])) - p[1]) * idir[1];
 	float tz = (floorf(p[2] + 0.5f + 0.5f * signf1(dir[2])) - p[2]) * idir[2];
 	float t = fminf(fminf(tx, ty), tz);
-	return fmaxf(t / (float)res, 0.0f);
+	return fmaxf(t * (1.0f / (float)res), 0.0f);   // res is a power of two (128 >> mip): the product is the quotient, bit for bit, without the IEEE division sequence
 }
 __device__ __forceinline__ float advance_to_next_voxel(float t, float cone_angle, const float pos[3], const float dir[3], const float idir[3], uint32_t res) {
 	float t_target = t + distance_to_next_voxel(pos, dir, idir, res);

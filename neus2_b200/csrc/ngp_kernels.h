@@ -13,46 +13,29 @@ struct LossParamsDev {
 	float cos_anneal_ratio;
 };
 
-// everything one launch of sample generation reads and writes (gen_tile, sampling_tile.cuh)
-struct GenArgs {
-	uint32_t n_rays, ray_offset, ray_stride, n_rays_global, n_rays_total;
-	Pcg32 rng; DatasetDev ds; Aabb bb; GlobalMove gmv;
-	const uint8_t* bitfield; int snap; float cone_angle; uint32_t max_samples;
-	LookbackScan scan_samples, scan_rays;
-	uint32_t* numsteps_all; uint32_t* ray_indices; float* rays; uint32_t* numsteps; float* coords; uint32_t* ray_done; uint32_t* counters;
-};
-
 int launch_generate_training_samples(cudaStream_t stream, uint32_t n_rays, uint32_t ray_offset, uint32_t ray_stride, uint32_t n_rays_global, uint32_t n_rays_total, const uint64_t rng_state[2], const DatasetDev& ds,
                                      const Aabb& bb, const GlobalMove& gmv, const uint8_t* bitfield, int snap, float cone_angle, uint32_t max_samples,
                                      uint32_t* numsteps_all, uint32_t* base, uint32_t* slot, uint32_t* ray_indices, float* rays, uint32_t* numsteps,
                                      float* coords, uint32_t* counters, void* windows, uint32_t* n_windows, float* ray_setup,
-                                     uint32_t* ray_done /* nullable: per kept ray slot, set to 0xffffffff for the early-terminating first pass */,
-                                     // non-null: count, scans and emit in ONE kernel (lookback.cuh); desc: 2 x ceil(n_rays / 8) 64-bit words, never cleared
-                                     // (the two halves move with n_rays: the epoch must be new for every launch); tickets: two zeroed words
-                                     unsigned long long* lookback_desc, uint32_t* lookback_tickets, uint32_t lookback_epoch);
+                                     uint32_t* ray_done /* nullable: per kept ray slot, set to 0xffffffff for the early-terminating first pass */);
 size_t sampling_window_bytes_per_ray();
 
 // counters: [0] = kept rays (device, from sample generation), out_counter = total compacted samples (un-clamped)
+// Scratch of the by-samples loss (loss.cu): per marched sample the compositing state behind it, per compacted slot its sample and ray, per ray a 48-byte record
+struct LossScratch { float4* prefix4; float* prefix1; uint32_t* slot_sample; uint32_t* slot_ray; float* ray_rec; };
 int launch_compute_loss(cudaStream_t stream, uint32_t n_rays_local, uint32_t n_rays /* global: image mapping + normalisers */, uint32_t n_rays_total, const uint64_t rng_state[2], const DatasetDev& ds, const Aabb& bb,
                         const GlobalMove& gmv, const LossParamsDev& lp, uint32_t max_samples_compacted, const uint32_t* n_kept_ptr,
                         const __half* network_output, const uint32_t* ray_indices, const float* rays, uint32_t* numsteps, const float* coords,
                         float* ray_tmp, uint32_t* scan_tmp, float* coords_compacted, __half* dloss_doutput,
                         float* loss_output, float* ek_loss_output, float* mask_loss_output, uint32_t* out_counter,
-                        // non-null: both passes and the compaction scan in ONE kernel (lookback.cuh); desc: 64-bit word per 8 rays, never cleared;
-                        // ticket: one zeroed word; epoch: 1 .. 2^30 - 1, different from the previous launch's on the same desc
-                        unsigned long long* lookback_desc, uint32_t* lookback_ticket, uint32_t lookback_epoch);
+                        // all non-null: the loss by samples (k_loss_rays + k_loss_samples).  composite_in: {alpha, r, g, b} per sample as stored by
+                        // launch_network_forward_rays; lookback desc: 64-bit word per 8 rays, never cleared; ticket: one zeroed word; epoch: 1 .. 2^30 - 1,
+                        // different from the previous launch's on the same desc.  Otherwise: composite / scan / gradient kernels, one warp per ray.
+                        const float4* composite_in, const LossScratch* scratch, unsigned long long* lookback_desc, uint32_t* lookback_ticket, uint32_t lookback_epoch);
 
 int launch_adam_ema(cudaStream_t stream, uint64_t n, uint64_t n_matrix, float loss_scale, float lr, float beta1, float beta2, float eps, float l2_reg,
                     float ema_decay, uint32_t ema_step, float* grads, float* master, __half* params, float* m1, float* m2, uint32_t* steps, __half* ema,
-                    float* bias_table, uint32_t bias_table_size, int zero_grads, uint32_t* const zero_ptrs[3], const uint32_t zero_counts[3],
-                    // non-null: the step-tail kernel -- this update AND the next step's sample generation in one persistent launch;
-                    // tail_state: tail_state_bytes() of zeroed device memory, kept between launches
-                    const GenArgs* tail_gen = nullptr, void* tail_state = nullptr);
-size_t tail_state_bytes();
-GenArgs make_gen_args(uint32_t n_rays, uint32_t ray_offset, uint32_t ray_stride, uint32_t n_rays_global, uint32_t n_rays_total, const uint64_t rng_state[2], const DatasetDev& ds,
-                             const Aabb& bb, const GlobalMove& gmv, const uint8_t* bitfield, int snap, float cone_angle, uint32_t max_samples, uint32_t* numsteps_all,
-                             uint32_t* ray_indices, float* rays, uint32_t* numsteps, float* coords, uint32_t* counters, uint32_t* ray_done,
-                             unsigned long long* lookback_desc, uint32_t* lookback_tickets, uint32_t lookback_epoch);
+                    float* bias_table, uint32_t bias_table_size, int zero_grads, uint32_t* const zero_ptrs[3], const uint32_t zero_counts[3]);
 // table[k] = sqrt(1 - beta2^k) / (1 - beta1^k) for k in [first, last] (api.cu: compiled with FMA contraction like the reference's adam_step)
 int launch_adam_bias_table(cudaStream_t stream, float beta1, float beta2, uint32_t first, uint32_t last, float* bias_table, uint32_t bias_table_size);
 
@@ -120,4 +103,5 @@ int launch_mesh_extract_colors(cudaStream_t stream, uint32_t n_verts, const __ha
 // first network pass of the training step, ray by ray with the loss kernel's early termination (forward_rays.cu)
 int launch_network_forward_rays(cudaStream_t stream, const GridMeta& gm, const ParamLayout& pl, const __half* params, float sdf_bias, float cos_anneal_ratio,
                                 const uint32_t* n_kept_ptr, const uint32_t* longest_ptr, const uint32_t* numsteps, const float* coords, uint32_t max_samples,
-                                uint32_t n_rays_max, __half* out, uint32_t* ray_done, uint32_t* work_counter);
+                                uint32_t n_rays_max, __half* out, float4* composite_in /* nullable: {alpha, r, g, b} per evaluated sample, for launch_compute_loss */,
+                                uint32_t* ray_done, uint32_t* work_counter);

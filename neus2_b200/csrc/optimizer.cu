@@ -9,7 +9,20 @@
 #include "ngp_common.cuh"
 #include "ngp_kernels.h"
 #include "peer_sync.cuh"
-#include "sampling_tile.cuh"
+
+// Optimizer state (fp32 master copy, both moments, step counters) and the EMA copy are touched once per step and by nobody else.  With
+// ADAM_STREAM_HINTS=1 their loads and stores carry the streaming hint (ld / st.global.cs, evict-first in L2), so that the ~250 MB they amount to
+// do not push the fp16 parameters and the gradient buffer -- which the next step's network kernels gather from and reduce into -- out of the L2.
+#ifndef ADAM_STREAM_HINTS
+#define ADAM_STREAM_HINTS 0   // measured (same box, profiles/r02_bench_n1_adam_hints.json / _no_hints.json): first pass 2.7 us faster, optimizer 3.6 us slower, step equal
+#endif
+#if ADAM_STREAM_HINTS
+#define LD_STATE(p) __ldcs(p)
+#define ST_STATE(p, v) __stcs(p, v)
+#else
+#define LD_STATE(p) (*(p))
+#define ST_STATE(p, v) (*(p) = (v))
+#endif
 
 struct AdamHyper { float loss_scale, lr, beta1, beta2, eps, l2_reg, ema_decay, ema_debias_old, ema_debias_new;
                    uint32_t cur_step; const float* bias_table; uint32_t bias_table_size;
@@ -67,10 +80,10 @@ __device__ __forceinline__ void adam_ema_quad(uint64_t q, uint64_t n_matrix4, co
 	__half* ph = reinterpret_cast<__half*>(&pw);
 	const float g[4] = {g4.x, g4.y, g4.z, g4.w};
 	if ((is_matrix || g4.x != 0.f || g4.y != 0.f || g4.z != 0.f || g4.w != 0.f)) {
-		float4 w4 = reinterpret_cast<const float4*>(B.master)[q];
-		float4 a4 = reinterpret_cast<const float4*>(B.m1)[q];
-		float4 b4 = reinterpret_cast<const float4*>(B.m2)[q];
-		uint4 s4 = reinterpret_cast<const uint4*>(B.steps)[q];
+		float4 w4 = LD_STATE(reinterpret_cast<const float4*>(B.master) + q);
+		float4 a4 = LD_STATE(reinterpret_cast<const float4*>(B.m1) + q);
+		float4 b4 = LD_STATE(reinterpret_cast<const float4*>(B.m2) + q);
+		uint4 s4 = LD_STATE(reinterpret_cast<const uint4*>(B.steps) + q);
 		float* w = reinterpret_cast<float*>(&w4); float* a = reinterpret_cast<float*>(&a4); float* b = reinterpret_cast<float*>(&b4);
 		uint32_t* st = reinterpret_cast<uint32_t*>(&s4);
 		bool any = false;
@@ -81,21 +94,21 @@ __device__ __forceinline__ void adam_ema_quad(uint64_t q, uint64_t n_matrix4, co
 			any |= touched;
 		}
 		if (any) {
-			reinterpret_cast<float4*>(B.master)[q] = w4;
-			reinterpret_cast<float4*>(B.m1)[q] = a4;
-			reinterpret_cast<float4*>(B.m2)[q] = b4;
-			reinterpret_cast<uint4*>(B.steps)[q] = s4;
+			ST_STATE(reinterpret_cast<float4*>(B.master) + q, w4);
+			ST_STATE(reinterpret_cast<float4*>(B.m1) + q, a4);
+			ST_STATE(reinterpret_cast<float4*>(B.m2) + q, b4);
+			ST_STATE(reinterpret_cast<uint4*>(B.steps) + q, s4);
 			reinterpret_cast<uint2*>(B.params)[q] = pw;
 		}
 	}
-	uint2 ew = reinterpret_cast<const uint2*>(B.ema)[q];
+	uint2 ew = LD_STATE(reinterpret_cast<const uint2*>(B.ema) + q);
 	__half* eh = reinterpret_cast<__half*>(&ew);
 	#pragma unroll
 	for (int k = 0; k < 4; ++k) {
 		const float filtered = fmaf(__half2float(eh[k]) * h.ema_decay, h.ema_debias_old, __half2float(ph[k]) * (1 - h.ema_decay)) * h.ema_debias_new;
 		eh[k] = __float2half_rn(filtered);
 	}
-	reinterpret_cast<uint2*>(B.ema)[q] = ew;
+	ST_STATE(reinterpret_cast<uint2*>(B.ema) + q, ew);
 }
 
 __global__ void __launch_bounds__(256)
@@ -108,67 +121,9 @@ k_adam_ema(uint64_t n4, uint64_t n_matrix4, AdamHyper h, AdamBuffers B, AdamZero
 	if (q < n4) adam_ema_quad(q, n_matrix4, h, B);
 }
 
-// ------------------------------------------------------------------------------------------------------------------------
-// The tail of a pipelined single-GPU step as ONE persistent kernel: this step's Adam + EMA update and the NEXT step's sample generation
-// (gen_tile, sampling_tile.cuh) side by side on every SM.  As two kernels on two streams they do not share the GPU: whichever kernel's
-// blocks are queued first fill every SM, the other one's wait (measured: generation 108 us, then the optimizer 85 us, back to back), although
-// one is DRAM-bound and the other issue / latency-bound.  Here the grid is exactly what the GPU holds (8 blocks of 256 threads per SM) and a
-// block picks its role from the order in which it arrives ON ITS SM (even: generation, odd: optimizer), so every SM runs four blocks of each
-// for the whole kernel; generation tiles and optimizer chunks are handed out by tickets.  The block that finishes last resets the tickets.
-// ------------------------------------------------------------------------------------------------------------------------
-#define TAIL_MAX_SMS 256
-struct TailState { uint32_t sm_arrivals[TAIL_MAX_SMS]; uint32_t gen_ticket, adam_ticket, done; };
-
-#ifndef TAIL_MIN_BLOCKS
-#define TAIL_MIN_BLOCKS 5   // resident blocks per SM the register budget is cut for (4: 56 registers, 5: 48, 6: 40 with a few spilled words)
-#endif
-__global__ void __launch_bounds__(256, TAIL_MIN_BLOCKS)
-k_tail_adam_gen(uint64_t n4, uint64_t n_matrix4, AdamHyper h, AdamBuffers B, AdamZero z, GenArgs g, uint32_t n_gen_tiles, uint32_t gen_share, uint32_t period,
-                TailState* __restrict__ ts) {
-	__shared__ GenTileSmem s_gen;
-	__shared__ uint32_t s_role, s_item;
-	if (threadIdx.x == 0) {
-		uint32_t smid;
-		asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-		s_role = (atomicAdd(&ts->sm_arrivals[smid % TAIL_MAX_SMS], 1u) % period) < gen_share ? 0u : 1u;   // of every `period` blocks arriving on an SM, `gen_share` generate
-	}
-	__syncthreads();
-	const bool prefer_gen = s_role == 0u;
-	const uint32_t n_chunks = (uint32_t)((n4 + 255) / 256);
-	bool gen_left = true, adam_left = true;
-	while (gen_left || adam_left) {   // own kind of work first; when it runs out, help with the other kind
-		const bool do_gen = prefer_gen ? gen_left : !adam_left;
-		__syncthreads();
-		if (threadIdx.x == 0) s_item = atomicAdd(do_gen ? &ts->gen_ticket : &ts->adam_ticket, 1u);
-		__syncthreads();
-		const uint32_t item = s_item;
-		if (do_gen) {
-			if (item >= n_gen_tiles) { gen_left = false; continue; }
-			gen_tile(g, item, n_gen_tiles, s_gen);
-		} else {
-			if (item >= n_chunks) { adam_left = false; continue; }
-			if (h.zero_grads && item == 0) {
-				#pragma unroll
-				for (int a = 0; a < 3; ++a) for (uint32_t i = threadIdx.x; i < z.n[a]; i += blockDim.x) z.p[a][i] = 0u;
-			}
-			const uint64_t q = (uint64_t)item * 256 + threadIdx.x;
-			if (q < n4) adam_ema_quad(q, n_matrix4, h, B);
-		}
-	}
-	__syncthreads();
-	if (threadIdx.x == 0) {   // the block that finishes last puts the tickets and the arrival counts back (`done` wraps to 0 by itself)
-		__threadfence();
-		if (atomicInc(&ts->done, gridDim.x - 1) == gridDim.x - 1) {
-			ts->gen_ticket = 0u; ts->adam_ticket = 0u;
-			for (int i = 0; i < TAIL_MAX_SMS; ++i) ts->sm_arrivals[i] = 0u;
-		}
-	}
-}
-
 int launch_adam_ema(cudaStream_t stream, uint64_t n, uint64_t n_matrix, float loss_scale, float lr, float beta1, float beta2, float eps, float l2_reg,
                     float ema_decay, uint32_t ema_step, float* grads, float* master, __half* params, float* m1, float* m2, uint32_t* steps, __half* ema,
-                    float* bias_table, uint32_t bias_table_size, int zero_grads, uint32_t* const zero_ptrs[3], const uint32_t zero_counts[3],
-                    const GenArgs* tail_gen, void* tail_state) {
+                    float* bias_table, uint32_t bias_table_size, int zero_grads, uint32_t* const zero_ptrs[3], const uint32_t zero_counts[3]) {
 	const float ema_debias_old = 1 - (float)pow((double)ema_decay, (double)(ema_step - 1));
 	const float ema_debias_new = 1.0f / (1 - (float)pow((double)ema_decay, (double)ema_step));
 	if (n % 4 != 0 || n_matrix % 4 != 0) { neus_set_error("parameter counts must be multiples of 4", __FILE__, __LINE__); return -1; }
@@ -178,21 +133,6 @@ int launch_adam_ema(cudaStream_t stream, uint64_t n, uint64_t n_matrix, float lo
 	const uint64_t n4 = n / 4;
 	const uint32_t blocks = (uint32_t)((n4 + 255) / 256);
 	const AdamBuffers bufs = {grads, master, params, m1, m2, steps, ema};
-	if (tail_gen) {
-		if (!tail_state) { neus_set_error("the step-tail kernel needs its state block", __FILE__, __LINE__); return -1; }
-		static int per_sm[NEUS_MAX_DEVICES] = {};
-		int dev = 0; CUDA_CHECK(cudaGetDevice(&dev));
-		if (!per_sm[dev]) CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[dev], k_tail_adam_gen, 256, 0));
-		// of the blocks resident on an SM, how many generate samples (the rest run the optimizer); NEUS2_TAIL_GEN_SHARE overrides (tuning)
-		const char* e = getenv("NEUS2_TAIL_GEN_SHARE");
-		const uint32_t period = (uint32_t)std::max(per_sm[dev], 2);
-		const uint32_t gen_share = std::min(period - 1u, (uint32_t)std::max(1, e ? atoi(e) : (int)(period + 1) / 2));
-		const uint32_t n_tiles = (tail_gen->n_rays + GF_RAYS - 1) / GF_RAYS;
-		k_tail_adam_gen<<<device_sm_count() * period, 256, 0, stream>>>(n4, n_matrix / 4, h, bufs, z, *tail_gen, n_tiles, gen_share, period, (TailState*)tail_state);
-		COUNT_LAUNCH(1);
-		CUDA_CHECK(cudaGetLastError());
-		return 0;
-	}
 	k_adam_ema<<<blocks, 256, 0, stream>>>(n4, n_matrix / 4, h, bufs, z);
 	COUNT_LAUNCH(1);
 	CUDA_CHECK(cudaGetLastError());
@@ -256,10 +196,10 @@ __device__ __forceinline__ void adam_ema_p2p_quad(uint64_t q, uint64_t n_matrix4
 	__half* ph = reinterpret_cast<__half*>(&pw);
 	const float g[4] = {g4.x, g4.y, g4.z, g4.w};
 	if ((is_matrix || g4.x != 0.f || g4.y != 0.f || g4.z != 0.f || g4.w != 0.f)) {
-		float4 w4 = reinterpret_cast<const float4*>(master)[q];
-		float4 a4 = reinterpret_cast<const float4*>(m1)[q];
-		float4 b4 = reinterpret_cast<const float4*>(m2)[q];
-		uint4 s4 = reinterpret_cast<const uint4*>(steps)[q];
+		float4 w4 = LD_STATE(reinterpret_cast<const float4*>(master) + q);
+		float4 a4 = LD_STATE(reinterpret_cast<const float4*>(m1) + q);
+		float4 b4 = LD_STATE(reinterpret_cast<const float4*>(m2) + q);
+		uint4 s4 = LD_STATE(reinterpret_cast<const uint4*>(steps) + q);
 		float* w = reinterpret_cast<float*>(&w4); float* a = reinterpret_cast<float*>(&a4); float* b = reinterpret_cast<float*>(&b4);
 		uint32_t* st = reinterpret_cast<uint32_t*>(&s4);
 		bool any = false;
@@ -270,10 +210,10 @@ __device__ __forceinline__ void adam_ema_p2p_quad(uint64_t q, uint64_t n_matrix4
 			any |= touched;
 		}
 		if (any) {
-			reinterpret_cast<float4*>(master)[q] = w4;
-			reinterpret_cast<float4*>(m1)[q] = a4;
-			reinterpret_cast<float4*>(m2)[q] = b4;
-			reinterpret_cast<uint4*>(steps)[q] = s4;
+			ST_STATE(reinterpret_cast<float4*>(master) + q, w4);
+			ST_STATE(reinterpret_cast<float4*>(m1) + q, a4);
+			ST_STATE(reinterpret_cast<float4*>(m2) + q, b4);
+			ST_STATE(reinterpret_cast<uint4*>(steps) + q, s4);
 			#pragma unroll
 			for (int r = 0; r < NEUS2_MAX_PEERS; ++r) if (r < world) reinterpret_cast<uint2*>(peers.params[r])[q] = pw;
 		}
@@ -319,5 +259,3 @@ int launch_adam_ema_p2p(cudaStream_t stream, uint64_t n, uint64_t n_matrix, uint
 // belongs to rank b % world.  (Contiguous slices gave the rank holding the finest hash-grid levels -- touched by every sample -- up to 25 %
 // more Adam work than the rank holding the sparsely touched coarse hashed levels, and the barrier behind the optimizer waits for the slowest.)
 uint32_t optimizer_block_owner(uint64_t param_index, uint32_t world) { return (uint32_t)((param_index / (4ull * OPTIMIZER_BLOCK_QUADS)) % world); }
-
-size_t tail_state_bytes() { return sizeof(TailState); }

@@ -215,8 +215,9 @@ def test_step_end_and_training_progress(stepped):
 def test_early_termination_changes_nothing_downstream(variant, monkeypatch):
     """Two contexts, same seed / data / parameters, first network pass with and without the early cut: every buffer the loss
     writes is bit-identical step after step (sample counts, compacted coordinates, dL/doutput, per-ray losses), and the first
-    pass evaluates far fewer samples.  Variant "fused_loss": the same comparison between the loss as ONE kernel (default) and as
-    composite / scan / gradient kernels (NEUS2_LOSS_FUSED=0, read per step), plus the eikonal / mask terms and the loss scalars."""
+    pass evaluates far fewer samples.  Variant "fused_loss": the same comparison between the loss by samples (default: k_loss_rays replays
+    the recurrences over what the first pass stored, k_loss_samples does the per-sample work one thread per compacted sample) and the
+    one-warp-per-ray composite / scan / gradient kernels (NEUS2_LOSS_BY_SAMPLES=0, read per step), incl. the eikonal / mask terms."""
     import torch
     import neus2_b200 as N
     from neus2_b200 import synthetic
@@ -237,7 +238,7 @@ def test_early_termination_changes_nothing_downstream(variant, monkeypatch):
         for step in range(6):
             outs = []
             for c, env in zip(ctxs, fused_env):
-                monkeypatch.setenv("NEUS2_LOSS_FUSED", env)
+                monkeypatch.setenv("NEUS2_LOSS_BY_SAMPLES", env)
                 c.train_step_begin()
                 torch.cuda.synchronize()
                 cnt = _np(c.debug_buffer("counters", "<u4", (8,))).copy()
@@ -332,75 +333,3 @@ def test_pipelined_step_generates_the_same_samples():
     finally:
         c.close()
 
-
-def test_merged_tail_equals_separate_kernels(monkeypatch):
-    """The tail of a pipelined single-GPU step is ONE kernel (this step's Adam + EMA and the next step's sample generation side by
-    side, k_tail_adam_gen); NEUS2_TAIL_MERGED=0 launches the optimizer kernel and, on the second stream, the generation kernels instead.
-    Two contexts on the same trajectory, one of each kind, fed the same gradients: master / fp16 / EMA parameters, both moments and the
-    per-parameter step counters are bit-identical after every step, and so are the samples the next step starts from."""
-    import torch
-    import neus2_b200 as N
-    from neus2_b200 import synthetic
-    data = synthetic.render_sphere_views(n_views=6, width=128, height=96, seed=5)
-    ctxs = []
-    for _ in range(2):
-        c = N.Context(N.default_config(batch_size=B, mask_loss_weight=0.1))
-        c.init_params()
-        c.set_dataset(data["pixels"], data["focal"], data["principal"], data["xforms"])
-        ctxs.append(c)
-    try:
-        for c in ctxs:                      # a few ordinary steps (occupancy refresh every step), then jump to where refreshes are rare
-            for _ in range(3):
-                c.train_step()
-        st = ctxs[0].get_state()
-        for c in ctxs:
-            c.set_state(training_step=97, rays_per_batch=st["rays_per_batch"], n_rays_total=st["n_rays_total"], measured_before=st["measured_before"])
-
-        def sync_from_first():
-            for t_dst, t_src in zip(ctxs[1].buffers(), ctxs[0].buffers()):
-                t_dst.copy_(t_src)
-            for t_dst, t_src in zip(ctxs[1].optimizer_buffers()[:3], ctxs[0].optimizer_buffers()[:3]):
-                t_dst.copy_(t_src)
-            ctxs[1].debug_buffer("density_grid", "<f4", (G3,)).copy_(ctxs[0].debug_buffer("density_grid", "<f4", (G3,)))
-            ctxs[1].set_bitfield(_np(ctxs[0].debug_buffer("bitfield", "|u1", (G3 // 8 * 8,))))
-        sync_from_first()                   # from here on both see the same parameters, optimizer state and occupancy grid: nothing is copied again but the gradients
-        merged_steps = 0
-        for step in range(10):
-            outs = []
-            for c, env in zip(ctxs, ("1", "0")):
-                monkeypatch.setenv("NEUS2_TAIL_MERGED", env)
-                c.train_step_begin()
-                torch.cuda.synchronize()
-                cnt = _np(c.debug_buffer("counters", "<u4", (8,))).copy()
-                R = c.get_state()["rays_per_batch"]
-                k, m = int(cnt[0]), min(int(cnt[2]), B)
-                outs.append(dict(cnt=cnt[:3].copy(), numsteps=_np(c.debug_buffer("numsteps", "<u4", (R, 2)))[:k].copy(),
-                                 idx=_np(c.debug_buffer("ray_indices", "<u4", (R,)))[:k].copy(), rays=_np(c.debug_buffer("rays", "<f4", (R, 6)))[:k].copy(),
-                                 cc=_np(c.debug_buffer("coords_compacted", "<f4", (B, 7)))[:m].copy()))
-            a, b = outs
-            assert np.array_equal(a["cnt"], b["cnt"]), (step, a["cnt"], b["cnt"])
-            assert int(a["cnt"][0]) > 100 and int(a["cnt"][2]) > 1000
-            for key in ("numsteps", "idx"):
-                assert np.array_equal(a[key], b[key]), (step, key)
-            assert np.array_equal(a["rays"].view(np.uint32), b["rays"].view(np.uint32)) and np.array_equal(a["cc"].view(np.uint32), b["cc"].view(np.uint32))
-            ctxs[1].buffers()[3].copy_(ctxs[0].buffers()[3])       # the optimizer's input: gradients differ by the order of fp32 atomics only; make them equal
-            torch.cuda.synchronize()
-            stats, launches = [], []
-            for c, env in zip(ctxs, ("1", "0")):
-                monkeypatch.setenv("NEUS2_TAIL_MERGED", env)
-                l0 = c.launch_count()
-                stats.append(c.train_step_end())
-                torch.cuda.synchronize()
-                launches.append(c.launch_count() - l0)
-            assert stats[0].rays_per_batch_next == stats[1].rays_per_batch_next and stats[0].measured_batch_size == stats[1].measured_batch_size
-            if launches[0] < launches[1]:
-                merged_steps += 1                                   # one launch (optimizer + generation) against optimizer + count / scan / emit
-                assert launches[0] == 1, launches
-            for ta, tb in zip(ctxs[0].buffers(), ctxs[1].buffers()):             # master, fp16, EMA, (cleared) gradients
-                assert torch.equal(ta.view(torch.int32) if ta.dtype == torch.float32 else ta.view(torch.int16), tb.view(torch.int32) if tb.dtype == torch.float32 else tb.view(torch.int16))
-            for ta, tb in zip(ctxs[0].optimizer_buffers()[:3], ctxs[1].optimizer_buffers()[:3]):
-                assert torch.equal(ta.view(torch.int32), tb.view(torch.int32))
-        assert merged_steps >= 5, merged_steps
-    finally:
-        for c in ctxs:
-            c.close()
