@@ -64,7 +64,7 @@ struct neus2_ctx {
 	float *partials, *var_acc, *w1row0_acc, *scalar_tmp;
 	uint32_t* fwdbwd_done;      // CTA arrival counter of the training kernel (self-resetting)
 	// prefix sums across the blocks of one launch (lookback.cuh): descriptors (never cleared, validated by epoch), ticket counters, launch epoch
-	unsigned long long* lb_loss_desc; uint32_t* lb_tickets; uint32_t lb_epoch;
+	unsigned long long *lb_loss_desc, *lb_grid_desc; uint32_t* lb_tickets; uint32_t lb_epoch;   // tickets: [0] loss, [1] occupancy-grid samples
 	// the loss by samples (loss.cu): {alpha, r, g, b} per marched sample from the first pass, and the loss kernels' own scratch
 	float4* composite_in; LossScratch loss_ws;
 
@@ -427,7 +427,7 @@ int neus2_ctx_create(const neus2_config* cfg, int device, neus2_ctx** out) {
 		CDM(ctx->composite_in, S); CDM(ctx->loss_ws.prefix4, S); CDM(ctx->loss_ws.prefix1, S);
 		CDM(ctx->loss_ws.slot_sample, B); CDM(ctx->loss_ws.slot_ray, B); CDM(ctx->loss_ws.ray_rec, 12 * (size_t)R);
 	}
-	CDM(ctx->lb_loss_desc, (size_t)R / 8 + 2); CDM(ctx->lb_tickets, 4);
+	CDM(ctx->lb_loss_desc, (size_t)R / 8 + 2); CDM(ctx->lb_grid_desc, (size_t)NERF_GRIDSIZE * NERF_GRIDSIZE * NERF_GRIDSIZE / 256 + 2); CDM(ctx->lb_tickets, 4);
 	const size_t G3n = (size_t)NERF_GRIDSIZE * NERF_GRIDSIZE * NERF_GRIDSIZE;
 	CDM(ctx->density_grid, G3n * ctx->n_cascades); CDM(ctx->density_grid_tmp, G3n * ctx->n_cascades);
 	CDM(ctx->grid_positions, 3 * G3n * ctx->n_cascades); CDM(ctx->grid_indices, G3n * ctx->n_cascades); CDM(ctx->grid_density, G3n * ctx->n_cascades);
@@ -463,7 +463,7 @@ void neus2_ctx_destroy(neus2_ctx* ctx) {
 		ctx->coords_compacted, ctx->loss, ctx->ek_loss, ctx->mask_loss, ctx->mlp_out, ctx->dloss, ctx->so.dOUT, ctx->so.H2, ctx->so.dH2, ctx->so.H1, ctx->so.dH1,
 		ctx->so.CIN, ctx->so.dSO, ctx->so.H0, ctx->so.dH0, ctx->so.X0, ctx->so.dI, ctx->partials, ctx->var_acc, ctx->w1row0_acc, ctx->scalar_tmp, ctx->fwdbwd_done,
 		ctx->density_grid, ctx->density_grid_tmp, ctx->grid_positions, ctx->grid_indices, ctx->grid_density, ctx->bitfield, ctx->density_grid_mean,
-		ctx->d_xform, ctx->d_acc, ctx->d_master, ctx->d_m1, ctx->d_m2, ctx->d_steps, ctx->d_params, ctx->counters_buf[0], ctx->counters_buf[1], ctx->sync_block, ctx->sync_done, ctx->lb_loss_desc, ctx->lb_tickets, ctx->composite_in, ctx->loss_ws.prefix4, ctx->loss_ws.prefix1, ctx->loss_ws.slot_sample, ctx->loss_ws.slot_ray, ctx->loss_ws.ray_rec};
+		ctx->d_xform, ctx->d_acc, ctx->d_master, ctx->d_m1, ctx->d_m2, ctx->d_steps, ctx->d_params, ctx->counters_buf[0], ctx->counters_buf[1], ctx->sync_block, ctx->sync_done, ctx->lb_loss_desc, ctx->lb_grid_desc, ctx->lb_tickets, ctx->composite_in, ctx->loss_ws.prefix4, ctx->loss_ws.prefix1, ctx->loss_ws.slot_sample, ctx->loss_ws.slot_ray, ctx->loss_ws.ray_rec};
 	for (uint32_t r = 0; r < ctx->peer_world; ++r) if (r != ctx->peer_rank) {   // unmap the peers' buffers before this rank's own are freed
 		if (ctx->peer_grads[r]) cudaIpcCloseMemHandle(ctx->peer_grads[r]);
 		if (ctx->peer_params[r]) cudaIpcCloseMemHandle(ctx->peer_params[r]);
@@ -735,8 +735,11 @@ static int update_density_grid_on_stream(neus2_ctx* ctx, cudaStream_t stream, bo
 		CUDA_CHECK(cudaMemsetAsync(ctx->density_grid, 0, sizeof(float) * n_elements, stream));
 	}
 	uint64_t st[2] = {ctx->density_grid_rng.state, ctx->density_grid_rng.inc};
+	const char* ordered_env = getenv("NEUS2_GRID_SAMPLES_ORDERED");   // =0: A/B switch (uniform samples in the reference's sample order)
+	const bool ordered = ordered_env ? atoi(ordered_env) != 0 : true;
+	ctx->lb_epoch = ctx->lb_epoch % 0x3ffffffeu + 1u;
 	CHECK(launch_density_grid_samples(stream, n_uniform, st, ctx->density_grid_ema_step, ctx->aabb, ctx->density_grid, ctx->n_cascades, -0.01f,
-	                                  ctx->grid_positions, ctx->grid_indices));
+	                                  ctx->grid_positions, ctx->grid_indices, ordered ? ctx->lb_grid_desc : nullptr, ctx->lb_tickets + 1, ctx->lb_epoch));
 	ctx->density_grid_rng.advance();
 	st[0] = ctx->density_grid_rng.state;
 	CHECK(launch_density_grid_samples(stream, n_nonuniform, st, ctx->density_grid_ema_step, ctx->aabb, ctx->density_grid, ctx->n_cascades, 0.1f,

@@ -60,7 +60,10 @@ int launch_adam_ema_p2p(cudaStream_t stream, uint64_t n, uint64_t n_matrix, uint
                         uint32_t* done_counter = nullptr);
 
 int launch_density_grid_samples(cudaStream_t stream, uint32_t n, const uint64_t rng_state[2], uint32_t step, const Aabb& bb, const float* grid_in,
-                                uint32_t n_cascades, float thresh, float* positions, uint32_t* indices);
+                                uint32_t n_cascades, float thresh, float* positions, uint32_t* indices,
+                                // non-null: the uniform samples (thresh < 0) of a one-cascade grid are written in cell order (density_grid.cu); desc: 128^3 / 256
+                                // 64-bit words, never cleared; ticket: one zeroed word; epoch as for launch_compute_loss
+                                unsigned long long* lookback_desc = nullptr, uint32_t* lookback_ticket = nullptr, uint32_t lookback_epoch = 0);
 int launch_density_grid_splat_decay(cudaStream_t stream, uint32_t n_samples, const uint32_t* indices, const __half* density, uint32_t n_elements,
                                     float decay, float* grid_tmp, float* grid);
 int launch_density_grid_bitfield(cudaStream_t stream, const float* grid, uint32_t n_cascades_used, float* mean_tmp, uint8_t* bitfield);

@@ -66,8 +66,12 @@ def test_density_grid_stage(stepped):
     pos, idx = O.generate_grid_samples(G3, dg_rng, 1, grid0, 1, -0.01)
     g_pos = _np(ctx.debug_buffer("grid_positions", "<f4", (G3, 3)))
     g_idx = _np(ctx.debug_buffer("grid_indices", "<u4", (G3,)))
-    assert np.array_equal(g_idx, idx)                                    # integer: bit exact
-    assert np.array_equal(g_pos.view(np.uint32), pos.view(np.uint32))    # fp32 positions: bit exact (same op order)
+    # the same samples, written in CELL order instead of sample order (density_grid.cu: the uniform samples' cell index is an invertible
+    # map of the sample index; neighbours in space become neighbours in the buffer the network pass reads)
+    order = np.argsort(idx, kind="stable")
+    assert np.array_equal(np.sort(idx), np.unique(idx))                  # every cell at most once
+    assert np.array_equal(g_idx, idx[order])                             # integer: bit exact
+    assert np.array_equal(g_pos.view(np.uint32), pos[order].view(np.uint32))   # fp32 positions: bit exact (same op order)
     # density: network in half
     sub = np.arange(0, G3, 97)
     dens_ref = O.net_sdf(U.base_cfg(valid_level=3), np.ascontiguousarray(g_pos[sub]), U.to_half_bits(p), as_density=True)
@@ -87,6 +91,43 @@ def test_density_grid_stage(stepped):
         assert np.array_equal(g_bits, bitfield)
     else:   # threshold differs in the last bit of an fp32 mean: at most a handful of cells may flip
         assert np.count_nonzero(np.unpackbits(g_bits ^ bitfield)) <= 8
+
+
+def test_density_grid_samples_after_step_256():
+    """From step 256 on an occupancy refresh draws 128^3 / 4 uniform + 128^3 / 4 non-uniform samples (testbed_nerf.cu:4011).  The uniform
+    ones are written in cell order through a prefix sum across blocks (density_grid.cu); every sample -- cell index and position bits --
+    is the reference's, the non-uniform ones keep their sample order."""
+    import torch
+    import neus2_b200 as N
+    from neus2_b200 import synthetic
+    ctx = N.Context(N.default_config(batch_size=B))
+    try:
+        ctx.init_params()
+        data = synthetic.render_sphere_views(n_views=3, width=64, height=48, seed=1)
+        ctx.set_dataset(data["pixels"], data["focal"], data["principal"], data["xforms"])
+        ctx.set_state(training_step=300, rays_per_batch=4096)
+        n = G3 // 4
+        m_rng = O.Pcg32(seed=1337)
+        dg_rng = O.Pcg32(seed=m_rng.next_uint())
+        grid = np.zeros(G3, dtype=np.float32)
+        for ema_step in range(2):                                          # the second refresh sees a non-trivial grid and another step offset
+            ctx.update_density_grid()
+            torch.cuda.synchronize()
+            pos_u, idx_u = O.generate_grid_samples(n, dg_rng, ema_step, grid, 1, -0.01)
+            dg_rng.advance()
+            pos_n, idx_n = O.generate_grid_samples(n, dg_rng, ema_step, grid, 1, 0.1)
+            dg_rng.advance()
+            g_pos = _np(ctx.debug_buffer("grid_positions", "<f4", (G3, 3)))[:2 * n]
+            g_idx = _np(ctx.debug_buffer("grid_indices", "<u4", (G3,)))[:2 * n]
+            order = np.argsort(idx_u, kind="stable")
+            assert len(np.unique(idx_u)) == n
+            assert np.array_equal(g_idx[:n], idx_u[order]) and np.array_equal(g_pos[:n].view(np.uint32), pos_u[order].view(np.uint32))
+            assert np.array_equal(g_idx[n:], idx_n) and np.array_equal(g_pos[n:].view(np.uint32), pos_n.view(np.uint32))
+            g_dens = _np(ctx.debug_buffer("grid_density", "<f2", (G3,)))[:2 * n].view(np.uint16)
+            O.splat_and_decay(g_idx, g_dens, 0.95, grid)
+            assert np.array_equal(_np(ctx.debug_buffer("density_grid", "<f4", (G3,))).view(np.uint32), grid.view(np.uint32))
+    finally:
+        ctx.close()
 
 
 def test_sample_generation_stage(stepped):
