@@ -383,7 +383,7 @@ def main():
                     "note": "wall clock through Context.train_step(); dataset upload from pinned host memory amortised over the 2000-step schedule"},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "k_network_fwdbwd<0, 1> (fused second forward + backward + tcgen05 weight gradients)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": 69.77e6, "traffic_source": "profiles/r02_captureB.md: dram__bytes_read 67.3 MB + dram__bytes_write 2.4 MB per launch (ncu --set full); far below the algorithmic bytes because the hash tables and their gradients are served by L2 (see l2)",
+                         "traffic": 70.15e6, "traffic_source": "profiles/r02_captureC.md: dram__bytes_read 66.6 MB + dram__bytes_write 3.5 MB per launch (ncu --set full); far below the algorithmic bytes because the hash tables and their gradients are served by L2 (see l2)",
                          "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes, "avg_launch_ms": dom_ms, "l2": l2},
             "stage_ms": {k: round(v[0], 4) for k, v in stages.items()},
             **({"stage_ms_per_rank": stages_all} if stages_all else {}),

@@ -180,3 +180,114 @@ def test_canonical_training_step_follows_the_reference_counter():
     # what hangs off it while the canonical model is frozen (frames >= 1, first P steps): the counter stays 0, so the occupancy grid is
     # refreshed on every step (n_prep_to_skip = clamp(0 / 16, 1, 16) = 1) from uniform samples (< 256) and n_rays_total restarts each step
     assert all(f(1, 50, s) == 0 for s in range(51)) and f(1, 50, 51) == 1 and f(1, 50, 306) == 256
+
+
+# ---- arithmetic the kernels rely on, restated in numpy (fp32, round to nearest even like the device) --------------------------------
+
+def test_chain_positions_from_an_integer_stride_equal_the_serial_additions():
+    """sampling.cu: chain_position().  Inside one binade adding the same dt moves the fp32 bit pattern by a constant number of ulps (after the
+    first addition, which settles the parity in the tie case), so chain position L of a window is bits(t1) + (L - 1) * stride instead of L
+    dependent additions.  Checked against the serial additions for the marching step of the unit cube and for arbitrary steps, over start
+    values spread across binades, next to powers of two and next to zero; outside the fast path's condition the kernel adds serially."""
+    rs = np.random.RandomState(0)
+    ts = np.concatenate([rs.uniform(0, 8, 100000), 2.0 ** rs.randint(-12, 4, 30000) * (1 + rs.uniform(-1e-3, 1e-3, 30000)), rs.uniform(0, 0.01, 30000)]).astype(np.float32)
+    ts = ts[ts > 0]
+    steps = [np.float32(1.73205080757 / 1024)]
+    for _ in range(40):
+        b = np.float32(rs.uniform(1e-4, 1e-2)).view(np.uint32)
+        steps.append((b & ~np.uint32((1 << rs.randint(0, 12)) - 1)).view(np.float32))      # trailing zero bits: exact ties at some exponents
+    for dt in steps:
+        seq = np.empty((33, len(ts)), np.float32)
+        seq[0] = ts
+        for k in range(1, 33):
+            seq[k] = seq[k - 1] + dt
+        t_far = ts + np.float32(33.0) * dt
+        fast = ((t_far.view(np.uint32) >> 23) == (ts.view(np.uint32) >> 23)) & (ts < 256)
+        assert fast.mean() > 0.5
+        t1 = ts + dt
+        t2 = t1 + dt
+        stride = t2.view(np.uint32) - t1.view(np.uint32)
+        for L in range(1, 33):
+            pred = (t1.view(np.uint32) + np.uint32(L - 1) * stride).view(np.float32)
+            assert np.array_equal(pred.view(np.uint32)[fast], seq[L].view(np.uint32)[fast]), (float(dt), L)
+
+
+def test_occupancy_sample_index_is_inverted_exactly():
+    """density_grid.cu: k_grid_samples_uniform_ordered visits CELLS and finds the sample that the reference's walk
+    idx(i) = ((i + step * n) * 56924617 + 96925573) mod 128^3 (src/testbed_nerf.cu:651) sends there."""
+    G3, a, b, a_inv = 128 ** 3, 56924617, 96925573, 2759905401
+    assert (a * a_inv) % 2 ** 32 == 1
+    rs = np.random.RandomState(1)
+    for n in (G3, G3 // 4):
+        for step in (0, 1, 7, 12345):
+            i = rs.randint(0, n, 20000).astype(np.uint64)
+            t = (((i + step * n) * a) % 2 ** 32 + b) % 2 ** 32 % G3                       # the reference's uint32 arithmetic
+            back = ((a_inv * ((t - b) % 2 ** 32)) % 2 ** 32 - step * n) % 2 ** 32 % G3
+            assert np.array_equal(back, i)
+            # and a cell that no sample below n visits maps to an index >= n
+            cells = rs.randint(0, G3, 20000).astype(np.uint64)
+            pre = ((a_inv * ((cells - b) % 2 ** 32)) % 2 ** 32 - step * n) % 2 ** 32 % G3
+            visited = np.isin(cells, (((np.arange(n, dtype=np.uint64) + step * n) * a) % 2 ** 32 + b) % 2 ** 32 % G3) if n < G3 else np.ones(len(cells), bool)
+            assert np.array_equal(pre < n, visited)
+
+
+def test_compositing_with_short_chains_equals_the_serial_loop():
+    """loss.cu: composite_chunk().  The reference composites a ray serially (src/testbed_nerf.cu:1567-1627: stop before the first sample whose
+    incoming transmittance is below 1e-4; weight = alpha * T; rgb += weight * c; weight_sum += weight; T *= 1 - alpha).  The kernel runs the
+    transmittance product over a whole 32-sample chunk first, finds the stop with one ballot (T never grows), forms the weights and products
+    per lane and adds them in sample order, with +0 for samples that were not consumed.  Same bits, chunk after chunk."""
+    rs = np.random.RandomState(2)
+    f32 = np.float32
+    for trial in range(300):
+        ns = int(rs.randint(1, 200))
+        sharp = rs.choice([0.02, 0.2, 0.9])
+        alpha = np.clip(rs.beta(0.3, 0.3 / sharp, ns), 0, 1).astype(f32)
+        if trial % 7 == 0:
+            alpha[rs.randint(0, ns)] = f32(1.0)                        # a fully opaque sample: T drops to exactly 0
+        rgb = rs.uniform(0, 1, (ns, 3)).astype(f32)
+        # serial reference
+        T, ws, acc, kept = f32(1), f32(0), np.zeros(3, f32), 0
+        cap_ref = []
+        for j in range(ns):
+            if T < f32(1e-4):
+                break
+            w = alpha[j] * T
+            acc = acc + w * rgb[j]
+            ws = ws + w
+            T = T * (f32(1) - alpha[j])
+            kept += 1
+            cap_ref.append((w, T, acc.copy()))
+        # chunked, short chains
+        T2, ws2, acc2, kept2, stop = f32(1), f32(0), np.zeros(3, f32), 0, False
+        cap = []
+        for c0 in range(0, ns, 32):
+            if stop:
+                break
+            cnt = min(32, ns - c0)
+            a = np.zeros(32, f32)
+            c = np.zeros((32, 3), f32)
+            a[:cnt], c[:cnt] = alpha[c0:c0 + cnt], rgb[c0:c0 + cnt]
+            keep = f32(1) - a
+            T_in, T_out = np.empty(32, f32), np.empty(32, f32)
+            t = T2
+            for j in range(32):
+                T_in[j] = t
+                t = t * keep[j]
+                T_out[j] = t
+            below = np.nonzero((T_in < f32(1e-4)) & (np.arange(32) < cnt))[0]
+            consumed = int(below[0]) if len(below) else cnt
+            w = a * T_in
+            prod = w[:, None] * c
+            for j in range(32):
+                mine = j < consumed
+                acc2 = acc2 + (prod[j] if mine else np.zeros(3, f32))
+                ws2 = ws2 + (w[j] if mine else f32(0))
+                if mine:
+                    cap.append((w[j], T_out[j], acc2.copy()))
+            kept2 += consumed
+            stop = len(below) > 0
+            T2 = T_in[consumed] if stop else t
+        assert kept2 == kept
+        assert T2.view(np.uint32) == T.view(np.uint32) and ws2.view(np.uint32) == ws.view(np.uint32) and np.array_equal(acc2.view(np.uint32), acc.view(np.uint32))
+        for (w1, t1, r1), (w0, t0, r0) in zip(cap, cap_ref):
+            assert w1.view(np.uint32) == w0.view(np.uint32) and t1.view(np.uint32) == t0.view(np.uint32) and np.array_equal(r1.view(np.uint32), r0.view(np.uint32))
