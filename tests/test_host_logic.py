@@ -291,3 +291,73 @@ def test_compositing_with_short_chains_equals_the_serial_loop():
         assert T2.view(np.uint32) == T.view(np.uint32) and ws2.view(np.uint32) == ws.view(np.uint32) and np.array_equal(acc2.view(np.uint32), acc.view(np.uint32))
         for (w1, t1, r1), (w0, t0, r0) in zip(cap, cap_ref):
             assert w1.view(np.uint32) == w0.view(np.uint32) and t1.view(np.uint32) == t0.view(np.uint32) and np.array_equal(r1.view(np.uint32), r0.view(np.uint32))
+
+
+def test_lookback_prefix_sum_protocol_under_arbitrary_scheduling():
+    """lookback.cuh: exclusive prefix sums across the blocks of ONE launch.  A model of the protocol, stepped in random interleavings: tiles are
+    numbered by a ticket drawn when the block starts (so every predecessor of a running tile is running or done), a tile publishes
+    [epoch | 1 | own sum], walks back over windows of 32 predecessors -- waiting for descriptors of THIS launch's epoch -- until it meets an
+    inclusive prefix, then publishes [epoch | 2 | prefix].  The descriptor array is never cleared: it starts out full of the previous
+    launches' words (other epochs, both states, arbitrary values), which must not be taken for this launch's."""
+    rs = np.random.RandomState(3)
+
+    def run(n_tiles, sums, epoch, desc, max_resident):
+        ticket = [0]
+        result = {}
+
+        def block():
+            tile = ticket[0]
+            ticket[0] += 1
+            yield                                           # ... the block's own work (pass 1) takes a while
+            for _ in range(rs.randint(0, 4)):
+                yield
+            agg = int(sums[tile])
+            if tile == 0:
+                desc[0] = (epoch, 2, agg)
+                result[0] = 0
+                return
+            desc[tile] = (epoch, 1, agg)
+            excl, p = 0, tile - 1
+            while True:
+                window = []
+                for lane in range(32):
+                    idx = p - lane
+                    if idx < 0:
+                        window.append((2, 0))
+                        continue
+                    while desc[idx][0] != epoch or desc[idx][1] == 0:
+                        yield                               # spin: the predecessor has not published in this launch yet
+                    window.append((desc[idx][1], desc[idx][2]))
+                    if rs.rand() < 0.3:
+                        yield                               # lanes do not read at the same instant
+                first = next((k for k, (st, _) in enumerate(window) if st == 2), None)
+                last = first if first is not None else 31
+                excl += sum(v for _, v in window[:last + 1])
+                if first is not None:
+                    break
+                p -= 32
+            desc[tile] = (epoch, 2, excl + agg)
+            result[tile] = excl
+
+        pending, running = n_tiles, []
+        while pending or running:
+            while pending and len(running) < max_resident:   # the hardware starts blocks in any order; tickets are drawn at start
+                running.append(block())
+                pending -= 1
+            g = running[rs.randint(len(running))]
+            try:
+                next(g)
+            except StopIteration:
+                running.remove(g)
+        return result
+
+    for trial in range(30):
+        n_tiles = int(rs.randint(1, 200))
+        size = 256
+        desc = [(int(rs.randint(0, 5)), int(rs.randint(0, 3)), int(rs.randint(0, 1000))) for _ in range(size)]   # stale words of other launches
+        for epoch in (7, 8):                                # two launches in a row on the same, never cleared, array
+            sums = rs.randint(0, 50, n_tiles)
+            res = run(n_tiles, sums, epoch, desc, max_resident=int(rs.randint(1, 40)))
+            want = np.concatenate([[0], np.cumsum(sums)[:-1]])
+            assert [res[t] for t in range(n_tiles)] == want.tolist(), (trial, epoch)
+            n_tiles = int(rs.randint(1, 200))               # the next launch has another number of tiles
