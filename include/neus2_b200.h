@@ -58,7 +58,9 @@ typedef struct neus2_config {
 	uint32_t world_size;             /* 1 */
 	uint32_t max_rays_per_batch;     /* 1<<18 (testbed_nerf.cu:3435); raise to world_size<<18 for weak scaling */
 	/* 1 (default): the step's first network pass stops along each ray where the loss stops reading (T < 1e-4, testbed_nerf.cu:1567);
-	 * 0: evaluate every marched sample like the reference.  Same loss, gradients and counters either way (tests/test_gpu_step.py). */
+	 * 0: evaluate every marched sample like the reference.  Same loss, gradients and counters either way (tests/test_gpu_step.py).
+	 * With 1 the first pass also leaves {alpha, r, g, b} per evaluated sample and the loss runs by samples (loss.cu: a light per-ray replay
+	 * of the compositing recurrences, then one thread per kept sample); with 0 the loss kernels work one warp per ray.  Same bits. */
 	int32_t forward_early_termination;
 	/* 1 (default, single-GPU contexts): pipelined step.  The step's only host read-back (the sample counts, final after the loss kernel)
 	 * is taken BEFORE the backward pass is queued; while the GPU runs backward pass + optimizer the host computes the next step's
