@@ -206,7 +206,7 @@ k_scan_compacted(const uint32_t* __restrict__ n_ptr, const uint32_t* __restrict_
 	for (uint32_t i = b; i < e; ++i) { base[i] = off; off += counts[i]; }
 }
 
-// ---- pieces shared by the two-kernel path (k_loss_composite / k_loss_gradient) and the fused kernel (k_loss_fused) ----
+// ---- pieces shared by the warp-per-ray kernels (k_loss_composite / k_loss_gradient) and the by-samples kernels (k_loss_rays / k_loss_samples) ----
 // What the ray is compared against (:1629-1676): the training pixel under the ray, composited over the (random) background, in sRGB.
 struct RayTarget { float rgbtarget[3]; float bg[3]; float mask_gt; };
 __device__ __forceinline__ RayTarget ray_target(uint32_t ray_idx, uint32_t n_rays, uint32_t n_rays_total, Pcg32 rng, const DatasetDev& ds, const LossParamsDev& lp) {
